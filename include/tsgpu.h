@@ -1,0 +1,213 @@
+/* tsgpu — C-ABI of the B200-native query hot path for Typesense (libtsgpu.so).
+ *
+ * The reference has NO plugin/FFI seam for this path: it is reached by ordinary C++ member calls inlined into
+ * src/index.cpp. This header introduces the boundary at the narrowest existing seams; each entry
+ * point names the reference call it replaces. INTEGRATION.md shows the binding a maintainer adds on the reference
+ * side.
+ *
+ * Conventions (mirroring the reference's):
+ *   - plain C, opaque handle, caller-allocated outputs (the reference's `uint32_t*&` / `KV*` out-param style);
+ *   - every call returns tsgpu_status; nothing throws across the ABI; tsgpu_last_error() gives the message for the
+ *     calling thread (the reference's Option<T>{code,error}, include/option.h);
+ *   - tsgpu_index_load_* need exclusive access (host holds unique_lock(Index::mutex), src/index.cpp:7513);
+ *     search calls are safe for concurrent readers (shared_lock, src/index.cpp:3488) — they serialise on an internal
+ *     stream mutex;
+ *   - seq_id == hnswlib label == row of every per-document array;
+ *   - there is NO CPU fallback: without a CUDA device every call returns TSGPU_ERR_NO_DEVICE.
+ */
+#ifndef TSGPU_H
+#define TSGPU_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int tsgpu_status;
+enum {
+    TSGPU_OK = 0,
+    TSGPU_ERR_NO_DEVICE = 1,
+    TSGPU_ERR_INVALID = 2,
+    TSGPU_ERR_CUDA = 3,
+    TSGPU_ERR_CAPACITY = 4
+};
+
+#define TSGPU_NO_LIST 0xFFFFFFFFu
+#define TSGPU_MAX_FIELDS 8      /* searched fields per query (reference: FIELD_LIMIT_NUM 100) */
+#define TSGPU_MAX_TOKENS 16     /* token rows per combination (Match considers at most 10, include/match_score.h:11) */
+#define TSGPU_MAX_TOPK 1024     /* Topster capacity per query handled on device (DEFAULT_TOPSTER_SIZE 250) */
+
+typedef struct tsgpu_index tsgpu_index;
+
+/* One searchable string field, flattened. Replaces, for reading, the per-token posting_list_t chains
+ * (include/posting_list.h:56-77,130): token t owns postings [list_off[t], list_off[t+1]). */
+typedef struct {
+    uint32_t n_lists;
+    uint32_t is_array;            /* string[]: offsets carry the in-band array protocol of src/index.cpp:1384-1393 */
+    const uint64_t* list_off;     /* [n_lists+1] */
+    const uint32_t* ids;          /* ascending seq_ids per list */
+    const uint64_t* pos_off;      /* [n_postings+1] */
+    const uint32_t* positions;    /* raw reference offsets (src/index.cpp:1341-1348) */
+} tsgpu_field;
+
+/* Scalar fields of the reference's KV (include/topster.h:20-33), same meaning. */
+typedef struct {
+    uint64_t key;                 /* seq_id */
+    uint64_t distinct_key;
+    int64_t  scores[3];
+    int64_t  text_match_score;
+    float    vector_distance;
+    int8_t   match_score_index;
+    uint8_t  pad0;
+    uint16_t query_index;
+} tsgpu_kv;   /* 56 bytes */
+
+enum { TSGPU_SORT_NONE = 0, TSGPU_SORT_TEXT_MATCH = 1, TSGPU_SORT_SEQ_ID = 2, TSGPU_SORT_NUMERIC = 3, TSGPU_SORT_VECTOR_DISTANCE = 4 };
+enum { TSGPU_MATCH_MAX_SCORE = 0, TSGPU_MATCH_MAX_WEIGHT = 1, TSGPU_MATCH_SUM_SCORE = 2 };   /* text_match_type_t */
+enum { TSGPU_FLAG_PRIORITIZE_EXACT_MATCH = 1, TSGPU_FLAG_PRIORITIZE_TOKEN_POSITION = 2, TSGPU_FLAG_PRIORITIZE_NUM_MATCHING_FIELDS = 4 };
+enum { TSGPU_CFLAG_SYNONYM = 1, TSGPU_CFLAG_DEMOTE_SYNONYM = 2 };
+
+/* A batch of keyword searches. Query q is ONE Index::search_all_candidates call (src/index.cpp:1794-1894): a list
+ * of resolved token combinations, all scored into the same Topster. The host keeps the typo/drop-token control loop
+ * (fuzzy_search_fields, src/index.cpp:4784) and calls this once per round, for all searches of a multi_search
+ * (src/core_api.cpp:1080) at once. */
+typedef struct {
+    uint32_t n_queries;
+    uint32_t n_combos;
+    uint32_t n_fields;                 /* F searched fields; slot f -> index field field_ids[f] */
+    uint32_t n_filters;                /* inline filters in this batch */
+    const uint32_t* field_ids;         /* [F] */
+    /* per query */
+    const uint32_t* q_combo_off;       /* [nq+1] */
+    const int32_t*  q_filter;          /* [nq]: -1 none; >=0 inline filter slot; <=-2 persistent handle -(v+2) */
+    const uint32_t* q_excl_off;        /* [nq+1] -> excl_ids */
+    const uint32_t* excl_ids;          /* sorted excluded_result_ids per query */
+    const uint32_t* q_topk;            /* [nq] Topster capacity (src/index.cpp:3506-3512), <= TSGPU_MAX_TOPK */
+    const uint8_t*  q_sort_type;       /* [nq*3] TSGPU_SORT_* */
+    const int32_t*  q_sort_col;        /* [nq*3] sort column for TSGPU_SORT_NUMERIC */
+    const int8_t*   q_sort_order;      /* [nq*3] +1 desc, -1 asc (src/index.cpp:6853-6856) */
+    const uint8_t*  q_sort_missing_first; /* [nq*3] or NULL */
+    const uint8_t*  q_flags;           /* [nq] TSGPU_FLAG_* */
+    const uint8_t*  q_match_type;      /* [nq] */
+    const uint8_t*  q_num_query_tokens;/* [nq] query_tokens.size() */
+    const uint8_t*  q_field_weight;    /* [nq*F] search_field_t::weight */
+    /* per combination */
+    const uint32_t* c_tok_off;         /* [nc+1] -> token rows */
+    const uint32_t* c_total_cost;      /* [nc] next_suggestion2 cost (src/index.cpp:7204) */
+    const uint8_t*  c_n_required;      /* [nc] first n rows are ANDed; the remaining rows are dropped_tokens */
+    const uint8_t*  c_flags;           /* [nc] TSGPU_CFLAG_* or NULL */
+    const int32_t*  c_syn_orig_num_tokens; /* [nc] or NULL (= -1) */
+    const int32_t*  c_orig_num_tokens; /* [nc] or NULL (= -1) */
+    /* per token row */
+    const uint32_t* t_list;            /* [n_rows*F] posting list id in field slot f, TSGPU_NO_LIST if absent */
+    /* inline filters: the materialised filter_result_iterator_t::to_filter_id_array() (sorted seq_ids) */
+    const uint64_t* filter_off;        /* [n_filters+1] */
+    const uint32_t* filter_ids;
+} tsgpu_kw_batch;
+
+/* hnswlib graph + vectors as exported from HierarchicalNSW<float> (include/index.h:356-368). */
+typedef struct {
+    uint32_t n_nodes;
+    uint32_t dim;
+    uint32_t M;                  /* maxM_; level 0 holds maxM0_ = 2M */
+    uint32_t max_level;
+    uint32_t entry_point;        /* enterpoint_node_ */
+    uint32_t metric;             /* 0 ip, 1 cosine (vectors normalised at index time, src/index.cpp:1049-1052) */
+    const float*    vectors;     /* [n*dim], row = internal id = label = seq_id */
+    const uint32_t* labels;      /* [n] or NULL (identity) */
+    const uint8_t*  levels;      /* [n] element_levels_ */
+    const uint32_t* links0;      /* [n*(2M+1)] count, neighbours (get_linklist0) */
+    const uint64_t* upper_off;   /* [n+1] record offsets; one (M+1)-u32 record per level 1..levels[i] */
+    const uint32_t* links_up;
+} tsgpu_hnsw;
+
+typedef struct {
+    uint32_t k;                  /* vector_query.k (0 = default, src/index.cpp:3646, 4061-4063) */
+    uint32_t ef;                 /* vector_query.ef (default 10); effective max(ef, k) */
+    uint32_t flat_search_cutoff;
+    float    distance_threshold; /* FLT_MAX default */
+    float    alpha;              /* 0.3 default */
+    uint32_t fetch_size;
+} tsgpu_vec_params;
+
+const char* tsgpu_last_error(void);
+int tsgpu_device_count(void);
+
+/* ---- index mirror ------------------------------------------------------------------------------------------- */
+tsgpu_status tsgpu_index_create(uint32_t n_docs, int device, tsgpu_index** out);
+void         tsgpu_index_destroy(tsgpu_index* idx);
+/* Mirror one field's posting lists (subscribes to Index::index_field_in_memory, src/index.cpp:700). Pointers may be
+ * host or device memory. Returns the field id in *out_field. */
+tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint32_t* out_field);
+/* Mirror sort_index[field] (include/index.h:442-447): dense [n_docs], INT64_MIN where the doc has no value. */
+tsgpu_status tsgpu_index_load_sort_column(tsgpu_index* idx, const int64_t* vals, uint32_t* out_col);
+/* Mirror hnsw_index_t (vectors + graph). Pointers may be host or device memory. */
+tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g);
+/* Persistent filter (a mirrored filter leaf / cached filter result): sorted seq_ids -> device bitmap. */
+tsgpu_status tsgpu_filter_create(tsgpu_index* idx, const uint32_t* ids, size_t n, int32_t* out_handle);
+tsgpu_status tsgpu_filter_destroy(tsgpu_index* idx, int32_t handle);
+
+/* ---- search -------------------------------------------------------------------------------------------------- */
+/* posting_list_t::intersect / posting_t::intersect (src/posting_list.cpp:708, src/posting.cpp:388): k-way AND of
+ * whole posting lists of one field. out_ids capacity `cap`; *out_n = result count (ascending). */
+tsgpu_status tsgpu_intersect(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k,
+                             uint32_t* out_ids, size_t cap, size_t* out_n);
+
+/* posting_t::get_phrase_matches (src/posting_list.cpp:1791; call site src/index.cpp:5960): of the ascending `ids`,
+ * keep those where the k lists' tokens occur as a consecutive sequence. */
+tsgpu_status tsgpu_phrase_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k,
+                                  const uint32_t* ids, size_t n, uint32_t* out_ids, size_t* out_n);
+
+/* search_all_candidates -> search_across_fields -> or_iterator_t::intersect + compute_aggregated_score +
+ * compute_sort_scores + Topster::add (src/index.cpp:1794, 5385-5596), batched over queries.
+ * out_kv[q*kv_stride ..] = the query's Topster in Topster::sort() order, out_count[q] entries;
+ * out_found[q] = |all_result_ids| contributed by this call. */
+tsgpu_status tsgpu_keyword_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, tsgpu_kv* out_kv,
+                                        uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found);
+
+/* VectorIndex::searchKnn: vecdex->searchKnnCloserFirst(q, k, ef, &VectorFilterFunctor) (src/index.cpp:3384-3386),
+ * batched. queries [nq*dim] (already normalised for cosine). q_filter as in tsgpu_kw_batch (inline slots refer to
+ * filter_off/filter_ids). Outputs [nq*k] closest first; out_n[q] valid entries. */
+tsgpu_status tsgpu_knn_batch(tsgpu_index* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                             const int32_t* q_filter, uint32_t n_filters, const uint64_t* filter_off,
+                             const uint32_t* filter_ids, float* out_dist, uint32_t* out_labels, uint32_t* out_n);
+
+/* process_results_bruteforce (src/index.cpp:3345-3374): distance of the query to every id, in id order. */
+tsgpu_status tsgpu_flat_distances(tsgpu_index* idx, const float* query, const uint32_t* ids, size_t n, float* out_dist);
+
+/* Wildcard + vector query (src/index.cpp:3645-3732). Filters / exclusions / sort clauses / topk come from `b`
+ * (its combinations are ignored). */
+tsgpu_status tsgpu_vector_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const float* qvecs,
+                                       const tsgpu_vec_params* vp, tsgpu_kv* out_kv, uint32_t kv_stride,
+                                       uint32_t* out_count, uint32_t* out_found);
+
+/* Keyword + vector query with reciprocal-rank fusion (src/index.cpp:4036-4221). */
+tsgpu_status tsgpu_hybrid_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const float* qvecs,
+                                       const tsgpu_vec_params* vp, tsgpu_kv* out_kv, uint32_t kv_stride,
+                                       uint32_t* out_count, uint32_t* out_found);
+
+/* ---- instrumentation ------------------------------------------------------------------------------------------ */
+/* Device-time breakdown of the last search call on this index (CUDA events on the library's stream), kernel launch
+ * count since index creation, and algorithmic work counters of the last call. */
+typedef struct {
+    float    ms_total;           /* whole call on the device stream, including H2D / D2H copies */
+    float    ms_kernels;         /* between first kernel launch and last kernel completion */
+    float    ms_keyword;         /* intersect+score+select kernels */
+    float    ms_knn;             /* HNSW / flat kernels */
+    float    ms_fuse;            /* RRF / final top-k kernels */
+    uint64_t launches_total;     /* kernels launched by this library since index creation */
+    uint64_t kw_driver_ids;      /* candidate (driver-list) ids scanned */
+    uint64_t kw_probe_ids;       /* posting ids covered by probed blocks */
+    uint64_t kw_matches;         /* docs scored */
+    uint64_t knn_dist;           /* distance evaluations */
+    uint64_t knn_expanded;       /* expanded nodes */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+} tsgpu_stats;
+tsgpu_status tsgpu_get_stats(tsgpu_index* idx, tsgpu_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

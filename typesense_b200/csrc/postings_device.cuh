@@ -1,0 +1,102 @@
+// Device posting-list layout and block probe, written as __host__ __device__ code (see score_device.cuh for why).
+//
+// Replaces, for reading: posting_list_t::block_t + iterator_t (include/posting_list.h:56-127,
+// src/posting_list.cpp:1954-2061) and the FOR containers behind them (src/sorted_array.cpp, libfor).
+//
+// Layout per field (all arrays in HBM, built once by tsgpu_index_load_field):
+//   list_off[L+1]      u64  posting index range of token list l            (-> pos_off, df = difference)
+//   list_blk_off[L+1]  u32  block index range of list l; blocks hold kBlock ids, only the last may be short
+//   blk_first[NB]      u32  first (= minimum) id of the block: the skip index (reference: id_block_map keyed by LAST id)
+//   blk_info[NB]       u64  bits 0..39 word offset into `packed`, bits 40..47 bit width b
+//   packed[]           u32  per block kBlock * b bits, LSB-first: (id - blk_first) in b bits — frame of reference,
+//                           the same scheme as the reference's sorted_array (base + fixed bit width), so any id of a
+//                           block can be extracted without decoding its neighbours
+//   pos_off[P+1]       u64  -> positions
+//   positions[]        u32  raw reference offsets
+#pragma once
+#include <stdint.h>
+#include "score_device.cuh"
+
+namespace tsdev {
+
+constexpr int kBlock = 128;                 // ids per block (reference: posting_t::MAX_BLOCK_ELEMENTS 256)
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+struct DevField {
+    uint32_t n_lists;
+    uint32_t is_array;
+    const uint64_t* list_off;
+    const uint32_t* list_blk_off;
+    const uint32_t* blk_first;
+    const uint64_t* blk_info;
+    const uint32_t* packed;
+    const uint64_t* pos_off;
+    const uint32_t* positions;
+};
+
+TS_HD uint32_t bits_required(uint32_t v) {
+    uint32_t b = 0;
+    while(v) { b++; v >>= 1; }
+    return b;
+}
+
+TS_HD uint32_t unpack_at(const uint32_t* __restrict__ w, uint32_t bits, uint32_t idx) {
+    // w points at the block's first word; one padding word follows the last block so w[wi+1] is always readable
+    const uint32_t bitpos = idx * bits;
+    const uint32_t wi = bitpos >> 5, sh = bitpos & 31;
+    const uint32_t lo = w[wi];
+    if(bits == 0) return 0;
+    if(sh + bits <= 32) return bits == 32 ? lo : ((lo >> sh) & ((1u << bits) - 1u));
+    const uint32_t hi = w[wi + 1];
+    const uint64_t both = ((uint64_t) hi << 32) | lo;
+    return (uint32_t) (both >> sh) & (bits == 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u));
+}
+
+// Last block b in [lo, hi] (absolute block indices, lo <= hi) with blk_first[b] <= id, or kNone if id < blk_first[lo].
+TS_HD uint32_t find_block(const uint32_t* __restrict__ blk_first, uint32_t lo, uint32_t hi, uint32_t id) {
+    if(blk_first[lo] > id) return kNone;
+    while(lo < hi) {
+        const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+        if(blk_first[mid] <= id) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// Index (0..cnt) of `id` inside block `b`, or kNone. Binary search directly on the packed words.
+TS_HD uint32_t probe_block(const DevField& f, uint32_t b, uint32_t cnt, uint32_t id) {
+    const uint32_t first = f.blk_first[b];
+    const uint64_t info = f.blk_info[b];
+    const uint32_t bits = (uint32_t) (info >> 40) & 0xFF;
+    const uint32_t* w = f.packed + (info & 0xFFFFFFFFFFull);
+    const uint32_t delta = id - first;
+    if(bits < 32 && (delta >> bits) != 0) return kNone;        // beyond the block's range: falls between two blocks
+    uint32_t lo = 0, hi = cnt;                                  // first idx with value >= delta
+    while(lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if(unpack_at(w, bits, mid) < delta) lo = mid + 1; else hi = mid;
+    }
+    if(lo < cnt && unpack_at(w, bits, lo) == delta) return lo;
+    return kNone;
+}
+
+// number of ids in block b of a list with df ids whose first block is lb0
+TS_HD uint32_t block_count(uint32_t b, uint32_t lb0, uint64_t df) {
+    const uint64_t before = (uint64_t) (b - lb0) * kBlock;
+    const uint64_t rem = df - before;
+    return rem < (uint64_t) kBlock ? (uint32_t) rem : (uint32_t) kBlock;
+}
+
+// Membership probe of `id` in list `l` restricted to blocks [b_lo, b_hi] (absolute). Returns the list-local posting
+// index (0..df) or kNone.
+TS_HD uint32_t probe_list(const DevField& f, uint32_t l, uint32_t b_lo, uint32_t b_hi, uint32_t id) {
+    const uint32_t lb0 = f.list_blk_off[l];
+    const uint32_t b = find_block(f.blk_first, b_lo, b_hi, id);
+    if(b == kNone) return kNone;
+    const uint64_t df = f.list_off[l + 1] - f.list_off[l];
+    const uint32_t cnt = block_count(b, lb0, df);
+    const uint32_t idx = probe_block(f, b, cnt, id);
+    if(idx == kNone) return kNone;
+    return (b - lb0) * kBlock + idx;
+}
+
+}  // namespace tsdev

@@ -1,0 +1,67 @@
+// Host-side builder of the device posting layout (postings_device.cuh) from a flattened field (tsgpu_field).
+// Runs at mirror-load time only (the write path is out of scope), never inside a search call.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <vector>
+#include "postings_device.cuh"
+
+namespace tspack {
+
+struct PackedField {
+    std::vector<uint32_t> list_blk_off;   // [L+1]
+    std::vector<uint32_t> blk_first;      // [NB]
+    std::vector<uint64_t> blk_info;       // [NB]
+    std::vector<uint32_t> packed;         // words (+1 padding word)
+};
+
+inline void pack_field(uint32_t n_lists, const uint64_t* list_off, const uint32_t* ids, PackedField& out) {
+    using tsdev::kBlock;
+    out.list_blk_off.assign((size_t) n_lists + 1, 0);
+    uint64_t nb = 0;
+    for(uint32_t l = 0; l < n_lists; l++) {
+        out.list_blk_off[l] = (uint32_t) nb;
+        const uint64_t df = list_off[l + 1] - list_off[l];
+        nb += (df + kBlock - 1) / kBlock;
+    }
+    out.list_blk_off[n_lists] = (uint32_t) nb;
+    out.blk_first.resize(nb);
+    out.blk_info.resize(nb);
+    // pass 1: widths and word offsets
+    uint64_t words = 0;
+    for(uint32_t l = 0; l < n_lists; l++) {
+        const uint64_t base = list_off[l], df = list_off[l + 1] - base;
+        uint32_t b = out.list_blk_off[l];
+        for(uint64_t s = 0; s < df; s += kBlock, b++) {
+            const uint64_t cnt = (df - s) < (uint64_t) kBlock ? (df - s) : (uint64_t) kBlock;
+            const uint32_t first = ids[base + s], last = ids[base + s + cnt - 1];
+            const uint32_t bits = tsdev::bits_required(last - first);
+            out.blk_first[b] = first;
+            out.blk_info[b] = (words & 0xFFFFFFFFFFull) | ((uint64_t) bits << 40);
+            words += ((uint64_t) kBlock * bits + 31) / 32;       // fixed kBlock slots keep every block word-aligned
+        }
+    }
+    out.packed.assign(words + 1, 0);
+    // pass 2: pack
+    for(uint32_t l = 0; l < n_lists; l++) {
+        const uint64_t base = list_off[l], df = list_off[l + 1] - base;
+        uint32_t b = out.list_blk_off[l];
+        for(uint64_t s = 0; s < df; s += kBlock, b++) {
+            const uint64_t cnt = (df - s) < (uint64_t) kBlock ? (df - s) : (uint64_t) kBlock;
+            const uint32_t first = out.blk_first[b];
+            const uint32_t bits = (uint32_t) (out.blk_info[b] >> 40) & 0xFF;
+            if(bits == 0) continue;
+            uint32_t* w = out.packed.data() + (out.blk_info[b] & 0xFFFFFFFFFFull);
+            for(uint64_t i = 0; i < cnt; i++) {
+                const uint64_t v = ids[base + s + i] - first;
+                const uint64_t bitpos = i * bits;
+                const uint64_t wi = bitpos >> 5, sh = bitpos & 31;
+                const uint64_t both = v << sh;
+                w[wi] |= (uint32_t) both;
+                if(sh + bits > 32) w[wi + 1] |= (uint32_t) (both >> 32);
+            }
+        }
+    }
+}
+
+}  // namespace tspack
