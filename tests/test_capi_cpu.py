@@ -1,0 +1,45 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/tsgpu.h declares, and refuses to run
+without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from typesense_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "tsgpu.h")).read()
+    declared = set(re.findall(r"^(?:tsgpu_status|const char\*|int|void)\s+(tsgpu_[a-z0-9_]+)\(", hdr, re.M))
+    assert len(declared) >= 17
+    L = capi.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/tsgpu.h but not exported"
+    assert set(capi.EXPORTS) <= declared
+
+
+def test_struct_sizes_match_header():
+    assert capi.KV_DTYPE.itemsize == 56
+    assert C.sizeof(capi.FieldStruct) == 8 + 4 * 8
+    assert C.sizeof(capi.VecParamsStruct) == 24
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful without a GPU")
+def test_no_cpu_fallback():
+    L = capi.lib()
+    assert L.tsgpu_device_count() == 0
+    h = C.c_void_p()
+    rc = L.tsgpu_index_create(10, 0, C.byref(h))
+    assert rc == 1   # TSGPU_ERR_NO_DEVICE
+    assert b"no CPU fallback" in L.tsgpu_last_error()

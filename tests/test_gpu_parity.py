@@ -1,0 +1,248 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every call goes through the C-ABI of libtsgpu.so and is
+compared with the CPU oracle on the same seeded inputs — bit-exact for ids / integer scores, 1e-4 relative for float
+distances (they are in fact bit-equal because both sides use the same summation order)."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from typesense_b200 import capi, structs as S, synth
+from test_oracle_ref import random_batch, small_collection  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_kv_equal(kv, cnt, found, okv, ocnt, ofound, check_query_index=True, vd_tol=None):
+    assert cnt.tolist() == ocnt.tolist()
+    assert found.tolist() == ofound.tolist()
+    for q in range(len(cnt)):
+        n = int(cnt[q])
+        assert kv["key"][q, :n].tolist() == okv["key"][q, :n].tolist(), f"query {q}: ids"
+        assert kv["scores"][q, :n].tolist() == okv["scores"][q, :n].tolist(), f"query {q}: scores"
+        assert kv["text_match_score"][q, :n].tolist() == okv["text_match_score"][q, :n].tolist(), f"query {q}: text score"
+        assert kv["match_score_index"][q, :n].tolist() == okv["match_score_index"][q, :n].tolist(), f"query {q}: msi"
+        if check_query_index:
+            assert kv["query_index"][q, :n].tolist() == okv["query_index"][q, :n].tolist(), f"query {q}: query_index"
+        if vd_tol is None:
+            assert kv["vector_distance"][q, :n].tolist() == okv["vector_distance"][q, :n].tolist(), f"query {q}: vdist"
+        else:
+            assert np.allclose(kv["vector_distance"][q, :n], okv["vector_distance"][q, :n], rtol=vd_tol, atol=1e-6)
+
+
+@pytest.fixture(scope="module")
+def coll(small_collection):
+    n_docs, fds, pts = small_collection
+    flats = [fd.flat for fd in fds]
+    gi = capi.GpuIndex(n_docs, 0)
+    for f in flats:
+        gi.load_field(f)
+    gi.load_sort_column(pts)
+    oi = ol.OracleIndex(n_docs, flats, [pts])
+    yield n_docs, fds, flats, pts, gi, oi
+    gi.close()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_keyword_search_random(coll, seed):
+    n_docs, fds, flats, pts, gi, oi = coll
+    rng = np.random.default_rng(900 + seed)
+    filters = [np.unique(rng.integers(0, n_docs, 1500)).astype(np.uint32), np.arange(0, n_docs, 7, dtype=np.uint32),
+               np.zeros(0, np.uint32)]
+    b = random_batch(rng, fds, 60, filters)
+    kv, cnt, found = gi.keyword_search(b, 256)
+    okv, ocnt, ofound = oi.keyword_search(b, 256)
+    assert_kv_equal(kv, cnt, found, okv, ocnt, ofound)
+    assert int(cnt.sum()) > 500
+
+
+def test_keyword_persistent_filter_and_big_k(coll):
+    n_docs, fds, flats, pts, gi, oi = coll
+    rng = np.random.default_rng(5)
+    fil = np.unique(rng.integers(0, n_docs, 2500)).astype(np.uint32)
+    h = gi.filter_create(fil)
+    toks = synth.sample_queries(fds[0], 30, 2, 3)
+    qs, qso = [], []
+    for i, row in enumerate(toks):
+        combos = [S.Combo([[int(t), S.NO_LIST, int(t) if fds[2].flat.df(int(t)) else S.NO_LIST] for t in row], 2)]
+        kw = dict(topk=int(rng.choice([3, 100, 600, 1024])), sort=((S.SORT_NUMERIC, 0, -1, 1), (S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_SEQ_ID, -1, 1, 0)))
+        qs.append(S.Query(combos, filter=h if i % 2 else -1, **kw))
+        qso.append(S.Query(combos, filter=0 if i % 2 else -1, **kw))
+    b = S.KwBatch(qs, [0, 1, 2])
+    bo = S.KwBatch(qso, [0, 1, 2], [fil])
+    kv, cnt, found = gi.keyword_search(b, 1024)
+    okv, ocnt, ofound = oi.keyword_search(bo, 1024)
+    assert_kv_equal(kv, cnt, found, okv, ocnt, ofound)
+
+
+def test_keyword_single_token_large_lists():
+    # one frequent token: every posting matches; exercises the streaming top-K with threshold pruning across units
+    n_docs = 300000
+    fd = synth.make_string_field(n_docs, 50, 2, 6, seed=21)
+    pts = synth.make_points(n_docs, 4, hi=1000)
+    gi = capi.GpuIndex(n_docs, 0)
+    gi.load_field(fd.flat)
+    gi.load_sort_column(pts)
+    oi = ol.OracleIndex(n_docs, [fd.flat], [pts])
+    qs = [S.Query([S.Combo([[t]], 1)], topk=k, sort=((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_NUMERIC, 0, 1, 0), (S.SORT_NONE, -1, 1, 0)))
+          for t, k in [(0, 250), (1, 10), (3, 1000), (7, 1)]]
+    qs.append(S.Query([S.Combo([[0], [1]], 2), S.Combo([[0], [2]], 2, total_cost=1), S.Combo([[1], [2]], 2, total_cost=2)], topk=250, num_query_tokens=2))
+    b = S.KwBatch(qs, [0])
+    kv, cnt, found = gi.keyword_search(b, 1024)
+    okv, ocnt, ofound = oi.keyword_search(b, 1024)
+    assert_kv_equal(kv, cnt, found, okv, ocnt, ofound)
+    st = gi.stats()
+    assert st["kw_matches"] > 100000 and st["launches_total"] >= 2
+    gi.close()
+
+
+def test_intersect_and_phrase(coll):
+    n_docs, fds, flats, pts, gi, oi = coll
+    from test_oracle_ref import tso_intersect, KAT
+    # reference golden vectors through the C-ABI
+    for case in KAT["posting_intersect"]:
+        flat = S.FlatField.from_postings([[(i, [1]) for i in l] for l in case["lists"]])
+        g2 = capi.GpuIndex(64, 0)
+        g2.load_field(flat)
+        assert g2.intersect(0, list(range(len(case["lists"]))), 64).tolist() == case["expect"]
+        g2.close()
+    rng = np.random.default_rng(12)
+    L = ol.oracle()
+    for fi in (0, 1, 2):
+        fl = flats[fi]
+        for _ in range(15):
+            k = int(rng.integers(1, 4))
+            lists = rng.integers(0, 40, k).astype(np.uint32)
+            if any(fl.df(int(l)) == 0 for l in lists):
+                continue
+            exp = tso_intersect([fl.ids[int(fl.list_off[l]):int(fl.list_off[l + 1])] for l in lists])
+            got = gi.intersect(fi, lists.tolist(), n_docs)
+            assert got.tolist() == exp
+            if len(exp) and k > 1:
+                ids = np.asarray(exp, np.uint32)
+                out = np.zeros(len(ids), np.uint32)
+                oix = ol.OracleIndex(n_docs, [fl], [])
+                n = L.tso_phrase_matches(oix.h, 0, ol.p32(np.ascontiguousarray(lists)), k, ol.p32(ids), len(ids), ol.p32(out))
+                assert gi.phrase_matches(fi, lists.tolist(), ids).tolist() == out[:n].tolist()
+
+
+@pytest.fixture(scope="module")
+def vec_coll():
+    n, dim = 6000, 128
+    vec = synth.make_vectors(n, dim, 5).numpy()
+    g = ol.hnsw_build(vec, 16, 100, 100)
+    fd = synth.make_string_field(n, 200, 3, 8, seed=31)
+    pts = synth.make_points(n, 8, hi=100)
+    gi = capi.GpuIndex(n, 0)
+    gi.load_field(fd.flat)
+    gi.load_sort_column(pts)
+    gi.load_hnsw(g)
+    oi = ol.OracleIndex(n, [fd.flat], [pts], g)
+    yield n, dim, vec, g, fd, pts, gi, oi
+    gi.close()
+
+
+def test_knn_matches_oracle(vec_coll):
+    n, dim, vec, g, fd, pts, gi, oi = vec_coll
+    qv = synth.make_vectors(200, dim, 77).numpy()
+    for k, ef in [(10, 10), (100, 10), (5, 200)]:
+        d, l, cnt = gi.knn(qv, k, ef)
+        od, olab, ocnt, _ = oi.knn(qv, k, ef)
+        assert cnt.tolist() == ocnt.tolist()
+        assert l.tolist() == olab.tolist()
+        assert np.allclose(d, od, rtol=1e-4, atol=1e-6)
+        assert (d == od).all(), "same summation order => bit-equal distances"
+    # filtered
+    rng = np.random.default_rng(1)
+    filters = [np.unique(rng.integers(0, n, 600)).astype(np.uint32), np.arange(0, n, 3, dtype=np.uint32)]
+    qf = rng.integers(-1, 2, len(qv)).astype(np.int32)
+    d, l, cnt = gi.knn(qv, 20, 40, qf, filters)
+    od, olab, ocnt, _ = oi.knn(qv, 20, 40, qf, filters)
+    assert cnt.tolist() == ocnt.tolist() and l.tolist() == olab.tolist() and (d == od).all()
+
+
+def test_knn_generic_dim_and_reference_kat():
+    from test_oracle_ref import KAT
+    k = KAT["vector_cosine"]
+    L = ol.oracle()
+    docs = np.asarray(k["docs"], np.float32)
+    q = np.asarray(k["query"], np.float32)
+    nd = np.zeros_like(docs)
+    for i in range(len(docs)):
+        L.tso_normalize(docs[i].ctypes.data_as(S.f32p), nd[i].ctypes.data_as(S.f32p), 4)
+    nq = np.zeros_like(q)
+    L.tso_normalize(q.ctypes.data_as(S.f32p), nq.ctypes.data_as(S.f32p), 4)
+    g = ol.hnsw_build(nd, 16, 200, 100, metric=1)
+    gi = capi.GpuIndex(3, 0)
+    gi.load_hnsw(g)
+    d, l, n = gi.knn(nq[None, :], 10, 10)
+    assert n[0] == 3 and l[0][:3].tolist() == k["expect_ids"]
+    assert np.allclose(np.abs(d[0][:3]), k["expect_distances"], rtol=0, atol=2e-7)
+    d, l, n = gi.knn(nq[None, :], 10, 10, np.asarray([0], np.int32), [np.asarray(k["filtered"]["filter_ids"], np.uint32)])
+    assert l[0][:n[0]].tolist() == k["filtered"]["expect_ids"]
+    gi.close()
+    # odd dimension through the generic path
+    vec = synth.make_vectors(1500, 50, 3).numpy()
+    g = ol.hnsw_build(vec, 8, 60, 100)
+    gi = capi.GpuIndex(1500, 0)
+    gi.load_hnsw(g)
+    oi = ol.OracleIndex(1500, [], [], g)
+    qv = synth.make_vectors(40, 50, 4).numpy()
+    d, l, n = gi.knn(qv, 7, 30)
+    od, olab, on, _ = oi.knn(qv, 7, 30)
+    assert l.tolist() == olab.tolist() and (d == od).all()
+    ids = np.arange(0, 1500, 11, dtype=np.uint32)
+    fd = gi.flat_distances(qv[0], ids)
+    od = np.zeros(len(ids), np.float32)
+    L.tso_flat_distances(oi.hs, qv[0].ctypes.data_as(S.f32p), ol.p32(ids), len(ids), od.ctypes.data_as(S.f32p))
+    assert (fd == od).all()
+    gi.close()
+
+
+def _vec_queries(rng, fd, n, filters, sort, with_combos):
+    toks = synth.sample_queries(fd, n, 2, int(rng.integers(0, 1 << 30)))
+    qs = []
+    for i, row in enumerate(toks):
+        combos = [S.Combo([[int(t)] for t in row], 2)] if with_combos else []
+        if with_combos and i % 3 == 0:
+            combos.append(S.Combo([[int(row[0])], [int(rng.integers(0, 30))]], 2, total_cost=1))
+        q = S.Query(combos, topk=int(rng.choice([10, 250])), sort=sort, num_query_tokens=2)
+        if filters and i % 2:
+            q.filter = int(rng.integers(0, len(filters)))
+        if i % 5 == 0:
+            q.excl = np.unique(rng.integers(0, 6000, 30)).tolist()
+        qs.append(q)
+    return S.KwBatch(qs, [0], filters)
+
+
+def test_vector_search_matches_oracle(vec_coll):
+    n, dim, vec, g, fd, pts, gi, oi = vec_coll
+    rng = np.random.default_rng(41)
+    filters = [np.unique(rng.integers(0, n, 900)).astype(np.uint32), np.arange(0, n, 40, dtype=np.uint32)]
+    sort = ((S.SORT_VECTOR_DISTANCE, -1, -1, 0), (S.SORT_NUMERIC, 0, 1, 0), (S.SORT_NONE, -1, 1, 0))
+    b = _vec_queries(rng, fd, 60, filters, sort, False)
+    qv = synth.make_vectors(60, dim, 43).numpy()
+    for vp in [S.vec_params(k=0, ef=10, fetch_size=20), S.vec_params(k=50, ef=80, flat_search_cutoff=500, fetch_size=10),
+               S.vec_params(k=30, ef=30, distance_threshold=0.9, fetch_size=10)]:
+        kv, cnt, found = gi.vector_search(b, qv, vp, 256)
+        okv, ocnt, ofound = oi.vector_search(b, qv, vp, 256)
+        assert_kv_equal(kv, cnt, found, okv, ocnt, ofound)
+
+
+def test_hybrid_search_matches_oracle(vec_coll):
+    n, dim, vec, g, fd, pts, gi, oi = vec_coll
+    rng = np.random.default_rng(51)
+    filters = [np.unique(rng.integers(0, n, 1200)).astype(np.uint32), np.arange(0, n, 50, dtype=np.uint32)]
+    sort = ((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_NUMERIC, 0, 1, 0), (S.SORT_NONE, -1, 1, 0))
+    b = _vec_queries(rng, fd, 80, filters, sort, True)
+    qv = synth.make_vectors(80, dim, 53).numpy()
+    for vp in [S.vec_params(k=0, ef=10, alpha=0.3, fetch_size=10), S.vec_params(k=40, ef=60, alpha=0.7, flat_search_cutoff=300, fetch_size=10)]:
+        kv, cnt, found = gi.hybrid_search(b, qv, vp, 256)
+        okv, ocnt, ofound = oi.hybrid_search(b, qv, vp, 256)
+        assert_kv_equal(kv, cnt, found, okv, ocnt, ofound)
+    # sort clause with _vector_distance as tie-breaker and a full Topster (the add()-on-sorted-array path)
+    sort2 = ((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_VECTOR_DISTANCE, -1, -1, 0), (S.SORT_SEQ_ID, -1, 1, 0))
+    b2 = _vec_queries(rng, fd, 40, [], sort2, True)
+    for i in range(b2.n_queries):
+        b2.q_topk[i] = 10
+    kv, cnt, found = gi.hybrid_search(b2, qv[:40], S.vec_params(k=25, ef=25, fetch_size=10), 256)
+    okv, ocnt, ofound = oi.hybrid_search(b2, qv[:40], S.vec_params(k=25, ef=25, fetch_size=10), 256)
+    assert_kv_equal(kv, cnt, found, okv, ocnt, ofound)

@@ -1,0 +1,111 @@
+"""CPU check of the product's __host__ __device__ headers (score_device.cuh / postings_device.cuh / postings_pack.h)
+against the oracle: tests/hostsim compiles them with g++ and replays the per-thread call sequence of
+kw_search_kernel. This is test infrastructure — the product itself has no CPU path."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from typesense_b200 import structs as S
+from typesense_b200 import synth
+from test_oracle_ref import random_batch, small_collection  # noqa: F401  (fixture)
+
+HS_DIR = os.path.join(os.path.dirname(__file__), "hostsim")
+HS_SO = os.path.join(HS_DIR, "libhostsim.so")
+
+
+@pytest.fixture(scope="module")
+def hs():
+    src = os.path.join(HS_DIR, "hostsim.cpp")
+    csrc = os.path.join(ol.ROOT, "typesense_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("score_device.cuh", "postings_device.cuh", "postings_pack.h")]
+    if not os.path.exists(HS_SO) or any(os.path.getmtime(d) > os.path.getmtime(HS_SO) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++", src, "-o", HS_SO])
+    L = C.CDLL(HS_SO)
+    L.hs_keyword_combo.restype = C.c_size_t
+    L.hs_keyword_combo.argtypes = [C.POINTER(S.FieldStruct), C.c_uint32, C.POINTER(S.KwBatchStruct), C.c_uint32, C.c_uint32,
+                                   S.u32p, S.u64p, C.c_size_t]
+    L.hs_phrase_match_doc.argtypes = [C.c_uint32, S.u32p, S.u32p]
+    return L
+
+
+def hs_combo(L, flats, b, q, c, cap=1 << 20):
+    arr = (S.FieldStruct * len(flats))(*[f.struct() for f in flats])
+    ids = np.zeros(cap, np.uint32)
+    sc = np.zeros(cap, np.uint64)
+    s = b.struct()
+    n = L.hs_keyword_combo(arr, len(flats), C.byref(s), q, c, ol.p32(ids), sc.ctypes.data_as(S.u64p), cap)
+    assert n <= cap
+    return ids[:n].copy(), sc[:n].copy()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_device_scoring_matches_oracle(hs, small_collection, seed):
+    n_docs, fds, pts = small_collection
+    rng = np.random.default_rng(500 + seed)
+    filters = [np.unique(rng.integers(0, n_docs, 1500)).astype(np.uint32), np.arange(0, n_docs, 7, dtype=np.uint32)]
+    flats = [fd.flat for fd in fds]
+    ix = ol.OracleIndex(n_docs, flats, [pts])
+    b = random_batch(rng, fds, 40, filters)
+    total = 0
+    for q in range(b.n_queries):
+        for c in range(int(b.q_combo_off[q]), int(b.q_combo_off[q + 1])):
+            ids, sc, _ = ix.keyword_combo(b, q, c)
+            hids, hsc = hs_combo(hs, flats, b, q, c)
+            assert ids.tolist() == hids.tolist(), (q, c)
+            assert sc.tolist() == hsc.tolist(), (q, c)
+            total += len(ids)
+    assert total > 200
+
+
+def test_device_scoring_synonym_and_wide_positions(hs):
+    # synonym rescale branch (src/index.cpp:7038-7061) + positions beyond 255 / 65535 wrap
+    rng = np.random.default_rng(9)
+    n_docs = 300
+    lists = []
+    for t in range(6):
+        pl = []
+        for d in np.unique(rng.integers(0, n_docs, 150)):
+            k = int(rng.integers(1, 4))
+            pos = np.sort(rng.choice([1, 2, 3, 4, 5, 9, 40, 254, 255, 256, 300, 65534, 65535, 65536, 70000], k, replace=False)).tolist()
+            if rng.random() < 0.3:
+                pos.append(0)
+            pl.append((int(d), pos))
+        lists.append(pl)
+    flat = S.FlatField.from_postings(lists)
+    ix = ol.OracleIndex(n_docs, [flat], [])
+    qs = []
+    for i in range(30):
+        nt = int(rng.integers(1, 5))
+        toks = rng.choice(6, nt, replace=(nt > 6)).tolist()
+        syn = bool(i % 2)
+        qs.append(S.Query([S.Combo([[t] for t in toks], nt, total_cost=int(rng.integers(0, 5)),
+                                   flags=(S.CFLAG_SYNONYM | (S.CFLAG_DEMOTE_SYNONYM if i % 4 == 1 else 0)) if syn else 0,
+                                   syn_orig_num_tokens=int(rng.integers(1, 4)) if syn else -1,
+                                   orig_num_tokens=int(rng.integers(1, 4)) if syn else -1)],
+                          flags=int(rng.integers(0, 8)), match_type=int(rng.integers(0, 3)), num_query_tokens=nt))
+    b = S.KwBatch(qs, [0])
+    n = 0
+    for q in range(b.n_queries):
+        ids, sc, _ = ix.keyword_combo(b, q, q)
+        hids, hsc = hs_combo(hs, [flat], b, q, q)
+        assert ids.tolist() == hids.tolist()
+        assert sc.tolist() == hsc.tolist(), q
+        n += len(ids)
+    assert n > 100
+
+
+def test_device_block_probe_random(hs):
+    # dense and sparse lists, bit widths 0..32, via a 2-token AND through the packed-block probe
+    rng = np.random.default_rng(3)
+    for trial in range(12):
+        hi = int(rng.choice([200, 5000, 1 << 20, (1 << 32) - 1]))
+        a = np.unique(rng.integers(0, hi, int(rng.integers(1, 3000)), dtype=np.uint64)).astype(np.uint32)
+        bb = np.unique(np.concatenate([rng.choice(a, min(len(a), 200)), rng.integers(0, hi, 500, dtype=np.uint64).astype(np.uint32)]))
+        flat = S.FlatField.from_postings([[(int(i), [1]) for i in a], [(int(i), [2]) for i in bb]])
+        b = S.KwBatch([S.Query([S.Combo([[0], [1]], 2)])], [0])
+        ids, _ = hs_combo(hs, [flat], b, 0, 0)
+        assert ids.tolist() == np.intersect1d(a, bb).tolist()

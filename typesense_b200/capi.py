@@ -1,0 +1,231 @@
+"""ctypes binding of libtsgpu.so (include/tsgpu.h) — harness side.
+
+Importing this module never falls back to a CPU implementation: if the shared library is missing it raises, and on a
+machine without a CUDA device every call returns TSGPU_ERR_NO_DEVICE.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .structs import (FieldStruct, FlatField, HnswGraph, HnswStruct, KV_DTYPE, KwBatch, KwBatchStruct, StatsStruct,
+                      VecParamsStruct, f32p, i32p, u32p, u64p)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtsgpu.so")
+
+EXPORTS = [
+    "tsgpu_last_error", "tsgpu_device_count", "tsgpu_index_create", "tsgpu_index_destroy", "tsgpu_index_load_field",
+    "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy",
+    "tsgpu_intersect", "tsgpu_phrase_matches", "tsgpu_keyword_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
+    "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats",
+]
+
+
+class TsgpuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TsgpuError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.tsgpu_last_error.restype = C.c_char_p
+        L.tsgpu_index_create.argtypes = [C.c_uint32, C.c_int, C.POINTER(vp)]
+        L.tsgpu_index_destroy.argtypes = [vp]
+        L.tsgpu_index_load_field.argtypes = [vp, C.POINTER(FieldStruct), u32p]
+        L.tsgpu_index_load_sort_column.argtypes = [vp, C.c_void_p, u32p]
+        L.tsgpu_index_load_hnsw.argtypes = [vp, C.POINTER(HnswStruct)]
+        L.tsgpu_filter_create.argtypes = [vp, C.c_void_p, C.c_size_t, i32p]
+        L.tsgpu_filter_destroy.argtypes = [vp, C.c_int32]
+        L.tsgpu_intersect.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.tsgpu_phrase_matches.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, C.c_size_t, u32p, C.POINTER(C.c_size_t)]
+        L.tsgpu_keyword_search_batch.argtypes = [vp, C.POINTER(KwBatchStruct), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.tsgpu_knn_batch.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, i32p, C.c_uint32, u64p, u32p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tsgpu_flat_distances.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        for n in ("tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch"):
+            getattr(L, n).argtypes = [vp, C.POINTER(KwBatchStruct), C.c_void_p, C.POINTER(VecParamsStruct), C.c_void_p,
+                                      C.c_uint32, C.c_void_p, C.c_void_p]
+        L.tsgpu_get_stats.argtypes = [vp, C.POINTER(StatsStruct)]
+        _lib = L
+    return _lib
+
+
+def _ck(rc: int):
+    if rc != 0:
+        raise TsgpuError(f"tsgpu status {rc}: {lib().tsgpu_last_error().decode()}")
+
+
+def _addr(x):
+    """numpy array / torch tensor (cpu, pinned or cuda) / int -> raw address."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        assert x.is_contiguous()
+        return x.data_ptr()
+    return int(x)
+
+
+class GpuIndex:
+    """Device mirror of one Typesense Index (postings, sort columns, HNSW graph + vectors) behind the C-ABI."""
+
+    def __init__(self, n_docs: int, device: int = 0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        _ck(self.L.tsgpu_index_create(n_docs, device, C.byref(self.h)))
+        self.n_docs = n_docs
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.L.tsgpu_index_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- mirror loading
+    def load_field(self, f: FlatField) -> int:
+        s = f.struct()
+        out = C.c_uint32(0)
+        _ck(self.L.tsgpu_index_load_field(self.h, C.byref(s), C.byref(out)))
+        return out.value
+
+    def load_field_raw(self, n_lists: int, is_array: bool, list_off, ids, pos_off, positions) -> int:
+        """Pointers may be torch CUDA tensors (device-resident synthetic data)."""
+        s = FieldStruct()
+        s.n_lists, s.is_array = n_lists, int(is_array)
+        s.list_off = C.cast(_addr(list_off), u64p)
+        s.ids = C.cast(_addr(ids), u32p)
+        s.pos_off = C.cast(_addr(pos_off), u64p)
+        s.positions = C.cast(_addr(positions), u32p)
+        out = C.c_uint32(0)
+        _ck(self.L.tsgpu_index_load_field(self.h, C.byref(s), C.byref(out)))
+        return out.value
+
+    def load_sort_column(self, vals) -> int:
+        if isinstance(vals, np.ndarray):
+            vals = np.ascontiguousarray(vals, np.int64)
+        out = C.c_uint32(0)
+        _ck(self.L.tsgpu_index_load_sort_column(self.h, _addr(vals), C.byref(out)))
+        return out.value
+
+    def load_hnsw(self, g: HnswGraph):
+        s = g.struct()
+        _ck(self.L.tsgpu_index_load_hnsw(self.h, C.byref(s)))
+
+    def load_hnsw_raw(self, n, dim, M, max_level, entry_point, metric, vectors, levels, links0, upper_off, links_up):
+        s = HnswStruct()
+        s.n_nodes, s.dim, s.M, s.max_level, s.entry_point, s.metric = n, dim, M, max_level, entry_point, metric
+        s.vectors = C.cast(_addr(vectors), f32p)
+        s.labels = C.cast(None, u32p)
+        s.levels = C.cast(_addr(levels), C.POINTER(C.c_uint8))
+        s.links0 = C.cast(_addr(links0), u32p)
+        s.upper_off = C.cast(_addr(upper_off), u64p)
+        s.links_up = C.cast(_addr(links_up), u32p)
+        _ck(self.L.tsgpu_index_load_hnsw(self.h, C.byref(s)))
+
+    def filter_create(self, ids) -> int:
+        if isinstance(ids, np.ndarray):
+            ids = np.ascontiguousarray(ids, np.uint32)
+        n = int(ids.shape[0]) if hasattr(ids, "shape") else len(ids)
+        out = C.c_int32(0)
+        _ck(self.L.tsgpu_filter_create(self.h, _addr(ids) if n else None, n, C.byref(out)))
+        return out.value
+
+    # ---- search
+    def intersect(self, field: int, lists: Sequence[int], cap: int) -> np.ndarray:
+        ls = np.asarray(lists, np.uint32)
+        out = np.zeros(max(cap, 1), np.uint32)
+        n = C.c_size_t(0)
+        _ck(self.L.tsgpu_intersect(self.h, field, ls.ctypes.data_as(u32p), len(ls), out.ctypes.data_as(u32p), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def phrase_matches(self, field: int, lists: Sequence[int], ids: np.ndarray) -> np.ndarray:
+        ls = np.asarray(lists, np.uint32)
+        ids = np.ascontiguousarray(ids, np.uint32)
+        out = np.zeros(max(len(ids), 1), np.uint32)
+        n = C.c_size_t(0)
+        _ck(self.L.tsgpu_phrase_matches(self.h, field, ls.ctypes.data_as(u32p), len(ls), ids.ctypes.data_as(u32p), len(ids),
+                                        out.ctypes.data_as(u32p), C.byref(n)))
+        return out[:n.value].copy()
+
+    def _outs(self, nq, stride, out):
+        if out is None:
+            kv = np.zeros((nq, stride), KV_DTYPE)
+            cnt = np.zeros(nq, np.uint32)
+            found = np.zeros(nq, np.uint32)
+            return kv, cnt, found
+        return out
+
+    def keyword_search(self, b: KwBatch, stride: int = 256, out=None, bstruct=None):
+        kv, cnt, found = self._outs(b.n_queries, stride, out)
+        s = bstruct if bstruct is not None else b.struct()
+        _ck(self.L.tsgpu_keyword_search_batch(self.h, C.byref(s), _addr(kv), stride, _addr(cnt), _addr(found)))
+        return kv, cnt, found
+
+    def vector_search(self, b: KwBatch, qvecs, vp: VecParamsStruct, stride: int = 256, out=None, bstruct=None):
+        kv, cnt, found = self._outs(b.n_queries, stride, out)
+        if isinstance(qvecs, np.ndarray):
+            qvecs = np.ascontiguousarray(qvecs, np.float32)
+        s = bstruct if bstruct is not None else b.struct()
+        _ck(self.L.tsgpu_vector_search_batch(self.h, C.byref(s), _addr(qvecs), C.byref(vp), _addr(kv), stride, _addr(cnt), _addr(found)))
+        return kv, cnt, found
+
+    def hybrid_search(self, b: KwBatch, qvecs, vp: VecParamsStruct, stride: int = 256, out=None, bstruct=None):
+        kv, cnt, found = self._outs(b.n_queries, stride, out)
+        if isinstance(qvecs, np.ndarray):
+            qvecs = np.ascontiguousarray(qvecs, np.float32)
+        s = bstruct if bstruct is not None else b.struct()
+        _ck(self.L.tsgpu_hybrid_search_batch(self.h, C.byref(s), _addr(qvecs), C.byref(vp), _addr(kv), stride, _addr(cnt), _addr(found)))
+        return kv, cnt, found
+
+    def knn(self, queries, k: int, ef: int, q_filter=None, filters=(), out=None):
+        if isinstance(queries, np.ndarray):
+            queries = np.ascontiguousarray(queries, np.float32)
+        nq = int(queries.shape[0])
+        if out is None:
+            d = np.zeros((nq, k), np.float32)
+            l = np.zeros((nq, k), np.uint32)
+            n = np.zeros(nq, np.uint32)
+        else:
+            d, l, n = out
+        off = [0]
+        for f in filters:
+            off.append(off[-1] + len(f))
+        foff = np.asarray(off, np.uint64)
+        fids = np.concatenate([np.asarray(f, np.uint32) for f in filters]) if filters and off[-1] else np.zeros(1, np.uint32)
+        qf = None if q_filter is None else np.ascontiguousarray(q_filter, np.int32)
+        _ck(self.L.tsgpu_knn_batch(self.h, _addr(queries), nq, k, ef,
+                                   qf.ctypes.data_as(i32p) if qf is not None else C.cast(None, i32p), len(filters),
+                                   foff.ctypes.data_as(u64p), fids.ctypes.data_as(u32p), _addr(d), _addr(l), _addr(n)))
+        return d, l, n
+
+    def flat_distances(self, query: np.ndarray, ids: np.ndarray) -> np.ndarray:
+        q = np.ascontiguousarray(query, np.float32)
+        ids = np.ascontiguousarray(ids, np.uint32)
+        out = np.zeros(max(len(ids), 1), np.float32)
+        _ck(self.L.tsgpu_flat_distances(self.h, q.ctypes.data, ids.ctypes.data, len(ids), out.ctypes.data))
+        return out[:len(ids)]
+
+    def stats(self) -> dict:
+        s = StatsStruct()
+        _ck(self.L.tsgpu_get_stats(self.h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in StatsStruct._fields_}

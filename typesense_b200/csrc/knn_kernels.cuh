@@ -1,0 +1,413 @@
+// Vector hot path on sm_100a: batched HNSW search (K6), flat filtered scan (K7).
+//
+// Replaces (reference file:line):
+//   hnswlib::HierarchicalNSW<float>::searchKnnCloserFirst(q, k, ef, filter)   call site src/index.cpp:3384-3386
+//       (hnswlib itself is a build-time download, cmake/hnsw.cmake:3 — its published searchKnn / searchBaseLayerST
+//        algorithm is what is implemented)
+//   VectorFilterFunctor::operator()                                            include/index.h:338-353
+//   InnerProductSpace distance 1 - <a,b>, process_results_bruteforce           src/index.cpp:3345-3374
+//
+// Execution model: the graph (level-0 link table, upper-level records) and the fp32 vectors stay
+// resident in HBM. ONE WARP PER QUERY, persistent warps pulling queries from an atomic counter:
+//   - the query vector lives in registers (d/128 float4 per lane); a neighbour's vector is read with coalesced
+//     512-byte warp loads, two neighbours (2*d/128 LDG.128 per lane) in flight before the first FMA;
+//   - dot products use the fixed "W128" order (element e -> accumulator e mod 128 by FMA, 4->1 per lane, xor
+//     butterfly), the same order the oracle uses, so CPU and GPU take identical branches on the same graph;
+//   - visited set = one bit per node in a per-warp global bitmap (atomicOr), undone from a visit log afterwards;
+//   - result heap (size ef) in shared memory, candidate heap in a per-warp global arena (L2-resident);
+//     both are binary heaps of u64 keys (order-preserving float bits << 32 | id) reproducing std::priority_queue<
+//     pair<float,id>> order exactly;
+//   - the 32 neighbours of an expansion are tested/marked in parallel (ballot), distances are computed two at a
+//     time, and admission to the heaps is replayed in neighbour order by lane 0 — the same sequence of
+//     lowerBound updates as hnswlib's loop.
+// This kernel is HBM-latency/bandwidth bound (one 4*d-byte vector per 2*d flop); tensor cores are not used here.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+namespace tsv {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr int kKnnThreads = 128;            // 4 warps = 4 queries per CTA
+
+struct HnswDev {
+    uint32_t n_nodes, dim, M, max_level, entry_point, metric;
+    const float* vectors;
+    const uint32_t* labels;        // nullptr = identity
+    const uint8_t* levels;
+    const uint32_t* links0;        // [n*(2M+1)]
+    const unsigned long long* upper_off;
+    const uint32_t* links_up;
+};
+
+struct KnnParams {
+    const float* queries;          // [nq*dim]
+    uint32_t nq, k, ef;
+    const uint32_t* const* q_filter_bitmap;   // [nq] device pointers (nullptr = no filter) or nullptr array
+    const uint32_t* const* q_excl;            // [nq] or nullptr
+    const uint32_t* q_n_excl;
+    const uint8_t* q_skip;                    // [nq] 1 = query not run (e.g. goes to the flat path) or nullptr
+    float* out_dist;               // [nq*k]
+    uint32_t* out_labels;          // [nq*k]
+    uint32_t* out_n;               // [nq]
+    // per-warp-slot scratch
+    uint32_t* visited;             // [n_slots * vis_words]
+    uint32_t vis_words;
+    uint32_t* vis_log;             // [n_slots * log_cap]
+    uint32_t log_cap;
+    unsigned long long* cand;      // [n_slots * cand_cap]
+    uint32_t cand_cap;
+    uint32_t* counter;             // query ticket
+    unsigned long long* stats;     // [0] n_dist, [1] n_expanded
+    int* error;                    // set to 1 on candidate-heap overflow
+};
+
+__device__ __forceinline__ uint32_t ord_f32(float f) {          // order-preserving float -> u32
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unord_f32(uint32_t o) {
+    const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    return __uint_as_float(u);
+}
+
+// W128 dot product. NCH = dim/128 when dim is a multiple of 128 (query in registers), 0 = generic (scalar, guarded).
+template <int NCH>
+struct QReg { float4 v[NCH > 0 ? NCH : 1]; };
+
+__device__ __forceinline__ float warp_tree(float a0, float a1, float a2, float a3) {
+    float t = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+#pragma unroll
+    for(int off = 16; off >= 1; off >>= 1) t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, off));
+    return t;
+}
+
+template <int NCH>
+__device__ __forceinline__ float dot_one(const QReg<NCH>& q, const float* __restrict__ qs, const float* __restrict__ v,
+                                         uint32_t dim, uint32_t lane) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if(NCH > 0) {
+        float4 x[NCH > 0 ? NCH : 1];
+#pragma unroll
+        for(int s = 0; s < NCH; s++) x[s] = __ldg(reinterpret_cast<const float4*>(v + s * 128) + lane);
+#pragma unroll
+        for(int s = 0; s < NCH; s++) {
+            a0 = __fmaf_rn(q.v[s].x, x[s].x, a0); a1 = __fmaf_rn(q.v[s].y, x[s].y, a1);
+            a2 = __fmaf_rn(q.v[s].z, x[s].z, a2); a3 = __fmaf_rn(q.v[s].w, x[s].w, a3);
+        }
+    } else {
+        for(uint32_t s = 0; s * 128 < dim; s++) {
+            const uint32_t e = s * 128 + 4 * lane;
+            if(e + 0 < dim) a0 = __fmaf_rn(qs[e + 0], __ldg(v + e + 0), a0);
+            if(e + 1 < dim) a1 = __fmaf_rn(qs[e + 1], __ldg(v + e + 1), a1);
+            if(e + 2 < dim) a2 = __fmaf_rn(qs[e + 2], __ldg(v + e + 2), a2);
+            if(e + 3 < dim) a3 = __fmaf_rn(qs[e + 3], __ldg(v + e + 3), a3);
+        }
+    }
+    return warp_tree(a0, a1, a2, a3);
+}
+
+// two vectors with all loads issued before the first FMA (memory-level parallelism)
+template <int NCH>
+__device__ __forceinline__ void dot_two(const QReg<NCH>& q, const float* __restrict__ qs, const float* __restrict__ va,
+                                        const float* __restrict__ vb, uint32_t dim, uint32_t lane, float& da, float& db) {
+    if(NCH > 0) {
+        float4 x[NCH > 0 ? NCH : 1], y[NCH > 0 ? NCH : 1];
+#pragma unroll
+        for(int s = 0; s < NCH; s++) {
+            x[s] = __ldg(reinterpret_cast<const float4*>(va + s * 128) + lane);
+            y[s] = __ldg(reinterpret_cast<const float4*>(vb + s * 128) + lane);
+        }
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll
+        for(int s = 0; s < NCH; s++) {
+            a0 = __fmaf_rn(q.v[s].x, x[s].x, a0); a1 = __fmaf_rn(q.v[s].y, x[s].y, a1);
+            a2 = __fmaf_rn(q.v[s].z, x[s].z, a2); a3 = __fmaf_rn(q.v[s].w, x[s].w, a3);
+            b0 = __fmaf_rn(q.v[s].x, y[s].x, b0); b1 = __fmaf_rn(q.v[s].y, y[s].y, b1);
+            b2 = __fmaf_rn(q.v[s].z, y[s].z, b2); b3 = __fmaf_rn(q.v[s].w, y[s].w, b3);
+        }
+        da = warp_tree(a0, a1, a2, a3);
+        db = warp_tree(b0, b1, b2, b3);
+    } else {
+        da = dot_one<NCH>(q, qs, va, dim, lane);
+        db = dot_one<NCH>(q, qs, vb, dim, lane);
+    }
+}
+
+// ---- binary heaps of u64 keys, single-lane operations
+__device__ __forceinline__ void heap_push_max(unsigned long long* h, uint32_t& n, unsigned long long key) {
+    uint32_t i = n++;
+    while(i > 0) { const uint32_t p = (i - 1) >> 1; const unsigned long long hp = h[p]; if(hp >= key) break; h[i] = hp; i = p; }
+    h[i] = key;
+}
+__device__ __forceinline__ void heap_pop_max(unsigned long long* h, uint32_t& n) {
+    const unsigned long long last = h[--n];
+    uint32_t i = 0;
+    for(;;) {
+        uint32_t c = 2 * i + 1;
+        if(c >= n) break;
+        unsigned long long hc = h[c];
+        if(c + 1 < n) { const unsigned long long hr = h[c + 1]; if(hr > hc) { hc = hr; c++; } }
+        if(hc <= last) break;
+        h[i] = hc; i = c;
+    }
+    if(n) h[i] = last;
+}
+__device__ __forceinline__ void heap_push_min(unsigned long long* h, uint32_t& n, unsigned long long key) {
+    uint32_t i = n++;
+    while(i > 0) { const uint32_t p = (i - 1) >> 1; const unsigned long long hp = h[p]; if(hp <= key) break; h[i] = hp; i = p; }
+    h[i] = key;
+}
+__device__ __forceinline__ void heap_pop_min(unsigned long long* h, uint32_t& n) {
+    const unsigned long long last = h[--n];
+    uint32_t i = 0;
+    for(;;) {
+        uint32_t c = 2 * i + 1;
+        if(c >= n) break;
+        unsigned long long hc = h[c];
+        if(c + 1 < n) { const unsigned long long hr = h[c + 1]; if(hr < hc) { hc = hr; c++; } }
+        if(hc >= last) break;
+        h[i] = hc; i = c;
+    }
+    if(n) h[i] = last;
+}
+
+// result key: max-heap on (dist, id)            -> ord(dist) << 32 | id
+// candidate key: min-heap on (dist, larger id first) (priority_queue<pair<-dist,id>> top) -> ord(dist) << 32 | ~id
+__device__ __forceinline__ unsigned long long res_key(float d, uint32_t id) { return ((unsigned long long) ord_f32(d) << 32) | id; }
+__device__ __forceinline__ unsigned long long cand_key(float d, uint32_t id) { return ((unsigned long long) ord_f32(d) << 32) | (uint32_t) ~id; }
+
+__device__ __forceinline__ bool allowed(const HnswDev& g, const uint32_t* fbm, const uint32_t* excl, uint32_t n_excl, uint32_t node) {
+    const uint32_t label = g.labels ? __ldg(g.labels + node) : node;
+    if(n_excl) {
+        uint32_t lo = 0, hi = n_excl;
+        while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(excl[mid] < label) lo = mid + 1; else hi = mid; }
+        if(lo < n_excl && excl[lo] == label) return false;
+    }
+    if(!fbm) return true;
+    return (__ldg(fbm + (label >> 5)) >> (label & 31)) & 1;
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(kKnnThreads)
+hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t slot = blockIdx.x * (kKnnThreads / 32) + warp;
+    const uint32_t ef = P.ef > P.k ? P.ef : P.k;           // Typesense fork: effective ef = max(ef, k)
+    const uint32_t dim = g.dim;
+    const uint32_t dim_pad = (dim + 3) & ~3u;
+    // shared: per warp [ef+1] u64 result heap, then (generic path) the query vector
+    unsigned long long* res = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t) warp * (ef + 1);
+    float* qs = reinterpret_cast<float*>(reinterpret_cast<unsigned long long*>(smem_raw) + (size_t) (kKnnThreads / 32) * (ef + 1)) + (size_t) warp * dim_pad;
+    uint32_t* vis = P.visited + (size_t) slot * P.vis_words;
+    uint32_t* vlog = P.vis_log + (size_t) slot * P.log_cap;
+    unsigned long long* cand = P.cand + (size_t) slot * P.cand_cap;
+    const uint32_t L0 = 2 * g.M + 1, LU = g.M + 1;
+    unsigned long long n_dist_acc = 0, n_exp_acc = 0;
+
+    for(;;) {
+        uint32_t qi = 0;
+        if(lane == 0) qi = atomicAdd(P.counter, 1u);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if(qi >= P.nq) break;
+        if(P.q_skip && P.q_skip[qi]) { if(lane == 0) P.out_n[qi] = 0; continue; }
+        const float* qv = P.queries + (size_t) qi * dim;
+        QReg<NCH> q;
+        if(NCH > 0) {
+#pragma unroll
+            for(int s = 0; s < NCH; s++) q.v[s] = __ldg(reinterpret_cast<const float4*>(qv + s * 128) + lane);
+        } else {
+            for(uint32_t e = lane; e < dim; e += 32) qs[e] = qv[e];
+            __syncwarp();
+        }
+        const uint32_t* fbm = P.q_filter_bitmap ? P.q_filter_bitmap[qi] : nullptr;
+        const uint32_t* excl = P.q_excl ? P.q_excl[qi] : nullptr;
+        const uint32_t n_excl = P.q_n_excl ? P.q_n_excl[qi] : 0;
+        if(g.n_nodes == 0 || g.entry_point == kNone) { if(lane == 0) P.out_n[qi] = 0; continue; }
+
+        // ---- greedy descent through the upper layers (searchKnn)
+        uint32_t cur = g.entry_point;
+        float curdist = 1.0f - dot_one<NCH>(q, qs, g.vectors + (size_t) cur * dim, dim, lane);
+        n_dist_acc++;
+        for(int level = (int) g.max_level; level > 0; level--) {
+            bool changed = true;
+            while(changed) {
+                changed = false;
+                const uint32_t* rec = g.links_up + (g.upper_off[cur] + (unsigned long long) (level - 1)) * LU;
+                const uint32_t size = __ldg(rec);
+                const uint32_t nb = (lane < size) ? __ldg(rec + 1 + lane) : kNone;     // M <= 32
+                for(uint32_t i = 0; i < size; i += 2) {
+                    const uint32_t c0 = __shfl_sync(0xffffffffu, nb, i);
+                    const uint32_t c1 = (i + 1 < size) ? __shfl_sync(0xffffffffu, nb, i + 1) : c0;
+                    float d0, d1;
+                    dot_two<NCH>(q, qs, g.vectors + (size_t) c0 * dim, g.vectors + (size_t) c1 * dim, dim, lane, d0, d1);
+                    d0 = 1.0f - d0; d1 = 1.0f - d1;
+                    n_dist_acc += (i + 1 < size) ? 2 : 1;
+                    if(d0 < curdist) { curdist = d0; cur = c0; changed = true; }
+                    if(i + 1 < size && d1 < curdist) { curdist = d1; cur = c1; changed = true; }
+                }
+            }
+        }
+
+        // ---- best-first search of the base layer (searchBaseLayerST, non-"bare bone" branch)
+        uint32_t n_res = 0, n_cand = 0, n_log = 0;
+        bool log_overflow = false;
+        float lowerBound;
+        {
+            const bool ok = allowed(g, fbm, excl, n_excl, cur);
+            if(ok) {
+                const float d = curdist;      // same value hnswlib recomputes for the entry point
+                n_dist_acc++;
+                lowerBound = d;
+                if(lane == 0) { heap_push_max(res, n_res, res_key(d, cur)); heap_push_min(cand, n_cand, cand_key(d, cur)); }
+            } else {
+                lowerBound = FLT_MAX;
+                if(lane == 0) heap_push_min(cand, n_cand, cand_key(FLT_MAX, cur));
+            }
+            if(lane == 0) { atomicOr(vis + (cur >> 5), 1u << (cur & 31)); vlog[0] = cur; }
+            n_log = 1;
+            n_res = __shfl_sync(0xffffffffu, n_res, 0);
+            n_cand = __shfl_sync(0xffffffffu, n_cand, 0);
+            __syncwarp();
+        }
+        for(;;) {
+            if(n_cand == 0) break;
+            unsigned long long top = 0;
+            if(lane == 0) top = cand[0];
+            top = __shfl_sync(0xffffffffu, top, 0);
+            const float cdist = unord_f32((uint32_t) (top >> 32));
+            if(cdist > lowerBound && n_res == ef) break;
+            const uint32_t cnode = ~(uint32_t) top;
+            if(lane == 0) heap_pop_min(cand, n_cand);
+            n_cand = __shfl_sync(0xffffffffu, n_cand, 0);
+            n_exp_acc++;
+
+            const uint32_t* rec = g.links0 + (size_t) cnode * L0;
+            const uint32_t size = __ldg(rec);
+            uint32_t nb = kNone;
+            bool fresh = false;
+            // 2M <= 32 neighbours handled one per lane; (2M > 32 is processed in chunks of 32)
+            for(uint32_t base = 0; base < size; base += 32) {
+                const uint32_t j = base + lane;
+                nb = (j < size) ? __ldg(rec + 1 + j) : kNone;
+                fresh = false;
+                if(nb != kNone) {
+                    const uint32_t old = atomicOr(vis + (nb >> 5), 1u << (nb & 31));
+                    fresh = !((old >> (nb & 31)) & 1);
+                }
+                uint32_t mask = __ballot_sync(0xffffffffu, fresh);
+                // visit log for the bitmap undo
+                if(fresh) {
+                    const uint32_t pos = n_log + __popc(mask & ((1u << lane) - 1u));
+                    if(pos < P.log_cap) vlog[pos] = nb;
+                }
+                n_log += __popc(mask);
+                if(n_log > P.log_cap) log_overflow = true;
+                while(mask) {
+                    const int j0 = __ffs(mask) - 1; mask &= mask - 1;
+                    int j1 = -1;
+                    if(mask) { j1 = __ffs(mask) - 1; mask &= mask - 1; }
+                    const uint32_t c0 = __shfl_sync(0xffffffffu, nb, j0);
+                    const uint32_t c1 = j1 >= 0 ? __shfl_sync(0xffffffffu, nb, j1) : c0;
+                    float d0, d1;
+                    dot_two<NCH>(q, qs, g.vectors + (size_t) c0 * dim, g.vectors + (size_t) c1 * dim, dim, lane, d0, d1);
+                    d0 = 1.0f - d0; d1 = 1.0f - d1;
+                    n_dist_acc += j1 >= 0 ? 2 : 1;
+                    // admission replayed in neighbour order (lane 0 owns the heaps)
+                    const bool ok0 = allowed(g, fbm, excl, n_excl, c0);
+                    const bool ok1 = j1 >= 0 ? allowed(g, fbm, excl, n_excl, c1) : false;
+                    if(lane == 0) {
+#pragma unroll
+                        for(int t = 0; t < 2; t++) {
+                            if(t == 1 && j1 < 0) break;
+                            const float d = t ? d1 : d0;
+                            const uint32_t c = t ? c1 : c0;
+                            const bool ok = t ? ok1 : ok0;
+                            if(n_res < ef || lowerBound > d) {
+                                if(n_cand < P.cand_cap) heap_push_min(cand, n_cand, cand_key(d, c)); else *P.error = 1;
+                                if(ok) heap_push_max(res, n_res, res_key(d, c));
+                                while(n_res > ef) heap_pop_max(res, n_res);
+                                if(n_res) lowerBound = unord_f32((uint32_t) (res[0] >> 32));
+                            }
+                        }
+                    }
+                    lowerBound = __shfl_sync(0xffffffffu, lowerBound, 0);
+                    n_res = __shfl_sync(0xffffffffu, n_res, 0);
+                    n_cand = __shfl_sync(0xffffffffu, n_cand, 0);
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- emit: keep the k closest, closest first (searchKnnCloserFirst)
+        if(lane == 0) {
+            while(n_res > P.k) heap_pop_max(res, n_res);
+            const uint32_t n = n_res;
+            P.out_n[qi] = n;
+            for(uint32_t i = n; i-- > 0;) {
+                const unsigned long long t = res[0];
+                heap_pop_max(res, n_res);
+                const uint32_t node = (uint32_t) t;
+                P.out_dist[(size_t) qi * P.k + i] = unord_f32((uint32_t) (t >> 32));
+                P.out_labels[(size_t) qi * P.k + i] = g.labels ? g.labels[node] : node;
+            }
+        }
+        __syncwarp();
+        // ---- undo the visited bits
+        if(!log_overflow) {
+            for(uint32_t i = lane; i < n_log; i += 32) { const uint32_t nd = vlog[i]; vis[nd >> 5] = 0; }
+        } else {
+            for(uint32_t i = lane; i < P.vis_words; i += 32) vis[i] = 0;
+        }
+        __syncwarp();
+    }
+    if(lane == 0) { atomicAdd(P.stats + 0, n_dist_acc); atomicAdd(P.stats + 1, n_exp_acc); }
+}
+
+// process_results_bruteforce: one warp per (query, id)
+struct FlatParams {
+    const float* queries;          // [nq*dim]
+    const uint32_t* ids;           // concatenated candidate ids
+    const unsigned long long* q_off; // [nq+1] ranges into ids
+    uint32_t nq;
+    float* out_dist;               // aligned with ids
+    unsigned long long* stats;
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(256)
+flat_distance_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ FlatParams P, unsigned long long total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t dim = g.dim, dim_pad = (dim + 3) & ~3u;
+    float* qs = reinterpret_cast<float*>(smem_raw) + (size_t) warp * dim_pad;
+    const unsigned long long wid = (unsigned long long) blockIdx.x * (blockDim.x >> 5) + warp;
+    const unsigned long long nw = (unsigned long long) gridDim.x * (blockDim.x >> 5);
+    uint32_t cur_q = kNone;
+    QReg<NCH> q;
+    for(unsigned long long i = wid; i < total; i += nw) {
+        // locate the query of element i (binary search over q_off)
+        uint32_t lo = 0, hi = P.nq;
+        while(lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; if(P.q_off[mid] <= i) lo = mid; else hi = mid; }
+        if(lo != cur_q) {
+            cur_q = lo;
+            const float* qv = P.queries + (size_t) cur_q * dim;
+            if(NCH > 0) {
+#pragma unroll
+                for(int s = 0; s < NCH; s++) q.v[s] = __ldg(reinterpret_cast<const float4*>(qv + s * 128) + lane);
+            } else {
+                __syncwarp();
+                for(uint32_t e = lane; e < dim; e += 32) qs[e] = qv[e];
+                __syncwarp();
+            }
+        }
+        const uint32_t id = P.ids[i];
+        float d = 0.f;
+        if(id < g.n_nodes) d = 1.0f - dot_one<NCH>(q, qs, g.vectors + (size_t) id * dim, dim, lane);
+        if(lane == 0) P.out_dist[i] = d;
+    }
+}
+
+}  // namespace tsv

@@ -1,0 +1,703 @@
+// Keyword hot path on sm_100a: block decode + k-way intersection (K1/K2), match scoring (K3), sort-key assembly
+// and streaming top-K (K4), phrase check (K5).
+//
+// Replaces (reference file:line):
+//   or_iterator_t::intersect + take_id           include/or_iterator.h:61-181, src/or_iterator.cpp:218-272
+//   posting_list_t::iterator_t next/skip_to      src/posting_list.cpp:1954-2061 (FOR decode + std::map skip index)
+//   Index::compute_aggregated_score / score_results2 / Match     src/index.cpp:5227-5383, 6966-7098
+//   Index::compute_sort_scores, Topster<KV>::add/sort            src/index.cpp:5662-5907, include/topster.h:321-473
+//   posting_list_t::intersect / get_phrase_matches               src/posting_list.cpp:708-756, 1791-1825
+//
+// Execution model: a work UNIT is (token combination, run of driver tiles). The driver is the
+// required token with the fewest postings; a tile is one 128-id block of one of its field lists. One 128-thread CTA
+// per unit, one candidate id per thread:
+//   decode   : thread i extracts id i of the packed block (FOR: first + b-bit delta) — coalesced, no neighbours needed
+//   filter   : bitmap test (filter_result_iterator_t materialised to bits) + binary search in the exclusion list
+//   narrow   : 2 threads per probed list gallop the skip index (blk_first) from the previous tile's position to the
+//              blocks covering [tile min id, tile max id]
+//   probe    : each live candidate binary-searches those few skip entries, then the b-bit packed block itself
+//   compact  : warp ballots -> dense list of matches (so scoring threads are not diverged)
+//   score    : score_field()/Match per field from the raw offsets in HBM, sort keys from the dense sort columns
+//   select   : CTA-local top-K kept in shared memory: append survivors above the running K-th threshold, bitonic
+//              sort + truncate when the 2*KP buffer fills; unit writes <= K entries
+// kw_final_kernel then merges a query's units (all combinations), de-duplicates seq_ids keeping the greater KV
+// (Topster::add, include/topster.h:392-406) and emits KV records in Topster::sort() order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "postings_device.cuh"
+
+namespace tsk {
+
+using namespace tsdev;
+
+constexpr int kThreads = 128;          // == kBlock: one candidate per thread
+constexpr int kMaxFieldSlots = 8;      // TSGPU_MAX_FIELDS
+constexpr int kMaxLists = 32;          // rows * fields per combination
+constexpr int kMaxIndexFields = 16;
+constexpr int kMaxCombosPerQuery = 256;
+
+struct IndexDev {
+    DevField fields[kMaxIndexFields];
+    uint32_t n_docs;
+};
+
+struct QDesc {
+    const int64_t* sort_col[3];
+    const uint32_t* filter_bitmap;     // nullptr: no filter
+    const uint32_t* excl;
+    uint32_t* found_bitmap;            // nullptr unless the query has several combinations
+    uint32_t n_excl;
+    uint32_t topk;
+    uint32_t combo_begin, combo_end;
+    uint32_t unit_begin, unit_end;
+    uint8_t  sort_type[3];
+    int8_t   sort_order[3];
+    uint8_t  missing_first[3];
+    uint8_t  flags, match_type, num_query_tokens;
+    uint8_t  field_weight[kMaxFieldSlots];
+    uint8_t  filter_empty;             // filter given but matches no doc (src/index.cpp:4823-4826)
+    uint8_t  pad[3];
+};
+
+struct CDesc {
+    uint32_t q;
+    uint32_t total_cost;
+    int32_t  syn_orig, orig;
+    uint8_t  n_rows, n_req, driver_row, cflags;
+    uint32_t req_mask;                 // rows that are required AND present in at least one field
+    uint32_t lists[kMaxLists];         // [row * F + f]
+    uint32_t drv_tile_off[kMaxFieldSlots + 1];
+    uint8_t  probe_order[16];
+};
+
+struct UDesc {
+    uint32_t combo;
+    uint32_t tile_begin, tile_end;
+    uint32_t out_off;                  // first pool slot of this unit
+};
+
+struct KwParams {
+    const QDesc* qd;
+    const CDesc* cd;
+    const UDesc* ud;
+    int64_t* pool_s0; int64_t* pool_s1; int64_t* pool_s2;
+    uint32_t* pool_key;
+    uint32_t* unit_cnt;                // [n_units]
+    uint32_t* combo_matches;           // [n_combos]
+    unsigned long long* stats;         // [0] driver ids, [1] probed block ids, [2] matches
+    uint32_t F;
+    uint32_t field_ids[kMaxFieldSlots];
+    uint32_t KP;                       // power of two >= max topk in the batch
+    uint32_t NL;                       // max rows*F in the batch (shared-memory stride)
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared-memory top-K buffer (structure of arrays, 2*KP slots)
+struct TopBuf {
+    int64_t* s0; int64_t* s1; int64_t* s2;
+    uint32_t* key;
+    uint16_t* cmb;     // combination index local to the query (final kernel only; nullptr in the unit kernel)
+    float* vd;         // vector distance payload (vector assembly only; nullptr otherwise)
+};
+
+__device__ __forceinline__ bool tb_greater(const TopBuf& b, uint32_t i, uint32_t j) {
+    const uint32_t ki = b.key[i], kj = b.key[j];
+    if(ki == kNone) return false;
+    if(kj == kNone) return true;
+    const int64_t a0 = b.s0[i], b0 = b.s0[j];
+    if(a0 != b0) return a0 > b0;
+    const int64_t a1 = b.s1[i], b1 = b.s1[j];
+    if(a1 != b1) return a1 > b1;
+    const int64_t a2 = b.s2[i], b2 = b.s2[j];
+    if(a2 != b2) return a2 > b2;
+    if(ki != kj) return ki > kj;
+    return b.cmb ? (b.cmb[i] > b.cmb[j]) : false;
+}
+// order for the de-duplication pass: key ascending, then the KV order descending (best entry of a key first)
+__device__ __forceinline__ bool tb_before_bykey(const TopBuf& b, uint32_t i, uint32_t j) {
+    const uint32_t ki = b.key[i], kj = b.key[j];
+    if(ki != kj) return ki < kj;          // kNone (invalid) sorts last
+    if(ki == kNone) return false;
+    return tb_greater(b, i, j);
+}
+__device__ __forceinline__ void tb_swap(const TopBuf& b, uint32_t i, uint32_t j) {
+    int64_t t;
+    t = b.s0[i]; b.s0[i] = b.s0[j]; b.s0[j] = t;
+    t = b.s1[i]; b.s1[i] = b.s1[j]; b.s1[j] = t;
+    t = b.s2[i]; b.s2[i] = b.s2[j]; b.s2[j] = t;
+    uint32_t k = b.key[i]; b.key[i] = b.key[j]; b.key[j] = k;
+    if(b.cmb) { uint16_t c = b.cmb[i]; b.cmb[i] = b.cmb[j]; b.cmb[j] = c; }
+    if(b.vd) { float v = b.vd[i]; b.vd[i] = b.vd[j]; b.vd[j] = v; }
+}
+
+// bitonic sort of N (power of two) slots; BYKEY selects the de-dup order. All threads of the CTA call it.
+template <bool BYKEY>
+__device__ void tb_sort(const TopBuf& b, uint32_t N) {
+    for(uint32_t k = 2; k <= N; k <<= 1) {
+        for(uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for(uint32_t t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const uint32_t p = i + j;
+                const bool up = ((i & k) == 0);
+                const bool p_first = BYKEY ? tb_before_bykey(b, p, i) : tb_greater(b, p, i);
+                const bool i_first = BYKEY ? tb_before_bykey(b, i, p) : tb_greater(b, i, p);
+                if(up ? p_first : i_first) tb_swap(b, i, p);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ void tb_fill_invalid(const TopBuf& b, uint32_t from, uint32_t N) {
+    for(uint32_t i = from + threadIdx.x; i < N; i += blockDim.x) b.key[i] = kNone;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Last block b in [start, end] with blk_first[b] <= target, galloping from `start`; kNone if blk_first[start] > target.
+__device__ __forceinline__ uint32_t gallop_block(const uint32_t* __restrict__ blk_first, uint32_t start, uint32_t end,
+                                                 uint32_t target) {
+    if(__ldg(blk_first + start) > target) return kNone;
+    uint32_t lo = start, step = 1;
+    while(lo + step <= end && __ldg(blk_first + lo + step) <= target) { lo += step; step <<= 1; }
+    uint32_t hi = lo + step - 1;
+    if(hi > end) hi = end;
+    return find_block(blk_first, lo, hi, target);
+}
+
+__device__ __forceinline__ bool excluded(const uint32_t* __restrict__ excl, uint32_t n, uint32_t id) {
+    uint32_t lo = 0, hi = n;
+    while(lo < hi) { uint32_t mid = (lo + hi) >> 1; if(excl[mid] < id) lo = mid + 1; else hi = mid; }
+    return lo < n && excl[lo] == id;
+}
+
+// exclusive prefix of `flag` over the CTA; returns this thread's rank, *total = CTA count. s_warp: >= 4 u32 scratch.
+__device__ __forceinline__ uint32_t cta_rank(bool flag, uint32_t* s_warp, uint32_t* total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+    if(lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+    const uint32_t nw = blockDim.x >> 5;
+    for(uint32_t w = 0; w < nw; w++) { const uint32_t c = s_warp[w]; if(w < warp) base += c; tot += c; }
+    __syncthreads();
+    *total = tot;
+    return base + __popc(bal & ((1u << lane) - 1u));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ KwParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t KP = P.KP, N2 = 2 * KP, NL = P.NL, F = P.F;
+    TopBuf tb;
+    tb.s0 = reinterpret_cast<int64_t*>(smem_raw);
+    tb.s1 = tb.s0 + N2;
+    tb.s2 = tb.s1 + N2;
+    tb.key = reinterpret_cast<uint32_t*>(tb.s2 + N2);
+    tb.cmb = nullptr;
+    tb.vd = nullptr;
+    uint32_t* hp = tb.key + N2;                       // [NL][128] list-local posting index of candidate in list j
+    uint32_t* s_cand = hp + NL * kThreads;            // [128]
+    uint32_t* s_mlist = s_cand + kThreads;            // [128]
+
+    __shared__ CDesc cd;
+    __shared__ QDesc qd;
+    __shared__ uint32_t l_blk0[kMaxLists], l_blk1[kMaxLists], l_gal[kMaxLists], l_lo[kMaxLists], l_hi[kMaxLists];
+    __shared__ unsigned long long l_df[kMaxLists], l_base[kMaxLists];
+    __shared__ uint32_t s_warp[8];
+    __shared__ int64_t thr[3];
+    __shared__ uint32_t thr_key;
+    __shared__ uint32_t s_n, s_have_thr, s_matches, s_driver_ids, s_probe_blocks;
+
+    const uint32_t tid = threadIdx.x;
+    const UDesc ud = P.ud[blockIdx.x];
+    {   // descriptors -> shared
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.cd + ud.combo);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&cd);
+        for(uint32_t i = tid; i < sizeof(CDesc) / 4; i += kThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.qd + cd.q);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&qd);
+        for(uint32_t i = tid; i < sizeof(QDesc) / 4; i += kThreads) dst[i] = src[i];
+    }
+    const uint32_t n_lists = (uint32_t) cd.n_rows * F;
+    if(tid < n_lists) {
+        const uint32_t l = cd.lists[tid];
+        if(l != kNone) {
+            const DevField& fld = ix.fields[P.field_ids[tid % F]];
+            const uint32_t b0 = fld.list_blk_off[l], b1 = fld.list_blk_off[l + 1];
+            l_blk0[tid] = b0; l_blk1[tid] = b1 - 1;      // lists are never empty
+            l_base[tid] = fld.list_off[l];
+            l_df[tid] = fld.list_off[l + 1] - fld.list_off[l];
+            l_gal[tid] = b0;
+        } else { l_blk0[tid] = 0; l_blk1[tid] = 0; l_base[tid] = 0; l_df[tid] = 0; l_gal[tid] = 0; }
+    }
+    if(tid == 0) { s_n = 0; s_have_thr = 0; s_matches = 0; s_driver_ids = 0; s_probe_blocks = 0; }
+    __syncthreads();
+
+    ScoreParams SP;
+    SP.total_cost = cd.total_cost;
+    SP.num_query_tokens = qd.num_query_tokens;
+    SP.syn_orig_num_tokens = cd.syn_orig;
+    SP.orig_num_tokens = cd.orig;
+    SP.is_synonym_query = cd.cflags & 1;
+    SP.demote_synonym_match = (cd.cflags >> 1) & 1;
+    SP.prioritize_exact_match = qd.flags & 1;
+    SP.prioritize_token_position = (qd.flags >> 1) & 1;
+    SP.prioritize_num_matching_fields = (qd.flags >> 2) & 1;
+    SP.match_type = qd.match_type;
+    SortSpec SS;
+    for(int i = 0; i < 3; i++) {
+        SS.type[i] = qd.sort_type[i]; SS.order[i] = qd.sort_order[i]; SS.missing_first[i] = qd.missing_first[i];
+        SS.col[i] = qd.sort_col[i];
+    }
+    const uint32_t K = qd.topk;
+    const uint32_t drv = cd.driver_row;
+    uint32_t prev_fd = 0xFFFFFFFFu;
+
+    for(uint32_t tile = ud.tile_begin; tile < ud.tile_end; tile++) {
+        // ---- which driver field / block
+        uint32_t fd = 0;
+        while(fd + 1 < F && tile >= cd.drv_tile_off[fd + 1]) fd++;
+        const uint32_t jd = drv * F + fd;
+        const DevField& dfld = ix.fields[P.field_ids[fd]];
+        const uint32_t b = l_blk0[jd] + (tile - cd.drv_tile_off[fd]);
+        const uint32_t cnt = block_count(b, l_blk0[jd], l_df[jd]);
+        if(fd != prev_fd) {                        // ids restart with a new driver list: reset the gallop cursors
+            __syncthreads();
+            if(tid < n_lists) l_gal[tid] = l_blk0[tid];
+            prev_fd = fd;
+            __syncthreads();
+        }
+        // ---- decode (K2)
+        const uint32_t first = __ldg(dfld.blk_first + b);
+        const unsigned long long info = __ldg(reinterpret_cast<const unsigned long long*>(dfld.blk_info) + b);
+        const uint32_t bits = (uint32_t) (info >> 40) & 0xFF;
+        const uint32_t* w = dfld.packed + (info & 0xFFFFFFFFFFull);
+        const uint32_t id = first + unpack_at(w, bits, tid < cnt ? tid : 0);
+        const uint32_t tmax = first + unpack_at(w, bits, cnt - 1);
+        bool alive = tid < cnt;
+        if(alive && qd.filter_bitmap) alive = (__ldg(qd.filter_bitmap + (id >> 5)) >> (id & 31)) & 1;
+        if(alive && qd.n_excl) alive = !excluded(qd.excl, qd.n_excl, id);
+        if(qd.filter_empty) alive = false;
+        s_cand[tid] = id;
+        const int any_alive = __syncthreads_or(alive);
+        if(tid == 0) s_driver_ids += cnt;
+        if(!any_alive) continue;
+
+        // ---- narrow every probed list to the blocks covering [first, tmax]
+        if(tid < 2 * n_lists) {
+            const uint32_t j = tid >> 1;
+            if(cd.lists[j] != kNone && j != jd) {
+                const uint32_t* bf = ix.fields[P.field_ids[j % F]].blk_first;
+                const uint32_t target = (tid & 1) ? tmax : first;
+                const uint32_t r = gallop_block(bf, l_gal[j], l_blk1[j], target);
+                if(tid & 1) l_hi[j] = r; else l_lo[j] = r;
+            }
+        }
+        __syncthreads();
+        if(tid < n_lists && cd.lists[tid] != kNone && tid != jd) {
+            // lo == kNone: tile starts before the list's first remaining block -> clamp; hi == kNone: nothing to hit
+            if(l_lo[tid] == kNone) l_lo[tid] = l_gal[tid]; else l_gal[tid] = l_lo[tid];
+            if(l_hi[tid] != kNone) atomicAdd(&s_probe_blocks, l_hi[tid] - l_lo[tid] + 1);
+        }
+        __syncthreads();
+
+        // ---- probe (K1): rows in probe order, all field slots of a row
+        for(uint32_t oi = 0; oi < cd.n_rows; oi++) {
+            const uint32_t r = cd.probe_order[oi];
+            bool any = false;
+            for(uint32_t f = 0; f < F; f++) {
+                const uint32_t j = r * F + f;
+                const uint32_t l = cd.lists[j];
+                uint32_t h = kNone;
+                if(l != kNone) {
+                    if(j == jd) h = (b - l_blk0[jd]) * kBlock + tid;
+                    else if(alive && l_hi[j] != kNone) {
+                        const DevField& g = ix.fields[P.field_ids[f]];
+                        const uint32_t bb = find_block(g.blk_first, l_lo[j], l_hi[j], id);
+                        if(bb != kNone) {
+                            const uint32_t c2 = block_count(bb, l_blk0[j], l_df[j]);
+                            const uint32_t ii = probe_block(g, bb, c2, id);
+                            if(ii != kNone) h = (bb - l_blk0[j]) * kBlock + ii;
+                        }
+                    }
+                }
+                hp[j * kThreads + tid] = h;
+                if(h != kNone) { any = true; if(r == drv && f < fd) alive = false; }   // produced by an earlier field's tile
+            }
+            if(((cd.req_mask >> r) & 1) && !any) alive = false;
+        }
+
+        // ---- compact matches
+        uint32_t m_total;
+        const uint32_t rank = cta_rank(alive, s_warp, &m_total);
+        if(alive) s_mlist[rank] = tid;
+        __syncthreads();
+        if(m_total == 0) continue;
+
+        // ---- score (K3) + sort keys: thread k scores match k
+        bool keep = false;
+        int64_t sc[3] = {0, 0, 0};
+        uint32_t mid = 0;
+        if(tid < m_total) {
+            const uint32_t src = s_mlist[tid];
+            mid = s_cand[src];
+            FieldAgg agg; field_agg_init(agg);
+            uint32_t query_len = 0;
+            for(uint32_t r = 0; r < cd.n_rows; r++) {
+                bool any = false;
+                for(uint32_t f = 0; f < F; f++) any |= (hp[(r * F + f) * kThreads + src] != kNone);
+                query_len += any;
+            }
+            for(uint32_t f = 0; f < F; f++) {
+                const DevField& g = ix.fields[P.field_ids[f]];
+                RawTok toks[kMaxTokens];
+                int nt = 0;
+                for(uint32_t r = 0; r < cd.n_rows; r++) {
+                    const uint32_t j = r * F + f;
+                    const uint32_t h = hp[j * kThreads + src];
+                    if(h == kNone) continue;
+                    const unsigned long long p = l_base[j] + h;
+                    const unsigned long long o0 = __ldg(reinterpret_cast<const unsigned long long*>(g.pos_off) + p);
+                    const unsigned long long o1 = __ldg(reinterpret_cast<const unsigned long long*>(g.pos_off) + p + 1);
+                    toks[nt].p = g.positions + o0;
+                    toks[nt].n = (uint32_t) (o1 - o0);
+                    nt++;
+                }
+                if(nt == 0) continue;
+                const bool single_exact = (SP.total_cost == 0 && SP.num_query_tokens == 1);
+                const int64_t fs = score_field(SP, g.is_array != 0, single_exact, toks, nt);
+                field_agg_add(agg, SP.match_type, fs, (int64_t) qd.field_weight[f]);
+            }
+            const uint64_t aggs = field_agg_finish(agg, SP, query_len);
+            const int msi = compute_sort_scores(SS, mid, (int64_t) aggs, 0.0f, sc);
+            if(msi >= 0) sc[msi] = (int64_t) aggs;            // src/index.cpp:5541-5544 (undoes the ASC negation)
+            if(qd.found_bitmap) atomicOr(qd.found_bitmap + (mid >> 5), 1u << (mid & 31));
+            keep = true;
+            if(s_have_thr) keep = kv_greater(sc[0], sc[1], sc[2], mid, thr[0], thr[1], thr[2], thr_key);
+        }
+        // ---- append survivors (K4)
+        uint32_t a_total;
+        const uint32_t arank = cta_rank(keep, s_warp, &a_total);
+        const uint32_t n0 = s_n;
+        if(keep) {
+            const uint32_t slot = n0 + arank;
+            tb.s0[slot] = sc[0]; tb.s1[slot] = sc[1]; tb.s2[slot] = sc[2]; tb.key[slot] = mid;
+        }
+        __syncthreads();
+        if(tid == 0) { s_n = n0 + a_total; s_matches += m_total; }
+        __syncthreads();
+        if(s_n + kThreads > N2) {                 // the next tile might not fit: sort, keep the best K
+            const uint32_t n = s_n;
+            tb_fill_invalid(tb, n, N2);
+            __syncthreads();
+            tb_sort<false>(tb, N2);
+            if(tid == 0) {
+                const uint32_t nn = n < K ? n : K;
+                s_n = nn;
+                if(nn == K) { s_have_thr = 1; thr[0] = tb.s0[K - 1]; thr[1] = tb.s1[K - 1]; thr[2] = tb.s2[K - 1]; thr_key = tb.key[K - 1]; }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- unit epilogue: best <= K entries to the pool
+    __syncthreads();
+    {
+        const uint32_t n = s_n;
+        uint32_t nn = n;
+        if(n > K) {
+            tb_fill_invalid(tb, n, N2);
+            __syncthreads();
+            tb_sort<false>(tb, N2);
+            nn = K;
+        }
+        for(uint32_t i = tid; i < nn; i += kThreads) {
+            const uint32_t o = ud.out_off + i;
+            P.pool_s0[o] = tb.s0[i]; P.pool_s1[o] = tb.s1[i]; P.pool_s2[o] = tb.s2[i]; P.pool_key[o] = tb.key[i];
+        }
+        if(tid == 0) {
+            P.unit_cnt[blockIdx.x] = nn;
+            if(s_matches) atomicAdd(P.combo_matches + ud.combo, s_matches);
+            atomicAdd(P.stats + 0, (unsigned long long) s_driver_ids);
+            atomicAdd(P.stats + 1, (unsigned long long) s_probe_blocks * kBlock);
+            atomicAdd(P.stats + 2, (unsigned long long) s_matches);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// KV record as in include/tsgpu.h (56 bytes)
+struct KVOut {
+    uint64_t key, distinct_key;
+    int64_t  scores[3];
+    int64_t  text_match_score;
+    float    vector_distance;
+    int8_t   match_score_index;
+    uint8_t  pad0;
+    uint16_t query_index;
+};
+static_assert(sizeof(KVOut) == 56, "tsgpu_kv layout");
+
+struct FinalParams {
+    const QDesc* qd;
+    const UDesc* ud;
+    const int64_t* pool_s0; const int64_t* pool_s1; const int64_t* pool_s2;
+    const uint32_t* pool_key;
+    const uint32_t* unit_cnt;
+    const uint32_t* combo_matches;
+    KVOut* out_kv;
+    uint32_t* out_count;
+    uint32_t* out_found;
+    uint32_t* out_searched;     // [nq] combinations with results = searched_queries.size() (may be nullptr)
+    uint32_t kv_stride;
+    uint32_t KP;
+};
+
+constexpr int kFinalThreads = 256;
+
+// One CTA per query: merge the units of all its combinations into the final Topster content.
+__global__ void __launch_bounds__(kFinalThreads)
+kw_final_kernel(const __grid_constant__ FinalParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t KP = P.KP, N2 = 2 * KP;
+    TopBuf tb;
+    tb.s0 = reinterpret_cast<int64_t*>(smem_raw);
+    tb.s1 = tb.s0 + N2;
+    tb.s2 = tb.s1 + N2;
+    tb.key = reinterpret_cast<uint32_t*>(tb.s2 + N2);
+    tb.cmb = reinterpret_cast<uint16_t*>(tb.key + N2);
+    tb.vd = nullptr;
+    __shared__ uint16_t s_qidx[kMaxCombosPerQuery];
+    __shared__ uint32_t s_n, s_found;
+
+    const uint32_t q = blockIdx.x, tid = threadIdx.x;
+    const QDesc qd = P.qd[q];
+    const uint32_t K = qd.topk;
+    const uint32_t n_combos = qd.combo_end - qd.combo_begin;
+    const bool multi = n_combos > 1;
+    if(tid == 0) {
+        // query_index = searched_queries.size() when the combination ran = number of earlier combinations with
+        // results (src/index.cpp:5575-5580)
+        uint32_t qi = 0, found = 0;
+        for(uint32_t c = 0; c < n_combos; c++) {
+            const uint32_t m = P.combo_matches[qd.combo_begin + c];
+            if(c < kMaxCombosPerQuery) s_qidx[c] = (uint16_t) qi;
+            if(m) qi++;
+            found += m;
+        }
+        s_found = found;
+        s_n = 0;
+        if(P.out_searched) P.out_searched[q] = qi;
+    }
+    __syncthreads();
+
+    auto reduce = [&](uint32_t n) -> uint32_t {
+        tb_fill_invalid(tb, n, N2);
+        __syncthreads();
+        if(multi) {
+            tb_sort<true>(tb, N2);
+            // entries of one seq_id are adjacent, best first: drop the rest (Topster keeps the greater KV per key)
+            bool dup[8];
+            int cnt = 0;
+            for(uint32_t i = tid; i < N2; i += kFinalThreads) dup[cnt++] = (i > 0 && tb.key[i] != kNone && tb.key[i] == tb.key[i - 1]);
+            __syncthreads();
+            cnt = 0;
+            for(uint32_t i = tid; i < N2; i += kFinalThreads) if(dup[cnt++]) tb.key[i] = kNone;
+            __syncthreads();
+        }
+        tb_sort<false>(tb, N2);
+        // count valid (they are in front)
+        uint32_t lo = 0, hi = N2;
+        while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(tb.key[mid] != kNone) lo = mid + 1; else hi = mid; }
+        return lo < K ? lo : K;
+    };
+
+    uint32_t n = 0;
+    for(uint32_t u = qd.unit_begin; u < qd.unit_end; u++) {
+        const uint32_t cnt = P.unit_cnt[u];
+        if(cnt == 0) continue;
+        const UDesc ud = P.ud[u];
+        uint32_t done = 0;
+        while(done < cnt) {
+            if(n == N2) { n = reduce(n); __syncthreads(); }
+            const uint32_t take = min(cnt - done, N2 - n);
+            for(uint32_t i = tid; i < take; i += kFinalThreads) {
+                const uint32_t o = ud.out_off + done + i;
+                tb.s0[n + i] = P.pool_s0[o]; tb.s1[n + i] = P.pool_s1[o]; tb.s2[n + i] = P.pool_s2[o];
+                tb.key[n + i] = P.pool_key[o];
+                tb.cmb[n + i] = (uint16_t) (ud.combo - qd.combo_begin);
+            }
+            n += take; done += take;
+            __syncthreads();
+        }
+    }
+    n = reduce(n);
+    __syncthreads();
+
+    int msi = -1;
+    for(int i = 0; i < 3; i++) if(qd.sort_type[i] == 1) msi = i;
+    const uint32_t n_out = n < P.kv_stride ? n : P.kv_stride;
+    for(uint32_t i = tid; i < n_out; i += kFinalThreads) {
+        KVOut kv;
+        kv.key = tb.key[i]; kv.distinct_key = tb.key[i];
+        kv.scores[0] = tb.s0[i]; kv.scores[1] = tb.s1[i]; kv.scores[2] = tb.s2[i];
+        kv.text_match_score = msi >= 0 ? kv.scores[msi] : 0;
+        kv.vector_distance = -1.0f;
+        kv.match_score_index = (int8_t) msi;
+        kv.pad0 = 0;
+        const uint16_t c = tb.cmb[i];
+        kv.query_index = c < kMaxCombosPerQuery ? s_qidx[c] : 0;
+        P.out_kv[(size_t) q * P.kv_stride + i] = kv;
+    }
+    if(tid == 0) {
+        P.out_count[q] = n_out;
+        if(!(multi && qd.found_bitmap)) P.out_found[q] = s_found;     // else: popcount of the union bitmap
+    }
+}
+
+// found = |union of result ids| for queries with several combinations (the reference ORs id_buff into
+// all_result_ids, src/index.cpp:5081-5090)
+__global__ void __launch_bounds__(256)
+found_popcount_kernel(const QDesc* qd, const uint32_t* multi_q, uint32_t n_words, uint32_t* out_found) {
+    const uint32_t q = multi_q[blockIdx.x];
+    const uint32_t* bm = qd[q].found_bitmap;
+    uint32_t c = 0;
+    for(uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) c += __popc(bm[i]);
+    for(int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    __shared__ uint32_t s[8];
+    if((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if(threadIdx.x == 0) { uint32_t t = 0; for(int i = 0; i < 8; i++) t += s[i]; out_found[q] = t; }
+}
+
+// sorted ids -> bitmap (filter_result_iterator_t::to_filter_id_array() mirrored as bits)
+__global__ void bitmap_from_ids_kernel(const uint32_t* __restrict__ ids, size_t n, uint32_t* __restrict__ bitmap, uint32_t n_docs) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) { const uint32_t id = ids[i]; if(id < n_docs) atomicOr(bitmap + (id >> 5), 1u << (id & 31)); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tsgpu_intersect / tsgpu_phrase_matches: per-tile flags -> (count, compacted ids) -> scan -> gather.
+struct IsectParams {
+    uint32_t field;          // index field id
+    uint32_t k;
+    uint32_t lists[kMaxTokens];
+    uint32_t driver;         // index into lists (intersect); unused for phrase
+    const uint32_t* ids;     // phrase: candidate ids (ascending); nullptr for intersect
+    size_t n_ids;
+    uint32_t n_tiles;
+    uint32_t* tile_cnt;      // [n_tiles]
+    uint32_t* tile_ids;      // [n_tiles*128]
+    int phrase;
+};
+
+__global__ void __launch_bounds__(kThreads)
+isect_tiles_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ IsectParams P) {
+    __shared__ uint32_t l_blk0[kMaxTokens], l_blk1[kMaxTokens], l_lo[kMaxTokens], l_hi[kMaxTokens];
+    __shared__ unsigned long long l_df[kMaxTokens], l_base[kMaxTokens];
+    __shared__ uint32_t s_warp[8];
+    const DevField& g = ix.fields[P.field];
+    const uint32_t tid = threadIdx.x, tile = blockIdx.x;
+    if(tid < P.k) {
+        const uint32_t l = P.lists[tid];
+        l_blk0[tid] = g.list_blk_off[l]; l_blk1[tid] = g.list_blk_off[l + 1] - 1;
+        l_base[tid] = g.list_off[l]; l_df[tid] = g.list_off[l + 1] - g.list_off[l];
+    }
+    __syncthreads();
+    uint32_t id = 0, first = 0, tmax = 0, cnt = 0;
+    uint32_t own = kNone;      // posting index of the candidate in the driver list (intersect)
+    if(!P.phrase) {
+        const uint32_t d = P.driver;
+        const uint32_t b = l_blk0[d] + tile;
+        cnt = block_count(b, l_blk0[d], l_df[d]);
+        first = __ldg(g.blk_first + b);
+        const unsigned long long info = __ldg(reinterpret_cast<const unsigned long long*>(g.blk_info) + b);
+        const uint32_t bits = (uint32_t) (info >> 40) & 0xFF;
+        const uint32_t* w = g.packed + (info & 0xFFFFFFFFFFull);
+        id = first + unpack_at(w, bits, tid < cnt ? tid : 0);
+        tmax = first + unpack_at(w, bits, cnt - 1);
+        own = tile * kBlock + tid;
+    } else {
+        const size_t base = (size_t) tile * kBlock;
+        cnt = (uint32_t) min((size_t) kBlock, P.n_ids - base);
+        id = P.ids[base + (tid < cnt ? tid : 0)];
+        first = P.ids[base];
+        tmax = P.ids[base + cnt - 1];
+    }
+    bool alive = tid < cnt;
+    if(tid < 2 * P.k) {
+        const uint32_t j = tid >> 1;
+        const uint32_t r = gallop_block(g.blk_first, l_blk0[j], l_blk1[j], (tid & 1) ? tmax : first);
+        if(tid & 1) l_hi[j] = r; else l_lo[j] = (r == kNone ? l_blk0[j] : r);
+    }
+    __syncthreads();
+    uint32_t hidx[kMaxTokens];
+    for(uint32_t j = 0; j < P.k; j++) {
+        uint32_t h = kNone;
+        if(!P.phrase && j == P.driver) h = own;
+        else if(alive && l_hi[j] != kNone) {
+            const uint32_t bb = find_block(g.blk_first, l_lo[j], l_hi[j], id);
+            if(bb != kNone) {
+                const uint32_t ii = probe_block(g, bb, block_count(bb, l_blk0[j], l_df[j]), id);
+                if(ii != kNone) h = (bb - l_blk0[j]) * kBlock + ii;
+            }
+        }
+        hidx[j] = h;
+        if(h == kNone) alive = false;
+    }
+    if(alive && P.phrase) {
+        RawTok toks[kMaxTokens];
+        for(uint32_t j = 0; j < P.k; j++) {
+            const unsigned long long p = l_base[j] + hidx[j];
+            const unsigned long long o0 = g.pos_off[p], o1 = g.pos_off[p + 1];
+            toks[j].p = g.positions + o0; toks[j].n = (uint32_t) (o1 - o0);
+        }
+        alive = phrase_match_doc(toks, (int) P.k);
+    }
+    uint32_t total;
+    const uint32_t rank = cta_rank(alive, s_warp, &total);
+    if(alive) P.tile_ids[(size_t) tile * kBlock + rank] = id;
+    if(tid == 0) P.tile_cnt[tile] = total;
+}
+
+// single-CTA exclusive scan of tile counts (n_tiles <= a few hundred thousand)
+__global__ void __launch_bounds__(1024)
+scan_tiles_kernel(const uint32_t* __restrict__ cnt, uint32_t n, unsigned long long* __restrict__ off, unsigned long long* total) {
+    __shared__ unsigned long long s[1024];
+    __shared__ unsigned long long carry;
+    if(threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for(uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long v = i < n ? cnt[i] : 0;
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for(uint32_t d = 1; d < 1024; d <<= 1) {
+            const unsigned long long t = threadIdx.x >= d ? s[threadIdx.x - d] : 0;
+            __syncthreads();
+            s[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if(i < n) off[i] = carry + s[threadIdx.x] - v;
+        __syncthreads();
+        if(threadIdx.x == 0) carry += s[1023];
+        __syncthreads();
+    }
+    if(threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(kThreads)
+gather_tiles_kernel(const uint32_t* __restrict__ cnt, const unsigned long long* __restrict__ off,
+                    const uint32_t* __restrict__ tile_ids, uint32_t* __restrict__ out, size_t cap) {
+    const uint32_t tile = blockIdx.x;
+    const uint32_t c = cnt[tile];
+    const unsigned long long o = off[tile];
+    if(threadIdx.x < c && o + threadIdx.x < cap) out[o + threadIdx.x] = tile_ids[(size_t) tile * kBlock + threadIdx.x];
+}
+
+}  // namespace tsk

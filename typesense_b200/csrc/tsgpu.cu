@@ -1,0 +1,1072 @@
+// libtsgpu.so — C-ABI (include/tsgpu.h) over the sm_100a kernels in kw_kernels.cuh / knn_kernels.cuh /
+// fuse_kernels.cuh. Host code here only mirrors data into HBM, turns a batch of resolved queries into work
+// descriptors, launches kernels on one stream and copies results out. There is no CPU compute path: every entry point
+// fails with TSGPU_ERR_NO_DEVICE when no CUDA device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tsgpu.h"
+#include "fuse_kernels.cuh"
+#include "knn_kernels.cuh"
+#include "postings_pack.h"
+
+using namespace tsk;
+
+namespace {
+
+thread_local std::string g_err;
+tsgpu_status fail(tsgpu_status s, const std::string& m) { g_err = m; return s; }
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if(e__ != cudaSuccess) {                                                                              \
+            return fail(TSGPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " @" + std::to_string(__LINE__)); \
+        }                                                                                                     \
+    } while(0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes, bool zero_new = false) {
+        if(bytes <= cap) return cudaSuccess;
+        if(p) cudaFree(p);
+        p = nullptr;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if(e != cudaSuccess) { cap = 0; return e; }
+        cap = want;
+        if(zero_new) return cudaMemset(p, 0, cap);
+        return cudaSuccess;
+    }
+    void release() { if(p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if(bytes <= cap) return cudaSuccess;
+        if(p) cudaFreeHost(p);
+        p = nullptr;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if(e != cudaSuccess) { cap = 0; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if(p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// sequential packer of several arrays into one staging buffer (8-byte aligned pieces)
+struct Stager {
+    std::vector<unsigned char> host;
+    size_t add(const void* src, size_t bytes) {
+        size_t off = (host.size() + 15) & ~size_t(15);
+        host.resize(off + bytes);
+        if(bytes && src) memcpy(host.data() + off, src, bytes);
+        return off;
+    }
+    size_t reserve(size_t bytes) { return add(nullptr, bytes); }
+};
+
+struct FieldMirror {
+    DevField dev{};
+    std::vector<uint64_t> h_list_off;
+    std::vector<uint32_t> h_list_blk_off;
+    void* d_alloc[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+struct Filter {
+    uint32_t* d_bitmap = nullptr;
+    uint32_t* d_ids = nullptr;
+    size_t n = 0;
+    bool live = false;
+};
+
+}  // namespace
+
+struct tsgpu_index {
+    int device = 0;
+    uint32_t n_docs = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::vector<FieldMirror> fields;
+    IndexDev ixdev{};
+    std::vector<int64_t*> sort_cols;
+    bool has_hnsw = false;
+    tsv::HnswDev hnsw{};
+    std::vector<void*> hnsw_alloc;
+    std::vector<Filter> filters;
+    int n_sms = 148;
+    // scratch
+    DevBuf d_stage, d_pool, d_small, d_bitmaps, d_out, d_knn_vis, d_knn_log, d_knn_cand, d_knn_out, d_isect, d_kw_out;
+    PinBuf h_stage;
+    size_t knn_slots = 0, knn_vis_words = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    tsgpu_stats stats{};
+};
+
+namespace {
+
+tsgpu_status check_device(tsgpu_index* idx) {
+    if(!idx) return fail(TSGPU_ERR_INVALID, "null index");
+    CU(cudaSetDevice(idx->device));
+    return TSGPU_OK;
+}
+
+uint32_t pow2_ceil(uint32_t v) { uint32_t p = 1; while(p < v) p <<= 1; return p; }
+
+// ------------------------------------------------------------------------------------------------- keyword prep
+struct KwPlan {
+    uint32_t nq = 0, nc = 0, F = 0, n_units = 0;
+    uint32_t KP = 128, NL = 1, KMAX = 1;
+    uint32_t field_ids[kMaxFieldSlots] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<QDesc> qd;
+    std::vector<CDesc> cd;
+    std::vector<UDesc> ud;
+    std::vector<uint32_t> multi_q;        // queries whose found count needs the union bitmap
+    size_t pool_slots = 0;
+    // device views (valid after upload)
+    QDesc* d_qd = nullptr; CDesc* d_cd = nullptr; UDesc* d_ud = nullptr; uint32_t* d_multi_q = nullptr;
+    uint32_t* d_unit_cnt = nullptr; uint32_t* d_combo_matches = nullptr; unsigned long long* d_stats = nullptr;
+    std::vector<const uint32_t*> q_bitmap;   // per query filter bitmap (device) or nullptr
+    std::vector<const uint32_t*> q_filter_ids; std::vector<size_t> q_filter_n;   // device ids (flat path)
+    std::vector<const uint32_t*> q_excl_dev;
+};
+
+tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_combos, KwPlan& pl) {
+    if(!b) return fail(TSGPU_ERR_INVALID, "null batch");
+    const uint32_t nq = b->n_queries, F = b->n_fields;
+    if(with_combos && (F == 0 || F > TSGPU_MAX_FIELDS)) return fail(TSGPU_ERR_CAPACITY, "n_fields must be 1.." + std::to_string(TSGPU_MAX_FIELDS));
+    for(uint32_t f = 0; f < F; f++) if(b->field_ids[f] >= idx->fields.size()) return fail(TSGPU_ERR_INVALID, "field id out of range");
+    pl.nq = nq; pl.F = F; pl.nc = with_combos ? b->n_combos : 0;
+    for(uint32_t f = 0; f < F && f < (uint32_t) kMaxFieldSlots; f++) pl.field_ids[f] = b->field_ids[f];
+    pl.qd.assign(nq, QDesc{});
+    pl.cd.assign(pl.nc, CDesc{});
+    pl.q_bitmap.assign(nq, nullptr); pl.q_filter_ids.assign(nq, nullptr); pl.q_filter_n.assign(nq, 0); pl.q_excl_dev.assign(nq, nullptr);
+    uint32_t kmax = 1, nl_max = 1;
+    auto df_of = [&](uint32_t f, uint32_t l) -> uint64_t {
+        const FieldMirror& fm = idx->fields[b->field_ids[f]];
+        return fm.h_list_off[l + 1] - fm.h_list_off[l];
+    };
+    // ---- combos
+    std::vector<uint32_t> combo_tiles(pl.nc, 0);
+    uint64_t total_tiles = 0;
+    for(uint32_t c = 0; c < pl.nc; c++) {
+        CDesc& cd = pl.cd[c];
+        const uint32_t r0 = b->c_tok_off[c], n_rows = b->c_tok_off[c + 1] - r0;
+        if(n_rows > TSGPU_MAX_TOKENS) return fail(TSGPU_ERR_CAPACITY, "more than TSGPU_MAX_TOKENS token rows in a combination");
+        if(n_rows * F > (uint32_t) kMaxLists) return fail(TSGPU_ERR_CAPACITY, "rows*fields exceeds 32 in a combination");
+        const uint32_t n_req = std::min<uint32_t>(b->c_n_required[c], n_rows);
+        cd.total_cost = b->c_total_cost[c];
+        cd.syn_orig = b->c_syn_orig_num_tokens ? b->c_syn_orig_num_tokens[c] : -1;
+        cd.orig = b->c_orig_num_tokens ? b->c_orig_num_tokens[c] : -1;
+        cd.cflags = b->c_flags ? b->c_flags[c] : 0;
+        cd.n_rows = (uint8_t) n_rows; cd.n_req = (uint8_t) n_req;
+        nl_max = std::max(nl_max, n_rows * F);
+        uint64_t sumdf[TSGPU_MAX_TOKENS];
+        for(uint32_t i = 0; i < (uint32_t) kMaxLists; i++) cd.lists[i] = kNone;
+        for(uint32_t r = 0; r < n_rows; r++) {
+            sumdf[r] = 0;
+            for(uint32_t f = 0; f < F; f++) {
+                uint32_t l = b->t_list[(size_t) (r0 + r) * F + f];
+                if(l != TSGPU_NO_LIST) {
+                    const FieldMirror& fm = idx->fields[b->field_ids[f]];
+                    if(l >= fm.dev.n_lists) return fail(TSGPU_ERR_INVALID, "posting list id out of range");
+                    if(df_of(f, l) == 0) l = TSGPU_NO_LIST;       // empty list == token absent from the field
+                }
+                cd.lists[r * F + f] = l;
+                if(l != TSGPU_NO_LIST) sumdf[r] += df_of(f, l);
+            }
+        }
+        cd.req_mask = 0;
+        uint32_t drv = kNone;
+        for(uint32_t r = 0; r < n_req; r++) if(sumdf[r]) { cd.req_mask |= 1u << r; if(drv == kNone || sumdf[r] < sumdf[drv]) drv = r; }
+        uint32_t tiles = 0;
+        for(uint32_t f = 0; f <= (uint32_t) kMaxFieldSlots; f++) cd.drv_tile_off[f] = 0;
+        if(drv != kNone) {
+            cd.driver_row = (uint8_t) drv;
+            for(uint32_t f = 0; f < F; f++) {
+                cd.drv_tile_off[f] = tiles;
+                const uint32_t l = cd.lists[drv * F + f];
+                if(l != TSGPU_NO_LIST) tiles += (uint32_t) ((df_of(f, l) + tsdev::kBlock - 1) / tsdev::kBlock);
+            }
+            for(uint32_t f = F; f <= (uint32_t) kMaxFieldSlots; f++) cd.drv_tile_off[f] = tiles;
+            // probe order: driver, other required rows by ascending postings, then the dropped rows
+            std::vector<uint32_t> order;
+            order.push_back(drv);
+            std::vector<uint32_t> rest;
+            for(uint32_t r = 0; r < n_req; r++) if(r != drv) rest.push_back(r);
+            std::stable_sort(rest.begin(), rest.end(), [&](uint32_t a, uint32_t c2) { return sumdf[a] < sumdf[c2]; });
+            for(uint32_t r: rest) order.push_back(r);
+            for(uint32_t r = n_req; r < n_rows; r++) order.push_back(r);
+            for(uint32_t i = 0; i < 16; i++) cd.probe_order[i] = i < order.size() ? (uint8_t) order[i] : 0;
+        }
+        combo_tiles[c] = tiles;
+        total_tiles += tiles;
+    }
+    // ---- queries
+    uint32_t tpu = (uint32_t) std::min<uint64_t>(32, std::max<uint64_t>(4, total_tiles / 4096));
+    for(uint32_t q = 0; q < nq; q++) {
+        QDesc& qd = pl.qd[q];
+        const uint32_t K = b->q_topk[q];
+        if(K == 0 || K > TSGPU_MAX_TOPK) return fail(TSGPU_ERR_CAPACITY, "topk must be 1.." + std::to_string(TSGPU_MAX_TOPK));
+        qd.topk = K; kmax = std::max(kmax, K);
+        for(int i = 0; i < 3; i++) {
+            qd.sort_type[i] = b->q_sort_type[q * 3 + i];
+            qd.sort_order[i] = b->q_sort_order[q * 3 + i];
+            qd.missing_first[i] = b->q_sort_missing_first ? b->q_sort_missing_first[q * 3 + i] : 0;
+            qd.sort_col[i] = nullptr;
+            if(qd.sort_type[i] == TSGPU_SORT_NUMERIC) {
+                const int32_t col = b->q_sort_col[q * 3 + i];
+                if(col < 0 || (size_t) col >= idx->sort_cols.size()) return fail(TSGPU_ERR_INVALID, "sort column out of range");
+                qd.sort_col[i] = idx->sort_cols[col];
+            }
+        }
+        qd.flags = b->q_flags[q]; qd.match_type = b->q_match_type[q]; qd.num_query_tokens = b->q_num_query_tokens[q];
+        for(uint32_t f = 0; f < (uint32_t) kMaxFieldSlots; f++) qd.field_weight[f] = f < F ? b->q_field_weight[(size_t) q * F + f] : 0;
+        qd.n_excl = b->q_excl_off[q + 1] - b->q_excl_off[q];
+        qd.combo_begin = with_combos ? b->q_combo_off[q] : 0;
+        qd.combo_end = with_combos ? b->q_combo_off[q + 1] : 0;
+        if(qd.combo_end - qd.combo_begin > (uint32_t) kMaxCombosPerQuery) return fail(TSGPU_ERR_CAPACITY, "more than 256 combinations in a query");
+        qd.unit_begin = (uint32_t) pl.ud.size();
+        uint32_t combos_with_tiles = 0;
+        for(uint32_t c = qd.combo_begin; c < qd.combo_end; c++) {
+            pl.cd[c].q = q;
+            if(combo_tiles[c]) combos_with_tiles++;
+            for(uint32_t t = 0; t < combo_tiles[c]; t += tpu) {
+                UDesc u;
+                u.combo = c; u.tile_begin = t; u.tile_end = std::min(combo_tiles[c], t + tpu);
+                u.out_off = (uint32_t) pl.pool_slots;
+                pl.pool_slots += K;
+                pl.ud.push_back(u);
+            }
+        }
+        qd.unit_end = (uint32_t) pl.ud.size();
+        if(combos_with_tiles > 1) pl.multi_q.push_back(q);
+        const int32_t fs = b->q_filter[q];
+        if(fs >= 0 && (uint32_t) fs >= b->n_filters) return fail(TSGPU_ERR_INVALID, "inline filter slot out of range");
+        if(fs <= -2) {
+            const size_t h = (size_t) (-(fs + 2));
+            if(h >= idx->filters.size() || !idx->filters[h].live) return fail(TSGPU_ERR_INVALID, "unknown filter handle");
+        }
+    }
+    if(pl.pool_slots > 0xFFFFFFF0ull) return fail(TSGPU_ERR_CAPACITY, "result pool too large; split the batch");
+    pl.n_units = (uint32_t) pl.ud.size();
+    pl.KMAX = kmax;
+    pl.KP = std::max<uint32_t>(128, pow2_ceil(kmax));
+    pl.NL = nl_max;
+    return TSGPU_OK;
+}
+
+// uploads descriptors, exclusion lists and inline filters; builds filter / found bitmaps
+tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& pl) {
+    cudaStream_t st = idx->stream;
+    const uint32_t nq = pl.nq;
+    const size_t words = ((size_t) idx->n_docs + 31) / 32;
+    // device bitmaps: [inline filters][found bitmaps]
+    const size_t n_inline = b->n_filters;
+    const size_t n_bm = n_inline + pl.multi_q.size();
+    if(n_bm) {
+        CU(idx->d_bitmaps.reserve(n_bm * words * 4));
+        CU(cudaMemsetAsync(idx->d_bitmaps.p, 0, n_bm * words * 4, st));
+    }
+    uint32_t* bm = idx->d_bitmaps.as<uint32_t>();
+    Stager sg;
+    const size_t n_excl_total = b->q_excl_off[nq];
+    const size_t o_excl = sg.add(b->excl_ids, n_excl_total * 4);
+    const size_t n_fids = n_inline ? (size_t) b->filter_off[n_inline] : 0;
+    const size_t o_fids = sg.add(b->filter_ids, n_fids * 4);
+    // descriptor pointers need the device base first: compute offsets, then patch
+    const size_t o_qd = sg.reserve(pl.qd.size() * sizeof(QDesc));
+    const size_t o_cd = sg.reserve(pl.cd.size() * sizeof(CDesc));
+    const size_t o_ud = sg.reserve(pl.ud.size() * sizeof(UDesc));
+    const size_t o_mq = sg.reserve(pl.multi_q.size() * 4);
+    const size_t o_cnt = sg.reserve(((size_t) pl.n_units + pl.nc + 8) * 4 + 64);
+    CU(idx->d_stage.reserve(sg.host.size()));
+    unsigned char* dbase = idx->d_stage.as<unsigned char>();
+    const uint32_t* d_excl = reinterpret_cast<const uint32_t*>(dbase + o_excl);
+    const uint32_t* d_fids = reinterpret_cast<const uint32_t*>(dbase + o_fids);
+    for(uint32_t q = 0; q < nq; q++) {
+        QDesc& qd = pl.qd[q];
+        qd.excl = d_excl + b->q_excl_off[q];
+        pl.q_excl_dev[q] = qd.excl;
+        const int32_t fs = b->q_filter[q];
+        qd.filter_bitmap = nullptr; qd.filter_empty = 0;
+        if(fs >= 0) {
+            const size_t n = (size_t) (b->filter_off[fs + 1] - b->filter_off[fs]);
+            qd.filter_bitmap = bm + (size_t) fs * words;
+            qd.filter_empty = n == 0;
+            pl.q_filter_ids[q] = d_fids + b->filter_off[fs]; pl.q_filter_n[q] = n;
+        } else if(fs <= -2) {
+            const Filter& fl = idx->filters[(size_t) (-(fs + 2))];
+            qd.filter_bitmap = fl.d_bitmap;
+            qd.filter_empty = fl.n == 0;
+            pl.q_filter_ids[q] = fl.d_ids; pl.q_filter_n[q] = fl.n;
+        }
+        pl.q_bitmap[q] = qd.filter_bitmap;
+        qd.found_bitmap = nullptr;
+    }
+    for(size_t i = 0; i < pl.multi_q.size(); i++) pl.qd[pl.multi_q[i]].found_bitmap = bm + (n_inline + i) * words;
+    memcpy(sg.host.data() + o_qd, pl.qd.data(), pl.qd.size() * sizeof(QDesc));
+    memcpy(sg.host.data() + o_cd, pl.cd.data(), pl.cd.size() * sizeof(CDesc));
+    memcpy(sg.host.data() + o_ud, pl.ud.data(), pl.ud.size() * sizeof(UDesc));
+    memcpy(sg.host.data() + o_mq, pl.multi_q.data(), pl.multi_q.size() * 4);
+    memset(sg.host.data() + o_cnt, 0, ((size_t) pl.n_units + pl.nc + 8) * 4 + 64);
+    CU(idx->h_stage.reserve(sg.host.size()));
+    memcpy(idx->h_stage.p, sg.host.data(), sg.host.size());
+    CU(cudaMemcpyAsync(dbase, idx->h_stage.p, sg.host.size(), cudaMemcpyHostToDevice, st));
+    idx->stats.h2d_bytes += sg.host.size();
+    pl.d_qd = reinterpret_cast<QDesc*>(dbase + o_qd);
+    pl.d_cd = reinterpret_cast<CDesc*>(dbase + o_cd);
+    pl.d_ud = reinterpret_cast<UDesc*>(dbase + o_ud);
+    pl.d_multi_q = reinterpret_cast<uint32_t*>(dbase + o_mq);
+    unsigned char* cnt = dbase + ((o_cnt + 63) & ~size_t(63));
+    pl.d_stats = reinterpret_cast<unsigned long long*>(cnt);                 // 4 x u64
+    pl.d_combo_matches = reinterpret_cast<uint32_t*>(cnt + 32);
+    pl.d_unit_cnt = pl.d_combo_matches + pl.nc;
+    // inline filter bitmaps
+    for(size_t s = 0; s < n_inline; s++) {
+        const size_t n = (size_t) (b->filter_off[s + 1] - b->filter_off[s]);
+        if(!n) continue;
+        bitmap_from_ids_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(d_fids + b->filter_off[s], n, bm + s * words, idx->n_docs);
+        idx->stats.launches_total++;
+    }
+    CU(cudaGetLastError());
+    return TSGPU_OK;
+}
+
+size_t kw_search_smem(const KwPlan& pl) { return (size_t) 2 * pl.KP * 28 + (size_t) pl.NL * kThreads * 4 + 2 * kThreads * 4; }
+size_t kw_final_smem(const KwPlan& pl) { return (size_t) 2 * pl.KP * 30 + 16; }
+
+struct KwDeviceOut { KVOut* kv; uint32_t* count; uint32_t* found; uint32_t* searched; uint32_t stride; };
+
+// intersect/score/select + per-query merge; leaves KVOut/count/found/searched in idx->d_kw_out
+tsgpu_status run_keyword(tsgpu_index* idx, KwPlan& pl, uint32_t kv_stride, KwDeviceOut& out) {
+    cudaStream_t st = idx->stream;
+    const uint32_t nq = pl.nq;
+    const size_t kv_bytes = (size_t) nq * kv_stride * sizeof(KVOut);
+    CU(idx->d_kw_out.reserve(kv_bytes + (size_t) nq * 12 + 64));
+    out.kv = idx->d_kw_out.as<KVOut>();
+    out.count = reinterpret_cast<uint32_t*>(idx->d_kw_out.as<unsigned char>() + ((kv_bytes + 15) & ~size_t(15)));
+    out.found = out.count + nq;
+    out.searched = out.found + nq;
+    out.stride = kv_stride;
+    CU(idx->d_pool.reserve(pl.pool_slots * 28 + 64));
+    int64_t* p0 = idx->d_pool.as<int64_t>();
+    int64_t* p1 = p0 + pl.pool_slots;
+    int64_t* p2 = p1 + pl.pool_slots;
+    uint32_t* pk = reinterpret_cast<uint32_t*>(p2 + pl.pool_slots);
+    CU(cudaEventRecord(idx->ev[1], st));
+    if(pl.n_units) {
+        KwParams P{};
+        P.qd = pl.d_qd; P.cd = pl.d_cd; P.ud = pl.d_ud;
+        P.pool_s0 = p0; P.pool_s1 = p1; P.pool_s2 = p2; P.pool_key = pk;
+        P.unit_cnt = pl.d_unit_cnt; P.combo_matches = pl.d_combo_matches; P.stats = pl.d_stats;
+        P.F = pl.F; P.KP = pl.KP; P.NL = pl.NL;
+        for(uint32_t f = 0; f < (uint32_t) kMaxFieldSlots; f++) P.field_ids[f] = pl.field_ids[f];
+        const size_t smem = kw_search_smem(pl);
+        CU(cudaFuncSetAttribute(kw_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024)));
+        kw_search_kernel<<<pl.n_units, kThreads, smem, st>>>(idx->ixdev, P);
+        idx->stats.launches_total++;
+        CU(cudaGetLastError());
+    }
+    {
+        FinalParams P{};
+        P.qd = pl.d_qd; P.ud = pl.d_ud;
+        P.pool_s0 = p0; P.pool_s1 = p1; P.pool_s2 = p2; P.pool_key = pk;
+        P.unit_cnt = pl.d_unit_cnt; P.combo_matches = pl.d_combo_matches;
+        P.out_kv = out.kv; P.out_count = out.count; P.out_found = out.found; P.out_searched = out.searched;
+        P.kv_stride = kv_stride; P.KP = pl.KP;
+        const size_t smem = kw_final_smem(pl);
+        CU(cudaFuncSetAttribute(kw_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024)));
+        if(nq) {
+            kw_final_kernel<<<nq, kFinalThreads, smem, st>>>(P);
+            idx->stats.launches_total++;
+        }
+        CU(cudaGetLastError());
+        if(!pl.multi_q.empty()) {
+            found_popcount_kernel<<<(unsigned) pl.multi_q.size(), 256, 0, st>>>(pl.d_qd, pl.d_multi_q, (uint32_t) (((size_t) idx->n_docs + 31) / 32), out.found);
+            idx->stats.launches_total++;
+            CU(cudaGetLastError());
+        }
+    }
+    CU(cudaEventRecord(idx->ev[2], st));
+    return TSGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- knn
+struct KnnDeviceOut { float* dist; uint32_t* labels; uint32_t* n; uint32_t stride; };
+
+template <int NCH>
+void launch_hnsw(tsgpu_index* idx, const tsv::KnnParams& P, unsigned grid, size_t smem) {
+    cudaFuncSetAttribute(tsv::hnsw_search_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024));
+    tsv::hnsw_search_kernel<NCH><<<grid, tsv::kKnnThreads, smem, idx->stream>>>(idx->hnsw, P);
+}
+
+// d_queries: [nq*dim] on device. q_bitmap/q_excl/q_nexcl/q_skip: host vectors (uploaded here). Results in d_knn_out.
+tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef,
+                     const std::vector<const uint32_t*>& q_bitmap, const std::vector<const uint32_t*>& q_excl,
+                     const std::vector<uint32_t>& q_nexcl, const std::vector<uint8_t>& q_skip, KnnDeviceOut& out) {
+    cudaStream_t st = idx->stream;
+    if(!idx->has_hnsw) return fail(TSGPU_ERR_INVALID, "no vector index loaded");
+    if(k == 0) return fail(TSGPU_ERR_INVALID, "k must be > 0");
+    const uint32_t efe = std::max(ef, k);
+    if(efe > 4096) return fail(TSGPU_ERR_CAPACITY, "max(ef,k) must be <= 4096");
+    const tsv::HnswDev& g = idx->hnsw;
+    // persistent warps: 4 per CTA
+    const unsigned max_blocks = (unsigned) idx->n_sms * 4;
+    const unsigned grid = std::max(1u, std::min(max_blocks, (nq + 3) / 4));
+    const size_t slots = (size_t) grid * 4;
+    const size_t vis_words = ((size_t) g.n_nodes + 31) / 32;
+    const uint32_t log_cap = 16384, cand_cap = 32768;
+    if(slots * vis_words > idx->knn_slots * idx->knn_vis_words || vis_words != idx->knn_vis_words) {
+        idx->d_knn_vis.release();
+        CU(idx->d_knn_vis.reserve(slots * vis_words * 4));
+        CU(cudaMemsetAsync(idx->d_knn_vis.p, 0, idx->d_knn_vis.cap, st));
+        idx->knn_slots = slots; idx->knn_vis_words = vis_words;
+    }
+    CU(idx->d_knn_log.reserve(slots * log_cap * 4));
+    CU(idx->d_knn_cand.reserve(slots * (size_t) cand_cap * 8));
+    // outputs + per-query pointer tables
+    Stager sg;
+    const size_t o_bm = sg.add(q_bitmap.empty() ? nullptr : q_bitmap.data(), (size_t) nq * 8);
+    const size_t o_ex = sg.add(q_excl.empty() ? nullptr : q_excl.data(), (size_t) nq * 8);
+    const size_t o_ne = sg.add(q_nexcl.empty() ? nullptr : q_nexcl.data(), (size_t) nq * 4);
+    const size_t o_sk = sg.add(q_skip.empty() ? nullptr : q_skip.data(), (size_t) nq);
+    const size_t o_misc = sg.reserve(64);
+    memset(sg.host.data() + o_misc, 0, 64);
+    const size_t tbl_bytes = sg.host.size();
+    const size_t out_bytes = (size_t) nq * k * 8 + (size_t) nq * 4;
+    CU(idx->d_knn_out.reserve(tbl_bytes + out_bytes + 256));
+    unsigned char* base = idx->d_knn_out.as<unsigned char>();
+    // staging through a dedicated pinned region at the tail of h_stage is not safe while the kw stage is in flight,
+    // so use a plain async copy from the pageable vector (small)
+    CU(cudaMemcpyAsync(base, sg.host.data(), tbl_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));      // sg.host is pageable and about to go out of scope
+    idx->stats.h2d_bytes += tbl_bytes;
+    unsigned char* ob = base + ((tbl_bytes + 255) & ~size_t(255));
+    out.dist = reinterpret_cast<float*>(ob);
+    out.labels = reinterpret_cast<uint32_t*>(ob + (size_t) nq * k * 4);
+    out.n = reinterpret_cast<uint32_t*>(ob + (size_t) nq * k * 8);
+    out.stride = k;
+    tsv::KnnParams P{};
+    P.queries = d_queries; P.nq = nq; P.k = k; P.ef = ef;
+    P.q_filter_bitmap = q_bitmap.empty() ? nullptr : reinterpret_cast<const uint32_t* const*>(base + o_bm);
+    P.q_excl = q_excl.empty() ? nullptr : reinterpret_cast<const uint32_t* const*>(base + o_ex);
+    P.q_n_excl = q_nexcl.empty() ? nullptr : reinterpret_cast<const uint32_t*>(base + o_ne);
+    P.q_skip = q_skip.empty() ? nullptr : reinterpret_cast<const uint8_t*>(base + o_sk);
+    P.out_dist = out.dist; P.out_labels = out.labels; P.out_n = out.n;
+    P.visited = idx->d_knn_vis.as<uint32_t>(); P.vis_words = (uint32_t) vis_words;
+    P.vis_log = idx->d_knn_log.as<uint32_t>(); P.log_cap = log_cap;
+    P.cand = idx->d_knn_cand.as<unsigned long long>(); P.cand_cap = cand_cap;
+    P.counter = reinterpret_cast<uint32_t*>(base + o_misc);
+    P.stats = reinterpret_cast<unsigned long long*>(base + o_misc + 8);
+    P.error = reinterpret_cast<int*>(base + o_misc + 32);
+    const uint32_t dim = g.dim;
+    const int nch = (dim % 128 == 0) ? (int) (dim / 128) : 0;
+    const size_t heap_bytes = (size_t) 4 * (efe + 1) * 8;
+    const size_t q_bytes = (size_t) 4 * ((dim + 3) & ~3u) * 4;
+    CU(cudaEventRecord(idx->ev[3], st));
+    switch(nch) {
+        case 1: launch_hnsw<1>(idx, P, grid, heap_bytes); break;
+        case 2: launch_hnsw<2>(idx, P, grid, heap_bytes); break;
+        case 3: launch_hnsw<3>(idx, P, grid, heap_bytes); break;
+        case 4: launch_hnsw<4>(idx, P, grid, heap_bytes); break;
+        case 6: launch_hnsw<6>(idx, P, grid, heap_bytes); break;
+        case 8: launch_hnsw<8>(idx, P, grid, heap_bytes); break;
+        default: launch_hnsw<0>(idx, P, grid, heap_bytes + q_bytes); break;
+    }
+    idx->stats.launches_total++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(idx->ev[4], st));
+    // stats + overflow flag
+    unsigned long long hst[5];
+    CU(cudaMemcpyAsync(hst, base + o_misc + 8, 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    idx->stats.knn_dist += hst[0]; idx->stats.knn_expanded += hst[1];
+    if((int) hst[3]) return fail(TSGPU_ERR_CAPACITY, "HNSW candidate heap overflow (more than 32768 live candidates in one query)");
+    return TSGPU_OK;
+}
+
+template <int NCH>
+void launch_flat(tsgpu_index* idx, const tsv::FlatParams& P, unsigned long long total, unsigned grid, size_t smem) {
+    tsv::flat_distance_kernel<NCH><<<grid, 256, smem, idx->stream>>>(idx->hnsw, P, total);
+}
+
+tsgpu_status run_flat(tsgpu_index* idx, const tsv::FlatParams& P, unsigned long long total) {
+    if(total == 0) return TSGPU_OK;
+    const uint32_t dim = idx->hnsw.dim;
+    const int nch = (dim % 128 == 0) ? (int) (dim / 128) : 0;
+    const unsigned grid = (unsigned) std::min<unsigned long long>((total + 7) / 8, (unsigned long long) idx->n_sms * 8);
+    const size_t q_bytes = (size_t) 8 * ((dim + 3) & ~3u) * 4;
+    switch(nch) {
+        case 1: launch_flat<1>(idx, P, total, grid, 0); break;
+        case 2: launch_flat<2>(idx, P, total, grid, 0); break;
+        case 3: launch_flat<3>(idx, P, total, grid, 0); break;
+        case 4: launch_flat<4>(idx, P, total, grid, 0); break;
+        case 6: launch_flat<6>(idx, P, total, grid, 0); break;
+        case 8: launch_flat<8>(idx, P, total, grid, 0); break;
+        default: launch_flat<0>(idx, P, total, grid, q_bytes); break;
+    }
+    idx->stats.launches_total++;
+    CU(cudaGetLastError());
+    return TSGPU_OK;
+}
+
+void begin_call(tsgpu_index* idx) {
+    const uint64_t launches = idx->stats.launches_total;
+    idx->stats = tsgpu_stats{};
+    idx->stats.launches_total = launches;
+    cudaEventRecord(idx->ev[0], idx->stream);
+}
+
+tsgpu_status end_call(tsgpu_index* idx, bool kw, bool knn) {
+    cudaStream_t st = idx->stream;
+    CU(cudaEventRecord(idx->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, idx->ev[0], idx->ev[5]); idx->stats.ms_total = ms;
+    if(kw) { cudaEventElapsedTime(&ms, idx->ev[1], idx->ev[2]); idx->stats.ms_keyword = ms; }
+    if(knn) { cudaEventElapsedTime(&ms, idx->ev[3], idx->ev[4]); idx->stats.ms_knn = ms; }
+    idx->stats.ms_kernels = idx->stats.ms_keyword + idx->stats.ms_knn + idx->stats.ms_fuse;
+    return TSGPU_OK;
+}
+
+tsgpu_status fetch_kw_stats(tsgpu_index* idx, const KwPlan& pl) {
+    unsigned long long h[4];
+    CU(cudaMemcpyAsync(h, pl.d_stats, 32, cudaMemcpyDeviceToHost, idx->stream));
+    CU(cudaStreamSynchronize(idx->stream));
+    idx->stats.kw_driver_ids = h[0]; idx->stats.kw_probe_ids = h[1]; idx->stats.kw_matches = h[2];
+    return TSGPU_OK;
+}
+
+// vector stage shared by tsgpu_vector_search_batch / tsgpu_hybrid_search_batch: uploads the query vectors, splits
+// queries into the flat (filtered set below flat_search_cutoff) and HNSW paths exactly as src/index.cpp:3664-3670 /
+// 4056-4065 do, and runs both.
+struct VecStage {
+    KnnDeviceOut knn{};
+    const float* flat_dist = nullptr; const uint32_t* flat_ids = nullptr; const unsigned long long* flat_off = nullptr;
+    const uint8_t* d_is_flat = nullptr;
+    bool any_flat = false;
+    uint32_t k = 0;
+};
+
+tsgpu_status run_vector_stage(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& pl, const float* qvecs,
+                              const tsgpu_vec_params* vp, uint32_t k, VecStage& vs) {
+    cudaStream_t st = idx->stream;
+    const uint32_t nq = pl.nq, dim = idx->hnsw.dim;
+    vs.k = k;
+    // decide paths
+    std::vector<uint8_t> is_flat(nq, 0);
+    std::vector<unsigned long long> foff(nq + 1, 0);
+    for(uint32_t q = 0; q < nq; q++) {
+        const bool filter_given = b->q_filter[q] != -1;
+        if(filter_given && pl.q_filter_n[q] < vp->flat_search_cutoff) is_flat[q] = 1;
+        foff[q + 1] = foff[q] + (is_flat[q] ? pl.q_filter_n[q] : 0);
+    }
+    const unsigned long long total_flat = foff[nq];
+    vs.any_flat = total_flat > 0 || std::any_of(is_flat.begin(), is_flat.end(), [](uint8_t x) { return x != 0; });
+    // device scratch: queries | is_flat | flat_off | flat ids | flat dist
+    const size_t q_bytes = (size_t) nq * dim * 4;
+    const size_t o_q = 0;
+    const size_t o_if = (q_bytes + 255) & ~size_t(255);
+    const size_t o_fo = (o_if + nq + 255) & ~size_t(255);
+    const size_t o_fi = (o_fo + (size_t) (nq + 1) * 8 + 255) & ~size_t(255);
+    const size_t o_fd = (o_fi + total_flat * 4 + 255) & ~size_t(255);
+    const size_t tot = o_fd + total_flat * 4 + 256;
+    CU(idx->d_small.reserve(tot));
+    unsigned char* base = idx->d_small.as<unsigned char>();
+    CU(cudaMemcpyAsync(base + o_q, qvecs, q_bytes, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(base + o_if, is_flat.data(), nq, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_fo, foff.data(), (size_t) (nq + 1) * 8, cudaMemcpyHostToDevice, st));
+    idx->stats.h2d_bytes += q_bytes + nq + (size_t) (nq + 1) * 8;
+    for(uint32_t q = 0; q < nq; q++) {
+        if(is_flat[q] && pl.q_filter_n[q])
+            CU(cudaMemcpyAsync(base + o_fi + foff[q] * 4, pl.q_filter_ids[q], pl.q_filter_n[q] * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    CU(cudaStreamSynchronize(st));       // host vectors above are pageable
+    vs.d_is_flat = base + o_if;
+    vs.flat_off = reinterpret_cast<const unsigned long long*>(base + o_fo);
+    vs.flat_ids = reinterpret_cast<const uint32_t*>(base + o_fi);
+    vs.flat_dist = reinterpret_cast<const float*>(base + o_fd);
+    if(total_flat) {
+        tsv::FlatParams FP{};
+        FP.queries = reinterpret_cast<const float*>(base + o_q);
+        FP.ids = vs.flat_ids; FP.q_off = vs.flat_off; FP.nq = nq;
+        FP.out_dist = reinterpret_cast<float*>(base + o_fd);
+        FP.stats = nullptr;
+        tsgpu_status s = run_flat(idx, FP, total_flat);
+        if(s != TSGPU_OK) return s;
+    }
+    // HNSW for the rest
+    std::vector<uint32_t> nexcl(nq);
+    for(uint32_t q = 0; q < nq; q++) nexcl[q] = pl.qd[q].n_excl;
+    // a filter that matches nothing lets VectorFilterFunctor through only without exclusions; the reference returns
+    // before searching in that case — mark such queries as skipped
+    std::vector<uint8_t> skip(is_flat);
+    for(uint32_t q = 0; q < nq; q++) if(pl.qd[q].filter_empty) skip[q] = 1;
+    return run_knn(idx, reinterpret_cast<const float*>(base + o_q), nq, k, vp->ef, pl.q_bitmap, pl.q_excl_dev, nexcl, skip, vs.knn);
+}
+
+}  // namespace
+
+// ===================================================================================================== C API
+extern "C" {
+
+const char* tsgpu_last_error(void) { return g_err.c_str(); }
+
+int tsgpu_device_count(void) {
+    int n = 0;
+    if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+tsgpu_status tsgpu_index_create(uint32_t n_docs, int device, tsgpu_index** out) {
+    if(!out) return fail(TSGPU_ERR_INVALID, "null out");
+    int n = 0;
+    if(cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(TSGPU_ERR_NO_DEVICE, "no CUDA device: libtsgpu has no CPU fallback");
+    }
+    if(device < 0 || device >= n) return fail(TSGPU_ERR_INVALID, "bad device ordinal");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    tsgpu_index* idx = new tsgpu_index();
+    idx->device = device; idx->n_docs = n_docs; idx->n_sms = prop.multiProcessorCount;
+    idx->ixdev.n_docs = n_docs;
+    if(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete idx; return fail(TSGPU_ERR_CUDA, "stream create failed"); }
+    for(auto& e: idx->ev) cudaEventCreate(&e);
+    *out = idx;
+    return TSGPU_OK;
+}
+
+void tsgpu_index_destroy(tsgpu_index* idx) {
+    if(!idx) return;
+    cudaSetDevice(idx->device);
+    cudaStreamSynchronize(idx->stream);
+    for(auto& f: idx->fields) for(void* p: f.d_alloc) if(p) cudaFree(p);
+    for(auto* c: idx->sort_cols) cudaFree(c);
+    for(void* p: idx->hnsw_alloc) cudaFree(p);
+    for(auto& f: idx->filters) { if(f.d_bitmap) cudaFree(f.d_bitmap); if(f.d_ids) cudaFree(f.d_ids); }
+    DevBuf* bufs[] = {&idx->d_stage, &idx->d_pool, &idx->d_small, &idx->d_bitmaps, &idx->d_out, &idx->d_knn_vis,
+                      &idx->d_knn_log, &idx->d_knn_cand, &idx->d_knn_out, &idx->d_isect, &idx->d_kw_out};
+    for(auto* b: bufs) b->release();
+    idx->h_stage.release();
+    for(auto& e: idx->ev) if(e) cudaEventDestroy(e);
+    cudaStreamDestroy(idx->stream);
+    delete idx;
+}
+
+tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint32_t* out_field) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!f || !out_field) return fail(TSGPU_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if(idx->fields.size() >= (size_t) kMaxIndexFields) return fail(TSGPU_ERR_CAPACITY, "too many fields");
+    FieldMirror fm;
+    const uint32_t L = f->n_lists;
+    fm.h_list_off.resize((size_t) L + 1);
+    CU(cudaMemcpy(fm.h_list_off.data(), f->list_off, ((size_t) L + 1) * 8, cudaMemcpyDefault));
+    const uint64_t n_post = fm.h_list_off[L];
+    std::vector<uint32_t> h_ids(n_post ? n_post : 1);
+    if(n_post) CU(cudaMemcpy(h_ids.data(), f->ids, n_post * 4, cudaMemcpyDefault));
+    for(uint32_t l = 0; l < L; l++) if(fm.h_list_off[l + 1] < fm.h_list_off[l]) return fail(TSGPU_ERR_INVALID, "list_off not monotone");
+    tspack::PackedField pk;
+    tspack::pack_field(L, fm.h_list_off.data(), h_ids.data(), pk);
+    fm.h_list_blk_off = pk.list_blk_off;
+    uint64_t n_pos = 0;
+    CU(cudaMemcpy(&n_pos, f->pos_off + n_post, 8, cudaMemcpyDefault));
+    auto up = [&](int slot, const void* src, size_t bytes, bool from_user) -> cudaError_t {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, bytes ? bytes : 16);
+        if(e != cudaSuccess) return e;
+        fm.d_alloc[slot] = d;
+        if(bytes) e = cudaMemcpy(d, src, bytes, from_user ? cudaMemcpyDefault : cudaMemcpyHostToDevice);
+        return e;
+    };
+    CU(up(0, fm.h_list_off.data(), ((size_t) L + 1) * 8, false));
+    CU(up(1, pk.list_blk_off.data(), pk.list_blk_off.size() * 4, false));
+    CU(up(2, pk.blk_first.data(), pk.blk_first.size() * 4, false));
+    CU(up(3, pk.blk_info.data(), pk.blk_info.size() * 8, false));
+    CU(up(4, pk.packed.data(), pk.packed.size() * 4, false));
+    CU(up(5, f->pos_off, (n_post + 1) * 8, true));
+    CU(up(6, f->positions, n_pos * 4, true));
+    fm.dev.n_lists = L; fm.dev.is_array = f->is_array;
+    fm.dev.list_off = (const uint64_t*) fm.d_alloc[0];
+    fm.dev.list_blk_off = (const uint32_t*) fm.d_alloc[1];
+    fm.dev.blk_first = (const uint32_t*) fm.d_alloc[2];
+    fm.dev.blk_info = (const uint64_t*) fm.d_alloc[3];
+    fm.dev.packed = (const uint32_t*) fm.d_alloc[4];
+    fm.dev.pos_off = (const uint64_t*) fm.d_alloc[5];
+    fm.dev.positions = (const uint32_t*) fm.d_alloc[6];
+    idx->ixdev.fields[idx->fields.size()] = fm.dev;
+    *out_field = (uint32_t) idx->fields.size();
+    idx->fields.push_back(std::move(fm));
+    return TSGPU_OK;
+}
+
+tsgpu_status tsgpu_index_load_sort_column(tsgpu_index* idx, const int64_t* vals, uint32_t* out_col) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!vals || !out_col) return fail(TSGPU_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    int64_t* d = nullptr;
+    CU(cudaMalloc(&d, (size_t) std::max<uint32_t>(idx->n_docs, 1) * 8));
+    CU(cudaMemcpy(d, vals, (size_t) idx->n_docs * 8, cudaMemcpyDefault));
+    *out_col = (uint32_t) idx->sort_cols.size();
+    idx->sort_cols.push_back(d);
+    return TSGPU_OK;
+}
+
+tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!g) return fail(TSGPU_ERR_INVALID, "null graph");
+    if(g->M == 0 || g->M > 32) return fail(TSGPU_ERR_CAPACITY, "M must be 1..32");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    for(void* p: idx->hnsw_alloc) cudaFree(p);
+    idx->hnsw_alloc.clear();
+    const size_t n = g->n_nodes;
+    auto up = [&](const void* src, size_t bytes, const void** dst) -> cudaError_t {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, bytes ? bytes : 16);
+        if(e != cudaSuccess) return e;
+        idx->hnsw_alloc.push_back(d);
+        *dst = d;
+        return bytes ? cudaMemcpy(d, src, bytes, cudaMemcpyDefault) : cudaSuccess;
+    };
+    tsv::HnswDev h{};
+    h.n_nodes = g->n_nodes; h.dim = g->dim; h.M = g->M; h.max_level = g->max_level; h.entry_point = g->entry_point; h.metric = g->metric;
+    uint64_t n_up = 0;
+    if(n) CU(cudaMemcpy(&n_up, g->upper_off + n, 8, cudaMemcpyDefault));
+    const void* p = nullptr;
+    CU(up(g->vectors, n * g->dim * 4, &p)); h.vectors = (const float*) p;
+    if(g->labels) { CU(up(g->labels, n * 4, &p)); h.labels = (const uint32_t*) p; } else h.labels = nullptr;
+    CU(up(g->levels, n, &p)); h.levels = (const uint8_t*) p;
+    CU(up(g->links0, n * (2 * (size_t) g->M + 1) * 4, &p)); h.links0 = (const uint32_t*) p;
+    CU(up(g->upper_off, (n + 1) * 8, &p)); h.upper_off = (const unsigned long long*) p;
+    CU(up(g->links_up, n_up * ((size_t) g->M + 1) * 4, &p)); h.links_up = (const uint32_t*) p;
+    if(h.labels) {   // identity labels are the common case: detect and drop the indirection
+        std::vector<uint32_t> hl(n);
+        CU(cudaMemcpy(hl.data(), h.labels, n * 4, cudaMemcpyDeviceToHost));
+        bool ident = true;
+        for(size_t i = 0; i < n && ident; i++) ident = hl[i] == i;
+        if(ident) h.labels = nullptr;
+    }
+    idx->hnsw = h;
+    idx->has_hnsw = true;
+    return TSGPU_OK;
+}
+
+tsgpu_status tsgpu_filter_create(tsgpu_index* idx, const uint32_t* ids, size_t n, int32_t* out_handle) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!out_handle || (n && !ids)) return fail(TSGPU_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    Filter f;
+    const size_t words = ((size_t) idx->n_docs + 31) / 32;
+    CU(cudaMalloc(&f.d_bitmap, std::max<size_t>(words, 4) * 4));
+    CU(cudaMemset(f.d_bitmap, 0, std::max<size_t>(words, 4) * 4));
+    CU(cudaMalloc(&f.d_ids, std::max<size_t>(n, 4) * 4));
+    if(n) {
+        CU(cudaMemcpy(f.d_ids, ids, n * 4, cudaMemcpyDefault));
+        bitmap_from_ids_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, idx->stream>>>(f.d_ids, n, f.d_bitmap, idx->n_docs);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(idx->stream));
+    }
+    f.n = n; f.live = true;
+    idx->filters.push_back(f);
+    *out_handle = -((int32_t) idx->filters.size() - 1) - 2;      // encoded for tsgpu_kw_batch::q_filter
+    return TSGPU_OK;
+}
+
+tsgpu_status tsgpu_filter_destroy(tsgpu_index* idx, int32_t handle) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if(handle > -2) return fail(TSGPU_ERR_INVALID, "bad filter handle");
+    const size_t h = (size_t) (-(handle + 2));
+    if(h >= idx->filters.size() || !idx->filters[h].live) return fail(TSGPU_ERR_INVALID, "bad filter handle");
+    cudaFree(idx->filters[h].d_bitmap); cudaFree(idx->filters[h].d_ids);
+    idx->filters[h] = Filter{};
+    return TSGPU_OK;
+}
+
+static tsgpu_status isect_common(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, const uint32_t* ids,
+                                 size_t n_ids, bool phrase, uint32_t* out_ids, size_t cap, size_t* out_n) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!lists || !out_n || k == 0) return fail(TSGPU_ERR_INVALID, "bad argument");
+    if(field >= idx->fields.size()) return fail(TSGPU_ERR_INVALID, "field out of range");
+    if(k > TSGPU_MAX_TOKENS) return fail(TSGPU_ERR_CAPACITY, "k exceeds TSGPU_MAX_TOKENS");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    begin_call(idx);
+    cudaStream_t st = idx->stream;
+    const FieldMirror& fm = idx->fields[field];
+    IsectParams P{};
+    P.field = field; P.k = k; P.phrase = phrase ? 1 : 0;
+    uint64_t best = ~0ull;
+    for(uint32_t j = 0; j < k; j++) {
+        if(lists[j] >= fm.dev.n_lists) return fail(TSGPU_ERR_INVALID, "list out of range");
+        P.lists[j] = lists[j];
+        const uint64_t df = fm.h_list_off[lists[j] + 1] - fm.h_list_off[lists[j]];
+        if(df == 0) { *out_n = 0; return end_call(idx, false, false); }
+        if(df < best) { best = df; P.driver = j; }
+    }
+    uint32_t n_tiles;
+    if(phrase) {
+        if(n_ids == 0) { *out_n = 0; return end_call(idx, false, false); }
+        n_tiles = (uint32_t) ((n_ids + tsdev::kBlock - 1) / tsdev::kBlock);
+    } else n_tiles = (uint32_t) ((best + tsdev::kBlock - 1) / tsdev::kBlock);
+    // scratch: [ids?][tile_cnt][tile_off u64][total u64][tile_ids][out]
+    const size_t o_ids = 0;
+    const size_t o_cnt = (o_ids + (phrase ? n_ids * 4 : 0) + 255) & ~size_t(255);
+    const size_t o_off = (o_cnt + (size_t) n_tiles * 4 + 255) & ~size_t(255);
+    const size_t o_tot = o_off + (size_t) n_tiles * 8;
+    const size_t o_tid = (o_tot + 8 + 255) & ~size_t(255);
+    const size_t o_out = o_tid + (size_t) n_tiles * tsdev::kBlock * 4;
+    CU(idx->d_isect.reserve(o_out + (size_t) n_tiles * tsdev::kBlock * 4 + 256));
+    unsigned char* base = idx->d_isect.as<unsigned char>();
+    if(phrase) { CU(cudaMemcpyAsync(base + o_ids, ids, n_ids * 4, cudaMemcpyDefault, st)); idx->stats.h2d_bytes += n_ids * 4; }
+    P.ids = phrase ? reinterpret_cast<const uint32_t*>(base + o_ids) : nullptr;
+    P.n_ids = n_ids; P.n_tiles = n_tiles;
+    P.tile_cnt = reinterpret_cast<uint32_t*>(base + o_cnt);
+    P.tile_ids = reinterpret_cast<uint32_t*>(base + o_tid);
+    CU(cudaEventRecord(idx->ev[1], st));
+    isect_tiles_kernel<<<n_tiles, kThreads, 0, st>>>(idx->ixdev, P);
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(P.tile_cnt, n_tiles, reinterpret_cast<unsigned long long*>(base + o_off),
+                                          reinterpret_cast<unsigned long long*>(base + o_tot));
+    gather_tiles_kernel<<<n_tiles, kThreads, 0, st>>>(P.tile_cnt, reinterpret_cast<unsigned long long*>(base + o_off), P.tile_ids,
+                                                      reinterpret_cast<uint32_t*>(base + o_out), (size_t) n_tiles * tsdev::kBlock);
+    idx->stats.launches_total += 3;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(idx->ev[2], st));
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, base + o_tot, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *out_n = (size_t) total;
+    if(total > cap) return fail(TSGPU_ERR_CAPACITY, "output buffer too small");
+    if(total) { CU(cudaMemcpyAsync(out_ids, base + o_out, total * 4, cudaMemcpyDefault, st)); idx->stats.d2h_bytes += total * 4 + 8; }
+    return end_call(idx, true, false);
+}
+
+tsgpu_status tsgpu_intersect(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, uint32_t* out_ids,
+                             size_t cap, size_t* out_n) {
+    return isect_common(idx, field, lists, k, nullptr, 0, false, out_ids, cap, out_n);
+}
+
+tsgpu_status tsgpu_phrase_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, const uint32_t* ids,
+                                  size_t n, uint32_t* out_ids, size_t* out_n) {
+    return isect_common(idx, field, lists, k, ids, n, true, out_ids, n, out_n);
+}
+
+tsgpu_status tsgpu_keyword_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, tsgpu_kv* out_kv, uint32_t kv_stride,
+                                        uint32_t* out_count, uint32_t* out_found) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!b || !out_kv || !out_count || !out_found || kv_stride == 0) return fail(TSGPU_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    begin_call(idx);
+    KwPlan pl;
+    s = build_kw_plan(idx, b, true, pl); if(s) return s;
+    if(pl.nq == 0) return end_call(idx, false, false);
+    s = upload_kw_plan(idx, b, pl); if(s) return s;
+    KwDeviceOut o{};
+    s = run_keyword(idx, pl, kv_stride, o); if(s) return s;
+    cudaStream_t st = idx->stream;
+    CU(cudaMemcpyAsync(out_kv, o.kv, (size_t) pl.nq * kv_stride * sizeof(KVOut), cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(out_count, o.count, (size_t) pl.nq * 4, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(out_found, o.found, (size_t) pl.nq * 4, cudaMemcpyDefault, st));
+    idx->stats.d2h_bytes += (size_t) pl.nq * kv_stride * sizeof(KVOut) + (size_t) pl.nq * 8;
+    s = end_call(idx, true, false); if(s) return s;
+    return fetch_kw_stats(idx, pl);
+}
+
+tsgpu_status tsgpu_knn_batch(tsgpu_index* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                             const int32_t* q_filter, uint32_t n_filters, const uint64_t* filter_off,
+                             const uint32_t* filter_ids, float* out_dist, uint32_t* out_labels, uint32_t* out_n) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!queries || !out_dist || !out_labels || !out_n) return fail(TSGPU_ERR_INVALID, "null argument");
+    if(!idx->has_hnsw) return fail(TSGPU_ERR_INVALID, "no vector index loaded");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    begin_call(idx);
+    if(nq == 0) return end_call(idx, false, false);
+    cudaStream_t st = idx->stream;
+    const uint32_t dim = idx->hnsw.dim;
+    const size_t words = ((size_t) idx->n_docs + 31) / 32;
+    // queries + inline filter ids -> device
+    const size_t q_bytes = (size_t) nq * dim * 4;
+    const size_t n_fids = (q_filter && n_filters) ? (size_t) filter_off[n_filters] : 0;
+    const size_t o_f = (q_bytes + 255) & ~size_t(255);
+    CU(idx->d_small.reserve(o_f + n_fids * 4 + 256));
+    unsigned char* base = idx->d_small.as<unsigned char>();
+    CU(cudaMemcpyAsync(base, queries, q_bytes, cudaMemcpyDefault, st));
+    idx->stats.h2d_bytes += q_bytes;
+    std::vector<const uint32_t*> q_bitmap;
+    std::vector<uint8_t> skip;
+    if(q_filter) {
+        q_bitmap.assign(nq, nullptr);
+        skip.assign(nq, 0);
+        if(n_fids) { CU(cudaMemcpyAsync(base + o_f, filter_ids, n_fids * 4, cudaMemcpyDefault, st)); idx->stats.h2d_bytes += n_fids * 4; }
+        if(n_filters) {
+            CU(idx->d_bitmaps.reserve((size_t) n_filters * words * 4));
+            CU(cudaMemsetAsync(idx->d_bitmaps.p, 0, (size_t) n_filters * words * 4, st));
+        }
+        uint32_t* bm = idx->d_bitmaps.as<uint32_t>();
+        for(uint32_t f = 0; f < n_filters; f++) {
+            const size_t n = (size_t) (filter_off[f + 1] - filter_off[f]);
+            if(n) bitmap_from_ids_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(base + o_f) + filter_off[f], n, bm + (size_t) f * words, idx->n_docs);
+        }
+        CU(cudaGetLastError());
+        for(uint32_t q = 0; q < nq; q++) {
+            const int32_t fs = q_filter[q];
+            if(fs >= 0) {
+                if((uint32_t) fs >= n_filters) return fail(TSGPU_ERR_INVALID, "filter slot out of range");
+                q_bitmap[q] = bm + (size_t) fs * words;
+            } else if(fs <= -2) {
+                const size_t h = (size_t) (-(fs + 2));
+                if(h >= idx->filters.size() || !idx->filters[h].live) return fail(TSGPU_ERR_INVALID, "unknown filter handle");
+                q_bitmap[q] = idx->filters[h].d_bitmap;
+            }
+        }
+    }
+    KnnDeviceOut o{};
+    s = run_knn(idx, reinterpret_cast<const float*>(base), nq, k, ef, q_bitmap, {}, {}, {}, o); if(s) return s;
+    CU(cudaMemcpyAsync(out_dist, o.dist, (size_t) nq * k * 4, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(out_labels, o.labels, (size_t) nq * k * 4, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(out_n, o.n, (size_t) nq * 4, cudaMemcpyDefault, st));
+    idx->stats.d2h_bytes += (size_t) nq * k * 8 + (size_t) nq * 4;
+    return end_call(idx, false, true);
+}
+
+tsgpu_status tsgpu_flat_distances(tsgpu_index* idx, const float* query, const uint32_t* ids, size_t n, float* out_dist) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!query || (n && (!ids || !out_dist))) return fail(TSGPU_ERR_INVALID, "null argument");
+    if(!idx->has_hnsw) return fail(TSGPU_ERR_INVALID, "no vector index loaded");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    begin_call(idx);
+    if(n == 0) return end_call(idx, false, false);
+    cudaStream_t st = idx->stream;
+    const uint32_t dim = idx->hnsw.dim;
+    const size_t o_off = ((size_t) dim * 4 + 255) & ~size_t(255);
+    const size_t o_ids = o_off + 256;
+    const size_t o_d = (o_ids + n * 4 + 255) & ~size_t(255);
+    CU(idx->d_small.reserve(o_d + n * 4 + 256));
+    unsigned char* base = idx->d_small.as<unsigned char>();
+    unsigned long long off[2] = {0, (unsigned long long) n};
+    CU(cudaMemcpyAsync(base, query, (size_t) dim * 4, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(base + o_off, off, 16, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_ids, ids, n * 4, cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+    idx->stats.h2d_bytes += (size_t) dim * 4 + n * 4;
+    tsv::FlatParams FP{};
+    FP.queries = reinterpret_cast<const float*>(base); FP.ids = reinterpret_cast<const uint32_t*>(base + o_ids);
+    FP.q_off = reinterpret_cast<const unsigned long long*>(base + o_off); FP.nq = 1;
+    FP.out_dist = reinterpret_cast<float*>(base + o_d);
+    CU(cudaEventRecord(idx->ev[3], st));
+    s = run_flat(idx, FP, n); if(s) return s;
+    CU(cudaEventRecord(idx->ev[4], st));
+    CU(cudaMemcpyAsync(out_dist, base + o_d, n * 4, cudaMemcpyDefault, st));
+    idx->stats.d2h_bytes += n * 4;
+    return end_call(idx, false, true);
+}
+
+static tsgpu_status vec_or_hybrid(tsgpu_index* idx, const tsgpu_kw_batch* b, const float* qvecs, const tsgpu_vec_params* vp,
+                                  tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found, bool hybrid) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!b || !qvecs || !vp || !out_kv || !out_count || !out_found || kv_stride == 0) return fail(TSGPU_ERR_INVALID, "null argument");
+    if(!idx->has_hnsw) return fail(TSGPU_ERR_INVALID, "no vector index loaded");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    begin_call(idx);
+    KwPlan pl;
+    s = build_kw_plan(idx, b, hybrid, pl); if(s) return s;
+    if(pl.nq == 0) return end_call(idx, false, false);
+    s = upload_kw_plan(idx, b, pl); if(s) return s;
+    cudaStream_t st = idx->stream;
+    const uint32_t nq = pl.nq;
+    KwDeviceOut kwo{};
+    if(hybrid) { s = run_keyword(idx, pl, std::max(kv_stride, pl.KMAX), kwo); if(s) return s; }
+    // k as in src/index.cpp:3646 (wildcard) and :4061-4063 (hybrid)
+    const uint32_t k = hybrid ? (vp->k == 0 ? std::max<uint32_t>(vp->fetch_size, 100) : vp->k)
+                              : (vp->k == 0 ? std::max<uint32_t>(vp->k, vp->fetch_size) : vp->k);
+    if(k == 0) return fail(TSGPU_ERR_INVALID, "k resolves to 0 (set k or fetch_size)");
+    if(hybrid && k > 1024) return fail(TSGPU_ERR_CAPACITY, "hybrid k must be <= 1024");
+    VecStage vs;
+    s = run_vector_stage(idx, b, pl, qvecs, vp, k, vs); if(s) return s;
+    // final assembly
+    const size_t kv_bytes = (size_t) nq * kv_stride * sizeof(KVOut);
+    CU(idx->d_out.reserve(kv_bytes + (size_t) nq * 8 + 64));
+    KVOut* d_kv = idx->d_out.as<KVOut>();
+    uint32_t* d_cnt = reinterpret_cast<uint32_t*>(idx->d_out.as<unsigned char>() + ((kv_bytes + 15) & ~size_t(15)));
+    uint32_t* d_found = d_cnt + nq;
+    tsf::VecParams dvp{k, vp->distance_threshold, vp->alpha, idx->hnsw.metric};
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    if(!hybrid) {
+        tsf::VecAssembleParams P{};
+        P.qd = pl.d_qd;
+        P.res_dist = vs.knn.dist; P.res_ids = vs.knn.labels; P.res_n = vs.knn.n; P.res_stride = vs.knn.stride;
+        P.flat_dist = vs.flat_dist; P.flat_ids = vs.flat_ids;
+        P.res_off = vs.flat_off; P.q_is_flat = vs.any_flat ? vs.d_is_flat : nullptr;
+        P.vp = dvp;
+        P.out_kv = d_kv; P.out_count = d_cnt; P.out_found = d_found; P.kv_stride = kv_stride;
+        P.KP = std::max<uint32_t>(pl.KP, 256);          // 256 threads append per round
+        const size_t smem = (size_t) 2 * P.KP * 32 + 16;
+        CU(cudaFuncSetAttribute(tsf::vec_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024)));
+        tsf::vec_assemble_kernel<<<nq, kFinalThreads, smem, st>>>(P);
+        idx->stats.launches_total++;
+        CU(cudaGetLastError());
+    } else {
+        tsf::HybridParams P{};
+        P.ix = idx->ixdev; P.qd = pl.d_qd; P.cd = pl.d_cd; P.F = pl.F;
+        for(uint32_t f = 0; f < (uint32_t) kMaxFieldSlots; f++) P.field_ids[f] = pl.field_ids[f];
+        P.kw_kv = kwo.kv; P.kw_count = kwo.count; P.kw_found = kwo.found; P.kw_searched = kwo.searched; P.kw_stride = kwo.stride;
+        P.res_dist = vs.knn.dist; P.res_ids = vs.knn.labels; P.res_n = vs.knn.n; P.res_stride = vs.knn.stride;
+        P.flat_dist = vs.flat_dist; P.flat_ids = vs.flat_ids;
+        P.res_off = vs.flat_off; P.q_is_flat = vs.any_flat ? vs.d_is_flat : nullptr;
+        P.vp = dvp;
+        P.out_kv = d_kv; P.out_count = d_cnt; P.out_found = d_found; P.kv_stride = kv_stride;
+        P.KMAX = pl.KMAX; P.VMAX = k;
+        const uint32_t KP2 = pow2_ceil(pl.KMAX), VP2 = pow2_ceil(k);
+        const size_t smem = (size_t) pl.KMAX * sizeof(KVOut) + (size_t) (KP2 + 2) * 2 + (size_t) VP2 * 12 + 32;
+        CU(cudaFuncSetAttribute(tsf::hybrid_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024)));
+        tsf::hybrid_fuse_kernel<<<nq, kThreads, smem, st>>>(P);
+        idx->stats.launches_total++;
+        CU(cudaGetLastError());
+    }
+    cudaEventRecord(e1, st);
+    CU(cudaMemcpyAsync(out_kv, d_kv, kv_bytes, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(out_count, d_cnt, (size_t) nq * 4, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(out_found, d_found, (size_t) nq * 4, cudaMemcpyDefault, st));
+    idx->stats.d2h_bytes += kv_bytes + (size_t) nq * 8;
+    s = end_call(idx, hybrid, true);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    idx->stats.ms_fuse = ms; idx->stats.ms_kernels += ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if(s) return s;
+    if(hybrid) return fetch_kw_stats(idx, pl);
+    return TSGPU_OK;
+}
+
+tsgpu_status tsgpu_vector_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const float* qvecs, const tsgpu_vec_params* vp,
+                                       tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
+    return vec_or_hybrid(idx, b, qvecs, vp, out_kv, kv_stride, out_count, out_found, false);
+}
+
+tsgpu_status tsgpu_hybrid_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const float* qvecs, const tsgpu_vec_params* vp,
+                                       tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
+    return vec_or_hybrid(idx, b, qvecs, vp, out_kv, kv_stride, out_count, out_found, true);
+}
+
+tsgpu_status tsgpu_get_stats(tsgpu_index* idx, tsgpu_stats* out) {
+    if(!idx || !out) return fail(TSGPU_ERR_INVALID, "null argument");
+    *out = idx->stats;
+    return TSGPU_OK;
+}
+
+}  // extern "C"
