@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py — queries/sec of the Typesense query hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA path through the tsgpu C-ABI
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU implementation of the same path (oracle port)
+
+Workload (config.workload = "hybrid10m"): BASELINE.json configs[3] on one GPU — 10 M docs, one `title` string field
+(Zipf 1.07 over 1 M words, 4-12 tokens), int64 `points`, int `cat` in [0,10) mirrored as 10 persistent filters, 10 M
+x 768 fp32 unit vectors with an HNSW-shaped graph (M=16); a step is ONE multi_search batch of 4096 hybrid queries
+(3 resolved terms, 30 % of the queries carry 4 typo-candidate combinations, half carry `cat:=c`, vector k=100 ef=100,
+alpha 0.3, sort _text_match desc, points desc, Topster 250, 100 hits returned). Synthetic, seeded; every rank holds a
+full replica and runs its own batch (weak scaling, no data-path collective except the NVLink gather of the top-k).
+
+`value`  : queries/s with query vectors + result buffers resident in HBM (wall clock of K steps, synchronised on both
+           sides, max over ranks).
+`e2e`    : the same metric through the same C-ABI call with HOST (pinned) buffers: H2D of the query vectors and batch
+           descriptors and D2H of the KV records happen inside the timed region.
+`roofline`: dominant kernel, algorithmic bytes / CUDA-event time measured inside the library on its own stream.
+`cpu_baseline`: the CPU oracle (a port of the reference algorithm, see oracle/) on all host cores, bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="tsgpu", choices=["tsgpu", "reference"])
+    ap.add_argument("--docs", type=int, default=10_000_000)
+    ap.add_argument("--vocab", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="queries per CPU-baseline sample")
+    ap.add_argument("--workload", default="hybrid10m", choices=["hybrid10m", "keyword10m", "knn"])
+    ap.add_argument("--recall-queries", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for l in self.lines:
+            p = [x.strip() for x in l.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); smax = float(p[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+class Workload:
+    pass
+
+
+def build_workload(args, device, rank, need_host_copy):
+    """Seeded synthetic collection. Returns host-side flat postings (always: the loader packs on the host and the
+    oracle reads them) and device-side vectors/graph."""
+    import torch
+    from typesense_b200 import synth
+    t0 = time.time()
+    w = Workload()
+    w.n_docs, w.dim = args.docs, args.dim
+    fd = synth.make_string_field(args.docs, args.vocab, 4, 12, seed=7, device=device)
+    w.fd = fd
+    w.points = synth.make_points(args.docs, seed=13)
+    g = torch.Generator(device="cpu"); g.manual_seed(17)
+    w.cat = torch.randint(0, 10, (args.docs,), generator=g).numpy().astype(np.int32)
+    w.filters = [np.nonzero(w.cat == c)[0].astype(np.uint32) for c in range(10)]
+    log(f"rank{rank}: postings {len(fd.flat.ids)/1e6:.1f}M in {time.time()-t0:.1f}s")
+    w.graph_host = None
+    w.vec_dev = None
+    if args.workload != "keyword10m":
+        t1 = time.time()
+        vec = synth.make_vectors(args.docs, args.dim, seed=1234, device=device)
+        lv, l0, uo, lu, ml, ep = synth.build_graph_bulk(vec, 16, 100)
+        if device != "cpu":
+            torch.cuda.synchronize()
+        log(f"rank{rank}: vectors + bulk graph ({args.docs/1e6:.1f}M x {args.dim}, max_level {ml}) in {time.time()-t1:.1f}s")
+        w.vec_dev, w.graph_dev = vec, (lv, l0.to(torch.int32), uo, lu.to(torch.int32), ml, ep)
+        if need_host_copy:
+            t2 = time.time()
+            from typesense_b200.structs import HnswGraph
+            w.graph_host = HnswGraph(vec.cpu().numpy(), lv.cpu().numpy(), l0.cpu().numpy().astype(np.uint32),
+                                     uo.cpu().numpy().astype(np.uint64), lu.cpu().numpy().astype(np.uint32), 16, ml, ep)
+            log(f"rank{rank}: host copy of vectors/graph for the CPU baseline in {time.time()-t2:.1f}s")
+    return w
+
+
+def make_batches(args, w, n_batches, rank):
+    """Resolved query batches (what the host hands over after tokenising + candidate generation)."""
+    from typesense_b200 import structs as S, synth
+    import torch
+    rng = np.random.default_rng(1000 + rank)
+    out = []
+    df = np.diff(w.fd.flat.list_off.astype(np.int64))
+    for bi in range(n_batches):
+        toks = synth.sample_queries(w.fd, args.batch, 3, int(rng.integers(0, 1 << 30)))
+        qs = []
+        for i in range(args.batch):
+            row = [int(t) for t in toks[i]]
+            combos = [S.Combo([[t] for t in row], 3)]
+            if rng.random() < 0.30:
+                # typo on one term: the host's fuzzy lookup returns up to max_candidates=4 tokens at cost 1; the
+                # original term is one of them, the others are vocabulary neighbours (other words of similar rank)
+                j = int(rng.integers(0, 3))
+                cands = [row[j]]
+                while len(cands) < 4:
+                    c = int(np.clip(row[j] + rng.integers(-50, 51), 0, args.vocab - 1))
+                    if c not in cands and df[c] > 0:
+                        cands.append(c)
+                combos = []
+                for c in cands:
+                    r2 = list(row); r2[j] = c
+                    combos.append(S.Combo([[t] for t in r2], 3, total_cost=2))
+            q = S.Query(combos, topk=250, num_query_tokens=3,
+                        sort=((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_NUMERIC, 0, 1, 0), (S.SORT_NONE, -1, 1, 0)))
+            if i % 2 == 1:
+                q.filter = int(rng.integers(0, 10))
+            qs.append(q)
+        b = S.KwBatch(qs, [0], w.filters)
+        qv = synth.make_vectors(args.batch, args.dim, seed=4321 + 97 * rank + bi).numpy() if args.workload != "keyword10m" else None
+        out.append((b, qv))
+    return out
+
+
+def kw_algorithmic_bytes(b, flat, matches):
+    """4*sum df over every executed (combination, token) + per match [T*(8+4p) + 8S] + 36*K per query."""
+    df = np.diff(flat.list_off.astype(np.int64))
+    lists = b.t_list[b.t_list != 0xFFFFFFFF]
+    return int(4 * df[lists].sum() + matches * (3 * (8 + 4 * 1.3) + 8) + 36 * 250 * b.n_queries)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle_lib as ol
+    from typesense_b200 import structs as S
+    import torch
+    ol.build_oracle()
+    device = "cuda" if torch.cuda.is_available() else "cpu"
+    w = build_workload(args, device, 0, True)
+    oi = ol.OracleIndex(w.n_docs, [w.fd.flat], [w.points], w.graph_host)
+    batches = make_batches(args, w, min(args.steps + args.warmup, 4), 0)
+    cores = os.cpu_count() or 1
+    S_n = min(args.cpu_sample, args.batch)
+    vp = S.vec_params(k=0, ef=10, alpha=0.3, fetch_size=100)
+
+    def step(i):
+        b, qv = batches[i % len(batches)]
+        bh = b.head(S_n)
+        if args.workload == "keyword10m":
+            oi.keyword_search(bh, 100, cores)
+        else:
+            oi.hybrid_search(bh, qv[:S_n], vp, 100, cores)
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    dt = time.perf_counter() - t0
+    qps = S_n * args.steps / dt
+    out = {"impl": "reference", "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic",
+           "config": workload_config(args, S_n),
+           "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                            "sample": f"{S_n} queries of the batch per step, {args.steps} steps"},
+           "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, batch):
+    return {"workload": args.workload, "docs": args.docs, "vocab": args.vocab, "dim": args.dim, "batch": batch,
+            "terms": 3, "typo_candidate_queries": 0.30, "filtered_queries": 0.5, "topster": 250, "hits": 100,
+            "vector": {"k": 100, "ef": 100, "alpha": 0.3, "M": 16, "graph": "bulk local-kNN (harness), shared with the CPU oracle"},
+            "cache": "index working set (>= 30 GB vectors + postings) >> 126 MB L2; a different query batch every step",
+            "parallelism": f"replica x{args.gpus}, queries sharded"}
+
+
+# ------------------------------------------------------------------------------------------------ tsgpu arm
+def run_tsgpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from typesense_b200 import capi, structs as S
+    assert torch.cuda.is_available(), "bench.py --impl tsgpu needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    want_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
+    w = build_workload(args, device, rank, want_cpu)
+    gi = capi.GpuIndex(w.n_docs, local_rank)
+    t0 = time.time()
+    gi.load_field(w.fd.flat)
+    gi.load_sort_column(w.points)
+    handles = [gi.filter_create(f) for f in w.filters]
+    if w.vec_dev is not None:
+        lv, l0, uo, lu, ml, ep = w.graph_dev
+        gi.load_hnsw_raw(w.n_docs, w.dim, 16, ml, ep, 0, w.vec_dev, lv, l0, uo, lu)
+        w.vec_dev = None; w.graph_dev = None
+        del lv, l0, uo, lu
+        torch.cuda.empty_cache()
+    log(f"rank{rank}: mirror loaded in {time.time()-t0:.1f}s")
+    n_b = min(args.steps + args.warmup, 6)
+    batches = make_batches(args, w, n_b, rank)
+    vp = S.vec_params(k=0, ef=10, alpha=0.3, fetch_size=100)
+    stride = 100
+    nq = args.batch
+    gbatches = [(b.with_filter_handles(handles), qv) for b, qv in batches]
+    structs = [gb.struct() for gb, _ in gbatches]
+    hybrid = args.workload != "keyword10m"
+
+    # device-resident inputs/outputs (value) and pinned host ones (e2e)
+    kv_dev = torch.empty(nq * stride * 56, dtype=torch.uint8, device=device)
+    cnt_dev = torch.empty(nq, dtype=torch.int32, device=device)
+    fnd_dev = torch.empty(nq, dtype=torch.int32, device=device)
+    qv_dev = [torch.from_numpy(qv).to(device) for _, qv in gbatches] if hybrid else [None] * n_b
+    kv_pin = torch.empty(nq * stride * 56, dtype=torch.uint8).pin_memory()
+    cnt_pin = torch.empty(nq, dtype=torch.int32).pin_memory()
+    fnd_pin = torch.empty(nq, dtype=torch.int32).pin_memory()
+    qv_pin = [torch.from_numpy(qv).pin_memory() for _, qv in gbatches] if hybrid else [None] * n_b
+    gathered = [torch.empty_like(kv_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def step(i, resident):
+        j = i % n_b
+        gb, _ = gbatches[j]
+        out = (kv_dev, cnt_dev, fnd_dev) if resident else (kv_pin, cnt_pin, fnd_pin)
+        if hybrid:
+            gi.hybrid_search(gb, qv_dev[j] if resident else qv_pin[j], vp, stride, out=out, bstruct=structs[j])
+        else:
+            gi.keyword_search(gb, stride, out=out, bstruct=structs[j])
+        if resident and world > 1:
+            dist.gather(kv_dev, gathered, dst=0)            # top-k gather over NVLink (NCCL)
+        return gi.stats()
+
+    def timed(resident):
+        for i in range(args.warmup):
+            step(i, resident)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sts = []
+        for i in range(args.steps):
+            sts.append(step(args.warmup + i, resident))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, sts
+
+    launches0 = gi.stats()["launches_total"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dt_res, sts = timed(True)
+    launches = gi.stats()["launches_total"] - launches0 - 0
+    dt_e2e, sts_e2e = timed(False)
+    clocks = sampler.stop() if rank == 0 else None
+    launches_per_region = (launches * args.steps) // (args.steps + args.warmup)
+
+    # parity spot check + recall on rank 0 (outside the timed region)
+    extra = {}
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        ms_kw = statistics.mean(s["ms_keyword"] for s in sts)
+        ms_knn = statistics.mean(s["ms_knn"] for s in sts)
+        ms_fuse = statistics.mean(s["ms_fuse"] for s in sts)
+        ms_dev = statistics.mean(s["ms_total"] for s in sts)
+        n_dist = statistics.mean(s["knn_dist"] for s in sts)
+        n_exp = statistics.mean(s["knn_expanded"] for s in sts)
+        matches = statistics.mean(s["kw_matches"] for s in sts)
+        knn_bytes = n_dist * 4 * args.dim + n_exp * 4 * 33
+        kw_bytes = kw_algorithmic_bytes(gbatches[0][0], w.fd.flat, matches)
+        roof = []
+        if hybrid and ms_knn > 0:
+            a = knn_bytes / (ms_knn * 1e-3) / 1e9
+            roof.append({"kernel": "hnsw_search_kernel", "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": a / hbm_peak, "traffic": None, "ms": ms_knn, "algorithmic_bytes": knn_bytes,
+                         "n_dist_per_query": n_dist / nq, "n_expanded_per_query": n_exp / nq, "peak_source": peak_src})
+        if ms_kw > 0:
+            a = kw_bytes / (ms_kw * 1e-3) / 1e9
+            roof.append({"kernel": "kw_search_kernel+kw_final_kernel", "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": a / hbm_peak, "traffic": None, "ms": ms_kw, "algorithmic_bytes": kw_bytes,
+                         "matches_per_query": matches / nq, "peak_source": peak_src})
+        roof.sort(key=lambda r: -r["ms"])
+        extra["roofline"] = roof[0] if roof else None
+        extra["roofline_other"] = roof[1:]
+        extra["device_ms_per_step"] = {"total": ms_dev, "keyword": ms_kw, "knn": ms_knn, "fuse": ms_fuse}
+        if want_cpu:
+            import oracle_lib as ol
+            ol.build_oracle()
+            oi = ol.OracleIndex(w.n_docs, [w.fd.flat], [w.points], w.graph_host)
+            cores = os.cpu_count() or 1
+            S_n = min(args.cpu_sample, nq)
+            b0, qv0 = batches[0]
+            bh = b0.head(S_n)
+            t0 = time.perf_counter()
+            if hybrid:
+                okv, ocnt, ofound = oi.hybrid_search(bh, qv0[:S_n], vp, stride, cores)
+            else:
+                okv, ocnt, ofound = oi.keyword_search(bh, stride, cores)
+            dt_cpu = time.perf_counter() - t0
+            extra["cpu_baseline"] = {"value": S_n / dt_cpu, "unit": "queries/s", "cores": cores, "kind": "port",
+                                     "sample": f"first {S_n} queries of batch 0, all {cores} host threads, one pass"}
+            # parity on that sample (identical top-k ids is the acceptance bar)
+            kv, cnt, found = gi.hybrid_search(gbatches[0][0], qv0, vp, stride) if hybrid else gi.keyword_search(gbatches[0][0], stride)
+            same = sum(int(cnt[q] == ocnt[q] and (kv["key"][q, :cnt[q]] == okv["key"][q, :ocnt[q]]).all()) for q in range(S_n))
+            extra["parity_sample"] = {"queries": S_n, "identical_topk": same, "found_equal": int((found[:S_n] == ofound).sum())}
+            if hybrid and args.recall_queries:
+                R = min(args.recall_queries, nq)
+                d, l, n = gi.knn(qv0[:R], 100, 100)
+                vh = torch.from_numpy(w.graph_host.vectors)
+                qh = torch.from_numpy(qv0[:R])
+                exact = torch.topk(qh.to(device) @ vh.to(device).T, 100, dim=1).indices.cpu().numpy() if args.docs <= 20_000_000 else None
+                if exact is not None:
+                    extra["knn_recall_at_100"] = float(np.mean([len(set(l[i][:n[i]]) & set(exact[i])) / 100 for i in range(R)]))
+        else:
+            extra["cpu_baseline"] = None
+
+    if rank == 0:
+        value = nq * world * args.steps / dt_res
+        e2e = nq * world * args.steps / dt_e2e
+        st = sts_e2e[-1]
+        out = {"metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": 1000 * dt_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u32+f32", "data": "synthetic", "config": workload_config(args, nq),
+               "e2e": {"value": e2e, "unit": "queries/s", "ms_per_step": 1000 * dt_e2e / args.steps,
+                       "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"])},
+               "gpu_launches": int(launches_per_region), "clocks": clocks}
+        out.update(extra)
+        print(json.dumps(out), flush=True)
+    gi.close()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_tsgpu(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -212,6 +212,23 @@ class KwBatch:
         self.filter_ids = (np.concatenate([np.asarray(f, np.uint32) for f in filters]) if filters and off[-1] > 0
                            else np.zeros(1, np.uint32))
 
+    def with_filter_handles(self, handles: Sequence[int]) -> "KwBatch":
+        """Shallow copy whose inline filter slots are replaced by persistent filter handles (tsgpu_filter_create)."""
+        import copy
+        b = copy.copy(self)
+        h = np.asarray(list(handles) + [0], np.int32)
+        b.q_filter = np.where(self.q_filter >= 0, h[np.clip(self.q_filter, 0, len(h) - 1)], self.q_filter).astype(np.int32)
+        b.set_filters([])
+        return b
+
+    def head(self, n: int) -> "KwBatch":
+        """First n queries (shares the per-combination / per-row arrays)."""
+        import copy
+        b = copy.copy(self)
+        b.n_queries = n
+        b.n_combos = int(self.q_combo_off[n])
+        return b
+
     def struct(self) -> KwBatchStruct:
         s = KwBatchStruct()
         s.n_queries, s.n_combos, s.n_fields, s.n_filters = self.n_queries, self.n_combos, self.n_fields, self.n_filters

@@ -135,3 +135,93 @@ def sample_queries(fd: FieldData, n_queries: int, n_terms: int, seed: int) -> np
         sel = np.sort(rng.choice(b - a, n_terms, replace=False))
         out[i] = fd.doc_tok[a + sel]
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Bulk graph builder for bench-scale vector sets (10 M x 768 cannot be inserted point by point on the CPU within a
+# bench run: hnswlib-style construction is hours at that size). This is HARNESS code for the write path, which is out
+# of scope: it produces an HNSW-SHAPED graph (same level distribution, 2M links at level 0, M above,
+# entry point at the top level) by local exact kNN inside two independent random-projection partitions. The CPU oracle
+# and the CUDA path traverse the SAME exported graph, so parity and the CPU/GPU ratio are unaffected by how it was
+# built; recall against brute force is reported next to every number that uses it.
+def _local_knn_links(vec: torch.Tensor, ids: torch.Tensor, m: int, gen: torch.Generator, chunk: int = 4096,
+                     batch_chunks: int = 32) -> torch.Tensor:
+    """For the node subset `ids`, m nearest (inner product) neighbours inside chunks of a random-projection order.
+    Returns [len(ids), m] global ids (int64)."""
+    dev = vec.device
+    n = ids.numel()
+    d = vec.shape[1]
+    out = torch.empty(n, m, dtype=torch.int64, device=dev)
+    if n <= m:
+        # tiny level: everybody links to everybody else (pad with self-excluded wraparound)
+        for j in range(m):
+            out[:, j] = ids[(torch.arange(n, device=dev) + 1 + j % max(n - 1, 1)) % n]
+        return out
+    proj = torch.randn(d, generator=gen, device=dev, dtype=torch.float32)
+    order = torch.argsort(vec[ids] @ proj) if n < (1 << 22) else None
+    if order is None:
+        p = torch.empty(n, device=dev, dtype=torch.float32)
+        step = 1 << 20
+        for s in range(0, n, step):
+            p[s:s + step] = vec[ids[s:s + step]] @ proj
+        order = torch.argsort(p)
+        del p
+    c = min(chunk, n)
+    n_chunks = (n + c - 1) // c
+    starts = torch.arange(n_chunks, device=dev) * c
+    starts[-1] = n - c                                   # last chunk overlaps its predecessor
+    ar = torch.arange(c, device=dev)
+    for b0 in range(0, n_chunks, batch_chunks):
+        st = starts[b0:b0 + batch_chunks]
+        loc = order[(st[:, None] + ar[None, :])]          # [B, c] positions in ids
+        gid = ids[loc]                                    # [B, c] global ids
+        x = vec[gid].to(torch.bfloat16)                   # [B, c, d]
+        sims = torch.bmm(x, x.transpose(1, 2)).float()
+        sims.diagonal(dim1=1, dim2=2).fill_(float("-inf"))
+        nb = torch.topk(sims, m, dim=2).indices           # [B, c, m] local
+        out[loc.reshape(-1)] = torch.gather(gid[:, None, :].expand(-1, c, -1), 2, nb).reshape(-1, m)
+        del x, sims, nb
+    return out
+
+
+def build_graph_bulk(vec: torch.Tensor, M: int = 16, seed: int = 100, max_level_cap: int = 6):
+    """Returns (levels u8 [n], links0 i32 [n*(2M+1)], upper_off i64 [n+1], links_up i32 [R*(M+1)], max_level, entry)."""
+    dev = vec.device
+    n = vec.shape[0]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    u = torch.rand(n, generator=gen, device=dev, dtype=torch.float64).clamp_(min=1e-300)
+    levels = torch.floor(-torch.log(u) * (1.0 / np.log(M))).clamp_(max=max_level_cap).to(torch.int64)
+    all_ids = torch.arange(n, device=dev)
+
+    def merged_rows(ids, m_total):
+        a = _local_knn_links(vec, ids, m_total // 2, gen)
+        b = _local_knn_links(vec, ids, m_total - m_total // 2, gen)
+        rows = torch.cat([a, b], dim=1)
+        rows, _ = torch.sort(rows, dim=1)
+        dup = torch.zeros_like(rows, dtype=torch.bool)
+        dup[:, 1:] = rows[:, 1:] == rows[:, :-1]
+        rows = torch.where(dup, torch.full_like(rows, n), rows)
+        rows, _ = torch.sort(rows, dim=1)
+        cnt = (rows < n).sum(1)
+        rows = torch.where(rows < n, rows, torch.zeros_like(rows))
+        return rows, cnt
+
+    rows, cnt = merged_rows(all_ids, 2 * M)
+    links0 = torch.zeros(n, 2 * M + 1, dtype=torch.int32, device=dev)
+    links0[:, 0] = cnt.to(torch.int32)
+    links0[:, 1:] = rows.to(torch.int32)
+    del rows, cnt
+    max_level = int(levels.max())
+    upper_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    upper_off[1:] = torch.cumsum(levels, 0)
+    R = int(upper_off[-1])
+    links_up = torch.zeros(max(R, 1), M + 1, dtype=torch.int32, device=dev)
+    for l in range(1, max_level + 1):
+        ids = torch.nonzero(levels >= l).flatten()
+        rows, cnt = merged_rows(ids, M)
+        rec = upper_off[ids] + (l - 1)
+        links_up[rec, 0] = cnt.to(torch.int32)
+        links_up[rec, 1:] = rows.to(torch.int32)
+    entry = int(torch.nonzero(levels == max_level).flatten()[0])
+    return (levels.to(torch.uint8), links0.reshape(-1), upper_off, links_up.reshape(-1), max_level, entry)
