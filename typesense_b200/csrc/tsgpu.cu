@@ -427,7 +427,9 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     const unsigned grid = std::max(1u, std::min(max_blocks, (nq + 3) / 4));
     const size_t slots = (size_t) grid * 4;
     const size_t vis_words = ((size_t) g.n_nodes + 31) / 32;
-    const uint32_t log_cap = 16384, cand_cap = 32768;
+    // per-warp scratch: with a selective filter hnswlib pushes every visited node into the candidate set until `ef`
+    // allowed results exist, so the heap must hold ~visited-count entries; 256 Ki keys (2 MiB) per warp slot
+    const uint32_t log_cap = 65536, cand_cap = std::min<uint32_t>(262144, std::max<uint32_t>(1024, g.n_nodes + 1));
     if(slots * vis_words > idx->knn_slots * idx->knn_vis_words || vis_words != idx->knn_vis_words) {
         idx->d_knn_vis.release();
         CU(idx->d_knn_vis.reserve(slots * vis_words * 4));
@@ -493,7 +495,7 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     CU(cudaMemcpyAsync(hst, base + o_misc + 8, 32, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     idx->stats.knn_dist += hst[0]; idx->stats.knn_expanded += hst[1];
-    if((int) hst[3]) return fail(TSGPU_ERR_CAPACITY, "HNSW candidate heap overflow (more than 32768 live candidates in one query)");
+    if((int) hst[3]) return fail(TSGPU_ERR_CAPACITY, "HNSW candidate heap overflow (more than 262144 live candidates in one query)");
     return TSGPU_OK;
 }
 

@@ -137,77 +137,112 @@ def sample_queries(fd: FieldData, n_queries: int, n_terms: int, seed: int) -> np
     return out
 
 
+def make_vectors_clustered(n: int, dim: int, n_clusters: int, seed: int, device="cpu", spread: float = 0.7,
+                            latent: int = 8, centers_seed: Optional[int] = None):
+    """Synthetic embeddings with the structure real ones have: a mixture of n_clusters bumps on the unit sphere whose
+    members vary along a `latent`-dimensional subspace (low intrinsic dimension), scattered over seq_ids at random.
+    (i.i.d. Gaussian vectors in 768-d have no neighbourhood structure at all: no ANN index, hnswlib included, retrieves
+    meaningful neighbours from them, so recall would say nothing.) x = normalize(center_c + spread * B z), z ~ N(0, I).
+    Returns (vectors, cluster id). Queries are drawn with the same centers_seed and a different seed."""
+    gc = torch.Generator(device=device)
+    gc.manual_seed(seed if centers_seed is None else centers_seed)
+    centers = torch.randn(n_clusters, dim, generator=gc, device=device, dtype=torch.float32)
+    centers = centers / centers.norm(dim=1, keepdim=True)
+    basis = torch.linalg.qr(torch.randn(dim, latent, generator=gc, device=device, dtype=torch.float32))[0]   # [dim, latent]
+    g = torch.Generator(device=device)
+    g.manual_seed(seed + 7919)
+    cid = torch.randint(0, n_clusters, (n,), generator=g, device=device)
+    v = torch.empty(n, dim, device=device, dtype=torch.float32)
+    step = 1 << 20
+    for s0 in range(0, n, step):
+        e = min(n, s0 + step)
+        z = torch.randn(e - s0, latent, generator=g, device=device, dtype=torch.float32)
+        x = centers[cid[s0:e]] + spread * (z @ basis.T) / latent ** 0.5
+        v[s0:e] = x / x.norm(dim=1, keepdim=True)
+    return v, cid
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # Bulk graph builder for bench-scale vector sets (10 M x 768 cannot be inserted point by point on the CPU within a
 # bench run: hnswlib-style construction is hours at that size). This is HARNESS code for the write path, which is out
 # of scope (SURVEY.md §3.4): it produces an HNSW-SHAPED graph (same level distribution, 2M links at level 0, M above,
-# entry point at the top level) by local exact kNN inside two independent random-projection partitions. The CPU oracle
-# and the CUDA path traverse the SAME exported graph, so parity and the CPU/GPU ratio are unaffected by how it was
-# built; recall against brute force is reported next to every number that uses it.
-def _local_knn_links(vec: torch.Tensor, ids: torch.Tensor, m: int, gen: torch.Generator, chunk: int = 4096,
-                     batch_chunks: int = 32) -> torch.Tensor:
-    """For the node subset `ids`, m nearest (inner product) neighbours inside chunks of a random-projection order.
-    Returns [len(ids), m] global ids (int64)."""
+# entry point at the top level) from exact local kNN inside overlapping windows of a locality-preserving order (the
+# generating cluster when known, a random projection otherwise); small upper levels get an exact global kNN graph.
+# The CPU oracle and the CUDA path traverse the SAME exported graph, so parity and the CPU/GPU ratio do not depend on
+# how it was built; recall against brute force is reported next to every number that uses it.
+def _local_knn_links(vec: torch.Tensor, ids: torch.Tensor, m: int, order: torch.Tensor, chunk: int, shift: int,
+                     budget_elems: int = 1 << 29, n_random: int = 0, gen=None) -> torch.Tensor:
+    """For the node subset `ids` visited in `order` (a permutation of range(len(ids))), the m nearest (inner product)
+    neighbours inside windows of `chunk` consecutive nodes, windows offset by `shift`. Returns [len(ids), m] global ids."""
     dev = vec.device
     n = ids.numel()
-    d = vec.shape[1]
     out = torch.empty(n, m, dtype=torch.int64, device=dev)
     if n <= m:
-        # tiny level: everybody links to everybody else (pad with self-excluded wraparound)
         for j in range(m):
             out[:, j] = ids[(torch.arange(n, device=dev) + 1 + j % max(n - 1, 1)) % n]
         return out
-    proj = torch.randn(d, generator=gen, device=dev, dtype=torch.float32)
-    order = torch.argsort(vec[ids] @ proj) if n < (1 << 22) else None
-    if order is None:
-        p = torch.empty(n, device=dev, dtype=torch.float32)
-        step = 1 << 20
-        for s in range(0, n, step):
-            p[s:s + step] = vec[ids[s:s + step]] @ proj
-        order = torch.argsort(p)
-        del p
     c = min(chunk, n)
-    n_chunks = (n + c - 1) // c
-    starts = torch.arange(n_chunks, device=dev) * c
-    starts[-1] = n - c                                   # last chunk overlaps its predecessor
+    n_chunks = (n - shift + c - 1) // c + (1 if shift else 0)
+    starts = (torch.arange(n_chunks, device=dev) * c - (c - shift if shift else 0)).clamp_(min=0, max=n - c)
     ar = torch.arange(c, device=dev)
+    batch_chunks = max(1, budget_elems // (c * c))
     for b0 in range(0, n_chunks, batch_chunks):
         st = starts[b0:b0 + batch_chunks]
         loc = order[(st[:, None] + ar[None, :])]          # [B, c] positions in ids
         gid = ids[loc]                                    # [B, c] global ids
-        x = vec[gid].to(torch.bfloat16)                   # [B, c, d]
+        x = vec[gid].to(torch.bfloat16 if vec.is_cuda else torch.float32)
         sims = torch.bmm(x, x.transpose(1, 2)).float()
         sims.diagonal(dim1=1, dim2=2).fill_(float("-inf"))
         nb = torch.topk(sims, m, dim=2).indices           # [B, c, m] local
+        if n_random:                                      # small-world shortcuts: random members of the window
+            rnd = torch.randint(0, c, (nb.shape[0], c, n_random), generator=gen, device=dev)
+            nb[:, :, m - n_random:] = rnd
         out[loc.reshape(-1)] = torch.gather(gid[:, None, :].expand(-1, c, -1), 2, nb).reshape(-1, m)
         del x, sims, nb
     return out
 
 
-def build_graph_bulk(vec: torch.Tensor, M: int = 16, seed: int = 100, max_level_cap: int = 6):
-    """Returns (levels u8 [n], links0 i32 [n*(2M+1)], upper_off i64 [n+1], links_up i32 [R*(M+1)], max_level, entry)."""
+def build_graph_bulk(vec: torch.Tensor, M: int = 16, seed: int = 100, max_level_cap: int = 6,
+                     order_key: Optional[torch.Tensor] = None, n_random_links: int = 0):
+    """Returns (levels u8 [n], links0 i32 [n*(2M+1)], upper_off i64 [n+1], links_up i32 [R*(M+1)], max_level, entry).
+    order_key: per-node locality key (e.g. generating cluster id); None -> a random projection."""
     dev = vec.device
-    n = vec.shape[0]
+    n, d = vec.shape
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
     u = torch.rand(n, generator=gen, device=dev, dtype=torch.float64).clamp_(min=1e-300)
     levels = torch.floor(-torch.log(u) * (1.0 / np.log(M))).clamp_(max=max_level_cap).to(torch.int64)
+    if order_key is None:
+        proj = torch.randn(d, generator=gen, device=dev, dtype=torch.float32)
+        key = torch.empty(n, device=dev, dtype=torch.float64)
+        step = 1 << 20
+        for s0 in range(0, n, step):
+            key[s0:s0 + step] = (vec[s0:s0 + step] @ proj).double()
+    else:
+        key = order_key.double() + torch.rand(n, generator=gen, device=dev, dtype=torch.float64) * 0.999
     all_ids = torch.arange(n, device=dev)
 
-    def merged_rows(ids, m_total):
-        a = _local_knn_links(vec, ids, m_total // 2, gen)
-        b = _local_knn_links(vec, ids, m_total - m_total // 2, gen)
-        rows = torch.cat([a, b], dim=1)
+    def merged_rows(ids, m_total, chunk):
+        order = torch.argsort(key[ids])
+        nn = ids.numel()
+        if nn <= 65536:                                   # small level: exact global kNN graph
+            rows = _local_knn_links(vec, ids, m_total, order, nn, 0)
+        else:
+            a = _local_knn_links(vec, ids, m_total - m_total // 2, order, chunk, 0)
+            b = _local_knn_links(vec, ids, m_total // 2 + m_total // 4, order, chunk, chunk // 2,
+                                 n_random=n_random_links if nn == n else 0, gen=gen)
+            rows = torch.cat([a, b], dim=1)
         rows, _ = torch.sort(rows, dim=1)
         dup = torch.zeros_like(rows, dtype=torch.bool)
         dup[:, 1:] = rows[:, 1:] == rows[:, :-1]
         rows = torch.where(dup, torch.full_like(rows, n), rows)
         rows, _ = torch.sort(rows, dim=1)
+        rows = rows[:, :m_total]
         cnt = (rows < n).sum(1)
         rows = torch.where(rows < n, rows, torch.zeros_like(rows))
         return rows, cnt
 
-    rows, cnt = merged_rows(all_ids, 2 * M)
+    rows, cnt = merged_rows(all_ids, 2 * M, 4096)
     links0 = torch.zeros(n, 2 * M + 1, dtype=torch.int32, device=dev)
     links0[:, 0] = cnt.to(torch.int32)
     links0[:, 1:] = rows.to(torch.int32)
@@ -219,7 +254,7 @@ def build_graph_bulk(vec: torch.Tensor, M: int = 16, seed: int = 100, max_level_
     links_up = torch.zeros(max(R, 1), M + 1, dtype=torch.int32, device=dev)
     for l in range(1, max_level + 1):
         ids = torch.nonzero(levels >= l).flatten()
-        rows, cnt = merged_rows(ids, M)
+        rows, cnt = merged_rows(ids, M, 8192)
         rec = upper_off[ids] + (l - 1)
         links_up[rec, 0] = cnt.to(torch.int32)
         links_up[rec, 1:] = rows.to(torch.int32)
