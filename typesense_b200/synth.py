@@ -138,17 +138,23 @@ def sample_queries(fd: FieldData, n_queries: int, n_terms: int, seed: int) -> np
 
 
 def make_vectors_clustered(n: int, dim: int, n_clusters: int, seed: int, device="cpu", spread: float = 0.7,
-                            latent: int = 8, centers_seed: Optional[int] = None):
-    """Synthetic embeddings with the structure real ones have: a mixture of n_clusters bumps on the unit sphere whose
-    members vary along a `latent`-dimensional subspace (low intrinsic dimension), scattered over seq_ids at random.
-    (i.i.d. Gaussian vectors in 768-d have no neighbourhood structure at all: no ANN index, hnswlib included, retrieves
-    meaningful neighbours from them, so recall would say nothing.) x = normalize(center_c + spread * B z), z ~ N(0, I).
-    Returns (vectors, cluster id). Queries are drawn with the same centers_seed and a different seed."""
+                            latent: int = 8, centers_seed: Optional[int] = None, center_latent: int = 16):
+    """Synthetic embeddings with the structure real ones have — low intrinsic dimension at every scale: cluster centres
+    live in a `center_latent`-dimensional subspace, members vary along a further `latent`-dimensional subspace, and
+    members are scattered over seq_ids at random. (i.i.d. Gaussian vectors in 768-d have no neighbourhood structure:
+    no ANN index, hnswlib included, retrieves meaningful neighbours from them, so recall would say nothing.)
+    x = normalize(A u_c + spread * B z / sqrt(latent)), u_c ~ N(0, I)/sqrt(center_latent), z ~ N(0, I).
+    Returns (vectors, cluster key) where the key orders clusters along the first latent axis (a locality hint for the
+    bulk graph builder). Queries are drawn with the same centers_seed and a different seed."""
     gc = torch.Generator(device=device)
     gc.manual_seed(seed if centers_seed is None else centers_seed)
-    centers = torch.randn(n_clusters, dim, generator=gc, device=device, dtype=torch.float32)
-    centers = centers / centers.norm(dim=1, keepdim=True)
-    basis = torch.linalg.qr(torch.randn(dim, latent, generator=gc, device=device, dtype=torch.float32))[0]   # [dim, latent]
+    basis = torch.linalg.qr(torch.randn(dim, center_latent + latent, generator=gc, device=device, dtype=torch.float32))[0]
+    A, B = basis[:, :center_latent], basis[:, center_latent:]
+    u = torch.randn(n_clusters, center_latent, generator=gc, device=device, dtype=torch.float32)
+    u = u / u.norm(dim=1, keepdim=True)
+    centers = u @ A.T                                                   # unit vectors
+    rank_of = torch.empty(n_clusters, dtype=torch.int64, device=device)
+    rank_of[torch.argsort(u[:, 0])] = torch.arange(n_clusters, device=device)
     g = torch.Generator(device=device)
     g.manual_seed(seed + 7919)
     cid = torch.randint(0, n_clusters, (n,), generator=g, device=device)
@@ -157,9 +163,9 @@ def make_vectors_clustered(n: int, dim: int, n_clusters: int, seed: int, device=
     for s0 in range(0, n, step):
         e = min(n, s0 + step)
         z = torch.randn(e - s0, latent, generator=g, device=device, dtype=torch.float32)
-        x = centers[cid[s0:e]] + spread * (z @ basis.T) / latent ** 0.5
+        x = centers[cid[s0:e]] + spread * (z @ B.T) / latent ** 0.5
         v[s0:e] = x / x.norm(dim=1, keepdim=True)
-    return v, cid
+    return v, rank_of[cid]
 
 
 # ----------------------------------------------------------------------------------------------------------------
