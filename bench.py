@@ -127,11 +127,11 @@ def build_workload(args, device, rank, need_host_copy):
     if args.workload != "keyword10m":
         t1 = time.time()
         w.n_clusters = max(8, args.docs // 2000)
-        vec, cid = synth.make_vectors_clustered(args.docs, args.dim, w.n_clusters, seed=1234, device=device)
+        vec, cid = synth.make_vectors_clustered(args.docs, args.dim, w.n_clusters, seed=1234, device=device, spread=0.35)
         lv, l0, uo, lu, ml, ep = synth.build_graph_bulk(vec, 16, 100, order_key=cid)
         # brute-force ground truth for the recall report (outside every timed region)
         R = args.recall_queries
-        w.recall_q = synth.make_vectors_clustered(R, args.dim, w.n_clusters, seed=555, device=device, centers_seed=1234)[0] if R else None
+        w.recall_q = synth.make_vectors_clustered(R, args.dim, w.n_clusters, seed=555, device=device, centers_seed=1234, spread=0.35)[0] if R else None
         w.recall_exact = None
         if R:
             ex = torch.empty(R, 100, dtype=torch.int64, device=device)
@@ -190,7 +190,7 @@ def make_batches(args, w, n_batches, rank):
                 q.filter = int(rng.integers(0, 10))
             qs.append(q)
         b = S.KwBatch(qs, [0], w.filters)
-        qv = (synth.make_vectors_clustered(args.batch, args.dim, w.n_clusters, seed=4321 + 97 * rank + bi, centers_seed=1234)[0].numpy()
+        qv = (synth.make_vectors_clustered(args.batch, args.dim, w.n_clusters, seed=4321 + 97 * rank + bi, centers_seed=1234, spread=0.35)[0].numpy()
               if args.workload != "keyword10m" else None)
         out.append((b, qv))
     return out

@@ -28,7 +28,8 @@ size_t hs_keyword_combo(const tsgpu_field* fields, uint32_t n_index_fields, cons
     for(uint32_t i = 0; i < n_index_fields; i++) {
         tspack::pack_field(fields[i].n_lists, fields[i].list_off, fields[i].ids, hf[i].pk);
         DevField& d = hf[i].dev;
-        d.n_lists = fields[i].n_lists; d.is_array = fields[i].is_array; d.list_off = fields[i].list_off;
+        d.n_lists = fields[i].n_lists; d.list_off = fields[i].list_off;
+        d.is_array = fields[i].is_array ? kFieldIsArray : (tspack::plain_wellformed(fields[i].pos_off, fields[i].positions, fields[i].list_off[fields[i].n_lists]) ? kFieldPlainOk : 0);
         d.list_blk_off = hf[i].pk.list_blk_off.data(); d.blk_first = hf[i].pk.blk_first.data();
         d.blk_info = hf[i].pk.blk_info.data(); d.packed = hf[i].pk.packed.data();
         d.pos_off = fields[i].pos_off; d.positions = fields[i].positions;
@@ -118,7 +119,7 @@ size_t hs_keyword_combo(const tsgpu_field* fields, uint32_t n_index_fields, cons
                 }
                 if(nt == 0) continue;
                 bool single_exact = (P.total_cost == 0 && P.num_query_tokens == 1);
-                int64_t fs = score_field(P, G.is_array != 0, single_exact, toks, nt);
+                int64_t fs = (G.is_array & kFieldPlainOk) ? score_field_plain(P, single_exact, toks, nt) : score_field(P, (G.is_array & kFieldIsArray) != 0, single_exact, toks, nt);
                 field_agg_add(agg, P.match_type, fs, b->q_field_weight[(size_t) q * F + f]);
             }
             uint64_t s = field_agg_finish(agg, P, query_len);

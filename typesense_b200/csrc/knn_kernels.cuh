@@ -30,6 +30,7 @@ namespace tsv {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr int kKnnThreads = 128;            // 4 warps = 4 queries per CTA
+constexpr uint32_t kCandSmem = 512;         // candidate-heap entries kept in shared memory per warp (rest spills to HBM)
 
 struct HnswDev {
     uint32_t n_nodes, dim, M, max_level, entry_point, metric;
@@ -199,8 +200,11 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
     const uint32_t dim = g.dim;
     const uint32_t dim_pad = (dim + 3) & ~3u;
     // shared: per warp [ef+1] u64 result heap, then (generic path) the query vector
-    unsigned long long* res = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t) warp * (ef + 1);
-    float* qs = reinterpret_cast<float*>(reinterpret_cast<unsigned long long*>(smem_raw) + (size_t) (kKnnThreads / 32) * (ef + 1)) + (size_t) warp * dim_pad;
+    // shared per warp: [ef+1] u64 result heap + [kCandSmem] u64 first tier of the candidate heap; then (generic path) q
+    const size_t per_warp = (size_t) (ef + 1) + kCandSmem;
+    unsigned long long* res = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t) warp * per_warp;
+    unsigned long long* cand_s = res + (ef + 1);
+    float* qs = reinterpret_cast<float*>(reinterpret_cast<unsigned long long*>(smem_raw) + (size_t) (kKnnThreads / 32) * per_warp) + (size_t) warp * dim_pad;
     uint32_t* vis = P.visited + (size_t) slot * P.vis_words;
     uint32_t* vlog = P.vis_log + (size_t) slot * P.log_cap;
     unsigned long long* cand = P.cand + (size_t) slot * P.cand_cap;
@@ -252,7 +256,7 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
         }
 
         // ---- best-first search of the base layer (searchBaseLayerST, non-"bare bone" branch)
-        uint32_t n_res = 0, n_cand = 0, n_log = 0;
+        uint32_t n_res = 0, n_cand = 0, n_cs = 0, n_cg = 0, n_log = 0;     // n_cand = n_cs (shared tier) + n_cg (HBM tier)
         bool log_overflow = false;
         float lowerBound;
         {
@@ -261,27 +265,32 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
                 const float d = curdist;      // same value hnswlib recomputes for the entry point
                 n_dist_acc++;
                 lowerBound = d;
-                if(lane == 0) { heap_push_max(res, n_res, res_key(d, cur)); heap_push_min(cand, n_cand, cand_key(d, cur)); }
+                if(lane == 0) { heap_push_max(res, n_res, res_key(d, cur)); heap_push_min(cand_s, n_cs, cand_key(d, cur)); }
             } else {
                 lowerBound = FLT_MAX;
-                if(lane == 0) heap_push_min(cand, n_cand, cand_key(FLT_MAX, cur));
+                if(lane == 0) heap_push_min(cand_s, n_cs, cand_key(FLT_MAX, cur));
             }
             if(lane == 0) { atomicOr(vis + (cur >> 5), 1u << (cur & 31)); vlog[0] = cur; }
             n_log = 1;
             n_res = __shfl_sync(0xffffffffu, n_res, 0);
-            n_cand = __shfl_sync(0xffffffffu, n_cand, 0);
+            n_cand = 1;
             __syncwarp();
         }
         for(;;) {
             if(n_cand == 0) break;
+            // global minimum = the smaller of the two tiers' tops
             unsigned long long top = 0;
-            if(lane == 0) top = cand[0];
+            int from_g = 0;
+            if(lane == 0) {
+                top = n_cs ? cand_s[0] : ~0ull;
+                if(n_cg) { const unsigned long long tg = cand[0]; if(tg < top) { top = tg; from_g = 1; } }
+            }
             top = __shfl_sync(0xffffffffu, top, 0);
             const float cdist = unord_f32((uint32_t) (top >> 32));
             if(cdist > lowerBound && n_res == ef) break;
             const uint32_t cnode = ~(uint32_t) top;
-            if(lane == 0) heap_pop_min(cand, n_cand);
-            n_cand = __shfl_sync(0xffffffffu, n_cand, 0);
+            if(lane == 0) { if(from_g) heap_pop_min(cand, n_cg); else heap_pop_min(cand_s, n_cs); }
+            n_cand--;
             n_exp_acc++;
 
             const uint32_t* rec = g.links0 + (size_t) cnode * L0;
@@ -326,7 +335,9 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
                             const uint32_t c = t ? c1 : c0;
                             const bool ok = t ? ok1 : ok0;
                             if(n_res < ef || lowerBound > d) {
-                                if(n_cand < P.cand_cap) heap_push_min(cand, n_cand, cand_key(d, c)); else *P.error = 1;
+                                if(n_cs < kCandSmem) heap_push_min(cand_s, n_cs, cand_key(d, c));
+                                else if(n_cg < P.cand_cap) heap_push_min(cand, n_cg, cand_key(d, c));
+                                else *P.error = 1;
                                 if(ok) heap_push_max(res, n_res, res_key(d, c));
                                 while(n_res > ef) heap_pop_max(res, n_res);
                                 if(n_res) lowerBound = unord_f32((uint32_t) (res[0] >> 32));
@@ -335,7 +346,7 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
                     }
                     lowerBound = __shfl_sync(0xffffffffu, lowerBound, 0);
                     n_res = __shfl_sync(0xffffffffu, n_res, 0);
-                    n_cand = __shfl_sync(0xffffffffu, n_cand, 0);
+                    n_cand = __shfl_sync(0xffffffffu, n_cs + n_cg, 0);
                 }
             }
             __syncwarp();

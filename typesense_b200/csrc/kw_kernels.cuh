@@ -83,6 +83,7 @@ struct KwParams {
     const UDesc* ud;
     int64_t* pool_s0; int64_t* pool_s1; int64_t* pool_s2;
     uint32_t* pool_key;
+    uint16_t* pool_cmb;                // combination index local to the query
     uint32_t* unit_cnt;                // [n_units]
     uint32_t* combo_matches;           // [n_combos]
     unsigned long long* stats;         // [0] driver ids, [1] probed block ids, [2] matches
@@ -186,6 +187,8 @@ __device__ __forceinline__ uint32_t cta_rank(bool flag, uint32_t* s_warp, uint32
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kQCap = 2 * kThreads;        // pending-match queue slots per CTA
+
 __global__ void __launch_bounds__(kThreads)
 kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ KwParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -197,9 +200,9 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
     tb.key = reinterpret_cast<uint32_t*>(tb.s2 + N2);
     tb.cmb = nullptr;
     tb.vd = nullptr;
-    uint32_t* hp = tb.key + N2;                       // [NL][128] list-local posting index of candidate in list j
-    uint32_t* s_cand = hp + NL * kThreads;            // [128]
-    uint32_t* s_mlist = s_cand + kThreads;            // [128]
+    uint32_t* hp = tb.key + N2;                       // [NL][128] staging: list-local posting index of candidate in list j
+    uint32_t* q_id = hp + NL * kThreads;              // [kQCap] queue of matched docs waiting to be scored
+    uint32_t* q_hp = q_id + kQCap;                    // [NL][kQCap]
 
     __shared__ CDesc cd;
     __shared__ QDesc qd;
@@ -208,7 +211,7 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
     __shared__ uint32_t s_warp[8];
     __shared__ int64_t thr[3];
     __shared__ uint32_t thr_key;
-    __shared__ uint32_t s_n, s_have_thr, s_matches, s_driver_ids, s_probe_blocks;
+    __shared__ uint32_t s_n, s_have_thr, s_matches, s_driver_ids, s_probe_blocks, s_qn;
 
     const uint32_t tid = threadIdx.x;
     const UDesc ud = P.ud[blockIdx.x];
@@ -235,7 +238,7 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
             l_gal[tid] = b0;
         } else { l_blk0[tid] = 0; l_blk1[tid] = 0; l_base[tid] = 0; l_df[tid] = 0; l_gal[tid] = 0; }
     }
-    if(tid == 0) { s_n = 0; s_have_thr = 0; s_matches = 0; s_driver_ids = 0; s_probe_blocks = 0; }
+    if(tid == 0) { s_n = 0; s_have_thr = 0; s_matches = 0; s_driver_ids = 0; s_probe_blocks = 0; s_qn = 0; }
     __syncthreads();
 
     ScoreParams SP;
@@ -256,7 +259,76 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
     }
     const uint32_t K = qd.topk;
     const uint32_t drv = cd.driver_row;
+    const uint16_t cmb_local = (uint16_t) (ud.combo - qd.combo_begin);
     uint32_t prev_fd = 0xFFFFFFFFu;
+
+    // Scores queue entries [base, base+cnt) (cnt <= 128) with all threads busy, appends the survivors to the top-K
+    // buffer and compacts that buffer when the next batch might not fit.
+    auto score_batch = [&](uint32_t base, uint32_t cnt) {
+        bool keep = false;
+        int64_t sc[3] = {0, 0, 0};
+        uint32_t mid = 0;
+        if(tid < cnt) {
+            const uint32_t src = base + tid;
+            mid = q_id[src];
+            FieldAgg agg; field_agg_init(agg);
+            uint32_t query_len = 0;
+            for(uint32_t r = 0; r < cd.n_rows; r++) {
+                bool any = false;
+                for(uint32_t f = 0; f < F; f++) any |= (q_hp[(r * F + f) * kQCap + src] != kNone);
+                query_len += any;
+            }
+            for(uint32_t f = 0; f < F; f++) {
+                const DevField& g = ix.fields[P.field_ids[f]];
+                RawTok toks[kMaxTokens];
+                int nt = 0;
+                for(uint32_t r = 0; r < cd.n_rows; r++) {
+                    const uint32_t j = r * F + f;
+                    const uint32_t h = q_hp[j * kQCap + src];
+                    if(h == kNone) continue;
+                    const unsigned long long p = l_base[j] + h;
+                    const unsigned long long o0 = __ldg(reinterpret_cast<const unsigned long long*>(g.pos_off) + p);
+                    const unsigned long long o1 = __ldg(reinterpret_cast<const unsigned long long*>(g.pos_off) + p + 1);
+                    toks[nt].p = g.positions + o0;
+                    toks[nt].n = (uint32_t) (o1 - o0);
+                    nt++;
+                }
+                if(nt == 0) continue;
+                const bool single_exact = (SP.total_cost == 0 && SP.num_query_tokens == 1);
+                const int64_t fs = (g.is_array & kFieldPlainOk) ? score_field_plain(SP, single_exact, toks, nt)
+                                                                : score_field(SP, (g.is_array & kFieldIsArray) != 0, single_exact, toks, nt);
+                field_agg_add(agg, SP.match_type, fs, (int64_t) qd.field_weight[f]);
+            }
+            const uint64_t aggs = field_agg_finish(agg, SP, query_len);
+            const int msi = compute_sort_scores(SS, mid, (int64_t) aggs, 0.0f, sc);
+            if(msi >= 0) sc[msi] = (int64_t) aggs;            // src/index.cpp:5541-5544 (undoes the ASC negation)
+            if(qd.found_bitmap) atomicOr(qd.found_bitmap + (mid >> 5), 1u << (mid & 31));
+            keep = true;
+            if(s_have_thr) keep = kv_greater(sc[0], sc[1], sc[2], mid, thr[0], thr[1], thr[2], thr_key);
+        }
+        uint32_t a_total;
+        const uint32_t arank = cta_rank(keep, s_warp, &a_total);
+        const uint32_t n0 = s_n;
+        if(keep) {
+            const uint32_t slot = n0 + arank;
+            tb.s0[slot] = sc[0]; tb.s1[slot] = sc[1]; tb.s2[slot] = sc[2]; tb.key[slot] = mid;
+        }
+        __syncthreads();
+        if(tid == 0) s_n = n0 + a_total;
+        __syncthreads();
+        if(s_n + kThreads > N2) {                 // the next batch might not fit: sort, keep the best K
+            const uint32_t n = s_n;
+            tb_fill_invalid(tb, n, N2);
+            __syncthreads();
+            tb_sort<false>(tb, N2);
+            if(tid == 0) {
+                const uint32_t nn = n < K ? n : K;
+                s_n = nn;
+                if(nn == K) { s_have_thr = 1; thr[0] = tb.s0[K - 1]; thr[1] = tb.s1[K - 1]; thr[2] = tb.s2[K - 1]; thr_key = tb.key[K - 1]; }
+            }
+            __syncthreads();
+        }
+    };
 
     for(uint32_t tile = ud.tile_begin; tile < ud.tile_end; tile++) {
         // ---- which driver field / block
@@ -283,28 +355,29 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
         if(alive && qd.filter_bitmap) alive = (__ldg(qd.filter_bitmap + (id >> 5)) >> (id & 31)) & 1;
         if(alive && qd.n_excl) alive = !excluded(qd.excl, qd.n_excl, id);
         if(qd.filter_empty) alive = false;
-        s_cand[tid] = id;
         const int any_alive = __syncthreads_or(alive);
         if(tid == 0) s_driver_ids += cnt;
         if(!any_alive) continue;
 
         // ---- narrow every probed list to the blocks covering [first, tmax]
-        if(tid < 2 * n_lists) {
-            const uint32_t j = tid >> 1;
-            if(cd.lists[j] != kNone && j != jd) {
-                const uint32_t* bf = ix.fields[P.field_ids[j % F]].blk_first;
-                const uint32_t target = (tid & 1) ? tmax : first;
-                const uint32_t r = gallop_block(bf, l_gal[j], l_blk1[j], target);
-                if(tid & 1) l_hi[j] = r; else l_lo[j] = r;
+        if(n_lists > 1) {
+            if(tid < 2 * n_lists) {
+                const uint32_t j = tid >> 1;
+                if(cd.lists[j] != kNone && j != jd) {
+                    const uint32_t* bf = ix.fields[P.field_ids[j % F]].blk_first;
+                    const uint32_t target = (tid & 1) ? tmax : first;
+                    const uint32_t r = gallop_block(bf, l_gal[j], l_blk1[j], target);
+                    if(tid & 1) l_hi[j] = r; else l_lo[j] = r;
+                }
             }
+            __syncthreads();
+            if(tid < n_lists && cd.lists[tid] != kNone && tid != jd) {
+                // lo == kNone: tile starts before the list's first remaining block -> clamp; hi == kNone: nothing to hit
+                if(l_lo[tid] == kNone) l_lo[tid] = l_gal[tid]; else l_gal[tid] = l_lo[tid];
+                if(l_hi[tid] != kNone) atomicAdd(&s_probe_blocks, l_hi[tid] - l_lo[tid] + 1);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        if(tid < n_lists && cd.lists[tid] != kNone && tid != jd) {
-            // lo == kNone: tile starts before the list's first remaining block -> clamp; hi == kNone: nothing to hit
-            if(l_lo[tid] == kNone) l_lo[tid] = l_gal[tid]; else l_gal[tid] = l_lo[tid];
-            if(l_hi[tid] != kNone) atomicAdd(&s_probe_blocks, l_hi[tid] - l_lo[tid] + 1);
-        }
-        __syncthreads();
 
         // ---- probe (K1): rows in probe order, all field slots of a row
         for(uint32_t oi = 0; oi < cd.n_rows; oi++) {
@@ -332,81 +405,33 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
             if(((cd.req_mask >> r) & 1) && !any) alive = false;
         }
 
-        // ---- compact matches
+        // ---- enqueue matches (compaction): scoring happens 128 docs at a time so no lane idles
         uint32_t m_total;
         const uint32_t rank = cta_rank(alive, s_warp, &m_total);
-        if(alive) s_mlist[rank] = tid;
-        __syncthreads();
-        if(m_total == 0) continue;
-
-        // ---- score (K3) + sort keys: thread k scores match k
-        bool keep = false;
-        int64_t sc[3] = {0, 0, 0};
-        uint32_t mid = 0;
-        if(tid < m_total) {
-            const uint32_t src = s_mlist[tid];
-            mid = s_cand[src];
-            FieldAgg agg; field_agg_init(agg);
-            uint32_t query_len = 0;
-            for(uint32_t r = 0; r < cd.n_rows; r++) {
-                bool any = false;
-                for(uint32_t f = 0; f < F; f++) any |= (hp[(r * F + f) * kThreads + src] != kNone);
-                query_len += any;
-            }
-            for(uint32_t f = 0; f < F; f++) {
-                const DevField& g = ix.fields[P.field_ids[f]];
-                RawTok toks[kMaxTokens];
-                int nt = 0;
-                for(uint32_t r = 0; r < cd.n_rows; r++) {
-                    const uint32_t j = r * F + f;
-                    const uint32_t h = hp[j * kThreads + src];
-                    if(h == kNone) continue;
-                    const unsigned long long p = l_base[j] + h;
-                    const unsigned long long o0 = __ldg(reinterpret_cast<const unsigned long long*>(g.pos_off) + p);
-                    const unsigned long long o1 = __ldg(reinterpret_cast<const unsigned long long*>(g.pos_off) + p + 1);
-                    toks[nt].p = g.positions + o0;
-                    toks[nt].n = (uint32_t) (o1 - o0);
-                    nt++;
-                }
-                if(nt == 0) continue;
-                const bool single_exact = (SP.total_cost == 0 && SP.num_query_tokens == 1);
-                const int64_t fs = score_field(SP, g.is_array != 0, single_exact, toks, nt);
-                field_agg_add(agg, SP.match_type, fs, (int64_t) qd.field_weight[f]);
-            }
-            const uint64_t aggs = field_agg_finish(agg, SP, query_len);
-            const int msi = compute_sort_scores(SS, mid, (int64_t) aggs, 0.0f, sc);
-            if(msi >= 0) sc[msi] = (int64_t) aggs;            // src/index.cpp:5541-5544 (undoes the ASC negation)
-            if(qd.found_bitmap) atomicOr(qd.found_bitmap + (mid >> 5), 1u << (mid & 31));
-            keep = true;
-            if(s_have_thr) keep = kv_greater(sc[0], sc[1], sc[2], mid, thr[0], thr[1], thr[2], thr_key);
-        }
-        // ---- append survivors (K4)
-        uint32_t a_total;
-        const uint32_t arank = cta_rank(keep, s_warp, &a_total);
-        const uint32_t n0 = s_n;
-        if(keep) {
-            const uint32_t slot = n0 + arank;
-            tb.s0[slot] = sc[0]; tb.s1[slot] = sc[1]; tb.s2[slot] = sc[2]; tb.key[slot] = mid;
+        const uint32_t qn0 = s_qn;
+        if(alive) {
+            const uint32_t slot = qn0 + rank;
+            q_id[slot] = id;
+            for(uint32_t j = 0; j < n_lists; j++) q_hp[j * kQCap + slot] = hp[j * kThreads + tid];
         }
         __syncthreads();
-        if(tid == 0) { s_n = n0 + a_total; s_matches += m_total; }
+        if(tid == 0) { s_qn = qn0 + m_total; s_matches += m_total; }
         __syncthreads();
-        if(s_n + kThreads > N2) {                 // the next tile might not fit: sort, keep the best K
-            const uint32_t n = s_n;
-            tb_fill_invalid(tb, n, N2);
-            __syncthreads();
-            tb_sort<false>(tb, N2);
-            if(tid == 0) {
-                const uint32_t nn = n < K ? n : K;
-                s_n = nn;
-                if(nn == K) { s_have_thr = 1; thr[0] = tb.s0[K - 1]; thr[1] = tb.s1[K - 1]; thr[2] = tb.s2[K - 1]; thr_key = tb.key[K - 1]; }
-            }
+        if(s_qn >= kThreads) {
+            const uint32_t qn = s_qn;
+            score_batch(qn - kThreads, kThreads);
+            if(tid == 0) s_qn = qn - kThreads;
             __syncthreads();
         }
     }
+    // ---- drain the queue
+    __syncthreads();
+    if(s_qn) {
+        score_batch(0, s_qn);
+        __syncthreads();
+    }
 
     // ---- unit epilogue: best <= K entries to the pool
-    __syncthreads();
     {
         const uint32_t n = s_n;
         uint32_t nn = n;
@@ -419,6 +444,7 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
         for(uint32_t i = tid; i < nn; i += kThreads) {
             const uint32_t o = ud.out_off + i;
             P.pool_s0[o] = tb.s0[i]; P.pool_s1[o] = tb.s1[i]; P.pool_s2[o] = tb.s2[i]; P.pool_key[o] = tb.key[i];
+            P.pool_cmb[o] = cmb_local;
         }
         if(tid == 0) {
             P.unit_cnt[blockIdx.x] = nn;
@@ -443,12 +469,22 @@ struct KVOut {
 };
 static_assert(sizeof(KVOut) == 56, "tsgpu_kv layout");
 
+// A merge group: reads the entries of units [in_begin, in_end) of one query, writes its best K (after de-duplication)
+// either back to the pool as unit `out_unit` (intermediate level) or as KV records (final level).
+struct MDesc {
+    uint32_t q;
+    uint32_t in_begin, in_end;
+    uint32_t out_unit;
+};
+
 struct FinalParams {
     const QDesc* qd;
-    const UDesc* ud;
-    const int64_t* pool_s0; const int64_t* pool_s1; const int64_t* pool_s2;
-    const uint32_t* pool_key;
-    const uint32_t* unit_cnt;
+    const UDesc* ud;             // unit table: level-0 units followed by merge outputs
+    const MDesc* md;             // intermediate levels only
+    int64_t* pool_s0; int64_t* pool_s1; int64_t* pool_s2;
+    uint32_t* pool_key;
+    uint16_t* pool_cmb;
+    uint32_t* unit_cnt;
     const uint32_t* combo_matches;
     KVOut* out_kv;
     uint32_t* out_count;
@@ -460,7 +496,80 @@ struct FinalParams {
 
 constexpr int kFinalThreads = 256;
 
-// One CTA per query: merge the units of all its combinations into the final Topster content.
+// shared by the intermediate and the final merge: leaves the best <= K de-duplicated entries sorted in tb[0..n)
+__device__ uint32_t merge_units(const TopBuf& tb, uint32_t N2, uint32_t K, bool multi, const UDesc* ud, const uint32_t* unit_cnt,
+                                uint32_t u_begin, uint32_t u_end, const int64_t* p0, const int64_t* p1, const int64_t* p2,
+                                const uint32_t* pk, const uint16_t* pc) {
+    const uint32_t tid = threadIdx.x;
+    auto reduce = [&](uint32_t n) -> uint32_t {
+        tb_fill_invalid(tb, n, N2);
+        __syncthreads();
+        if(multi) {
+            tb_sort<true>(tb, N2);
+            // entries of one seq_id are adjacent, best first: drop the rest (Topster keeps the greater KV per key)
+            bool dup[8];
+            int cnt = 0;
+            for(uint32_t i = tid; i < N2; i += kFinalThreads) dup[cnt++] = (i > 0 && tb.key[i] != kNone && tb.key[i] == tb.key[i - 1]);
+            __syncthreads();
+            cnt = 0;
+            for(uint32_t i = tid; i < N2; i += kFinalThreads) if(dup[cnt++]) tb.key[i] = kNone;
+            __syncthreads();
+        }
+        tb_sort<false>(tb, N2);
+        uint32_t lo = 0, hi = N2;                 // valid entries are in front
+        while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(tb.key[mid] != kNone) lo = mid + 1; else hi = mid; }
+        return lo < K ? lo : K;
+    };
+    uint32_t n = 0;
+    for(uint32_t u = u_begin; u < u_end; u++) {
+        const uint32_t cnt = unit_cnt[u];
+        if(cnt == 0) continue;
+        const uint32_t off = ud[u].out_off;
+        uint32_t done = 0;
+        while(done < cnt) {
+            if(n == N2) { n = reduce(n); __syncthreads(); }
+            const uint32_t take = min(cnt - done, N2 - n);
+            for(uint32_t i = tid; i < take; i += kFinalThreads) {
+                const uint32_t o = off + done + i;
+                tb.s0[n + i] = p0[o]; tb.s1[n + i] = p1[o]; tb.s2[n + i] = p2[o];
+                tb.key[n + i] = pk[o];
+                tb.cmb[n + i] = pc[o];
+            }
+            n += take; done += take;
+            __syncthreads();
+        }
+    }
+    n = reduce(n);
+    __syncthreads();
+    return n;
+}
+
+__global__ void __launch_bounds__(kFinalThreads)
+kw_merge_kernel(const __grid_constant__ FinalParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t KP = P.KP, N2 = 2 * KP;
+    TopBuf tb;
+    tb.s0 = reinterpret_cast<int64_t*>(smem_raw);
+    tb.s1 = tb.s0 + N2;
+    tb.s2 = tb.s1 + N2;
+    tb.key = reinterpret_cast<uint32_t*>(tb.s2 + N2);
+    tb.cmb = reinterpret_cast<uint16_t*>(tb.key + N2);
+    tb.vd = nullptr;
+    const MDesc md = P.md[blockIdx.x];
+    const QDesc& qd = P.qd[md.q];
+    const uint32_t K = qd.topk;
+    const bool multi = (qd.combo_end - qd.combo_begin) > 1;
+    const uint32_t n = merge_units(tb, N2, K, multi, P.ud, P.unit_cnt, md.in_begin, md.in_end, P.pool_s0, P.pool_s1, P.pool_s2,
+                                   P.pool_key, P.pool_cmb);
+    const uint32_t off = P.ud[md.out_unit].out_off;
+    for(uint32_t i = threadIdx.x; i < n; i += kFinalThreads) {
+        P.pool_s0[off + i] = tb.s0[i]; P.pool_s1[off + i] = tb.s1[i]; P.pool_s2[off + i] = tb.s2[i];
+        P.pool_key[off + i] = tb.key[i]; P.pool_cmb[off + i] = tb.cmb[i];
+    }
+    if(threadIdx.x == 0) P.unit_cnt[md.out_unit] = n;
+}
+
+// One CTA per query: merge the (remaining) units of all its combinations into the final Topster content.
 __global__ void __launch_bounds__(kFinalThreads)
 kw_final_kernel(const __grid_constant__ FinalParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -473,7 +582,7 @@ kw_final_kernel(const __grid_constant__ FinalParams P) {
     tb.cmb = reinterpret_cast<uint16_t*>(tb.key + N2);
     tb.vd = nullptr;
     __shared__ uint16_t s_qidx[kMaxCombosPerQuery];
-    __shared__ uint32_t s_n, s_found;
+    __shared__ uint32_t s_found;
 
     const uint32_t q = blockIdx.x, tid = threadIdx.x;
     const QDesc qd = P.qd[q];
@@ -491,54 +600,11 @@ kw_final_kernel(const __grid_constant__ FinalParams P) {
             found += m;
         }
         s_found = found;
-        s_n = 0;
         if(P.out_searched) P.out_searched[q] = qi;
     }
     __syncthreads();
-
-    auto reduce = [&](uint32_t n) -> uint32_t {
-        tb_fill_invalid(tb, n, N2);
-        __syncthreads();
-        if(multi) {
-            tb_sort<true>(tb, N2);
-            // entries of one seq_id are adjacent, best first: drop the rest (Topster keeps the greater KV per key)
-            bool dup[8];
-            int cnt = 0;
-            for(uint32_t i = tid; i < N2; i += kFinalThreads) dup[cnt++] = (i > 0 && tb.key[i] != kNone && tb.key[i] == tb.key[i - 1]);
-            __syncthreads();
-            cnt = 0;
-            for(uint32_t i = tid; i < N2; i += kFinalThreads) if(dup[cnt++]) tb.key[i] = kNone;
-            __syncthreads();
-        }
-        tb_sort<false>(tb, N2);
-        // count valid (they are in front)
-        uint32_t lo = 0, hi = N2;
-        while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(tb.key[mid] != kNone) lo = mid + 1; else hi = mid; }
-        return lo < K ? lo : K;
-    };
-
-    uint32_t n = 0;
-    for(uint32_t u = qd.unit_begin; u < qd.unit_end; u++) {
-        const uint32_t cnt = P.unit_cnt[u];
-        if(cnt == 0) continue;
-        const UDesc ud = P.ud[u];
-        uint32_t done = 0;
-        while(done < cnt) {
-            if(n == N2) { n = reduce(n); __syncthreads(); }
-            const uint32_t take = min(cnt - done, N2 - n);
-            for(uint32_t i = tid; i < take; i += kFinalThreads) {
-                const uint32_t o = ud.out_off + done + i;
-                tb.s0[n + i] = P.pool_s0[o]; tb.s1[n + i] = P.pool_s1[o]; tb.s2[n + i] = P.pool_s2[o];
-                tb.key[n + i] = P.pool_key[o];
-                tb.cmb[n + i] = (uint16_t) (ud.combo - qd.combo_begin);
-            }
-            n += take; done += take;
-            __syncthreads();
-        }
-    }
-    n = reduce(n);
-    __syncthreads();
-
+    const uint32_t n = merge_units(tb, N2, K, multi, P.ud, P.unit_cnt, qd.unit_begin, qd.unit_end, P.pool_s0, P.pool_s1, P.pool_s2,
+                                   P.pool_key, P.pool_cmb);
     int msi = -1;
     for(int i = 0; i < 3; i++) if(qd.sort_type[i] == 1) msi = i;
     const uint32_t n_out = n < P.kv_stride ? n : P.kv_stride;

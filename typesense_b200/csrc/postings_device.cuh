@@ -22,9 +22,12 @@ namespace tsdev {
 constexpr int kBlock = 128;                 // ids per block (reference: posting_t::MAX_BLOCK_ELEMENTS 256)
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
+constexpr uint32_t kFieldIsArray = 1;       // string[] (in-band array protocol in the offsets)
+constexpr uint32_t kFieldPlainOk = 2;        // plain string field whose offsets were validated as well formed at load
+
 struct DevField {
     uint32_t n_lists;
-    uint32_t is_array;
+    uint32_t is_array;          // bit flags kField*
     const uint64_t* list_off;
     const uint32_t* list_blk_off;
     const uint32_t* blk_first;

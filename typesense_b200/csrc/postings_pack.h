@@ -64,4 +64,19 @@ inline void pack_field(uint32_t n_lists, const uint64_t* list_off, const uint32_
     }
 }
 
+// True when every posting of a plain string field has well-formed raw offsets: strictly increasing non-zero
+// positions, optionally followed by one trailing 0 (src/index.cpp:1341-1348). Enables score_field_plain().
+inline bool plain_wellformed(const uint64_t* pos_off, const uint32_t* positions, uint64_t n_post) {
+    for(uint64_t p = 0; p < n_post; p++) {
+        const uint64_t a = pos_off[p], b = pos_off[p + 1];
+        if(b <= a) return false;
+        uint64_t e = b;
+        if(positions[b - 1] == 0) e = b - 1;
+        if(e <= a) return false;
+        uint32_t prev = 0;
+        for(uint64_t i = a; i < e; i++) { if(positions[i] == 0 || positions[i] <= prev) return false; prev = positions[i]; }
+    }
+    return true;
+}
+
 }  // namespace tspack

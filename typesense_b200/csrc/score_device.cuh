@@ -331,6 +331,45 @@ TS_HD_NOINLINE int64_t score_field(const ScoreParams& P, bool field_is_array, bo
     return match_score;
 }
 
+// Fast path for plain string fields whose raw offsets were validated at mirror-load time to be well formed
+// (strictly increasing positions, optionally one trailing 0): every token is exactly one group with array index 0, so
+// the segment cursors and the k-way merge of score_field() collapse to direct slices. Same result as score_field().
+TS_HD_NOINLINE int64_t score_field_plain(const ScoreParams& P, bool single_exact_query_token, const RawTok* toks, int n_toks) {
+    if(n_toks <= 1) return score_field(P, false, single_exact_query_token, toks, n_toks);
+    Seg gs[kMaxTokens];
+    for(int t = 0; t < n_toks; t++) {
+        const uint32_t n = toks[t].n;
+        const bool last = n && toks[t].p[n - 1] == 0;
+        gs[t].array_index = 0; gs[t].start = 0; gs[t].count = n - (last ? 1u : 0u); gs[t].last_token = last; gs[t].valid = 1;
+    }
+    MatchOut m = match_window(toks, gs, n_toks, P.prioritize_exact_match != 0);
+    const uint32_t synonym_score0 = (P.is_synonym_query && P.demote_synonym_match) ? 0 : 1;
+    uint64_t this_match_score = pack_match_score(m.words_present, m.distance, m.max_offset, m.exact_match,
+                                                 P.total_cost, (uint32_t) n_toks, synonym_score0);
+    uint64_t this_words_present = ((this_match_score >> 40) & 0xFF);
+    uint64_t unique_words = ((this_match_score >> 32) & 0xFF);
+    uint64_t typo_score = ((this_match_score >> 24) & 0xFF);
+    uint64_t proximity = ((this_match_score >> 16) & 0xFF);
+    uint64_t verbatim = ((this_match_score >> 12) & 0xF);
+    uint64_t offset_score = P.prioritize_token_position ? ((this_match_score >> 4) & 0xFF) : 0;
+    uint64_t syn = ((this_match_score >> 0) & 0xF);
+    if(P.is_synonym_query && P.num_query_tokens == (uint32_t) n_toks) {
+        unique_words = (uint64_t) (int64_t) P.syn_orig_num_tokens;
+        this_words_present = (uint64_t) (int64_t) P.syn_orig_num_tokens;
+    }
+    if(P.is_synonym_query && P.syn_orig_num_tokens > 0 && P.orig_num_tokens > 0) {
+        double rel_factor = (double) P.orig_num_tokens / (double) P.syn_orig_num_tokens;
+        this_words_present = scale_component(this_words_present, rel_factor);
+        unique_words = scale_component(unique_words, rel_factor);
+        uint64_t r1 = scale_component(255 - typo_score, rel_factor); typo_score = 255 - r1;
+        uint64_t r2 = scale_component(100 - proximity, rel_factor); proximity = 100 - r2;
+        uint64_t r3 = scale_component(255 - offset_score, rel_factor);
+        offset_score = P.prioritize_token_position ? 255 - r3 : 0;
+    }
+    return (int64_t) (uint64_t) (((int64_t) this_words_present << 40) | ((int64_t) unique_words << 32) | ((int64_t) typo_score << 24) |
+                                 ((int64_t) proximity << 16) | ((int64_t) verbatim << 12) | ((int64_t) offset_score << 4) | ((int64_t) syn));
+}
+
 // running reduction of compute_aggregated_score over fields
 struct FieldAgg {
     int64_t best_field_match_score, best_field_weight, sum_field_weighted_score;

@@ -122,6 +122,8 @@ tsgpu_status check_device(tsgpu_index* idx) {
     return TSGPU_OK;
 }
 
+constexpr uint32_t kMergeFan = 16;
+
 uint32_t pow2_ceil(uint32_t v) { uint32_t p = 1; while(p < v) p <<= 1; return p; }
 
 // ------------------------------------------------------------------------------------------------- keyword prep
@@ -133,6 +135,9 @@ struct KwPlan {
     std::vector<CDesc> cd;
     std::vector<UDesc> ud;
     std::vector<uint32_t> multi_q;        // queries whose found count needs the union bitmap
+    std::vector<std::vector<MDesc>> levels;   // intermediate merge levels (only queries with many units)
+    std::vector<MDesc*> d_levels;
+    uint32_t n_units_total = 0;           // level-0 units + merge outputs
     size_t pool_slots = 0;
     // device views (valid after upload)
     QDesc* d_qd = nullptr; CDesc* d_cd = nullptr; UDesc* d_ud = nullptr; uint32_t* d_multi_q = nullptr;
@@ -215,6 +220,7 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
     }
     // ---- queries
     uint32_t tpu = (uint32_t) std::min<uint64_t>(32, std::max<uint64_t>(4, total_tiles / 4096));
+    std::vector<std::pair<uint32_t, uint32_t>> q_units0;
     for(uint32_t q = 0; q < nq; q++) {
         QDesc& qd = pl.qd[q];
         const uint32_t K = b->q_topk[q];
@@ -242,15 +248,17 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
         for(uint32_t c = qd.combo_begin; c < qd.combo_end; c++) {
             pl.cd[c].q = q;
             if(combo_tiles[c]) combos_with_tiles++;
-            for(uint32_t t = 0; t < combo_tiles[c]; t += tpu) {
+            const uint32_t ctpu = tpu;
+            for(uint32_t t = 0; t < combo_tiles[c]; t += ctpu) {
                 UDesc u;
-                u.combo = c; u.tile_begin = t; u.tile_end = std::min(combo_tiles[c], t + tpu);
+                u.combo = c; u.tile_begin = t; u.tile_end = std::min(combo_tiles[c], t + ctpu);
                 u.out_off = (uint32_t) pl.pool_slots;
                 pl.pool_slots += K;
                 pl.ud.push_back(u);
             }
         }
         qd.unit_end = (uint32_t) pl.ud.size();
+        q_units0.push_back({qd.unit_begin, qd.unit_end});
         if(combos_with_tiles > 1) pl.multi_q.push_back(q);
         const int32_t fs = b->q_filter[q];
         if(fs >= 0 && (uint32_t) fs >= b->n_filters) return fail(TSGPU_ERR_INVALID, "inline filter slot out of range");
@@ -259,8 +267,35 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
             if(h >= idx->filters.size() || !idx->filters[h].live) return fail(TSGPU_ERR_INVALID, "unknown filter handle");
         }
     }
-    if(pl.pool_slots > 0xFFFFFFF0ull) return fail(TSGPU_ERR_CAPACITY, "result pool too large; split the batch");
     pl.n_units = (uint32_t) pl.ud.size();
+    // queries with more than kMergeFan units get intermediate merge levels (fan-in kMergeFan) so the per-query final
+    // merge stays short and the work of a heavy query is spread over many CTAs
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> cur = q_units0;
+        for(int level = 0; level < 6; level++) {
+            std::vector<MDesc> groups;
+            bool any = false;
+            for(uint32_t q = 0; q < nq; q++) {
+                const uint32_t a = cur[q].first, e = cur[q].second;
+                if(e - a <= kMergeFan) continue;
+                any = true;
+                const uint32_t ob = (uint32_t) pl.ud.size();
+                for(uint32_t s0 = a; s0 < e; s0 += kMergeFan) {
+                    MDesc m; m.q = q; m.in_begin = s0; m.in_end = std::min(e, s0 + kMergeFan); m.out_unit = (uint32_t) pl.ud.size();
+                    UDesc u; u.combo = 0; u.tile_begin = u.tile_end = 0; u.out_off = (uint32_t) pl.pool_slots;
+                    pl.pool_slots += pl.qd[q].topk;
+                    pl.ud.push_back(u);
+                    groups.push_back(m);
+                }
+                cur[q] = {ob, (uint32_t) pl.ud.size()};
+            }
+            if(!any) break;
+            pl.levels.push_back(std::move(groups));
+        }
+        for(uint32_t q = 0; q < nq; q++) { pl.qd[q].unit_begin = cur[q].first; pl.qd[q].unit_end = cur[q].second; }
+    }
+    if(pl.pool_slots > 0xFFFFFFF0ull) return fail(TSGPU_ERR_CAPACITY, "result pool too large; split the batch");
+    pl.n_units_total = (uint32_t) pl.ud.size();
     pl.KMAX = kmax;
     pl.KP = std::max<uint32_t>(128, pow2_ceil(kmax));
     pl.NL = nl_max;
@@ -290,7 +325,9 @@ tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& p
     const size_t o_cd = sg.reserve(pl.cd.size() * sizeof(CDesc));
     const size_t o_ud = sg.reserve(pl.ud.size() * sizeof(UDesc));
     const size_t o_mq = sg.reserve(pl.multi_q.size() * 4);
-    const size_t o_cnt = sg.reserve(((size_t) pl.n_units + pl.nc + 8) * 4 + 64);
+    std::vector<size_t> o_lv;
+    for(auto& lv: pl.levels) o_lv.push_back(sg.add(lv.data(), lv.size() * sizeof(MDesc)));
+    const size_t o_cnt = sg.reserve(((size_t) pl.n_units_total + pl.nc + 8) * 4 + 64);
     CU(idx->d_stage.reserve(sg.host.size()));
     unsigned char* dbase = idx->d_stage.as<unsigned char>();
     const uint32_t* d_excl = reinterpret_cast<const uint32_t*>(dbase + o_excl);
@@ -320,7 +357,7 @@ tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& p
     memcpy(sg.host.data() + o_cd, pl.cd.data(), pl.cd.size() * sizeof(CDesc));
     memcpy(sg.host.data() + o_ud, pl.ud.data(), pl.ud.size() * sizeof(UDesc));
     memcpy(sg.host.data() + o_mq, pl.multi_q.data(), pl.multi_q.size() * 4);
-    memset(sg.host.data() + o_cnt, 0, ((size_t) pl.n_units + pl.nc + 8) * 4 + 64);
+    memset(sg.host.data() + o_cnt, 0, ((size_t) pl.n_units_total + pl.nc + 8) * 4 + 64);
     CU(idx->h_stage.reserve(sg.host.size()));
     memcpy(idx->h_stage.p, sg.host.data(), sg.host.size());
     CU(cudaMemcpyAsync(dbase, idx->h_stage.p, sg.host.size(), cudaMemcpyHostToDevice, st));
@@ -329,6 +366,8 @@ tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& p
     pl.d_cd = reinterpret_cast<CDesc*>(dbase + o_cd);
     pl.d_ud = reinterpret_cast<UDesc*>(dbase + o_ud);
     pl.d_multi_q = reinterpret_cast<uint32_t*>(dbase + o_mq);
+    pl.d_levels.clear();
+    for(size_t o: o_lv) pl.d_levels.push_back(reinterpret_cast<MDesc*>(dbase + o));
     unsigned char* cnt = dbase + ((o_cnt + 63) & ~size_t(63));
     pl.d_stats = reinterpret_cast<unsigned long long*>(cnt);                 // 4 x u64
     pl.d_combo_matches = reinterpret_cast<uint32_t*>(cnt + 32);
@@ -344,7 +383,7 @@ tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& p
     return TSGPU_OK;
 }
 
-size_t kw_search_smem(const KwPlan& pl) { return (size_t) 2 * pl.KP * 28 + (size_t) pl.NL * kThreads * 4 + 2 * kThreads * 4; }
+size_t kw_search_smem(const KwPlan& pl) { return (size_t) 2 * pl.KP * 28 + (size_t) pl.NL * kThreads * 4 + (size_t) kQCap * 4 + (size_t) pl.NL * kQCap * 4; }
 size_t kw_final_smem(const KwPlan& pl) { return (size_t) 2 * pl.KP * 30 + 16; }
 
 struct KwDeviceOut { KVOut* kv; uint32_t* count; uint32_t* found; uint32_t* searched; uint32_t stride; };
@@ -360,16 +399,17 @@ tsgpu_status run_keyword(tsgpu_index* idx, KwPlan& pl, uint32_t kv_stride, KwDev
     out.found = out.count + nq;
     out.searched = out.found + nq;
     out.stride = kv_stride;
-    CU(idx->d_pool.reserve(pl.pool_slots * 28 + 64));
+    CU(idx->d_pool.reserve(pl.pool_slots * 30 + 64));
     int64_t* p0 = idx->d_pool.as<int64_t>();
     int64_t* p1 = p0 + pl.pool_slots;
     int64_t* p2 = p1 + pl.pool_slots;
     uint32_t* pk = reinterpret_cast<uint32_t*>(p2 + pl.pool_slots);
+    uint16_t* pc = reinterpret_cast<uint16_t*>(pk + pl.pool_slots);
     CU(cudaEventRecord(idx->ev[1], st));
     if(pl.n_units) {
         KwParams P{};
         P.qd = pl.d_qd; P.cd = pl.d_cd; P.ud = pl.d_ud;
-        P.pool_s0 = p0; P.pool_s1 = p1; P.pool_s2 = p2; P.pool_key = pk;
+        P.pool_s0 = p0; P.pool_s1 = p1; P.pool_s2 = p2; P.pool_key = pk; P.pool_cmb = pc;
         P.unit_cnt = pl.d_unit_cnt; P.combo_matches = pl.d_combo_matches; P.stats = pl.d_stats;
         P.F = pl.F; P.KP = pl.KP; P.NL = pl.NL;
         for(uint32_t f = 0; f < (uint32_t) kMaxFieldSlots; f++) P.field_ids[f] = pl.field_ids[f];
@@ -381,13 +421,20 @@ tsgpu_status run_keyword(tsgpu_index* idx, KwPlan& pl, uint32_t kv_stride, KwDev
     }
     {
         FinalParams P{};
-        P.qd = pl.d_qd; P.ud = pl.d_ud;
-        P.pool_s0 = p0; P.pool_s1 = p1; P.pool_s2 = p2; P.pool_key = pk;
+        P.qd = pl.d_qd; P.ud = pl.d_ud; P.md = nullptr;
+        P.pool_s0 = p0; P.pool_s1 = p1; P.pool_s2 = p2; P.pool_key = pk; P.pool_cmb = pc;
         P.unit_cnt = pl.d_unit_cnt; P.combo_matches = pl.d_combo_matches;
         P.out_kv = out.kv; P.out_count = out.count; P.out_found = out.found; P.out_searched = out.searched;
         P.kv_stride = kv_stride; P.KP = pl.KP;
         const size_t smem = kw_final_smem(pl);
         CU(cudaFuncSetAttribute(kw_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024)));
+        CU(cudaFuncSetAttribute(kw_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024)));
+        for(size_t lv = 0; lv < pl.levels.size(); lv++) {
+            P.md = pl.d_levels[lv];
+            kw_merge_kernel<<<(unsigned) pl.levels[lv].size(), kFinalThreads, smem, st>>>(P);
+            idx->stats.launches_total++;
+        }
+        CU(cudaGetLastError());
         if(nq) {
             kw_final_kernel<<<nq, kFinalThreads, smem, st>>>(P);
             idx->stats.launches_total++;
@@ -423,7 +470,7 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     if(efe > 4096) return fail(TSGPU_ERR_CAPACITY, "max(ef,k) must be <= 4096");
     const tsv::HnswDev& g = idx->hnsw;
     // persistent warps: 4 per CTA
-    const unsigned max_blocks = (unsigned) idx->n_sms * 4;
+    const unsigned max_blocks = (unsigned) idx->n_sms * 7;      // register-limited residency (72 regs x 128 threads)
     const unsigned grid = std::max(1u, std::min(max_blocks, (nq + 3) / 4));
     const size_t slots = (size_t) grid * 4;
     const size_t vis_words = ((size_t) g.n_nodes + 31) / 32;
@@ -475,7 +522,7 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     P.error = reinterpret_cast<int*>(base + o_misc + 32);
     const uint32_t dim = g.dim;
     const int nch = (dim % 128 == 0) ? (int) (dim / 128) : 0;
-    const size_t heap_bytes = (size_t) 4 * (efe + 1) * 8;
+    const size_t heap_bytes = (size_t) 4 * ((size_t) efe + 1 + tsv::kCandSmem) * 8;
     const size_t q_bytes = (size_t) 4 * ((dim + 3) & ~3u) * 4;
     CU(cudaEventRecord(idx->ev[3], st));
     switch(nch) {
@@ -702,7 +749,15 @@ tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint
     CU(up(4, pk.packed.data(), pk.packed.size() * 4, false));
     CU(up(5, f->pos_off, (n_post + 1) * 8, true));
     CU(up(6, f->positions, n_pos * 4, true));
-    fm.dev.n_lists = L; fm.dev.is_array = f->is_array;
+    fm.dev.n_lists = L;
+    fm.dev.is_array = f->is_array ? tsdev::kFieldIsArray : 0;
+    if(!f->is_array) {      // validate once so the kernels may take the plain-field fast path
+        std::vector<uint64_t> h_po(n_post + 1);
+        std::vector<uint32_t> h_pos(n_pos ? n_pos : 1);
+        CU(cudaMemcpy(h_po.data(), f->pos_off, (n_post + 1) * 8, cudaMemcpyDefault));
+        if(n_pos) CU(cudaMemcpy(h_pos.data(), f->positions, n_pos * 4, cudaMemcpyDefault));
+        if(tspack::plain_wellformed(h_po.data(), h_pos.data(), n_post)) fm.dev.is_array |= tsdev::kFieldPlainOk;
+    }
     fm.dev.list_off = (const uint64_t*) fm.d_alloc[0];
     fm.dev.list_blk_off = (const uint32_t*) fm.d_alloc[1];
     fm.dev.blk_first = (const uint32_t*) fm.d_alloc[2];
