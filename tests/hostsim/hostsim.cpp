@@ -137,6 +137,17 @@ size_t hs_keyword_combo(const tsgpu_field* fields, uint32_t n_index_fields, cons
     return n;
 }
 
+// probe every query id in a single packed list; out[i] = list-local index or 0xFFFFFFFF
+void hs_probe_ids(const uint32_t* ids, uint64_t n, const uint32_t* queries, uint64_t nq, uint32_t* out) {
+    uint64_t list_off[2] = {0, n};
+    tspack::PackedField pk;
+    tspack::pack_field(1, list_off, ids, pk);
+    DevField d{};
+    d.n_lists = 1; d.list_off = list_off; d.list_blk_off = pk.list_blk_off.data(); d.blk_first = pk.blk_first.data();
+    d.blk_info = pk.blk_info.data(); d.packed = pk.packed.data();
+    for(uint64_t i = 0; i < nq; i++) out[i] = n ? probe_list(d, 0, 0, pk.list_blk_off[1] - 1, queries[i]) : kNone;
+}
+
 int hs_phrase_match_doc(uint32_t k, const uint32_t* tok_off, const uint32_t* raw) {
     RawTok toks[kMaxTokens];
     for(uint32_t t = 0; t < k; t++) { toks[t].p = raw + tok_off[t]; toks[t].n = tok_off[t + 1] - tok_off[t]; }

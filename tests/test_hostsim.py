@@ -29,6 +29,7 @@ def hs():
     L.hs_keyword_combo.argtypes = [C.POINTER(S.FieldStruct), C.c_uint32, C.POINTER(S.KwBatchStruct), C.c_uint32, C.c_uint32,
                                    S.u32p, S.u64p, C.c_size_t]
     L.hs_phrase_match_doc.argtypes = [C.c_uint32, S.u32p, S.u32p]
+    L.hs_probe_ids.argtypes = [S.u32p, C.c_uint64, S.u32p, C.c_uint64, S.u32p]
     return L
 
 
@@ -109,3 +110,30 @@ def test_device_block_probe_random(hs):
         b = S.KwBatch([S.Query([S.Combo([[0], [1]], 2)])], [0])
         ids, _ = hs_combo(hs, [flat], b, 0, 0)
         assert ids.tolist() == np.intersect1d(a, bb).tolist()
+
+
+def test_device_probe_fuzz(hs):
+    # every id of the list must be found at its index, every absent id must miss; all bit widths and block fills
+    rng = np.random.default_rng(17)
+    for trial in range(300):
+        n = int(rng.choice([1, 2, 3, 127, 128, 129, 255, 256, 257, 1000, 5000]))
+        kind = trial % 5
+        if kind == 0:
+            ids = np.sort(rng.choice(max(n, int(n * rng.uniform(1.0, 1.5))), n, replace=False))
+        elif kind == 1:
+            ids = np.unique(rng.integers(0, (1 << 32) - 1, n, dtype=np.uint64))
+        elif kind == 2:   # clustered: dense runs separated by big gaps
+            ids = np.unique(np.concatenate([np.arange(s, s + int(rng.integers(1, 300))) for s in rng.integers(0, 1 << 31, max(1, n // 100), dtype=np.uint64)]))
+        elif kind == 3:   # skewed inside blocks
+            ids = np.unique((rng.random(n) ** 4 * (1 << 24)).astype(np.uint64))
+        else:
+            ids = np.unique(rng.integers(0, max(2, 8 * n), n, dtype=np.uint64))
+        ids = ids.astype(np.uint32)
+        absent = rng.integers(0, int(ids[-1]) + 3, 500, dtype=np.uint64).astype(np.uint32)
+        q = np.concatenate([ids, absent, np.asarray([0, int(ids[0]), int(ids[-1]), min(int(ids[-1]) + 1, (1 << 32) - 1)], np.uint32)])
+        out = np.zeros(len(q), np.uint32)
+        hs.hs_probe_ids(ol.p32(np.ascontiguousarray(ids)), len(ids), ol.p32(np.ascontiguousarray(q)), len(q), ol.p32(out))
+        pos = np.searchsorted(ids, q)
+        hit = (pos < len(ids)) & (ids[np.minimum(pos, len(ids) - 1)] == q)
+        exp = np.where(hit, pos, 0xFFFFFFFF).astype(np.uint32)
+        assert (out == exp).all(), (trial, kind, n)

@@ -87,6 +87,7 @@ struct KwParams {
     uint32_t* unit_cnt;                // [n_units]
     uint32_t* combo_matches;           // [n_combos]
     unsigned long long* stats;         // [0] driver ids, [1] probed block ids, [2] matches
+    long long* q_thr;                  // [nq] best "K-th scores[0]" published by any finished top-K of the query
     uint32_t F;
     uint32_t field_ids[kMaxFieldSlots];
     uint32_t KP;                       // power of two >= max topk in the batch
@@ -206,7 +207,8 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
 
     __shared__ CDesc cd;
     __shared__ QDesc qd;
-    __shared__ uint32_t l_blk0[kMaxLists], l_blk1[kMaxLists], l_gal[kMaxLists], l_lo[kMaxLists], l_hi[kMaxLists];
+    __shared__ uint32_t l_blk0[kMaxLists], l_blk1[kMaxLists];
+    __shared__ uint32_t w_gal[kThreads / 32][kMaxLists], w_lo[kThreads / 32][kMaxLists], w_hi[kThreads / 32][kMaxLists];
     __shared__ unsigned long long l_df[kMaxLists], l_base[kMaxLists];
     __shared__ uint32_t s_warp[8];
     __shared__ int64_t thr[3];
@@ -235,8 +237,7 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
             l_blk0[tid] = b0; l_blk1[tid] = b1 - 1;      // lists are never empty
             l_base[tid] = fld.list_off[l];
             l_df[tid] = fld.list_off[l + 1] - fld.list_off[l];
-            l_gal[tid] = b0;
-        } else { l_blk0[tid] = 0; l_blk1[tid] = 0; l_base[tid] = 0; l_df[tid] = 0; l_gal[tid] = 0; }
+        } else { l_blk0[tid] = 0; l_blk1[tid] = 0; l_base[tid] = 0; l_df[tid] = 0; }
     }
     if(tid == 0) { s_n = 0; s_have_thr = 0; s_matches = 0; s_driver_ids = 0; s_probe_blocks = 0; s_qn = 0; }
     __syncthreads();
@@ -260,11 +261,14 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
     const uint32_t K = qd.topk;
     const uint32_t drv = cd.driver_row;
     const uint16_t cmb_local = (uint16_t) (ud.combo - qd.combo_begin);
+    const uint32_t warp = tid >> 5, lane = tid & 31;
+    long long* const gthr_p = P.q_thr + cd.q;
     uint32_t prev_fd = 0xFFFFFFFFu;
 
     // Scores queue entries [base, base+cnt) (cnt <= 128) with all threads busy, appends the survivors to the top-K
     // buffer and compacts that buffer when the next batch might not fit.
     auto score_batch = [&](uint32_t base, uint32_t cnt) {
+        const long long gthr = *reinterpret_cast<volatile long long*>(gthr_p);
         bool keep = false;
         int64_t sc[3] = {0, 0, 0};
         uint32_t mid = 0;
@@ -303,8 +307,8 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
             const int msi = compute_sort_scores(SS, mid, (int64_t) aggs, 0.0f, sc);
             if(msi >= 0) sc[msi] = (int64_t) aggs;            // src/index.cpp:5541-5544 (undoes the ASC negation)
             if(qd.found_bitmap) atomicOr(qd.found_bitmap + (mid >> 5), 1u << (mid & 31));
-            keep = true;
-            if(s_have_thr) keep = kv_greater(sc[0], sc[1], sc[2], mid, thr[0], thr[1], thr[2], thr_key);
+            keep = sc[0] >= gthr;          // K distinct docs of this query already have scores[0] >= gthr
+            if(keep && s_have_thr) keep = kv_greater(sc[0], sc[1], sc[2], mid, thr[0], thr[1], thr[2], thr_key);
         }
         uint32_t a_total;
         const uint32_t arank = cta_rank(keep, s_warp, &a_total);
@@ -324,7 +328,10 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
             if(tid == 0) {
                 const uint32_t nn = n < K ? n : K;
                 s_n = nn;
-                if(nn == K) { s_have_thr = 1; thr[0] = tb.s0[K - 1]; thr[1] = tb.s1[K - 1]; thr[2] = tb.s2[K - 1]; thr_key = tb.key[K - 1]; }
+                if(nn == K) {
+                    s_have_thr = 1; thr[0] = tb.s0[K - 1]; thr[1] = tb.s1[K - 1]; thr[2] = tb.s2[K - 1]; thr_key = tb.key[K - 1];
+                    atomicMax(gthr_p, (long long) tb.s0[K - 1]);
+                }
             }
             __syncthreads();
         }
@@ -338,11 +345,11 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
         const DevField& dfld = ix.fields[P.field_ids[fd]];
         const uint32_t b = l_blk0[jd] + (tile - cd.drv_tile_off[fd]);
         const uint32_t cnt = block_count(b, l_blk0[jd], l_df[jd]);
-        if(fd != prev_fd) {                        // ids restart with a new driver list: reset the gallop cursors
-            __syncthreads();
-            if(tid < n_lists) l_gal[tid] = l_blk0[tid];
+        if(fd != prev_fd) {                        // ids restart with a new driver list: reset this warp's gallop cursors
+            __syncwarp();
+            if(lane < n_lists) w_gal[warp][lane] = l_blk0[lane];
             prev_fd = fd;
-            __syncthreads();
+            __syncwarp();
         }
         // ---- decode (K2)
         const uint32_t first = __ldg(dfld.blk_first + b);
@@ -350,74 +357,76 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
         const uint32_t bits = (uint32_t) (info >> 40) & 0xFF;
         const uint32_t* w = dfld.packed + (info & 0xFFFFFFFFFFull);
         const uint32_t id = first + unpack_at(w, bits, tid < cnt ? tid : 0);
-        const uint32_t tmax = first + unpack_at(w, bits, cnt - 1);
         bool alive = tid < cnt;
         if(alive && qd.filter_bitmap) alive = (__ldg(qd.filter_bitmap + (id >> 5)) >> (id & 31)) & 1;
         if(alive && qd.n_excl) alive = !excluded(qd.excl, qd.n_excl, id);
         if(qd.filter_empty) alive = false;
-        const int any_alive = __syncthreads_or(alive);
         if(tid == 0) s_driver_ids += cnt;
-        if(!any_alive) continue;
 
-        // ---- narrow every probed list to the blocks covering [first, tmax]
-        if(n_lists > 1) {
-            if(tid < 2 * n_lists) {
-                const uint32_t j = tid >> 1;
-                if(cd.lists[j] != kNone && j != jd) {
-                    const uint32_t* bf = ix.fields[P.field_ids[j % F]].blk_first;
-                    const uint32_t target = (tid & 1) ? tmax : first;
-                    const uint32_t r = gallop_block(bf, l_gal[j], l_blk1[j], target);
-                    if(tid & 1) l_hi[j] = r; else l_lo[j] = r;
-                }
-            }
-            __syncthreads();
-            if(tid < n_lists && cd.lists[tid] != kNone && tid != jd) {
-                // lo == kNone: tile starts before the list's first remaining block -> clamp; hi == kNone: nothing to hit
-                if(l_lo[tid] == kNone) l_lo[tid] = l_gal[tid]; else l_gal[tid] = l_lo[tid];
-                if(l_hi[tid] != kNone) atomicAdd(&s_probe_blocks, l_hi[tid] - l_lo[tid] + 1);
-            }
-            __syncthreads();
-        }
-
-        // ---- probe (K1): rows in probe order, all field slots of a row
-        for(uint32_t oi = 0; oi < cd.n_rows; oi++) {
-            const uint32_t r = cd.probe_order[oi];
-            bool any = false;
-            for(uint32_t f = 0; f < F; f++) {
-                const uint32_t j = r * F + f;
-                const uint32_t l = cd.lists[j];
-                uint32_t h = kNone;
-                if(l != kNone) {
-                    if(j == jd) h = (b - l_blk0[jd]) * kBlock + tid;
-                    else if(alive && l_hi[j] != kNone) {
-                        const DevField& g = ix.fields[P.field_ids[f]];
-                        const uint32_t bb = find_block(g.blk_first, l_lo[j], l_hi[j], id);
-                        if(bb != kNone) {
-                            const uint32_t c2 = block_count(bb, l_blk0[j], l_df[j]);
-                            const uint32_t ii = probe_block(g, bb, c2, id);
-                            if(ii != kNone) h = (bb - l_blk0[j]) * kBlock + ii;
-                        }
+        // Everything up to the enqueue is warp-private (no CTA barrier): each warp owns 32 consecutive candidates.
+        const uint32_t wbase = warp * 32;
+        if(wbase < cnt && __any_sync(0xffffffffu, alive)) {
+            // ---- narrow every probed list to the blocks covering this warp's [min id, max id]
+            if(n_lists > 1) {
+                const uint32_t last_lane = (cnt - wbase) >= 32 ? 31 : (cnt - wbase - 1);
+                const uint32_t wmin = __shfl_sync(0xffffffffu, id, 0);
+                const uint32_t wmax = __shfl_sync(0xffffffffu, id, last_lane);
+                for(uint32_t t = lane; t < 2 * n_lists; t += 32) {
+                    const uint32_t j = t >> 1;
+                    if(cd.lists[j] != kNone && j != jd) {
+                        const uint32_t* bf = ix.fields[P.field_ids[j % F]].blk_first;
+                        const uint32_t r = gallop_block(bf, w_gal[warp][j], l_blk1[j], (t & 1) ? wmax : wmin);
+                        if(t & 1) w_hi[warp][j] = r; else w_lo[warp][j] = r;
                     }
                 }
-                hp[j * kThreads + tid] = h;
-                if(h != kNone) { any = true; if(r == drv && f < fd) alive = false; }   // produced by an earlier field's tile
+                __syncwarp();
+                if(lane < n_lists && cd.lists[lane] != kNone && lane != jd) {
+                    // lo == kNone: the warp starts before the list's first remaining block -> clamp; hi == kNone: no hit possible
+                    if(w_lo[warp][lane] == kNone) w_lo[warp][lane] = w_gal[warp][lane]; else w_gal[warp][lane] = w_lo[warp][lane];
+                    if(w_hi[warp][lane] != kNone) atomicAdd(&s_probe_blocks, w_hi[warp][lane] - w_lo[warp][lane] + 1);
+                }
+                __syncwarp();
             }
-            if(((cd.req_mask >> r) & 1) && !any) alive = false;
+            // ---- probe (K1): rows in probe order, all field slots of a row
+            for(uint32_t oi = 0; oi < cd.n_rows; oi++) {
+                const uint32_t r = cd.probe_order[oi];
+                bool any = false;
+                for(uint32_t f = 0; f < F; f++) {
+                    const uint32_t j = r * F + f;
+                    const uint32_t l = cd.lists[j];
+                    uint32_t h = kNone;
+                    if(l != kNone) {
+                        if(j == jd) h = (b - l_blk0[jd]) * kBlock + tid;
+                        else if(alive && w_hi[warp][j] != kNone) {
+                            const DevField& g = ix.fields[P.field_ids[f]];
+                            const uint32_t bb = find_block(g.blk_first, w_lo[warp][j], w_hi[warp][j], id);
+                            if(bb != kNone) {
+                                const uint32_t c2 = block_count(bb, l_blk0[j], l_df[j]);
+                                const uint32_t ii = probe_block(g, bb, c2, id);
+                                if(ii != kNone) h = (bb - l_blk0[j]) * kBlock + ii;
+                            }
+                        }
+                    }
+                    hp[j * kThreads + tid] = h;
+                    if(h != kNone) { any = true; if(r == drv && f < fd) alive = false; }   // produced by an earlier field's tile
+                }
+                if(((cd.req_mask >> r) & 1) && !any) alive = false;
+            }
+            // ---- enqueue matches: one shared-memory atomic per warp reserves the slots
+            const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+            if(bal) {
+                uint32_t qb = 0;
+                if(lane == 0) { qb = atomicAdd(&s_qn, (uint32_t) __popc(bal)); atomicAdd(&s_matches, (uint32_t) __popc(bal)); }
+                qb = __shfl_sync(0xffffffffu, qb, 0);
+                if(alive) {
+                    const uint32_t slot = qb + __popc(bal & ((1u << lane) - 1u));
+                    q_id[slot] = id;
+                    for(uint32_t j = 0; j < n_lists; j++) q_hp[j * kQCap + slot] = hp[j * kThreads + tid];
+                }
+            }
         }
-
-        // ---- enqueue matches (compaction): scoring happens 128 docs at a time so no lane idles
-        uint32_t m_total;
-        const uint32_t rank = cta_rank(alive, s_warp, &m_total);
-        const uint32_t qn0 = s_qn;
-        if(alive) {
-            const uint32_t slot = qn0 + rank;
-            q_id[slot] = id;
-            for(uint32_t j = 0; j < n_lists; j++) q_hp[j * kQCap + slot] = hp[j * kThreads + tid];
-        }
-        __syncthreads();
-        if(tid == 0) { s_qn = qn0 + m_total; s_matches += m_total; }
-        __syncthreads();
-        if(s_qn >= kThreads) {
+        __syncthreads();                          // the only CTA barrier of a tile: queue writes are visible
+        if(s_qn >= kThreads) {                    // scoring happens 128 docs at a time so no lane idles
             const uint32_t qn = s_qn;
             score_batch(qn - kThreads, kThreads);
             if(tid == 0) s_qn = qn - kThreads;

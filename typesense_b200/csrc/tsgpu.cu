@@ -142,6 +142,7 @@ struct KwPlan {
     // device views (valid after upload)
     QDesc* d_qd = nullptr; CDesc* d_cd = nullptr; UDesc* d_ud = nullptr; uint32_t* d_multi_q = nullptr;
     uint32_t* d_unit_cnt = nullptr; uint32_t* d_combo_matches = nullptr; unsigned long long* d_stats = nullptr;
+    long long* d_q_thr = nullptr;
     std::vector<const uint32_t*> q_bitmap;   // per query filter bitmap (device) or nullptr
     std::vector<const uint32_t*> q_filter_ids; std::vector<size_t> q_filter_n;   // device ids (flat path)
     std::vector<const uint32_t*> q_excl_dev;
@@ -219,7 +220,7 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
         total_tiles += tiles;
     }
     // ---- queries
-    uint32_t tpu = (uint32_t) std::min<uint64_t>(32, std::max<uint64_t>(4, total_tiles / 4096));
+    uint32_t tpu = (uint32_t) std::min<uint64_t>(128, std::max<uint64_t>(4, total_tiles / 8192));
     std::vector<std::pair<uint32_t, uint32_t>> q_units0;
     for(uint32_t q = 0; q < nq; q++) {
         QDesc& qd = pl.qd[q];
@@ -328,6 +329,7 @@ tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& p
     std::vector<size_t> o_lv;
     for(auto& lv: pl.levels) o_lv.push_back(sg.add(lv.data(), lv.size() * sizeof(MDesc)));
     const size_t o_cnt = sg.reserve(((size_t) pl.n_units_total + pl.nc + 8) * 4 + 64);
+    const size_t o_thr = sg.reserve((size_t) nq * 8);
     CU(idx->d_stage.reserve(sg.host.size()));
     unsigned char* dbase = idx->d_stage.as<unsigned char>();
     const uint32_t* d_excl = reinterpret_cast<const uint32_t*>(dbase + o_excl);
@@ -358,6 +360,7 @@ tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& p
     memcpy(sg.host.data() + o_ud, pl.ud.data(), pl.ud.size() * sizeof(UDesc));
     memcpy(sg.host.data() + o_mq, pl.multi_q.data(), pl.multi_q.size() * 4);
     memset(sg.host.data() + o_cnt, 0, ((size_t) pl.n_units_total + pl.nc + 8) * 4 + 64);
+    for(uint32_t q = 0; q < nq; q++) reinterpret_cast<long long*>(sg.host.data() + o_thr)[q] = INT64_MIN;
     CU(idx->h_stage.reserve(sg.host.size()));
     memcpy(idx->h_stage.p, sg.host.data(), sg.host.size());
     CU(cudaMemcpyAsync(dbase, idx->h_stage.p, sg.host.size(), cudaMemcpyHostToDevice, st));
@@ -372,6 +375,7 @@ tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& p
     pl.d_stats = reinterpret_cast<unsigned long long*>(cnt);                 // 4 x u64
     pl.d_combo_matches = reinterpret_cast<uint32_t*>(cnt + 32);
     pl.d_unit_cnt = pl.d_combo_matches + pl.nc;
+    pl.d_q_thr = reinterpret_cast<long long*>(dbase + o_thr);
     // inline filter bitmaps
     for(size_t s = 0; s < n_inline; s++) {
         const size_t n = (size_t) (b->filter_off[s + 1] - b->filter_off[s]);
@@ -411,6 +415,7 @@ tsgpu_status run_keyword(tsgpu_index* idx, KwPlan& pl, uint32_t kv_stride, KwDev
         P.qd = pl.d_qd; P.cd = pl.d_cd; P.ud = pl.d_ud;
         P.pool_s0 = p0; P.pool_s1 = p1; P.pool_s2 = p2; P.pool_key = pk; P.pool_cmb = pc;
         P.unit_cnt = pl.d_unit_cnt; P.combo_matches = pl.d_combo_matches; P.stats = pl.d_stats;
+        P.q_thr = pl.d_q_thr;
         P.F = pl.F; P.KP = pl.KP; P.NL = pl.NL;
         for(uint32_t f = 0; f < (uint32_t) kMaxFieldSlots; f++) P.field_ids[f] = pl.field_ids[f];
         const size_t smem = kw_search_smem(pl);
