@@ -368,7 +368,8 @@ def run_tsgpu(args, rank, world, local_rank):
         roof.sort(key=lambda r: -r["ms"])
         extra["roofline"] = roof[0] if roof else None
         extra["roofline_other"] = roof[1:]
-        extra["device_ms_per_step"] = {"total": ms_dev, "keyword": ms_kw, "knn": ms_knn, "fuse": ms_fuse}
+        extra["device_ms_per_step"] = {"total": ms_dev, "keyword": ms_kw, "kw_search": statistics.mean(s["ms_kw_search"] for s in sts),
+                                       "kw_merge": statistics.mean(s["ms_kw_merge"] for s in sts), "knn": ms_knn, "fuse": ms_fuse}
         if want_cpu:
             import oracle_lib as ol
             ol.build_oracle()

@@ -204,6 +204,8 @@ typedef struct {
     uint64_t knn_expanded;       /* expanded nodes */
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
+    float    ms_kw_search;       // kw_search_kernel alone
+    float    ms_kw_merge;        // kw_merge_kernel levels + kw_final_kernel + found_popcount_kernel
 } tsgpu_stats;
 tsgpu_status tsgpu_get_stats(tsgpu_index* idx, tsgpu_stats* out);
 

@@ -33,6 +33,13 @@ size_t hs_keyword_combo(const tsgpu_field* fields, uint32_t n_index_fields, cons
         d.list_blk_off = hf[i].pk.list_blk_off.data(); d.blk_first = hf[i].pk.blk_first.data();
         d.blk_info = hf[i].pk.blk_info.data(); d.packed = hf[i].pk.packed.data();
         d.pos_off = fields[i].pos_off; d.positions = fields[i].positions;
+        {   // dense lists: low threshold here so the bitmap/rank path is exercised on small test collections
+            uint32_t max_id = 0;
+            for(uint64_t k = 0; k < fields[i].list_off[fields[i].n_lists]; k++) if(fields[i].ids[k] > max_id) max_id = fields[i].ids[k];
+            tspack::pack_dense(fields[i].n_lists, fields[i].list_off, fields[i].ids, max_id + 1, 64, hf[i].pk);
+            d.list_dense = hf[i].pk.list_dense.data(); d.dense_bits = hf[i].pk.dense_bits.data(); d.dense_rank = hf[i].pk.dense_rank.data();
+            d.dense_words = hf[i].pk.dense_words; d.dense_groups = hf[i].pk.dense_groups;
+        }
     }
     const uint32_t F = b->n_fields;
     const uint32_t row0 = b->c_tok_off[c], n_rows = b->c_tok_off[c + 1] - row0, n_req = b->c_n_required[c];

@@ -207,7 +207,7 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
 
     __shared__ CDesc cd;
     __shared__ QDesc qd;
-    __shared__ uint32_t l_blk0[kMaxLists], l_blk1[kMaxLists];
+    __shared__ uint32_t l_blk0[kMaxLists], l_blk1[kMaxLists], l_dense[kMaxLists];
     __shared__ uint32_t w_gal[kThreads / 32][kMaxLists], w_lo[kThreads / 32][kMaxLists], w_hi[kThreads / 32][kMaxLists];
     __shared__ unsigned long long l_df[kMaxLists], l_base[kMaxLists];
     __shared__ uint32_t s_warp[8];
@@ -237,7 +237,8 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
             l_blk0[tid] = b0; l_blk1[tid] = b1 - 1;      // lists are never empty
             l_base[tid] = fld.list_off[l];
             l_df[tid] = fld.list_off[l + 1] - fld.list_off[l];
-        } else { l_blk0[tid] = 0; l_blk1[tid] = 0; l_base[tid] = 0; l_df[tid] = 0; }
+            l_dense[tid] = fld.list_dense ? fld.list_dense[l] : kNone;
+        } else { l_blk0[tid] = 0; l_blk1[tid] = 0; l_base[tid] = 0; l_df[tid] = 0; l_dense[tid] = kNone; }
     }
     if(tid == 0) { s_n = 0; s_have_thr = 0; s_matches = 0; s_driver_ids = 0; s_probe_blocks = 0; s_qn = 0; }
     __syncthreads();
@@ -373,14 +374,14 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
                 const uint32_t wmax = __shfl_sync(0xffffffffu, id, last_lane);
                 for(uint32_t t = lane; t < 2 * n_lists; t += 32) {
                     const uint32_t j = t >> 1;
-                    if(cd.lists[j] != kNone && j != jd) {
+                    if(cd.lists[j] != kNone && j != jd && l_dense[j] == kNone) {
                         const uint32_t* bf = ix.fields[P.field_ids[j % F]].blk_first;
                         const uint32_t r = gallop_block(bf, w_gal[warp][j], l_blk1[j], (t & 1) ? wmax : wmin);
                         if(t & 1) w_hi[warp][j] = r; else w_lo[warp][j] = r;
                     }
                 }
                 __syncwarp();
-                if(lane < n_lists && cd.lists[lane] != kNone && lane != jd) {
+                if(lane < n_lists && cd.lists[lane] != kNone && lane != jd && l_dense[lane] == kNone) {
                     // lo == kNone: the warp starts before the list's first remaining block -> clamp; hi == kNone: no hit possible
                     if(w_lo[warp][lane] == kNone) w_lo[warp][lane] = w_gal[warp][lane]; else w_gal[warp][lane] = w_lo[warp][lane];
                     if(w_hi[warp][lane] != kNone) atomicAdd(&s_probe_blocks, w_hi[warp][lane] - w_lo[warp][lane] + 1);
@@ -397,6 +398,9 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
                     uint32_t h = kNone;
                     if(l != kNone) {
                         if(j == jd) h = (b - l_blk0[jd]) * kBlock + tid;
+                        else if(l_dense[j] != kNone) {          // dense list: one bit test in an L2-resident bitmap
+                            if(alive && dense_test(ix.fields[P.field_ids[f]], l_dense[j], id)) h = kDenseHit;
+                        }
                         else if(alive && w_hi[warp][j] != kNone) {
                             const DevField& g = ix.fields[P.field_ids[f]];
                             const uint32_t bb = find_block(g.blk_first, w_lo[warp][j], w_hi[warp][j], id);
@@ -421,7 +425,11 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
                 if(alive) {
                     const uint32_t slot = qb + __popc(bal & ((1u << lane) - 1u));
                     q_id[slot] = id;
-                    for(uint32_t j = 0; j < n_lists; j++) q_hp[j * kQCap + slot] = hp[j * kThreads + tid];
+                    for(uint32_t j = 0; j < n_lists; j++) {
+                        uint32_t h = hp[j * kThreads + tid];
+                        if(h == kDenseHit) h = dense_rank_of(ix.fields[P.field_ids[j % F]], l_dense[j], id);   // only matches pay for the rank
+                        q_hp[j * kQCap + slot] = h;
+                    }
                 }
             }
         }
@@ -714,7 +722,9 @@ isect_tiles_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ 
     uint32_t hidx[kMaxTokens];
     for(uint32_t j = 0; j < P.k; j++) {
         uint32_t h = kNone;
+        const uint32_t dslot = g.list_dense ? g.list_dense[P.lists[j]] : kNone;
         if(!P.phrase && j == P.driver) h = own;
+        else if(dslot != kNone) { if(alive && dense_test(g, dslot, id)) h = dense_rank_of(g, dslot, id); }
         else if(alive && l_hi[j] != kNone) {
             const uint32_t bb = find_block(g.blk_first, l_lo[j], l_hi[j], id);
             if(bb != kNone) {

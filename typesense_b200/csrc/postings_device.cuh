@@ -13,6 +13,14 @@
 //                           block can be extracted without decoding its neighbours
 //   pos_off[P+1]       u64  -> positions
 //   positions[]        u32  raw reference offsets
+// Dense lists (df >= n_docs/64) additionally get a bitmap over seq_ids plus a rank directory (one running popcount
+// per 512 bits): membership of a candidate is ONE bit test in an L2-resident bitmap instead of a skip-index + block
+// search, and the posting index of a hit (needed to reach its offsets) is directory + popcounts. At the 10 M-doc
+// bench shape ~50 tokens are dense (62 MB of bitmaps) and they receive most of the probes, because the driver is
+// always the shortest list of a combination.
+//   list_dense[L]      u32  dense slot of list l or kNone
+//   dense_bits[]       u32  slot s owns words [s*dense_words, (s+1)*dense_words)
+//   dense_rank[]       u32  slot s owns [s*dense_groups, ...): number of set bits before 512-bit group g
 #pragma once
 #include <stdint.h>
 #include "score_device.cuh"
@@ -35,7 +43,39 @@ struct DevField {
     const uint32_t* packed;
     const uint64_t* pos_off;
     const uint32_t* positions;
+    const uint32_t* list_dense;
+    const uint32_t* dense_bits;
+    const uint32_t* dense_rank;
+    uint32_t dense_words;       // words per bitmap (multiple of 16)
+    uint32_t dense_groups;      // dense_words / 16
 };
+
+constexpr uint32_t kDenseHit = 0xFFFFFFFEu;   // probe marker: member of a dense list, rank not computed yet
+
+TS_HD bool dense_test(const DevField& f, uint32_t slot, uint32_t id) {
+    return (f.dense_bits[(size_t) slot * f.dense_words + (id >> 5)] >> (id & 31)) & 1u;
+}
+// list-local posting index of a member id of dense slot `slot`
+TS_HD uint32_t dense_rank_of(const DevField& f, uint32_t slot, uint32_t id) {
+    const uint32_t w = id >> 5, g = w >> 4;
+    const uint32_t* bits = f.dense_bits + (size_t) slot * f.dense_words + ((size_t) g << 4);
+    uint32_t r = f.dense_rank[(size_t) slot * f.dense_groups + g];
+    const uint32_t wi = w & 15;
+    for(uint32_t i = 0; i < wi; i++) {
+#if defined(__CUDA_ARCH__)
+        r += __popc(bits[i]);
+#else
+        r += (uint32_t) __builtin_popcount(bits[i]);
+#endif
+    }
+    const uint32_t part = bits[wi] & ((1u << (id & 31)) - 1u);
+#if defined(__CUDA_ARCH__)
+    r += __popc(part);
+#else
+    r += (uint32_t) __builtin_popcount(part);
+#endif
+    return r;
+}
 
 TS_HD uint32_t bits_required(uint32_t v) {
     uint32_t b = 0;
@@ -111,6 +151,10 @@ TS_HD uint32_t block_count(uint32_t b, uint32_t lb0, uint64_t df) {
 // Membership probe of `id` in list `l` restricted to blocks [b_lo, b_hi] (absolute). Returns the list-local posting
 // index (0..df) or kNone.
 TS_HD uint32_t probe_list(const DevField& f, uint32_t l, uint32_t b_lo, uint32_t b_hi, uint32_t id) {
+    if(f.list_dense) {
+        const uint32_t slot = f.list_dense[l];
+        if(slot != kNone) return ((id >> 5) < f.dense_words && dense_test(f, slot, id)) ? dense_rank_of(f, slot, id) : kNone;
+    }
     const uint32_t lb0 = f.list_blk_off[l];
     const uint32_t b = find_block(f.blk_first, b_lo, b_hi, id);
     if(b == kNone) return kNone;

@@ -13,7 +13,36 @@ struct PackedField {
     std::vector<uint32_t> blk_first;      // [NB]
     std::vector<uint64_t> blk_info;       // [NB]
     std::vector<uint32_t> packed;         // words (+1 padding word)
+    // dense lists
+    std::vector<uint32_t> list_dense;     // [L] slot or kNone
+    std::vector<uint32_t> dense_bits, dense_rank;
+    uint32_t dense_words = 0, dense_groups = 0, n_dense = 0;
 };
+
+// bitmap + rank directory for every list with df >= min_df (and at most max_lists of them, longest first by id order)
+inline void pack_dense(uint32_t n_lists, const uint64_t* list_off, const uint32_t* ids, uint32_t n_docs, uint64_t min_df,
+                       PackedField& out) {
+    out.list_dense.assign(n_lists ? n_lists : 1, tsdev::kNone);
+    out.dense_words = (((n_docs + 31) / 32) + 15) & ~15u;
+    out.dense_groups = out.dense_words / 16;
+    out.n_dense = 0;
+    if(min_df == 0) min_df = 1;
+    for(uint32_t l = 0; l < n_lists; l++) if(list_off[l + 1] - list_off[l] >= min_df) out.list_dense[l] = out.n_dense++;
+    out.dense_bits.assign((size_t) out.n_dense * out.dense_words + 16, 0);
+    out.dense_rank.assign((size_t) out.n_dense * out.dense_groups + 1, 0);
+    for(uint32_t l = 0; l < n_lists; l++) {
+        const uint32_t s = out.list_dense[l];
+        if(s == tsdev::kNone) continue;
+        uint32_t* bits = out.dense_bits.data() + (size_t) s * out.dense_words;
+        for(uint64_t i = list_off[l]; i < list_off[l + 1]; i++) bits[ids[i] >> 5] |= 1u << (ids[i] & 31);
+        uint32_t* rk = out.dense_rank.data() + (size_t) s * out.dense_groups;
+        uint32_t run = 0;
+        for(uint32_t g = 0; g < out.dense_groups; g++) {
+            rk[g] = run;
+            for(int i = 0; i < 16; i++) run += (uint32_t) __builtin_popcount(bits[(size_t) g * 16 + i]);
+        }
+    }
+}
 
 inline void pack_field(uint32_t n_lists, const uint64_t* list_off, const uint32_t* ids, PackedField& out) {
     using tsdev::kBlock;

@@ -81,7 +81,7 @@ struct FieldMirror {
     DevField dev{};
     std::vector<uint64_t> h_list_off;
     std::vector<uint32_t> h_list_blk_off;
-    void* d_alloc[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* d_alloc[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct Filter {
@@ -110,7 +110,7 @@ struct tsgpu_index {
     DevBuf d_stage, d_pool, d_small, d_bitmaps, d_out, d_knn_vis, d_knn_log, d_knn_cand, d_knn_out, d_isect, d_kw_out;
     PinBuf h_stage;
     size_t knn_slots = 0, knn_vis_words = 0;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     tsgpu_stats stats{};
 };
 
@@ -424,6 +424,7 @@ tsgpu_status run_keyword(tsgpu_index* idx, KwPlan& pl, uint32_t kv_stride, KwDev
         idx->stats.launches_total++;
         CU(cudaGetLastError());
     }
+    CU(cudaEventRecord(idx->ev[6], st));
     {
         FinalParams P{};
         P.qd = pl.d_qd; P.ud = pl.d_ud; P.md = nullptr;
@@ -589,7 +590,12 @@ tsgpu_status end_call(tsgpu_index* idx, bool kw, bool knn) {
     CU(cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, idx->ev[0], idx->ev[5]); idx->stats.ms_total = ms;
-    if(kw) { cudaEventElapsedTime(&ms, idx->ev[1], idx->ev[2]); idx->stats.ms_keyword = ms; }
+    if(kw) {
+        cudaEventElapsedTime(&ms, idx->ev[1], idx->ev[2]); idx->stats.ms_keyword = ms;
+        if(cudaEventElapsedTime(&ms, idx->ev[1], idx->ev[6]) == cudaSuccess) idx->stats.ms_kw_search = ms;
+        if(cudaEventElapsedTime(&ms, idx->ev[6], idx->ev[2]) == cudaSuccess) idx->stats.ms_kw_merge = ms;
+        cudaGetLastError();
+    }
     if(knn) { cudaEventElapsedTime(&ms, idx->ev[3], idx->ev[4]); idx->stats.ms_knn = ms; }
     idx->stats.ms_kernels = idx->stats.ms_keyword + idx->stats.ms_knn + idx->stats.ms_fuse;
     return TSGPU_OK;
@@ -734,6 +740,13 @@ tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint
     std::vector<uint32_t> h_ids(n_post ? n_post : 1);
     if(n_post) CU(cudaMemcpy(h_ids.data(), f->ids, n_post * 4, cudaMemcpyDefault));
     for(uint32_t l = 0; l < L; l++) if(fm.h_list_off[l + 1] < fm.h_list_off[l]) return fail(TSGPU_ERR_INVALID, "list_off not monotone");
+    for(uint32_t l = 0; l < L; l++) {
+        const uint64_t a0 = fm.h_list_off[l], a1 = fm.h_list_off[l + 1];
+        for(uint64_t i = a0; i < a1; i++) {
+            if(h_ids[i] >= idx->n_docs) return fail(TSGPU_ERR_INVALID, "seq_id >= n_docs in a posting list");
+            if(i > a0 && h_ids[i] <= h_ids[i - 1]) return fail(TSGPU_ERR_INVALID, "posting list ids must be strictly ascending");
+        }
+    }
     tspack::PackedField pk;
     tspack::pack_field(L, fm.h_list_off.data(), h_ids.data(), pk);
     fm.h_list_blk_off = pk.list_blk_off;
@@ -754,6 +767,11 @@ tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint
     CU(up(4, pk.packed.data(), pk.packed.size() * 4, false));
     CU(up(5, f->pos_off, (n_post + 1) * 8, true));
     CU(up(6, f->positions, n_pos * 4, true));
+    // dense lists: bitmap + rank directory (see postings_device.cuh)
+    tspack::pack_dense(L, fm.h_list_off.data(), h_ids.data(), idx->n_docs, std::max<uint64_t>(64, idx->n_docs / 64), pk);
+    CU(up(7, pk.list_dense.data(), pk.list_dense.size() * 4, false));
+    CU(up(8, pk.dense_bits.data(), pk.dense_bits.size() * 4, false));
+    CU(up(9, pk.dense_rank.data(), pk.dense_rank.size() * 4, false));
     fm.dev.n_lists = L;
     fm.dev.is_array = f->is_array ? tsdev::kFieldIsArray : 0;
     if(!f->is_array) {      // validate once so the kernels may take the plain-field fast path
@@ -770,6 +788,10 @@ tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint
     fm.dev.packed = (const uint32_t*) fm.d_alloc[4];
     fm.dev.pos_off = (const uint64_t*) fm.d_alloc[5];
     fm.dev.positions = (const uint32_t*) fm.d_alloc[6];
+    fm.dev.list_dense = (const uint32_t*) fm.d_alloc[7];
+    fm.dev.dense_bits = (const uint32_t*) fm.d_alloc[8];
+    fm.dev.dense_rank = (const uint32_t*) fm.d_alloc[9];
+    fm.dev.dense_words = pk.dense_words; fm.dev.dense_groups = pk.dense_groups;
     idx->ixdev.fields[idx->fields.size()] = fm.dev;
     *out_field = (uint32_t) idx->fields.size();
     idx->fields.push_back(std::move(fm));
