@@ -97,6 +97,13 @@ struct tsgpu_index {
     int device = 0;
     uint32_t n_docs = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;      // vector stage of hybrid calls (overlaps the keyword kernels)
+    cudaStream_t vs = nullptr;           // stream the vector stage is issued on for the current call
+    cudaEvent_t evA = nullptr, evB = nullptr;
+    unsigned knn_blocks_per_sm = 7;
+    unsigned char* knn_misc_dev = nullptr;    // counters of the last HNSW launch (read after the final sync)
+    std::vector<unsigned char> knn_tables;   // host copies that must outlive the async uploads
+    std::vector<uint8_t> tmp_is_flat; std::vector<unsigned long long> tmp_foff;
     std::mutex mu;
     std::vector<FieldMirror> fields;
     IndexDev ixdev{};
@@ -462,21 +469,21 @@ struct KnnDeviceOut { float* dist; uint32_t* labels; uint32_t* n; uint32_t strid
 template <int NCH>
 void launch_hnsw(tsgpu_index* idx, const tsv::KnnParams& P, unsigned grid, size_t smem) {
     cudaFuncSetAttribute(tsv::hnsw_search_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024));
-    tsv::hnsw_search_kernel<NCH><<<grid, tsv::kKnnThreads, smem, idx->stream>>>(idx->hnsw, P);
+    tsv::hnsw_search_kernel<NCH><<<grid, tsv::kKnnThreads, smem, idx->vs>>>(idx->hnsw, P);
 }
 
 // d_queries: [nq*dim] on device. q_bitmap/q_excl/q_nexcl/q_skip: host vectors (uploaded here). Results in d_knn_out.
 tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef,
                      const std::vector<const uint32_t*>& q_bitmap, const std::vector<const uint32_t*>& q_excl,
                      const std::vector<uint32_t>& q_nexcl, const std::vector<uint8_t>& q_skip, KnnDeviceOut& out) {
-    cudaStream_t st = idx->stream;
+    cudaStream_t st = idx->vs;
     if(!idx->has_hnsw) return fail(TSGPU_ERR_INVALID, "no vector index loaded");
     if(k == 0) return fail(TSGPU_ERR_INVALID, "k must be > 0");
     const uint32_t efe = std::max(ef, k);
     if(efe > 4096) return fail(TSGPU_ERR_CAPACITY, "max(ef,k) must be <= 4096");
     const tsv::HnswDev& g = idx->hnsw;
     // persistent warps: 4 per CTA
-    const unsigned max_blocks = (unsigned) idx->n_sms * 7;      // register-limited residency (72 regs x 128 threads)
+    const unsigned max_blocks = (unsigned) idx->n_sms * idx->knn_blocks_per_sm;   // 7 = register-limited residency (72 regs x 128 threads)
     const unsigned grid = std::max(1u, std::min(max_blocks, (nq + 3) / 4));
     const size_t slots = (size_t) grid * 4;
     const size_t vis_words = ((size_t) g.n_nodes + 31) / 32;
@@ -499,14 +506,14 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     const size_t o_sk = sg.add(q_skip.empty() ? nullptr : q_skip.data(), (size_t) nq);
     const size_t o_misc = sg.reserve(64);
     memset(sg.host.data() + o_misc, 0, 64);
-    const size_t tbl_bytes = sg.host.size();
+    idx->knn_tables.swap(sg.host);                 // keep the pageable source alive until the call ends
+    const size_t tbl_bytes = idx->knn_tables.size();
     const size_t out_bytes = (size_t) nq * k * 8 + (size_t) nq * 4;
     CU(idx->d_knn_out.reserve(tbl_bytes + out_bytes + 256));
     unsigned char* base = idx->d_knn_out.as<unsigned char>();
     // staging through a dedicated pinned region at the tail of h_stage is not safe while the kw stage is in flight,
     // so use a plain async copy from the pageable vector (small)
-    CU(cudaMemcpyAsync(base, sg.host.data(), tbl_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));      // sg.host is pageable and about to go out of scope
+    CU(cudaMemcpyAsync(base, idx->knn_tables.data(), tbl_bytes, cudaMemcpyHostToDevice, st));
     idx->stats.h2d_bytes += tbl_bytes;
     unsigned char* ob = base + ((tbl_bytes + 255) & ~size_t(255));
     out.dist = reinterpret_cast<float*>(ob);
@@ -543,10 +550,15 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     idx->stats.launches_total++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(idx->ev[4], st));
-    // stats + overflow flag
-    unsigned long long hst[5];
-    CU(cudaMemcpyAsync(hst, base + o_misc + 8, 32, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    idx->knn_misc_dev = base + o_misc;        // counters + overflow flag are read by finish_knn() after the final sync
+    return TSGPU_OK;
+}
+
+tsgpu_status finish_knn(tsgpu_index* idx) {
+    if(!idx->knn_misc_dev) return TSGPU_OK;
+    unsigned long long hst[4];
+    CU(cudaMemcpy(hst, idx->knn_misc_dev + 8, 32, cudaMemcpyDeviceToHost));
+    idx->knn_misc_dev = nullptr;
     idx->stats.knn_dist += hst[0]; idx->stats.knn_expanded += hst[1];
     if((int) hst[3]) return fail(TSGPU_ERR_CAPACITY, "HNSW candidate heap overflow (more than 262144 live candidates in one query)");
     return TSGPU_OK;
@@ -554,7 +566,7 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
 
 template <int NCH>
 void launch_flat(tsgpu_index* idx, const tsv::FlatParams& P, unsigned long long total, unsigned grid, size_t smem) {
-    tsv::flat_distance_kernel<NCH><<<grid, 256, smem, idx->stream>>>(idx->hnsw, P, total);
+    tsv::flat_distance_kernel<NCH><<<grid, 256, smem, idx->vs>>>(idx->hnsw, P, total);
 }
 
 tsgpu_status run_flat(tsgpu_index* idx, const tsv::FlatParams& P, unsigned long long total) {
@@ -622,12 +634,13 @@ struct VecStage {
 
 tsgpu_status run_vector_stage(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& pl, const float* qvecs,
                               const tsgpu_vec_params* vp, uint32_t k, VecStage& vs) {
-    cudaStream_t st = idx->stream;
+    cudaStream_t st = idx->vs;
     const uint32_t nq = pl.nq, dim = idx->hnsw.dim;
     vs.k = k;
     // decide paths
-    std::vector<uint8_t> is_flat(nq, 0);
-    std::vector<unsigned long long> foff(nq + 1, 0);
+    std::vector<uint8_t>& is_flat = idx->tmp_is_flat;
+    std::vector<unsigned long long>& foff = idx->tmp_foff;
+    is_flat.assign(nq, 0); foff.assign((size_t) nq + 1, 0);
     for(uint32_t q = 0; q < nq; q++) {
         const bool filter_given = b->q_filter[q] != -1;
         if(filter_given && pl.q_filter_n[q] < vp->flat_search_cutoff) is_flat[q] = 1;
@@ -653,7 +666,6 @@ tsgpu_status run_vector_stage(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan&
         if(is_flat[q] && pl.q_filter_n[q])
             CU(cudaMemcpyAsync(base + o_fi + foff[q] * 4, pl.q_filter_ids[q], pl.q_filter_n[q] * 4, cudaMemcpyDeviceToDevice, st));
     }
-    CU(cudaStreamSynchronize(st));       // host vectors above are pageable
     vs.d_is_flat = base + o_if;
     vs.flat_off = reinterpret_cast<const unsigned long long*>(base + o_fo);
     vs.flat_ids = reinterpret_cast<const uint32_t*>(base + o_fi);
@@ -705,7 +717,11 @@ tsgpu_status tsgpu_index_create(uint32_t n_docs, int device, tsgpu_index** out) 
     idx->device = device; idx->n_docs = n_docs; idx->n_sms = prop.multiProcessorCount;
     idx->ixdev.n_docs = n_docs;
     if(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete idx; return fail(TSGPU_ERR_CUDA, "stream create failed"); }
+    cudaStreamCreateWithFlags(&idx->stream2, cudaStreamNonBlocking);
+    idx->vs = idx->stream;
     for(auto& e: idx->ev) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&idx->evA, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&idx->evB, cudaEventDisableTiming);
     *out = idx;
     return TSGPU_OK;
 }
@@ -723,6 +739,9 @@ void tsgpu_index_destroy(tsgpu_index* idx) {
     for(auto* b: bufs) b->release();
     idx->h_stage.release();
     for(auto& e: idx->ev) if(e) cudaEventDestroy(e);
+    if(idx->evA) cudaEventDestroy(idx->evA);
+    if(idx->evB) cudaEventDestroy(idx->evB);
+    if(idx->stream2) cudaStreamDestroy(idx->stream2);
     cudaStreamDestroy(idx->stream);
     delete idx;
 }
@@ -1018,12 +1037,14 @@ tsgpu_status tsgpu_knn_batch(tsgpu_index* idx, const float* queries, uint32_t nq
         }
     }
     KnnDeviceOut o{};
+    idx->vs = idx->stream; idx->knn_blocks_per_sm = 7;
     s = run_knn(idx, reinterpret_cast<const float*>(base), nq, k, ef, q_bitmap, {}, {}, {}, o); if(s) return s;
     CU(cudaMemcpyAsync(out_dist, o.dist, (size_t) nq * k * 4, cudaMemcpyDefault, st));
     CU(cudaMemcpyAsync(out_labels, o.labels, (size_t) nq * k * 4, cudaMemcpyDefault, st));
     CU(cudaMemcpyAsync(out_n, o.n, (size_t) nq * 4, cudaMemcpyDefault, st));
     idx->stats.d2h_bytes += (size_t) nq * k * 8 + (size_t) nq * 4;
-    return end_call(idx, false, true);
+    s = end_call(idx, false, true); if(s) return s;
+    return finish_knn(idx);
 }
 
 tsgpu_status tsgpu_flat_distances(tsgpu_index* idx, const float* query, const uint32_t* ids, size_t n, float* out_dist) {
@@ -1050,6 +1071,7 @@ tsgpu_status tsgpu_flat_distances(tsgpu_index* idx, const float* query, const ui
     FP.queries = reinterpret_cast<const float*>(base); FP.ids = reinterpret_cast<const uint32_t*>(base + o_ids);
     FP.q_off = reinterpret_cast<const unsigned long long*>(base + o_off); FP.nq = 1;
     FP.out_dist = reinterpret_cast<float*>(base + o_d);
+    idx->vs = st;
     CU(cudaEventRecord(idx->ev[3], st));
     s = run_flat(idx, FP, n); if(s) return s;
     CU(cudaEventRecord(idx->ev[4], st));
@@ -1072,14 +1094,26 @@ static tsgpu_status vec_or_hybrid(tsgpu_index* idx, const tsgpu_kw_batch* b, con
     cudaStream_t st = idx->stream;
     const uint32_t nq = pl.nq;
     KwDeviceOut kwo{};
-    if(hybrid) { s = run_keyword(idx, pl, std::max(kv_stride, pl.KMAX), kwo); if(s) return s; }
     // k as in src/index.cpp:3646 (wildcard) and :4061-4063 (hybrid)
     const uint32_t k = hybrid ? (vp->k == 0 ? std::max<uint32_t>(vp->fetch_size, 100) : vp->k)
                               : (vp->k == 0 ? std::max<uint32_t>(vp->k, vp->fetch_size) : vp->k);
     if(k == 0) return fail(TSGPU_ERR_INVALID, "k resolves to 0 (set k or fetch_size)");
     if(hybrid && k > 1024) return fail(TSGPU_ERR_CAPACITY, "hybrid k must be <= 1024");
+    // The vector stage and the keyword kernels are independent until the fusion: issue the vector stage on its own
+    // stream (after the filter bitmaps built by upload_kw_plan) with a reduced residency so keyword CTAs co-run, and
+    // let the long latency-bound tail of the graph walk hide under the keyword kernels.
     VecStage vs;
+    if(hybrid) {
+        CU(cudaEventRecord(idx->evA, st));
+        CU(cudaStreamWaitEvent(idx->stream2, idx->evA, 0));
+        idx->vs = idx->stream2; idx->knn_blocks_per_sm = 3;
+    } else { idx->vs = st; idx->knn_blocks_per_sm = 7; }
     s = run_vector_stage(idx, b, pl, qvecs, vp, k, vs); if(s) return s;
+    if(hybrid) {
+        CU(cudaEventRecord(idx->evB, idx->stream2));
+        s = run_keyword(idx, pl, std::max(kv_stride, pl.KMAX), kwo); if(s) return s;
+        CU(cudaStreamWaitEvent(st, idx->evB, 0));
+    }
     // final assembly
     const size_t kv_bytes = (size_t) nq * kv_stride * sizeof(KVOut);
     CU(idx->d_out.reserve(kv_bytes + (size_t) nq * 8 + 64));
@@ -1128,6 +1162,7 @@ static tsgpu_status vec_or_hybrid(tsgpu_index* idx, const tsgpu_kw_batch* b, con
     CU(cudaMemcpyAsync(out_found, d_found, (size_t) nq * 4, cudaMemcpyDefault, st));
     idx->stats.d2h_bytes += kv_bytes + (size_t) nq * 8;
     s = end_call(idx, hybrid, true);
+    if(!s) s = finish_knn(idx);
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     idx->stats.ms_fuse = ms; idx->stats.ms_kernels += ms;
