@@ -166,6 +166,12 @@ tsgpu_status tsgpu_phrase_matches(tsgpu_index* idx, uint32_t field, const uint32
 tsgpu_status tsgpu_keyword_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, tsgpu_kv* out_kv,
                                         uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found);
 
+/* Index::search_wildcard (src/index.cpp:6616-6800), `q=*`: every id of the query's filter (all seq_ids < n_docs when it
+ * has none) minus the exclusion list is given sort scores (text-match clause = 100) and goes through the Topster.
+ * The combinations of `b` are ignored. Same outputs as tsgpu_keyword_search_batch; query_index is 0. */
+tsgpu_status tsgpu_wildcard_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, tsgpu_kv* out_kv, uint32_t kv_stride,
+                                         uint32_t* out_count, uint32_t* out_found);
+
 /* VectorIndex::searchKnn: vecdex->searchKnnCloserFirst(q, k, ef, &VectorFilterFunctor) (src/index.cpp:3384-3386),
  * batched. queries [nq*dim] (already normalised for cosine). q_filter as in tsgpu_kw_batch (inline slots refer to
  * filter_off/filter_ids). Outputs [nq*k] closest first; out_n[q] valid entries. */

@@ -917,6 +917,37 @@ int tso_keyword_search_batch(void* idx, const tso_kw_batch* b, tso_kv* out_kv, u
     return 0;
 }
 
+int tso_wildcard_search_batch(void* idx, const tso_kw_batch* b, tso_kv* out_kv, uint32_t kv_stride,
+                              uint32_t* out_count, uint32_t* out_found, uint32_t n_threads) {
+    const Index& ix = *(Index*) idx;
+    parallel_for(b->n_queries, n_threads, [&](uint32_t q) {
+        Topster t(std::max<uint32_t>(1, b->q_topk[q]));
+        SortSpec S = sort_spec_of(*b, q);
+        const uint32_t* excl = b->excl_ids + b->q_excl_off[q];
+        const size_t n_excl = b->q_excl_off[q + 1] - b->q_excl_off[q];
+        const int32_t fs = b->q_filter[q];
+        const uint32_t* filt = nullptr; size_t n = ix.n_docs;
+        if(fs >= 0) { filt = b->filter_ids + b->filter_off[fs]; n = (size_t) (b->filter_off[fs + 1] - b->filter_off[fs]); }
+        uint32_t found = 0;
+        for(size_t i = 0; i < n; i++) {
+            const uint32_t seq_id = filt ? filt[i] : (uint32_t) i;
+            if(n_excl && std::binary_search(excl, excl + n_excl, seq_id)) continue;      // get_n_ids skips excluded ids
+            tso_kv kv{};
+            int64_t msi = -1;
+            compute_sort_scores(ix, S, seq_id, 100, kv.scores, msi, 0);                  // src/index.cpp:6727-6729
+            kv.key = seq_id; kv.distinct_key = seq_id; kv.query_index = 0;
+            kv.match_score_index = (int8_t) msi;
+            kv.vector_distance = -1.0f;
+            kv.text_match_score = msi >= 0 ? kv.scores[msi] : 0;
+            t.add(kv);
+            found++;
+        }
+        write_topster(t, out_kv + (size_t) q * kv_stride, kv_stride, &out_count[q]);
+        out_found[q] = found;
+    });
+    return 0;
+}
+
 uint32_t tso_topster_run(uint32_t capacity, const tso_kv* in, uint32_t n, tso_kv* out) {
     Topster t(capacity);
     for(uint32_t i = 0; i < n; i++) t.add(in[i]);

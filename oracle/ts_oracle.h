@@ -131,6 +131,13 @@ size_t tso_keyword_combo(void* idx, const tso_kw_batch* b, uint32_t q, uint32_t 
 int tso_keyword_search_batch(void* idx, const tso_kw_batch* b, tso_kv* out_kv, uint32_t kv_stride,
                              uint32_t* out_count, uint32_t* out_found, uint32_t n_threads);
 
+/* ---- wildcard query (q=*): Index::search_wildcard (src/index.cpp:6616-6800): every filter id (all docs when the query
+ * has no filter) minus the exclusion list gets sort scores with text-match value 100 and goes into the Topster.
+ * Combinations of the batch are ignored. query_index is left 0 (the reference reads searched_queries.size() from worker
+ * threads while the enqueuing thread is still appending to it, i.e. it is not deterministic there). */
+int tso_wildcard_search_batch(void* idx, const tso_kw_batch* b, tso_kv* out_kv, uint32_t kv_stride,
+                              uint32_t* out_count, uint32_t* out_found, uint32_t n_threads);
+
 /* ---- Topster fed with an explicit stream (pins include/topster.h against test/topster_test.cpp) */
 uint32_t tso_topster_run(uint32_t capacity, const tso_kv* in, uint32_t n, tso_kv* out);
 

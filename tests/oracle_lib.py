@@ -58,6 +58,8 @@ def oracle():
                                         C.c_size_t, u64p]
         L.tso_keyword_search_batch.argtypes = [C.c_void_p, C.POINTER(KwBatchStruct), C.c_void_p, C.c_uint32, u32p, u32p,
                                                C.c_uint32]
+        L.tso_wildcard_search_batch.argtypes = [C.c_void_p, C.POINTER(KwBatchStruct), C.c_void_p, C.c_uint32, u32p, u32p,
+                                                C.c_uint32]
         L.tso_topster_run.restype = C.c_uint32
         L.tso_topster_run.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         L.tso_phrase_matches.restype = C.c_size_t
@@ -223,6 +225,9 @@ class OracleIndex:
 
     def keyword_search(self, b: KwBatch, stride: int = 256, threads: int = 1):
         return self._run(self.L.tso_keyword_search_batch, b, stride, threads)
+
+    def wildcard_search(self, b: KwBatch, stride: int = 256, threads: int = 1):
+        return self._run(self.L.tso_wildcard_search_batch, b, stride, threads)
 
     def hybrid_search(self, b: KwBatch, qvecs: np.ndarray, vp: VecParamsStruct, stride: int = 256, threads: int = 1):
         qv = np.ascontiguousarray(qvecs, np.float32)

@@ -246,3 +246,25 @@ def test_hybrid_search_matches_oracle(vec_coll):
     kv, cnt, found = gi.hybrid_search(b2, qv[:40], S.vec_params(k=25, ef=25, fetch_size=10), 256)
     okv, ocnt, ofound = oi.hybrid_search(b2, qv[:40], S.vec_params(k=25, ef=25, fetch_size=10), 256)
     assert_kv_equal(kv, cnt, found, okv, ocnt, ofound)
+
+
+def test_wildcard_search_matches_oracle(coll):
+    # Index::search_wildcard: q=* over the filter ids / all docs, exclusion list, sort clauses incl. ASC + missing-first
+    n_docs, fds, flats, pts, gi, oi = coll
+    rng = np.random.default_rng(61)
+    filters = [np.unique(rng.integers(0, n_docs, 1700)).astype(np.uint32), np.arange(3, n_docs, 11, dtype=np.uint32), np.zeros(0, np.uint32)]
+    h = gi.filter_create(filters[0])
+    qs, qso = [], []
+    for i in range(24):
+        sort = [((S.SORT_NUMERIC, 0, -1, 1), (S.SORT_SEQ_ID, -1, 1, 0), (S.SORT_NONE, -1, 1, 0)),
+                ((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_NUMERIC, 0, 1, 0), (S.SORT_SEQ_ID, -1, -1, 0)),
+                ((S.SORT_SEQ_ID, -1, 1, 0), (S.SORT_NONE, -1, 1, 0), (S.SORT_NONE, -1, 1, 0))][i % 3]
+        kw = dict(topk=int(rng.choice([1, 10, 250, 1000])), sort=sort, excl=np.unique(rng.integers(0, n_docs, 25)).tolist() if i % 4 == 0 else ())
+        f_inline = [-1, 0, 1, 2][i % 4]
+        qs.append(S.Query([], filter=(h if f_inline == 0 and i % 8 == 1 else f_inline), **kw))
+        qso.append(S.Query([], filter=f_inline, **kw))
+    b, bo = S.KwBatch(qs, [0], filters), S.KwBatch(qso, [0], filters)
+    kv, cnt, found = gi.wildcard_search(b, 1024)
+    okv, ocnt, ofound = oi.wildcard_search(bo, 1024)
+    assert_kv_equal(kv, cnt, found, okv, ocnt, ofound, check_query_index=False)
+    assert int(found.max()) == n_docs or int(found.max()) >= n_docs - 25

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libtsgpu.so")
 EXPORTS = [
     "tsgpu_last_error", "tsgpu_device_count", "tsgpu_index_create", "tsgpu_index_destroy", "tsgpu_index_load_field",
     "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy",
-    "tsgpu_intersect", "tsgpu_phrase_matches", "tsgpu_keyword_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
+    "tsgpu_intersect", "tsgpu_phrase_matches", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
     "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats",
 ]
 
@@ -51,6 +51,7 @@ def lib():
         L.tsgpu_intersect.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.tsgpu_phrase_matches.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, C.c_size_t, u32p, C.POINTER(C.c_size_t)]
         L.tsgpu_keyword_search_batch.argtypes = [vp, C.POINTER(KwBatchStruct), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.tsgpu_wildcard_search_batch.argtypes = [vp, C.POINTER(KwBatchStruct), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.tsgpu_knn_batch.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, i32p, C.c_uint32, u64p, u32p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
         L.tsgpu_flat_distances.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -179,6 +180,12 @@ class GpuIndex:
         kv, cnt, found = self._outs(b.n_queries, stride, out)
         s = bstruct if bstruct is not None else b.struct()
         _ck(self.L.tsgpu_keyword_search_batch(self.h, C.byref(s), _addr(kv), stride, _addr(cnt), _addr(found)))
+        return kv, cnt, found
+
+    def wildcard_search(self, b: KwBatch, stride: int = 256, out=None, bstruct=None):
+        kv, cnt, found = self._outs(b.n_queries, stride, out)
+        s = bstruct if bstruct is not None else b.struct()
+        _ck(self.L.tsgpu_wildcard_search_batch(self.h, C.byref(s), _addr(kv), stride, _addr(cnt), _addr(found)))
         return kv, cnt, found
 
     def vector_search(self, b: KwBatch, qvecs, vp: VecParamsStruct, stride: int = 256, out=None, bstruct=None):

@@ -335,6 +335,11 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
                             const uint32_t c = t ? c1 : c0;
                             const bool ok = t ? ok1 : ok0;
                             if(n_res < ef || lowerBound > d) {
+                                {   // the link row of a pushed candidate will be needed when it is expanded: start pulling it into L2
+                                    const char* lp = reinterpret_cast<const char*>(g.links0 + (size_t) c * L0);
+                                    asm volatile("prefetch.global.L2 [%0];" :: "l"(lp));
+                                    asm volatile("prefetch.global.L2 [%0];" :: "l"(lp + 128));
+                                }
                                 if(n_cs < kCandSmem) heap_push_min(cand_s, n_cs, cand_key(d, c));
                                 else if(n_cg < P.cand_cap) heap_push_min(cand, n_cg, cand_key(d, c));
                                 else *P.error = 1;

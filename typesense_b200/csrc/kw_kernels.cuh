@@ -643,6 +643,104 @@ kw_final_kernel(const __grid_constant__ FinalParams P) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Index::search_wildcard (src/index.cpp:6616-6800): the reference partitions the filter ids over `concurrency` threads,
+// each with its own Topster, then aggregates. Here a unit is a run of 128-id tiles of the query's id set (its filter
+// ids, or the id range [0, n_docs) when it has no filter); units feed the same pool / merge / final kernels as the
+// keyword path (pseudo-combination == query).
+struct WcParams {
+    const QDesc* qd;
+    const UDesc* ud;                   // ud.combo == query index
+    const uint32_t* const* q_ids;      // [nq] device id arrays or nullptr (= identity)
+    const uint32_t* q_nids;            // [nq]
+    int64_t* pool_s0; int64_t* pool_s1; int64_t* pool_s2;
+    uint32_t* pool_key; uint16_t* pool_cmb;
+    uint32_t* unit_cnt; uint32_t* combo_matches;
+    long long* q_thr;
+    uint32_t KP;
+};
+
+__global__ void __launch_bounds__(kThreads)
+wc_unit_kernel(const __grid_constant__ WcParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t KP = P.KP, N2 = 2 * KP;
+    TopBuf tb;
+    tb.s0 = reinterpret_cast<int64_t*>(smem_raw);
+    tb.s1 = tb.s0 + N2; tb.s2 = tb.s1 + N2;
+    tb.key = reinterpret_cast<uint32_t*>(tb.s2 + N2);
+    tb.cmb = nullptr; tb.vd = nullptr;
+    __shared__ uint32_t s_warp[8];
+    __shared__ int64_t thr[3];
+    __shared__ uint32_t thr_key, s_n, s_have_thr, s_matches;
+    const uint32_t tid = threadIdx.x;
+    const UDesc ud = P.ud[blockIdx.x];
+    const uint32_t q = ud.combo;
+    const QDesc qd = P.qd[q];
+    const uint32_t K = qd.topk;
+    const uint32_t* ids = P.q_ids[q];
+    const uint32_t n_ids = P.q_nids[q];
+    SortSpec SS;
+    for(int i = 0; i < 3; i++) { SS.type[i] = qd.sort_type[i]; SS.order[i] = qd.sort_order[i]; SS.missing_first[i] = qd.missing_first[i]; SS.col[i] = qd.sort_col[i]; }
+    long long* const gthr_p = P.q_thr + q;
+    if(tid == 0) { s_n = 0; s_have_thr = 0; s_matches = 0; }
+    __syncthreads();
+    for(uint32_t tile = ud.tile_begin; tile < ud.tile_end; tile++) {
+        const uint32_t i = tile * kThreads + tid;
+        bool keep = i < n_ids;
+        uint32_t id = 0;
+        int64_t sc[3] = {0, 0, 0};
+        if(keep) {
+            id = ids ? __ldg(ids + i) : i;
+            if(qd.n_excl && excluded(qd.excl, qd.n_excl, id)) keep = false;
+        }
+        const bool matched = keep;
+        if(keep) {
+            compute_sort_scores(SS, id, 100, 0.0f, sc);                       // src/index.cpp:6727-6729
+            const long long gthr = *reinterpret_cast<volatile long long*>(gthr_p);
+            keep = sc[0] >= gthr;
+            if(keep && s_have_thr) keep = kv_greater(sc[0], sc[1], sc[2], id, thr[0], thr[1], thr[2], thr_key);
+        }
+        uint32_t m_total, a_total;
+        cta_rank(matched, s_warp, &m_total);
+        const uint32_t arank = cta_rank(keep, s_warp, &a_total);
+        const uint32_t n0 = s_n;
+        if(keep) { const uint32_t slot = n0 + arank; tb.s0[slot] = sc[0]; tb.s1[slot] = sc[1]; tb.s2[slot] = sc[2]; tb.key[slot] = id; }
+        __syncthreads();
+        if(tid == 0) { s_n = n0 + a_total; s_matches += m_total; }
+        __syncthreads();
+        if(s_n + kThreads > N2) {
+            const uint32_t n = s_n;
+            tb_fill_invalid(tb, n, N2);
+            __syncthreads();
+            tb_sort<false>(tb, N2);
+            if(tid == 0) {
+                const uint32_t nn = n < K ? n : K;
+                s_n = nn;
+                if(nn == K) {
+                    s_have_thr = 1; thr[0] = tb.s0[K - 1]; thr[1] = tb.s1[K - 1]; thr[2] = tb.s2[K - 1]; thr_key = tb.key[K - 1];
+                    atomicMax(gthr_p, (long long) tb.s0[K - 1]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    const uint32_t n = s_n;
+    uint32_t nn = n;
+    if(n > K) {
+        tb_fill_invalid(tb, n, N2);
+        __syncthreads();
+        tb_sort<false>(tb, N2);
+        nn = K;
+    }
+    for(uint32_t i = tid; i < nn; i += kThreads) {
+        const uint32_t o = ud.out_off + i;
+        P.pool_s0[o] = tb.s0[i]; P.pool_s1[o] = tb.s1[i]; P.pool_s2[o] = tb.s2[i]; P.pool_key[o] = tb.key[i];
+        P.pool_cmb[o] = 0;
+    }
+    if(tid == 0) { P.unit_cnt[blockIdx.x] = nn; if(s_matches) atomicAdd(P.combo_matches + q, s_matches); }
+}
+
 // found = |union of result ids| for queries with several combinations (the reference ORs id_buff into
 // all_result_ids, src/index.cpp:5081-5090)
 __global__ void __launch_bounds__(256)

@@ -15,12 +15,12 @@
 //   positions[]        u32  raw reference offsets
 // Dense lists (df >= n_docs/64) additionally get a bitmap over seq_ids plus a rank directory (one running popcount
 // per 512 bits): membership of a candidate is ONE bit test in an L2-resident bitmap instead of a skip-index + block
-// search, and the posting index of a hit (needed to reach its offsets) is directory + popcounts. At the 10 M-doc
+// search, and the posting index of a hit (needed to reach its offsets) is directory + at most 4 popcounts. At the 10 M-doc
 // bench shape ~50 tokens are dense (62 MB of bitmaps) and they receive most of the probes, because the driver is
 // always the shortest list of a combination.
 //   list_dense[L]      u32  dense slot of list l or kNone
 //   dense_bits[]       u32  slot s owns words [s*dense_words, (s+1)*dense_words)
-//   dense_rank[]       u32  slot s owns [s*dense_groups, ...): number of set bits before 512-bit group g
+//   dense_rank[]       u32  slot s owns [s*dense_groups, ...): number of set bits before 128-bit group g
 #pragma once
 #include <stdint.h>
 #include "score_device.cuh"
@@ -47,7 +47,7 @@ struct DevField {
     const uint32_t* dense_bits;
     const uint32_t* dense_rank;
     uint32_t dense_words;       // words per bitmap (multiple of 16)
-    uint32_t dense_groups;      // dense_words / 16
+    uint32_t dense_groups;      // dense_words / 4 (one directory entry per 128 bits)
 };
 
 constexpr uint32_t kDenseHit = 0xFFFFFFFEu;   // probe marker: member of a dense list, rank not computed yet
@@ -55,25 +55,25 @@ constexpr uint32_t kDenseHit = 0xFFFFFFFEu;   // probe marker: member of a dense
 TS_HD bool dense_test(const DevField& f, uint32_t slot, uint32_t id) {
     return (f.dense_bits[(size_t) slot * f.dense_words + (id >> 5)] >> (id & 31)) & 1u;
 }
-// list-local posting index of a member id of dense slot `slot`
+// list-local posting index of a member id of dense slot `slot`: directory entry + popcount of one 16-byte group
 TS_HD uint32_t dense_rank_of(const DevField& f, uint32_t slot, uint32_t id) {
-    const uint32_t w = id >> 5, g = w >> 4;
-    const uint32_t* bits = f.dense_bits + (size_t) slot * f.dense_words + ((size_t) g << 4);
+    const uint32_t w = id >> 5, g = w >> 2, wi = w & 3;
+    const uint32_t* bits = f.dense_bits + (size_t) slot * f.dense_words + ((size_t) g << 2);
     uint32_t r = f.dense_rank[(size_t) slot * f.dense_groups + g];
-    const uint32_t wi = w & 15;
-    for(uint32_t i = 0; i < wi; i++) {
 #if defined(__CUDA_ARCH__)
-        r += __popc(bits[i]);
+    const uint4 v = *reinterpret_cast<const uint4*>(bits);
+    const uint32_t b0 = v.x, b1 = v.y, b2 = v.z, b3 = v.w;
+#define TS_POPC(x) __popc(x)
 #else
-        r += (uint32_t) __builtin_popcount(bits[i]);
+    const uint32_t b0 = bits[0], b1 = bits[1], b2 = bits[2], b3 = bits[3];
+#define TS_POPC(x) ((uint32_t) __builtin_popcount(x))
 #endif
-    }
-    const uint32_t part = bits[wi] & ((1u << (id & 31)) - 1u);
-#if defined(__CUDA_ARCH__)
-    r += __popc(part);
-#else
-    r += (uint32_t) __builtin_popcount(part);
-#endif
+    const uint32_t m = (1u << (id & 31)) - 1u;
+    r += TS_POPC(wi == 0 ? (b0 & m) : b0);
+    if(wi >= 1) r += TS_POPC(wi == 1 ? (b1 & m) : b1);
+    if(wi >= 2) r += TS_POPC(wi == 2 ? (b2 & m) : b2);
+    if(wi >= 3) r += TS_POPC(b3 & m);
+#undef TS_POPC
     return r;
 }
 

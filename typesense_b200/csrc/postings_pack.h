@@ -24,7 +24,7 @@ inline void pack_dense(uint32_t n_lists, const uint64_t* list_off, const uint32_
                        PackedField& out) {
     out.list_dense.assign(n_lists ? n_lists : 1, tsdev::kNone);
     out.dense_words = (((n_docs + 31) / 32) + 15) & ~15u;
-    out.dense_groups = out.dense_words / 16;
+    out.dense_groups = out.dense_words / 4;
     out.n_dense = 0;
     if(min_df == 0) min_df = 1;
     for(uint32_t l = 0; l < n_lists; l++) if(list_off[l + 1] - list_off[l] >= min_df) out.list_dense[l] = out.n_dense++;
@@ -39,7 +39,7 @@ inline void pack_dense(uint32_t n_lists, const uint64_t* list_off, const uint32_
         uint32_t run = 0;
         for(uint32_t g = 0; g < out.dense_groups; g++) {
             rk[g] = run;
-            for(int i = 0; i < 16; i++) run += (uint32_t) __builtin_popcount(bits[(size_t) g * 16 + i]);
+            for(int i = 0; i < 4; i++) run += (uint32_t) __builtin_popcount(bits[(size_t) g * 4 + i]);
         }
     }
 }

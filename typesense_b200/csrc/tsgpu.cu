@@ -146,6 +146,8 @@ struct KwPlan {
     std::vector<std::vector<MDesc>> levels;   // intermediate merge levels (only queries with many units)
     std::vector<MDesc*> d_levels;
     uint32_t n_units_total = 0;           // level-0 units + merge outputs
+    bool wildcard = false;                // units walk the filter ids (Index::search_wildcard) instead of posting lists
+    std::vector<uint32_t> q_nids;         // wildcard: ids per query
     size_t pool_slots = 0;
     // device views (valid after upload)
     QDesc* d_qd = nullptr; CDesc* d_cd = nullptr; UDesc* d_ud = nullptr; uint32_t* d_multi_q = nullptr;
@@ -156,12 +158,13 @@ struct KwPlan {
     std::vector<const uint32_t*> q_excl_dev;
 };
 
-tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_combos, KwPlan& pl) {
+tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_combos, KwPlan& pl, bool wildcard = false) {
     if(!b) return fail(TSGPU_ERR_INVALID, "null batch");
     const uint32_t nq = b->n_queries, F = b->n_fields;
     if(with_combos && (F == 0 || F > TSGPU_MAX_FIELDS)) return fail(TSGPU_ERR_CAPACITY, "n_fields must be 1.." + std::to_string(TSGPU_MAX_FIELDS));
     for(uint32_t f = 0; f < F; f++) if(b->field_ids[f] >= idx->fields.size()) return fail(TSGPU_ERR_INVALID, "field id out of range");
     pl.nq = nq; pl.F = F; pl.nc = with_combos ? b->n_combos : 0;
+    pl.wildcard = wildcard;
     for(uint32_t f = 0; f < F && f < (uint32_t) kMaxFieldSlots; f++) pl.field_ids[f] = b->field_ids[f];
     pl.qd.assign(nq, QDesc{});
     pl.cd.assign(pl.nc, CDesc{});
@@ -266,6 +269,23 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
                 pl.ud.push_back(u);
             }
         }
+        if(wildcard) {
+            // id set of the query: its filter ids, or every seq_id when it has no filter (src/index.cpp:3738-3745)
+            uint64_t n_ids = idx->n_docs;
+            const int32_t wfs = b->q_filter[q];
+            if(wfs >= 0 && (uint32_t) wfs < b->n_filters) n_ids = b->filter_off[wfs + 1] - b->filter_off[wfs];
+            else if(wfs <= -2 && (size_t) (-(wfs + 2)) < idx->filters.size()) n_ids = idx->filters[(size_t) (-(wfs + 2))].n;
+            pl.q_nids.push_back((uint32_t) n_ids);
+            qd.combo_begin = q; qd.combo_end = q + 1;
+            const uint32_t tiles = (uint32_t) ((n_ids + kThreads - 1) / kThreads), wtpu = 64;
+            for(uint32_t t = 0; t < tiles; t += wtpu) {
+                UDesc u;
+                u.combo = q; u.tile_begin = t; u.tile_end = std::min(tiles, t + wtpu);
+                u.out_off = (uint32_t) pl.pool_slots;
+                pl.pool_slots += K;
+                pl.ud.push_back(u);
+            }
+        }
         qd.unit_end = (uint32_t) pl.ud.size();
         q_units0.push_back({qd.unit_begin, qd.unit_end});
         if(combos_with_tiles > 1) pl.multi_q.push_back(q);
@@ -276,6 +296,7 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
             if(h >= idx->filters.size() || !idx->filters[h].live) return fail(TSGPU_ERR_INVALID, "unknown filter handle");
         }
     }
+    if(wildcard) pl.nc = nq;                // one pseudo-combination per query carries its match count
     pl.n_units = (uint32_t) pl.ud.size();
     // queries with more than kMergeFan units get intermediate merge levels (fan-in kMergeFan) so the per-query final
     // merge stays short and the work of a heavy query is spread over many CTAs
@@ -418,7 +439,27 @@ tsgpu_status run_keyword(tsgpu_index* idx, KwPlan& pl, uint32_t kv_stride, KwDev
     uint32_t* pk = reinterpret_cast<uint32_t*>(p2 + pl.pool_slots);
     uint16_t* pc = reinterpret_cast<uint16_t*>(pk + pl.pool_slots);
     CU(cudaEventRecord(idx->ev[1], st));
-    if(pl.n_units) {
+    if(pl.n_units && pl.wildcard) {
+        // per-query id arrays
+        std::vector<const uint32_t*> qids(nq);
+        for(uint32_t q = 0; q < nq; q++) qids[q] = pl.q_filter_ids[q];
+        const size_t tb = (size_t) nq * 12 + 64;
+        CU(idx->d_small.reserve(tb));
+        unsigned char* sb = idx->d_small.as<unsigned char>();
+        CU(cudaMemcpy(sb, qids.data(), (size_t) nq * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(sb + (size_t) nq * 8, pl.q_nids.data(), (size_t) nq * 4, cudaMemcpyHostToDevice));
+        idx->stats.h2d_bytes += (size_t) nq * 12;
+        WcParams P{};
+        P.qd = pl.d_qd; P.ud = pl.d_ud;
+        P.q_ids = reinterpret_cast<const uint32_t* const*>(sb); P.q_nids = reinterpret_cast<const uint32_t*>(sb + (size_t) nq * 8);
+        P.pool_s0 = p0; P.pool_s1 = p1; P.pool_s2 = p2; P.pool_key = pk; P.pool_cmb = pc;
+        P.unit_cnt = pl.d_unit_cnt; P.combo_matches = pl.d_combo_matches; P.q_thr = pl.d_q_thr; P.KP = pl.KP;
+        const size_t smem = (size_t) 2 * pl.KP * 28;
+        CU(cudaFuncSetAttribute(wc_unit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024)));
+        wc_unit_kernel<<<pl.n_units, kThreads, smem, st>>>(P);
+        idx->stats.launches_total++;
+        CU(cudaGetLastError());
+    } else if(pl.n_units) {
         KwParams P{};
         P.qd = pl.d_qd; P.cd = pl.d_cd; P.ud = pl.d_ud;
         P.pool_s0 = p0; P.pool_s1 = p1; P.pool_s2 = p2; P.pool_key = pk; P.pool_cmb = pc;
@@ -987,6 +1028,26 @@ tsgpu_status tsgpu_keyword_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* 
     idx->stats.d2h_bytes += (size_t) pl.nq * kv_stride * sizeof(KVOut) + (size_t) pl.nq * 8;
     s = end_call(idx, true, false); if(s) return s;
     return fetch_kw_stats(idx, pl);
+}
+
+tsgpu_status tsgpu_wildcard_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, tsgpu_kv* out_kv, uint32_t kv_stride,
+                                         uint32_t* out_count, uint32_t* out_found) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!b || !out_kv || !out_count || !out_found || kv_stride == 0) return fail(TSGPU_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    begin_call(idx);
+    KwPlan pl;
+    s = build_kw_plan(idx, b, false, pl, true); if(s) return s;
+    if(pl.nq == 0) return end_call(idx, false, false);
+    s = upload_kw_plan(idx, b, pl); if(s) return s;
+    KwDeviceOut o{};
+    s = run_keyword(idx, pl, kv_stride, o); if(s) return s;
+    cudaStream_t st = idx->stream;
+    CU(cudaMemcpyAsync(out_kv, o.kv, (size_t) pl.nq * kv_stride * sizeof(KVOut), cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(out_count, o.count, (size_t) pl.nq * 4, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(out_found, o.found, (size_t) pl.nq * 4, cudaMemcpyDefault, st));
+    idx->stats.d2h_bytes += (size_t) pl.nq * kv_stride * sizeof(KVOut) + (size_t) pl.nq * 8;
+    return end_call(idx, true, false);
 }
 
 tsgpu_status tsgpu_knn_batch(tsgpu_index* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
