@@ -1,0 +1,114 @@
+"""TEST INFRASTRUCTURE: the host-side control flow that stays on the host in the reference — ASCII tokenising
+(src/tokenizer.cpp:232-290), token lookup (art_search) and the drop-tokens loop of Index::search
+(src/index.cpp:3920-4017) — restated in Python on top of a pluggable backend (CPU oracle or the tsgpu C-ABI), so the
+reference's END-TO-END ranking expectations (test/collection_test.cpp) can be replayed against both."""
+from __future__ import annotations
+
+import json
+from typing import Dict, List, Sequence
+
+import numpy as np
+
+from typesense_b200 import structs as S
+
+
+def tokenize(text: str) -> List[str]:
+    """alnum kept and lower-cased; space / newline split; every other ASCII char is dropped, not a boundary."""
+    out, cur = [], []
+    for ch in text:
+        if ch.isalnum() and ord(ch) < 128:
+            cur.append(ch.lower())
+        elif ch in " \n":
+            if cur:
+                out.append("".join(cur)[:100])
+            cur = []
+    if cur:
+        out.append("".join(cur)[:100])
+    return out
+
+
+class Collection:
+    """String fields (default: `title`) + numeric `points`; seq_id = insertion order (for documents.jsonl a dummy doc
+    first, as the reference's fixture does, so seq_id == line number)."""
+
+    def __init__(self, docs: Sequence[dict], fields: Sequence[str] = ("title",)):
+        self.docs = list(docs)
+        self.fields = list(fields)
+        self.vocabs: List[Dict[str, int]] = []
+        self.flats: List[S.FlatField] = []
+        for fname in self.fields:
+            vocab: Dict[str, int] = {}
+            per_tok: List[list] = []
+            for sid, d in enumerate(self.docs):
+                toks = tokenize(d.get(fname, ""))
+                t2o: Dict[str, list] = {}
+                for i, t in enumerate(toks):
+                    t2o.setdefault(t, []).append(i + 1)
+                if toks:
+                    t2o[toks[-1]].append(0)           # src/index.cpp:1341-1348
+                for t, offs in t2o.items():
+                    if t not in vocab:
+                        vocab[t] = len(per_tok)
+                        per_tok.append([])
+                    per_tok[vocab[t]].append((sid, offs))
+            self.vocabs.append(vocab)
+            self.flats.append(S.FlatField.from_postings(per_tok))
+        self.vocab, self.flat = self.vocabs[0], self.flats[0]
+        self.points = np.asarray([d["points"] for d in self.docs], np.int64)
+        self.n_docs = len(self.docs)
+
+    @staticmethod
+    def from_jsonl(path: str) -> "Collection":
+        docs = [{"points": 10, "title": "z"}]
+        docs += [json.loads(l) for l in open(path) if l.strip()]
+        return Collection(docs)
+
+
+def search(backend, coll: Collection, q: str, sort, drop_tokens_threshold: int = 1, topster: int = 250):
+    """backend(batch, stride) -> (kv, cnt, found). Returns (ordered seq_ids, found)."""
+    tokens = tokenize(q)
+    K = max(1, min(max(topster, 250), coll.n_docs))          # src/index.cpp:3506-3512
+    best: Dict[int, tuple] = {}
+    all_ids = set()
+
+    F = len(coll.fields)
+
+    def row_of(t):
+        return [v.get(t, S.NO_LIST) for v in coll.vocabs]
+
+    def run_round(trunc: List[str], dropped: List[str]):
+        if not trunc or any(all(x == S.NO_LIST for x in row_of(t)) for t in trunc):
+            return                                           # no candidate at cost 0: fuzzy_search_fields returns
+        rows = [row_of(t) for t in trunc] + [row_of(t) for t in dropped]
+        query = S.Query([S.Combo(rows, len(trunc))], topk=K, sort=sort, num_query_tokens=len(trunc),
+                        field_weight=[max(0, 15 - f) for f in range(F)])      # src/collection.cpp:4219-4225
+        kv, cnt, found = backend(S.KwBatch([query], list(range(F))), K)
+        for i in range(int(cnt[0])):
+            key = int(kv["key"][0, i])
+            tup = tuple(int(x) for x in kv["scores"][0, i])
+            all_ids.add(key)
+            if key not in best or tup >= best[key]:          # Topster::add keeps the greater KV per key
+                best[key] = tup
+
+    run_round(tokens, [])
+    n = min(len(tokens), 20)
+    if len(all_ids) < drop_tokens_threshold:
+        n_dropped, dirs_done, rtl = 0, 0, True
+        while len(all_ids) < drop_tokens_threshold:
+            if n_dropped >= n - 1:
+                rtl = not rtl
+                n_dropped = 0
+                dirs_done += 1
+            if n > 1 and dirs_done < 2:
+                if rtl:
+                    tl = n - n_dropped - 1
+                    trunc, dropped = tokens[:tl], tokens[tl:n]
+                else:
+                    st = n_dropped + 1
+                    trunc, dropped = tokens[st:n], tokens[:st]
+                n_dropped += 1
+                run_round(trunc, dropped)
+            else:
+                break
+    order = sorted(best.items(), key=lambda kv_: (kv_[1], kv_[0]), reverse=True)
+    return [k for k, _ in order], len(all_ids)

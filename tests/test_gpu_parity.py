@@ -268,3 +268,76 @@ def test_wildcard_search_matches_oracle(coll):
     okv, ocnt, ofound = oi.wildcard_search(bo, 1024)
     assert_kv_equal(kv, cnt, found, okv, ocnt, ofound, check_query_index=False)
     assert int(found.max()) == n_docs or int(found.max()) >= n_docs - 25
+
+
+def test_edge_cases(coll):
+    n_docs, fds, flats, pts, gi, oi = coll
+    # empty batch
+    b = S.KwBatch([], [0])
+    kv, cnt, found = gi.keyword_search(b, 8)
+    assert len(cnt) == 0
+    # combination whose tokens exist in no field / query without combinations / K = 1 / stride smaller than K
+    qs = [S.Query([S.Combo([[S.NO_LIST, S.NO_LIST, S.NO_LIST]], 1)], topk=5),
+          S.Query([], topk=5),
+          S.Query([S.Combo([[0, S.NO_LIST, 0]], 1)], topk=1),
+          S.Query([S.Combo([[1, 1, 1], [S.NO_LIST, S.NO_LIST, S.NO_LIST]], 2)], topk=300),     # a required token found nowhere is skipped
+          S.Query([S.Combo([[2, 2, 2]] * 16, 16)], topk=250, num_query_tokens=16)]                 # TSGPU_MAX_TOKENS rows... 16*3 > 32 lists
+    b = S.KwBatch(qs[:4], [0, 1, 2])
+    kv, cnt, found = gi.keyword_search(b, 4)
+    okv, ocnt, ofound = oi.keyword_search(b, 4)
+    assert_kv_equal(kv, cnt, found, okv, ocnt, ofound)
+    assert cnt[0] == 0 and cnt[1] == 0 and cnt[2] == 1 and cnt[3] == 4
+    with pytest.raises(capi.TsgpuError):
+        gi.keyword_search(S.KwBatch(qs[4:], [0, 1, 2]), 4)
+    with pytest.raises(capi.TsgpuError):
+        gi.keyword_search(S.KwBatch([S.Query([S.Combo([[0]], 1)], topk=2000)], [0]), 4)
+    # ten tokens (Match window limit) + duplicates of the same token
+    row = [3, 3, 3]
+    q10 = S.Query([S.Combo([[t, S.NO_LIST, S.NO_LIST] for t in (0, 1, 0, 2, 1, 0, 3, 0, 1, 0)], 10)], topk=50, num_query_tokens=10)
+    b = S.KwBatch([q10], [0, 1, 2])
+    kv, cnt, found = gi.keyword_search(b, 64)
+    okv, ocnt, ofound = oi.keyword_search(b, 64)
+    assert_kv_equal(kv, cnt, found, okv, ocnt, ofound)
+
+
+def test_large_scale_properties_and_sample_parity():
+    """1 M docs / 100 k vocabulary: size-independent properties on every query, oracle parity on a sample."""
+    n_docs = 1_000_000
+    fd = synth.make_string_field(n_docs, 100_000, 4, 12, seed=7, device="cuda")
+    pts = synth.make_points(n_docs, 13)
+    gi = capi.GpuIndex(n_docs, 0)
+    gi.load_field(fd.flat)
+    gi.load_sort_column(pts)
+    toks = synth.sample_queries(fd, 512, 3, 99)
+    sort = ((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_NUMERIC, 0, 1, 0), (S.SORT_NONE, -1, 1, 0))
+    rng = np.random.default_rng(2)
+    fil = np.nonzero(rng.random(n_docs) < 0.1)[0].astype(np.uint32)
+    qs = []
+    for i, r in enumerate(toks):
+        combos = [S.Combo([[int(t)] for t in r], 3)]
+        if i % 3 == 0:
+            combos.append(S.Combo([[int(r[0])], [int(r[1])], [int(min(r[2] + 1, 99_999))]], 3, total_cost=2))
+        qs.append(S.Query(combos, topk=250, sort=sort, num_query_tokens=3, filter=0 if i % 2 else -1))
+    b = S.KwBatch(qs, [0], [fil])
+    kv, cnt, found = gi.keyword_search(b, 250)
+    kv2, cnt2, found2 = gi.keyword_search(b, 250)
+    assert (cnt == cnt2).all() and (found == found2).all() and (kv["key"] == kv2["key"]).all()       # idempotent
+    fset = set(fil.tolist())
+    for q in range(len(qs)):
+        n = int(cnt[q])
+        assert n == min(250, int(found[q]))
+        keys = kv["key"][q, :n].astype(np.int64)
+        sc = kv["scores"][q, :n]
+        assert len(set(keys.tolist())) == n                                                          # de-duplicated
+        tup = [(int(a), int(b_), int(c), int(k)) for (a, b_, c), k in zip(sc, keys)]
+        assert tup == sorted(tup, reverse=True)                                                      # Topster::sort order
+        assert (sc[:, 1] == pts[keys]).all()                                                         # sort column gathered right
+        if q % 2:
+            assert all(int(k) in fset for k in keys)                                                 # filter respected
+        ids0 = fd.flat.ids[int(fd.flat.list_off[toks[q][0]]):int(fd.flat.list_off[toks[q][0] + 1])]
+        assert np.isin(keys, ids0).all() or q % 3 == 0
+    oi = ol.OracleIndex(n_docs, [fd.flat], [pts])
+    sample = S.KwBatch(qs[:96], [0], [fil])
+    okv, ocnt, ofound = oi.keyword_search(sample, 250, threads=16)
+    assert_kv_equal(kv[:96], cnt[:96], found[:96], okv, ocnt, ofound)
+    gi.close()

@@ -1,0 +1,86 @@
+"""End-to-end ranking scenarios of the reference's own test-suite (test/collection_test.cpp over test/documents.jsonl),
+replayed through the oracle on the CPU and — with -m gpu — through libtsgpu. These pin intersection + Match + score
+packing + sort keys + Topster order + the drop-tokens flow together."""
+import os
+
+import pytest
+
+import oracle_lib as ol
+import refflow
+from typesense_b200 import structs as S
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SORT_DESC = ((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_NUMERIC, 0, 1, 0), (S.SORT_NONE, -1, 1, 0))
+SORT_POINTS_ASC_2ND = ((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_NUMERIC, 0, -1, 0), (S.SORT_NONE, -1, 1, 0))
+# sort_by points:asc alone: _text_match is appended because the list has < 3 entries (src/collection.cpp:1736-1812)
+SORT_POINTS_ASC = ((S.SORT_NUMERIC, 0, -1, 0), (S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_NONE, -1, 1, 0))
+
+
+def ids_of(coll, seq_ids):
+    return [str(coll.docs[s].get("id", s)) for s in seq_ids]
+
+
+def scenarios(backend, coll):
+    # MultiTokenSearch, test/collection_test.cpp:162-236 (drop_tokens_threshold = 10)
+    got, found = refflow.search(backend, coll, "rocket launch", SORT_DESC, drop_tokens_threshold=10)
+    assert ids_of(coll, got) == ["8", "1", "17", "16", "13"] and found == 5
+    got, found = refflow.search(backend, coll, "rocket launch", SORT_POINTS_ASC_2ND, drop_tokens_threshold=10)
+    assert ids_of(coll, got) == ["8", "17", "1", "16", "13"] and found == 5
+    # ExactSearchShouldBeStable, test/collection_test.cpp:117-160
+    got, found = refflow.search(backend, coll, "the", SORT_DESC)
+    assert ids_of(coll, got) == ["1", "6", "foo", "13", "10", "8", "16"] and found == 7
+    got, found = refflow.search(backend, coll, "the", SORT_POINTS_ASC)
+    assert ids_of(coll, got) == ["16", "13", "10", "8", "6", "foo", "1"] and found == 7
+    got, found = refflow.search(backend, coll, "zxsadqewsad", SORT_POINTS_ASC)
+    assert got == [] and found == 0
+
+
+def multi_field_scenarios(make_backend):
+    # MultiFieldRelevance, test/collection_test.cpp:3173-3258: title + artist, default weights 15/14, drop tokens <= 10
+    q = "Dustin Kensrue Down There by the Train"
+    for records, expect in (([("Down There by the Train", "Dustin Kensrue"), ("Down There by the Train", "Gord Downie"),
+                              ("State Trooper", "Dustin Kensrue")], [0, 1, 2]),
+                            ([("State Trooper", "Dustin Kensrue"), ("Down There by the Train", "Gord Downie"),
+                              ("Down There by the Train", "Dustin Kensrue")], [2, 1, 0])):
+        coll = refflow.Collection([{"title": t, "artist": a, "points": i} for i, (t, a) in enumerate(records)], ("title", "artist"))
+        backend, close = make_backend(coll)
+        got, found = refflow.search(backend, coll, q, SORT_DESC, drop_tokens_threshold=10)
+        close()
+        assert got == expect and found == 3
+
+
+def test_multi_field_scenarios_oracle():
+    def mk(coll):
+        oi = ol.OracleIndex(coll.n_docs, coll.flats, [coll.points])
+        return (lambda b, k: oi.keyword_search(b, k)), (lambda: None)
+    multi_field_scenarios(mk)
+
+
+@pytest.mark.gpu
+def test_multi_field_scenarios_gpu():
+    from typesense_b200 import capi
+
+    def mk(coll):
+        gi = capi.GpuIndex(coll.n_docs, 0)
+        for f in coll.flats:
+            gi.load_field(f)
+        gi.load_sort_column(coll.points)
+        return (lambda b, k: gi.keyword_search(b, k)), gi.close
+    multi_field_scenarios(mk)
+
+
+def test_reference_scenarios_oracle():
+    coll = refflow.Collection.from_jsonl(os.path.join(GOLD, "documents.jsonl"))
+    oi = ol.OracleIndex(coll.n_docs, [coll.flat], [coll.points])
+    scenarios(lambda b, k: oi.keyword_search(b, k), coll)
+
+
+@pytest.mark.gpu
+def test_reference_scenarios_gpu():
+    from typesense_b200 import capi
+    coll = refflow.Collection.from_jsonl(os.path.join(GOLD, "documents.jsonl"))
+    gi = capi.GpuIndex(coll.n_docs, 0)
+    gi.load_field(coll.flat)
+    gi.load_sort_column(coll.points)
+    scenarios(lambda b, k: gi.keyword_search(b, k), coll)
+    gi.close()
