@@ -1,0 +1,151 @@
+// C++ host-side scenarios over the tsgpu C-ABI, written the way the reference's own gtest cases read
+// (test/posting_list_test.cpp, test/or_iterator_test.cpp, test/collection_test.cpp, test/collection_vector_search_test.cpp).
+// Built and run by tests/test_cpp_host.py on a machine with a GPU; exit code = number of failed checks.
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../typesense_b200/host/tsgpu_host.hpp"
+#include "../../oracle/ts_oracle.h"      // test infrastructure: only used to build an HNSW graph for the vector case
+
+static int failures = 0;
+#define CHECK(cond) do { if(!(cond)) { failures++; printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); } } while(0)
+
+static std::string json_str(const std::string& line, const std::string& key) {
+    size_t p = line.find("\"" + key + "\"");
+    if(p == std::string::npos) return "";
+    p = line.find(':', p);
+    p = line.find('"', p);
+    size_t e = line.find('"', p + 1);
+    return line.substr(p + 1, e - p - 1);
+}
+static long json_int(const std::string& line, const std::string& key) {
+    size_t p = line.find("\"" + key + "\"");
+    p = line.find(':', p);
+    return std::strtol(line.c_str() + p + 1, nullptr, 10);
+}
+
+// TEST(PostingListTest, IntersectionBasics) test/posting_list_test.cpp:603-700
+static void posting_list_intersection_basics() {
+    tsgpu::Index index(64);
+    tsgpu::field_mirror_t f;
+    const std::vector<uint32_t> offsets = {0, 1, 3};
+    for(uint32_t i: {0u, 2u, 3u, 20u}) f.upsert("p1", i, offsets);
+    for(uint32_t i: {1u, 3u, 5u, 10u, 20u}) f.upsert("p2", i, offsets);
+    for(uint32_t i: {2u, 3u, 5u, 7u, 20u}) f.upsert("p3", i, offsets);
+    CHECK(index.add_field("f", f).ok());
+    std::vector<uint32_t> result_ids;
+    CHECK(index.intersect("f", {"p1", "p2", "p3"}, result_ids).ok());
+    CHECK((result_ids == std::vector<uint32_t>{3, 20}));
+    CHECK(index.intersect("f", {"p1"}, result_ids).ok());
+    CHECK((result_ids == std::vector<uint32_t>{0, 2, 3, 20}));
+    CHECK(index.intersect("f", {"p1", "missing"}, result_ids).ok());
+    CHECK(result_ids.empty());
+}
+
+// TEST(OrIteratorTest, IntersectAndFilterThreeIts) test/or_iterator_test.cpp:162-217
+static void or_iterator_intersect_and_filter() {
+    tsgpu::Index index(100000);
+    tsgpu::field_mirror_t f;
+    const std::vector<uint32_t> offsets = {1, 0};
+    for(uint32_t i: {4207u, 29159u, 47182u, 47250u, 47337u, 48518u, 99820u}) f.upsert("a", i, offsets);
+    for(uint32_t i: {62u, 330u, 367u, 4124u, 4207u, 4242u, 4418u, 28740u, 29099u, 29159u, 29284u, 40795u, 43556u, 46779u, 47182u, 47250u, 47322u,
+                     48494u, 48518u, 48633u, 98813u, 98821u, 99069u, 99368u, 99533u, 99670u, 99820u, 99888u, 99973u}) f.upsert("b", i, offsets);
+    for(uint32_t i: {723u, 1504u, 29038u, 29164u, 29390u, 30890u, 34743u, 35067u, 36466u, 40268u, 40965u, 42161u, 43425u, 45188u, 47326u, 47443u,
+                     49319u, 53043u, 58436u, 58774u, 61123u, 70973u, 71393u, 81575u, 82323u, 88301u, 88502u, 88594u, 88690u, 88951u, 90662u, 91016u,
+                     91915u, 92069u, 92844u, 99820u}) f.upsert("c", i, offsets);
+    CHECK(index.add_field("f", f).ok());
+    tsgpu::host_topster_t topster(250);
+    size_t found = 0;
+    const std::vector<uint32_t> filter_ids = {44424, 44425, 44447, 99820, 99834, 99854, 99859, 99963};
+    auto op = index.search_across_fields({{"a", "b", "c"}}, 0, {0}, {"f"}, {15}, {{tsgpu::sort_by::text_match, "", true}}, filter_ids, true, {}, 250,
+                                         true, topster, found);
+    CHECK(op.ok());
+    auto kvs = topster.sort();
+    CHECK(kvs.size() == 1 && found == 1);
+    if(!kvs.empty()) CHECK(kvs[0].key == 99820);
+}
+
+// TEST_F(CollectionTest, MultiTokenSearch / ExactSearchShouldBeStable) test/collection_test.cpp:117-236
+static void collection_scenarios(const std::string& jsonl) {
+    std::vector<std::pair<std::string, long>> docs = {{"z", 10}};        // dummy record for id 0
+    std::vector<std::string> ext_ids = {"0"};
+    std::ifstream in(jsonl);
+    std::string line;
+    while(std::getline(in, line)) {
+        if(line.empty()) continue;
+        docs.emplace_back(json_str(line, "title"), json_int(line, "points"));
+        std::string id = json_str(line, "id");
+        ext_ids.push_back(id.empty() ? std::to_string(docs.size() - 1) : id);
+    }
+    CHECK(docs.size() == 24);
+    tsgpu::Index index((uint32_t) docs.size());
+    tsgpu::field_mirror_t title;
+    std::unordered_map<uint32_t, int64_t> points;
+    for(uint32_t i = 0; i < docs.size(); i++) { title.index_plain_string(i, tsgpu::tokenize_ascii(docs[i].first)); points[i] = docs[i].second; }
+    CHECK(index.add_field("title", title).ok());
+    CHECK(index.add_sort_field("points", points).ok());
+    auto ids_of = [&](const std::vector<tsgpu::KV>& kvs) { std::vector<std::string> r; for(auto& kv: kvs) r.push_back(ext_ids[kv.key]); return r; };
+    std::vector<tsgpu::sort_by> sort_fields = {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::numeric, "points", true}};
+    std::vector<tsgpu::KV> kvs;
+    size_t found = 0;
+    CHECK(index.search(tsgpu::tokenize_ascii("rocket launch"), {"title"}, sort_fields, 10, 250, kvs, found).ok());
+    CHECK((ids_of(kvs) == std::vector<std::string>{"8", "1", "17", "16", "13"}));
+    CHECK(found == 5);
+    std::vector<tsgpu::sort_by> sort_fields_asc = {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::numeric, "points", false}};
+    CHECK(index.search(tsgpu::tokenize_ascii("rocket launch"), {"title"}, sort_fields_asc, 10, 250, kvs, found).ok());
+    CHECK((ids_of(kvs) == std::vector<std::string>{"8", "17", "1", "16", "13"}));
+    CHECK(index.search(tsgpu::tokenize_ascii("the"), {"title"}, sort_fields, 1, 250, kvs, found).ok());
+    CHECK((ids_of(kvs) == std::vector<std::string>{"1", "6", "foo", "13", "10", "8", "16"}));
+    CHECK(found == 7);
+    CHECK(index.search(tsgpu::tokenize_ascii("zxsadqewsad"), {"title"}, sort_fields, 1, 250, kvs, found).ok());
+    CHECK(kvs.empty() && found == 0);
+    // phrase: "rocket launch" as a phrase only in doc 8 ("... of a rocket launch these days")
+    std::vector<uint32_t> both, phrase;
+    CHECK(index.intersect("title", {"rocket", "launch"}, both).ok());
+    CHECK(index.get_phrase_matches("title", {"rocket", "launch"}, both, phrase).ok());
+    CHECK((phrase == std::vector<uint32_t>{8}));
+}
+
+// TEST_F(CollectionVectorTest, BasicVectorQuerying) test/collection_vector_search_test.cpp:75-135 (cosine, d = 4)
+static void vector_scenario() {
+    std::vector<std::vector<float>> values = {{0.851758f, 0.909671f, 0.823431f, 0.372063f}, {0.97826f, 0.933157f, 0.39557f, 0.306488f},
+                                               {0.230606f, 0.634397f, 0.514009f, 0.399594f}};
+    std::vector<float> vecs(12), q = {0.96826f, 0.94f, 0.39557f, 0.306488f}, nq(4);
+    for(int i = 0; i < 3; i++) tso_normalize(values[i].data(), vecs.data() + 4 * i, 4);        // hnsw_index_t::normalize_vector
+    tso_normalize(q.data(), nq.data(), 4);
+    void* bld = tso_hnsw_build(vecs.data(), 3, 4, 16, 200, 100);
+    uint32_t max_level = 0, entry = 0; uint64_t n_up = 0;
+    tso_hnsw_build_info(bld, &max_level, &entry, &n_up);
+    std::vector<uint8_t> levels(3); std::vector<uint32_t> links0(3 * 33), links_up((n_up + 1) * 17); std::vector<uint64_t> upper_off(4);
+    tso_hnsw_build_fetch(bld, levels.data(), links0.data(), upper_off.data(), links_up.data());
+    tso_hnsw_build_free(bld);
+    tsgpu_hnsw g{3, 4, 16, max_level, entry, 1, vecs.data(), nullptr, levels.data(), links0.data(), upper_off.data(), links_up.data()};
+    tsgpu::Index index(3);
+    CHECK(index.add_vector_field(g).ok());
+    auto pairs = index.searchKnnCloserFirst(nq.data(), 10, 10);
+    CHECK(pairs.size() == 3);
+    if(pairs.size() == 3) {
+        CHECK(pairs[0].second == 1 && pairs[1].second == 0 && pairs[2].second == 2);
+        CHECK(std::fabs(std::fabs(pairs[0].first) - 3.409385681152344e-05f) < 2e-7f);
+        CHECK(std::fabs(pairs[1].first - 0.04329806566238403f) < 2e-7f);
+        CHECK(std::fabs(pairs[2].first - 0.15141665935516357f) < 2e-7f);
+    }
+    std::vector<uint32_t> filter = {0, 1};          // filter_by points:[0,1]
+    pairs = index.searchKnnCloserFirst(nq.data(), 10, 10, &filter);
+    CHECK(pairs.size() == 2);
+    if(pairs.size() == 2) CHECK(pairs[0].second == 1 && pairs[1].second == 0);
+}
+
+int main(int argc, char** argv) {
+    if(tsgpu_device_count() == 0) { printf("no CUDA device: nothing to run (the library has no CPU path)\n"); return 99; }
+    posting_list_intersection_basics();
+    or_iterator_intersect_and_filter();
+    collection_scenarios(argc > 1 ? argv[1] : "tests/golden/documents.jsonl");
+    vector_scenario();
+    printf("%s (%d failed checks)\n", failures ? "FAILED" : "PASSED", failures);
+    return failures;
+}

@@ -1,0 +1,33 @@
+"""Builds the C++ host layer (typesense_b200/host/tsgpu_host.hpp) + its scenario program with g++. The build runs on
+the CPU (checks the header compiles against include/tsgpu.h and links libtsgpu.so); running it needs a GPU."""
+import os
+import subprocess
+
+import pytest
+
+import oracle_lib as ol
+
+ROOT = ol.ROOT
+BIN = os.path.join(ROOT, "tests", "cpp", "host_scenarios")
+
+
+def build():
+    ol.build_oracle()
+    src = os.path.join(ROOT, "tests", "cpp", "host_scenarios.cpp")
+    lib_dir = os.path.join(ROOT, "typesense_b200")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wno-unused", src, "-o", BIN, "-L", lib_dir, "-ltsgpu", "-L", os.path.join(ROOT, "oracle"),
+           "-l:liboracle.so", f"-Wl,-rpath,{lib_dir}", f"-Wl,-rpath,{os.path.join(ROOT, 'oracle')}", "-pthread"]
+    subprocess.check_call(cmd)
+
+
+def test_cpp_host_layer_builds():
+    build()
+    assert os.path.exists(BIN)
+
+
+@pytest.mark.gpu
+def test_cpp_host_scenarios():
+    build()
+    r = subprocess.run([BIN, os.path.join(ROOT, "tests", "golden", "documents.jsonl")], capture_output=True, text=True, cwd=ROOT)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -69,6 +69,8 @@ struct CDesc {
     uint32_t lists[kMaxLists];         // [row * F + f]
     uint32_t drv_tile_off[kMaxFieldSlots + 1];
     uint8_t  probe_order[16];
+    uint32_t mode;                     // 0: driver tiles + per-candidate probes; 1: word-parallel AND of dense bitmaps
+    uint32_t n_words;                  // mode 1: valid bitmap words = ceil(n_docs / 32)
 };
 
 struct UDesc {
@@ -338,6 +340,68 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
         }
     };
 
+    if(cd.mode == 1) {
+        // ---- all required tokens are dense lists: intersect their bitmaps 32 docs per instruction. A tile is 128
+        // consecutive bitmap words (4096 docs), one word per thread; set bits are popped one per thread and round into
+        // the same scoring queue. Replaces the whole decode/narrow/probe pipeline for the heaviest combinations.
+        for(uint32_t tile = ud.tile_begin; tile < ud.tile_end; tile++) {
+            const uint32_t wi = tile * kThreads + tid;
+            uint32_t word = 0;
+            if(wi < cd.n_words && !qd.filter_empty) {
+                word = 0xFFFFFFFFu;
+                for(uint32_t r = 0; r < cd.n_rows; r++) {
+                    if(!((cd.req_mask >> r) & 1)) continue;
+                    uint32_t rw = 0;
+                    for(uint32_t f = 0; f < F; f++) {
+                        const uint32_t j = r * F + f;
+                        if(cd.lists[j] == kNone) continue;
+                        const DevField& g = ix.fields[P.field_ids[f]];
+                        rw |= __ldg(g.dense_bits + (size_t) l_dense[j] * g.dense_words + wi);
+                    }
+                    word &= rw;
+                }
+                if(qd.filter_bitmap) word &= __ldg(qd.filter_bitmap + wi);
+            }
+            for(;;) {
+                const int any = __syncthreads_or(word != 0);          // also publishes the previous round's queue writes
+                if(s_qn >= kThreads) {
+                    const uint32_t qn = s_qn;
+                    score_batch(qn - kThreads, kThreads);
+                    if(tid == 0) s_qn = qn - kThreads;
+                    __syncthreads();
+                }
+                if(!any) break;
+                bool alive = word != 0;
+                uint32_t id = 0;
+                if(alive) {
+                    const uint32_t bit = __ffs(word) - 1;
+                    word &= word - 1;
+                    id = (wi << 5) | bit;
+                    if(qd.n_excl && excluded(qd.excl, qd.n_excl, id)) alive = false;
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+                if(bal) {
+                    uint32_t qb = 0;
+                    if(lane == 0) { qb = atomicAdd(&s_qn, (uint32_t) __popc(bal)); atomicAdd(&s_matches, (uint32_t) __popc(bal)); }
+                    qb = __shfl_sync(0xffffffffu, qb, 0);
+                    if(alive) {
+                        const uint32_t slot = qb + __popc(bal & ((1u << lane) - 1u));
+                        q_id[slot] = id;
+                        for(uint32_t j = 0; j < n_lists; j++) {
+                            const uint32_t l = cd.lists[j];
+                            uint32_t h = kNone;
+                            if(l != kNone) {
+                                const DevField& g = ix.fields[P.field_ids[j % F]];
+                                if(l_dense[j] != kNone) { if(dense_test(g, l_dense[j], id)) h = dense_rank_of(g, l_dense[j], id); }
+                                else h = probe_list(g, l, l_blk0[j], l_blk1[j], id);      // sparse list of a dropped token
+                            }
+                            q_hp[j * kQCap + slot] = h;
+                        }
+                    }
+                }
+            }
+        }
+    } else
     for(uint32_t tile = ud.tile_begin; tile < ud.tile_end; tile++) {
         // ---- which driver field / block
         uint32_t fd = 0;

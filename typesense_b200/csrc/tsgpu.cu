@@ -82,6 +82,7 @@ struct FieldMirror {
     DevField dev{};
     std::vector<uint64_t> h_list_off;
     std::vector<uint32_t> h_list_blk_off;
+    std::vector<uint32_t> h_list_dense;
     void* d_alloc[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -209,7 +210,23 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
         for(uint32_t r = 0; r < n_req; r++) if(sumdf[r]) { cd.req_mask |= 1u << r; if(drv == kNone || sumdf[r] < sumdf[drv]) drv = r; }
         uint32_t tiles = 0;
         for(uint32_t f = 0; f <= (uint32_t) kMaxFieldSlots; f++) cd.drv_tile_off[f] = 0;
-        if(drv != kNone) {
+        cd.mode = 0; cd.n_words = (uint32_t) (((uint64_t) idx->n_docs + 31) / 32);
+        bool all_dense = drv != kNone;
+        for(uint32_t r = 0; r < n_req && all_dense; r++) {
+            if(!((cd.req_mask >> r) & 1)) continue;
+            for(uint32_t f = 0; f < F; f++) {
+                const uint32_t l = cd.lists[r * F + f];
+                if(l != TSGPU_NO_LIST && idx->fields[b->field_ids[f]].h_list_dense[l] == kNone) { all_dense = false; break; }
+            }
+        }
+        if(all_dense) {
+            // every required token is a dense list: word-parallel bitmap AND over the whole id space (kw_kernels.cuh)
+            cd.mode = 1;
+            cd.driver_row = (uint8_t) drv;
+            tiles = (cd.n_words + kThreads - 1) / kThreads;
+            for(uint32_t f = 0; f <= (uint32_t) kMaxFieldSlots; f++) cd.drv_tile_off[f] = f == 0 ? 0 : tiles;
+            for(uint32_t i = 0; i < 16; i++) cd.probe_order[i] = (uint8_t) (i < n_rows ? i : 0);
+        } else if(drv != kNone) {
             cd.driver_row = (uint8_t) drv;
             for(uint32_t f = 0; f < F; f++) {
                 cd.drv_tile_off[f] = tiles;
@@ -260,7 +277,7 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
         for(uint32_t c = qd.combo_begin; c < qd.combo_end; c++) {
             pl.cd[c].q = q;
             if(combo_tiles[c]) combos_with_tiles++;
-            const uint32_t ctpu = tpu;
+            const uint32_t ctpu = pl.cd[c].mode == 1 ? 64u : tpu;      // a dense tile is 4096 docs of bitmap words
             for(uint32_t t = 0; t < combo_tiles[c]; t += ctpu) {
                 UDesc u;
                 u.combo = c; u.tile_begin = t; u.tile_end = std::min(combo_tiles[c], t + ctpu);
@@ -829,7 +846,8 @@ tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint
     CU(up(5, f->pos_off, (n_post + 1) * 8, true));
     CU(up(6, f->positions, n_pos * 4, true));
     // dense lists: bitmap + rank directory (see postings_device.cuh)
-    tspack::pack_dense(L, fm.h_list_off.data(), h_ids.data(), idx->n_docs, std::max<uint64_t>(64, idx->n_docs / 64), pk);
+    tspack::pack_dense(L, fm.h_list_off.data(), h_ids.data(), idx->n_docs, std::max<uint64_t>(64, idx->n_docs / 128), pk);
+    fm.h_list_dense = pk.list_dense;
     CU(up(7, pk.list_dense.data(), pk.list_dense.size() * 4, false));
     CU(up(8, pk.dense_bits.data(), pk.dense_bits.size() * 4, false));
     CU(up(9, pk.dense_rank.data(), pk.dense_rank.size() * 4, false));

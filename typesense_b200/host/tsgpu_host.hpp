@@ -1,0 +1,326 @@
+// tsgpu_host.hpp — C++ host side above the C-ABI (include/tsgpu.h), mirroring the reference's own call surface for the
+// hot path so that host code written against Typesense's interfaces can switch over with the same argument meaning:
+//
+//   reference                                                     here
+//   ---------------------------------------------------------     ------------------------------------------------
+//   Option<T>{ok, code, error}            include/option.h         tsgpu::Option<T>
+//   KV                                    include/topster.h:20     tsgpu::KV (== tsgpu_kv)
+//   posting_t::upsert(obj, id, offsets)   src/posting.cpp:247      field_mirror_t::upsert(token, id, offsets)
+//   posting_t::intersect(lists, ids)      src/posting.cpp:388      Index::intersect(field, tokens, ids)
+//   posting_t::get_phrase_matches         src/posting.cpp:543      Index::get_phrase_matches(field, tokens, ids, out)
+//   Index::search_across_fields           src/index.cpp:5385       Index::search_across_fields(query_suggestions, ...)
+//   hnsw_index_t + searchKnnCloserFirst   src/index.cpp:3384       Index::searchKnnCloserFirst(q, k, ef, filter_ids)
+//   Topster<KV>::add / sort               include/topster.h:321    host_topster_t (merges the <=K KVs of each device round)
+//   Index::search drop-tokens loop        src/index.cpp:3920-4017  Index::search(tokens, ...)  (control flow stays on host)
+//
+// Header-only; needs only libtsgpu.so. There is no CPU implementation behind these calls.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../../include/tsgpu.h"
+
+namespace tsgpu {
+
+template <class T>
+class Option {
+    T value_{};
+    bool ok_ = true;
+    int code_ = 200;
+    std::string error_;
+public:
+    Option(const T& v): value_(v) {}
+    Option(int code, std::string err): ok_(false), code_(code), error_(std::move(err)) {}
+    bool ok() const { return ok_; }
+    int code() const { return code_; }
+    const std::string& error() const { return error_; }
+    const T& get() const { return value_; }
+};
+
+using KV = tsgpu_kv;
+
+inline bool kv_is_greater(const KV& a, const KV& b) {          // KV::is_greater
+    if(a.scores[0] != b.scores[0]) return a.scores[0] > b.scores[0];
+    if(a.scores[1] != b.scores[1]) return a.scores[1] > b.scores[1];
+    if(a.scores[2] != b.scores[2]) return a.scores[2] > b.scores[2];
+    return a.key > b.key;
+}
+
+// Host-side accumulation across device rounds: same outcome as feeding every KV to one Topster<KV> — the greatest KV
+// per key survives, the best `capacity` are kept, sort() orders them (top-K of de-duplicated unions is decomposable).
+class host_topster_t {
+    size_t capacity;
+    std::unordered_map<uint64_t, KV> best;
+public:
+    explicit host_topster_t(size_t cap): capacity(cap) {}
+    void add(const KV& kv) {
+        auto it = best.find(kv.key);
+        if(it == best.end() || !kv_is_greater(it->second, kv)) best[kv.key] = kv;
+    }
+    std::vector<KV> sort() const {
+        std::vector<KV> v;
+        v.reserve(best.size());
+        for(auto& p: best) v.push_back(p.second);
+        std::sort(v.begin(), v.end(), kv_is_greater);
+        if(v.size() > capacity) v.resize(capacity);
+        return v;
+    }
+};
+
+// write side of one string field: what Index::index_field_in_memory feeds to posting_t::upsert per token
+class field_mirror_t {
+    friend class Index;
+    std::map<std::string, std::map<uint32_t, std::vector<uint32_t>>> postings;
+    bool is_array;
+public:
+    explicit field_mirror_t(bool is_array = false): is_array(is_array) {}
+    void upsert(const std::string& token, uint32_t seq_id, const std::vector<uint32_t>& offsets) { postings[token][seq_id] = offsets; }
+    // Index::tokenize_string (src/index.cpp:1323-1349): positions 1-based, trailing 0 on the doc's last token
+    void index_plain_string(uint32_t seq_id, const std::vector<std::string>& tokens) {
+        std::map<std::string, std::vector<uint32_t>> t2o;
+        for(size_t i = 0; i < tokens.size(); i++) t2o[tokens[i]].push_back((uint32_t) i + 1);
+        if(!tokens.empty()) t2o[tokens.back()].push_back(0);
+        for(auto& p: t2o) upsert(p.first, seq_id, p.second);
+    }
+};
+
+struct sort_by {
+    enum type_t { none = TSGPU_SORT_NONE, text_match = TSGPU_SORT_TEXT_MATCH, seq_id = TSGPU_SORT_SEQ_ID, numeric = TSGPU_SORT_NUMERIC,
+                  vector_distance = TSGPU_SORT_VECTOR_DISTANCE } type = none;
+    std::string name;          // numeric sort field
+    bool desc = true;          // "DESC" / "ASC"
+    bool missing_first = false;
+};
+
+class Index {
+    tsgpu_index* h = nullptr;
+    uint32_t n_docs;
+    std::vector<std::unordered_map<std::string, uint32_t>> token_ids;      // per field: token -> posting list id (art_search stand-in)
+    std::unordered_map<std::string, uint32_t> field_ids, sort_cols;
+    std::string err;
+public:
+    Index(uint32_t n_docs, int device = 0): n_docs(n_docs) {
+        if(tsgpu_index_create(n_docs, device, &h) != TSGPU_OK) { err = tsgpu_last_error(); h = nullptr; }
+    }
+    ~Index() { if(h) tsgpu_index_destroy(h); }
+    Index(const Index&) = delete;
+    bool ok() const { return h != nullptr; }
+    const std::string& error() const { return err; }
+
+    Option<uint32_t> add_field(const std::string& name, const field_mirror_t& f) {
+        std::vector<uint64_t> list_off{0}, pos_off{0};
+        std::vector<uint32_t> ids, positions;
+        std::unordered_map<std::string, uint32_t> tid;
+        for(auto& tok: f.postings) {
+            tid[tok.first] = (uint32_t) list_off.size() - 1;
+            for(auto& p: tok.second) {
+                ids.push_back(p.first);
+                positions.insert(positions.end(), p.second.begin(), p.second.end());
+                pos_off.push_back(positions.size());
+            }
+            list_off.push_back(ids.size());
+        }
+        if(ids.empty()) { ids.push_back(0); }
+        if(positions.empty()) positions.push_back(0);
+        tsgpu_field tf{(uint32_t) list_off.size() - 1, f.is_array ? 1u : 0u, list_off.data(), ids.data(), pos_off.data(), positions.data()};
+        uint32_t fid = 0;
+        if(tsgpu_index_load_field(h, &tf, &fid) != TSGPU_OK) return Option<uint32_t>(500, tsgpu_last_error());
+        field_ids[name] = fid;
+        if(token_ids.size() <= fid) token_ids.resize(fid + 1);
+        token_ids[fid] = std::move(tid);
+        return Option<uint32_t>(fid);
+    }
+    // sort_index[field] (spp::sparse_hash_map<uint32, int64>): docs without a value sort as INT64_MIN
+    Option<uint32_t> add_sort_field(const std::string& name, const std::unordered_map<uint32_t, int64_t>& values) {
+        std::vector<int64_t> dense(n_docs, INT64_MIN);
+        for(auto& p: values) if(p.first < n_docs) dense[p.first] = p.second;
+        uint32_t col = 0;
+        if(tsgpu_index_load_sort_column(h, dense.data(), &col) != TSGPU_OK) return Option<uint32_t>(500, tsgpu_last_error());
+        sort_cols[name] = col;
+        return Option<uint32_t>(col);
+    }
+    Option<bool> add_vector_field(const tsgpu_hnsw& g) {
+        if(tsgpu_index_load_hnsw(h, &g) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
+        return Option<bool>(true);
+    }
+
+    uint32_t token_id(uint32_t field, const std::string& tok) const {
+        auto it = token_ids[field].find(tok);
+        return it == token_ids[field].end() ? TSGPU_NO_LIST : it->second;
+    }
+
+    // posting_t::intersect(posting_lists, result_ids)
+    Option<bool> intersect(const std::string& field, const std::vector<std::string>& tokens, std::vector<uint32_t>& result_ids) {
+        const uint32_t f = field_ids.at(field);
+        std::vector<uint32_t> lists;
+        result_ids.clear();
+        for(auto& t: tokens) { uint32_t l = token_id(f, t); if(l == TSGPU_NO_LIST) return Option<bool>(true); lists.push_back(l); }
+        result_ids.resize(n_docs);
+        size_t n = 0;
+        if(tsgpu_intersect(h, f, lists.data(), (uint32_t) lists.size(), result_ids.data(), result_ids.size(), &n) != TSGPU_OK)
+            return Option<bool>(500, tsgpu_last_error());
+        result_ids.resize(n);
+        return Option<bool>(true);
+    }
+    // posting_t::get_phrase_matches(posting_lists, field_is_array, ids, num_ids, phrase_ids, num_phrase_ids)
+    Option<bool> get_phrase_matches(const std::string& field, const std::vector<std::string>& tokens, const std::vector<uint32_t>& ids,
+                                    std::vector<uint32_t>& phrase_ids) {
+        const uint32_t f = field_ids.at(field);
+        std::vector<uint32_t> lists;
+        phrase_ids.clear();
+        for(auto& t: tokens) { uint32_t l = token_id(f, t); if(l == TSGPU_NO_LIST) return Option<bool>(true); lists.push_back(l); }
+        phrase_ids.resize(ids.size() ? ids.size() : 1);
+        size_t n = 0;
+        if(tsgpu_phrase_matches(h, f, lists.data(), (uint32_t) lists.size(), ids.data(), ids.size(), phrase_ids.data(), &n) != TSGPU_OK)
+            return Option<bool>(500, tsgpu_last_error());
+        phrase_ids.resize(n);
+        return Option<bool>(true);
+    }
+
+    // One Index::search_all_candidates call: `query_suggestions` = the token combinations to run (each a list of
+    // tokens, the last `n_dropped` of which are dropped_tokens); all of them are scored into `topster`.
+    Option<bool> search_across_fields(const std::vector<std::vector<std::string>>& query_suggestions, size_t n_dropped,
+                                      const std::vector<uint32_t>& total_costs, const std::vector<std::string>& the_fields,
+                                      const std::vector<uint8_t>& field_weights, const std::vector<sort_by>& sort_fields,
+                                      const std::vector<uint32_t>& filter_ids, bool filter_by_provided,
+                                      const std::vector<uint32_t>& excluded_result_ids, size_t topster_size,
+                                      bool prioritize_exact_match, host_topster_t& topster, size_t& num_found) {
+        const uint32_t F = (uint32_t) the_fields.size();
+        std::vector<uint32_t> fids(F);
+        for(uint32_t f = 0; f < F; f++) fids[f] = field_ids.at(the_fields[f]);
+        std::vector<uint32_t> c_tok_off{0}, t_list, c_cost;
+        std::vector<uint8_t> c_nreq;
+        size_t n_query_tokens = 0;
+        for(size_t c = 0; c < query_suggestions.size(); c++) {
+            const auto& toks = query_suggestions[c];
+            for(auto& t: toks) for(uint32_t f = 0; f < F; f++) t_list.push_back(token_id(fids[f], t));
+            c_tok_off.push_back(c_tok_off.back() + (uint32_t) toks.size());
+            c_nreq.push_back((uint8_t) (toks.size() - n_dropped));
+            c_cost.push_back(c < total_costs.size() ? total_costs[c] : 0);
+            n_query_tokens = toks.size() - n_dropped;
+        }
+        uint32_t q_combo_off[2] = {0, (uint32_t) query_suggestions.size()};
+        int32_t q_filter = filter_by_provided ? 0 : -1;
+        uint32_t q_excl_off[2] = {0, (uint32_t) excluded_result_ids.size()};
+        uint32_t q_topk = (uint32_t) std::min<size_t>(topster_size, TSGPU_MAX_TOPK);
+        uint8_t sort_type[3] = {0, 0, 0}, missing_first[3] = {0, 0, 0};
+        int32_t sort_col[3] = {-1, -1, -1};
+        int8_t sort_order[3] = {1, 1, 1};
+        for(size_t i = 0; i < sort_fields.size() && i < 3; i++) {
+            sort_type[i] = (uint8_t) sort_fields[i].type;
+            sort_order[i] = sort_fields[i].desc ? 1 : -1;
+            missing_first[i] = sort_fields[i].missing_first;
+            if(sort_fields[i].type == sort_by::numeric) sort_col[i] = (int32_t) sort_cols.at(sort_fields[i].name);
+        }
+        uint8_t q_flags = prioritize_exact_match ? TSGPU_FLAG_PRIORITIZE_EXACT_MATCH : 0, q_match_type = TSGPU_MATCH_MAX_SCORE;
+        uint8_t q_nqt = (uint8_t) n_query_tokens;
+        uint64_t filter_off[2] = {0, filter_ids.size()};
+        const uint32_t zero = 0;
+        tsgpu_kw_batch b{};
+        b.n_queries = 1; b.n_combos = (uint32_t) query_suggestions.size(); b.n_fields = F; b.n_filters = filter_by_provided ? 1 : 0;
+        b.field_ids = fids.data(); b.q_combo_off = q_combo_off; b.q_filter = &q_filter; b.q_excl_off = q_excl_off;
+        b.excl_ids = excluded_result_ids.empty() ? &zero : excluded_result_ids.data(); b.q_topk = &q_topk;
+        b.q_sort_type = sort_type; b.q_sort_col = sort_col; b.q_sort_order = sort_order; b.q_sort_missing_first = missing_first;
+        b.q_flags = &q_flags; b.q_match_type = &q_match_type; b.q_num_query_tokens = &q_nqt; b.q_field_weight = field_weights.data();
+        b.c_tok_off = c_tok_off.data(); b.c_total_cost = c_cost.data(); b.c_n_required = c_nreq.data();
+        b.t_list = t_list.empty() ? &zero : t_list.data();
+        b.filter_off = filter_off; b.filter_ids = filter_ids.empty() ? &zero : filter_ids.data();
+        std::vector<KV> kvs(q_topk);
+        uint32_t count = 0, found = 0;
+        if(tsgpu_keyword_search_batch(h, &b, kvs.data(), q_topk, &count, &found) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
+        for(uint32_t i = 0; i < count; i++) topster.add(kvs[i]);
+        num_found = found;
+        return Option<bool>(true);
+    }
+
+    // Index::search for already-tokenised text: exact tokens (cost 0) + the drop-tokens loop (src/index.cpp:3920-4017,
+    // default right_to_left). Typo candidates come from the host's ART and would add combinations to each round.
+    Option<bool> search(const std::vector<std::string>& tokens, const std::vector<std::string>& the_fields,
+                        const std::vector<sort_by>& sort_fields, size_t drop_tokens_threshold, size_t topster_size,
+                        std::vector<KV>& raw_result_kvs, size_t& found) {
+        std::vector<uint8_t> weights;
+        for(size_t f = 0; f < the_fields.size(); f++) weights.push_back((uint8_t) (f < 15 ? 15 - f : 0));      // src/collection.cpp:4219-4225
+        host_topster_t topster(topster_size);
+        std::map<uint64_t, bool> all_result_ids;
+        auto run_round = [&](const std::vector<std::string>& trunc, const std::vector<std::string>& dropped) -> Option<bool> {
+            for(auto& t: trunc) {
+                bool any = false;
+                for(auto& fn: the_fields) any = any || token_id(field_ids.at(fn), t) != TSGPU_NO_LIST;
+                if(!any) return Option<bool>(true);          // no candidate at cost 0 -> fuzzy_search_fields returns
+            }
+            if(trunc.empty()) return Option<bool>(true);
+            std::vector<std::string> all = trunc;
+            all.insert(all.end(), dropped.begin(), dropped.end());
+            host_topster_t round(topster_size);
+            size_t nf = 0;
+            auto op = search_across_fields({all}, dropped.size(), {0}, the_fields, weights, sort_fields, {}, false, {}, topster_size, true, round, nf);
+            if(!op.ok()) return op;
+            for(auto& kv: round.sort()) { topster.add(kv); all_result_ids[kv.key] = true; }
+            return Option<bool>(true);
+        };
+        auto op = run_round(tokens, {});
+        if(!op.ok()) return op;
+        const size_t n = std::min<size_t>(tokens.size(), 20);
+        if(all_result_ids.size() < drop_tokens_threshold) {
+            size_t num_tokens_dropped = 0, total_dirs_done = 0;
+            bool right_to_left = true;
+            while(all_result_ids.size() < drop_tokens_threshold) {
+                if(num_tokens_dropped >= n - 1) { right_to_left = !right_to_left; num_tokens_dropped = 0; total_dirs_done++; }
+                if(n > 1 && total_dirs_done < 2) {
+                    std::vector<std::string> trunc, dropped;
+                    if(right_to_left) {
+                        const size_t tl = n - num_tokens_dropped - 1;
+                        for(size_t i = 0; i < n; i++) (i < tl ? trunc : dropped).push_back(tokens[i]);
+                    } else {
+                        const size_t st = num_tokens_dropped + 1;
+                        for(size_t i = 0; i < n; i++) (i >= st ? trunc : dropped).push_back(tokens[i]);
+                    }
+                    num_tokens_dropped++;
+                    op = run_round(trunc, dropped);
+                    if(!op.ok()) return op;
+                } else break;
+            }
+        }
+        raw_result_kvs = topster.sort();
+        found = all_result_ids.size();
+        return Option<bool>(true);
+    }
+
+    // vecdex->searchKnnCloserFirst(q, k, ef, &filterFunctor): closest first, label = seq_id
+    std::vector<std::pair<float, size_t>> searchKnnCloserFirst(const float* query, size_t k, size_t ef,
+                                                               const std::vector<uint32_t>* filter_ids = nullptr) {
+        std::vector<float> dist(k);
+        std::vector<uint32_t> labels(k);
+        uint32_t n = 0;
+        int32_t slot = filter_ids ? 0 : -1;
+        uint64_t off[2] = {0, filter_ids ? filter_ids->size() : 0};
+        const uint32_t zero = 0;
+        std::vector<std::pair<float, size_t>> out;
+        if(tsgpu_knn_batch(h, query, 1, (uint32_t) k, (uint32_t) ef, &slot, filter_ids ? 1 : 0, off,
+                           filter_ids && !filter_ids->empty() ? filter_ids->data() : &zero, dist.data(), labels.data(), &n) != TSGPU_OK) {
+            err = tsgpu_last_error();
+            return out;
+        }
+        for(uint32_t i = 0; i < n; i++) out.emplace_back(dist[i], (size_t) labels[i]);
+        return out;
+    }
+};
+
+// Tokenizer's ASCII rule (src/tokenizer.cpp:232-290): alnum kept and lower-cased, space/newline split, other chars dropped
+inline std::vector<std::string> tokenize_ascii(const std::string& text) {
+    std::vector<std::string> out;
+    std::string cur;
+    for(unsigned char ch: text) {
+        if(ch < 128 && std::isalnum(ch)) cur.push_back((char) std::tolower(ch));
+        else if(ch == ' ' || ch == '\n') { if(!cur.empty()) out.push_back(cur.substr(0, 100)); cur.clear(); }
+    }
+    if(!cur.empty()) out.push_back(cur.substr(0, 100));
+    return out;
+}
+
+}  // namespace tsgpu
