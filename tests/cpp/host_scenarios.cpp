@@ -81,7 +81,7 @@ static void collection_scenarios(const std::string& jsonl) {
         std::string id = json_str(line, "id");
         ext_ids.push_back(id.empty() ? std::to_string(docs.size() - 1) : id);
     }
-    CHECK(docs.size() == 24);
+    CHECK(docs.size() == 25);        // 24 lines + the dummy record
     tsgpu::Index index((uint32_t) docs.size());
     tsgpu::field_mirror_t title;
     std::unordered_map<uint32_t, int64_t> points;

@@ -267,6 +267,7 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
     const uint32_t warp = tid >> 5, lane = tid & 31;
     long long* const gthr_p = P.q_thr + cd.q;
     uint32_t prev_fd = 0xFFFFFFFFu;
+    uint32_t qn = 0;                               // queue length, identical in every thread (see the barriers below)
 
     // Scores queue entries [base, base+cnt) (cnt <= 128) with all threads busy, appends the survivors to the top-K
     // buffer and compacts that buffer when the next batch might not fit.
@@ -275,7 +276,13 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
         bool keep = false;
         int64_t sc[3] = {0, 0, 0};
         uint32_t mid = 0;
-        if(tid < cnt) {
+        bool valid = tid < cnt;
+        if(valid && cd.mode == 1 && qd.n_excl && excluded(qd.excl, qd.n_excl, q_id[base + tid])) valid = false;   // dense mode excludes here
+        if(cd.mode == 1) {
+            const uint32_t vb = __ballot_sync(0xffffffffu, valid);
+            if(lane == 0 && vb) atomicAdd(&s_matches, (uint32_t) __popc(vb));
+        }
+        if(valid) {
             const uint32_t src = base + tid;
             mid = q_id[src];
             FieldAgg agg; field_agg_init(agg);
@@ -363,28 +370,29 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
                 if(qd.filter_bitmap) word &= __ldg(qd.filter_bitmap + wi);
             }
             for(;;) {
-                const int any = __syncthreads_or(word != 0);          // also publishes the previous round's queue writes
-                if(s_qn >= kThreads) {
-                    const uint32_t qn = s_qn;
+                // Every decision below is taken from values that are uniform across the CTA by construction (the barrier's
+                // count and the register `qn`), never from shared memory that a faster warp may already be updating.
+                const uint32_t cnt = (uint32_t) __syncthreads_count(word != 0);    // also publishes the previous round's queue writes
+                if(cnt == 0) break;
+                if(qn >= kThreads) {                                   // make room: cnt <= 128 more entries are coming
                     score_batch(qn - kThreads, kThreads);
-                    if(tid == 0) s_qn = qn - kThreads;
+                    qn -= kThreads;
+                    if(tid == 0) s_qn = qn;
                     __syncthreads();
                 }
-                if(!any) break;
-                bool alive = word != 0;
+                const bool has = word != 0;
                 uint32_t id = 0;
-                if(alive) {
+                if(has) {
                     const uint32_t bit = __ffs(word) - 1;
                     word &= word - 1;
                     id = (wi << 5) | bit;
-                    if(qd.n_excl && excluded(qd.excl, qd.n_excl, id)) alive = false;
                 }
-                const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+                const uint32_t bal = __ballot_sync(0xffffffffu, has);
                 if(bal) {
                     uint32_t qb = 0;
-                    if(lane == 0) { qb = atomicAdd(&s_qn, (uint32_t) __popc(bal)); atomicAdd(&s_matches, (uint32_t) __popc(bal)); }
+                    if(lane == 0) qb = atomicAdd(&s_qn, (uint32_t) __popc(bal));
                     qb = __shfl_sync(0xffffffffu, qb, 0);
-                    if(alive) {
+                    if(has) {
                         const uint32_t slot = qb + __popc(bal & ((1u << lane) - 1u));
                         q_id[slot] = id;
                         for(uint32_t j = 0; j < n_lists; j++) {
@@ -399,6 +407,7 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
                         }
                     }
                 }
+                qn += cnt;
             }
         }
     } else
@@ -427,6 +436,7 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
         if(alive && qd.n_excl) alive = !excluded(qd.excl, qd.n_excl, id);
         if(qd.filter_empty) alive = false;
         if(tid == 0) s_driver_ids += cnt;
+        bool enq = false;
 
         // Everything up to the enqueue is warp-private (no CTA barrier): each warp owns 32 consecutive candidates.
         const uint32_t wbase = warp * 32;
@@ -481,6 +491,7 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
                 if(((cd.req_mask >> r) & 1) && !any) alive = false;
             }
             // ---- enqueue matches: one shared-memory atomic per warp reserves the slots
+            enq = alive;
             const uint32_t bal = __ballot_sync(0xffffffffu, alive);
             if(bal) {
                 uint32_t qb = 0;
@@ -497,18 +508,22 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
                 }
             }
         }
-        __syncthreads();                          // the only CTA barrier of a tile: queue writes are visible
-        if(s_qn >= kThreads) {                    // scoring happens 128 docs at a time so no lane idles
-            const uint32_t qn = s_qn;
+        // the only CTA barrier of a tile: queue writes become visible, and its count keeps the queue length `qn` uniform in
+        // registers (reading s_qn here would race with the next tile's enqueues of a faster warp)
+        qn += (uint32_t) __syncthreads_count(enq);
+        if(qn >= kThreads) {                      // scoring happens 128 docs at a time so no lane idles
             score_batch(qn - kThreads, kThreads);
-            if(tid == 0) s_qn = qn - kThreads;
+            qn -= kThreads;
+            if(tid == 0) s_qn = qn;
             __syncthreads();
         }
     }
     // ---- drain the queue
     __syncthreads();
-    if(s_qn) {
-        score_batch(0, s_qn);
+    while(qn) {
+        const uint32_t c = qn < (uint32_t) kThreads ? qn : (uint32_t) kThreads;
+        score_batch(qn - c, c);
+        qn -= c;
         __syncthreads();
     }
 

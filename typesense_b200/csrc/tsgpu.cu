@@ -211,7 +211,7 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
         uint32_t tiles = 0;
         for(uint32_t f = 0; f <= (uint32_t) kMaxFieldSlots; f++) cd.drv_tile_off[f] = 0;
         cd.mode = 0; cd.n_words = (uint32_t) (((uint64_t) idx->n_docs + 31) / 32);
-        bool all_dense = drv != kNone;
+        bool all_dense = drv != kNone && getenv("TSGPU_DENSE_MODE") && atoi(getenv("TSGPU_DENSE_MODE")) == 1;   // opt-in until measured faster at scale
         for(uint32_t r = 0; r < n_req && all_dense; r++) {
             if(!((cd.req_mask >> r) & 1)) continue;
             for(uint32_t f = 0; f < F; f++) {
@@ -219,6 +219,14 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
                 if(l != TSGPU_NO_LIST && idx->fields[b->field_ids[f]].h_list_dense[l] == kNone) { all_dense = false; break; }
             }
         }
+        // candidate-mode tiles of the driver vs word tiles of the whole id space: a word tile is ~3x cheaper than a
+        // candidate tile, so the bitmap AND only pays when the driver itself covers a good part of the collection
+        uint32_t cand_tiles = 0;
+        if(drv != kNone) for(uint32_t f = 0; f < F; f++) {
+            const uint32_t l = cd.lists[drv * F + f];
+            if(l != TSGPU_NO_LIST) cand_tiles += (uint32_t) ((df_of(f, l) + tsdev::kBlock - 1) / tsdev::kBlock);
+        }
+        if(all_dense && cand_tiles < 2 * ((cd.n_words + kThreads - 1) / kThreads)) all_dense = false;
         if(all_dense) {
             // every required token is a dense list: word-parallel bitmap AND over the whole id space (kw_kernels.cuh)
             cd.mode = 1;
@@ -846,7 +854,7 @@ tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint
     CU(up(5, f->pos_off, (n_post + 1) * 8, true));
     CU(up(6, f->positions, n_pos * 4, true));
     // dense lists: bitmap + rank directory (see postings_device.cuh)
-    tspack::pack_dense(L, fm.h_list_off.data(), h_ids.data(), idx->n_docs, std::max<uint64_t>(64, idx->n_docs / 128), pk);
+    tspack::pack_dense(L, fm.h_list_off.data(), h_ids.data(), idx->n_docs, std::max<uint64_t>(64, idx->n_docs / (uint64_t) std::max(1, getenv("TSGPU_DENSE_DIV") ? atoi(getenv("TSGPU_DENSE_DIV")) : 64)), pk);
     fm.h_list_dense = pk.list_dense;
     CU(up(7, pk.list_dense.data(), pk.list_dense.size() * 4, false));
     CU(up(8, pk.dense_bits.data(), pk.dense_bits.size() * 4, false));
