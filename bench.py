@@ -316,7 +316,9 @@ def run_tsgpu(args, rank, world, local_rank):
         t0 = time.perf_counter()
         sts = []
         for i in range(args.steps):
-            sts.append(step(args.warmup + i, resident))
+            t1 = time.perf_counter()
+            sts.append(step(args.warmup + i, resident))            # the C-ABI call is synchronous: results are final on return
+            sts[-1]["wall_ms"] = 1000 * (time.perf_counter() - t1)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -340,6 +342,20 @@ def run_tsgpu(args, rank, world, local_rank):
     sts_iso = [step(args.warmup + i, True) for i in range(min(args.steps, 4))]
     os.environ.pop("TSGPU_KNN_OVERLAP_BLOCKS", None)
     launches_per_region = (launches * args.steps) // (args.steps + args.warmup)
+    # latency of a small multi_search (64 queries, host buffers in and out), the p50/p99 half of BASELINE.json's metric
+    lat_small = []
+    if rank == 0:
+        nl = min(64, nq)
+        for i in range(48):
+            gb, qv = gbatches[i % n_b]
+            hb = gb.head(nl)
+            t1 = time.perf_counter()
+            if hybrid:
+                gi.hybrid_search(hb, qv_pin[i % n_b][:nl], vp, stride, out=(kv_pin, cnt_pin, fnd_pin))
+            else:
+                gi.keyword_search(hb, stride, out=(kv_pin, cnt_pin, fnd_pin))
+            lat_small.append(1000 * (time.perf_counter() - t1))
+        lat_small = lat_small[8:]
 
     # parity spot check + recall on rank 0 (outside the timed region)
     extra = {}
@@ -424,6 +440,12 @@ def run_tsgpu(args, rank, world, local_rank):
                "e2e": {"value": e2e, "unit": "queries/s", "ms_per_step": 1000 * dt_e2e / args.steps,
                        "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"])},
                "gpu_launches": int(launches_per_region), "clocks": clocks}
+        lat_b = sorted(s_["wall_ms"] for s_ in sts_e2e)
+        pct = lambda xs, p: float(xs[min(len(xs) - 1, int(round(p * (len(xs) - 1))))]) if xs else None
+        ls = sorted(lat_small)
+        out["latency_ms"] = {"note": "wall time of one synchronous multi_search call with host buffers; every query of a call completes with it",
+                             "batch": {"queries": nq, "p50": pct(lat_b, 0.5), "p99": pct(lat_b, 0.99), "calls": len(lat_b)},
+                             "small": {"queries": min(64, nq), "p50": pct(ls, 0.5), "p99": pct(ls, 0.99), "calls": len(ls)}}
         out.update(extra)
         print(json.dumps(out), flush=True)
     gi.close()

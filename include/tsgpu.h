@@ -159,6 +159,27 @@ tsgpu_status tsgpu_intersect(tsgpu_index* idx, uint32_t field, const uint32_t* l
 tsgpu_status tsgpu_phrase_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k,
                                   const uint32_t* ids, size_t n, uint32_t* out_ids, size_t* out_n);
 
+/* posting_t::get_exact_matches / posting_list_t::get_exact_matches (src/posting.cpp:485, src/posting_list.cpp:1281-1452;
+ * call sites src/index.cpp:3232, src/filter_result_iterator.cpp:3050 — the `:=` string filter): of the ascending
+ * `ids`, keep those whose field value (or one of its array elements) is exactly the k tokens in order.
+ * As at the reference's call sites, `ids` must come from the intersection of the same lists; an id absent from one
+ * of the lists is dropped (the reference would read the next posting's offsets instead). */
+tsgpu_status tsgpu_exact_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k,
+                                 const uint32_t* ids, size_t n, uint32_t* out_ids, size_t* out_n);
+
+/* posting_list_t::get_prefix_matches (src/posting_list.cpp:1129-1279; call site src/filter_result_iterator.cpp:3002):
+ * same, but the value only has to START with the k tokens. */
+tsgpu_status tsgpu_prefix_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k,
+                                  const uint32_t* ids, size_t n, uint32_t* out_ids, size_t* out_n);
+
+/* ArrayUtils::and_scalar / or_scalar / exclude_scalar (include/array_utils.h:13-19, src/array_utils.cpp:4-170; the
+ * all_result_ids maintenance at src/index.cpp:5081-5090 and the filter combinators): set operation on two STRICTLY
+ * ascending id arrays with ids < n_docs (what the index always holds; anything else is TSGPU_ERR_INVALID).
+ * EXCLUDE = a minus b. Result ascending in out_ids (capacity `cap`), count in *out_n. */
+enum { TSGPU_SET_AND = 0, TSGPU_SET_OR = 1, TSGPU_SET_EXCLUDE = 2 };
+tsgpu_status tsgpu_ids_setop(tsgpu_index* idx, int op, const uint32_t* a, size_t na, const uint32_t* b, size_t nb,
+                             uint32_t* out_ids, size_t cap, size_t* out_n);
+
 /* search_all_candidates -> search_across_fields -> or_iterator_t::intersect + compute_aggregated_score +
  * compute_sort_scores + Topster::add (src/index.cpp:1794, 5385-5596), batched over queries.
  * out_kv[q*kv_stride ..] = the query's Topster in Topster::sort() order, out_count[q] entries;

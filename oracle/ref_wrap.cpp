@@ -176,6 +176,16 @@ size_t ref_plist_exact_matches(void** hs, uint32_t k, int field_is_array, const 
     posting_list_t::get_exact_matches(its, field_is_array, ids, n, o, n_out);
     return n_out;
 }
+size_t ref_plist_prefix_matches(void** hs, uint32_t k, int field_is_array, const uint32_t* ids, uint32_t n,
+                                uint32_t* out) {
+    std::vector<posting_list_t::iterator_t> its;
+    its.reserve(k);
+    for(uint32_t i = 0; i < k; i++) its.push_back(((posting_list_t*) hs[i])->new_iterator());
+    size_t n_out = 0;
+    uint32_t* o = out;
+    posting_list_t::get_prefix_matches(its, field_is_array, ids, n, o, n_out);
+    return n_out;
+}
 
 // ---------------------------------------------------------------- Match (include/match_score.h:129-275)
 // tok_off[t]..tok_off[t+1] index `positions`; last_token[t] flags. out[4] = words_present, distance, max_offset, exact

@@ -23,6 +23,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <bitset>
 #include <queue>
 #include <random>
 #include <thread>
@@ -995,6 +996,102 @@ size_t tso_phrase_matches(void* idx, uint32_t field, const uint32_t* lists, uint
         }
     }
     return n_out;
+}
+
+// posting_list_t::get_exact_matches (src/posting_list.cpp:1281-1452) when `exact`, get_prefix_matches (:1129-1279)
+// otherwise. Restated per id; the iterator is expected to sit on `id` (callers pass ids of the lists' intersection),
+// ids missing from a list are skipped.
+static bool positional_match_one(const std::vector<OffSlice>& sl, bool field_is_array, bool exact) {
+    const size_t k = sl.size();
+    if(k == 1) {
+        if(exact) return is_single_token_verbatim_match(sl[0], field_is_array);
+        return sl[0].n != 0 && sl[0].p[0] == 1;                    // is_single_token_prefix_match (:1114-1127)
+    }
+    if(!field_is_array) {
+        bool is_match = true;
+        for(int j = (int) k - 1; j >= 0; j--) {
+            const uint32_t* offsets = sl[j].p;
+            size_t start = 0, end = sl[j].n;
+            if(end == 0) return false;
+            if(exact && j == (int) k - 1) {
+                if(offsets[end - 1] != 0 || (end >= 2 && offsets[end - 2] != k)) { is_match = false; break; }
+            }
+            while(start < end) {
+                uint32_t offset = offsets[start++];
+                if(offset == (uint32_t) (j + 1)) { is_match = true; break; }
+                if(offset > (uint32_t) (j + 1)) { is_match = false; break; }
+            }
+            if(!is_match) break;
+        }
+        return is_match;
+    }
+    struct Meta { std::bitset<128> token_index; bool has_last_token = false; };
+    std::map<size_t, Meta> by_elem;
+    for(int j = (int) k - 1; j >= 0; j--) {
+        const uint32_t* offsets = sl[j].p;
+        size_t start = 0, end = sl[j].n;
+        int prev_pos = -1;
+        bool any_last = false, found = false;
+        size_t n_matching = 0;
+        while(start < end) {
+            int pos = (int) offsets[start++];
+            if(pos == prev_pos) {
+                if(start >= end) break;
+                size_t array_index = offsets[start];
+                if(exact && start + 1 < end && offsets[start + 1] == 0 && (size_t) pos == k) {
+                    by_elem[array_index].has_last_token = true;
+                    any_last = true;
+                    start++;
+                }
+                if(found && j + 1 < 128) by_elem[array_index].token_index.set(j + 1);
+                start++;
+                prev_pos = -1;
+                found = false;
+                continue;
+            }
+            if(pos == j + 1) { found = true; n_matching++; }
+            prev_pos = pos;
+        }
+        if(exact && j == (int) k - 1 && !any_last) return false;
+        if(n_matching == 0) return false;
+    }
+    for(auto& kv: by_elem) if(kv.second.token_index.count() == k && (!exact || kv.second.has_last_token)) return true;
+    return false;
+}
+
+static size_t positional_matches(void* idx, uint32_t field, const uint32_t* lists, uint32_t k,
+                                 const uint32_t* ids, size_t n, uint32_t* out, bool exact) {
+    const Index& ix = *(Index*) idx;
+    const tso_field& fld = ix.fields[field];
+    std::vector<ListCur> its(k);
+    for(uint32_t j = 0; j < k; j++) {
+        its[j].ids = fld.ids + fld.list_off[lists[j]];
+        its[j].n = (size_t) (fld.list_off[lists[j] + 1] - fld.list_off[lists[j]]);
+        its[j].base = fld.list_off[lists[j]];
+    }
+    size_t n_out = 0;
+    std::vector<OffSlice> sl;
+    for(size_t i = 0; i < n; i++) {
+        sl.clear();
+        bool on_id = true;
+        for(uint32_t j = 0; j < k; j++) {
+            its[j].skip_to(ids[i]);
+            if(!its[j].valid() || its[j].id() != ids[i]) { on_id = false; break; }
+            uint64_t p = its[j].base + its[j].i;
+            sl.push_back(OffSlice{fld.positions + fld.pos_off[p], (uint32_t) (fld.pos_off[p + 1] - fld.pos_off[p])});
+        }
+        if(on_id && positional_match_one(sl, fld.is_array != 0, exact)) out[n_out++] = ids[i];
+    }
+    return n_out;
+}
+
+size_t tso_exact_matches(void* idx, uint32_t field, const uint32_t* lists, uint32_t k,
+                         const uint32_t* ids, size_t n, uint32_t* out) {
+    return positional_matches(idx, field, lists, k, ids, n, out, true);
+}
+size_t tso_prefix_matches(void* idx, uint32_t field, const uint32_t* lists, uint32_t k,
+                          const uint32_t* ids, size_t n, uint32_t* out) {
+    return positional_matches(idx, field, lists, k, ids, n, out, false);
 }
 
 int64_t tso_float_to_int64(float f) { return float_to_int64(f); }

@@ -145,6 +145,13 @@ uint32_t tso_topster_run(uint32_t capacity, const tso_kv* in, uint32_t n, tso_kv
 size_t tso_phrase_matches(void* idx, uint32_t field, const uint32_t* lists, uint32_t k,
                           const uint32_t* ids, size_t n, uint32_t* out);
 
+/* ---- `:=` / prefix string-filter checks over an id set (posting_list_t::get_exact_matches, src/posting_list.cpp:1281;
+ *      get_prefix_matches, :1129) */
+size_t tso_exact_matches(void* idx, uint32_t field, const uint32_t* lists, uint32_t k,
+                         const uint32_t* ids, size_t n, uint32_t* out);
+size_t tso_prefix_matches(void* idx, uint32_t field, const uint32_t* lists, uint32_t k,
+                          const uint32_t* ids, size_t n, uint32_t* out);
+
 /* ---- vectors */
 float tso_ip_distance(const float* a, const float* b, uint32_t dim);
 void  tso_normalize(const float* src, float* dst, uint32_t dim);

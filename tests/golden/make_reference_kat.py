@@ -52,6 +52,17 @@ kat = {
     "expect_ids": [1, 0, 2],
     "expect_distances": [3.409385681152344e-05, 0.04329806566238403, 0.15141665935516357],
     "filtered": {"filter_ids": [0, 1], "expect_ids": [1, 0]}},
+  "array_utils": [  # test/array_utils_test.cpp:5-176 (AndScalar, OrScalar*, FilterArray); op 0 and, 1 or, 2 exclude
+    {"src": "test/array_utils_test.cpp:5-37", "op": 0, "a": list(range(9)), "b": [3, 6, 9], "expect": [3, 6]},
+    {"src": "test/array_utils_test.cpp:39-71", "op": 1, "a": list(range(9)), "b": [3, 6, 9], "expect": list(range(10))},
+    {"src": "test/array_utils_test.cpp:73-98", "op": 1, "a": list(range(9)), "b": [0, 4, 5], "expect": list(range(9))},
+    {"src": "test/array_utils_test.cpp:100-118", "op": 1, "a": list(range(9)), "b": [], "expect": list(range(9))},
+    {"src": "test/array_utils_test.cpp:100-118", "op": 1, "a": [], "b": list(range(9)), "expect": list(range(9))},
+    {"src": "test/array_utils_test.cpp:120-144", "op": 2, "a": list(range(9)), "b": [0, 1, 5, 7, 8], "expect": [2, 3, 4, 6]},
+    {"src": "test/array_utils_test.cpp:146-158", "op": 2, "a": list(range(9)), "b": list(range(9)), "expect": []},
+    {"src": "test/array_utils_test.cpp:163-172", "op": 2, "a": [58, 118, 185, 260, 322, 334, 353],
+     "b": [58, 103, 116, 117, 137, 154, 191, 210, 211, 284, 299, 302, 306, 309, 332, 334, 360], "expect": [118, 185, 260, 322, 353]},
+  ],
   "text_match_layout": {  # test/union_test.cpp:810: single token, one field, weight 15, cost 0
     "src": "test/union_test.cpp:810", "value": 578730123365189753},
 }

@@ -155,6 +155,30 @@ void hs_probe_ids(const uint32_t* ids, uint64_t n, const uint32_t* queries, uint
     for(uint64_t i = 0; i < nq; i++) out[i] = n ? probe_list(d, 0, 0, pk.list_blk_off[1] - 1, queries[i]) : kNone;
 }
 
+// isect_tiles_kernel's id-set modes on one flat field: mode 1 phrase, 2 exact, 3 prefix. Per id: locate it in each list
+// (ids absent from a list are dropped) and run the same per-document routine the kernel thread runs.
+size_t hs_idset_matches(const tsgpu_field* f, const uint32_t* lists, uint32_t k, const uint32_t* ids, size_t n, int mode,
+                        uint32_t* out) {
+    size_t n_out = 0;
+    for(size_t i = 0; i < n; i++) {
+        RawTok toks[kMaxTokens];
+        bool alive = true;
+        for(uint32_t j = 0; j < k && alive; j++) {
+            const uint32_t* b = f->ids + f->list_off[lists[j]];
+            const uint32_t* e = f->ids + f->list_off[lists[j] + 1];
+            const uint32_t* it = std::lower_bound(b, e, ids[i]);
+            if(it == e || *it != ids[i]) { alive = false; break; }
+            const uint64_t p = (uint64_t) (it - f->ids);
+            toks[j].p = f->positions + f->pos_off[p];
+            toks[j].n = (uint32_t) (f->pos_off[p + 1] - f->pos_off[p]);
+        }
+        if(!alive) continue;
+        const bool ok = mode == 1 ? phrase_match_doc(toks, (int) k) : positional_match_doc(toks, (int) k, f->is_array != 0, mode == 2);
+        if(ok) out[n_out++] = ids[i];
+    }
+    return n_out;
+}
+
 int hs_phrase_match_doc(uint32_t k, const uint32_t* tok_off, const uint32_t* raw) {
     RawTok toks[kMaxTokens];
     for(uint32_t t = 0; t < k; t++) { toks[t].p = raw + tok_off[t]; toks[t].n = tok_off[t + 1] - tok_off[t]; }

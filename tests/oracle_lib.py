@@ -62,8 +62,9 @@ def oracle():
                                                 C.c_uint32]
         L.tso_topster_run.restype = C.c_uint32
         L.tso_topster_run.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
-        L.tso_phrase_matches.restype = C.c_size_t
-        L.tso_phrase_matches.argtypes = [C.c_void_p, C.c_uint32, u32p, C.c_uint32, u32p, C.c_size_t, u32p]
+        for n in ("tso_phrase_matches", "tso_exact_matches", "tso_prefix_matches"):
+            getattr(L, n).restype = C.c_size_t
+            getattr(L, n).argtypes = [C.c_void_p, C.c_uint32, u32p, C.c_uint32, u32p, C.c_size_t, u32p]
         L.tso_ip_distance.restype = C.c_float
         L.tso_ip_distance.argtypes = [f32p, f32p, C.c_uint32]
         L.tso_normalize.argtypes = [f32p, f32p, C.c_uint32]
@@ -131,7 +132,7 @@ def ref():
         L.ref_plist_block_intersect.restype = C.c_size_t
         L.ref_plist_block_intersect.argtypes = [C.POINTER(vp), C.c_uint32, u32p, C.c_size_t, u32p, C.c_size_t, u32p,
                                                 C.c_size_t]
-        for n in ("ref_plist_phrase_matches", "ref_plist_exact_matches"):
+        for n in ("ref_plist_phrase_matches", "ref_plist_exact_matches", "ref_plist_prefix_matches"):
             getattr(L, n).restype = C.c_size_t
             getattr(L, n).argtypes = [C.POINTER(vp), C.c_uint32, C.c_int, u32p, C.c_uint32, u32p]
         L.ref_match.argtypes = [C.c_uint32, u32p, u16p, u8p, C.c_int, u8p]

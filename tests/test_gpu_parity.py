@@ -124,6 +124,51 @@ def test_intersect_and_phrase(coll):
                 assert gi.phrase_matches(fi, lists.tolist(), ids).tolist() == out[:n].tolist()
 
 
+def test_exact_and_prefix_matches(coll):
+    """tsgpu_exact_matches / tsgpu_prefix_matches vs the oracle (itself pinned on the reference's compiled code)."""
+    from test_hostsim import idset_cases
+    n_docs, fds, flats, pts, gi, oi = coll
+    L = ol.oracle()
+    rng = np.random.default_rng(2024)
+    hits = {"exact": 0, "prefix": 0, "phrase": 0}
+    for fi in (0, 1, 2):
+        oix = ol.OracleIndex(n_docs, [flats[fi]], [])
+        for lists, ids in idset_cases(rng, fds[fi], 120):
+            k = len(lists)
+            for name, ofn, gfn in (("exact", L.tso_exact_matches, gi.exact_matches), ("prefix", L.tso_prefix_matches, gi.prefix_matches),
+                                   ("phrase", L.tso_phrase_matches, gi.phrase_matches)):
+                out = np.zeros(len(ids), np.uint32)
+                n = ofn(oix.h, 0, ol.p32(lists), k, ol.p32(ids), len(ids), ol.p32(out))
+                assert gfn(fi, lists.tolist(), ids).tolist() == out[:n].tolist(), (fi, name, lists.tolist())
+                hits[name] += n
+    assert min(hits.values()) > 20, hits
+
+
+def test_ids_setop(coll):
+    """tsgpu_ids_setop: the reference's array_utils_test.cpp vectors, then random strictly-ascending arrays vs the oracle."""
+    from test_oracle_ref import KAT
+    n_docs, fds, flats, pts, gi, oi = coll
+    for case in KAT["array_utils"]:
+        assert gi.ids_setop(case["op"], case["a"], case["b"]).tolist() == case["expect"], case["src"]
+    L = ol.oracle()
+    rng = np.random.default_rng(8)
+    names = ("tso_and_scalar", "tso_or_scalar", "tso_exclude_scalar")
+    for it in range(30):
+        hi = int(rng.choice([40, 500, n_docs]))
+        a = np.unique(rng.integers(0, hi, int(rng.integers(0, 3000)))).astype(np.uint32)
+        b = np.unique(rng.integers(0, hi, int(rng.integers(0, 3000)))).astype(np.uint32)
+        a0 = a if len(a) else np.zeros(1, np.uint32)
+        b0 = b if len(b) else np.zeros(1, np.uint32)
+        for op in range(3):
+            out = np.zeros(len(a) + len(b) + 1, np.uint32)
+            n = getattr(L, names[op])(ol.p32(a0), len(a), ol.p32(b0), len(b), ol.p32(out))
+            assert gi.ids_setop(op, a, b).tolist() == out[:n].tolist(), (it, op)
+    with pytest.raises(capi.TsgpuError):
+        gi.ids_setop(0, [3, 3, 4], [3])                   # not strictly ascending
+    with pytest.raises(capi.TsgpuError):
+        gi.ids_setop(1, [1, n_docs], [3])                 # id out of range
+
+
 @pytest.fixture(scope="module")
 def vec_coll():
     n, dim = 6000, 128

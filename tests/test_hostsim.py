@@ -29,6 +29,8 @@ def hs():
     L.hs_keyword_combo.argtypes = [C.POINTER(S.FieldStruct), C.c_uint32, C.POINTER(S.KwBatchStruct), C.c_uint32, C.c_uint32,
                                    S.u32p, S.u64p, C.c_size_t]
     L.hs_phrase_match_doc.argtypes = [C.c_uint32, S.u32p, S.u32p]
+    L.hs_idset_matches.restype = C.c_size_t
+    L.hs_idset_matches.argtypes = [C.POINTER(S.FieldStruct), S.u32p, C.c_uint32, S.u32p, C.c_size_t, C.c_int, S.u32p]
     L.hs_probe_ids.argtypes = [S.u32p, C.c_uint64, S.u32p, C.c_uint64, S.u32p]
     return L
 
@@ -137,3 +139,48 @@ def test_device_probe_fuzz(hs):
         hit = (pos < len(ids)) & (ids[np.minimum(pos, len(ids) - 1)] == q)
         exp = np.where(hit, pos, 0xFFFFFFFF).astype(np.uint32)
         assert (out == exp).all(), (trial, kind, n)
+
+
+def idset_cases(rng, fd, n_cases, kmax=4):
+    """(lists, candidate ids) pairs: the first k tokens of a doc (prefix/exact hits), a random window (phrase hits) or
+    random tokens; candidates = intersection of the lists, as at the reference's call sites."""
+    n_docs = len(fd.doc_off) - 1
+    for _ in range(n_cases):
+        d = int(rng.integers(0, n_docs))
+        a, e = int(fd.doc_off[d]), int(fd.doc_off[d + 1])
+        if e == a:
+            continue
+        k = int(rng.integers(1, min(kmax, e - a) + 1))
+        mode = int(rng.integers(0, 3))
+        s = a if mode == 0 else int(rng.integers(a, e - k + 1))
+        lists = fd.doc_tok[s:s + k].astype(np.uint32)
+        if mode == 2:
+            lists = lists[rng.permutation(k)]
+        cand = None
+        for l in lists:
+            ids = fd.flat.ids[int(fd.flat.list_off[l]):int(fd.flat.list_off[l + 1])]
+            cand = ids if cand is None else np.intersect1d(cand, ids)
+        if cand is None or len(cand) == 0:
+            continue
+        yield np.ascontiguousarray(lists), np.ascontiguousarray(cand, np.uint32)
+
+
+def test_device_idset_modes_match_oracle(hs, small_collection):
+    n_docs, fds, _ = small_collection
+    L = ol.oracle()
+    rng = np.random.default_rng(4242)
+    hits = {1: 0, 2: 0, 3: 0}
+    for fi in (1, 2, 0):
+        fd = fds[fi]
+        ix = ol.OracleIndex(n_docs, [fd.flat], [])
+        fs = fd.flat.struct()
+        for lists, ids in idset_cases(rng, fd, 150):
+            k = len(lists)
+            for mode, fn in ((1, L.tso_phrase_matches), (2, L.tso_exact_matches), (3, L.tso_prefix_matches)):
+                out = np.zeros(len(ids), np.uint32)
+                n = fn(ix.h, 0, ol.p32(lists), k, ol.p32(ids), len(ids), ol.p32(out))
+                hout = np.zeros(len(ids), np.uint32)
+                hn = hs.hs_idset_matches(C.byref(fs), ol.p32(lists), k, ol.p32(ids), len(ids), mode, ol.p32(hout))
+                assert out[:n].tolist() == hout[:hn].tolist(), (fi, mode, lists.tolist())
+                hits[mode] += n
+    assert min(hits.values()) > 20, hits

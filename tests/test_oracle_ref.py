@@ -458,3 +458,44 @@ def test_ref_phrase_matches(small_collection):
             assert out[:n].tolist() == rout[:rn].tolist()
             hits += n
     assert hits > 10
+
+
+@needs_ref
+def test_ref_exact_and_prefix_matches(small_collection):
+    """get_exact_matches / get_prefix_matches (src/posting_list.cpp:1129-1452): oracle restatement vs the reference's own
+    compiled code, plain and array fields."""
+    from test_hostsim import idset_cases
+    n_docs, fds, _ = small_collection
+    R, L = ol.ref(), ol.oracle()
+    rng = np.random.default_rng(91)
+    hits = {"exact": 0, "prefix": 0}
+    for fi in (2, 1, 0):
+        fd = fds[fi]
+        ix = ol.OracleIndex(n_docs, [fd.flat], [])
+        for lists, ids in idset_cases(rng, fd, 120):
+            k = len(lists)
+            pls = ol.ref_plists_of(fd.flat, lists.tolist(), 256)
+            hs = (C.c_void_p * k)(*[p.h for p in pls])
+            for name, ofn, rfn in (("exact", L.tso_exact_matches, R.ref_plist_exact_matches),
+                                   ("prefix", L.tso_prefix_matches, R.ref_plist_prefix_matches)):
+                out = np.zeros(len(ids), np.uint32)
+                n = ofn(ix.h, 0, ol.p32(lists), k, ol.p32(ids), len(ids), ol.p32(out))
+                rout = np.zeros(len(ids), np.uint32)
+                rn = rfn(hs, k, int(fd.flat.is_array), ol.p32(ids), len(ids), ol.p32(rout))
+                assert out[:n].tolist() == rout[:rn].tolist(), (fi, name, lists.tolist())
+                hits[name] += n
+    assert hits["exact"] > 20 and hits["prefix"] > 40, hits
+
+
+def test_kat_array_utils():
+    """test/array_utils_test.cpp literal vectors: oracle restatement (and the reference's own code when present)."""
+    fams = [("tso_", ol.oracle())] + ([("ref_", ol.ref())] if ol.have_ref() else [])
+    names = ("and_scalar", "or_scalar", "exclude_scalar")
+    for case in KAT["array_utils"]:
+        a = np.asarray(case["a"], np.uint32); b = np.asarray(case["b"], np.uint32)
+        a0 = a if len(a) else np.zeros(1, np.uint32)
+        b0 = b if len(b) else np.zeros(1, np.uint32)
+        for pre, lib in fams:
+            out = np.zeros(len(a) + len(b) + 1, np.uint32)
+            n = getattr(lib, pre + names[case["op"]])(ol.p32(a0), len(a), ol.p32(b0), len(b), ol.p32(out))
+            assert out[:n].tolist() == case["expect"], (pre, case["src"])

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libtsgpu.so")
 EXPORTS = [
     "tsgpu_last_error", "tsgpu_device_count", "tsgpu_index_create", "tsgpu_index_destroy", "tsgpu_index_load_field",
     "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy",
-    "tsgpu_intersect", "tsgpu_phrase_matches", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
+    "tsgpu_intersect", "tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches", "tsgpu_ids_setop", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
     "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats",
 ]
 
@@ -49,7 +49,9 @@ def lib():
         L.tsgpu_filter_create.argtypes = [vp, C.c_void_p, C.c_size_t, i32p]
         L.tsgpu_filter_destroy.argtypes = [vp, C.c_int32]
         L.tsgpu_intersect.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, C.c_size_t, C.POINTER(C.c_size_t)]
-        L.tsgpu_phrase_matches.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, C.c_size_t, u32p, C.POINTER(C.c_size_t)]
+        L.tsgpu_ids_setop.argtypes = [vp, C.c_int, u32p, C.c_size_t, u32p, C.c_size_t, u32p, C.c_size_t, C.POINTER(C.c_size_t)]
+        for n in ("tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches"):
+            getattr(L, n).argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, C.c_size_t, u32p, C.POINTER(C.c_size_t)]
         L.tsgpu_keyword_search_batch.argtypes = [vp, C.POINTER(KwBatchStruct), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.tsgpu_wildcard_search_batch.argtypes = [vp, C.POINTER(KwBatchStruct), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.tsgpu_knn_batch.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, i32p, C.c_uint32, u64p, u32p,
@@ -166,6 +168,31 @@ class GpuIndex:
         n = C.c_size_t(0)
         _ck(self.L.tsgpu_phrase_matches(self.h, field, ls.ctypes.data_as(u32p), len(ls), ids.ctypes.data_as(u32p), len(ids),
                                         out.ctypes.data_as(u32p), C.byref(n)))
+        return out[:n.value].copy()
+
+    def _idset(self, fn, field, lists, ids):
+        ls = np.asarray(lists, np.uint32)
+        ids = np.ascontiguousarray(ids, np.uint32)
+        out = np.zeros(max(len(ids), 1), np.uint32)
+        n = C.c_size_t(0)
+        _ck(fn(self.h, field, ls.ctypes.data_as(u32p), len(ls), ids.ctypes.data_as(u32p), len(ids), out.ctypes.data_as(u32p), C.byref(n)))
+        return out[:n.value].copy()
+
+    def exact_matches(self, field: int, lists: Sequence[int], ids: np.ndarray) -> np.ndarray:
+        return self._idset(self.L.tsgpu_exact_matches, field, lists, ids)
+
+    def prefix_matches(self, field: int, lists: Sequence[int], ids: np.ndarray) -> np.ndarray:
+        return self._idset(self.L.tsgpu_prefix_matches, field, lists, ids)
+
+    def ids_setop(self, op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        """op: 0 and, 1 or, 2 exclude (a minus b)"""
+        a = np.ascontiguousarray(a, np.uint32)
+        b = np.ascontiguousarray(b, np.uint32)
+        cap = max(1, len(a) + len(b))
+        out = np.zeros(cap, np.uint32)
+        n = C.c_size_t(0)
+        _ck(self.L.tsgpu_ids_setop(self.h, op, a.ctypes.data_as(u32p), len(a), b.ctypes.data_as(u32p), len(b),
+                                   out.ctypes.data_as(u32p), cap, C.byref(n)))
         return out[:n.value].copy()
 
     def _outs(self, nq, stride, out):

@@ -853,7 +853,7 @@ struct IsectParams {
     uint32_t n_tiles;
     uint32_t* tile_cnt;      // [n_tiles]
     uint32_t* tile_ids;      // [n_tiles*128]
-    int phrase;
+    int phrase;              // 0 intersect, 1 phrase, 2 exact (get_exact_matches), 3 prefix (get_prefix_matches)
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -919,7 +919,8 @@ isect_tiles_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ 
             const unsigned long long o0 = g.pos_off[p], o1 = g.pos_off[p + 1];
             toks[j].p = g.positions + o0; toks[j].n = (uint32_t) (o1 - o0);
         }
-        alive = phrase_match_doc(toks, (int) P.k);
+        if(P.phrase == 1) alive = phrase_match_doc(toks, (int) P.k);
+        else alive = positional_match_doc(toks, (int) P.k, (g.is_array & kFieldIsArray) != 0, P.phrase == 2);
     }
     uint32_t total;
     const uint32_t rank = cta_rank(alive, s_warp, &total);
@@ -960,6 +961,58 @@ gather_tiles_kernel(const uint32_t* __restrict__ cnt, const unsigned long long* 
     const uint32_t c = cnt[tile];
     const unsigned long long o = off[tile];
     if(threadIdx.x < c && o + threadIdx.x < cap) out[o + threadIdx.x] = tile_ids[(size_t) tile * kBlock + threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tsgpu_ids_setop: ArrayUtils::and_scalar / or_scalar / exclude_scalar (src/array_utils.cpp:4-170) on strictly
+// ascending id arrays, done in the bitmap domain: ids -> bits, one word-parallel pass combines the bitmaps and counts
+// the result per 128-word tile, scan, then every thread writes the ids of its own word in place.
+__global__ void bitmap_from_sorted_ids_kernel(const uint32_t* __restrict__ ids, size_t n, uint32_t* __restrict__ bitmap,
+                                              uint32_t n_docs, uint32_t* __restrict__ bad) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const uint32_t id = ids[i];
+    if(id >= n_docs || (i && ids[i - 1] >= id)) { *bad = 1; return; }
+    atomicOr(bitmap + (id >> 5), 1u << (id & 31));
+}
+
+__global__ void __launch_bounds__(kThreads)
+setop_count_kernel(uint32_t* __restrict__ A, const uint32_t* __restrict__ B, uint32_t n_words, int op, uint32_t* __restrict__ tile_cnt) {
+    __shared__ uint32_t s_warp[kThreads / 32];
+    const uint32_t wi = blockIdx.x * kThreads + threadIdx.x;
+    uint32_t w = 0;
+    if(wi < n_words) {
+        const uint32_t a = A[wi], b = B[wi];
+        w = op == 0 ? (a & b) : op == 1 ? (a | b) : (a & ~b);
+        A[wi] = w;
+    }
+    uint32_t c = __popc(w);
+    for(int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if(threadIdx.x == 0) { uint32_t t = 0; for(int i = 0; i < kThreads / 32; i++) t += s_warp[i]; tile_cnt[blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(kThreads)
+setop_extract_kernel(const uint32_t* __restrict__ R, uint32_t n_words, const unsigned long long* __restrict__ tile_off,
+                     uint32_t* __restrict__ out, size_t cap) {
+    __shared__ uint32_t s_warp[kThreads / 32];
+    const uint32_t wi = blockIdx.x * kThreads + threadIdx.x, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    uint32_t w = wi < n_words ? R[wi] : 0;
+    const uint32_t c = __popc(w);
+    uint32_t incl = c;                                   // inclusive warp scan of the per-word counts
+    for(int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if((int) lane >= o) incl += t; }
+    if(lane == 31) s_warp[wp] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for(uint32_t i = 0; i < wp; i++) before += s_warp[i];
+    unsigned long long o = tile_off[blockIdx.x] + before + incl - c;
+    while(w) {
+        const uint32_t bit = __ffs(w) - 1;
+        w &= w - 1;
+        if(o < cap) out[o] = (wi << 5) | bit;
+        o++;
+    }
 }
 
 }  // namespace tsk

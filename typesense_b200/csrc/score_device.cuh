@@ -507,4 +507,86 @@ TS_HD_NOINLINE bool phrase_match_doc(const RawTok* toks, int k) {
     return false;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// posting_list_t::get_exact_matches / get_prefix_matches body for one id (src/posting_list.cpp:1129-1279, 1281-1452):
+// token j of the filter value must sit at position j+1 of the field value (of some array element), and for an exact
+// match that element must also end with the last token. One walker yields the per-element facts both need.
+struct ElemFact { uint32_t array_index; bool matched; bool last; };
+struct ElemWalk { uint32_t i; uint32_t n_matching; };
+
+// next array element of token `t` (0-based query index jm1+1 == wanted position). `k` = number of query tokens;
+// `want_last` selects the exact-match variant, which also consumes the "last token of the element" flag.
+TS_HD bool elem_next(const RawTok& t, ElemWalk& w, uint32_t want_pos, uint32_t k, bool want_last, ElemFact& out) {
+    int64_t prev_pos = -1;
+    bool found = false;
+    while(w.i < t.n) {
+        const uint32_t pos = t.p[w.i];
+        w.i++;
+        if((int64_t) pos == prev_pos) {                 // end of an array element: next word is its index
+            if(w.i >= t.n) return false;                // malformed tail
+            out.array_index = t.p[w.i];
+            out.last = false;
+            if(want_last && w.i + 1 < t.n && t.p[w.i + 1] == 0 && pos == k) { out.last = true; w.i++; }
+            out.matched = found;
+            w.i++;
+            return true;
+        }
+        if(pos == want_pos) { found = true; w.n_matching++; }
+        prev_pos = pos;
+    }
+    return false;
+}
+
+// plain string field, k > 1
+TS_HD bool positional_match_plain(const RawTok* toks, int k, bool exact) {
+    for(int j = k - 1; j >= 0; j--) {
+        const RawTok& t = toks[j];
+        if(t.n == 0) return false;
+        if(exact && j == k - 1) {
+            // the last query token has to be the last token of the value: [.., k, 0]
+            if(t.p[t.n - 1] != 0 || (t.n >= 2 && t.p[t.n - 2] != (uint32_t) k)) return false;
+        }
+        for(uint32_t i = 0; i < t.n; i++) {
+            const uint32_t off = t.p[i];
+            if(off == (uint32_t) (j + 1)) break;
+            if(off > (uint32_t) (j + 1)) return false;
+        }
+    }
+    return true;
+}
+
+TS_HD_NOINLINE bool positional_match_doc(const RawTok* toks, int k, bool field_is_array, bool exact) {
+    if(k == 1) {
+        if(exact) return is_single_token_verbatim_match(toks[0], field_is_array);
+        return toks[0].n != 0 && toks[0].p[0] == 1;      // is_single_token_prefix_match (src/posting_list.cpp:1114-1127)
+    }
+    if(!field_is_array) return positional_match_plain(toks, k, exact);
+    // array field: some element must hold every token at its position (and, for exact, carry the last-token flag,
+    // which any token's walk may set). The reference's early exits are all implied failures of that test except
+    // "last query token is never a last token", kept explicitly.
+    for(int j = 0; j < k; j++) {
+        ElemWalk w{0, 0}; ElemFact f;
+        bool any_last = false;
+        while(elem_next(toks[j], w, (uint32_t) j + 1, (uint32_t) k, exact, f)) any_last |= f.last;
+        if(w.n_matching == 0) return false;
+        if(exact && j == k - 1 && !any_last) return false;
+    }
+    ElemWalk w0{0, 0}; ElemFact f0;
+    while(elem_next(toks[0], w0, 1, (uint32_t) k, exact, f0)) {
+        if(!f0.matched) continue;
+        bool all = true, last = f0.last;
+        for(int j = 0; j < k; j++) {
+            ElemWalk w{0, 0}; ElemFact f;
+            bool m = false;
+            while(elem_next(toks[j], w, (uint32_t) j + 1, (uint32_t) k, exact, f)) {
+                if(f.array_index != f0.array_index) continue;
+                m |= f.matched; last |= f.last;
+            }
+            if(!m) all = false;                           // keep walking: later tokens may still set `last`
+        }
+        if(all && (!exact || last)) return true;
+    }
+    return false;
+}
+
 }  // namespace tsdev

@@ -969,7 +969,8 @@ tsgpu_status tsgpu_filter_destroy(tsgpu_index* idx, int32_t handle) {
 }
 
 static tsgpu_status isect_common(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, const uint32_t* ids,
-                                 size_t n_ids, bool phrase, uint32_t* out_ids, size_t cap, size_t* out_n) {
+                                 size_t n_ids, int mode, uint32_t* out_ids, size_t cap, size_t* out_n) {
+    const bool phrase = mode != 0;          // every id-set mode (phrase / exact / prefix) shares the candidate-tile path
     tsgpu_status s = check_device(idx); if(s) return s;
     if(!lists || !out_n || k == 0) return fail(TSGPU_ERR_INVALID, "bad argument");
     if(field >= idx->fields.size()) return fail(TSGPU_ERR_INVALID, "field out of range");
@@ -979,7 +980,7 @@ static tsgpu_status isect_common(tsgpu_index* idx, uint32_t field, const uint32_
     cudaStream_t st = idx->stream;
     const FieldMirror& fm = idx->fields[field];
     IsectParams P{};
-    P.field = field; P.k = k; P.phrase = phrase ? 1 : 0;
+    P.field = field; P.k = k; P.phrase = mode;
     uint64_t best = ~0ull;
     for(uint32_t j = 0; j < k; j++) {
         if(lists[j] >= fm.dev.n_lists) return fail(TSGPU_ERR_INVALID, "list out of range");
@@ -1027,12 +1028,72 @@ static tsgpu_status isect_common(tsgpu_index* idx, uint32_t field, const uint32_
 
 tsgpu_status tsgpu_intersect(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, uint32_t* out_ids,
                              size_t cap, size_t* out_n) {
-    return isect_common(idx, field, lists, k, nullptr, 0, false, out_ids, cap, out_n);
+    return isect_common(idx, field, lists, k, nullptr, 0, 0, out_ids, cap, out_n);
 }
 
 tsgpu_status tsgpu_phrase_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, const uint32_t* ids,
                                   size_t n, uint32_t* out_ids, size_t* out_n) {
-    return isect_common(idx, field, lists, k, ids, n, true, out_ids, n, out_n);
+    return isect_common(idx, field, lists, k, ids, n, 1, out_ids, n, out_n);
+}
+
+tsgpu_status tsgpu_exact_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, const uint32_t* ids,
+                                 size_t n, uint32_t* out_ids, size_t* out_n) {
+    return isect_common(idx, field, lists, k, ids, n, 2, out_ids, n, out_n);
+}
+
+tsgpu_status tsgpu_prefix_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, const uint32_t* ids,
+                                  size_t n, uint32_t* out_ids, size_t* out_n) {
+    return isect_common(idx, field, lists, k, ids, n, 3, out_ids, n, out_n);
+}
+
+tsgpu_status tsgpu_ids_setop(tsgpu_index* idx, int op, const uint32_t* a, size_t na, const uint32_t* b, size_t nb,
+                             uint32_t* out_ids, size_t cap, size_t* out_n) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!out_n || op < TSGPU_SET_AND || op > TSGPU_SET_EXCLUDE || (na && !a) || (nb && !b)) return fail(TSGPU_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    begin_call(idx);
+    *out_n = 0;
+    // the reference's degenerate cases (src/array_utils.cpp:6-8, 44-58, 118-133)
+    if(op == TSGPU_SET_AND && (na == 0 || nb == 0)) return end_call(idx, false, false);
+    if(op == TSGPU_SET_EXCLUDE && na == 0) return end_call(idx, false, false);
+    if(na == 0 && nb == 0) return end_call(idx, false, false);
+    cudaStream_t st = idx->stream;
+    const uint32_t n_words = (uint32_t) (((size_t) idx->n_docs + 31) / 32);
+    const uint32_t n_tiles = (n_words + kThreads - 1) / kThreads;
+    auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t o_a = 0, o_b = al(na * 4), o_bma = al(o_b + nb * 4), o_bmb = al(o_bma + (size_t) n_words * 4);
+    const size_t o_cnt = al(o_bmb + (size_t) n_words * 4), o_off = al(o_cnt + (size_t) n_tiles * 4), o_tot = o_off + (size_t) n_tiles * 8;
+    const size_t o_bad = o_tot + 8, o_out = al(o_bad + 8);
+    const size_t max_out = op == TSGPU_SET_AND ? std::min(na, nb) : op == TSGPU_SET_OR ? na + nb : na;
+    CU(idx->d_isect.reserve(o_out + max_out * 4 + 256));
+    unsigned char* base = idx->d_isect.as<unsigned char>();
+    if(na) CU(cudaMemcpyAsync(base + o_a, a, na * 4, cudaMemcpyDefault, st));
+    if(nb) CU(cudaMemcpyAsync(base + o_b, b, nb * 4, cudaMemcpyDefault, st));
+    idx->stats.h2d_bytes += (na + nb) * 4;
+    CU(cudaMemsetAsync(base + o_bma, 0, o_cnt - o_bma, st));
+    CU(cudaMemsetAsync(base + o_tot, 0, 16, st));
+    uint32_t* bma = reinterpret_cast<uint32_t*>(base + o_bma);
+    uint32_t* bmb = reinterpret_cast<uint32_t*>(base + o_bmb);
+    uint32_t* bad = reinterpret_cast<uint32_t*>(base + o_bad);
+    CU(cudaEventRecord(idx->ev[1], st));
+    if(na) bitmap_from_sorted_ids_kernel<<<(unsigned) ((na + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(base + o_a), na, bma, idx->n_docs, bad);
+    if(nb) bitmap_from_sorted_ids_kernel<<<(unsigned) ((nb + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(base + o_b), nb, bmb, idx->n_docs, bad);
+    setop_count_kernel<<<n_tiles, kThreads, 0, st>>>(bma, bmb, n_words, op, reinterpret_cast<uint32_t*>(base + o_cnt));
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<uint32_t*>(base + o_cnt), n_tiles, reinterpret_cast<unsigned long long*>(base + o_off),
+                                          reinterpret_cast<unsigned long long*>(base + o_tot));
+    setop_extract_kernel<<<n_tiles, kThreads, 0, st>>>(bma, n_words, reinterpret_cast<unsigned long long*>(base + o_off),
+                                                       reinterpret_cast<uint32_t*>(base + o_out), max_out);
+    idx->stats.launches_total += 3 + (na ? 1 : 0) + (nb ? 1 : 0);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(idx->ev[2], st));
+    unsigned long long tot_bad[2] = {0, 0};
+    CU(cudaMemcpyAsync(tot_bad, base + o_tot, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if((uint32_t) tot_bad[1]) return fail(TSGPU_ERR_INVALID, "ids must be strictly ascending and below n_docs");
+    *out_n = (size_t) tot_bad[0];
+    if(tot_bad[0] > cap) return fail(TSGPU_ERR_CAPACITY, "output buffer too small");
+    if(tot_bad[0]) { CU(cudaMemcpyAsync(out_ids, base + o_out, tot_bad[0] * 4, cudaMemcpyDefault, st)); idx->stats.d2h_bytes += tot_bad[0] * 4 + 16; }
+    return end_call(idx, true, false);
 }
 
 tsgpu_status tsgpu_keyword_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, tsgpu_kv* out_kv, uint32_t kv_stride,
