@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--workload", default="hybrid10m", choices=["hybrid10m", "keyword10m", "knn"])
     ap.add_argument("--recall-queries", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exp-sorted-vectors", action="store_true",
+                    help="experiment only: store vectors in cluster order (seq_id locality) to measure what row locality is worth")
     return ap.parse_args()
 
 
@@ -128,6 +130,10 @@ def build_workload(args, device, rank, need_host_copy):
         t1 = time.time()
         w.n_clusters = max(8, args.docs // 2000)
         vec, cid = synth.make_vectors_clustered(args.docs, args.dim, w.n_clusters, seed=1234, device=device, spread=0.35)
+        if args.exp_sorted_vectors:
+            perm = torch.argsort(cid)
+            vec = vec[perm]; cid = cid[perm]
+            del perm
         lv, l0, uo, lu, ml, ep = synth.build_graph_bulk(vec, 16, 100, order_key=cid)
         # brute-force ground truth for the recall report (outside every timed region)
         R = args.recall_queries

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Per-source-line stall samples: joins `ncu --page source --csv` (SASS view) with `nvdisasm -g` line info.
-usage: tools/ncu_lines.py REP.ncu-rep LIB.so KERNEL_SUBSTRING [top_n]"""
+usage: tools/ncu_lines.py REP.ncu-rep LIB.so KERNEL_SUBSTRING [top_n] [SECTION_SUBSTRING]
+SECTION_SUBSTRING picks the template instance in the cubin (mangled, e.g. hnsw_search_kernelILi6E); default = KERNEL."""
 import csv
 import io
 import os
@@ -14,6 +15,7 @@ from collections import defaultdict
 def main():
     rep, so, kern = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    sect = sys.argv[5] if len(sys.argv) > 5 else kern
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kern}"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
@@ -25,7 +27,7 @@ def main():
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, capture_output=True)
     cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
     sass = subprocess.run(["nvdisasm", "-g", os.path.join(d, cubin)], capture_output=True, text=True).stdout.splitlines()
-    start = next(i for i, l in enumerate(sass) if l.startswith(".text.") and kern in l)
+    start = next(i for i, l in enumerate(sass) if l.startswith(".text.") and sect in l)
     off2line = {}
     cur = ("?", 0)
     for l in sass[start + 1:]:

@@ -15,7 +15,7 @@ from .structs import (FieldStruct, FlatField, HnswGraph, HnswStruct, KV_DTYPE, K
                       VecParamsStruct, f32p, i32p, u32p, u64p)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtsgpu.so")
+LIB_PATH = os.environ.get("TSGPU_LIB_PATH") or os.path.join(HERE, "libtsgpu.so")   # override: A/B builds only
 
 EXPORTS = [
     "tsgpu_last_error", "tsgpu_device_count", "tsgpu_index_create", "tsgpu_index_destroy", "tsgpu_index_load_field",

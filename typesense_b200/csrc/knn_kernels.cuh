@@ -295,6 +295,18 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
 
             const uint32_t* rec = g.links0 + (size_t) cnode * L0;
             const uint32_t size = __ldg(rec);
+            // Speculation (hints only, no effect on results): the new top of the shared-memory tier is the most likely next
+            // expansion. Its link row rides along with this node's, its visited words with this node's atomics, and the
+            // vectors of its unvisited neighbours are started towards L2 before this node's distances are computed — so
+            // the next expansion finds links, visited words and vectors in L2 instead of paying three DRAM round trips.
+            uint32_t spec = kNone, nb2 = kNone, size2 = 0;
+            if(lane == 0 && n_cs) spec = ~(uint32_t) cand_s[0];
+            spec = __shfl_sync(0xffffffffu, spec, 0);
+            if(spec != kNone) {
+                const uint32_t* rec2 = g.links0 + (size_t) spec * L0;
+                size2 = __ldg(rec2);
+                nb2 = (lane + 1 < L0) ? __ldg(rec2 + 1 + lane) : kNone;
+            }
             uint32_t nb = kNone;
             bool fresh = false;
             // 2M <= 32 neighbours handled one per lane; (2M > 32 is processed in chunks of 32)
@@ -306,7 +318,13 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
                     const uint32_t old = atomicOr(vis + (nb >> 5), 1u << (nb & 31));
                     fresh = !((old >> (nb & 31)) & 1);
                 }
+                uint32_t w2 = 0xFFFFFFFFu;
+                if(base == 0 && lane < size2 && nb2 < g.n_nodes) w2 = __ldcg(vis + (nb2 >> 5)) >> (nb2 & 31);
                 uint32_t mask = __ballot_sync(0xffffffffu, fresh);
+                if(!(w2 & 1u)) {
+                    const char* vp = reinterpret_cast<const char*>(g.vectors + (size_t) nb2 * dim);
+                    for(uint32_t o = 0; o < dim * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(vp + o));
+                }
                 // visit log for the bitmap undo
                 if(fresh) {
                     const uint32_t pos = n_log + __popc(mask & ((1u << lane) - 1u));
@@ -314,19 +332,26 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
                 }
                 n_log += __popc(mask);
                 if(n_log > P.log_cap) log_overflow = true;
+                // every fresh neighbour's vector will be read below, two at a time: start all of them towards L2 now so only
+                // the first pair pays the full DRAM (and page-walk) latency
+                if(fresh && __popc(mask) > 2) {
+                    const char* vp = reinterpret_cast<const char*>(g.vectors + (size_t) nb * dim);
+                    for(uint32_t o = 0; o < dim * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(vp + o));
+                }
                 while(mask) {
                     const int j0 = __ffs(mask) - 1; mask &= mask - 1;
                     int j1 = -1;
                     if(mask) { j1 = __ffs(mask) - 1; mask &= mask - 1; }
                     const uint32_t c0 = __shfl_sync(0xffffffffu, nb, j0);
                     const uint32_t c1 = j1 >= 0 ? __shfl_sync(0xffffffffu, nb, j1) : c0;
+                    // filter-functor loads are issued ahead of the vector loads so their latency hides under them
+                    const bool ok0 = allowed(g, fbm, excl, n_excl, c0);
+                    const bool ok1 = j1 >= 0 ? allowed(g, fbm, excl, n_excl, c1) : false;
                     float d0, d1;
                     dot_two<NCH>(q, qs, g.vectors + (size_t) c0 * dim, g.vectors + (size_t) c1 * dim, dim, lane, d0, d1);
                     d0 = 1.0f - d0; d1 = 1.0f - d1;
                     n_dist_acc += j1 >= 0 ? 2 : 1;
                     // admission replayed in neighbour order (lane 0 owns the heaps)
-                    const bool ok0 = allowed(g, fbm, excl, n_excl, c0);
-                    const bool ok1 = j1 >= 0 ? allowed(g, fbm, excl, n_excl, c1) : false;
                     if(lane == 0) {
 #pragma unroll
                         for(int t = 0; t < 2; t++) {

@@ -192,7 +192,12 @@ __device__ __forceinline__ uint32_t cta_rank(bool flag, uint32_t* s_warp, uint32
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kQCap = 2 * kThreads;        // pending-match queue slots per CTA
 
-__global__ void __launch_bounds__(kThreads)
+// The kernel is latency-bound on dependent HBM loads (gallop -> probe -> offsets), so resident warps matter more than
+// registers per thread: cap at 64 registers (no spills at -O3) for 8 CTAs = 32 warps per SM.
+#ifndef TSGPU_KW_MIN_CTAS
+#define TSGPU_KW_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(kThreads, TSGPU_KW_MIN_CTAS)
 kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ KwParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t KP = P.KP, N2 = 2 * KP, NL = P.NL, F = P.F;

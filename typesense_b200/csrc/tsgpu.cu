@@ -256,7 +256,8 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
         total_tiles += tiles;
     }
     // ---- queries
-    uint32_t tpu = (uint32_t) std::min<uint64_t>(128, std::max<uint64_t>(4, total_tiles / 8192));
+    static const uint64_t unit_target = getenv("TSGPU_KW_UNIT_TARGET") ? (uint64_t) std::max(1, atoi(getenv("TSGPU_KW_UNIT_TARGET"))) : 8192;
+    uint32_t tpu = (uint32_t) std::min<uint64_t>(256, std::max<uint64_t>(4, total_tiles / unit_target));
     std::vector<std::pair<uint32_t, uint32_t>> q_units0;
     for(uint32_t q = 0; q < nq; q++) {
         QDesc& qd = pl.qd[q];

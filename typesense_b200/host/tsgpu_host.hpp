@@ -8,6 +8,8 @@
 //   posting_t::upsert(obj, id, offsets)   src/posting.cpp:247      field_mirror_t::upsert(token, id, offsets)
 //   posting_t::intersect(lists, ids)      src/posting.cpp:388      Index::intersect(field, tokens, ids)
 //   posting_t::get_phrase_matches         src/posting.cpp:543      Index::get_phrase_matches(field, tokens, ids, out)
+//   posting_t::get_exact_matches          src/posting.cpp:485      Index::get_exact_matches(field, tokens, ids, out[, prefix])
+//   ArrayUtils::and/or/exclude_scalar     include/array_utils.h    Index::ids_setop(op, a, b, out)
 //   Index::search_across_fields           src/index.cpp:5385       Index::search_across_fields(query_suggestions, ...)
 //   hnsw_index_t + searchKnnCloserFirst   src/index.cpp:3384       Index::searchKnnCloserFirst(q, k, ef, filter_ids)
 //   Topster<KV>::add / sort               include/topster.h:321    host_topster_t (merges the <=K KVs of each device round)
@@ -179,6 +181,32 @@ public:
         if(tsgpu_phrase_matches(h, f, lists.data(), (uint32_t) lists.size(), ids.data(), ids.size(), phrase_ids.data(), &n) != TSGPU_OK)
             return Option<bool>(500, tsgpu_last_error());
         phrase_ids.resize(n);
+        return Option<bool>(true);
+    }
+
+    // posting_t::get_exact_matches(posting_lists, field_is_array, ids, num_ids, exact_ids, num_exact_ids) — the `:=`
+    // string filter (src/index.cpp:3232); `prefix` selects posting_list_t::get_prefix_matches instead.
+    Option<bool> get_exact_matches(const std::string& field, const std::vector<std::string>& tokens, const std::vector<uint32_t>& ids,
+                                   std::vector<uint32_t>& exact_ids, bool prefix = false) {
+        const uint32_t f = field_ids.at(field);
+        std::vector<uint32_t> lists;
+        exact_ids.clear();
+        for(auto& t: tokens) { uint32_t l = token_id(f, t); if(l == TSGPU_NO_LIST) return Option<bool>(true); lists.push_back(l); }
+        exact_ids.resize(ids.size() ? ids.size() : 1);
+        size_t n = 0;
+        auto fn = prefix ? tsgpu_prefix_matches : tsgpu_exact_matches;
+        if(fn(h, f, lists.data(), (uint32_t) lists.size(), ids.data(), ids.size(), exact_ids.data(), &n) != TSGPU_OK)
+            return Option<bool>(500, tsgpu_last_error());
+        exact_ids.resize(n);
+        return Option<bool>(true);
+    }
+    // ArrayUtils::and_scalar / or_scalar / exclude_scalar (include/array_utils.h:13-19) on the device
+    Option<bool> ids_setop(int op, const std::vector<uint32_t>& a, const std::vector<uint32_t>& b, std::vector<uint32_t>& out) {
+        out.resize(a.size() + b.size() + 1);
+        size_t n = 0;
+        if(tsgpu_ids_setop(h, op, a.data(), a.size(), b.data(), b.size(), out.data(), out.size(), &n) != TSGPU_OK)
+            return Option<bool>(500, tsgpu_last_error());
+        out.resize(n);
         return Option<bool>(true);
     }
 
