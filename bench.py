@@ -35,6 +35,23 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: libraries that print there (NCCL's version banner does) go to stderr."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, line)
+
+
 def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
@@ -242,12 +259,12 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic",
-           "config": workload_config(args, S_n),
+           "config": workload_config(args, args.batch),
            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                             "sample": f"{S_n} queries of the batch per step, {args.steps} steps"},
            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(args, batch):
@@ -453,12 +470,13 @@ def run_tsgpu(args, rank, world, local_rank):
                              "batch": {"queries": nq, "p50": pct(lat_b, 0.5), "p99": pct(lat_b, 0.99), "calls": len(lat_b)},
                              "small": {"queries": min(64, nq), "p50": pct(ls, 0.5), "p99": pct(ls, 0.99), "calls": len(ls)}}
         out.update(extra)
-        print(json.dumps(out), flush=True)
+        emit(out)
     gi.close()
 
 
 def main():
     args = parse()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
