@@ -420,9 +420,12 @@ def run_tsgpu(args, rank, world, local_rank):
         extra["roofline_other"] = roof[1:]
         extra["device_ms_per_step"] = {"total": ms_dev, "note": "timed region: vector stage on its own stream, overlapped",
                                        "keyword": statistics.mean(s["ms_keyword"] for s in sts),
-                                       "knn_overlapped": statistics.mean(s["ms_knn"] for s in sts), "fuse": ms_fuse}
+                                       "knn_overlapped": statistics.mean(s["ms_knn"] for s in sts), "fuse": ms_fuse,
+                                       "host_plan": statistics.mean(s["ms_host_plan"] for s in sts)}
         extra["device_ms_isolated"] = {"kw_search": ms_kw, "kw_merge": statistics.mean(s["ms_kw_merge"] for s in sts_iso),
                                        "knn": ms_knn, "total": statistics.mean(s["ms_total"] for s in sts_iso)}
+        extra["work_per_step"] = {k: float(statistics.mean(s_[k] for s_ in sts_iso)) for k in
+                                  ("kw_driver_ids", "kw_probe_ids", "kw_matches", "knn_dist", "knn_expanded")}
         if traffic:
             extra["roofline_traffic_source"] = traffic.get("source")
         if want_cpu:

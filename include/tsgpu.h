@@ -233,6 +233,7 @@ typedef struct {
     uint64_t d2h_bytes;
     float    ms_kw_search;       // kw_search_kernel alone
     float    ms_kw_merge;        // kw_merge_kernel levels + kw_final_kernel + found_popcount_kernel
+    float    ms_host_plan;       /* host wall time of batch planning (build_kw_plan) inside the call; the GPU idles meanwhile */
 } tsgpu_stats;
 tsgpu_status tsgpu_get_stats(tsgpu_index* idx, tsgpu_stats* out);
 

@@ -723,7 +723,7 @@ kw_final_kernel(const __grid_constant__ FinalParams P) {
     }
     if(tid == 0) {
         P.out_count[q] = n_out;
-        if(!(multi && qd.found_bitmap)) P.out_found[q] = s_found;     // else: popcount of the union bitmap
+        P.out_found[q] = (multi && qd.found_bitmap) ? 0 : s_found;   // multi: found_popcount_kernel adds the union's popcount
     }
 }
 
@@ -826,18 +826,28 @@ wc_unit_kernel(const __grid_constant__ WcParams P) {
 }
 
 // found = |union of result ids| for queries with several combinations (the reference ORs id_buff into
-// all_result_ids, src/index.cpp:5081-5090)
+// all_result_ids, src/index.cpp:5081-5090). grid = (queries, splits); 16-byte loads; every word is cleared after it is
+// counted, so the bitmaps are all-zero again for the next call and no memset pass is needed. out_found[q] was zeroed by
+// kw_final_kernel.
 __global__ void __launch_bounds__(256)
-found_popcount_kernel(const QDesc* qd, const uint32_t* multi_q, uint32_t n_words, uint32_t* out_found) {
+found_popcount_kernel(const QDesc* qd, const uint32_t* multi_q, uint32_t n_vec, uint32_t* out_found) {
     const uint32_t q = multi_q[blockIdx.x];
-    const uint32_t* bm = qd[q].found_bitmap;
+    uint4* bm = reinterpret_cast<uint4*>(qd[q].found_bitmap);
+    const uint32_t per = (n_vec + gridDim.y - 1) / gridDim.y;
+    const uint32_t v0 = blockIdx.y * per, v1 = min(n_vec, v0 + per);
     uint32_t c = 0;
-    for(uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) c += __popc(bm[i]);
+    for(uint32_t i = v0 + threadIdx.x; i < v1; i += blockDim.x) {
+        const uint4 w = bm[i];
+        if(w.x | w.y | w.z | w.w) {
+            c += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+            bm[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
     for(int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     __shared__ uint32_t s[8];
     if((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
     __syncthreads();
-    if(threadIdx.x == 0) { uint32_t t = 0; for(int i = 0; i < 8; i++) t += s[i]; out_found[q] = t; }
+    if(threadIdx.x == 0) { uint32_t t = 0; for(int i = 0; i < 8; i++) t += s[i]; if(t) atomicAdd(out_found + q, t); }
 }
 
 // sorted ids -> bitmap (filter_result_iterator_t::to_filter_id_array() mirrored as bits)

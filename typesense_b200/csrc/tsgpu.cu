@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -116,9 +117,10 @@ struct tsgpu_index {
     std::vector<Filter> filters;
     int n_sms = 148;
     // scratch
-    DevBuf d_stage, d_pool, d_small, d_bitmaps, d_out, d_knn_vis, d_knn_log, d_knn_cand, d_knn_out, d_isect, d_kw_out;
+    DevBuf d_stage, d_pool, d_small, d_bitmaps, d_found_bm, d_out, d_knn_vis, d_knn_log, d_knn_cand, d_knn_out, d_isect, d_kw_out;
     PinBuf h_stage;
     size_t knn_slots = 0, knn_vis_words = 0;
+    bool found_dirty = false;            // d_found_bm is all-zero between calls unless a call died before its popcount pass
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     tsgpu_stats stats{};
 };
@@ -211,7 +213,8 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
         uint32_t tiles = 0;
         for(uint32_t f = 0; f <= (uint32_t) kMaxFieldSlots; f++) cd.drv_tile_off[f] = 0;
         cd.mode = 0; cd.n_words = (uint32_t) (((uint64_t) idx->n_docs + 31) / 32);
-        bool all_dense = drv != kNone && getenv("TSGPU_DENSE_MODE") && atoi(getenv("TSGPU_DENSE_MODE")) == 1;   // opt-in until measured faster at scale
+        static const bool dense_mode_on = getenv("TSGPU_DENSE_MODE") && atoi(getenv("TSGPU_DENSE_MODE")) == 1;   // opt-in: measured slower at 10 M docs
+        bool all_dense = drv != kNone && dense_mode_on;
         for(uint32_t r = 0; r < n_req && all_dense; r++) {
             if(!((cd.req_mask >> r) & 1)) continue;
             for(uint32_t f = 0; f < F; f++) {
@@ -243,14 +246,16 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
             }
             for(uint32_t f = F; f <= (uint32_t) kMaxFieldSlots; f++) cd.drv_tile_off[f] = tiles;
             // probe order: driver, other required rows by ascending postings, then the dropped rows
-            std::vector<uint32_t> order;
-            order.push_back(drv);
-            std::vector<uint32_t> rest;
-            for(uint32_t r = 0; r < n_req; r++) if(r != drv) rest.push_back(r);
-            std::stable_sort(rest.begin(), rest.end(), [&](uint32_t a, uint32_t c2) { return sumdf[a] < sumdf[c2]; });
-            for(uint32_t r: rest) order.push_back(r);
-            for(uint32_t r = n_req; r < n_rows; r++) order.push_back(r);
-            for(uint32_t i = 0; i < 16; i++) cd.probe_order[i] = i < order.size() ? (uint8_t) order[i] : 0;
+            uint32_t order[TSGPU_MAX_TOKENS + 1], n_order = 0;
+            order[n_order++] = drv;
+            for(uint32_t r = 0; r < n_req; r++) {            // stable insertion by ascending postings
+                if(r == drv) continue;
+                uint32_t i = n_order++;
+                while(i > 1 && sumdf[order[i - 1]] > sumdf[r]) { order[i] = order[i - 1]; i--; }
+                order[i] = r;
+            }
+            for(uint32_t r = n_req; r < n_rows; r++) order[n_order++] = r;
+            for(uint32_t i = 0; i < 16; i++) cd.probe_order[i] = i < n_order ? (uint8_t) order[i] : 0;
         }
         combo_tiles[c] = tiles;
         total_tiles += tiles;
@@ -365,12 +370,20 @@ tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& p
     const size_t words = ((size_t) idx->n_docs + 31) / 32;
     // device bitmaps: [inline filters][found bitmaps]
     const size_t n_inline = b->n_filters;
-    const size_t n_bm = n_inline + pl.multi_q.size();
-    if(n_bm) {
-        CU(idx->d_bitmaps.reserve(n_bm * words * 4));
-        CU(cudaMemsetAsync(idx->d_bitmaps.p, 0, n_bm * words * 4, st));
+    if(n_inline) {
+        CU(idx->d_bitmaps.reserve(n_inline * words * 4));
+        CU(cudaMemsetAsync(idx->d_bitmaps.p, 0, n_inline * words * 4, st));
     }
     uint32_t* bm = idx->d_bitmaps.as<uint32_t>();
+    // found bitmaps live in their own buffer that is all-zero between calls (found_popcount_kernel clears what it counts)
+    const size_t fwords = (words + 3) & ~size_t(3);
+    if(!pl.multi_q.empty()) {
+        const size_t old_cap = idx->d_found_bm.cap;
+        CU(idx->d_found_bm.reserve(pl.multi_q.size() * fwords * 4));
+        if(idx->found_dirty || idx->d_found_bm.cap != old_cap) CU(cudaMemsetAsync(idx->d_found_bm.p, 0, idx->d_found_bm.cap, st));
+        idx->found_dirty = true;
+    }
+    uint32_t* fbm = idx->d_found_bm.as<uint32_t>();
     Stager sg;
     const size_t n_excl_total = b->q_excl_off[nq];
     const size_t o_excl = sg.add(b->excl_ids, n_excl_total * 4);
@@ -409,7 +422,7 @@ tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& p
         pl.q_bitmap[q] = qd.filter_bitmap;
         qd.found_bitmap = nullptr;
     }
-    for(size_t i = 0; i < pl.multi_q.size(); i++) pl.qd[pl.multi_q[i]].found_bitmap = bm + (n_inline + i) * words;
+    for(size_t i = 0; i < pl.multi_q.size(); i++) pl.qd[pl.multi_q[i]].found_bitmap = fbm + i * fwords;
     memcpy(sg.host.data() + o_qd, pl.qd.data(), pl.qd.size() * sizeof(QDesc));
     memcpy(sg.host.data() + o_cd, pl.cd.data(), pl.cd.size() * sizeof(CDesc));
     memcpy(sg.host.data() + o_ud, pl.ud.data(), pl.ud.size() * sizeof(UDesc));
@@ -522,9 +535,11 @@ tsgpu_status run_keyword(tsgpu_index* idx, KwPlan& pl, uint32_t kv_stride, KwDev
         }
         CU(cudaGetLastError());
         if(!pl.multi_q.empty()) {
-            found_popcount_kernel<<<(unsigned) pl.multi_q.size(), 256, 0, st>>>(pl.d_qd, pl.d_multi_q, (uint32_t) (((size_t) idx->n_docs + 31) / 32), out.found);
+            const uint32_t n_vec = (uint32_t) (((((size_t) idx->n_docs + 31) / 32) + 3) / 4);
+            found_popcount_kernel<<<dim3((unsigned) pl.multi_q.size(), 4), 256, 0, st>>>(pl.d_qd, pl.d_multi_q, n_vec, out.found);
             idx->stats.launches_total++;
             CU(cudaGetLastError());
+            idx->found_dirty = false;
         }
     }
     CU(cudaEventRecord(idx->ev[2], st));
@@ -802,7 +817,7 @@ void tsgpu_index_destroy(tsgpu_index* idx) {
     for(auto* c: idx->sort_cols) cudaFree(c);
     for(void* p: idx->hnsw_alloc) cudaFree(p);
     for(auto& f: idx->filters) { if(f.d_bitmap) cudaFree(f.d_bitmap); if(f.d_ids) cudaFree(f.d_ids); }
-    DevBuf* bufs[] = {&idx->d_stage, &idx->d_pool, &idx->d_small, &idx->d_bitmaps, &idx->d_out, &idx->d_knn_vis,
+    DevBuf* bufs[] = {&idx->d_stage, &idx->d_pool, &idx->d_small, &idx->d_bitmaps, &idx->d_found_bm, &idx->d_out, &idx->d_knn_vis,
                       &idx->d_knn_log, &idx->d_knn_cand, &idx->d_knn_out, &idx->d_isect, &idx->d_kw_out};
     for(auto* b: bufs) b->release();
     idx->h_stage.release();
@@ -1104,7 +1119,10 @@ tsgpu_status tsgpu_keyword_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* 
     std::lock_guard<std::mutex> lk(idx->mu);
     begin_call(idx);
     KwPlan pl;
-    s = build_kw_plan(idx, b, true, pl); if(s) return s;
+    { const auto t0 = std::chrono::steady_clock::now();
+      s = build_kw_plan(idx, b, true, pl);
+      idx->stats.ms_host_plan = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+    if(s) return s;
     if(pl.nq == 0) return end_call(idx, false, false);
     s = upload_kw_plan(idx, b, pl); if(s) return s;
     KwDeviceOut o{};
@@ -1125,7 +1143,10 @@ tsgpu_status tsgpu_wildcard_search_batch(tsgpu_index* idx, const tsgpu_kw_batch*
     std::lock_guard<std::mutex> lk(idx->mu);
     begin_call(idx);
     KwPlan pl;
-    s = build_kw_plan(idx, b, false, pl, true); if(s) return s;
+    { const auto t0 = std::chrono::steady_clock::now();
+      s = build_kw_plan(idx, b, false, pl, true);
+      idx->stats.ms_host_plan = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+    if(s) return s;
     if(pl.nq == 0) return end_call(idx, false, false);
     s = upload_kw_plan(idx, b, pl); if(s) return s;
     KwDeviceOut o{};
@@ -1238,7 +1259,10 @@ static tsgpu_status vec_or_hybrid(tsgpu_index* idx, const tsgpu_kw_batch* b, con
     std::lock_guard<std::mutex> lk(idx->mu);
     begin_call(idx);
     KwPlan pl;
-    s = build_kw_plan(idx, b, hybrid, pl); if(s) return s;
+    { const auto t0 = std::chrono::steady_clock::now();
+      s = build_kw_plan(idx, b, hybrid, pl);
+      idx->stats.ms_host_plan = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+    if(s) return s;
     if(pl.nq == 0) return end_call(idx, false, false);
     s = upload_kw_plan(idx, b, pl); if(s) return s;
     cudaStream_t st = idx->stream;
@@ -1261,10 +1285,15 @@ static tsgpu_status vec_or_hybrid(tsgpu_index* idx, const tsgpu_kw_batch* b, con
         if(ovb > 0) { idx->vs = idx->stream2; idx->knn_blocks_per_sm = (unsigned) std::min(ovb, 7); }
         else { idx->vs = st; idx->knn_blocks_per_sm = 7; }
     } else { idx->vs = st; idx->knn_blocks_per_sm = 7; }
+    // Launch order decides who owns the SMs: the keyword kernels go first and fill every SM (8 CTAs each); the persistent
+    // graph-walk CTAs then take the slots that free up (kw_search's tail, the small merge / final grids) and finish alone.
+    // The other order lets the latency-bound walk hold half the register file while it uses a fifth of the memory system.
+    static const bool kw_first = !(getenv("TSGPU_KW_FIRST") && atoi(getenv("TSGPU_KW_FIRST")) == 0);
+    if(hybrid && kw_first) { s = run_keyword(idx, pl, std::max(kv_stride, pl.KMAX), kwo); if(s) return s; }
     s = run_vector_stage(idx, b, pl, qvecs, vp, k, vs); if(s) return s;
     if(hybrid) {
         CU(cudaEventRecord(idx->evB, idx->stream2));
-        s = run_keyword(idx, pl, std::max(kv_stride, pl.KMAX), kwo); if(s) return s;
+        if(!kw_first) { s = run_keyword(idx, pl, std::max(kv_stride, pl.KMAX), kwo); if(s) return s; }
         CU(cudaStreamWaitEvent(st, idx->evB, 0));
     }
     // final assembly
