@@ -155,6 +155,19 @@ __device__ __forceinline__ void heap_pop_max(unsigned long long* h, uint32_t& n)
     }
     if(n) h[i] = last;
 }
+// pop the maximum and push `key` (key below the current maximum) in one sift-down
+__device__ __forceinline__ void heap_replace_max(unsigned long long* h, uint32_t n, unsigned long long key) {
+    uint32_t i = 0;
+    for(;;) {
+        uint32_t c = 2 * i + 1;
+        if(c >= n) break;
+        unsigned long long hc = h[c];
+        if(c + 1 < n) { const unsigned long long hr = h[c + 1]; if(hr > hc) { hc = hr; c++; } }
+        if(hc <= key) break;
+        h[i] = hc; i = c;
+    }
+    h[i] = key;
+}
 __device__ __forceinline__ void heap_push_min(unsigned long long* h, uint32_t& n, unsigned long long key) {
     uint32_t i = n++;
     while(i > 0) { const uint32_t p = (i - 1) >> 1; const unsigned long long hp = h[p]; if(hp <= key) break; h[i] = hp; i = p; }
@@ -190,8 +203,14 @@ __device__ __forceinline__ bool allowed(const HnswDev& g, const uint32_t* fbm, c
     return (__ldg(fbm + (label >> 5)) >> (label & 31)) & 1;
 }
 
+// One query per warp. Measured on the 10 M x 768 workload: 96 registers / 5 CTAs per SM walks 4096 queries in 10.7 ms,
+// the 72-register build (7 CTAs per SM, a warp for every query) needs 12.4 ms — the extra residency does not pay for the
+// serialised loads the tighter register budget forces, because the batch time is set by the slowest walks.
+#ifndef TSGPU_KNN_MIN_CTAS
+#define TSGPU_KNN_MIN_CTAS 5
+#endif
 template <int NCH>
-__global__ void __launch_bounds__(kKnnThreads)
+__global__ void __launch_bounds__(kKnnThreads, TSGPU_KNN_MIN_CTAS)
 hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -276,6 +295,7 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
             n_cand = 1;
             __syncwarp();
         }
+        uint32_t prev_spec = kNone, prev_nb2 = kNone, prev_size2 = 0;
         for(;;) {
             if(n_cand == 0) break;
             // global minimum = the smaller of the two tiers' tops
@@ -294,7 +314,10 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
             n_exp_acc++;
 
             const uint32_t* rec = g.links0 + (size_t) cnode * L0;
-            const uint32_t size = __ldg(rec);
+            // a right guess already holds this node's link row in registers
+            const bool reuse = cnode == prev_spec;
+            const uint32_t size = reuse ? prev_size2 : __ldg(rec);
+            const uint32_t nb_first = reuse ? prev_nb2 : ((lane + 1 < L0) ? __ldg(rec + 1 + lane) : kNone);
             // Speculation (hints only, no effect on results): the new top of the shared-memory tier is the most likely next
             // expansion. Its link row rides along with this node's, its visited words with this node's atomics, and the
             // vectors of its unvisited neighbours are started towards L2 before this node's distances are computed — so
@@ -312,7 +335,7 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
             // 2M <= 32 neighbours handled one per lane; (2M > 32 is processed in chunks of 32)
             for(uint32_t base = 0; base < size; base += 32) {
                 const uint32_t j = base + lane;
-                nb = (j < size) ? __ldg(rec + 1 + j) : kNone;
+                nb = (j < size) ? (base == 0 ? nb_first : __ldg(rec + 1 + j)) : kNone;
                 fresh = false;
                 if(nb != kNone) {
                     const uint32_t old = atomicOr(vis + (nb >> 5), 1u << (nb & 31));
@@ -368,8 +391,10 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
                                 if(n_cs < kCandSmem) heap_push_min(cand_s, n_cs, cand_key(d, c));
                                 else if(n_cg < P.cand_cap) heap_push_min(cand, n_cg, cand_key(d, c));
                                 else *P.error = 1;
-                                if(ok) heap_push_max(res, n_res, res_key(d, c));
-                                while(n_res > ef) heap_pop_max(res, n_res);
+                                if(ok) {       // push, then pop while over ef (hnswlib) == replace the maximum when already full
+                                    if(n_res < ef) heap_push_max(res, n_res, res_key(d, c));
+                                    else heap_replace_max(res, n_res, res_key(d, c));
+                                }
                                 if(n_res) lowerBound = unord_f32((uint32_t) (res[0] >> 32));
                             }
                         }
@@ -379,6 +404,7 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
                     n_cand = __shfl_sync(0xffffffffu, n_cs + n_cg, 0);
                 }
             }
+            prev_spec = spec; prev_nb2 = nb2; prev_size2 = size2;
             __syncwarp();
         }
 

@@ -1281,7 +1281,7 @@ static tsgpu_status vec_or_hybrid(tsgpu_index* idx, const tsgpu_kw_batch* b, con
         CU(cudaEventRecord(idx->evA, st));
         CU(cudaStreamWaitEvent(idx->stream2, idx->evA, 0));
         const char* ov = getenv("TSGPU_KNN_OVERLAP_BLOCKS");      // 0 = no overlap (same stream, full residency)
-        const int ovb = ov ? atoi(ov) : 4;
+        const int ovb = ov ? atoi(ov) : 5;
         if(ovb > 0) { idx->vs = idx->stream2; idx->knn_blocks_per_sm = (unsigned) std::min(ovb, 7); }
         else { idx->vs = st; idx->knn_blocks_per_sm = 7; }
     } else { idx->vs = st; idx->knn_blocks_per_sm = 7; }
