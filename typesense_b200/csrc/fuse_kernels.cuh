@@ -164,6 +164,11 @@ hybrid_fuse_kernel(const __grid_constant__ HybridParams P) {
     uint32_t* v_id = reinterpret_cast<uint32_t*>(kvs + KP2 + (KP2 & 1));    // [VP2] knn results sorted by seq_id
     float* v_dist = reinterpret_cast<float*>(v_id + VP2);
     uint32_t* v_rank = reinterpret_cast<uint32_t*>(v_dist + VP2);
+    // per vector result, computed by all threads before the serial replay (graph results only): the three sort scores of
+    // the vector-only KV, its match_score_index, and flags (bit0 passes the filter, bit1 counts towards `found`)
+    int64_t* v_sc = reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(v_rank + VP2) + ((8 - ((size_t) (v_rank + VP2) & 7)) & 7));
+    int8_t* v_msi = reinterpret_cast<int8_t*>(v_sc + 3 * VP2);
+    uint8_t* v_flag = reinterpret_cast<uint8_t*>(v_msi + VP2);
     __shared__ uint32_t s_size, s_vec_only_new;
 
     const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
@@ -237,6 +242,32 @@ hybrid_fuse_kernel(const __grid_constant__ HybridParams P) {
     }
     __syncthreads();
 
+    // ---- order-independent part of the loop body, one vector result per thread: filter bit, the vector-only KV's sort
+    // scores, and whether the id adds to `found` (a vector result that is not a keyword match; ids found in the Topster
+    // are keyword matches, so the count does not depend on the replay). Takes ~100 dependent global loads per result off
+    // the single-lane critical path.
+    if(!flat) {
+        for(uint32_t vi = tid; vi < (uint32_t) n_v; vi += kThreads) {
+            const uint32_t seq_id = v_id[vi];
+            uint8_t fl = 0;
+            bool pass = !qd.filter_empty;
+            if(pass && qd.filter_bitmap) pass = (qd.filter_bitmap[seq_id >> 5] >> (seq_id & 31)) & 1;
+            if(pass) {
+                fl = 1;
+                const double vec_part = (1.0 / (double) (v_rank[vi] + 1)) * (double) VECTOR_SEARCH_WEIGHT;
+                int64_t sc[3];
+                v_msi[vi] = (int8_t) compute_sort_scores(SS, seq_id, float_to_int64(__double2float_rn(vec_part)), v_dist[vi], sc);
+                v_sc[3 * vi] = sc[0]; v_sc[3 * vi + 1] = sc[1]; v_sc[3 * vi + 2] = sc[2];
+                bool in_kw = true;
+                if(qd.n_excl && excluded(qd.excl, qd.n_excl, seq_id)) in_kw = false;
+                if(in_kw) in_kw = is_keyword_match(P, qd, seq_id);
+                if(!in_kw) fl |= 2;
+            }
+            v_flag[vi] = fl;
+        }
+    }
+    __syncthreads();
+
     // ---- replay of the fusion loop (warp 0)
     if(tid < 32) {
         uint32_t size = s_size, vec_new = 0;
@@ -244,8 +275,11 @@ hybrid_fuse_kernel(const __grid_constant__ HybridParams P) {
             uint32_t seq_id; float dist; uint32_t rank;
             if(flat) { seq_id = ri[vi]; dist = rd[vi]; rank = (uint32_t) vi; }
             else { seq_id = v_id[vi]; dist = v_dist[vi]; rank = v_rank[vi]; }
-            if(qd.filter_bitmap && !((qd.filter_bitmap[seq_id >> 5] >> (seq_id & 31)) & 1)) continue;
-            if(qd.filter_empty) continue;
+            if(!flat) { if(!(v_flag[vi] & 1)) continue; }
+            else {
+                if(qd.filter_bitmap && !((qd.filter_bitmap[seq_id >> 5] >> (seq_id & 31)) & 1)) continue;
+                if(qd.filter_empty) continue;
+            }
             // topster->map.find(seq_id)
             uint32_t found_pos = kNone;
             for(uint32_t b0 = 0; b0 < size; b0 += 32) {
@@ -268,9 +302,10 @@ hybrid_fuse_kernel(const __grid_constant__ HybridParams P) {
                     }
                 } else {
                     KVOut kv;
-                    const int64_t match_score = float_to_int64(__double2float_rn(vec_part));
                     int64_t sc[3];
-                    const int msi = compute_sort_scores(SS, seq_id, match_score, dist, sc);
+                    int msi;
+                    if(!flat) { sc[0] = v_sc[3 * vi]; sc[1] = v_sc[3 * vi + 1]; sc[2] = v_sc[3 * vi + 2]; msi = v_msi[vi]; }
+                    else msi = compute_sort_scores(SS, seq_id, float_to_int64(__double2float_rn(vec_part)), dist, sc);
                     kv.key = seq_id; kv.distinct_key = seq_id;
                     kv.scores[0] = sc[0]; kv.scores[1] = sc[1]; kv.scores[2] = sc[2];
                     kv.match_score_index = (int8_t) msi; kv.pad0 = 0;
@@ -302,10 +337,13 @@ hybrid_fuse_kernel(const __grid_constant__ HybridParams P) {
                         }
                     }
                     // vec_search_ids.push_back(seq_id) happens whether or not the heap took it (src/index.cpp:4197)
-                    bool in_kw = true;
-                    if(qd.n_excl && excluded(qd.excl, qd.n_excl, seq_id)) in_kw = false;
-                    if(in_kw) in_kw = is_keyword_match(P, qd, seq_id);
-                    if(!in_kw) vec_new++;
+                    if(!flat) { if(v_flag[vi] & 2) vec_new++; }
+                    else {
+                        bool in_kw = true;
+                        if(qd.n_excl && excluded(qd.excl, qd.n_excl, seq_id)) in_kw = false;
+                        if(in_kw) in_kw = is_keyword_match(P, qd, seq_id);
+                        if(!in_kw) vec_new++;
+                    }
                 }
             }
             size = __shfl_sync(0xffffffffu, size, 0);

@@ -136,55 +136,57 @@ __device__ __forceinline__ void dot_two(const QReg<NCH>& q, const float* __restr
     }
 }
 
-// ---- binary heaps of u64 keys, single-lane operations
+// ---- 4-ary heaps of u64 keys, single-lane operations. Keys are unique ((distance, id) pairs), so the pop order — the
+// only thing the search observes — is the key order whatever the heap's shape; four children per node halve the depth
+// of the dependent load chain of a sift and their loads are independent.
 __device__ __forceinline__ void heap_push_max(unsigned long long* h, uint32_t& n, unsigned long long key) {
     uint32_t i = n++;
-    while(i > 0) { const uint32_t p = (i - 1) >> 1; const unsigned long long hp = h[p]; if(hp >= key) break; h[i] = hp; i = p; }
+    while(i > 0) { const uint32_t p = (i - 1) >> 2; const unsigned long long hp = h[p]; if(hp >= key) break; h[i] = hp; i = p; }
+    h[i] = key;
+}
+__device__ __forceinline__ void heap_sift_max(unsigned long long* h, uint32_t n, unsigned long long key) {
+    uint32_t i = 0;
+    for(;;) {
+        const uint32_t c = 4 * i + 1;
+        if(c >= n) break;
+        unsigned long long best = h[c]; uint32_t bi = c;
+        const unsigned long long h1 = c + 1 < n ? h[c + 1] : 0ull, h2 = c + 2 < n ? h[c + 2] : 0ull, h3 = c + 3 < n ? h[c + 3] : 0ull;
+        if(c + 1 < n && h1 > best) { best = h1; bi = c + 1; }
+        if(c + 2 < n && h2 > best) { best = h2; bi = c + 2; }
+        if(c + 3 < n && h3 > best) { best = h3; bi = c + 3; }
+        if(best <= key) break;
+        h[i] = best; i = bi;
+    }
     h[i] = key;
 }
 __device__ __forceinline__ void heap_pop_max(unsigned long long* h, uint32_t& n) {
     const unsigned long long last = h[--n];
-    uint32_t i = 0;
-    for(;;) {
-        uint32_t c = 2 * i + 1;
-        if(c >= n) break;
-        unsigned long long hc = h[c];
-        if(c + 1 < n) { const unsigned long long hr = h[c + 1]; if(hr > hc) { hc = hr; c++; } }
-        if(hc <= last) break;
-        h[i] = hc; i = c;
-    }
-    if(n) h[i] = last;
+    if(n) heap_sift_max(h, n, last);
 }
 // pop the maximum and push `key` (key below the current maximum) in one sift-down
-__device__ __forceinline__ void heap_replace_max(unsigned long long* h, uint32_t n, unsigned long long key) {
-    uint32_t i = 0;
-    for(;;) {
-        uint32_t c = 2 * i + 1;
-        if(c >= n) break;
-        unsigned long long hc = h[c];
-        if(c + 1 < n) { const unsigned long long hr = h[c + 1]; if(hr > hc) { hc = hr; c++; } }
-        if(hc <= key) break;
-        h[i] = hc; i = c;
-    }
-    h[i] = key;
-}
+__device__ __forceinline__ void heap_replace_max(unsigned long long* h, uint32_t n, unsigned long long key) { heap_sift_max(h, n, key); }
+
 __device__ __forceinline__ void heap_push_min(unsigned long long* h, uint32_t& n, unsigned long long key) {
     uint32_t i = n++;
-    while(i > 0) { const uint32_t p = (i - 1) >> 1; const unsigned long long hp = h[p]; if(hp <= key) break; h[i] = hp; i = p; }
+    while(i > 0) { const uint32_t p = (i - 1) >> 2; const unsigned long long hp = h[p]; if(hp <= key) break; h[i] = hp; i = p; }
     h[i] = key;
 }
 __device__ __forceinline__ void heap_pop_min(unsigned long long* h, uint32_t& n) {
     const unsigned long long last = h[--n];
+    if(n == 0) return;
     uint32_t i = 0;
     for(;;) {
-        uint32_t c = 2 * i + 1;
+        const uint32_t c = 4 * i + 1;
         if(c >= n) break;
-        unsigned long long hc = h[c];
-        if(c + 1 < n) { const unsigned long long hr = h[c + 1]; if(hr < hc) { hc = hr; c++; } }
-        if(hc >= last) break;
-        h[i] = hc; i = c;
+        unsigned long long best = h[c]; uint32_t bi = c;
+        const unsigned long long h1 = c + 1 < n ? h[c + 1] : ~0ull, h2 = c + 2 < n ? h[c + 2] : ~0ull, h3 = c + 3 < n ? h[c + 3] : ~0ull;
+        if(h1 < best) { best = h1; bi = c + 1; }
+        if(h2 < best) { best = h2; bi = c + 2; }
+        if(h3 < best) { best = h3; bi = c + 3; }
+        if(best >= last) break;
+        h[i] = best; i = bi;
     }
-    if(n) h[i] = last;
+    h[i] = last;
 }
 
 // result key: max-heap on (dist, id)            -> ord(dist) << 32 | id

@@ -1332,7 +1332,7 @@ static tsgpu_status vec_or_hybrid(tsgpu_index* idx, const tsgpu_kw_batch* b, con
         P.out_kv = d_kv; P.out_count = d_cnt; P.out_found = d_found; P.kv_stride = kv_stride;
         P.KMAX = pl.KMAX; P.VMAX = k;
         const uint32_t KP2 = pow2_ceil(pl.KMAX), VP2 = pow2_ceil(k);
-        const size_t smem = (size_t) pl.KMAX * sizeof(KVOut) + (size_t) (KP2 + 2) * 2 + (size_t) VP2 * 12 + 32;
+        const size_t smem = (size_t) pl.KMAX * sizeof(KVOut) + (size_t) (KP2 + 2) * 2 + (size_t) VP2 * (12 + 24 + 2) + 48;
         CU(cudaFuncSetAttribute(tsf::hybrid_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024)));
         tsf::hybrid_fuse_kernel<<<nq, kThreads, smem, st>>>(P);
         idx->stats.launches_total++;
