@@ -144,9 +144,8 @@ __device__ void tb_sort(const TopBuf& b, uint32_t N) {
                 const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const uint32_t p = i + j;
                 const bool up = ((i & k) == 0);
-                const bool p_first = BYKEY ? tb_before_bykey(b, p, i) : tb_greater(b, p, i);
-                const bool i_first = BYKEY ? tb_before_bykey(b, i, p) : tb_greater(b, i, p);
-                if(up ? p_first : i_first) tb_swap(b, i, p);
+                const uint32_t x = up ? p : i, y = up ? i : p;          // swap when x has to come before y
+                if(BYKEY ? tb_before_bykey(b, x, y) : tb_greater(b, x, y)) tb_swap(b, i, p);
             }
             __syncthreads();
         }
@@ -536,11 +535,13 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
     {
         const uint32_t n = s_n;
         uint32_t nn = n;
-        if(n > K) {
-            tb_fill_invalid(tb, n, N2);
+        if(n > 1) {                               // always sorted best-first: the merges read only the heads of their inputs
+            uint32_t NS = 2;
+            while(NS < n) NS <<= 1;
+            tb_fill_invalid(tb, n, NS);
             __syncthreads();
-            tb_sort<false>(tb, N2);
-            nn = K;
+            tb_sort<false>(tb, NS);
+            if(n > K) nn = K;
         }
         for(uint32_t i = tid; i < nn; i += kThreads) {
             const uint32_t o = ud.out_off + i;
@@ -596,6 +597,7 @@ struct FinalParams {
 };
 
 constexpr int kFinalThreads = 256;
+constexpr uint32_t kMergeIn = 32;          // inputs a merge group can interleave (planning uses fan-in 16)
 
 // shared by the intermediate and the final merge: leaves the best <= K de-duplicated entries sorted in tb[0..n)
 __device__ uint32_t merge_units(const TopBuf& tb, uint32_t N2, uint32_t K, bool multi, const UDesc* ud, const uint32_t* unit_cnt,
@@ -603,25 +605,86 @@ __device__ uint32_t merge_units(const TopBuf& tb, uint32_t N2, uint32_t K, bool 
                                 const uint32_t* pk, const uint16_t* pc) {
     const uint32_t tid = threadIdx.x;
     auto reduce = [&](uint32_t n) -> uint32_t {
-        tb_fill_invalid(tb, n, N2);
+        uint32_t NS = 64;                          // sort the smallest power of two that covers the n held entries
+        while(NS < n) NS <<= 1;
+        tb_fill_invalid(tb, n, NS);
         __syncthreads();
         if(multi) {
-            tb_sort<true>(tb, N2);
+            tb_sort<true>(tb, NS);
             // entries of one seq_id are adjacent, best first: drop the rest (Topster keeps the greater KV per key)
             bool dup[8];
             int cnt = 0;
-            for(uint32_t i = tid; i < N2; i += kFinalThreads) dup[cnt++] = (i > 0 && tb.key[i] != kNone && tb.key[i] == tb.key[i - 1]);
+            for(uint32_t i = tid; i < NS; i += kFinalThreads) dup[cnt++] = (i > 0 && tb.key[i] != kNone && tb.key[i] == tb.key[i - 1]);
             __syncthreads();
             cnt = 0;
-            for(uint32_t i = tid; i < N2; i += kFinalThreads) if(dup[cnt++]) tb.key[i] = kNone;
+            for(uint32_t i = tid; i < NS; i += kFinalThreads) if(dup[cnt++]) tb.key[i] = kNone;
             __syncthreads();
         }
-        tb_sort<false>(tb, N2);
-        uint32_t lo = 0, hi = N2;                 // valid entries are in front
+        tb_sort<false>(tb, NS);
+        uint32_t lo = 0, hi = NS;                 // valid entries are in front
         while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(tb.key[mid] != kNone) lo = mid + 1; else hi = mid; }
         return lo < K ? lo : K;
     };
     uint32_t n = 0;
+    const uint32_t nu = u_end - u_begin;
+    if(nu <= kMergeIn) {
+        // Inputs are sorted best-first, so only their heads can reach the top K. Rounds: every unit whose next entry is
+        // not below the current K-th (or any unit while fewer than K are held) contributes an equal share of the free
+        // slots; reduce; repeat until no unit qualifies. An entry left unread is <= its unit's last-read entry <= the
+        // K-th of K distinct held keys, so it cannot be in the result; entries EQUAL to the K-th are read (the later
+        // combination wins ties). Typically 2-3 reductions instead of one per 256 entries.
+        __shared__ uint32_t s_cur[kMergeIn], s_take[kMergeIn], s_base[kMergeIn];
+        __shared__ uint32_t s_total;
+        if(tid < nu) s_cur[tid] = 0;
+        __syncthreads();
+        for(;;) {
+            bool live = false;
+            if(tid < nu) {
+                const uint32_t u = u_begin + tid, c = s_cur[tid];
+                if(c < unit_cnt[u]) {
+                    live = true;
+                    if(n >= K) {                     // tb[0..n) is sorted and n == K: compare with the K-th
+                        const uint32_t o = ud[u].out_off + c, t = K - 1;
+                        const int64_t a0 = p0[o], a1 = p1[o], a2 = p2[o]; const uint32_t ak = pk[o];
+                        bool below;
+                        if(a0 != tb.s0[t]) below = a0 < tb.s0[t];
+                        else if(a1 != tb.s1[t]) below = a1 < tb.s1[t];
+                        else if(a2 != tb.s2[t]) below = a2 < tb.s2[t];
+                        else below = ak < tb.key[t];
+                        live = !below;
+                    }
+                }
+                s_take[tid] = live ? 1u : 0u;
+            }
+            const uint32_t n_live = (uint32_t) __syncthreads_count(live);
+            if(n_live == 0) break;
+            if(tid == 0) {
+                const uint32_t share = max(1u, (N2 - n) / n_live);
+                uint32_t tot = 0;
+                for(uint32_t i = 0; i < nu; i++) {
+                    uint32_t t = 0;
+                    if(s_take[i]) { const uint32_t rem = unit_cnt[u_begin + i] - s_cur[i]; t = rem < share ? rem : share; }
+                    s_base[i] = tot; s_take[i] = t; tot += t;
+                }
+                s_total = tot;
+            }
+            __syncthreads();
+            for(uint32_t i = 0; i < nu; i++) {
+                const uint32_t take = s_take[i];
+                if(take == 0) continue;
+                const uint32_t o0 = ud[u_begin + i].out_off + s_cur[i], d0 = n + s_base[i];
+                for(uint32_t j = tid; j < take; j += kFinalThreads) {
+                    tb.s0[d0 + j] = p0[o0 + j]; tb.s1[d0 + j] = p1[o0 + j]; tb.s2[d0 + j] = p2[o0 + j];
+                    tb.key[d0 + j] = pk[o0 + j]; tb.cmb[d0 + j] = pc[o0 + j];
+                }
+            }
+            __syncthreads();
+            if(tid < nu) s_cur[tid] += s_take[tid];
+            n = reduce(n + s_total);
+            __syncthreads();
+        }
+        return n;
+    }
     for(uint32_t u = u_begin; u < u_end; u++) {
         const uint32_t cnt = unit_cnt[u];
         if(cnt == 0) continue;
@@ -811,11 +874,13 @@ wc_unit_kernel(const __grid_constant__ WcParams P) {
     __syncthreads();
     const uint32_t n = s_n;
     uint32_t nn = n;
-    if(n > K) {
-        tb_fill_invalid(tb, n, N2);
+    if(n > 1) {                                   // always sorted best-first (see merge_units)
+        uint32_t NS = 2;
+        while(NS < n) NS <<= 1;
+        tb_fill_invalid(tb, n, NS);
         __syncthreads();
-        tb_sort<false>(tb, N2);
-        nn = K;
+        tb_sort<false>(tb, NS);
+        if(n > K) nn = K;
     }
     for(uint32_t i = tid; i < nn; i += kThreads) {
         const uint32_t o = ud.out_off + i;
