@@ -425,7 +425,7 @@ def run_tsgpu(args, rank, world, local_rank):
         extra["device_ms_isolated"] = {"kw_search": ms_kw, "kw_merge": statistics.mean(s["ms_kw_merge"] for s in sts_iso),
                                        "knn": ms_knn, "total": statistics.mean(s["ms_total"] for s in sts_iso)}
         extra["work_per_step"] = {k: float(statistics.mean(s_[k] for s_ in sts_iso)) for k in
-                                  ("kw_driver_ids", "kw_probe_ids", "kw_matches", "knn_dist", "knn_expanded")}
+                                  ("kw_driver_ids", "kw_probe_ids", "kw_matches", "knn_dist", "knn_expanded", "knn_spec_hits")}
         if traffic:
             extra["roofline_traffic_source"] = traffic.get("source")
         if want_cpu:

@@ -234,6 +234,7 @@ typedef struct {
     float    ms_kw_search;       // kw_search_kernel alone
     float    ms_kw_merge;        // kw_merge_kernel levels + kw_final_kernel + found_popcount_kernel
     float    ms_host_plan;       /* host wall time of batch planning (build_kw_plan) inside the call; the GPU idles meanwhile */
+    uint64_t knn_spec_hits;      /* expansions whose node was the one the walk had prefetched for (speculation hit) */
 } tsgpu_stats;
 tsgpu_status tsgpu_get_stats(tsgpu_index* idx, tsgpu_stats* out);
 

@@ -230,7 +230,7 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
     uint32_t* vlog = P.vis_log + (size_t) slot * P.log_cap;
     unsigned long long* cand = P.cand + (size_t) slot * P.cand_cap;
     const uint32_t L0 = 2 * g.M + 1, LU = g.M + 1;
-    unsigned long long n_dist_acc = 0, n_exp_acc = 0;
+    unsigned long long n_dist_acc = 0, n_exp_acc = 0, n_hit_acc = 0;
 
     for(;;) {
         uint32_t qi = 0;
@@ -318,6 +318,7 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
             const uint32_t* rec = g.links0 + (size_t) cnode * L0;
             // a right guess already holds this node's link row in registers
             const bool reuse = cnode == prev_spec;
+            n_hit_acc += reuse ? 1 : 0;
             const uint32_t size = reuse ? prev_size2 : __ldg(rec);
             const uint32_t nb_first = reuse ? prev_nb2 : ((lane + 1 < L0) ? __ldg(rec + 1 + lane) : kNone);
             // Speculation (hints only, no effect on results): the new top of the shared-memory tier is the most likely next
@@ -432,7 +433,7 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
         }
         __syncwarp();
     }
-    if(lane == 0) { atomicAdd(P.stats + 0, n_dist_acc); atomicAdd(P.stats + 1, n_exp_acc); }
+    if(lane == 0) { atomicAdd(P.stats + 0, n_dist_acc); atomicAdd(P.stats + 1, n_exp_acc); atomicAdd(P.stats + 2, n_hit_acc); }
 }
 
 // process_results_bruteforce: one warp per (query, id)

@@ -642,7 +642,7 @@ tsgpu_status finish_knn(tsgpu_index* idx) {
     unsigned long long hst[4];
     CU(cudaMemcpy(hst, idx->knn_misc_dev + 8, 32, cudaMemcpyDeviceToHost));
     idx->knn_misc_dev = nullptr;
-    idx->stats.knn_dist += hst[0]; idx->stats.knn_expanded += hst[1];
+    idx->stats.knn_dist += hst[0]; idx->stats.knn_expanded += hst[1]; idx->stats.knn_spec_hits += hst[2];
     if((int) hst[3]) return fail(TSGPU_ERR_CAPACITY, "HNSW candidate heap overflow (more than 262144 live candidates in one query)");
     return TSGPU_OK;
 }
