@@ -64,9 +64,39 @@ class Collection:
         return Collection(docs)
 
 
-def search(backend, coll: Collection, q: str, sort, drop_tokens_threshold: int = 1, topster: int = 250):
+def split_query(q: str):
+    """`-word` is an exclusion token (Collection::parse_search_query, src/collection.cpp): returns (include, exclude)."""
+    inc, exc = [], []
+    for w in q.split(" "):
+        if w.startswith("-") and len(w) > 1:
+            exc += tokenize(w[1:])
+        else:
+            inc += tokenize(w)
+    return inc, exc
+
+
+def excluded_ids(coll: Collection, exc: List[str]) -> List[int]:
+    """ids holding any exclusion token in any searched field (the host builds `excluded_result_ids` from the tokens' posting
+    lists before run_search)."""
+    out = set()
+    for t in exc:
+        for v, fl in zip(coll.vocabs, coll.flats):
+            l = v.get(t)
+            if l is not None:
+                out.update(int(x) for x in fl.ids[int(fl.list_off[l]):int(fl.list_off[l + 1])])
+    return sorted(out)
+
+
+def search(backend, coll: Collection, q: str, sort, drop_tokens_threshold: int = 1, topster: int = 250, wildcard_backend=None):
     """backend(batch, stride) -> (kv, cnt, found). Returns (ordered seq_ids, found)."""
-    tokens = tokenize(q)
+    tokens, exc = split_query(q)
+    excl = excluded_ids(coll, exc)
+    if not tokens and exc and wildcard_backend is not None:
+        # only exclusion tokens: the query becomes `*` minus the excluded ids (Index::search_wildcard path)
+        Kw = max(1, min(max(topster, 250), coll.n_docs))
+        query = S.Query([], topk=Kw, sort=sort, excl=excl)
+        kv, cnt, found = wildcard_backend(S.KwBatch([query], list(range(len(coll.fields)))), Kw)
+        return [int(kv["key"][0, i]) for i in range(int(cnt[0]))], int(found[0])
     K = max(1, min(max(topster, 250), coll.n_docs))          # src/index.cpp:3506-3512
     best: Dict[int, tuple] = {}
     all_ids = set()
@@ -80,7 +110,7 @@ def search(backend, coll: Collection, q: str, sort, drop_tokens_threshold: int =
         if not trunc or any(all(x == S.NO_LIST for x in row_of(t)) for t in trunc):
             return                                           # no candidate at cost 0: fuzzy_search_fields returns
         rows = [row_of(t) for t in trunc] + [row_of(t) for t in dropped]
-        query = S.Query([S.Combo(rows, len(trunc))], topk=K, sort=sort, num_query_tokens=len(trunc),
+        query = S.Query([S.Combo(rows, len(trunc))], topk=K, sort=sort, num_query_tokens=len(trunc), excl=excl,
                         field_weight=[max(0, 15 - f) for f in range(F)])      # src/collection.cpp:4219-4225
         kv, cnt, found = backend(S.KwBatch([query], list(range(F))), K)
         for i in range(int(cnt[0])):

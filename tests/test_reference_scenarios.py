@@ -35,6 +35,35 @@ def scenarios(backend, coll):
     assert got == [] and found == 0
 
 
+def more_scenarios(backend, coll, wildcard_backend=None):
+    """num_typos = 0 cases of PartialMultiTokenSearch, SkipUnindexedTokensDuringMultiTokenSearch and
+    SearchWithExcludedTokens (test/collection_test.cpp:238-372): drop-tokens flow in both directions, tokens missing
+    from the index, exclusion tokens."""
+    # PartialMultiTokenSearch :358-372
+    got, found = refflow.search(backend, coll, "rocket research", SORT_DESC, drop_tokens_threshold=10)
+    assert ids_of(coll, got) == ["19", "1", "10", "8", "16", "17"]
+    # SkipUnindexedTokensDuringMultiTokenSearch :269-356
+    got, found = refflow.search(backend, coll, "DoesNotExist from", SORT_DESC)
+    assert ids_of(coll, got) == ["2", "17"]
+    got, found = refflow.search(backend, coll, "the a", SORT_DESC, drop_tokens_threshold=10)
+    assert len(got) == 9
+    got, found = refflow.search(backend, coll, "the a", SORT_DESC, drop_tokens_threshold=0)
+    assert ids_of(coll, got) == ["8", "16", "10"]
+    got, found = refflow.search(backend, coll, "the a insurance", SORT_DESC, drop_tokens_threshold=0)
+    assert got == []
+    got, found = refflow.search(backend, coll, "DoesNotExist1 DoesNotExist2", SORT_DESC)
+    assert got == []
+    # SearchWithExcludedTokens :238-267
+    got, found = refflow.search(backend, coll, "how -propellants -are", SORT_DESC, drop_tokens_threshold=10)
+    assert ids_of(coll, got) == ["9", "17"] and found == 2
+    if wildcard_backend is not None:
+        # 23 documents + the fixture's dummy record 0 (test/collection_test.cpp:53-55), which matches `*` too
+        got, found = refflow.search(backend, coll, "-rocket", SORT_DESC, wildcard_backend=wildcard_backend)
+        assert found == 21 and len(got) == 21
+        got, found = refflow.search(backend, coll, "-rocket -cryovolcanism", SORT_DESC, wildcard_backend=wildcard_backend)
+        assert found == 20
+
+
 def multi_field_scenarios(make_backend):
     # MultiFieldRelevance, test/collection_test.cpp:3173-3258: title + artist, default weights 15/14, drop tokens <= 10
     q = "Dustin Kensrue Down There by the Train"
@@ -73,6 +102,7 @@ def test_reference_scenarios_oracle():
     coll = refflow.Collection.from_jsonl(os.path.join(GOLD, "documents.jsonl"))
     oi = ol.OracleIndex(coll.n_docs, [coll.flat], [coll.points])
     scenarios(lambda b, k: oi.keyword_search(b, k), coll)
+    more_scenarios(lambda b, k: oi.keyword_search(b, k), coll, lambda b, k: oi.wildcard_search(b, k))
 
 
 @pytest.mark.gpu
@@ -83,4 +113,5 @@ def test_reference_scenarios_gpu():
     gi.load_field(coll.flat)
     gi.load_sort_column(coll.points)
     scenarios(lambda b, k: gi.keyword_search(b, k), coll)
+    more_scenarios(lambda b, k: gi.keyword_search(b, k), coll, lambda b, k: gi.wildcard_search(b, k))
     gi.close()
