@@ -39,20 +39,37 @@ class Collection:
         for fname in self.fields:
             vocab: Dict[str, int] = {}
             per_tok: List[list] = []
+            is_array = any(isinstance(d.get(fname), (list, tuple)) for d in self.docs)
             for sid, d in enumerate(self.docs):
-                toks = tokenize(d.get(fname, ""))
                 t2o: Dict[str, list] = {}
-                for i, t in enumerate(toks):
-                    t2o.setdefault(t, []).append(i + 1)
-                if toks:
-                    t2o[toks[-1]].append(0)           # src/index.cpp:1341-1348
+                if is_array:
+                    # string[]: per element and token positions..., last position repeated, array index; the element's last
+                    # token also gets 0 (src/index.cpp:1357-1393)
+                    for ai, elem in enumerate(d.get(fname) or []):
+                        toks = tokenize(elem)
+                        seen: List[str] = []
+                        for i, t in enumerate(toks):
+                            t2o.setdefault(t, []).append(i + 1)
+                            if t not in seen:
+                                seen.append(t)
+                        for t in seen:
+                            t2o[t].append(t2o[t][-1])
+                            t2o[t].append(ai)
+                        if toks:
+                            t2o[toks[-1]].append(0)
+                else:
+                    toks = tokenize(d.get(fname, ""))
+                    for i, t in enumerate(toks):
+                        t2o.setdefault(t, []).append(i + 1)
+                    if toks:
+                        t2o[toks[-1]].append(0)           # src/index.cpp:1341-1348
                 for t, offs in t2o.items():
                     if t not in vocab:
                         vocab[t] = len(per_tok)
                         per_tok.append([])
                     per_tok[vocab[t]].append((sid, offs))
             self.vocabs.append(vocab)
-            self.flats.append(S.FlatField.from_postings(per_tok))
+            self.flats.append(S.FlatField.from_postings(per_tok, is_array))
         self.vocab, self.flat = self.vocabs[0], self.flats[0]
         self.points = np.asarray([d["points"] for d in self.docs], np.int64)
         self.n_docs = len(self.docs)
@@ -87,7 +104,9 @@ def excluded_ids(coll: Collection, exc: List[str]) -> List[int]:
     return sorted(out)
 
 
-def search(backend, coll: Collection, q: str, sort, drop_tokens_threshold: int = 1, topster: int = 250, wildcard_backend=None):
+def search(backend, coll: Collection, q: str, sort, drop_tokens_threshold: int = 1, topster: int = 250, wildcard_backend=None,
+           field_weights: Sequence[int] = None,
+           flags: int = S.FLAG_PRIORITIZE_EXACT_MATCH | S.FLAG_PRIORITIZE_NUM_MATCHING_FIELDS):   # Collection::search defaults
     """backend(batch, stride) -> (kv, cnt, found). Returns (ordered seq_ids, found)."""
     tokens, exc = split_query(q)
     excl = excluded_ids(coll, exc)
@@ -110,8 +129,8 @@ def search(backend, coll: Collection, q: str, sort, drop_tokens_threshold: int =
         if not trunc or any(all(x == S.NO_LIST for x in row_of(t)) for t in trunc):
             return                                           # no candidate at cost 0: fuzzy_search_fields returns
         rows = [row_of(t) for t in trunc] + [row_of(t) for t in dropped]
-        query = S.Query([S.Combo(rows, len(trunc))], topk=K, sort=sort, num_query_tokens=len(trunc), excl=excl,
-                        field_weight=[max(0, 15 - f) for f in range(F)])      # src/collection.cpp:4219-4225
+        query = S.Query([S.Combo(rows, len(trunc))], topk=K, sort=sort, num_query_tokens=len(trunc), excl=excl, flags=flags,
+                        field_weight=list(field_weights) if field_weights else [max(0, 15 - f) for f in range(F)])   # src/collection.cpp:4219-4225
         kv, cnt, found = backend(S.KwBatch([query], list(range(F))), K)
         for i in range(int(cnt[0])):
             key = int(kv["key"][0, i])

@@ -78,11 +78,93 @@ def multi_field_scenarios(make_backend):
         assert got == expect and found == 3
 
 
+def exact_match_scenario(make_backend):
+    # ExactMatch, test/collection_test.cpp:3638-3688 (query_by title only; typos/prefix find no other candidate in this
+    # vocabulary, so the flow is the exact tokens and then the drop-tokens round)
+    records = [("Alpha", "DJ"), ("Alpha Beta", "DJ"), ("Alpha Beta Gamma", "DJ")]
+    coll = refflow.Collection([{"title": t, "artist": a, "points": i} for i, (t, a) in enumerate(records)], ("title",))
+    backend, close = make_backend(coll)
+    got, found = refflow.search(backend, coll, "alpha beta", SORT_DESC, drop_tokens_threshold=10)
+    assert got == [1, 2, 0] and found == 3
+    got, found = refflow.search(backend, coll, "alpha", SORT_DESC, drop_tokens_threshold=10)
+    assert got == [0, 2, 1] and found == 3
+    close()
+
+
+def ranked_weights(given):
+    """query_by_weights are re-ranked into 15, 14, ... preserving ties (src/collection.cpp:4236-4271)."""
+    order = sorted(set(given), reverse=True)
+    return [15 - order.index(w) for w in given]
+
+
+def match_ranking_scenarios(make_backend):
+    # MultiFieldMatchRanking, test/collection_test.cpp:3788-3835: query_by artist,title; drop_tokens_threshold 5
+    titles = ["Style", "Blank Space", "Balance Overkill", "Cardigan", "Invisible String", "The Last Great American Dynasty",
+              "Mirrorball", "Peace", "Betty", "Mad Woman"]
+    coll = refflow.Collection([{"title": t, "artist": "Taylor Swift", "points": i} for i, t in enumerate(titles)], ("artist", "title"))
+    backend, close = make_backend(coll)
+    got, found = refflow.search(backend, coll, "taylor swift style", SORT_DESC, drop_tokens_threshold=5)
+    close()
+    assert got[:3] == [0, 9, 8] and found == 10
+    # MultiFieldMatchRankingOnArray :3837-3877: two string[] fields, drop_tokens_threshold 1
+    recs = [(["Golang", "Vue", "React"], ["Docker", "Goa", "Elixir"]), (["Golang", "Phoenix", "React"], ["Docker", "Vue", "Kubernetes"])]
+    coll = refflow.Collection([{"strong_skills": a, "skills": b, "points": i} for i, (a, b) in enumerate(recs)], ("strong_skills", "skills"))
+    backend, close = make_backend(coll)
+    got, found = refflow.search(backend, coll, "golang vue", SORT_DESC, drop_tokens_threshold=1)
+    close()
+    assert got == [0, 1] and found == 2
+    # MultiFieldMatchRankingOnFieldOrder :3879-3920: query_by title,artist with query_by_weights {1, 6}
+    recs = [("Toxic", "Britney Spears"), ("Bad", "Michael Jackson")]
+    coll = refflow.Collection([{"title": t, "artist": a, "points": i} for i, (t, a) in enumerate(recs)], ("title", "artist"))
+    backend, close = make_backend(coll)
+    got, found = refflow.search(backend, coll, "michael jackson toxic", SORT_DESC, drop_tokens_threshold=5, field_weights=ranked_weights([1, 6]))
+    close()
+    assert got == [1, 0] and found == 2
+
+
+def relevance2_scenarios(make_backend):
+    # MultiFieldRelevance2, test/collection_test.cpp:3276-3355: query_by title,artist; drop_tokens_threshold 10
+    recs = [("A Daikon Freestyle", "Ghosts on a Trampoline"), ("Leaving on a Jetplane", "Coby Grant")]
+    coll = refflow.Collection([{"title": t, "artist": a, "points": i} for i, (t, a) in enumerate(recs)], ("title", "artist"))
+    backend, close = make_backend(coll)
+    for weights in (None, ranked_weights([1, 4]), ranked_weights([1, 1])):
+        got, found = refflow.search(backend, coll, "on a jetplane", SORT_DESC, drop_tokens_threshold=10, field_weights=weights)
+        assert got == [1, 0] and found == 2, weights
+    got, found = refflow.search(backend, coll, "on a helicopter", SORT_DESC, drop_tokens_threshold=10, field_weights=ranked_weights([1, 4]))
+    close()
+    assert got == [0, 1] and found == 2
+
+
+def relevance36_scenarios(make_backend):
+    same = ranked_weights([1, 1])
+    # MultiFieldRelevance3, test/collection_test.cpp:3403-3460
+    recs = [("Taylor Swift Karaoke: reputation", "Taylor Swift"), ("Style", "Taylor Swift")]
+    coll = refflow.Collection([{"title": t, "artist": a, "points": i} for i, (t, a) in enumerate(recs)], ("title", "artist"))
+    backend, close = make_backend(coll)
+    got, found = refflow.search(backend, coll, "style taylor swift", SORT_DESC, drop_tokens_threshold=10, field_weights=same)
+    assert got == [1, 0] and found == 2
+    got, found = refflow.search(backend, coll, "swift", SORT_DESC, drop_tokens_threshold=10, field_weights=same)
+    close()
+    assert got == [0, 1] and found == 2
+    # MultiFieldRelevance6 :3581-3636: the number of fields with an exact match is not a ranking signal
+    recs = [("Taylor Swift", "Taylor Swift"), ("Taylor Swift Song", "Taylor Swift")]
+    coll = refflow.Collection([{"title": t, "artist": a, "points": i} for i, (t, a) in enumerate(recs)], ("title", "artist"))
+    backend, close = make_backend(coll)
+    for flags in (S.FLAG_PRIORITIZE_EXACT_MATCH | S.FLAG_PRIORITIZE_NUM_MATCHING_FIELDS, S.FLAG_PRIORITIZE_NUM_MATCHING_FIELDS):
+        got, found = refflow.search(backend, coll, "taylor swift", SORT_DESC, drop_tokens_threshold=10, field_weights=same, flags=flags)
+        assert got == [1, 0] and found == 2, flags
+    close()
+
+
 def test_multi_field_scenarios_oracle():
     def mk(coll):
         oi = ol.OracleIndex(coll.n_docs, coll.flats, [coll.points])
         return (lambda b, k: oi.keyword_search(b, k)), (lambda: None)
     multi_field_scenarios(mk)
+    exact_match_scenario(mk)
+    match_ranking_scenarios(mk)
+    relevance2_scenarios(mk)
+    relevance36_scenarios(mk)
 
 
 @pytest.mark.gpu
@@ -96,6 +178,10 @@ def test_multi_field_scenarios_gpu():
         gi.load_sort_column(coll.points)
         return (lambda b, k: gi.keyword_search(b, k)), gi.close
     multi_field_scenarios(mk)
+    exact_match_scenario(mk)
+    match_ranking_scenarios(mk)
+    relevance2_scenarios(mk)
+    relevance36_scenarios(mk)
 
 
 def test_reference_scenarios_oracle():
