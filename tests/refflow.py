@@ -160,4 +160,5 @@ def search(backend, coll: Collection, q: str, sort, drop_tokens_threshold: int =
             else:
                 break
     order = sorted(best.items(), key=lambda kv_: (kv_[1], kv_[0]), reverse=True)
+    search.last_scores = {k: v for k, v in order}            # seq_id -> scores[0..2] of the last call (for text_match KATs)
     return [k for k, _ in order], len(all_ids)

@@ -92,7 +92,10 @@ def exact_match_scenario(make_backend):
 
 
 def ranked_weights(given):
-    """query_by_weights are re-ranked into 15, 14, ... preserving ties (src/collection.cpp:4236-4271)."""
+    """Collection::process_search_field_weights (src/collection.cpp:4210-4275): weights already in descending order and
+    <= 15 are used as they are; otherwise they are re-ranked into 15, 14, ... preserving ties."""
+    if all(given[i] <= given[i - 1] for i in range(1, len(given))) and all(w <= 15 for w in given):
+        return list(given)
     order = sorted(set(given), reverse=True)
     return [15 - order.index(w) for w in given]
 
@@ -156,6 +159,19 @@ def relevance36_scenarios(make_backend):
     close()
 
 
+def repeating_token_scenario(make_backend):
+    # RepeatingTokenRanking, test/collection_sorting_test.cpp:1800-1855: a repeated query token, with the reference's
+    # literal text_match values
+    recs = [("Mong Mong", 100), ("Mong Spencer", 200), ("Mong Mong Spencer", 300), ("Spencer Mong Mong", 400)]
+    coll = refflow.Collection([{"title": t, "points": p} for t, p in recs], ("title",))
+    backend, close = make_backend(coll)
+    got, found = refflow.search(backend, coll, "mong mong", SORT_DESC, drop_tokens_threshold=10, field_weights=ranked_weights([3]))
+    close()
+    assert got == [0, 3, 2, 1]
+    tm = {k: v[0] for k, v in refflow.search.last_scores.items()}
+    assert tm[0] == 1157451471583709209 and tm[3] == tm[2] == tm[1] == 1157451471575320601
+
+
 def test_multi_field_scenarios_oracle():
     def mk(coll):
         oi = ol.OracleIndex(coll.n_docs, coll.flats, [coll.points])
@@ -165,6 +181,7 @@ def test_multi_field_scenarios_oracle():
     match_ranking_scenarios(mk)
     relevance2_scenarios(mk)
     relevance36_scenarios(mk)
+    repeating_token_scenario(mk)
 
 
 @pytest.mark.gpu
@@ -182,6 +199,7 @@ def test_multi_field_scenarios_gpu():
     match_ranking_scenarios(mk)
     relevance2_scenarios(mk)
     relevance36_scenarios(mk)
+    repeating_token_scenario(mk)
 
 
 def test_reference_scenarios_oracle():
