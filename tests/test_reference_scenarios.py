@@ -172,6 +172,19 @@ def repeating_token_scenario(make_backend):
     assert tm[0] == 1157451471583709209 and tm[3] == tm[2] == tm[1] == 1157451471575320601
 
 
+def text_match_literals_scenario(make_backend):
+    # test/collection_vector_search_test.cpp:5403-5497: text_match of "nike running shoes" per document. The reference
+    # reports doc 0 from the keyword pass and docs 1/2 through compute_aux_scores; the same values fall out of the
+    # drop-tokens rounds ("nike running", "shoes") here. 578730123365189753 is also test/union_test.cpp:810.
+    names = ["Nike running shoes for men", "Nike running sneakers", "adidas shoes", "puma"]
+    coll = refflow.Collection([{"name": n, "points": 0} for n in names], ("name",))
+    backend, close = make_backend(coll)
+    got, found = refflow.search(backend, coll, "nike running shoes", SORT_DESC, drop_tokens_threshold=10)
+    close()
+    tm = {k: v[0] for k, v in refflow.search.last_scores.items()}
+    assert got == [0, 1, 2] and tm == {0: 1736172819517016185, 1: 1157451471441102969, 2: 578730123365189753}
+
+
 def test_multi_field_scenarios_oracle():
     def mk(coll):
         oi = ol.OracleIndex(coll.n_docs, coll.flats, [coll.points])
@@ -182,6 +195,7 @@ def test_multi_field_scenarios_oracle():
     relevance2_scenarios(mk)
     relevance36_scenarios(mk)
     repeating_token_scenario(mk)
+    text_match_literals_scenario(mk)
 
 
 @pytest.mark.gpu
@@ -200,6 +214,7 @@ def test_multi_field_scenarios_gpu():
     relevance2_scenarios(mk)
     relevance36_scenarios(mk)
     repeating_token_scenario(mk)
+    text_match_literals_scenario(mk)
 
 
 def test_reference_scenarios_oracle():
