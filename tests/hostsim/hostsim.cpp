@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <random>
 #include <vector>
 
 #include "../../include/tsgpu.h"
@@ -177,6 +178,20 @@ size_t hs_idset_matches(const tsgpu_field* f, const uint32_t* lists, uint32_t k,
         if(ok) out[n_out++] = ids[i];
     }
     return n_out;
+}
+
+// Data of test/collection_vector_search_test.cpp:5094-5125 (TestDistanceThresholdWithIP): std::mt19937 seeded with 47,
+// five documents of five uniform_real_distribution<>(-1,1) draws (stored as float) each followed by one
+// uniform_int_distribution<>(0,100) draw for rank_score. libstdc++'s distributions, like the reference's build.
+void hs_ip_kat_data(float* vec_out, int* rank_out) {
+    std::mt19937 rng;
+    rng.seed(47);
+    std::uniform_real_distribution<> distrib(-1, 1);
+    std::uniform_int_distribution<> distrib2(0, 100);
+    for(int i = 0; i < 5; i++) {
+        for(int j = 0; j < 5; j++) vec_out[i * 5 + j] = (float) distrib(rng);
+        rank_out[i] = distrib2(rng);
+    }
 }
 
 int hs_phrase_match_doc(uint32_t k, const uint32_t* tok_off, const uint32_t* raw) {

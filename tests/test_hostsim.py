@@ -29,6 +29,7 @@ def hs():
     L.hs_keyword_combo.argtypes = [C.POINTER(S.FieldStruct), C.c_uint32, C.POINTER(S.KwBatchStruct), C.c_uint32, C.c_uint32,
                                    S.u32p, S.u64p, C.c_size_t]
     L.hs_phrase_match_doc.argtypes = [C.c_uint32, S.u32p, S.u32p]
+    L.hs_ip_kat_data.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.hs_idset_matches.restype = C.c_size_t
     L.hs_idset_matches.argtypes = [C.POINTER(S.FieldStruct), S.u32p, C.c_uint32, S.u32p, C.c_size_t, C.c_int, S.u32p]
     L.hs_probe_ids.argtypes = [S.u32p, C.c_uint64, S.u32p, C.c_uint64, S.u32p]
@@ -184,3 +185,27 @@ def test_device_idset_modes_match_oracle(hs, small_collection):
                 assert out[:n].tolist() == hout[:hn].tolist(), (fi, mode, lists.tolist())
                 hits[mode] += n
     assert min(hits.values()) > 20, hits
+
+
+def test_ip_distance_reference_kat(hs):
+    """test/collection_vector_search_test.cpp:5094-5196 (TestDistanceThresholdWithIP): inner-product distances 1 - dot on
+    data regenerated with the reference's own RNG recipe; the rank_score literals prove the stream is the same."""
+    vec = np.zeros((5, 5), np.float32)
+    rank = np.zeros(5, np.int32)
+    hs.hs_ip_kat_data(vec.ctypes.data_as(C.POINTER(C.c_float)), rank.ctypes.data_as(C.POINTER(C.c_int)))
+    assert sorted(rank.tolist()) == sorted([93, 51, 94, 80, 18])
+    L = ol.oracle()
+    f32p = C.POINTER(C.c_float)
+
+    def dist(q):
+        q = np.asarray(q, np.float32)
+        return [float(L.tso_ip_distance(q.ctypes.data_as(f32p), np.ascontiguousarray(vec[i]).ctypes.data_as(f32p), 5)) for i in range(5)]
+    d = dist([0.11731103425347378, -0.6694758317235057, -0.6211945774857595, -0.27966758971688255, -0.4683744007950299])
+    by_rank = {int(rank[i]): d[i] for i in range(5)}
+    assert by_rank[93] == pytest.approx(0.2189185470342636, rel=1e-5) and by_rank[51] == pytest.approx(0.7371898889541626, rel=1e-5)
+    assert all(by_rank[r] > 1.0 for r in (94, 80, 18))          # beyond distance_threshold:1 in the reference test
+    d = dist([-100] * 5)
+    expect = {1: -45.23314666748047, 2: -38.66290283203125, 4: -36.0988655090332, 3: 9.637892723083496, 0: 288.0364685058594}
+    for i, e in expect.items():
+        assert d[i] == pytest.approx(e, rel=1e-5), i
+    assert sorted(range(5), key=lambda i: d[i]) == [1, 2, 4, 3, 0]
