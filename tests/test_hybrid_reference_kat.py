@@ -1,0 +1,82 @@
+"""Rank-fusion expectations of the reference's own hybrid tests, replayed on the oracle (CPU; the GPU path is compared with the oracle on
+random hybrid batches in test_gpu_parity.py). The reference embeds text with a model that is not available offline; only the ORDER of the vector distances
+matters to these assertions, so vectors with that order stand in. What is pinned: text ranks (ties share a rank), vector
+ranks, the 0.7 / 0.3 weights, the float arithmetic of the fused score and the final order.
+  test/collection_test.cpp:4779-4850            HybridSearchRankFusionTest
+  test/collection_vector_search_test.cpp:5674-5753   TestRankFusionOrdering"""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from typesense_b200 import structs as S
+
+SORT = ((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_SEQ_ID, -1, 1, 0), (S.SORT_NONE, -1, 1, 0))   # no default_sorting_field
+FLAGS = S.FLAG_PRIORITIZE_EXACT_MATCH | S.FLAG_PRIORITIZE_NUM_MATCHING_FIELDS
+
+
+def unit(v):
+    v = np.asarray(v, np.float32)
+    return v / np.linalg.norm(v)
+
+
+def fused(kv, cnt):
+    """[(seq_id, rank_fusion_score as float)] of query 0 in result order."""
+    out = []
+    for i in range(int(cnt[0])):
+        msi = int(kv["match_score_index"][0, i])
+        bits = np.int64(kv["scores"][0, i][msi]).astype(np.int32)
+        out.append((int(kv["key"][0, i]), float(bits.view(np.float32))))
+    return out
+
+
+def field_of(docs):
+    """plain string field: docs = list of token lists"""
+    vocab, per_tok = {}, []
+    for sid, toks in enumerate(docs):
+        t2o = {}
+        for i, t in enumerate(toks):
+            t2o.setdefault(t, []).append(i + 1)
+        t2o[toks[-1]].append(0)
+        for t, offs in t2o.items():
+            if t not in vocab:
+                vocab[t] = len(per_tok)
+                per_tok.append([])
+            per_tok[vocab[t]].append((sid, offs))
+    return vocab, S.FlatField.from_postings(per_tok)
+
+
+def cases():
+    q = unit([1, 0.2, 0, 0])
+    # HybridSearchRankFusionTest: "butter" with prefix search -> candidates butter (cost 0), butterfly / butterball (prefix,
+    # cost 1: next_suggestion2 adds 1 for a prefix-found candidate). Vector order butter < butterball < butterfly.
+    vocab, flat = field_of([["butter"], ["butterball"], ["butterfly"]])
+    vecs = np.stack([q, unit([1, 0.5, 0, 0]), unit([1, 1.5, 0, 0])])
+    combos = [S.Combo([[vocab["butter"]]], 1, total_cost=0), S.Combo([[vocab["butterfly"]]], 1, total_cost=1),
+              S.Combo([[vocab["butterball"]]], 1, total_cost=1)]
+    yield ("HybridSearchRankFusionTest", flat, vecs, q, combos,
+           [(0, 1.0 / 1.0 * 0.7 + 1.0 / 1.0 * 0.3), (1, 1.0 / 2.0 * 0.7 + 1.0 / 2.0 * 0.3), (2, 1.0 / 2.0 * 0.7 + 1.0 / 3.0 * 0.3)])
+    # TestRankFusionOrdering: "apple" matches all three with the same text score (one shared text rank); vector order
+    # green apple < apple pie < red apple
+    vocab, flat = field_of([["red", "apple"], ["green", "apple"], ["apple", "pie"]])
+    vecs = np.stack([unit([1, 2.0, 0, 0]), q, unit([1, 0.8, 0, 0])])
+    yield ("TestRankFusionOrdering", flat, vecs, q, [S.Combo([[vocab["apple"]]], 1, total_cost=0)],
+           [(1, 0.7 + 0.3 * 1.0 / 1.0), (2, 0.7 + 0.3 * 1.0 / 2.0), (0, 0.7 + 0.3 * 1.0 / 3.0)])
+
+
+def check(run):
+    for name, flat, vecs, q, combos, expect in cases():
+        graph = ol.hnsw_build(vecs, 16, 200, 100)
+        b = S.KwBatch([S.Query(combos, topk=250, sort=SORT, flags=FLAGS, num_query_tokens=1, field_weight=[15])], [0])
+        kv, cnt, found = run(flat, graph, b, q[None, :].copy(), S.vec_params(k=0, ef=10, alpha=0.3, fetch_size=10))
+        got = fused(kv, cnt)
+        assert [k for k, _ in got] == [k for k, _ in expect], name
+        for (_, g), (_, e) in zip(got, expect):
+            assert g == pytest.approx(np.float32(e), rel=3e-7), name          # ASSERT_FLOAT_EQ in the reference
+        assert int(found[0]) == 3, name
+
+
+def test_rank_fusion_reference_kats_oracle():
+    def run(flat, graph, b, qv, vp):
+        oi = ol.OracleIndex(3, [flat], [], graph)
+        return oi.hybrid_search(b, qv, vp, 256)
+    check(run)
