@@ -30,6 +30,8 @@ def hs():
                                    S.u32p, S.u64p, C.c_size_t]
     L.hs_phrase_match_doc.argtypes = [C.c_uint32, S.u32p, S.u32p]
     L.hs_ip_kat_data.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.hs_sort_scores.argtypes = [S.u8p, S.i8p, S.u8p, C.POINTER(C.POINTER(C.c_int64)), C.c_uint32, C.c_int64, C.c_float,
+                                 C.POINTER(C.c_int64), C.POINTER(C.c_int)]
     L.hs_idset_matches.restype = C.c_size_t
     L.hs_idset_matches.argtypes = [C.POINTER(S.FieldStruct), S.u32p, C.c_uint32, S.u32p, C.c_size_t, C.c_int, S.u32p]
     L.hs_probe_ids.argtypes = [S.u32p, C.c_uint64, S.u32p, C.c_uint64, S.u32p]
@@ -209,3 +211,54 @@ def test_ip_distance_reference_kat(hs):
     for i, e in expect.items():
         assert d[i] == pytest.approx(e, rel=1e-5), i
     assert sorted(range(5), key=lambda i: d[i]) == [1, 2, 4, 3, 0]
+
+
+def hostsim_backend(L, coll):
+    """refflow backend that runs every combination of a one-query batch through the product's device functions compiled
+    for the host (probe, scoring, sort keys) and keeps the top-K on the CPU — the kernels' per-document logic without a GPU."""
+    pts = np.ascontiguousarray(coll.points, np.int64)
+    cols = (C.POINTER(C.c_int64) * 3)()
+
+    def run(b, K):
+        assert b.n_queries == 1
+        best = {}
+        for c in range(int(b.q_combo_off[0]), int(b.q_combo_off[1])):
+            ids, sc = hs_combo(L, coll.flats, b, 0, c)
+            for sid, text in zip(ids.tolist(), sc.tolist()):
+                for i in range(3):
+                    col = int(b.q_sort_col[i])
+                    cols[i] = pts.ctypes.data_as(C.POINTER(C.c_int64)) if int(b.q_sort_type[i]) == S.SORT_NUMERIC and col == 0 else None
+                out = (C.c_int64 * 3)()
+                msi = C.c_int(0)
+                L.hs_sort_scores(b.q_sort_type.ctypes.data_as(S.u8p), b.q_sort_order.ctypes.data_as(S.i8p),
+                                 b.q_sort_missing_first.ctypes.data_as(S.u8p), cols, sid, np.int64(np.uint64(text).astype(np.int64)), 0.0,
+                                 out, C.byref(msi))
+                tup = (int(out[0]), int(out[1]), int(out[2]))
+                if sid not in best or tup >= best[sid]:
+                    best[sid] = tup
+        order = sorted(best.items(), key=lambda kv_: (kv_[1], kv_[0]), reverse=True)[:K]
+        kv = np.zeros((1, max(K, 1)), S.KV_DTYPE)
+        for i, (sid, tup) in enumerate(order):
+            kv["key"][0, i] = sid
+            kv["scores"][0, i] = tup
+        return kv, np.asarray([len(order)], np.uint32), np.asarray([len(best)], np.uint32)
+    return run
+
+
+def test_device_functions_reproduce_reference_scenarios(hs):
+    """The reference's end-to-end expectations (incl. its literal text_match values) through score_device.cuh /
+    postings_device.cuh compiled for the host: what the CUDA threads compute per document, checked here without a GPU."""
+    import test_reference_scenarios as trs
+
+    def mk(coll):
+        return hostsim_backend(hs, coll), (lambda: None)
+    trs.multi_field_scenarios(mk)
+    trs.exact_match_scenario(mk)
+    trs.match_ranking_scenarios(mk)
+    trs.relevance2_scenarios(mk)
+    trs.relevance36_scenarios(mk)
+    trs.repeating_token_scenario(mk)
+    trs.text_match_literals_scenario(mk)
+    coll = trs.refflow.Collection.from_jsonl(os.path.join(trs.GOLD, "documents.jsonl"))
+    trs.scenarios(hostsim_backend(hs, coll), coll)
+    trs.more_scenarios(hostsim_backend(hs, coll), coll)
