@@ -8,6 +8,7 @@ kat = {
   "posting_intersect": [  # test/posting_list_test.cpp:603-700 (IntersectionBasics), block size 2
     {"src": "test/posting_list_test.cpp:603-652", "lists": [[0, 2, 3, 20], [1, 3, 5, 10, 20], [2, 3, 5, 7, 20]], "expect": [3, 20]},
     {"src": "test/posting_list_test.cpp:654-662", "lists": [[0, 2, 3, 20]], "expect": [0, 2, 3, 20]},
+    {"src": "test/posting_list_test.cpp:1295-1328 (BlockIntersectionOnMixedLists: compact list x full list)", "lists": [[5, 6, 7, 8], [0, 5, 8, 20]], "expect": [5, 8]},
     {"src": "test/posting_list_test.cpp:774-823 (IntersectionSkipBlocks)", "lists": [[9, 11], [1, 2, 3, 4, 5, 6, 7, 8, 9, 11], [2, 3, 8, 9, 11, 20]], "expect": [9, 11]},
   ],
   "posting_merge": [      # test/posting_list_test.cpp:559-601 (MergeBasics)
