@@ -140,12 +140,46 @@ static void vector_scenario() {
     if(pairs.size() == 2) CHECK(pairs[0].second == 1 && pairs[1].second == 0);
 }
 
+// posting_t::get_exact_matches / get_prefix_matches (src/posting_list.cpp:1129-1452) on the ExactMatch documents of
+// test/collection_test.cpp:3638, and ArrayUtils (test/array_utils_test.cpp:5-172)
+static void exact_prefix_and_setops() {
+    tsgpu::Index index(3);
+    tsgpu::field_mirror_t title;
+    const char* docs[] = {"Alpha", "Alpha Beta", "Alpha Beta Gamma"};
+    for(uint32_t i = 0; i < 3; i++) title.index_plain_string(i, tsgpu::tokenize_ascii(docs[i]));
+    CHECK(index.add_field("title", title).ok());
+    std::vector<uint32_t> both, exact, prefix;
+    CHECK(index.intersect("title", {"alpha", "beta"}, both).ok());
+    CHECK((both == std::vector<uint32_t>{1, 2}));
+    CHECK(index.get_exact_matches("title", {"alpha", "beta"}, both, exact).ok());
+    CHECK((exact == std::vector<uint32_t>{1}));
+    CHECK(index.get_exact_matches("title", {"alpha", "beta"}, both, prefix, true).ok());
+    CHECK((prefix == std::vector<uint32_t>{1, 2}));
+    std::vector<uint32_t> all;
+    CHECK(index.intersect("title", {"alpha"}, all).ok());
+    CHECK(index.get_exact_matches("title", {"alpha"}, all, exact).ok());
+    CHECK((exact == std::vector<uint32_t>{0}));
+
+    tsgpu::Index ids(400);
+    std::vector<uint32_t> a = {0, 1, 2, 3, 4, 5, 6, 7, 8}, out;
+    CHECK(ids.ids_setop(TSGPU_SET_AND, a, {3, 6, 9}, out).ok());
+    CHECK((out == std::vector<uint32_t>{3, 6}));
+    CHECK(ids.ids_setop(TSGPU_SET_OR, a, {3, 6, 9}, out).ok());
+    CHECK((out == std::vector<uint32_t>{0, 1, 2, 3, 4, 5, 6, 7, 8, 9}));
+    CHECK(ids.ids_setop(TSGPU_SET_EXCLUDE, a, {0, 1, 5, 7, 8}, out).ok());
+    CHECK((out == std::vector<uint32_t>{2, 3, 4, 6}));
+    CHECK(ids.ids_setop(TSGPU_SET_EXCLUDE, {58, 118, 185, 260, 322, 334, 353},
+                        {58, 103, 116, 117, 137, 154, 191, 210, 211, 284, 299, 302, 306, 309, 332, 334, 360}, out).ok());
+    CHECK((out == std::vector<uint32_t>{118, 185, 260, 322, 353}));
+}
+
 int main(int argc, char** argv) {
     if(tsgpu_device_count() == 0) { printf("no CUDA device: nothing to run (the library has no CPU path)\n"); return 99; }
     posting_list_intersection_basics();
     or_iterator_intersect_and_filter();
     collection_scenarios(argc > 1 ? argv[1] : "tests/golden/documents.jsonl");
     vector_scenario();
+    exact_prefix_and_setops();
     printf("%s (%d failed checks)\n", failures ? "FAILED" : "PASSED", failures);
     return failures;
 }

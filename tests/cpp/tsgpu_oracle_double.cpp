@@ -1,0 +1,139 @@
+// TEST INFRASTRUCTURE — a test double of the tsgpu C-ABI (include/tsgpu.h) that answers from the CPU oracle, so the C++
+// host layer (typesense_b200/host/tsgpu_host.hpp: tokenising, field mirrors, the drop-tokens loop, host_topster_t, the
+// call marshalling) can be exercised by tests/cpp/host_scenarios.cpp on a machine WITHOUT a GPU. It lives under tests/,
+// is linked only into the CPU build of that one test program, and is never part of libtsgpu.so: the product has no CPU
+// path. Layouts of tsgpu_* and tso_* structs are identical by construction (tests/oracle_lib.py passes one ctypes
+// struct to both), which the static_asserts below re-check.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tsgpu.h"
+#include "../../oracle/ts_oracle.h"
+
+static_assert(sizeof(tsgpu_kv) == sizeof(tso_kv), "KV layout");
+static_assert(sizeof(tsgpu_field) == sizeof(tso_field), "field layout");
+static_assert(sizeof(tsgpu_kw_batch) == sizeof(tso_kw_batch), "batch layout");
+static_assert(sizeof(tsgpu_hnsw) == sizeof(tso_hnsw), "hnsw layout");
+
+namespace {
+struct FieldCopy {
+    std::vector<uint64_t> list_off, pos_off;
+    std::vector<uint32_t> ids, positions;
+    tso_field view{};
+};
+struct Double {
+    uint32_t n_docs = 0;
+    void* oi = nullptr;
+    std::vector<FieldCopy*> fields;
+    std::vector<std::vector<int64_t>*> cols;
+    std::vector<float> vec; std::vector<uint32_t> labels, links0, links_up; std::vector<uint8_t> levels; std::vector<uint64_t> upper_off;
+    tso_hnsw g{};
+    bool has_g = false;
+};
+thread_local std::string g_err;
+Double* D(tsgpu_index* p) { return reinterpret_cast<Double*>(p); }
+}
+
+extern "C" {
+
+const char* tsgpu_last_error(void) { return g_err.c_str(); }
+int tsgpu_device_count(void) { return 1; }   /* the double stands in for one device so the scenario program runs */
+
+tsgpu_status tsgpu_index_create(uint32_t n_docs, int, tsgpu_index** out) {
+    Double* d = new Double();
+    d->n_docs = n_docs;
+    d->oi = tso_index_new(n_docs);
+    *out = reinterpret_cast<tsgpu_index*>(d);
+    return TSGPU_OK;
+}
+void tsgpu_index_destroy(tsgpu_index* idx) {
+    if(!idx) return;
+    Double* d = D(idx);
+    tso_index_free(d->oi);
+    for(auto f: d->fields) delete f;
+    for(auto c: d->cols) delete c;
+    delete d;
+}
+tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint32_t* out_field) {
+    Double* d = D(idx);
+    FieldCopy* c = new FieldCopy();
+    const uint64_t n_post = f->list_off[f->n_lists];
+    c->list_off.assign(f->list_off, f->list_off + f->n_lists + 1);
+    c->ids.assign(f->ids, f->ids + n_post);
+    c->pos_off.assign(f->pos_off, f->pos_off + n_post + 1);
+    c->positions.assign(f->positions, f->positions + f->pos_off[n_post]);
+    if(c->ids.empty()) c->ids.push_back(0);
+    if(c->positions.empty()) c->positions.push_back(0);
+    c->view.n_lists = f->n_lists; c->view.is_array = f->is_array;
+    c->view.list_off = c->list_off.data(); c->view.ids = c->ids.data(); c->view.pos_off = c->pos_off.data(); c->view.positions = c->positions.data();
+    d->fields.push_back(c);
+    const int id = tso_index_add_field(d->oi, &c->view);
+    if(out_field) *out_field = (uint32_t) id;
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_index_load_sort_column(tsgpu_index* idx, const int64_t* vals, uint32_t* out_col) {
+    Double* d = D(idx);
+    auto* c = new std::vector<int64_t>(vals, vals + d->n_docs);
+    d->cols.push_back(c);
+    const int id = tso_index_add_sort_column(d->oi, c->data());
+    if(out_col) *out_col = (uint32_t) id;
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g) {
+    Double* d = D(idx);
+    const size_t n = g->n_nodes;
+    d->vec.assign(g->vectors, g->vectors + n * g->dim);
+    if(g->labels) d->labels.assign(g->labels, g->labels + n);
+    else { d->labels.resize(n); for(size_t i = 0; i < n; i++) d->labels[i] = (uint32_t) i; }   // tsgpu: NULL labels = identity
+    d->levels.assign(g->levels, g->levels + n);
+    d->links0.assign(g->links0, g->links0 + n * (2 * g->M + 1));
+    d->upper_off.assign(g->upper_off, g->upper_off + n + 1);
+    d->links_up.assign(g->links_up, g->links_up + (size_t) g->upper_off[n] * (g->M + 1));
+    if(d->links_up.empty()) d->links_up.push_back(0);
+    d->g.n_nodes = g->n_nodes; d->g.dim = g->dim; d->g.M = g->M; d->g.max_level = g->max_level; d->g.entry_point = g->entry_point; d->g.metric = g->metric;
+    d->g.vectors = d->vec.data(); d->g.labels = d->labels.data(); d->g.levels = d->levels.data();
+    d->g.links0 = d->links0.data(); d->g.upper_off = d->upper_off.data(); d->g.links_up = d->links_up.data();
+    d->has_g = true;
+    tso_index_set_hnsw(d->oi, &d->g);
+    return TSGPU_OK;
+}
+
+tsgpu_status tsgpu_intersect(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, uint32_t* out_ids, size_t cap, size_t* out_n) {
+    Double* d = D(idx);
+    const FieldCopy& f = *d->fields[field];
+    std::vector<const uint32_t*> ptr(k); std::vector<size_t> len(k);
+    for(uint32_t j = 0; j < k; j++) { ptr[j] = f.ids.data() + f.list_off[lists[j]]; len[j] = (size_t) (f.list_off[lists[j] + 1] - f.list_off[lists[j]]); }
+    *out_n = tso_intersect(k, ptr.data(), len.data(), out_ids, cap);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_phrase_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, const uint32_t* ids, size_t n, uint32_t* out_ids, size_t* out_n) {
+    *out_n = tso_phrase_matches(D(idx)->oi, field, lists, k, ids, n, out_ids);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_exact_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, const uint32_t* ids, size_t n, uint32_t* out_ids, size_t* out_n) {
+    *out_n = tso_exact_matches(D(idx)->oi, field, lists, k, ids, n, out_ids);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_prefix_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, const uint32_t* ids, size_t n, uint32_t* out_ids, size_t* out_n) {
+    *out_n = tso_prefix_matches(D(idx)->oi, field, lists, k, ids, n, out_ids);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_ids_setop(tsgpu_index*, int op, const uint32_t* a, size_t na, const uint32_t* b, size_t nb, uint32_t* out_ids, size_t, size_t* out_n) {
+    *out_n = op == TSGPU_SET_AND ? tso_and_scalar(a, na, b, nb, out_ids) : op == TSGPU_SET_OR ? tso_or_scalar(a, na, b, nb, out_ids) : tso_exclude_scalar(a, na, b, nb, out_ids);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_keyword_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
+    tso_keyword_search_batch(D(idx)->oi, reinterpret_cast<const tso_kw_batch*>(b), reinterpret_cast<tso_kv*>(out_kv), kv_stride, out_count, out_found, 1);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_knn_batch(tsgpu_index* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef, const int32_t* q_filter, uint32_t,
+                             const uint64_t* filter_off, const uint32_t* filter_ids, float* out_dist, uint32_t* out_labels, uint32_t* out_n) {
+    Double* d = D(idx);
+    if(!d->has_g) { g_err = "no vector index loaded"; return TSGPU_ERR_INVALID; }
+    uint64_t stats[2] = {0, 0};
+    tso_hnsw_search_batch(&d->g, queries, nq, k, ef, q_filter, filter_off, filter_ids, out_dist, out_labels, out_n, stats, 1);
+    return TSGPU_OK;
+}
+
+}  // extern "C"

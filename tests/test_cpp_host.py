@@ -20,6 +20,23 @@ def build():
     subprocess.check_call(cmd)
 
 
+def test_cpp_host_scenarios_on_oracle_double():
+    """The same scenario program linked against tests/cpp/tsgpu_oracle_double.cpp (the C-ABI answered by the CPU oracle)
+    instead of libtsgpu.so: checks the C++ host layer's own logic — tokenising, field mirrors, the drop-tokens loop,
+    host_topster_t, marshalling — on a machine without a GPU. A test double, not a fallback: it is never linked into
+    the product."""
+    ol.build_oracle()
+    src = os.path.join(ROOT, "tests", "cpp", "host_scenarios.cpp")
+    dbl = os.path.join(ROOT, "tests", "cpp", "tsgpu_oracle_double.cpp")
+    exe = BIN + "_oracle_double"
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wno-unused", src, dbl, "-o", exe, "-L", os.path.join(ROOT, "oracle"),
+           "-l:liboracle.so", f"-Wl,-rpath,{os.path.join(ROOT, 'oracle')}", "-pthread"]
+    subprocess.check_call(cmd)
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "documents.jsonl")], capture_output=True, text=True, cwd=ROOT)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_cpp_host_layer_builds():
     build()
     assert os.path.exists(BIN)
