@@ -103,6 +103,23 @@ static void collection_scenarios(const std::string& jsonl) {
     CHECK(found == 7);
     CHECK(index.search(tsgpu::tokenize_ascii("zxsadqewsad"), {"title"}, sort_fields, 1, 250, kvs, found).ok());
     CHECK(kvs.empty() && found == 0);
+    // PartialMultiTokenSearch :358-372, SkipUnindexedTokensDuringMultiTokenSearch :269-356, SearchWithExcludedTokens :238-267
+    CHECK(index.search(tsgpu::tokenize_ascii("rocket research"), {"title"}, sort_fields, 10, 250, kvs, found).ok());
+    CHECK((ids_of(kvs) == std::vector<std::string>{"19", "1", "10", "8", "16", "17"}));
+    CHECK(index.search(tsgpu::tokenize_ascii("DoesNotExist from"), {"title"}, sort_fields, 1, 250, kvs, found).ok());
+    CHECK((ids_of(kvs) == std::vector<std::string>{"2", "17"}));
+    CHECK(index.search(tsgpu::tokenize_ascii("the a"), {"title"}, sort_fields, 10, 250, kvs, found).ok());
+    CHECK(kvs.size() == 9);
+    CHECK(index.search(tsgpu::tokenize_ascii("the a"), {"title"}, sort_fields, 0, 250, kvs, found).ok());
+    CHECK((ids_of(kvs) == std::vector<std::string>{"8", "16", "10"}));
+    CHECK(index.search(tsgpu::tokenize_ascii("the a insurance"), {"title"}, sort_fields, 0, 250, kvs, found).ok());
+    CHECK(kvs.empty());
+    {
+        tsgpu::search_options o;
+        o.exclude_tokens = {"propellants", "are"};
+        CHECK(index.search(tsgpu::tokenize_ascii("how"), {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
+        CHECK((ids_of(kvs) == std::vector<std::string>{"9", "17"}) && found == 2);
+    }
     // phrase: "rocket launch" as a phrase only in doc 8 ("... of a rocket launch these days")
     std::vector<uint32_t> both, phrase;
     CHECK(index.intersect("title", {"rocket", "launch"}, both).ok());
@@ -173,6 +190,123 @@ static void exact_prefix_and_setops() {
     CHECK((out == std::vector<uint32_t>{118, 185, 260, 322, 353}));
 }
 
+// ---- more of the reference's end-to-end expectations, through Index::search with Collection::search's defaults
+struct Rec { std::vector<std::string> values; };     // one string per field
+
+static std::vector<uint32_t> keys_of(const std::vector<tsgpu::KV>& kvs) { std::vector<uint32_t> r; for(auto& kv: kvs) r.push_back((uint32_t) kv.key); return r; }
+
+// builds an index over `fields` (plain strings) with points = row number
+static void build_plain(tsgpu::Index& index, const std::vector<std::string>& fields, const std::vector<Rec>& recs) {
+    for(size_t f = 0; f < fields.size(); f++) {
+        tsgpu::field_mirror_t m;
+        for(uint32_t i = 0; i < recs.size(); i++) m.index_plain_string(i, tsgpu::tokenize_ascii(recs[i].values[f]));
+        CHECK(index.add_field(fields[f], m).ok());
+    }
+    std::unordered_map<uint32_t, int64_t> points;
+    for(uint32_t i = 0; i < recs.size(); i++) points[i] = i;
+    CHECK(index.add_sort_field("points", points).ok());
+}
+
+static void relevance_scenarios() {
+    const std::vector<tsgpu::sort_by> sort_fields = {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::numeric, "points", true}};
+    std::vector<tsgpu::KV> kvs;
+    size_t found = 0;
+    {   // ExactMatch, test/collection_test.cpp:3638-3688
+        tsgpu::Index index(3);
+        build_plain(index, {"title"}, {{{"Alpha"}}, {{"Alpha Beta"}}, {{"Alpha Beta Gamma"}}});
+        CHECK(index.search(tsgpu::tokenize_ascii("alpha beta"), {"title"}, sort_fields, 10, 250, kvs, found).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 2, 0}) && found == 3);
+        CHECK(index.search(tsgpu::tokenize_ascii("alpha"), {"title"}, sort_fields, 10, 250, kvs, found).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 2, 1}) && found == 3);
+    }
+    {   // MultiFieldMatchRanking :3788-3835 (query_by artist,title)
+        const char* titles[] = {"Style", "Blank Space", "Balance Overkill", "Cardigan", "Invisible String", "The Last Great American Dynasty",
+                                "Mirrorball", "Peace", "Betty", "Mad Woman"};
+        std::vector<Rec> recs;
+        for(auto t: titles) recs.push_back({{"Taylor Swift", t}});
+        tsgpu::Index index(10);
+        build_plain(index, {"artist", "title"}, recs);
+        CHECK(index.search(tsgpu::tokenize_ascii("taylor swift style"), {"artist", "title"}, sort_fields, 5, 250, kvs, found).ok());
+        CHECK(found == 10 && kvs.size() == 10);
+        if(kvs.size() >= 3) CHECK(kvs[0].key == 0 && kvs[1].key == 9 && kvs[2].key == 8);
+    }
+    {   // MultiFieldMatchRankingOnArray :3837-3877 (two string[] fields)
+        tsgpu::Index index(2);
+        const std::vector<std::vector<std::vector<std::string>>> strong = {{{"golang"}, {"vue"}, {"react"}}, {{"golang"}, {"phoenix"}, {"react"}}};
+        const std::vector<std::vector<std::vector<std::string>>> skills = {{{"docker"}, {"goa"}, {"elixir"}}, {{"docker"}, {"vue"}, {"kubernetes"}}};
+        tsgpu::field_mirror_t a(true), b(true);
+        for(uint32_t i = 0; i < 2; i++) { a.index_string_array(i, strong[i]); b.index_string_array(i, skills[i]); }
+        CHECK(index.add_field("strong_skills", a).ok());
+        CHECK(index.add_field("skills", b).ok());
+        CHECK(index.add_sort_field("points", {{0, 0}, {1, 1}}).ok());
+        CHECK(index.search(tsgpu::tokenize_ascii("golang vue"), {"strong_skills", "skills"}, sort_fields, 1, 250, kvs, found).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 1}) && found == 2);
+    }
+    {   // MultiFieldMatchRankingOnFieldOrder :3879-3920 (query_by_weights {1, 6})
+        tsgpu::Index index(2);
+        build_plain(index, {"title", "artist"}, {{{"Toxic", "Britney Spears"}}, {{"Bad", "Michael Jackson"}}});
+        tsgpu::search_options o;
+        o.query_by_weights = {1, 6};
+        CHECK(index.search(tsgpu::tokenize_ascii("michael jackson toxic"), {"title", "artist"}, sort_fields, 5, 250, kvs, found, o).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 0}) && found == 2);
+    }
+    {   // MultiFieldRelevance2 :3276-3355
+        tsgpu::Index index(2);
+        build_plain(index, {"title", "artist"}, {{{"A Daikon Freestyle", "Ghosts on a Trampoline"}}, {{"Leaving on a Jetplane", "Coby Grant"}}});
+        for(auto w: std::vector<std::vector<uint32_t>>{{}, {1, 4}, {1, 1}}) {
+            tsgpu::search_options o;
+            o.query_by_weights = w;
+            CHECK(index.search(tsgpu::tokenize_ascii("on a jetplane"), {"title", "artist"}, sort_fields, 10, 250, kvs, found, o).ok());
+            CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 0}) && found == 2);
+        }
+        tsgpu::search_options o;
+        o.query_by_weights = {1, 4};
+        CHECK(index.search(tsgpu::tokenize_ascii("on a helicopter"), {"title", "artist"}, sort_fields, 10, 250, kvs, found, o).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 1}) && found == 2);
+    }
+    {   // MultiFieldRelevance3 :3403-3460 and 6 :3581-3636
+        tsgpu::search_options same;
+        same.query_by_weights = {1, 1};
+        tsgpu::Index i3(2);
+        build_plain(i3, {"title", "artist"}, {{{"Taylor Swift Karaoke: reputation", "Taylor Swift"}}, {{"Style", "Taylor Swift"}}});
+        CHECK(i3.search(tsgpu::tokenize_ascii("style taylor swift"), {"title", "artist"}, sort_fields, 10, 250, kvs, found, same).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 0}) && found == 2);
+        CHECK(i3.search(tsgpu::tokenize_ascii("swift"), {"title", "artist"}, sort_fields, 10, 250, kvs, found, same).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 1}) && found == 2);
+        tsgpu::Index i6(2);
+        build_plain(i6, {"title", "artist"}, {{{"Taylor Swift", "Taylor Swift"}}, {{"Taylor Swift Song", "Taylor Swift"}}});
+        for(bool exact: {true, false}) {
+            tsgpu::search_options o = same;
+            o.prioritize_exact_match = exact;
+            CHECK(i6.search(tsgpu::tokenize_ascii("taylor swift"), {"title", "artist"}, sort_fields, 10, 250, kvs, found, o).ok());
+            CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 0}) && found == 2);
+        }
+    }
+    {   // RepeatingTokenRanking, test/collection_sorting_test.cpp:1800-1855: literal text_match values, weight {3}
+        tsgpu::Index index(4);
+        tsgpu::field_mirror_t m;
+        const char* t[] = {"Mong Mong", "Mong Spencer", "Mong Mong Spencer", "Spencer Mong Mong"};
+        for(uint32_t i = 0; i < 4; i++) m.index_plain_string(i, tsgpu::tokenize_ascii(t[i]));
+        CHECK(index.add_field("title", m).ok());
+        CHECK(index.add_sort_field("points", {{0, 100}, {1, 200}, {2, 300}, {3, 400}}).ok());
+        tsgpu::search_options o;
+        o.query_by_weights = {3};
+        CHECK(index.search(tsgpu::tokenize_ascii("mong mong"), {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 3, 2, 1}));
+        if(kvs.size() == 4) {
+            CHECK(kvs[0].scores[0] == 1157451471583709209LL);
+            CHECK(kvs[1].scores[0] == 1157451471575320601LL && kvs[2].scores[0] == 1157451471575320601LL && kvs[3].scores[0] == 1157451471575320601LL);
+        }
+    }
+    {   // text_match literals of test/collection_vector_search_test.cpp:5462-5496 (and test/union_test.cpp:810)
+        tsgpu::Index index(4);
+        build_plain(index, {"name"}, {{{"Nike running shoes for men"}}, {{"Nike running sneakers"}}, {{"adidas shoes"}}, {{"puma"}}});
+        CHECK(index.search(tsgpu::tokenize_ascii("nike running shoes"), {"name"}, {{tsgpu::sort_by::text_match, "", true}}, 10, 250, kvs, found).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 1, 2}));
+        if(kvs.size() == 3) CHECK(kvs[0].scores[0] == 1736172819517016185LL && kvs[1].scores[0] == 1157451471441102969LL && kvs[2].scores[0] == 578730123365189753LL);
+    }
+}
+
 int main(int argc, char** argv) {
     if(tsgpu_device_count() == 0) { printf("no CUDA device: nothing to run (the library has no CPU path)\n"); return 99; }
     posting_list_intersection_basics();
@@ -180,6 +314,7 @@ int main(int argc, char** argv) {
     collection_scenarios(argc > 1 ? argv[1] : "tests/golden/documents.jsonl");
     vector_scenario();
     exact_prefix_and_setops();
+    relevance_scenarios();
     printf("%s (%d failed checks)\n", failures ? "FAILED" : "PASSED", failures);
     return failures;
 }

@@ -14,6 +14,8 @@
 //   hnsw_index_t + searchKnnCloserFirst   src/index.cpp:3384       Index::searchKnnCloserFirst(q, k, ef, filter_ids)
 //   Topster<KV>::add / sort               include/topster.h:321    host_topster_t (merges the <=K KVs of each device round)
 //   Index::search drop-tokens loop        src/index.cpp:3920-4017  Index::search(tokens, ...)  (control flow stays on host)
+//   Collection::search switches/weights   src/collection.cpp:4210   search_options, process_search_field_weights
+//   Index::tokenize_string_array          src/index.cpp:1357-1393  field_mirror_t::index_string_array
 //
 // Header-only; needs only libtsgpu.so. There is no CPU implementation behind these calls.
 #pragma once
@@ -89,7 +91,52 @@ public:
         if(!tokens.empty()) t2o[tokens.back()].push_back(0);
         for(auto& p: t2o) upsert(p.first, seq_id, p.second);
     }
+    // Index::tokenize_string_array (src/index.cpp:1357-1393): per element and token positions..., the last position
+    // repeated, the array index; the element's last token additionally gets 0. The field must be built with is_array.
+    void index_string_array(uint32_t seq_id, const std::vector<std::vector<std::string>>& elements) {
+        std::map<std::string, std::vector<uint32_t>> t2o;
+        for(size_t ai = 0; ai < elements.size(); ai++) {
+            const auto& tokens = elements[ai];
+            std::vector<std::string> seen;
+            for(size_t i = 0; i < tokens.size(); i++) {
+                t2o[tokens[i]].push_back((uint32_t) i + 1);
+                if(std::find(seen.begin(), seen.end(), tokens[i]) == seen.end()) seen.push_back(tokens[i]);
+            }
+            for(auto& t: seen) { auto& o = t2o[t]; o.push_back(o.back()); o.push_back((uint32_t) ai); }
+            if(!tokens.empty()) t2o[tokens.back()].push_back(0);
+        }
+        for(auto& p: t2o) upsert(p.first, seq_id, p.second);
+    }
 };
+
+// The scoring switches of Collection::search with the reference's defaults, exclusion tokens (`-word` in the query) and
+// query_by_weights.
+struct search_options {
+    bool prioritize_exact_match = true;
+    bool prioritize_token_position = false;
+    bool prioritize_num_matching_fields = true;
+    std::vector<std::string> exclude_tokens;
+    std::vector<uint32_t> query_by_weights;      // empty: 15, 14, ... by field order
+};
+
+// Collection::process_search_field_weights (src/collection.cpp:4210-4275): weights already in descending order and
+// <= FIELD_MAX_WEIGHT are used as they are; otherwise they are re-ranked into 15, 14, ... preserving ties.
+inline std::vector<uint8_t> process_search_field_weights(size_t n_fields, const std::vector<uint32_t>& given) {
+    std::vector<uint8_t> w(n_fields);
+    if(given.empty()) { for(size_t f = 0; f < n_fields; f++) w[f] = (uint8_t) (f < 15 ? 15 - f : 0); return w; }
+    bool desc = true, under = true;
+    for(size_t i = 0; i < n_fields && i < given.size(); i++) { if(i && given[i] > given[i - 1]) desc = false; if(given[i] > 15) under = false; }
+    if(desc && under) { for(size_t f = 0; f < n_fields; f++) w[f] = (uint8_t) (f < given.size() ? given[f] : 0); return w; }
+    std::vector<size_t> order(n_fields);
+    for(size_t i = 0; i < n_fields; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t c) { return given[a] > given[c]; });
+    uint32_t cur = 15;
+    for(size_t i = 0; i < n_fields; i++) {
+        if(i && given[order[i]] != given[order[i - 1]]) cur = cur ? cur - 1 : 0;
+        w[order[i]] = (uint8_t) cur;
+    }
+    return w;
+}
 
 struct sort_by {
     enum type_t { none = TSGPU_SORT_NONE, text_match = TSGPU_SORT_TEXT_MATCH, seq_id = TSGPU_SORT_SEQ_ID, numeric = TSGPU_SORT_NUMERIC,
@@ -217,7 +264,8 @@ public:
                                       const std::vector<uint8_t>& field_weights, const std::vector<sort_by>& sort_fields,
                                       const std::vector<uint32_t>& filter_ids, bool filter_by_provided,
                                       const std::vector<uint32_t>& excluded_result_ids, size_t topster_size,
-                                      bool prioritize_exact_match, host_topster_t& topster, size_t& num_found) {
+                                      bool prioritize_exact_match, host_topster_t& topster, size_t& num_found,
+                                      bool prioritize_token_position = false, bool prioritize_num_matching_fields = true) {
         const uint32_t F = (uint32_t) the_fields.size();
         std::vector<uint32_t> fids(F);
         for(uint32_t f = 0; f < F; f++) fids[f] = field_ids.at(the_fields[f]);
@@ -245,7 +293,10 @@ public:
             missing_first[i] = sort_fields[i].missing_first;
             if(sort_fields[i].type == sort_by::numeric) sort_col[i] = (int32_t) sort_cols.at(sort_fields[i].name);
         }
-        uint8_t q_flags = prioritize_exact_match ? TSGPU_FLAG_PRIORITIZE_EXACT_MATCH : 0, q_match_type = TSGPU_MATCH_MAX_SCORE;
+        uint8_t q_flags = (uint8_t) ((prioritize_exact_match ? TSGPU_FLAG_PRIORITIZE_EXACT_MATCH : 0) |
+                                     (prioritize_token_position ? TSGPU_FLAG_PRIORITIZE_TOKEN_POSITION : 0) |
+                                     (prioritize_num_matching_fields ? TSGPU_FLAG_PRIORITIZE_NUM_MATCHING_FIELDS : 0));
+        uint8_t q_match_type = TSGPU_MATCH_MAX_SCORE;
         uint8_t q_nqt = (uint8_t) n_query_tokens;
         uint64_t filter_off[2] = {0, filter_ids.size()};
         const uint32_t zero = 0;
@@ -270,9 +321,20 @@ public:
     // default right_to_left). Typo candidates come from the host's ART and would add combinations to each round.
     Option<bool> search(const std::vector<std::string>& tokens, const std::vector<std::string>& the_fields,
                         const std::vector<sort_by>& sort_fields, size_t drop_tokens_threshold, size_t topster_size,
-                        std::vector<KV>& raw_result_kvs, size_t& found) {
-        std::vector<uint8_t> weights;
-        for(size_t f = 0; f < the_fields.size(); f++) weights.push_back((uint8_t) (f < 15 ? 15 - f : 0));      // src/collection.cpp:4219-4225
+                        std::vector<KV>& raw_result_kvs, size_t& found, const search_options& opts = search_options()) {
+        const std::vector<uint8_t> weights = process_search_field_weights(the_fields.size(), opts.query_by_weights);
+        // excluded_result_ids: every doc holding an exclusion token in a searched field (the host resolves them from the
+        // tokens' posting lists before run_search)
+        std::vector<uint32_t> excluded;
+        for(auto& t: opts.exclude_tokens) for(auto& fn: the_fields) {
+            std::vector<uint32_t> ids, merged;
+            auto iop = intersect(fn, {t}, ids);
+            if(!iop.ok()) return iop;
+            if(ids.empty()) continue;
+            merged.resize(excluded.size() + ids.size());
+            merged.resize(std::set_union(excluded.begin(), excluded.end(), ids.begin(), ids.end(), merged.begin()) - merged.begin());
+            excluded.swap(merged);
+        }
         host_topster_t topster(topster_size);
         std::map<uint64_t, bool> all_result_ids;
         auto run_round = [&](const std::vector<std::string>& trunc, const std::vector<std::string>& dropped) -> Option<bool> {
@@ -286,7 +348,8 @@ public:
             all.insert(all.end(), dropped.begin(), dropped.end());
             host_topster_t round(topster_size);
             size_t nf = 0;
-            auto op = search_across_fields({all}, dropped.size(), {0}, the_fields, weights, sort_fields, {}, false, {}, topster_size, true, round, nf);
+            auto op = search_across_fields({all}, dropped.size(), {0}, the_fields, weights, sort_fields, {}, false, excluded, topster_size,
+                                           opts.prioritize_exact_match, round, nf, opts.prioritize_token_position, opts.prioritize_num_matching_fields);
             if(!op.ok()) return op;
             for(auto& kv: round.sort()) { topster.add(kv); all_result_ids[kv.key] = true; }
             return Option<bool>(true);
