@@ -1,0 +1,199 @@
+"""TEST INFRASTRUCTURE: the typo / prefix control flow that stays on the host in the reference, restated on top of
+refflow's backends so the reference's typo and prefix scenarios (test/collection_test.cpp) can be replayed:
+  Index::fuzzy_search_fields     src/index.cpp:4784-5109   cost combinations per token, candidate cache, early exits
+  Index::search_all_candidates   src/index.cpp:1794-1894   product of candidates, combination limit, qhash de-dup
+  Index::next_suggestion2        src/index.cpp:7204-7248   total_cost = sum(2*typo + prefix-found)
+  Index::get_bounded_typo_cost   src/index.cpp:6923-6951
+  drop-tokens loop               src/index.cpp:3920-4017
+Candidate generation is the reference's ART walk (src/art.cpp: art_fuzzy_search_i, SURVEY §8 f-1, not built); here a
+brute-force scan of the (tiny) test vocabulary stands in for it: optimal-string-alignment distance exactly equal to the
+cost, prefix rule of fuzzy_search_state, leaves ordered by frequency / max_score (ties: token order), the exact leaf
+first, at most max_candidates. Single searched field."""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import numpy as np
+
+import refflow
+from typesense_b200 import structs as S
+
+FREQUENCY, MAX_SCORE = 0, 1
+
+
+def osa_rows(term: str, key: str):
+    """rows of the incremental distance matrix: row i = costs after key[:i] against every prefix of term"""
+    prev2, prev = None, list(range(len(term) + 1))
+    rows = [prev]
+    for i, c in enumerate(key):
+        cur = [prev[0] + 1]
+        for col in range(1, len(term) + 1):
+            cost = 0 if c == term[col - 1] else 1
+            v = min(cur[col - 1] + 1, prev[col] + 1, prev[col - 1] + cost)
+            if i > 1 and col > 1 and c == term[col - 2] and key[i - 1] == term[col - 1]:      # src/art.cpp:1429 (depth > 1)
+                v = min(v, prev2[col - 2] + 1)
+            cur.append(v)
+        prev2, prev = prev, cur
+        rows.append(cur)
+    return rows
+
+
+def matches(term: str, key: str, cost: int, prefix: bool) -> bool:
+    rows = osa_rows(term, key)
+    q = len(term)
+    if prefix:
+        # fuzzy_search_state case b): once the key is at least as long as the query, a cost within bounds accepts
+        for klen in range(q, len(key) + 1):
+            if rows[klen][q] == cost:
+                return True
+    # (the "q=strawberries on key=strawberry" special case of src/art.cpp:1511-1516 needs min_cost <= max_cost - 1 and can
+    # never fire here: fuzzy_search_fields always searches with min_cost == max_cost)
+    return rows[len(key)][q] == cost
+
+
+class TypoSearcher:
+    def __init__(self, backend, coll: refflow.Collection, sort, num_typos: int = 2, token_order: int = FREQUENCY, prefix: bool = True,
+                 drop_tokens_threshold: int = 1, typo_tokens_threshold: int = 1, max_candidates: int = 4, min_len_1typo: int = 4,
+                 min_len_2typo: int = 7, topster: int = 250):
+        assert len(coll.fields) == 1
+        self.backend, self.coll, self.sort = backend, coll, sort
+        self.num_typos, self.token_order, self.prefix = num_typos, token_order, prefix
+        self.drop_thr, self.typo_thr, self.max_cand = drop_tokens_threshold, typo_tokens_threshold, max_candidates
+        self.min1, self.min2 = min_len_1typo, min_len_2typo
+        self.K = max(1, min(max(topster, 250), coll.n_docs))
+        fl = coll.flat
+        df = np.diff(fl.list_off.astype(np.int64))
+        self.freq = {t: int(df[l]) for t, l in coll.vocab.items()}
+        self.max_score = {t: int(max(coll.points[int(i)] for i in fl.ids[int(fl.list_off[l]):int(fl.list_off[l + 1])])) for t, l in coll.vocab.items()}
+
+    def bounded_cost(self, token: str) -> int:
+        if any(not ch.isalnum() for ch in token) or token.isdigit():
+            return 0
+        if len(token) < self.min1:
+            return 0
+        return min(self.num_typos, 1) if len(token) < self.min2 else min(self.num_typos, 2)
+
+    def candidates(self, token: str, cost: int, prefix_search: bool, unique_tokens: set) -> List[str]:
+        rank = self.freq if self.token_order == FREQUENCY else self.max_score
+        exact = token if (not prefix_search and token in self.coll.vocab) else None
+        if prefix_search and token in self.coll.vocab:
+            exact = token
+        found = [t for t in self.coll.vocab if matches(token, t, cost, prefix_search) and t not in unique_tokens and t != exact]
+        found.sort(key=lambda t: (-rank[t], t))
+        for t in found:
+            unique_tokens.add(t)
+        if exact is not None and cost == 0 and exact not in unique_tokens:
+            found.insert(0, exact)
+            unique_tokens.add(exact)
+        return found[:self.max_cand]
+
+    def search(self, q: str):
+        tokens = refflow.tokenize(q)
+        self.best: Dict[int, tuple] = {}
+        self.all_ids = set()
+        self.query_hashes = set()
+        is_prefix = [self.prefix and i == len(tokens) - 1 for i in range(len(tokens))]
+        self.fuzzy(list(zip(tokens, is_prefix)), [])
+        n = min(len(tokens), 20)
+        if len(self.all_ids) < self.drop_thr:
+            n_dropped, dirs_done, rtl = 0, 0, True
+            while len(self.all_ids) < self.drop_thr:
+                if n_dropped >= n - 1:
+                    rtl = not rtl
+                    n_dropped = 0
+                    dirs_done += 1
+                if n > 1 and dirs_done < 2:
+                    toks = list(zip(tokens, is_prefix))
+                    if rtl:
+                        tl = n - n_dropped - 1
+                        trunc, dropped = toks[:tl], toks[tl:n]
+                    else:
+                        st = n_dropped + 1
+                        trunc, dropped = toks[st:n], toks[:st]
+                    n_dropped += 1
+                    self.fuzzy(trunc, [t for t, _ in dropped])
+                else:
+                    break
+        order = sorted(self.best.items(), key=lambda kv_: (kv_[1], kv_[0]), reverse=True)
+        return [k for k, _ in order], len(self.all_ids)
+
+    # ---- Index::fuzzy_search_fields
+    def fuzzy(self, qtokens, dropped: List[str]):
+        if not qtokens:
+            return
+        token_to_costs = [list(range(0, self.bounded_cost(t) + 1)) for t, _ in qtokens]
+        cache: Dict[str, List[str]] = {}
+        n = 0
+        N = 1
+        for c in token_to_costs:
+            N *= len(c)
+        while n < N and n < 10:                                   # COMBINATION_MIN_LIMIT (not exhaustive)
+            costs, qn = [0] * len(qtokens), n
+            for i in range(len(qtokens) - 1, -1, -1):
+                qn, rem = divmod(qn, len(token_to_costs[i]))
+                costs[i] = token_to_costs[i][rem]
+            unique_tokens: set = set()
+            cands = []
+            restart = False
+            for ti, (token, pref) in enumerate(qtokens):
+                key = token + str(costs[ti])
+                if key in cache:
+                    leaf_tokens = cache[key]
+                else:
+                    leaf_tokens = []
+                    if costs[ti] <= self.num_typos:
+                        leaf_tokens = self.candidates(token, costs[ti], pref, unique_tokens)
+                        if leaf_tokens:
+                            cache[key] = leaf_tokens
+                if leaf_tokens:
+                    cands.append((token, costs[ti], pref, leaf_tokens))
+                else:
+                    if costs[ti] in token_to_costs[ti]:
+                        token_to_costs[ti].remove(costs[ti])
+                        if not token_to_costs[ti]:
+                            return
+                    n = -1
+                    N = 1
+                    for c in token_to_costs:
+                        N *= len(c)
+                    restart = True
+                    break
+            if not restart and len(cands) == len(qtokens):
+                self.search_all_candidates(cands, dropped)
+            if len(self.all_ids) >= self.typo_thr:
+                return
+            n += 1
+
+    # ---- Index::search_all_candidates + next_suggestion2
+    def search_all_candidates(self, cands, dropped: List[str]):
+        N = 1
+        for c in cands:
+            N *= len(c[3])
+        limit = self.max_cand if self.prefix else max(10, self.max_cand)       # one searched field
+        vocab = self.coll.vocab
+        combos = []
+        for n in range(min(N, limit)):
+            qn, total_cost, sugg = n, 0, []
+            for token, cost, pref, leaves in cands:
+                qn, rem = divmod(qn, len(leaves))
+                cand = leaves[rem]
+                is_prefix_searched = pref and len(cand) > len(token) + cost
+                total_cost += 2 * cost + (1 if is_prefix_searched else 0)
+                sugg.append(cand)
+            h = tuple(sugg)
+            if h in self.query_hashes:
+                continue
+            self.query_hashes.add(h)
+            rows = [[vocab[t]] for t in sugg] + [[vocab.get(t, S.NO_LIST)] for t in dropped]
+            combos.append(S.Combo(rows, len(sugg), total_cost=total_cost))
+        if not combos:
+            return
+        query = S.Query(combos, topk=self.K, sort=self.sort, num_query_tokens=len(cands), field_weight=[15],
+                        flags=S.FLAG_PRIORITIZE_EXACT_MATCH | S.FLAG_PRIORITIZE_NUM_MATCHING_FIELDS)
+        kv, cnt, found = self.backend(S.KwBatch([query], [0]), self.K)
+        for i in range(int(cnt[0])):
+            key = int(kv["key"][0, i])
+            tup = tuple(int(x) for x in kv["scores"][0, i])
+            self.all_ids.add(key)
+            if key not in self.best or tup >= self.best[key]:
+                self.best[key] = tup
