@@ -69,6 +69,15 @@ static void or_iterator_intersect_and_filter() {
     if(!kvs.empty()) CHECK(kvs[0].key == 99820);
 }
 
+// Collection::search(q, fields, "", facets, sort, {num_typos}, per_page, page, token_order, {prefix}, drop_tokens_threshold, ...,
+// typo_tokens_threshold): the switches each reference test passes
+static tsgpu::search_options opt(uint32_t num_typos, bool prefix, size_t typo_tokens_threshold = 1,
+                                 tsgpu::search_options::token_ordering order = tsgpu::search_options::FREQUENCY) {
+    tsgpu::search_options o;
+    o.num_typos = num_typos; o.prefix = prefix; o.typo_tokens_threshold = typo_tokens_threshold; o.token_order = order;
+    return o;
+}
+
 // TEST_F(CollectionTest, MultiTokenSearch / ExactSearchShouldBeStable) test/collection_test.cpp:117-236
 static void collection_scenarios(const std::string& jsonl) {
     std::vector<std::pair<std::string, long>> docs = {{"z", 10}};        // dummy record for id 0
@@ -92,33 +101,65 @@ static void collection_scenarios(const std::string& jsonl) {
     std::vector<tsgpu::sort_by> sort_fields = {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::numeric, "points", true}};
     std::vector<tsgpu::KV> kvs;
     size_t found = 0;
-    CHECK(index.search(tsgpu::tokenize_ascii("rocket launch"), {"title"}, sort_fields, 10, 250, kvs, found).ok());
+    CHECK(index.search(tsgpu::tokenize_ascii("rocket launch"), {"title"}, sort_fields, 10, 250, kvs, found, opt(0, false)).ok());
     CHECK((ids_of(kvs) == std::vector<std::string>{"8", "1", "17", "16", "13"}));
     CHECK(found == 5);
     std::vector<tsgpu::sort_by> sort_fields_asc = {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::numeric, "points", false}};
-    CHECK(index.search(tsgpu::tokenize_ascii("rocket launch"), {"title"}, sort_fields_asc, 10, 250, kvs, found).ok());
+    CHECK(index.search(tsgpu::tokenize_ascii("rocket launch"), {"title"}, sort_fields_asc, 10, 250, kvs, found, opt(0, false)).ok());
     CHECK((ids_of(kvs) == std::vector<std::string>{"8", "17", "1", "16", "13"}));
-    CHECK(index.search(tsgpu::tokenize_ascii("the"), {"title"}, sort_fields, 1, 250, kvs, found).ok());
+    CHECK(index.search(tsgpu::tokenize_ascii("the"), {"title"}, sort_fields, 1, 250, kvs, found, opt(0, false)).ok());
     CHECK((ids_of(kvs) == std::vector<std::string>{"1", "6", "foo", "13", "10", "8", "16"}));
     CHECK(found == 7);
-    CHECK(index.search(tsgpu::tokenize_ascii("zxsadqewsad"), {"title"}, sort_fields, 1, 250, kvs, found).ok());
+    CHECK(index.search(tsgpu::tokenize_ascii("zxsadqewsad"), {"title"}, sort_fields, 1, 250, kvs, found, opt(0, false)).ok());
     CHECK(kvs.empty() && found == 0);
     // PartialMultiTokenSearch :358-372, SkipUnindexedTokensDuringMultiTokenSearch :269-356, SearchWithExcludedTokens :238-267
-    CHECK(index.search(tsgpu::tokenize_ascii("rocket research"), {"title"}, sort_fields, 10, 250, kvs, found).ok());
+    CHECK(index.search(tsgpu::tokenize_ascii("rocket research"), {"title"}, sort_fields, 10, 250, kvs, found, opt(0, false)).ok());
     CHECK((ids_of(kvs) == std::vector<std::string>{"19", "1", "10", "8", "16", "17"}));
-    CHECK(index.search(tsgpu::tokenize_ascii("DoesNotExist from"), {"title"}, sort_fields, 1, 250, kvs, found).ok());
+    CHECK(index.search(tsgpu::tokenize_ascii("DoesNotExist from"), {"title"}, sort_fields, 1, 250, kvs, found, opt(0, true)).ok());
     CHECK((ids_of(kvs) == std::vector<std::string>{"2", "17"}));
-    CHECK(index.search(tsgpu::tokenize_ascii("the a"), {"title"}, sort_fields, 10, 250, kvs, found).ok());
+    CHECK(index.search(tsgpu::tokenize_ascii("the a"), {"title"}, sort_fields, 10, 250, kvs, found, opt(0, false, 10)).ok());
     CHECK(kvs.size() == 9);
-    CHECK(index.search(tsgpu::tokenize_ascii("the a"), {"title"}, sort_fields, 0, 250, kvs, found).ok());
+    CHECK(index.search(tsgpu::tokenize_ascii("the a"), {"title"}, sort_fields, 0, 250, kvs, found, opt(0, false)).ok());
     CHECK((ids_of(kvs) == std::vector<std::string>{"8", "16", "10"}));
-    CHECK(index.search(tsgpu::tokenize_ascii("the a insurance"), {"title"}, sort_fields, 0, 250, kvs, found).ok());
+    CHECK(index.search(tsgpu::tokenize_ascii("the a insurance"), {"title"}, sort_fields, 0, 250, kvs, found, opt(0, false)).ok());
     CHECK(kvs.empty());
     {
-        tsgpu::search_options o;
+        tsgpu::search_options o = opt(0, false, 10);
         o.exclude_tokens = {"propellants", "are"};
         CHECK(index.search(tsgpu::tokenize_ascii("how"), {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
         CHECK((ids_of(kvs) == std::vector<std::string>{"9", "17"}) && found == 2);
+    }
+    // QueryWithTypo :374, TypoTokenRankedByScoreAndFrequency :413, PrefixSearching :605, TypoTokensThreshold :686
+    {
+        using O = tsgpu::search_options;
+        struct Case { const char* q; tsgpu::search_options o; size_t drop; std::vector<std::string> expect; size_t per_page; long found; };
+        const std::vector<Case> cases = {
+            {"kind biologcal", opt(2, false, 10), 10, {"19", "3", "20"}, 3, -1},
+            {"lauxnch rcket", opt(1, false, 10), 10, {"8", "1", "17"}, 3, -1},
+            {"loox", opt(1, false, 1, O::MAX_SCORE), 1, {"22", "3"}, 2, 5},
+            {"loox", opt(1, false, 1, O::FREQUENCY), 1, {"22", "3", "12", "23", "24"}, 10, 5},
+            {"loox", opt(1, false, 1, O::MAX_SCORE), 1, {"22", "3", "12", "23", "24"}, 10, 5},
+            {"ex", opt(0, true, 1, O::FREQUENCY), 1, {"6", "12"}, 10, 2},
+            {"ex", opt(0, true, 1, O::MAX_SCORE), 1, {"6", "12"}, 10, 2},
+            {"what ex", opt(0, true, 10, O::MAX_SCORE), 10, {"6", "12", "19", "22", "13", "8", "15", "24", "21"}, 10, 9},
+            {"t", opt(0, true, 10, O::MAX_SCORE), 10, {"19", "22"}, 2, -1},
+            {"t", opt(0, true, 10, O::FREQUENCY), 10, {"1", "2"}, 2, -1},
+            {"math fx", opt(0, true), 0, {}, 1, 0},
+            {"x", opt(2, true), 1, {}, 2, 0},
+            {"late propx", opt(2, true), 1, {"16"}, 1, -1},
+        };
+        for(auto& c: cases) {
+            CHECK(index.search(tsgpu::tokenize_ascii(c.q), {"title"}, sort_fields, c.drop, 250, kvs, found, c.o).ok());
+            auto ids = ids_of(kvs);
+            if(ids.size() > c.per_page) ids.resize(c.per_page);
+            if(!(ids == c.expect)) { printf("typo case '%s':", c.q); for(auto& i: ids) printf(" %s", i.c_str()); printf("\n"); }
+            CHECK(ids == c.expect);
+            if(c.found >= 0) CHECK((long) found == c.found);
+        }
+        CHECK(index.search(tsgpu::tokenize_ascii("redundant"), {"title"}, sort_fields, 10, 250, kvs, found, opt(2, true, 0)).ok());
+        CHECK(kvs.size() == 1 && found == 1);
+        CHECK(index.search(tsgpu::tokenize_ascii("redundant"), {"title"}, sort_fields, 10, 250, kvs, found, opt(2, true, 10)).ok());
+        CHECK(kvs.size() == 2 && found == 2);
     }
     // phrase: "rocket launch" as a phrase only in doc 8 ("... of a rocket launch these days")
     std::vector<uint32_t> both, phrase;
@@ -214,9 +255,9 @@ static void relevance_scenarios() {
     {   // ExactMatch, test/collection_test.cpp:3638-3688
         tsgpu::Index index(3);
         build_plain(index, {"title"}, {{{"Alpha"}}, {{"Alpha Beta"}}, {{"Alpha Beta Gamma"}}});
-        CHECK(index.search(tsgpu::tokenize_ascii("alpha beta"), {"title"}, sort_fields, 10, 250, kvs, found).ok());
+        CHECK(index.search(tsgpu::tokenize_ascii("alpha beta"), {"title"}, sort_fields, 10, 250, kvs, found, opt(2, true)).ok());
         CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 2, 0}) && found == 3);
-        CHECK(index.search(tsgpu::tokenize_ascii("alpha"), {"title"}, sort_fields, 10, 250, kvs, found).ok());
+        CHECK(index.search(tsgpu::tokenize_ascii("alpha"), {"title"}, sort_fields, 10, 250, kvs, found, opt(2, true)).ok());
         CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 2, 1}) && found == 3);
     }
     {   // MultiFieldMatchRanking :3788-3835 (query_by artist,title)
@@ -226,7 +267,7 @@ static void relevance_scenarios() {
         for(auto t: titles) recs.push_back({{"Taylor Swift", t}});
         tsgpu::Index index(10);
         build_plain(index, {"artist", "title"}, recs);
-        CHECK(index.search(tsgpu::tokenize_ascii("taylor swift style"), {"artist", "title"}, sort_fields, 5, 250, kvs, found).ok());
+        CHECK(index.search(tsgpu::tokenize_ascii("taylor swift style"), {"artist", "title"}, sort_fields, 5, 250, kvs, found, opt(0, true)).ok());
         CHECK(found == 10 && kvs.size() == 10);
         if(kvs.size() >= 3) CHECK(kvs[0].key == 0 && kvs[1].key == 9 && kvs[2].key == 8);
     }
@@ -239,13 +280,13 @@ static void relevance_scenarios() {
         CHECK(index.add_field("strong_skills", a).ok());
         CHECK(index.add_field("skills", b).ok());
         CHECK(index.add_sort_field("points", {{0, 0}, {1, 1}}).ok());
-        CHECK(index.search(tsgpu::tokenize_ascii("golang vue"), {"strong_skills", "skills"}, sort_fields, 1, 250, kvs, found).ok());
+        CHECK(index.search(tsgpu::tokenize_ascii("golang vue"), {"strong_skills", "skills"}, sort_fields, 1, 250, kvs, found, opt(0, true)).ok());
         CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 1}) && found == 2);
     }
     {   // MultiFieldMatchRankingOnFieldOrder :3879-3920 (query_by_weights {1, 6})
         tsgpu::Index index(2);
         build_plain(index, {"title", "artist"}, {{{"Toxic", "Britney Spears"}}, {{"Bad", "Michael Jackson"}}});
-        tsgpu::search_options o;
+        tsgpu::search_options o = opt(0, true);
         o.query_by_weights = {1, 6};
         CHECK(index.search(tsgpu::tokenize_ascii("michael jackson toxic"), {"title", "artist"}, sort_fields, 5, 250, kvs, found, o).ok());
         CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 0}) && found == 2);
@@ -254,18 +295,18 @@ static void relevance_scenarios() {
         tsgpu::Index index(2);
         build_plain(index, {"title", "artist"}, {{{"A Daikon Freestyle", "Ghosts on a Trampoline"}}, {{"Leaving on a Jetplane", "Coby Grant"}}});
         for(auto w: std::vector<std::vector<uint32_t>>{{}, {1, 4}, {1, 1}}) {
-            tsgpu::search_options o;
+            tsgpu::search_options o = opt(0, true, 40);
             o.query_by_weights = w;
             CHECK(index.search(tsgpu::tokenize_ascii("on a jetplane"), {"title", "artist"}, sort_fields, 10, 250, kvs, found, o).ok());
             CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 0}) && found == 2);
         }
-        tsgpu::search_options o;
+        tsgpu::search_options o = opt(0, true, 40);
         o.query_by_weights = {1, 4};
         CHECK(index.search(tsgpu::tokenize_ascii("on a helicopter"), {"title", "artist"}, sort_fields, 10, 250, kvs, found, o).ok());
         CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 1}) && found == 2);
     }
     {   // MultiFieldRelevance3 :3403-3460 and 6 :3581-3636
-        tsgpu::search_options same;
+        tsgpu::search_options same = opt(0, true, 40);
         same.query_by_weights = {1, 1};
         tsgpu::Index i3(2);
         build_plain(i3, {"title", "artist"}, {{{"Taylor Swift Karaoke: reputation", "Taylor Swift"}}, {{"Style", "Taylor Swift"}}});
@@ -277,6 +318,7 @@ static void relevance_scenarios() {
         build_plain(i6, {"title", "artist"}, {{{"Taylor Swift", "Taylor Swift"}}, {{"Taylor Swift Song", "Taylor Swift"}}});
         for(bool exact: {true, false}) {
             tsgpu::search_options o = same;
+            o.num_typos = 2;
             o.prioritize_exact_match = exact;
             CHECK(i6.search(tsgpu::tokenize_ascii("taylor swift"), {"title", "artist"}, sort_fields, 10, 250, kvs, found, o).ok());
             CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 0}) && found == 2);
@@ -289,7 +331,7 @@ static void relevance_scenarios() {
         for(uint32_t i = 0; i < 4; i++) m.index_plain_string(i, tsgpu::tokenize_ascii(t[i]));
         CHECK(index.add_field("title", m).ok());
         CHECK(index.add_sort_field("points", {{0, 100}, {1, 200}, {2, 300}, {3, 400}}).ok());
-        tsgpu::search_options o;
+        tsgpu::search_options o = opt(2, true, 20);
         o.query_by_weights = {3};
         CHECK(index.search(tsgpu::tokenize_ascii("mong mong"), {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
         CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 3, 2, 1}));
@@ -301,7 +343,7 @@ static void relevance_scenarios() {
     {   // text_match literals of test/collection_vector_search_test.cpp:5462-5496 (and test/union_test.cpp:810)
         tsgpu::Index index(4);
         build_plain(index, {"name"}, {{{"Nike running shoes for men"}}, {{"Nike running sneakers"}}, {{"adidas shoes"}}, {{"puma"}}});
-        CHECK(index.search(tsgpu::tokenize_ascii("nike running shoes"), {"name"}, {{tsgpu::sort_by::text_match, "", true}}, 10, 250, kvs, found).ok());
+        CHECK(index.search(tsgpu::tokenize_ascii("nike running shoes"), {"name"}, {{tsgpu::sort_by::text_match, "", true}}, 10, 250, kvs, found, opt(0, false)).ok());
         CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 1, 2}));
         if(kvs.size() == 3) CHECK(kvs[0].scores[0] == 1736172819517016185LL && kvs[1].scores[0] == 1157451471441102969LL && kvs[2].scores[0] == 578730123365189753LL);
     }

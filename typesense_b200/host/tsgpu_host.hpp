@@ -14,6 +14,9 @@
 //   hnsw_index_t + searchKnnCloserFirst   src/index.cpp:3384       Index::searchKnnCloserFirst(q, k, ef, filter_ids)
 //   Topster<KV>::add / sort               include/topster.h:321    host_topster_t (merges the <=K KVs of each device round)
 //   Index::search drop-tokens loop        src/index.cpp:3920-4017  Index::search(tokens, ...)  (control flow stays on host)
+//   Index::fuzzy_search_fields            src/index.cpp:4784-5109  Index::fuzzy_search_fields (cost combinations, candidate cache)
+//   Index::search_all_candidates          src/index.cpp:1794-1894  Index::search_all_candidates (+ next_suggestion2 costs)
+//   art_fuzzy_search_i                    src/art.cpp:1825         Index::fuzzy_candidates — vocabulary scan standing in for the ART (f-1)
 //   Collection::search switches/weights   src/collection.cpp:4210   search_options, process_search_field_weights
 //   Index::tokenize_string_array          src/index.cpp:1357-1393  field_mirror_t::index_string_array
 //
@@ -22,6 +25,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <map>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -117,7 +121,39 @@ struct search_options {
     bool prioritize_num_matching_fields = true;
     std::vector<std::string> exclude_tokens;
     std::vector<uint32_t> query_by_weights;      // empty: 15, 14, ... by field order
+    // typo / prefix expansion (Collection::search defaults)
+    uint32_t num_typos = 2;
+    bool prefix = true;                          // prefix search on the query's last token
+    enum token_ordering { FREQUENCY, MAX_SCORE } token_order = FREQUENCY;
+    size_t typo_tokens_threshold = 1;            // Index::TYPO_TOKENS_THRESHOLD
+    size_t max_candidates = 4;
+    size_t min_len_1typo = 4, min_len_2typo = 7;
 };
+
+// Incremental optimal-string-alignment rows as src/art.cpp:1412-1433 computes them while it walks a key: rows[i][col] =
+// cost of key[0..i) against query[0..col). (The transposition case needs two characters before it: depth > 1.)
+inline std::vector<std::vector<int>> osa_rows(const std::string& term, const std::string& key) {
+    std::vector<std::vector<int>> rows(key.size() + 1, std::vector<int>(term.size() + 1));
+    for(size_t c = 0; c <= term.size(); c++) rows[0][c] = (int) c;
+    for(size_t i = 0; i < key.size(); i++) {
+        rows[i + 1][0] = rows[i][0] + 1;
+        for(size_t col = 1; col <= term.size(); col++) {
+            const int cost = key[i] == term[col - 1] ? 0 : 1;
+            int v = std::min(std::min(rows[i + 1][col - 1] + 1, rows[i][col] + 1), rows[i][col - 1] + cost);
+            if(i > 1 && col > 1 && key[i] == term[col - 2] && key[i - 1] == term[col - 1]) v = std::min(v, rows[i - 1][col - 2] + 1);
+            rows[i + 1][col] = v;
+        }
+    }
+    return rows;
+}
+// Does `key` match `term` at exactly `cost` edits (fuzzy_search_fields searches with min_cost == max_cost)? With
+// `prefix`, a key at least as long as the query matches as soon as one of its prefixes does (fuzzy_search_state, case b).
+inline bool fuzzy_key_matches(const std::string& term, const std::string& key, int cost, bool prefix) {
+    const auto rows = osa_rows(term, key);
+    const size_t q = term.size();
+    if(prefix) for(size_t klen = q; klen <= key.size(); klen++) if(rows[klen][q] == cost) return true;
+    return rows[key.size()][q] == cost;
+}
 
 // Collection::process_search_field_weights (src/collection.cpp:4210-4275): weights already in descending order and
 // <= FIELD_MAX_WEIGHT are used as they are; otherwise they are re-ranked into 15, 14, ... preserving ties.
@@ -151,6 +187,12 @@ class Index {
     uint32_t n_docs;
     std::vector<std::unordered_map<std::string, uint32_t>> token_ids;      // per field: token -> posting list id (art_search stand-in)
     std::unordered_map<std::string, uint32_t> field_ids, sort_cols;
+    // what the ART leaves carry for candidate ordering: per field token strings by list id, their document frequency and
+    // ids (for max_score over the default sorting field)
+    struct vocab_t { std::vector<std::string> tokens; std::vector<uint64_t> list_off; std::vector<uint32_t> ids; };
+    std::vector<vocab_t> vocabs;
+    std::unordered_map<std::string, std::vector<int64_t>> sort_values;
+    std::string default_sorting_field;
     std::string err;
 public:
     Index(uint32_t n_docs, int device = 0): n_docs(n_docs) {
@@ -181,6 +223,11 @@ public:
         if(tsgpu_index_load_field(h, &tf, &fid) != TSGPU_OK) return Option<uint32_t>(500, tsgpu_last_error());
         field_ids[name] = fid;
         if(token_ids.size() <= fid) token_ids.resize(fid + 1);
+        if(vocabs.size() <= fid) vocabs.resize(fid + 1);
+        vocabs[fid].tokens.resize(tid.size());
+        for(auto& p: tid) vocabs[fid].tokens[p.second] = p.first;
+        vocabs[fid].list_off = list_off;
+        vocabs[fid].ids = ids;
         token_ids[fid] = std::move(tid);
         return Option<uint32_t>(fid);
     }
@@ -191,6 +238,8 @@ public:
         uint32_t col = 0;
         if(tsgpu_index_load_sort_column(h, dense.data(), &col) != TSGPU_OK) return Option<uint32_t>(500, tsgpu_last_error());
         sort_cols[name] = col;
+        sort_values[name] = dense;
+        if(default_sorting_field.empty()) default_sorting_field = name;      // the schema's default_sorting_field
         return Option<uint32_t>(col);
     }
     Option<bool> add_vector_field(const tsgpu_hnsw& g) {
@@ -317,68 +366,199 @@ public:
         return Option<bool>(true);
     }
 
-    // Index::search for already-tokenised text: exact tokens (cost 0) + the drop-tokens loop (src/index.cpp:3920-4017,
-    // default right_to_left). Typo candidates come from the host's ART and would add combinations to each round.
+    // ---- typo / prefix expansion -------------------------------------------------------------------------------
+    // Index::get_bounded_typo_cost (src/index.cpp:6923-6951)
+    static int get_bounded_typo_cost(size_t max_cost, const std::string& token, size_t min_len_1typo, size_t min_len_2typo) {
+        bool all_digit = !token.empty();
+        for(unsigned char c: token) { if(!isalnum(c)) return 0; if(!isdigit(c)) all_digit = false; }
+        if(all_digit) return 0;
+        if(token.size() < min_len_1typo) return 0;
+        if(token.size() < min_len_2typo) return (int) std::min<size_t>(max_cost, 1);
+        return (int) std::min<size_t>(max_cost, 2);
+    }
+    // Stand-in for art_fuzzy_search_i (src/art.cpp:1825-1894; the ART walk itself is SURVEY §8 f-1): scans the field's
+    // vocabulary for tokens at exactly `cost` edits (or, for a prefix search, with such a prefix), orders them like the
+    // leaves are ordered (document frequency or max_score of the default sorting field, descending), puts the exact
+    // token first at cost 0, skips tokens another field already produced, keeps max_candidates.
+    std::vector<std::string> fuzzy_candidates(uint32_t fid, const std::string& token, int cost, bool prefix_search,
+                                              std::set<std::string>& unique_tokens, const search_options& o) const {
+        const vocab_t& v = vocabs[fid];
+        const std::vector<int64_t>* scores = nullptr;
+        auto sv = sort_values.find(default_sorting_field);
+        if(sv != sort_values.end()) scores = &sv->second;
+        struct cand { std::string tok; int64_t rank; };
+        std::vector<cand> found;
+        const bool has_exact = token_ids[fid].count(token) != 0;
+        for(uint32_t l = 0; l < v.tokens.size(); l++) {
+            const std::string& t = v.tokens[l];
+            if((has_exact && t == token) || unique_tokens.count(t) || v.list_off[l + 1] == v.list_off[l]) continue;
+            if(!fuzzy_key_matches(token, t, cost, prefix_search)) continue;
+            int64_t rank = (int64_t) (v.list_off[l + 1] - v.list_off[l]);
+            if(o.token_order == search_options::MAX_SCORE) {
+                rank = INT64_MIN;
+                if(scores) for(uint64_t i = v.list_off[l]; i < v.list_off[l + 1]; i++) rank = std::max(rank, (*scores)[v.ids[i]]);
+            }
+            found.push_back({t, rank});
+        }
+        std::sort(found.begin(), found.end(), [](const cand& a, const cand& c2) { return a.rank != c2.rank ? a.rank > c2.rank : a.tok < c2.tok; });
+        std::vector<std::string> out;
+        for(auto& c: found) { out.push_back(c.tok); unique_tokens.insert(c.tok); }
+        if(has_exact && cost == 0 && !unique_tokens.count(token)) { out.insert(out.begin(), token); unique_tokens.insert(token); }
+        if(out.size() > o.max_candidates) out.resize(o.max_candidates);
+        return out;
+    }
+
+    struct query_token { std::string value; bool is_prefix_searched; };
+    struct tok_candidates { query_token token; int cost; std::vector<std::string> candidates; };
+    struct search_state {              // what Index::search threads through its rounds
+        host_topster_t topster;
+        std::set<uint32_t> all_result_ids;
+        std::set<std::vector<std::string>> query_hashes;
+        std::vector<uint32_t> excluded;
+        std::vector<uint8_t> weights;
+        explicit search_state(size_t cap): topster(cap) {}
+    };
+
+    // Index::search_all_candidates (src/index.cpp:1794-1894) + next_suggestion2 (:7204-7248): the product of the tokens'
+    // candidates, first token fastest, up to the combination limit; a suggestion seen before is skipped; all of a call's
+    // suggestions go to the device as the combinations of one query.
+    Option<bool> search_all_candidates(const std::vector<tok_candidates>& cands, const std::vector<std::string>& dropped,
+                                       const std::vector<std::string>& the_fields, const std::vector<sort_by>& sort_fields,
+                                       size_t topster_size, const search_options& o, search_state& st) {
+        long long N = 1;
+        for(auto& c: cands) N *= (long long) c.candidates.size();
+        const long long limit = (the_fields.size() == 1 && o.prefix) ? (long long) o.max_candidates : (long long) std::max<size_t>(10, o.max_candidates);
+        std::vector<std::vector<std::string>> suggestions;
+        std::vector<uint32_t> costs;
+        for(long long n = 0; n < N && n < limit; n++) {
+            std::vector<std::string> sugg;
+            uint32_t total_cost = 0;
+            long long quot = n;
+            for(auto& c: cands) {
+                const std::string& cand = c.candidates[(size_t) (quot % (long long) c.candidates.size())];
+                quot /= (long long) c.candidates.size();
+                const bool is_prefix_searched = c.token.is_prefix_searched && cand.size() > c.token.value.size() + (size_t) c.cost;
+                total_cost += 2 * (uint32_t) c.cost + (is_prefix_searched ? 1u : 0u);
+                sugg.push_back(cand);
+            }
+            if(!st.query_hashes.insert(sugg).second) continue;
+            sugg.insert(sugg.end(), dropped.begin(), dropped.end());
+            suggestions.push_back(std::move(sugg));
+            costs.push_back(total_cost);
+        }
+        if(suggestions.empty()) return Option<bool>(true);
+        host_topster_t round(topster_size);
+        size_t nf = 0;
+        auto op = search_across_fields(suggestions, dropped.size(), costs, the_fields, st.weights, sort_fields, {}, false, st.excluded, topster_size,
+                                       o.prioritize_exact_match, round, nf, o.prioritize_token_position, o.prioritize_num_matching_fields);
+        if(!op.ok()) return op;
+        for(auto& kv: round.sort()) { st.topster.add(kv); st.all_result_ids.insert((uint32_t) kv.key); }
+        return Option<bool>(true);
+    }
+
+    // Index::fuzzy_search_fields (src/index.cpp:4784-5109): cost combinations per token ([0,0,0], [0,0,1], ...), a cost
+    // with no candidate is struck off and the enumeration restarts, results >= typo_tokens_threshold end it.
+    Option<bool> fuzzy_search_fields(const std::vector<query_token>& query_tokens, const std::vector<std::string>& dropped,
+                                     const std::vector<std::string>& the_fields, const std::vector<sort_by>& sort_fields,
+                                     size_t topster_size, const search_options& o, search_state& st) {
+        if(query_tokens.empty()) return Option<bool>(true);
+        std::vector<std::vector<int>> token_to_costs;
+        for(auto& t: query_tokens) {
+            std::vector<int> all;
+            for(int c = 0; c <= get_bounded_typo_cost(2, t.value, o.min_len_1typo, o.min_len_2typo); c++) all.push_back(c);
+            token_to_costs.push_back(all);
+        }
+        std::map<std::string, std::vector<std::string>> token_cost_cache;
+        auto product = [&]() { long long p = 1; for(auto& c: token_to_costs) p *= (long long) c.size(); return p; };
+        long long n = 0, N = token_to_costs.size() > 30 ? 1 : product();
+        while(n < N && n < 10) {                                  // COMBINATION_MIN_LIMIT (exhaustive_search off)
+            std::vector<int> costs(query_tokens.size());
+            long long quot = n;
+            for(size_t i = query_tokens.size(); i-- > 0;) { costs[i] = token_to_costs[i][(size_t) (quot % (long long) token_to_costs[i].size())]; quot /= (long long) token_to_costs[i].size(); }
+            std::set<std::string> unique_tokens;
+            std::vector<tok_candidates> cands;
+            bool restart = false;
+            for(size_t ti = 0; ti < query_tokens.size(); ti++) {
+                const std::string key = query_tokens[ti].value + std::to_string(costs[ti]);
+                std::vector<std::string> leaf_tokens;
+                auto hit = token_cost_cache.find(key);
+                if(hit != token_cost_cache.end()) leaf_tokens = hit->second;
+                else {
+                    for(auto& fn: the_fields) {
+                        if((uint32_t) costs[ti] > o.num_typos) continue;
+                        auto fl = fuzzy_candidates(field_ids.at(fn), query_tokens[ti].value, costs[ti], o.prefix && query_tokens[ti].is_prefix_searched, unique_tokens, o);
+                        if(fl.empty()) continue;
+                        leaf_tokens.insert(leaf_tokens.end(), fl.begin(), fl.end());
+                        token_cost_cache[key] = leaf_tokens;
+                        if(leaf_tokens.size() >= o.max_candidates) break;
+                    }
+                }
+                if(!leaf_tokens.empty()) cands.push_back({query_tokens[ti], costs[ti], leaf_tokens});
+                else {
+                    auto& tc = token_to_costs[ti];
+                    auto it = std::find(tc.begin(), tc.end(), costs[ti]);
+                    if(it != tc.end()) { tc.erase(it); if(tc.empty()) return Option<bool>(true); }
+                    n = -1; N = product();
+                    restart = true;
+                    break;
+                }
+            }
+            if(!restart && cands.size() == query_tokens.size()) {
+                auto op = search_all_candidates(cands, dropped, the_fields, sort_fields, topster_size, o, st);
+                if(!op.ok()) return op;
+            }
+            if(st.all_result_ids.size() >= o.typo_tokens_threshold) return Option<bool>(true);
+            n++;
+        }
+        return Option<bool>(true);
+    }
+
+    // Index::search for already-tokenised text: fuzzy_search_fields on the whole query, then the drop-tokens loop
+    // (src/index.cpp:3920-4017, right_to_left first) while fewer than drop_tokens_threshold results exist.
     Option<bool> search(const std::vector<std::string>& tokens, const std::vector<std::string>& the_fields,
                         const std::vector<sort_by>& sort_fields, size_t drop_tokens_threshold, size_t topster_size,
                         std::vector<KV>& raw_result_kvs, size_t& found, const search_options& opts = search_options()) {
-        const std::vector<uint8_t> weights = process_search_field_weights(the_fields.size(), opts.query_by_weights);
+        search_state st(topster_size);
+        st.weights = process_search_field_weights(the_fields.size(), opts.query_by_weights);
         // excluded_result_ids: every doc holding an exclusion token in a searched field (the host resolves them from the
         // tokens' posting lists before run_search)
-        std::vector<uint32_t> excluded;
         for(auto& t: opts.exclude_tokens) for(auto& fn: the_fields) {
             std::vector<uint32_t> ids, merged;
             auto iop = intersect(fn, {t}, ids);
             if(!iop.ok()) return iop;
             if(ids.empty()) continue;
-            merged.resize(excluded.size() + ids.size());
-            merged.resize(std::set_union(excluded.begin(), excluded.end(), ids.begin(), ids.end(), merged.begin()) - merged.begin());
-            excluded.swap(merged);
+            merged.resize(st.excluded.size() + ids.size());
+            merged.resize(std::set_union(st.excluded.begin(), st.excluded.end(), ids.begin(), ids.end(), merged.begin()) - merged.begin());
+            st.excluded.swap(merged);
         }
-        host_topster_t topster(topster_size);
-        std::map<uint64_t, bool> all_result_ids;
-        auto run_round = [&](const std::vector<std::string>& trunc, const std::vector<std::string>& dropped) -> Option<bool> {
-            for(auto& t: trunc) {
-                bool any = false;
-                for(auto& fn: the_fields) any = any || token_id(field_ids.at(fn), t) != TSGPU_NO_LIST;
-                if(!any) return Option<bool>(true);          // no candidate at cost 0 -> fuzzy_search_fields returns
-            }
-            if(trunc.empty()) return Option<bool>(true);
-            std::vector<std::string> all = trunc;
-            all.insert(all.end(), dropped.begin(), dropped.end());
-            host_topster_t round(topster_size);
-            size_t nf = 0;
-            auto op = search_across_fields({all}, dropped.size(), {0}, the_fields, weights, sort_fields, {}, false, excluded, topster_size,
-                                           opts.prioritize_exact_match, round, nf, opts.prioritize_token_position, opts.prioritize_num_matching_fields);
-            if(!op.ok()) return op;
-            for(auto& kv: round.sort()) { topster.add(kv); all_result_ids[kv.key] = true; }
-            return Option<bool>(true);
-        };
-        auto op = run_round(tokens, {});
+        std::vector<query_token> qt;
+        for(size_t i = 0; i < tokens.size(); i++) qt.push_back({tokens[i], opts.prefix && i + 1 == tokens.size()});
+        auto op = fuzzy_search_fields(qt, {}, the_fields, sort_fields, topster_size, opts, st);
         if(!op.ok()) return op;
         const size_t n = std::min<size_t>(tokens.size(), 20);
-        if(all_result_ids.size() < drop_tokens_threshold) {
+        if(st.all_result_ids.size() < drop_tokens_threshold) {
             size_t num_tokens_dropped = 0, total_dirs_done = 0;
             bool right_to_left = true;
-            while(all_result_ids.size() < drop_tokens_threshold) {
+            while(st.all_result_ids.size() < drop_tokens_threshold) {
                 if(num_tokens_dropped >= n - 1) { right_to_left = !right_to_left; num_tokens_dropped = 0; total_dirs_done++; }
                 if(n > 1 && total_dirs_done < 2) {
-                    std::vector<std::string> trunc, dropped;
+                    std::vector<query_token> trunc;
+                    std::vector<std::string> dropped;
                     if(right_to_left) {
                         const size_t tl = n - num_tokens_dropped - 1;
-                        for(size_t i = 0; i < n; i++) (i < tl ? trunc : dropped).push_back(tokens[i]);
+                        for(size_t i = 0; i < n; i++) { if(i < tl) trunc.push_back(qt[i]); else dropped.push_back(tokens[i]); }
                     } else {
-                        const size_t st = num_tokens_dropped + 1;
-                        for(size_t i = 0; i < n; i++) (i >= st ? trunc : dropped).push_back(tokens[i]);
+                        const size_t start = num_tokens_dropped + 1;
+                        for(size_t i = 0; i < n; i++) { if(i >= start) trunc.push_back(qt[i]); else dropped.push_back(tokens[i]); }
                     }
                     num_tokens_dropped++;
-                    op = run_round(trunc, dropped);
+                    op = fuzzy_search_fields(trunc, dropped, the_fields, sort_fields, topster_size, opts, st);
                     if(!op.ok()) return op;
                 } else break;
             }
         }
-        raw_result_kvs = topster.sort();
-        found = all_result_ids.size();
+        raw_result_kvs = st.topster.sort();
+        found = st.all_result_ids.size();
         return Option<bool>(true);
     }
 
