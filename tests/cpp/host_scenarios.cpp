@@ -144,6 +144,8 @@ static void collection_scenarios(const std::string& jsonl) {
             {"what ex", opt(0, true, 10, O::MAX_SCORE), 10, {"6", "12", "19", "22", "13", "8", "15", "24", "21"}, 10, 9},
             {"t", opt(0, true, 10, O::MAX_SCORE), 10, {"19", "22"}, 2, -1},
             {"t", opt(0, true, 10, O::FREQUENCY), 10, {"1", "2"}, 2, -1},
+            {"ISSX what", opt(1, false, 20), 20, {"19", "6", "21", "22"}, 4, 11},        // TextContainingAnActualTypo :473-508
+            {"ISSX", opt(1, false, 10), 10, {"20", "19", "6", "3", "21"}, 10, 5},
             {"math fx", opt(0, true), 0, {}, 1, 0},
             {"x", opt(2, true), 1, {}, 2, 0},
             {"late propx", opt(2, true), 1, {"16"}, 1, -1},
@@ -259,6 +261,13 @@ static void relevance_scenarios() {
         CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 2, 0}) && found == 3);
         CHECK(index.search(tsgpu::tokenize_ascii("alpha"), {"title"}, sort_fields, 10, 250, kvs, found, opt(2, true)).ok());
         CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 2, 1}) && found == 3);
+    }
+    {   // PrefixRankedAfterExactMatch :3922-3960
+        tsgpu::Index index(4);
+        build_plain(index, {"title"}, {{{"Rotini Puttanesca"}}, {{"Poulet Roti Tout Simple"}}, {{"Chapatis (Roti)"}}, {{"School Days Rotini Pasta Salad"}}});
+        CHECK(index.search(tsgpu::tokenize_ascii("roti"), {"title"}, sort_fields, 5, 250, kvs, found, opt(0, true)).ok());
+        CHECK(found == 4 && kvs.size() == 4);
+        if(kvs.size() >= 3) CHECK(kvs[0].key == 2 && kvs[1].key == 1 && kvs[2].key == 3);
     }
     {   // MultiFieldMatchRanking :3788-3835 (query_by artist,title)
         const char* titles[] = {"Style", "Blank Space", "Balance Overkill", "Cardigan", "Invisible String", "The Last Great American Dynasty",

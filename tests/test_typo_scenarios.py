@@ -29,6 +29,9 @@ CASES = [
     ("math fx", dict(num_typos=0, prefix=True, drop_tokens_threshold=0), [], 1, 0),
     ("x", dict(num_typos=2, prefix=True), [], 2, 0),
     ("late propx", dict(num_typos=2, prefix=True), ["16"], 1, None),
+    # TextContainingAnActualTypo :473-508
+    ("ISSX what", dict(num_typos=1, prefix=False, drop_tokens_threshold=20, typo_tokens_threshold=20), ["19", "6", "21", "22"], 4, 11),
+    ("ISSX", dict(num_typos=1, prefix=False, drop_tokens_threshold=10, typo_tokens_threshold=10), ["20", "19", "6", "3", "21"], 10, 5),
     # TypoTokensThreshold: typo correction only until typo_tokens_threshold results exist
     ("redundant", dict(num_typos=2, prefix=True, drop_tokens_threshold=10, typo_tokens_threshold=0), None, 10, 1),
     ("redundant", dict(num_typos=2, prefix=True, drop_tokens_threshold=10, typo_tokens_threshold=10), None, 10, 2),
@@ -45,10 +48,27 @@ def run_cases(backend, coll):
             assert found == found_expect and (expect is not None or len(ids) == found_expect), (q, opts, found)
 
 
+def small_collection_cases(make_backend):
+    # PrefixRankedAfterExactMatch :3922-3960
+    recs = ["Rotini Puttanesca", "Poulet Roti Tout Simple", "Chapatis (Roti)", "School Days Rotini Pasta Salad"]
+    coll = refflow.Collection([{"title": t, "points": i} for i, t in enumerate(recs)], ("title",))
+    got, found = tf.TypoSearcher(make_backend(coll), coll, SORT_DESC, num_typos=0, prefix=True, drop_tokens_threshold=5).search("roti")
+    assert got[:3] == [2, 1, 3] and found == 4
+    # MultiOccurrenceString :703-727
+    coll = refflow.Collection([{"title": "The brown fox was the tallest of the lot and the quickest of the trot.", "points": 100}], ("title",))
+    got, found = tf.TypoSearcher(make_backend(coll), coll, SORT_DESC, num_typos=0, prefix=False, drop_tokens_threshold=0).search("the")
+    assert got == [0] and found == 1
+
+
 def test_typo_and_prefix_scenarios_oracle():
     coll = refflow.Collection.from_jsonl(os.path.join(GOLD, "documents.jsonl"))
     oi = ol.OracleIndex(coll.n_docs, [coll.flat], [coll.points])
     run_cases(lambda b, k: oi.keyword_search(b, k), coll)
+
+    def mk(c):
+        o = ol.OracleIndex(c.n_docs, [c.flat], [c.points])
+        return lambda b, k: o.keyword_search(b, k)
+    small_collection_cases(mk)
 
 
 def test_typo_and_prefix_scenarios_device_functions():
@@ -58,6 +78,7 @@ def test_typo_and_prefix_scenarios_device_functions():
         pytest.skip("hostsim fixture not callable directly")
     coll = refflow.Collection.from_jsonl(os.path.join(GOLD, "documents.jsonl"))
     run_cases(th.hostsim_backend(hs, coll), coll)
+    small_collection_cases(lambda c: th.hostsim_backend(hs, c))
 
 
 @pytest.mark.gpu
@@ -69,3 +90,14 @@ def test_typo_and_prefix_scenarios_gpu():
     gi.load_sort_column(coll.points)
     run_cases(lambda b, k: gi.keyword_search(b, k), coll)
     gi.close()
+    opened = []
+
+    def mk(c):
+        g = capi.GpuIndex(c.n_docs, 0)
+        g.load_field(c.flat)
+        g.load_sort_column(c.points)
+        opened.append(g)
+        return lambda b, k: g.keyword_search(b, k)
+    small_collection_cases(mk)
+    for g in opened:
+        g.close()
