@@ -8,7 +8,8 @@ refflow's backends so the reference's typo and prefix scenarios (test/collection
 Candidate generation is the reference's ART walk (src/art.cpp: art_fuzzy_search_i, SURVEY §8 f-1, not built); here a
 brute-force scan of the (tiny) test vocabulary stands in for it: optimal-string-alignment distance exactly equal to the
 cost, prefix rule of fuzzy_search_state, leaves ordered by frequency / max_score (ties: token order), the exact leaf
-first, at most max_candidates. Single searched field."""
+first, at most max_candidates; fields are scanned in query_by order with one shared set of already-produced tokens. The
+last-token refinement of the reference (popular fields of the previous token first) is not restated."""
 from __future__ import annotations
 
 from typing import Dict, List
@@ -54,17 +55,22 @@ def matches(term: str, key: str, cost: int, prefix: bool) -> bool:
 class TypoSearcher:
     def __init__(self, backend, coll: refflow.Collection, sort, num_typos: int = 2, token_order: int = FREQUENCY, prefix: bool = True,
                  drop_tokens_threshold: int = 1, typo_tokens_threshold: int = 1, max_candidates: int = 4, min_len_1typo: int = 4,
-                 min_len_2typo: int = 7, topster: int = 250):
-        assert len(coll.fields) == 1
+                 min_len_2typo: int = 7, topster: int = 250, field_weights=None,
+                 flags: int = S.FLAG_PRIORITIZE_EXACT_MATCH | S.FLAG_PRIORITIZE_NUM_MATCHING_FIELDS):
         self.backend, self.coll, self.sort = backend, coll, sort
         self.num_typos, self.token_order, self.prefix = num_typos, token_order, prefix
         self.drop_thr, self.typo_thr, self.max_cand = drop_tokens_threshold, typo_tokens_threshold, max_candidates
         self.min1, self.min2 = min_len_1typo, min_len_2typo
         self.K = max(1, min(max(topster, 250), coll.n_docs))
-        fl = coll.flat
-        df = np.diff(fl.list_off.astype(np.int64))
-        self.freq = {t: int(df[l]) for t, l in coll.vocab.items()}
-        self.max_score = {t: int(max(coll.points[int(i)] for i in fl.ids[int(fl.list_off[l]):int(fl.list_off[l + 1])])) for t, l in coll.vocab.items()}
+        self.F = len(coll.fields)
+        self.weights = list(field_weights) if field_weights else [max(0, 15 - f) for f in range(self.F)]
+        self.flags = flags
+        self.freq, self.max_score = [], []
+        for vocab, fl in zip(coll.vocabs, coll.flats):
+            df = np.diff(fl.list_off.astype(np.int64))
+            self.freq.append({t: int(df[l]) for t, l in vocab.items()})
+            self.max_score.append({t: int(max(coll.points[int(i)] for i in fl.ids[int(fl.list_off[l]):int(fl.list_off[l + 1])]))
+                                   for t, l in vocab.items()})
 
     def bounded_cost(self, token: str) -> int:
         if any(not ch.isalnum() for ch in token) or token.isdigit():
@@ -73,12 +79,11 @@ class TypoSearcher:
             return 0
         return min(self.num_typos, 1) if len(token) < self.min2 else min(self.num_typos, 2)
 
-    def candidates(self, token: str, cost: int, prefix_search: bool, unique_tokens: set) -> List[str]:
-        rank = self.freq if self.token_order == FREQUENCY else self.max_score
-        exact = token if (not prefix_search and token in self.coll.vocab) else None
-        if prefix_search and token in self.coll.vocab:
-            exact = token
-        found = [t for t in self.coll.vocab if matches(token, t, cost, prefix_search) and t not in unique_tokens and t != exact]
+    def field_candidates(self, f: int, token: str, cost: int, prefix_search: bool, unique_tokens: set) -> List[str]:
+        vocab = self.coll.vocabs[f]
+        rank = self.freq[f] if self.token_order == FREQUENCY else self.max_score[f]
+        exact = token if token in vocab else None
+        found = [t for t in vocab if matches(token, t, cost, prefix_search) and t not in unique_tokens and t != exact]
         found.sort(key=lambda t: (-rank[t], t))
         for t in found:
             unique_tokens.add(t)
@@ -86,6 +91,14 @@ class TypoSearcher:
             found.insert(0, exact)
             unique_tokens.add(exact)
         return found[:self.max_cand]
+
+    def candidates(self, token: str, cost: int, prefix_search: bool, unique_tokens: set) -> List[str]:
+        out: List[str] = []
+        for f in range(self.F):
+            out += self.field_candidates(f, token, cost, prefix_search, unique_tokens)
+            if len(out) >= self.max_cand:
+                break
+        return out
 
     def search(self, q: str):
         tokens = refflow.tokenize(q)
@@ -169,8 +182,8 @@ class TypoSearcher:
         N = 1
         for c in cands:
             N *= len(c[3])
-        limit = self.max_cand if self.prefix else max(10, self.max_cand)       # one searched field
-        vocab = self.coll.vocab
+        limit = self.max_cand if (self.F == 1 and self.prefix) else max(10, self.max_cand)
+        vocabs = self.coll.vocabs
         combos = []
         for n in range(min(N, limit)):
             qn, total_cost, sugg = n, 0, []
@@ -184,13 +197,12 @@ class TypoSearcher:
             if h in self.query_hashes:
                 continue
             self.query_hashes.add(h)
-            rows = [[vocab[t]] for t in sugg] + [[vocab.get(t, S.NO_LIST)] for t in dropped]
+            rows = [[v.get(t, S.NO_LIST) for v in vocabs] for t in sugg] + [[v.get(t, S.NO_LIST) for v in vocabs] for t in dropped]
             combos.append(S.Combo(rows, len(sugg), total_cost=total_cost))
         if not combos:
             return
-        query = S.Query(combos, topk=self.K, sort=self.sort, num_query_tokens=len(cands), field_weight=[15],
-                        flags=S.FLAG_PRIORITIZE_EXACT_MATCH | S.FLAG_PRIORITIZE_NUM_MATCHING_FIELDS)
-        kv, cnt, found = self.backend(S.KwBatch([query], [0]), self.K)
+        query = S.Query(combos, topk=self.K, sort=self.sort, num_query_tokens=len(cands), field_weight=self.weights, flags=self.flags)
+        kv, cnt, found = self.backend(S.KwBatch([query], list(range(self.F))), self.K)
         for i in range(int(cnt[0])):
             key = int(kv["key"][0, i])
             tup = tuple(int(x) for x in kv["scores"][0, i])
