@@ -358,6 +358,51 @@ static void relevance_scenarios() {
     }
 }
 
+// test/collection_specific_test.cpp scenarios (typos, prefixes, several fields, weights, string[]): the table is
+// generated from the Python harness' CASES so both run the same reference expectations
+struct SpecificCase {
+    const char* name;
+    std::vector<std::string> fields;
+    std::vector<bool> is_array;
+    std::vector<std::vector<std::vector<std::string>>> docs;      // [doc][field][element]
+    std::vector<long> points;
+    const char* query;
+    uint32_t num_typos; bool prefix; size_t drop, typo_thr;
+    std::vector<uint32_t> weights;
+    std::vector<uint32_t> expect;
+};
+static void specific_scenarios() {
+    const std::vector<SpecificCase> cases = {
+#include "specific_cases.inc"
+    };
+    const std::vector<tsgpu::sort_by> sort_fields = {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::numeric, "points", true}};
+    for(auto& c: cases) {
+        tsgpu::Index index((uint32_t) c.docs.size());
+        for(size_t f = 0; f < c.fields.size(); f++) {
+            tsgpu::field_mirror_t m(c.is_array[f]);
+            for(uint32_t d = 0; d < c.docs.size(); d++) {
+                if(c.is_array[f]) {
+                    std::vector<std::vector<std::string>> elems;
+                    for(auto& e: c.docs[d][f]) elems.push_back(tsgpu::tokenize_ascii(e));
+                    m.index_string_array(d, elems);
+                } else m.index_plain_string(d, tsgpu::tokenize_ascii(c.docs[d][f].empty() ? std::string() : c.docs[d][f][0]));
+            }
+            CHECK(index.add_field(c.fields[f], m).ok());
+        }
+        std::unordered_map<uint32_t, int64_t> points;
+        for(uint32_t d = 0; d < c.points.size(); d++) points[d] = c.points[d];
+        CHECK(index.add_sort_field("points", points).ok());
+        tsgpu::search_options o = opt(c.num_typos, c.prefix, c.typo_thr);
+        o.query_by_weights = c.weights;
+        std::vector<tsgpu::KV> kvs;
+        size_t found = 0;
+        CHECK(index.search(tsgpu::tokenize_ascii(c.query), c.fields, sort_fields, c.drop, 250, kvs, found, o).ok());
+        const auto got = keys_of(kvs);
+        if(got != c.expect) { printf("specific case %s: got", c.name); for(auto k: got) printf(" %u", k); printf("\n"); }
+        CHECK(got == c.expect);
+    }
+}
+
 int main(int argc, char** argv) {
     if(tsgpu_device_count() == 0) { printf("no CUDA device: nothing to run (the library has no CPU path)\n"); return 99; }
     posting_list_intersection_basics();
@@ -366,6 +411,7 @@ int main(int argc, char** argv) {
     vector_scenario();
     exact_prefix_and_setops();
     relevance_scenarios();
+    specific_scenarios();
     printf("%s (%d failed checks)\n", failures ? "FAILED" : "PASSED", failures);
     return failures;
 }

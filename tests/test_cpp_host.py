@@ -37,6 +37,14 @@ def test_cpp_host_scenarios_on_oracle_double():
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def test_specific_cases_table_is_current():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_specific_cases", os.path.join(ROOT, "tests", "cpp", "make_specific_cases.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert open(os.path.join(ROOT, "tests", "cpp", "specific_cases.inc")).read() == mod.render(), "run tests/cpp/make_specific_cases.py"
+
+
 def test_cpp_host_layer_builds():
     build()
     assert os.path.exists(BIN)
