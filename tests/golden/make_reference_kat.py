@@ -1,7 +1,9 @@
 """Writes tests/golden/reference_kat.json: known-answer vectors lifted verbatim from the reference's OWN unit tests
 (literal tables in /root/reference/test/*.cpp; each entry cites file:line). Nothing is computed here — the script only
-records the literals so the fixture has a committed generator. topster_record_values.txt is a byte copy of
-/root/reference/test/resources/record_values.txt (data file used by test/topster_test.cpp:60-136)."""
+records the literals so the fixture has a committed generator. Byte copies of the reference's test DATA files (not code) that
+its tests read: topster_record_values.txt = test/resources/record_values.txt (test/topster_test.cpp:60-136);
+documents.jsonl, multi_field_documents.jsonl, float_documents.jsonl = test/*.jsonl (collection_test.cpp,
+collection_sorting_test.cpp fixtures). `cp /root/reference/test/<name> tests/golden/` regenerates them."""
 import json, os
 
 kat = {
