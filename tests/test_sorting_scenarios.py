@@ -61,11 +61,37 @@ def scenarios(backend_of):
     run(backend_of, docs, ("title",), cols, "Jeremy", (num(0, False), num(1, True), TM), ["5", "4", "6", "1", "3", "0", "2"])
 
 
+def wildcard_scenarios(wildcard_backend_of):
+    # WildcardQuery, test/collection_test.cpp:551-603: q=* over documents.jsonl (25 records with the fixture's dummy one)
+    docs = [{"points": 10, "title": "z"}] + [json.loads(l) for l in open(os.path.join(GOLD, "documents.jsonl")) if l.strip()]
+    coll = Coll(docs, ("title",), [[d["points"] for d in docs]])
+    backend, close = wildcard_backend_of(coll)
+    for sort, expect in (((num(0, True), (S.SORT_SEQ_ID, -1, 1, 0), NONE), None),
+                         ((num(0, False), (S.SORT_SEQ_ID, -1, 1, 0), NONE), ["21", "24", "17"])):
+        kv, cnt, found = backend(S.KwBatch([S.Query([], topk=250, sort=sort)], [0]), 250)
+        assert int(found[0]) == 25 and int(cnt[0]) == 25
+        if expect:
+            assert [str(docs[int(kv["key"][0, i])].get("id", int(kv["key"][0, i]))) for i in range(3)] == expect
+    close()
+    # WildcardSearchSequenceIdSort, test/collection_sorting_test.cpp:1962-1986: 30 identical docs, _seq_id DESC
+    docs = [{"category": "Shoes"} for _ in range(30)]
+    coll = Coll(docs, ("category",), [[0] * 30])
+    backend, close = wildcard_backend_of(coll)
+    kv, cnt, found = backend(S.KwBatch([S.Query([], topk=250, sort=((S.SORT_SEQ_ID, -1, 1, 0), NONE, NONE))], [0]), 250)
+    close()
+    assert int(found[0]) == 30 and [int(kv["key"][0, i]) for i in range(10)] == list(range(29, 19, -1))
+
+
 def test_sorting_scenarios_oracle():
     def mk(coll):
         oi = ol.OracleIndex(coll.n_docs, coll.flats, coll.cols)
         return (lambda b, k: oi.keyword_search(b, k)), (lambda: None)
     scenarios(mk)
+
+    def mkw(coll):
+        oi = ol.OracleIndex(coll.n_docs, coll.flats, coll.cols)
+        return (lambda b, k: oi.wildcard_search(b, k)), (lambda: None)
+    wildcard_scenarios(mkw)
 
 
 @pytest.mark.gpu
@@ -80,3 +106,12 @@ def test_sorting_scenarios_gpu():
             gi.load_sort_column(c)
         return (lambda b, k: gi.keyword_search(b, k)), gi.close
     scenarios(mk)
+
+    def mkw(coll):
+        gi = capi.GpuIndex(coll.n_docs, 0)
+        for f in coll.flats:
+            gi.load_field(f)
+        for c in coll.cols:
+            gi.load_sort_column(c)
+        return (lambda b, k: gi.wildcard_search(b, k)), gi.close
+    wildcard_scenarios(mkw)
