@@ -80,3 +80,20 @@ def test_rank_fusion_reference_kats_oracle():
         oi = ol.OracleIndex(3, [flat], [], graph)
         return oi.hybrid_search(b, qv, vp, 256)
     check(run)
+
+
+def test_distance_threshold_reference_kat_oracle():
+    """DistanceThresholdTest, test/collection_vector_search_test.cpp:1548-1598: cosine (the default vec_dist), wildcard
+    query + vector query; both documents without a threshold (nearest first), only the near one with
+    distance_threshold:0.01."""
+    docs = np.asarray([[0.1, 0.2, 0.3], [0.6, 0.7, 0.8]], np.float32)
+    vecs = np.stack([unit(v) for v in docs])                      # hnsw_index_t::normalize_vector at index time
+    q = unit([0.3, 0.4, 0.5])
+    graph = ol.hnsw_build(vecs, 16, 200, 100, metric=1)
+    oi = ol.OracleIndex(2, [], [], graph)
+    sort = ((S.SORT_VECTOR_DISTANCE, -1, -1, 0), (S.SORT_SEQ_ID, -1, 1, 0), (S.SORT_NONE, -1, 1, 0))
+    b = S.KwBatch([S.Query([], topk=250, sort=sort)], [])
+    kv, cnt, found = oi.vector_search(b, q[None, :].copy(), S.vec_params(k=0, ef=10, fetch_size=20), 256)
+    assert int(found[0]) == 2 and [int(kv["key"][0, i]) for i in range(int(cnt[0]))] == [1, 0]
+    kv, cnt, found = oi.vector_search(b, q[None, :].copy(), S.vec_params(k=0, ef=10, fetch_size=20, distance_threshold=0.01), 256)
+    assert int(found[0]) == 1 and [int(kv["key"][0, i]) for i in range(int(cnt[0]))] == [1]
