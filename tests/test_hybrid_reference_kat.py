@@ -97,3 +97,19 @@ def test_distance_threshold_reference_kat_oracle():
     assert int(found[0]) == 2 and [int(kv["key"][0, i]) for i in range(int(cnt[0]))] == [1, 0]
     kv, cnt, found = oi.vector_search(b, q[None, :].copy(), S.vec_params(k=0, ef=10, fetch_size=20, distance_threshold=0.01), 256)
     assert int(found[0]) == 1 and [int(kv["key"][0, i]) for i in range(int(cnt[0]))] == [1]
+
+
+def test_hybrid_flat_cutoff_reference_kat_oracle():
+    """HybridSearchWithFilteringAndFlatSearchCutoff, test/collection_vector_search_test.cpp:5199-5263: the query word matches
+    nothing, the filter (age:>0) holds all four documents, flat_search_cutoff:100 sends the vector part down the brute-force
+    path — all four documents come back. (Vectors are stand-ins; only the control flow is asserted, as in the reference.)"""
+    names = [["nike", "running", "shoes", "for", "men"], ["nike", "running", "sneakers"], ["adidas", "shoes"], ["puma"]]
+    vocab, flat = field_of(names)
+    rng = np.random.default_rng(5)
+    vecs = np.stack([unit(rng.normal(size=8)) for _ in range(4)])
+    graph = ol.hnsw_build(vecs, 16, 200, 100)
+    oi = ol.OracleIndex(4, [flat], [], graph)
+    q = S.Query([], topk=250, sort=SORT, flags=FLAGS, filter=0)        # "footwear": no candidate, so no combination to run
+    b = S.KwBatch([q], [0], [np.arange(4, dtype=np.uint32)])
+    kv, cnt, found = oi.hybrid_search(b, unit(rng.normal(size=8))[None, :].copy(), S.vec_params(k=0, ef=10, alpha=0.3, flat_search_cutoff=100, fetch_size=10), 256)
+    assert int(cnt[0]) == 4 and int(found[0]) == 4 and sorted(int(kv["key"][0, i]) for i in range(4)) == [0, 1, 2, 3]
