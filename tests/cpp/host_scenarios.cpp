@@ -358,6 +358,49 @@ static void relevance_scenarios() {
     }
 }
 
+// PhraseSearch, test/collection_specific_test.cpp:2504-2622 — the cases that combine phrases with tokens or exclusions
+// (phrase-only queries get do_phrase_search's own score and are not mirrored by the host layer)
+static void phrase_scenarios() {
+    tsgpu::Index index(3);
+    tsgpu::field_mirror_t m;
+    const char* t[] = {"Then and there by the down", "Down There by the Train", "The State Trooper"};
+    for(uint32_t i = 0; i < 3; i++) m.index_plain_string(i, tsgpu::tokenize_ascii(t[i]));
+    CHECK(index.add_field("title", m).ok());
+    const std::vector<tsgpu::sort_by> sort_fields = {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::seq_id, "", true}};   // no default_sorting_field
+    std::vector<tsgpu::KV> kvs;
+    size_t found = 0;
+    auto P = [](std::initializer_list<const char*> w) { std::vector<std::string> v; for(auto x: w) v.push_back(x); return v; };
+    // without phrase search: "down there by", drop_tokens_threshold 0
+    CHECK(index.search(tsgpu::tokenize_ascii("down there by"), {"title"}, sort_fields, 0, 250, kvs, found, opt(0, false)).ok());
+    CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 0}));
+    {   // "by the" and
+        tsgpu::search_options o = opt(0, false);
+        o.phrases = {P({"by", "the"})};
+        CHECK(index.search({"and"}, {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{0}));
+        // "by the" state
+        CHECK(index.search({"state"}, {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
+        CHECK(kvs.empty());
+    }
+    {   // -"by the down"  and  -"by the"  and  -"by the dinosaur"
+        tsgpu::search_options o = opt(0, false);
+        o.exclude_phrases = {P({"by", "the", "down"})};
+        CHECK(index.search({}, {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{2, 1}));
+        o.exclude_phrases = {P({"by", "the"})};
+        CHECK(index.search({}, {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{2}));
+        o.exclude_phrases = {P({"by", "the", "dinosaur"})};
+        CHECK(index.search({}, {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
+        CHECK(kvs.size() == 3);
+    }
+    {   // phrase-only queries are refused, not approximated
+        tsgpu::search_options o = opt(0, false);
+        o.phrases = {P({"down", "there", "by"})};
+        CHECK(!index.search({}, {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
+    }
+}
+
 // test/collection_specific_test.cpp scenarios (typos, prefixes, several fields, weights, string[]): the table is
 // generated from the Python harness' CASES so both run the same reference expectations
 struct SpecificCase {
@@ -412,6 +455,7 @@ int main(int argc, char** argv) {
     exact_prefix_and_setops();
     relevance_scenarios();
     specific_scenarios();
+    phrase_scenarios();
     printf("%s (%d failed checks)\n", failures ? "FAILED" : "PASSED", failures);
     return failures;
 }

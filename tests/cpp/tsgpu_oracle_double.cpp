@@ -127,6 +127,10 @@ tsgpu_status tsgpu_keyword_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* 
     tso_keyword_search_batch(D(idx)->oi, reinterpret_cast<const tso_kw_batch*>(b), reinterpret_cast<tso_kv*>(out_kv), kv_stride, out_count, out_found, 1);
     return TSGPU_OK;
 }
+tsgpu_status tsgpu_wildcard_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
+    tso_wildcard_search_batch(D(idx)->oi, reinterpret_cast<const tso_kw_batch*>(b), reinterpret_cast<tso_kv*>(out_kv), kv_stride, out_count, out_found, 1);
+    return TSGPU_OK;
+}
 tsgpu_status tsgpu_knn_batch(tsgpu_index* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef, const int32_t* q_filter, uint32_t,
                              const uint64_t* filter_off, const uint32_t* filter_ids, float* out_dist, uint32_t* out_labels, uint32_t* out_n) {
     Double* d = D(idx);

@@ -10,6 +10,9 @@
 //   posting_t::get_phrase_matches         src/posting.cpp:543      Index::get_phrase_matches(field, tokens, ids, out)
 //   posting_t::get_exact_matches          src/posting.cpp:485      Index::get_exact_matches(field, tokens, ids, out[, prefix])
 //   ArrayUtils::and/or/exclude_scalar     include/array_utils.h    Index::ids_setop(op, a, b, out)
+//   Index::handle_exclusion               src/index.cpp:6270-6318  Index::handle_exclusion (tokens and phrases)
+//   Index::do_phrase_search (id sets)     src/index.cpp:5909-6016  Index::phrase_filter_ids
+//   Index::search_wildcard                src/index.cpp:6616-6800  Index::search_wildcard
 //   Index::search_across_fields           src/index.cpp:5385       Index::search_across_fields(query_suggestions, ...)
 //   hnsw_index_t + searchKnnCloserFirst   src/index.cpp:3384       Index::searchKnnCloserFirst(q, k, ef, filter_ids)
 //   Topster<KV>::add / sort               include/topster.h:321    host_topster_t (merges the <=K KVs of each device round)
@@ -120,6 +123,8 @@ struct search_options {
     bool prioritize_token_position = false;
     bool prioritize_num_matching_fields = true;
     std::vector<std::string> exclude_tokens;
+    std::vector<std::vector<std::string>> exclude_phrases;   // -"a b c": phrase matches are excluded (Index::handle_exclusion)
+    std::vector<std::vector<std::string>> phrases;           // "a b c": results must hold every phrase (Index::do_phrase_search)
     std::vector<uint32_t> query_by_weights;      // empty: 15, 14, ... by field order
     // typo / prefix expansion (Collection::search defaults)
     uint32_t num_typos = 2;
@@ -366,6 +371,105 @@ public:
         return Option<bool>(true);
     }
 
+    // ids of `field` holding the tokens as a phrase (a single token: its posting list); false when a token is unknown
+    Option<bool> phrase_ids_of(const std::string& field, const std::vector<std::string>& phrase, std::vector<uint32_t>& out, bool& all_known) {
+        out.clear();
+        all_known = true;
+        const uint32_t f = field_ids.at(field);
+        for(auto& t: phrase) if(token_id(f, t) == TSGPU_NO_LIST) { all_known = false; return Option<bool>(true); }
+        std::vector<uint32_t> contains;
+        auto op = intersect(field, phrase, contains);
+        if(!op.ok()) return op;
+        if(phrase.size() == 1) { out = contains; return Option<bool>(true); }
+        return get_phrase_matches(field, phrase, contains, out);
+    }
+    // Index::handle_exclusion (src/index.cpp:6270-6318): every doc holding an exclusion token, or an exclusion phrase as a
+    // phrase, in a searched field
+    Option<bool> handle_exclusion(const std::vector<std::string>& the_fields, const search_options& o, std::vector<uint32_t>& excluded) {
+        std::vector<std::vector<std::string>> all = o.exclude_phrases;
+        for(auto& t: o.exclude_tokens) all.push_back({t});
+        for(auto& fn: the_fields) for(auto& ph: all) {
+            std::vector<uint32_t> ids, merged;
+            bool known = true;
+            auto op = phrase_ids_of(fn, ph, ids, known);
+            if(!op.ok()) return op;
+            if(!known || ids.empty()) continue;
+            op = ids_setop(TSGPU_SET_OR, excluded, ids, merged);
+            if(!op.ok()) return op;
+            excluded.swap(merged);
+        }
+        return Option<bool>(true);
+    }
+    // The id-set half of Index::do_phrase_search (src/index.cpp:5909-6016): per field the phrases are ANDed (a phrase with
+    // an unknown token or without matches is skipped, as the reference does), fields are ORed, excluded ids removed. The
+    // result restricts the keyword search like a filter. (Scoring a phrase-ONLY query with 100000 + field weight is the
+    // other half and is not mirrored here.)
+    Option<bool> phrase_filter_ids(const std::vector<std::string>& the_fields, const search_options& o,
+                                   const std::vector<uint32_t>& excluded, std::vector<uint32_t>& phrase_result_ids) {
+        phrase_result_ids.clear();
+        for(auto& fn: the_fields) {
+            std::vector<uint32_t> field_ids_acc;
+            bool have = false;
+            for(auto& ph: o.phrases) {
+                std::vector<uint32_t> ids, merged;
+                bool known = true;
+                auto op = phrase_ids_of(fn, ph, ids, known);
+                if(!op.ok()) return op;
+                if(!known || ids.empty()) continue;
+                if(!have) { field_ids_acc = ids; have = true; }
+                else { op = ids_setop(TSGPU_SET_AND, ids, field_ids_acc, merged); if(!op.ok()) return op; field_ids_acc.swap(merged); }
+            }
+            if(field_ids_acc.empty()) continue;
+            std::vector<uint32_t> merged;
+            auto op = ids_setop(TSGPU_SET_OR, phrase_result_ids, field_ids_acc, merged);
+            if(!op.ok()) return op;
+            phrase_result_ids.swap(merged);
+        }
+        if(!excluded.empty() && !phrase_result_ids.empty()) {
+            std::vector<uint32_t> merged;
+            auto op = ids_setop(TSGPU_SET_EXCLUDE, phrase_result_ids, excluded, merged);
+            if(!op.ok()) return op;
+            phrase_result_ids.swap(merged);
+        }
+        return Option<bool>(true);
+    }
+    // Index::search_wildcard (src/index.cpp:6616-6800) for q=*: every doc (or every filter id) minus the excluded ones
+    Option<bool> search_wildcard(const std::vector<sort_by>& sort_fields, const std::vector<uint32_t>* filter_ids,
+                                 const std::vector<uint32_t>& excluded_result_ids, size_t topster_size,
+                                 std::vector<KV>& raw_result_kvs, size_t& found) {
+        uint32_t q_combo_off[2] = {0, 0};
+        int32_t q_filter = filter_ids ? 0 : -1;
+        uint32_t q_excl_off[2] = {0, (uint32_t) excluded_result_ids.size()};
+        uint32_t q_topk = (uint32_t) std::min<size_t>(topster_size, TSGPU_MAX_TOPK);
+        uint8_t sort_type[3] = {0, 0, 0}, missing_first[3] = {0, 0, 0};
+        int32_t sort_col[3] = {-1, -1, -1};
+        int8_t sort_order[3] = {1, 1, 1};
+        for(size_t i = 0; i < sort_fields.size() && i < 3; i++) {
+            sort_type[i] = (uint8_t) sort_fields[i].type;
+            sort_order[i] = sort_fields[i].desc ? 1 : -1;
+            missing_first[i] = sort_fields[i].missing_first;
+            if(sort_fields[i].type == sort_by::numeric) sort_col[i] = (int32_t) sort_cols.at(sort_fields[i].name);
+        }
+        uint8_t q_flags = 0, q_match_type = TSGPU_MATCH_MAX_SCORE, q_nqt = 0, weight = 0;
+        uint64_t filter_off[2] = {0, filter_ids ? filter_ids->size() : 0};
+        const uint32_t zero = 0;
+        uint32_t c_tok_off[1] = {0};
+        tsgpu_kw_batch b{};
+        b.n_queries = 1; b.n_combos = 0; b.n_fields = field_ids.empty() ? 0u : 1u; b.n_filters = filter_ids ? 1 : 0;     // field slot 0 is unused by a wildcard query
+        b.field_ids = &zero; b.q_combo_off = q_combo_off; b.q_filter = &q_filter; b.q_excl_off = q_excl_off;
+        b.excl_ids = excluded_result_ids.empty() ? &zero : excluded_result_ids.data(); b.q_topk = &q_topk;
+        b.q_sort_type = sort_type; b.q_sort_col = sort_col; b.q_sort_order = sort_order; b.q_sort_missing_first = missing_first;
+        b.q_flags = &q_flags; b.q_match_type = &q_match_type; b.q_num_query_tokens = &q_nqt; b.q_field_weight = &weight;
+        b.c_tok_off = c_tok_off; b.c_total_cost = &zero; b.c_n_required = &weight; b.t_list = &zero;
+        b.filter_off = filter_off; b.filter_ids = (filter_ids && !filter_ids->empty()) ? filter_ids->data() : &zero;
+        raw_result_kvs.assign(q_topk, KV{});
+        uint32_t count = 0, nf = 0;
+        if(tsgpu_wildcard_search_batch(h, &b, raw_result_kvs.data(), q_topk, &count, &nf) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
+        raw_result_kvs.resize(count);
+        found = nf;
+        return Option<bool>(true);
+    }
+
     // ---- typo / prefix expansion -------------------------------------------------------------------------------
     // Index::get_bounded_typo_cost (src/index.cpp:6923-6951)
     static int get_bounded_typo_cost(size_t max_cost, const std::string& token, size_t min_len_1typo, size_t min_len_2typo) {
@@ -415,6 +519,8 @@ public:
         std::set<uint32_t> all_result_ids;
         std::set<std::vector<std::string>> query_hashes;
         std::vector<uint32_t> excluded;
+        std::vector<uint32_t> filter_ids;      // phrase ids (do_phrase_search) restricting the keyword search
+        bool filter_by_provided = false;
         std::vector<uint8_t> weights;
         explicit search_state(size_t cap): topster(cap) {}
     };
@@ -449,7 +555,7 @@ public:
         if(suggestions.empty()) return Option<bool>(true);
         host_topster_t round(topster_size);
         size_t nf = 0;
-        auto op = search_across_fields(suggestions, dropped.size(), costs, the_fields, st.weights, sort_fields, {}, false, st.excluded, topster_size,
+        auto op = search_across_fields(suggestions, dropped.size(), costs, the_fields, st.weights, sort_fields, st.filter_ids, st.filter_by_provided, st.excluded, topster_size,
                                        o.prioritize_exact_match, round, nf, o.prioritize_token_position, o.prioritize_num_matching_fields);
         if(!op.ok()) return op;
         for(auto& kv: round.sort()) { st.topster.add(kv); st.all_result_ids.insert((uint32_t) kv.key); }
@@ -520,16 +626,17 @@ public:
                         std::vector<KV>& raw_result_kvs, size_t& found, const search_options& opts = search_options()) {
         search_state st(topster_size);
         st.weights = process_search_field_weights(the_fields.size(), opts.query_by_weights);
-        // excluded_result_ids: every doc holding an exclusion token in a searched field (the host resolves them from the
-        // tokens' posting lists before run_search)
-        for(auto& t: opts.exclude_tokens) for(auto& fn: the_fields) {
-            std::vector<uint32_t> ids, merged;
-            auto iop = intersect(fn, {t}, ids);
-            if(!iop.ok()) return iop;
-            if(ids.empty()) continue;
-            merged.resize(st.excluded.size() + ids.size());
-            merged.resize(std::set_union(st.excluded.begin(), st.excluded.end(), ids.begin(), ids.end(), merged.begin()) - merged.begin());
-            st.excluded.swap(merged);
+        auto xop = handle_exclusion(the_fields, opts, st.excluded);
+        if(!xop.ok()) return xop;
+        if(!opts.phrases.empty()) {
+            auto pop = phrase_filter_ids(the_fields, opts, st.excluded, st.filter_ids);
+            if(!pop.ok()) return pop;
+            st.filter_by_provided = true;
+            if(tokens.empty()) return Option<bool>(400, "phrase-only queries are scored by do_phrase_search's 100000 + weight rule, which this layer does not mirror");
+        }
+        if(tokens.empty()) {
+            // only exclusions: the query is `*` minus the excluded ids (src/index.cpp:3738-3745)
+            return search_wildcard(sort_fields, nullptr, st.excluded, topster_size, raw_result_kvs, found);
         }
         std::vector<query_token> qt;
         for(size_t i = 0; i < tokens.size(); i++) qt.push_back({tokens[i], opts.prefix && i + 1 == tokens.size()});
