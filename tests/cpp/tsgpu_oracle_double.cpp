@@ -15,6 +15,7 @@ static_assert(sizeof(tsgpu_kv) == sizeof(tso_kv), "KV layout");
 static_assert(sizeof(tsgpu_field) == sizeof(tso_field), "field layout");
 static_assert(sizeof(tsgpu_kw_batch) == sizeof(tso_kw_batch), "batch layout");
 static_assert(sizeof(tsgpu_hnsw) == sizeof(tso_hnsw), "hnsw layout");
+static_assert(sizeof(tsgpu_vec_params) == sizeof(tso_vec_params), "vec params layout");
 
 namespace {
 struct FieldCopy {
@@ -30,7 +31,40 @@ struct Double {
     std::vector<float> vec; std::vector<uint32_t> labels, links0, links_up; std::vector<uint8_t> levels; std::vector<uint64_t> upper_off;
     tso_hnsw g{};
     bool has_g = false;
+    std::vector<std::vector<uint32_t>> filters;     // persistent filters: handle = -(slot + 2)
 };
+// a batch whose q_filter entries refer to persistent handles (<= -2) is rewritten so they become inline slots appended
+// after the batch's own filters — the oracle only knows inline filters
+struct Rewritten {
+    tso_kw_batch b;
+    std::vector<int32_t> q_filter;
+    std::vector<uint64_t> filter_off;
+    std::vector<uint32_t> filter_ids;
+};
+static const tso_kw_batch* rewrite(const Double* d, const tsgpu_kw_batch* in, Rewritten& r) {
+    const tso_kw_batch* src = reinterpret_cast<const tso_kw_batch*>(in);
+    bool any = false;
+    for(uint32_t q = 0; q < in->n_queries; q++) if(in->q_filter[q] <= -2) any = true;
+    if(!any) return src;
+    r.b = *src;
+    r.filter_off.assign(1, 0);
+    for(uint32_t f = 0; f < in->n_filters; f++) {
+        r.filter_ids.insert(r.filter_ids.end(), in->filter_ids + in->filter_off[f], in->filter_ids + in->filter_off[f + 1]);
+        r.filter_off.push_back(r.filter_ids.size());
+    }
+    r.q_filter.assign(in->q_filter, in->q_filter + in->n_queries);
+    for(uint32_t q = 0; q < in->n_queries; q++) {
+        if(in->q_filter[q] > -2) continue;
+        const auto& ids = d->filters[(size_t) (-(in->q_filter[q] + 2))];
+        r.filter_ids.insert(r.filter_ids.end(), ids.begin(), ids.end());
+        r.filter_off.push_back(r.filter_ids.size());
+        r.q_filter[q] = (int32_t) r.filter_off.size() - 2;
+    }
+    if(r.filter_ids.empty()) r.filter_ids.push_back(0);
+    r.b.n_filters = (uint32_t) r.filter_off.size() - 1;
+    r.b.q_filter = r.q_filter.data(); r.b.filter_off = r.filter_off.data(); r.b.filter_ids = r.filter_ids.data();
+    return &r.b;
+}
 thread_local std::string g_err;
 Double* D(tsgpu_index* p) { return reinterpret_cast<Double*>(p); }
 }
@@ -124,13 +158,49 @@ tsgpu_status tsgpu_ids_setop(tsgpu_index*, int op, const uint32_t* a, size_t na,
     return TSGPU_OK;
 }
 tsgpu_status tsgpu_keyword_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
-    tso_keyword_search_batch(D(idx)->oi, reinterpret_cast<const tso_kw_batch*>(b), reinterpret_cast<tso_kv*>(out_kv), kv_stride, out_count, out_found, 1);
+    Rewritten r;
+    tso_keyword_search_batch(D(idx)->oi, rewrite(D(idx), b, r), reinterpret_cast<tso_kv*>(out_kv), kv_stride, out_count, out_found, 1);
     return TSGPU_OK;
 }
 tsgpu_status tsgpu_wildcard_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
-    tso_wildcard_search_batch(D(idx)->oi, reinterpret_cast<const tso_kw_batch*>(b), reinterpret_cast<tso_kv*>(out_kv), kv_stride, out_count, out_found, 1);
+    Rewritten r;
+    tso_wildcard_search_batch(D(idx)->oi, rewrite(D(idx), b, r), reinterpret_cast<tso_kv*>(out_kv), kv_stride, out_count, out_found, 1);
     return TSGPU_OK;
 }
+tsgpu_status tsgpu_vector_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const float* qvecs, const tsgpu_vec_params* vp, tsgpu_kv* out_kv,
+                                       uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
+    Rewritten r;
+    if(tso_vector_search_batch(D(idx)->oi, rewrite(D(idx), b, r), qvecs, reinterpret_cast<const tso_vec_params*>(vp), reinterpret_cast<tso_kv*>(out_kv),
+                               kv_stride, out_count, out_found, 1) != 0) { g_err = "no vector index loaded"; return TSGPU_ERR_INVALID; }
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_hybrid_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const float* qvecs, const tsgpu_vec_params* vp, tsgpu_kv* out_kv,
+                                       uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
+    Rewritten r;
+    if(tso_hybrid_search_batch(D(idx)->oi, rewrite(D(idx), b, r), qvecs, reinterpret_cast<const tso_vec_params*>(vp), reinterpret_cast<tso_kv*>(out_kv),
+                               kv_stride, out_count, out_found, 1) != 0) { g_err = "no vector index loaded"; return TSGPU_ERR_INVALID; }
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_flat_distances(tsgpu_index* idx, const float* query, const uint32_t* ids, size_t n, float* out_dist) {
+    Double* d = D(idx);
+    if(!d->has_g) { g_err = "no vector index loaded"; return TSGPU_ERR_INVALID; }
+    tso_flat_distances(&d->g, query, ids, n, out_dist);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_filter_create(tsgpu_index* idx, const uint32_t* ids, size_t n, int32_t* out_handle) {
+    Double* d = D(idx);
+    d->filters.emplace_back(ids, ids + n);
+    *out_handle = -((int32_t) d->filters.size() - 1 + 2);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_filter_destroy(tsgpu_index* idx, int32_t handle) {
+    Double* d = D(idx);
+    const size_t h = (size_t) (-(handle + 2));
+    if(handle > -2 || h >= d->filters.size()) { g_err = "bad filter handle"; return TSGPU_ERR_INVALID; }
+    d->filters[h].clear();
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_get_stats(tsgpu_index*, tsgpu_stats* out) { memset(out, 0, sizeof(*out)); return TSGPU_OK; }
 tsgpu_status tsgpu_knn_batch(tsgpu_index* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef, const int32_t* q_filter, uint32_t,
                              const uint64_t* filter_off, const uint32_t* filter_ids, float* out_dist, uint32_t* out_labels, uint32_t* out_n) {
     Double* d = D(idx);

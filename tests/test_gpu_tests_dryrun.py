@@ -1,0 +1,34 @@
+"""Dry run of the gpu-marked tests on a machine without a GPU: the C-ABI is answered by tests/cpp/tsgpu_oracle_double.cpp
+(the oracle behind the tsgpu_* entry points, built here as a shared library and selected with TSGPU_LIB_PATH), so the
+Python side of every GPU test — batch construction, calls, the reference expectations — executes before the code ever
+reaches the GPU box. It proves nothing about the kernels (oracle is compared with oracle); tests that assert device
+counters, device error codes or need CUDA tensors are left out."""
+import os
+import subprocess
+import sys
+
+import oracle_lib as ol
+
+ROOT = ol.ROOT
+GPU_ONLY = [
+    "tests/test_cpp_host.py::test_cpp_host_scenarios",                            # links the real libtsgpu.so
+    "tests/test_gpu_parity.py::test_large_scale_properties_and_sample_parity",    # generates its data on the device
+    "tests/test_gpu_parity.py::test_keyword_single_token_large_lists",            # asserts device work counters
+    "tests/test_gpu_parity.py::test_ids_setop",                                   # asserts the library's argument validation
+    "tests/test_gpu_parity.py::test_edge_cases",                                  # asserts the library's capacity errors
+]
+
+
+def test_gpu_tests_execute_against_the_oracle_double():
+    ol.build_oracle()
+    so = os.path.join(ROOT, "tests", "cpp", "libtsgpu_double.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wno-unused", "-fPIC", "-shared", os.path.join(ROOT, "tests", "cpp", "tsgpu_oracle_double.cpp"),
+                           "-o", so, "-L", os.path.join(ROOT, "oracle"), "-l:liboracle.so", f"-Wl,-rpath,{os.path.join(ROOT, 'oracle')}", "-pthread"])
+    env = dict(os.environ, TSGPU_TEST_DOUBLE="1", TSGPU_LIB_PATH=so)
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-q", "-m", "gpu", "-p", "no:cacheprovider"]
+    for t in GPU_ONLY:
+        cmd += ["--deselect", t]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, env=env, timeout=1500)
+    tail = r.stdout[-3000:] + r.stderr[-1000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout, tail
