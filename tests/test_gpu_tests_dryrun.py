@@ -32,3 +32,13 @@ def test_gpu_tests_execute_against_the_oracle_double():
     tail = r.stdout[-3000:] + r.stderr[-1000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
+def test_smoke_executes_against_the_oracle_double():
+    """__graft_entry__.smoke() — the driver's first GPU step — with the same double behind the C-ABI."""
+    so = os.path.join(ROOT, "tests", "cpp", "libtsgpu_double.so")
+    if not os.path.exists(so):
+        test_gpu_tests_execute_against_the_oracle_double()
+    env = dict(os.environ, TSGPU_LIB_PATH=so)
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], capture_output=True, text=True, cwd=ROOT, env=env, timeout=900)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
