@@ -67,7 +67,7 @@ def parse():
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--cpu-sample", type=int, default=1024, help="queries per CPU-baseline sample")
-    ap.add_argument("--workload", default="hybrid10m", choices=["hybrid10m", "keyword10m", "knn"])
+    ap.add_argument("--workload", default="hybrid10m", choices=["hybrid10m", "keyword10m"])
     ap.add_argument("--recall-queries", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exp-sorted-vectors", action="store_true",
