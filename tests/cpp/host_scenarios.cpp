@@ -413,6 +413,7 @@ struct SpecificCase {
     uint32_t num_typos; bool prefix; size_t drop, typo_thr;
     std::vector<uint32_t> weights;
     std::vector<uint32_t> expect;
+    int token_order; size_t max_candidates; long found; bool head;
 };
 static void specific_scenarios() {
     const std::vector<SpecificCase> cases = {
@@ -435,12 +436,15 @@ static void specific_scenarios() {
         std::unordered_map<uint32_t, int64_t> points;
         for(uint32_t d = 0; d < c.points.size(); d++) points[d] = c.points[d];
         CHECK(index.add_sort_field("points", points).ok());
-        tsgpu::search_options o = opt(c.num_typos, c.prefix, c.typo_thr);
+        tsgpu::search_options o = opt(c.num_typos, c.prefix, c.typo_thr, c.token_order ? tsgpu::search_options::MAX_SCORE : tsgpu::search_options::FREQUENCY);
         o.query_by_weights = c.weights;
+        o.max_candidates = c.max_candidates;
         std::vector<tsgpu::KV> kvs;
         size_t found = 0;
         CHECK(index.search(tsgpu::tokenize_ascii(c.query), c.fields, sort_fields, c.drop, 250, kvs, found, o).ok());
-        const auto got = keys_of(kvs);
+        auto got = keys_of(kvs);
+        if(c.found >= 0) CHECK((long) found == c.found && (long) got.size() == c.found);
+        if(c.head && got.size() > c.expect.size()) got.resize(c.expect.size());
         if(got != c.expect) { printf("specific case %s: got", c.name); for(auto k: got) printf(" %u", k); printf("\n"); }
         CHECK(got == c.expect);
     }

@@ -15,8 +15,10 @@ LONG = ("Central Arizona Project. - Hearing, Eighty-eighth Congress, Second Sess
 TD, T = ("title", "description"), ("title",)
 
 
-def o(num_typos, prefix, drop, typo_thr, weights=None):
-    return dict(num_typos=num_typos, prefix=prefix, drop_tokens_threshold=drop, typo_tokens_threshold=typo_thr, weights=weights)
+def o(num_typos, prefix, drop, typo_thr, weights=None, order=tf.FREQUENCY, max_candidates=4, found=None, head=False):
+    """found: also assert the found count; head: `expect` is only the head of the result list"""
+    return dict(num_typos=num_typos, prefix=prefix, drop_tokens_threshold=drop, typo_tokens_threshold=typo_thr, weights=weights,
+                token_order=order, max_candidates=max_candidates, found=found, head=head)
 
 
 D_CHARGER = [{"title": "Fast Electric Charger", "description": "A product you should buy.", "points": 100},
@@ -37,8 +39,30 @@ D_BURGER = [{"name": "Hamburger", "brand": "Burger King", "points": 10}, {"name"
 D_SHOE = [{"title": "Dog Shoemaker", "points": 100}, {"title": "Shoe and Sock", "points": 200}]
 D_FAR = [{"title": LONG, "author": "JK", "points": 0}, {"title": "Project Aim Arizona", "author": "JK", "points": 1}]
 
+NAMES = ["Mark Jack", "John Jack", "John James", "John Joseph", "John Jim", "John Jordan", "Mark Nicholas", "Mark Abbey", "Mark Boucher",
+         "Mark Bicks", "Mark Potter"]
+D_NAMES = [{"title": t, "points": i} for i, t in enumerate(NAMES)]
+D_JOHNS = [{"location": l, "name": n, "points": i} for i, (n, l) in enumerate(zip(
+    ["John Stewart", "John Smith", "John Scott", "John Stone", "John Romero", "John Oliver", "John Adams"],
+    ["Switzerland", "Seoul", "Sydney", "Surat", "Stockholm", "Salem", "Sevilla"]))]
+MORE = "test/collection_specific_more_test.cpp "
+
 # (reference test, fields, docs, query, options, expected ids)
 CASES = [
+    # prefix expansion of the last token looks at leaves sharing a document with the previous token first
+    (MORE + "PrefixExpansionOnSingleField :93", T, D_NAMES, "mark j", o(0, True, 1, 1, order=tf.MAX_SCORE), [0]),
+    (MORE + "PrefixExpansionOnSingleField :93 (2)", T, D_NAMES, "mark b", o(0, True, 1, 1, order=tf.MAX_SCORE), [9, 8]),
+    (MORE + "PrefixExpansionOnMultiField :158", ("location", "name"), D_JOHNS, "john s", o(0, True, 0, 20, order=tf.MAX_SCORE, max_candidates=4), [3, 2, 1, 0]),
+    (MORE + "PrefixExpansionOnMultiField :158 (max_candidates 10)", ("location", "name"), D_JOHNS, "john s",
+     o(0, True, 0, 20, order=tf.MAX_SCORE, max_candidates=10, found=7, head=True), [3, 2, 1, 0, 6]),
+    (MORE + "TypoCorrectionShouldUseMaxCandidates :131", T, [{"title": "Independent" + str(i), "points": i} for i in range(20)], "independent",
+     o(2, False, 0, 20, max_candidates=20, found=20, head=True), []),
+    (MORE + "MaxCandidatesShouldBeRespected :42", ("company",), [{"company": "prefix" + str(i), "points": 0} for i in range(200)], "prefix",
+     o(0, True, 0, 20, max_candidates=1000, found=200, head=True), []),
+    (MORE + "PrefixExpansionWhenExactMatchExists :63", ("title", "author"),
+     [{"title": "The Little Prince [by] Antoine de Saint Exupery : teacher guide", "author": "Barbara Valdez", "points": 0},
+      {"title": "Little Prince", "author": "Antoine de Saint-Exupery", "points": 0}], "little prince antoine saint",
+     o(2, True, 1, 5, found=2, head=True), []),
     ("ExactSingleFieldMatch :195", TD, D_CHARGER, "charger", o(2, True, 10, 10), [0, 1]),
     ("ExactSingleFieldMatch :195 (typo_tokens_threshold 1)", TD, D_CHARGER, "charger", o(2, True, 10, 1), [0]),
     ("CheckProgressiveTypoSearching :242", TD, D_CONV, "convenient", o(2, True, 10, 1), [0]),
@@ -85,10 +109,12 @@ def run_cases(make_backend):
         coll = refflow.Collection(docs, fields)
         backend, close = make_backend(coll)
         kw = dict(opts)
-        w = kw.pop("weights")
+        w, found_expect, head = kw.pop("weights"), kw.pop("found"), kw.pop("head")
         got, found = tf.TypoSearcher(backend, coll, SORT, field_weights=ranked_weights(w) if w else None, **kw).search(q)
         close()
-        assert got == expect, (name, got)
+        assert (got[:len(expect)] if head else got) == expect, (name, got)
+        if found_expect is not None:
+            assert found == found_expect and len(got) == found_expect, (name, found)
 
 
 def test_specific_scenarios_oracle():

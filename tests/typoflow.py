@@ -8,8 +8,10 @@ refflow's backends so the reference's typo and prefix scenarios (test/collection
 Candidate generation is the reference's ART walk (src/art.cpp: art_fuzzy_search_i, SURVEY §8 f-1, not built); here a
 brute-force scan of the (tiny) test vocabulary stands in for it: optimal-string-alignment distance exactly equal to the
 cost, prefix rule of fuzzy_search_state, leaves ordered by frequency / max_score (ties: token order), the exact leaf
-first, at most max_candidates; fields are scanned in query_by order with one shared set of already-produced tokens. The
-last-token refinement of the reference (popular fields of the previous token first) is not restated."""
+first, at most max_candidates; fields are scanned in query_by order with one shared set of already-produced tokens. For the
+last token of a multi-token query the reference first looks only at the fields that hold the previous token (most
+documents first) and only at leaves sharing a document with it (validate_and_add_leaf, src/art.cpp:1004-1046), then
+falls back to all fields; that is restated too."""
 from __future__ import annotations
 
 from typing import Dict, List
@@ -79,11 +81,18 @@ class TypoSearcher:
             return 0
         return min(self.num_typos, 1) if len(token) < self.min2 else min(self.num_typos, 2)
 
-    def field_candidates(self, f: int, token: str, cost: int, prefix_search: bool, unique_tokens: set) -> List[str]:
+    def ids_of(self, f: int, t: str):
+        fl, l = self.coll.flats[f], self.coll.vocabs[f][t]
+        return fl.ids[int(fl.list_off[l]):int(fl.list_off[l + 1])]
+
+    def field_candidates(self, f: int, token: str, cost: int, prefix_search: bool, unique_tokens: set, prev_token: str = "") -> List[str]:
         vocab = self.coll.vocabs[f]
         rank = self.freq[f] if self.token_order == FREQUENCY else self.max_score[f]
         exact = token if token in vocab else None
         found = [t for t in vocab if matches(token, t, cost, prefix_search) and t not in unique_tokens and t != exact]
+        if prev_token and prev_token in vocab:             # leaves that share a document with the previous token in this field
+            prev_ids = self.ids_of(f, prev_token)
+            found = [t for t in found if len(np.intersect1d(prev_ids, self.ids_of(f, t), assume_unique=True))]
         found.sort(key=lambda t: (-rank[t], t))
         for t in found:
             unique_tokens.add(t)
@@ -92,8 +101,24 @@ class TypoSearcher:
             unique_tokens.add(exact)
         return found[:self.max_cand]
 
-    def candidates(self, token: str, cost: int, prefix_search: bool, unique_tokens: set) -> List[str]:
+    def candidates(self, token: str, cost: int, prefix_search: bool, unique_tokens: set, prev_token: str = None):
+        """prev_token None: not the last token. Returns None when the last token has no field to look in (the reference
+        abandons this cost combination)."""
         out: List[str] = []
+        if prev_token is not None:
+            popular = sorted([f for f in range(self.F) if prev_token in self.coll.vocabs[f]], key=lambda f: -self.freq[f][prev_token])
+            if not popular:
+                return None
+            for f in popular:
+                out += self.field_candidates(f, token, cost, prefix_search, unique_tokens, prev_token)
+                if len(out) >= self.max_cand:
+                    return out
+            if self.F > 1 and len(out) < self.max_cand:
+                for f in range(self.F):
+                    out += self.field_candidates(f, token, cost, prefix_search, unique_tokens)
+                    if len(out) >= self.max_cand:
+                        break
+            return out
         for f in range(self.F):
             out += self.field_candidates(f, token, cost, prefix_search, unique_tokens)
             if len(out) >= self.max_cand:
@@ -148,6 +173,7 @@ class TypoSearcher:
             unique_tokens: set = set()
             cands = []
             restart = False
+            abandon = False
             for ti, (token, pref) in enumerate(qtokens):
                 key = token + str(costs[ti])
                 if key in cache:
@@ -155,7 +181,11 @@ class TypoSearcher:
                 else:
                     leaf_tokens = []
                     if costs[ti] <= self.num_typos:
-                        leaf_tokens = self.candidates(token, costs[ti], pref, unique_tokens)
+                        last_token = len(qtokens) > 1 and not dropped and ti == len(qtokens) - 1
+                        leaf_tokens = self.candidates(token, costs[ti], pref, unique_tokens, cands[-1][3][0] if last_token else None)
+                        if leaf_tokens is None:           # popular_field_ids.empty(): `break` out of the token loop
+                            abandon = True
+                            break
                         if leaf_tokens:
                             cache[key] = leaf_tokens
                 if leaf_tokens:
@@ -171,7 +201,7 @@ class TypoSearcher:
                         N *= len(c)
                     restart = True
                     break
-            if not restart and len(cands) == len(qtokens):
+            if not restart and not abandon and len(cands) == len(qtokens):
                 self.search_all_candidates(cands, dropped)
             if len(self.all_ids) >= self.typo_thr:
                 return

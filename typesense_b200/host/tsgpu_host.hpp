@@ -484,9 +484,18 @@ public:
     // vocabulary for tokens at exactly `cost` edits (or, for a prefix search, with such a prefix), orders them like the
     // leaves are ordered (document frequency or max_score of the default sorting field, descending), puts the exact
     // token first at cost 0, skips tokens another field already produced, keeps max_candidates.
+    // With `prev_token` (the last token of a multi-token query) only tokens that share a document with it in this field
+    // qualify — validate_and_add_leaf's or_iterator_t::contains_atleast_one (src/art.cpp:1004-1046).
     std::vector<std::string> fuzzy_candidates(uint32_t fid, const std::string& token, int cost, bool prefix_search,
-                                              std::set<std::string>& unique_tokens, const search_options& o) const {
+                                              std::set<std::string>& unique_tokens, const search_options& o,
+                                              const std::string& prev_token = std::string()) const {
         const vocab_t& v = vocabs[fid];
+        const uint32_t prev_l = prev_token.empty() ? TSGPU_NO_LIST : token_id(fid, prev_token);
+        auto shares_doc = [&](uint32_t l) {
+            uint64_t a = v.list_off[prev_l], ae = v.list_off[prev_l + 1], c = v.list_off[l], ce = v.list_off[l + 1];
+            while(a < ae && c < ce) { if(v.ids[a] == v.ids[c]) return true; if(v.ids[a] < v.ids[c]) a++; else c++; }
+            return false;
+        };
         const std::vector<int64_t>* scores = nullptr;
         auto sv = sort_values.find(default_sorting_field);
         if(sv != sort_values.end()) scores = &sv->second;
@@ -497,6 +506,7 @@ public:
             const std::string& t = v.tokens[l];
             if((has_exact && t == token) || unique_tokens.count(t) || v.list_off[l + 1] == v.list_off[l]) continue;
             if(!fuzzy_key_matches(token, t, cost, prefix_search)) continue;
+            if(prev_l != TSGPU_NO_LIST && !shares_doc(l)) continue;
             int64_t rank = (int64_t) (v.list_off[l + 1] - v.list_off[l]);
             if(o.token_order == search_options::MAX_SCORE) {
                 rank = INT64_MIN;
@@ -583,20 +593,48 @@ public:
             for(size_t i = query_tokens.size(); i-- > 0;) { costs[i] = token_to_costs[i][(size_t) (quot % (long long) token_to_costs[i].size())]; quot /= (long long) token_to_costs[i].size(); }
             std::set<std::string> unique_tokens;
             std::vector<tok_candidates> cands;
-            bool restart = false;
+            bool restart = false, abandon = false;
             for(size_t ti = 0; ti < query_tokens.size(); ti++) {
                 const std::string key = query_tokens[ti].value + std::to_string(costs[ti]);
                 std::vector<std::string> leaf_tokens;
                 auto hit = token_cost_cache.find(key);
                 if(hit != token_cost_cache.end()) leaf_tokens = hit->second;
-                else {
-                    for(auto& fn: the_fields) {
-                        if((uint32_t) costs[ti] > o.num_typos) continue;
-                        auto fl = fuzzy_candidates(field_ids.at(fn), query_tokens[ti].value, costs[ti], o.prefix && query_tokens[ti].is_prefix_searched, unique_tokens, o);
+                else if((uint32_t) costs[ti] <= o.num_typos) {
+                    const bool prefix_search = o.prefix && query_tokens[ti].is_prefix_searched;
+                    // A prefix/typo expansion of the LAST token prefers continuations of the previous token ("steve j" for
+                    // "steve jobs"): first only the fields holding the previous token's best candidate, most documents
+                    // first (popular_fields_of_token, src/index.cpp:5111-5141), and only tokens sharing a document with it
+                    const bool last_token = query_tokens.size() > 1 && dropped.empty() && ti + 1 == query_tokens.size();
+                    std::vector<std::string> scan = the_fields;
+                    std::string prev_token;
+                    if(last_token) {
+                        prev_token = cands.back().candidates[0];
+                        std::vector<std::pair<uint64_t, std::string>> pop;
+                        for(auto& fn: the_fields) {
+                            const uint32_t f = field_ids.at(fn), l = token_id(f, prev_token);
+                            if(l != TSGPU_NO_LIST) pop.push_back({vocabs[f].list_off[l + 1] - vocabs[f].list_off[l], fn});
+                        }
+                        std::stable_sort(pop.begin(), pop.end(), [](const auto& a, const auto& c2) { return a.first > c2.first; });
+                        scan.clear();
+                        for(auto& p2: pop) scan.push_back(p2.second);
+                        if(scan.empty()) { abandon = true; break; }
+                    }
+                    bool full = false;
+                    for(auto& fn: scan) {
+                        auto fl = fuzzy_candidates(field_ids.at(fn), query_tokens[ti].value, costs[ti], prefix_search, unique_tokens, o, prev_token);
                         if(fl.empty()) continue;
                         leaf_tokens.insert(leaf_tokens.end(), fl.begin(), fl.end());
                         token_cost_cache[key] = leaf_tokens;
-                        if(leaf_tokens.size() >= o.max_candidates) break;
+                        if(leaf_tokens.size() >= o.max_candidates) { full = true; break; }
+                    }
+                    if(last_token && !full && the_fields.size() > 1 && leaf_tokens.size() < o.max_candidates) {
+                        for(auto& fn: the_fields) {         // matching the previous token has failed: look at all fields
+                            auto fl = fuzzy_candidates(field_ids.at(fn), query_tokens[ti].value, costs[ti], prefix_search, unique_tokens, o);
+                            if(fl.empty()) continue;
+                            leaf_tokens.insert(leaf_tokens.end(), fl.begin(), fl.end());
+                            token_cost_cache[key] = leaf_tokens;
+                            if(leaf_tokens.size() >= o.max_candidates) break;
+                        }
                     }
                 }
                 if(!leaf_tokens.empty()) cands.push_back({query_tokens[ti], costs[ti], leaf_tokens});
@@ -609,7 +647,7 @@ public:
                     break;
                 }
             }
-            if(!restart && cands.size() == query_tokens.size()) {
+            if(!restart && !abandon && cands.size() == query_tokens.size()) {
                 auto op = search_all_candidates(cands, dropped, the_fields, sort_fields, topster_size, o, st);
                 if(!op.ok()) return op;
             }
