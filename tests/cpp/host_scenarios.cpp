@@ -349,6 +349,30 @@ static void relevance_scenarios() {
             CHECK(kvs[1].scores[0] == 1157451471575320601LL && kvs[2].scores[0] == 1157451471575320601LL && kvs[3].scores[0] == 1157451471575320601LL);
         }
     }
+    {   // RelevanceConsiderAllFields, test/collection_specific_more_test.cpp:895-952: literal score, weights {3,2,1} used as given
+        tsgpu::Index index(3);
+        build_plain(index, {"f1", "f2", "f3"}, {{{"alpha", "alpha", "alpha"}}, {{"alpha", "alpha", "beta"}}, {{"alpha", "beta", "gamma"}}});
+        tsgpu::search_options o = opt(2, true, 40);
+        o.query_by_weights = {3, 2, 1};
+        CHECK(index.search(tsgpu::tokenize_ascii("alpha"), {"f1", "f2", "f3"}, {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::seq_id, "", true}}, 0, 250, kvs, found, o).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 1, 2}));
+        if(kvs.size() == 3) {
+            CHECK(kvs[0].scores[0] == 578730123373578267LL);
+            for(int i = 0; i < 3; i++) CHECK(((kvs[i].scores[0] >> 11) & ((1LL << 48) - 1)) == 1108091342849LL && ((kvs[i].scores[0] >> 3) & 0xFF) == 3 && (kvs[i].scores[0] & 7) == 3 - i);
+        }
+    }
+    {   // WeightTakingPrecendeceOverMatch :2196-2237: max_weight layout, literal best_field_score / weight / fields_matched
+        tsgpu::Index index(2);
+        build_plain(index, {"brand", "title"}, {{{"Light Plus", "Healthy Mayo"}}, {{"Vegabond", "Healthy Light Mayo"}}});
+        tsgpu::search_options o = opt(2, true, 20);
+        o.text_match_type = TSGPU_MATCH_MAX_WEIGHT;
+        CHECK(index.search(tsgpu::tokenize_ascii("light mayo"), {"brand", "title"}, {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::seq_id, "", true}}, 5, 250, kvs, found, o).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{0, 1}));
+        if(kvs.size() == 2) {
+            CHECK(((kvs[0].scores[0] >> 3) & ((1LL << 48) - 1)) == 1108091338753LL && ((kvs[0].scores[0] >> 51) & 0xFF) == 15 && (kvs[0].scores[0] & 7) == 2);
+            CHECK(((kvs[1].scores[0] >> 3) & ((1LL << 48) - 1)) == 2211897868289LL && ((kvs[1].scores[0] >> 51) & 0xFF) == 14 && (kvs[1].scores[0] & 7) == 1);
+        }
+    }
     {   // text_match literals of test/collection_vector_search_test.cpp:5462-5496 (and test/union_test.cpp:810)
         tsgpu::Index index(4);
         build_plain(index, {"name"}, {{{"Nike running shoes for men"}}, {{"Nike running sneakers"}}, {{"adidas shoes"}}, {{"puma"}}});
@@ -414,6 +438,7 @@ struct SpecificCase {
     std::vector<uint32_t> weights;
     std::vector<uint32_t> expect;
     int token_order; size_t max_candidates; long found; bool head;
+    int flags, match_type;
 };
 static void specific_scenarios() {
     const std::vector<SpecificCase> cases = {
@@ -439,6 +464,10 @@ static void specific_scenarios() {
         tsgpu::search_options o = opt(c.num_typos, c.prefix, c.typo_thr, c.token_order ? tsgpu::search_options::MAX_SCORE : tsgpu::search_options::FREQUENCY);
         o.query_by_weights = c.weights;
         o.max_candidates = c.max_candidates;
+        o.prioritize_exact_match = (c.flags & TSGPU_FLAG_PRIORITIZE_EXACT_MATCH) != 0;
+        o.prioritize_token_position = (c.flags & TSGPU_FLAG_PRIORITIZE_TOKEN_POSITION) != 0;
+        o.prioritize_num_matching_fields = (c.flags & TSGPU_FLAG_PRIORITIZE_NUM_MATCHING_FIELDS) != 0;
+        o.text_match_type = c.match_type;
         std::vector<tsgpu::KV> kvs;
         size_t found = 0;
         CHECK(index.search(tsgpu::tokenize_ascii(c.query), c.fields, sort_fields, c.drop, 250, kvs, found, o).ok());

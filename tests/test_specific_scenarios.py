@@ -15,10 +15,15 @@ LONG = ("Central Arizona Project. - Hearing, Eighty-eighth Congress, Second Sess
 TD, T = ("title", "description"), ("title",)
 
 
-def o(num_typos, prefix, drop, typo_thr, weights=None, order=tf.FREQUENCY, max_candidates=4, found=None, head=False):
+E = S.FLAG_PRIORITIZE_EXACT_MATCH | S.FLAG_PRIORITIZE_NUM_MATCHING_FIELDS          # Collection::search defaults
+POS = E | S.FLAG_PRIORITIZE_TOKEN_POSITION
+
+
+def o(num_typos, prefix, drop, typo_thr, weights=None, order=tf.FREQUENCY, max_candidates=4, found=None, head=False, flags=E,
+      match_type=S.MATCH_MAX_SCORE):
     """found: also assert the found count; head: `expect` is only the head of the result list"""
     return dict(num_typos=num_typos, prefix=prefix, drop_tokens_threshold=drop, typo_tokens_threshold=typo_thr, weights=weights,
-                token_order=order, max_candidates=max_candidates, found=found, head=head)
+                token_order=order, max_candidates=max_candidates, found=found, head=head, flags=flags, match_type=match_type)
 
 
 D_CHARGER = [{"title": "Fast Electric Charger", "description": "A product you should buy.", "points": 100},
@@ -47,8 +52,55 @@ D_JOHNS = [{"location": l, "name": n, "points": i} for i, (n, l) in enumerate(zi
     ["Switzerland", "Seoul", "Sydney", "Surat", "Stockholm", "Salem", "Sevilla"]))]
 MORE = "test/collection_specific_more_test.cpp "
 
+D_POS = [{"title": t, "points": i} for i, t in enumerate(["Alpha Beta Gamma", "Omega Alpha Theta", "Omega Theta Alpha", "Indigo Omega Theta Alpha"])]
+D_POS_ARR = [{"tags": ["alpha foo", "gamma", "beta alpha"], "points": 100}, {"tags": ["omega", "omega beta alpha"], "points": 200}]
+TAT = ("title", "author", "tags")
+MW = S.MATCH_MAX_WEIGHT
+
 # (reference test, fields, docs, query, options, expected ids)
 CASES = [
+    (MORE + "ArrayElementMatchShouldBeMoreImportantThanTotalMatch :211", TAT,
+     [{"title": "Harry Potter and the Prisoner of Azkaban", "author": "Rowling", "tags": ["harry", ""], "points": 0},
+      {"title": "Fantastic beasts and where to find them", "author": "Rowling", "tags": ["harry", "potter", "prisoner", "azkaban", "beasts", "guide", "rowling"], "points": 0},
+      {"title": "Fantastic beasts and where to find them", "author": "Rowling", "tags": ["harry potter", "prisoner azkaban", "beasts", "guide", "rowling"], "points": 0}],
+     "harry potter rowling prisoner azkaban", o(2, True, 1, 5), [0, 2, 1]),
+    (MORE + "ArrayMatchAcrossElementsMustNotMatter :253", TAT,
+     [{"title": "Por do sol immateur", "author": "Vermelho", "tags": ["por do sol", "immateur", "gemsor", "praia", "sol", "vermelho", "suyay"], "points": 0},
+      {"title": "Sunset Rising", "author": "Vermelho", "tags": ["sunset", "por do sol", "praia", "somao", "vermelho"], "points": 0}],
+     "praia por sol vermelho", o(2, True, 1, 5), [0, 1]),
+    (MORE + "MatchedSegmentMoreImportantThanTotalMatches :287", ("title", "author"),
+     [{"title": "One Two Three Four Five Six Seven Eight Nine Ten Eleven Twelve Thirteen Fourteen", "author": "Rowling", "points": 0},
+      {"title": "One Four Five Six Seven Eight Nine Ten Eleven Twelve Thirteen Fourteen Three Rowling", "author": "Two", "points": 0},
+      {"title": "One Three Four Five Six Seven Eight Nine Ten Eleven Twelve Thirteen Fourteen Two Rowling", "author": "Foo", "points": 0}],
+     "one two three rowling", o(2, True, 1, 5), [0, 2, 1]),
+    (MORE + "VerbatimMatchNotOnPartialTokenMatch :326", ("tags",),
+     [{"title": "Thirteen Fourteen", "tags": ["foo", "bar", "Hundred", "Thirteen Fourteen"], "points": 0},
+      {"title": "One Eleven Thirteen Fourteen Three", "tags": ["foo", "bar", "Hundred", "One Eleven Thirteen Fourteen Three"], "points": 0}],
+     "hundred thirteen fourteen", o(2, True, 1, 5), [0, 1]),
+    (MORE + "WrongTypoCorrection :527", T, [{"title": "Gold plated arvin", "points": 0}], "earrings", o(2, True, 1, 5), []),
+    (MORE + "PositionalTokenRanking :549 (prioritize_token_position)", T, D_POS, "alpha", o(0, True, 1, 10, order=tf.MAX_SCORE, flags=POS), [0, 1, 2, 3]),
+    (MORE + "PositionalTokenRanking :549", T, D_POS, "alpha", o(0, True, 1, 10, order=tf.MAX_SCORE), [3, 2, 1, 0]),
+    (MORE + "PositionalTokenRanking :549 (two tokens)", T, D_POS, "theta alpha", o(0, True, 1, 10, order=tf.MAX_SCORE), [3, 2, 1]),
+    (MORE + "PositionalTokenRanking :549 (two tokens, prioritize_token_position)", T, D_POS, "theta alpha", o(0, True, 1, 10, order=tf.MAX_SCORE, flags=POS), [2, 1, 3]),
+    (MORE + "PositionalTokenRankingWithArray :629", ("tags",), D_POS_ARR, "alpha", o(0, True, 1, 10, order=tf.MAX_SCORE), [1, 0]),
+    (MORE + "PositionalTokenRankingWithArray :629 (prioritize_token_position)", ("tags",), D_POS_ARR, "alpha", o(0, True, 1, 10, order=tf.MAX_SCORE, flags=POS), [0, 1]),
+    (MORE + "CrossFieldWeightIsNotAugmentated :954", ("type", "title"),
+     [{"title": "Nike Shoerack", "type": "shoe_rack", "points": 0}, {"title": "Nike Air Force 1", "type": "shoe", "points": 0}],
+     "nike shoe", o(2, True, 0, 40, [5, 1]), [0, 1]),
+    (MORE + "ConsiderDroppedTokensDuringTextMatchScoring :1809 (max_weight)", ("brand", "name"),
+     [{"brand": "Neutrogena", "name": "Neutrogena Ultra Sheer Oil-Free Face Serum With Vitamin E + SPF 60", "points": 0},
+      {"brand": "Neutrogena", "name": "Neutrogena Ultra Sheer Liquid Sunscreen SPF 70", "points": 0}],
+     "Neutrogena Ultra Sheer Moisturizing Face Serum", o(2, True, 5, 20, [3, 2], match_type=MW), [0, 1]),
+    # the reference's tokenizer folds the accent of "Avène" (ICU); the ASCII harness is given the folded form
+    (MORE + "ConsiderDroppedTokensDuringTextMatchScoring2 :1842 (max_weight)", ("name",),
+     [{"name": "Elizabeth Arden 5th Avenue Eau de Parfum 125ml", "points": 0}, {"name": "Avene Sun Very High Protection Mineral Cream SPF50+ 50ml", "points": 0}],
+     "avene eau mineral", o(2, True, 5, 20, [3], match_type=MW), [1, 0]),
+    (MORE + "DisableFieldCountForScoring :1872 (prioritize_num_matching_fields)", ("name", "brand"),
+     [{"name": "Alpha beta gamma", "brand": "Alpha beta gamma", "points": 0}, {"name": "Alpha beta gamma", "brand": "Theta", "points": 0}],
+     "beta", o(2, True, 5, 20, [3, 3]), [0, 1]),
+    (MORE + "WeightTakingPrecendeceOverMatch :2196 (max_weight)", ("brand", "title"),
+     [{"title": "Healthy Mayo", "brand": "Light Plus", "points": 0}, {"title": "Healthy Light Mayo", "brand": "Vegabond", "points": 0}],
+     "light mayo", o(2, True, 5, 20, match_type=MW), [0, 1]),
     # prefix expansion of the last token looks at leaves sharing a document with the previous token first
     (MORE + "PrefixExpansionOnSingleField :93", T, D_NAMES, "mark j", o(0, True, 1, 1, order=tf.MAX_SCORE), [0]),
     (MORE + "PrefixExpansionOnSingleField :93 (2)", T, D_NAMES, "mark b", o(0, True, 1, 1, order=tf.MAX_SCORE), [9, 8]),
@@ -117,17 +169,58 @@ def run_cases(make_backend):
             assert found == found_expect and len(got) == found_expect, (name, found)
 
 
+def literal_score_cases(make_backend):
+    """text_match_info literals of the reference: the whole 64-bit score and its fields, both match types."""
+    # RelevanceConsiderAllFields :895-952 — max_score layout [query_len:4 @59][best_field_score:48 @11][weight:8 @3][fields:3 @0]
+    docs = [{"f1": "alpha", "f2": "alpha", "f3": "alpha", "points": 0}, {"f1": "alpha", "f2": "alpha", "f3": "beta", "points": 0},
+            {"f1": "alpha", "f2": "beta", "f3": "gamma", "points": 0}]
+    coll = refflow.Collection(docs, ("f1", "f2", "f3"))
+    backend, close = make_backend(coll)
+    s = tf.TypoSearcher(backend, coll, SORT, field_weights=ranked_weights([3, 2, 1]), num_typos=2, prefix=True, drop_tokens_threshold=0, typo_tokens_threshold=40)
+    got, _ = s.search("alpha")
+    close()
+    assert got == [0, 1, 2] and s.best[0][0] == 578730123373578267
+    for k, fields_matched in ((0, 3), (1, 2), (2, 1)):
+        v = s.best[k][0]
+        assert (v >> 11) & ((1 << 48) - 1) == 1108091342849 and (v >> 3) & 0xFF == 3 and v & 7 == fields_matched and v >> 59 == 1
+    # WeightTakingPrecendeceOverMatch :2196-2237 — max_weight layout [query_len:4 @59][weight:8 @51][best_field_score:48 @3][fields:3 @0]
+    docs = [{"title": "Healthy Mayo", "brand": "Light Plus", "points": 0}, {"title": "Healthy Light Mayo", "brand": "Vegabond", "points": 0}]
+    coll = refflow.Collection(docs, ("brand", "title"))
+    backend, close = make_backend(coll)
+    s = tf.TypoSearcher(backend, coll, SORT, num_typos=2, prefix=True, drop_tokens_threshold=5, typo_tokens_threshold=20, match_type=MW)
+    got, _ = s.search("light mayo")
+    close()
+    assert got == [0, 1]
+    for k, best, weight, fields_matched in ((0, 1108091338753, 15, 2), (1, 2211897868289, 14, 1)):
+        v = s.best[k][0]
+        assert (v >> 3) & ((1 << 48) - 1) == best and (v >> 51) & 0xFF == weight and v & 7 == fields_matched and v >> 59 == 2
+    # DisableFieldCountForScoring :1872-1926: equal scores without prioritize_num_matching_fields
+    docs = [{"name": "Alpha beta gamma", "brand": "Alpha beta gamma", "points": 0}, {"name": "Alpha beta gamma", "brand": "Theta", "points": 0}]
+    coll = refflow.Collection(docs, ("name", "brand"))
+    backend, close = make_backend(coll)
+    s = tf.TypoSearcher(backend, coll, SORT, field_weights=[3, 3], num_typos=2, prefix=True, drop_tokens_threshold=5, typo_tokens_threshold=20,
+                        flags=S.FLAG_PRIORITIZE_EXACT_MATCH)
+    s.search("beta")
+    assert s.best[0][0] == s.best[1][0]
+    s = tf.TypoSearcher(backend, coll, SORT, field_weights=[3, 3], num_typos=2, prefix=True, drop_tokens_threshold=5, typo_tokens_threshold=20)
+    s.search("beta")
+    close()
+    assert s.best[0][0] > s.best[1][0]
+
+
 def test_specific_scenarios_oracle():
     def mk(coll):
         oi = ol.OracleIndex(coll.n_docs, coll.flats, [coll.points])
         return (lambda b, k: oi.keyword_search(b, k)), (lambda: None)
     run_cases(mk)
+    literal_score_cases(mk)
 
 
 def test_specific_scenarios_device_functions():
     import test_hostsim as th
     hs = th.hs.__wrapped__()
     run_cases(lambda coll: (th.hostsim_backend(hs, coll), (lambda: None)))
+    literal_score_cases(lambda coll: (th.hostsim_backend(hs, coll), (lambda: None)))
 
 
 @pytest.mark.gpu
@@ -141,3 +234,4 @@ def test_specific_scenarios_gpu():
         gi.load_sort_column(coll.points)
         return (lambda b, k: gi.keyword_search(b, k)), gi.close
     run_cases(mk)
+    literal_score_cases(mk)

@@ -58,7 +58,7 @@ class TypoSearcher:
     def __init__(self, backend, coll: refflow.Collection, sort, num_typos: int = 2, token_order: int = FREQUENCY, prefix: bool = True,
                  drop_tokens_threshold: int = 1, typo_tokens_threshold: int = 1, max_candidates: int = 4, min_len_1typo: int = 4,
                  min_len_2typo: int = 7, topster: int = 250, field_weights=None,
-                 flags: int = S.FLAG_PRIORITIZE_EXACT_MATCH | S.FLAG_PRIORITIZE_NUM_MATCHING_FIELDS):
+                 flags: int = S.FLAG_PRIORITIZE_EXACT_MATCH | S.FLAG_PRIORITIZE_NUM_MATCHING_FIELDS, match_type: int = S.MATCH_MAX_SCORE):
         self.backend, self.coll, self.sort = backend, coll, sort
         self.num_typos, self.token_order, self.prefix = num_typos, token_order, prefix
         self.drop_thr, self.typo_thr, self.max_cand = drop_tokens_threshold, typo_tokens_threshold, max_candidates
@@ -67,6 +67,7 @@ class TypoSearcher:
         self.F = len(coll.fields)
         self.weights = list(field_weights) if field_weights else [max(0, 15 - f) for f in range(self.F)]
         self.flags = flags
+        self.match_type = match_type
         self.freq, self.max_score = [], []
         for vocab, fl in zip(coll.vocabs, coll.flats):
             df = np.diff(fl.list_off.astype(np.int64))
@@ -231,7 +232,7 @@ class TypoSearcher:
             combos.append(S.Combo(rows, len(sugg), total_cost=total_cost))
         if not combos:
             return
-        query = S.Query(combos, topk=self.K, sort=self.sort, num_query_tokens=len(cands), field_weight=self.weights, flags=self.flags)
+        query = S.Query(combos, topk=self.K, sort=self.sort, num_query_tokens=len(cands), field_weight=self.weights, flags=self.flags, match_type=self.match_type)
         kv, cnt, found = self.backend(S.KwBatch([query], list(range(self.F))), self.K)
         for i in range(int(cnt[0])):
             key = int(kv["key"][0, i])

@@ -122,6 +122,7 @@ struct search_options {
     bool prioritize_exact_match = true;
     bool prioritize_token_position = false;
     bool prioritize_num_matching_fields = true;
+    int text_match_type = TSGPU_MATCH_MAX_SCORE;      // text_match_type_t: max_score | max_weight | sum_score
     std::vector<std::string> exclude_tokens;
     std::vector<std::vector<std::string>> exclude_phrases;   // -"a b c": phrase matches are excluded (Index::handle_exclusion)
     std::vector<std::vector<std::string>> phrases;           // "a b c": results must hold every phrase (Index::do_phrase_search)
@@ -319,7 +320,8 @@ public:
                                       const std::vector<uint32_t>& filter_ids, bool filter_by_provided,
                                       const std::vector<uint32_t>& excluded_result_ids, size_t topster_size,
                                       bool prioritize_exact_match, host_topster_t& topster, size_t& num_found,
-                                      bool prioritize_token_position = false, bool prioritize_num_matching_fields = true) {
+                                      bool prioritize_token_position = false, bool prioritize_num_matching_fields = true,
+                                      int text_match_type = TSGPU_MATCH_MAX_SCORE) {
         const uint32_t F = (uint32_t) the_fields.size();
         std::vector<uint32_t> fids(F);
         for(uint32_t f = 0; f < F; f++) fids[f] = field_ids.at(the_fields[f]);
@@ -350,7 +352,7 @@ public:
         uint8_t q_flags = (uint8_t) ((prioritize_exact_match ? TSGPU_FLAG_PRIORITIZE_EXACT_MATCH : 0) |
                                      (prioritize_token_position ? TSGPU_FLAG_PRIORITIZE_TOKEN_POSITION : 0) |
                                      (prioritize_num_matching_fields ? TSGPU_FLAG_PRIORITIZE_NUM_MATCHING_FIELDS : 0));
-        uint8_t q_match_type = TSGPU_MATCH_MAX_SCORE;
+        uint8_t q_match_type = (uint8_t) text_match_type;
         uint8_t q_nqt = (uint8_t) n_query_tokens;
         uint64_t filter_off[2] = {0, filter_ids.size()};
         const uint32_t zero = 0;
@@ -566,7 +568,7 @@ public:
         host_topster_t round(topster_size);
         size_t nf = 0;
         auto op = search_across_fields(suggestions, dropped.size(), costs, the_fields, st.weights, sort_fields, st.filter_ids, st.filter_by_provided, st.excluded, topster_size,
-                                       o.prioritize_exact_match, round, nf, o.prioritize_token_position, o.prioritize_num_matching_fields);
+                                       o.prioritize_exact_match, round, nf, o.prioritize_token_position, o.prioritize_num_matching_fields, o.text_match_type);
         if(!op.ok()) return op;
         for(auto& kv: round.sort()) { st.topster.add(kv); st.all_result_ids.insert((uint32_t) kv.key); }
         return Option<bool>(true);
