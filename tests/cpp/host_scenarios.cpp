@@ -438,7 +438,8 @@ struct SpecificCase {
     std::vector<uint32_t> weights;
     std::vector<uint32_t> expect;
     int token_order; size_t max_candidates; long found; bool head;
-    int flags, match_type;
+    int flags, match_type, drop_mode;
+    size_t both_sides_limit;
 };
 static void specific_scenarios() {
     const std::vector<SpecificCase> cases = {
@@ -468,6 +469,8 @@ static void specific_scenarios() {
         o.prioritize_token_position = (c.flags & TSGPU_FLAG_PRIORITIZE_TOKEN_POSITION) != 0;
         o.prioritize_num_matching_fields = (c.flags & TSGPU_FLAG_PRIORITIZE_NUM_MATCHING_FIELDS) != 0;
         o.text_match_type = c.match_type;
+        o.drop_tokens_mode = c.drop_mode == 0 ? tsgpu::search_options::right_to_left : c.drop_mode == 1 ? tsgpu::search_options::left_to_right : tsgpu::search_options::both_sides;
+        o.drop_both_sides_token_limit = c.both_sides_limit;
         std::vector<tsgpu::KV> kvs;
         size_t found = 0;
         CHECK(index.search(tsgpu::tokenize_ascii(c.query), c.fields, sort_fields, c.drop, 250, kvs, found, o).ok());

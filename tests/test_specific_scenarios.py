@@ -20,10 +20,11 @@ POS = E | S.FLAG_PRIORITIZE_TOKEN_POSITION
 
 
 def o(num_typos, prefix, drop, typo_thr, weights=None, order=tf.FREQUENCY, max_candidates=4, found=None, head=False, flags=E,
-      match_type=S.MATCH_MAX_SCORE):
+      match_type=S.MATCH_MAX_SCORE, drop_mode="right_to_left"):
     """found: also assert the found count; head: `expect` is only the head of the result list"""
     return dict(num_typos=num_typos, prefix=prefix, drop_tokens_threshold=drop, typo_tokens_threshold=typo_thr, weights=weights,
-                token_order=order, max_candidates=max_candidates, found=found, head=head, flags=flags, match_type=match_type)
+                token_order=order, max_candidates=max_candidates, found=found, head=head, flags=flags, match_type=match_type,
+                drop_tokens_mode=drop_mode)
 
 
 D_CHARGER = [{"title": "Fast Electric Charger", "description": "A product you should buy.", "points": 100},
@@ -57,8 +58,14 @@ D_POS_ARR = [{"tags": ["alpha foo", "gamma", "beta alpha"], "points": 100}, {"ta
 TAT = ("title", "author", "tags")
 MW = S.MATCH_MAX_WEIGHT
 
+D_AB = [{"title": "alpha beta", "points": 0}, {"title": "beta gamma", "points": 0}]
+
 # (reference test, fields, docs, query, options, expected ids)
 CASES = [
+    (MORE + "DropTokensLeftToRightFirst :2409 (left_to_right)", T, D_AB, "alpha beta gamma", o(0, False, 1, 20, drop_mode="left_to_right"), [1]),
+    (MORE + "DropTokensLeftToRightFirst :2409 (right_to_left)", T, D_AB, "alpha beta gamma", o(0, False, 1, 20), [0]),
+    (MORE + "DropTokensLeftToRightFirst :2409 (both_sides:3)", T, D_AB, "alpha gamma", o(0, False, 1, 20, drop_mode="both_sides:3", found=2, head=True), []),
+    (MORE + "DropTokensLeftToRightFirst :2409 (both_sides:1)", T, D_AB, "alpha gamma", o(0, False, 1, 20, drop_mode="both_sides:1"), [0]),
     (MORE + "ArrayElementMatchShouldBeMoreImportantThanTotalMatch :211", TAT,
      [{"title": "Harry Potter and the Prisoner of Azkaban", "author": "Rowling", "tags": ["harry", ""], "points": 0},
       {"title": "Fantastic beasts and where to find them", "author": "Rowling", "tags": ["harry", "potter", "prisoner", "azkaban", "beasts", "guide", "rowling"], "points": 0},

@@ -58,7 +58,8 @@ class TypoSearcher:
     def __init__(self, backend, coll: refflow.Collection, sort, num_typos: int = 2, token_order: int = FREQUENCY, prefix: bool = True,
                  drop_tokens_threshold: int = 1, typo_tokens_threshold: int = 1, max_candidates: int = 4, min_len_1typo: int = 4,
                  min_len_2typo: int = 7, topster: int = 250, field_weights=None,
-                 flags: int = S.FLAG_PRIORITIZE_EXACT_MATCH | S.FLAG_PRIORITIZE_NUM_MATCHING_FIELDS, match_type: int = S.MATCH_MAX_SCORE):
+                 flags: int = S.FLAG_PRIORITIZE_EXACT_MATCH | S.FLAG_PRIORITIZE_NUM_MATCHING_FIELDS, match_type: int = S.MATCH_MAX_SCORE,
+                 drop_tokens_mode: str = "right_to_left"):
         self.backend, self.coll, self.sort = backend, coll, sort
         self.num_typos, self.token_order, self.prefix = num_typos, token_order, prefix
         self.drop_thr, self.typo_thr, self.max_cand = drop_tokens_threshold, typo_tokens_threshold, max_candidates
@@ -68,6 +69,7 @@ class TypoSearcher:
         self.weights = list(field_weights) if field_weights else [max(0, 15 - f) for f in range(self.F)]
         self.flags = flags
         self.match_type = match_type
+        self.drop_mode = drop_tokens_mode          # right_to_left | left_to_right | both_sides:N (src/index.cpp:3920-4017)
         self.freq, self.max_score = [], []
         for vocab, fl in zip(coll.vocabs, coll.flats):
             df = np.diff(fl.list_off.astype(np.int64))
@@ -135,12 +137,20 @@ class TypoSearcher:
         self.fuzzy(list(zip(tokens, is_prefix)), [])
         n = min(len(tokens), 20)
         if len(self.all_ids) < self.drop_thr:
-            n_dropped, dirs_done, rtl = 0, 0, True
-            while len(self.all_ids) < self.drop_thr:
+            n_dropped, dirs_done = 0, 0
+            direction, both = self.drop_mode, False
+            if direction.startswith("both_sides"):
+                if n <= int(direction.split(":")[1]):
+                    both = True                      # every truncation of both directions runs, whatever the threshold
+                    direction = "both_sides"
+                else:
+                    direction = "right_to_left"
+            while len(self.all_ids) < self.drop_thr or both:
                 if n_dropped >= n - 1:
-                    rtl = not rtl
+                    direction = "left_to_right" if direction == "right_to_left" else "right_to_left"
                     n_dropped = 0
                     dirs_done += 1
+                rtl = direction == "right_to_left"
                 if n > 1 and dirs_done < 2:
                     toks = list(zip(tokens, is_prefix))
                     if rtl:

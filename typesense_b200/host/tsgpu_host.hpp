@@ -134,6 +134,10 @@ struct search_options {
     size_t typo_tokens_threshold = 1;            // Index::TYPO_TOKENS_THRESHOLD
     size_t max_candidates = 4;
     size_t min_len_1typo = 4, min_len_2typo = 7;
+    // drop_tokens_mode (src/index.cpp:3920-3945): which end loses tokens first; both_sides runs every truncation of both
+    // directions when the query has at most `drop_both_sides_token_limit` tokens
+    enum drop_mode_t { right_to_left, left_to_right, both_sides } drop_tokens_mode = right_to_left;
+    size_t drop_both_sides_token_limit = 0;
 };
 
 // Incremental optimal-string-alignment rows as src/art.cpp:1412-1433 computes them while it walks a key: rows[i][col] =
@@ -685,9 +689,18 @@ public:
         const size_t n = std::min<size_t>(tokens.size(), 20);
         if(st.all_result_ids.size() < drop_tokens_threshold) {
             size_t num_tokens_dropped = 0, total_dirs_done = 0;
-            bool right_to_left = true;
-            while(st.all_result_ids.size() < drop_tokens_threshold) {
-                if(num_tokens_dropped >= n - 1) { right_to_left = !right_to_left; num_tokens_dropped = 0; total_dirs_done++; }
+            auto curr_direction = opts.drop_tokens_mode;
+            bool drop_both_sides = false;
+            if(curr_direction == search_options::both_sides) {
+                if(n <= opts.drop_both_sides_token_limit) drop_both_sides = true;
+                else curr_direction = search_options::right_to_left;
+            }
+            while(st.all_result_ids.size() < drop_tokens_threshold || drop_both_sides) {
+                if(num_tokens_dropped >= n - 1) {
+                    curr_direction = curr_direction == search_options::right_to_left ? search_options::left_to_right : search_options::right_to_left;
+                    num_tokens_dropped = 0; total_dirs_done++;
+                }
+                const bool right_to_left = curr_direction == search_options::right_to_left;
                 if(n > 1 && total_dirs_done < 2) {
                     std::vector<query_token> trunc;
                     std::vector<std::string> dropped;
