@@ -482,6 +482,50 @@ static void specific_scenarios() {
     }
 }
 
+// test/collection_synonyms_test.cpp scenarios (table generated from tests/test_synonym_scenarios.py)
+struct SynonymCase {
+    const char* name;
+    std::vector<std::string> fields;
+    std::vector<std::vector<std::string>> docs;       // [doc][field]
+    std::vector<long> points;
+    const char* query;
+    std::vector<std::vector<std::string>> synonyms;
+    uint32_t num_typos; bool prefix; size_t drop, typo_thr; bool demote;
+    std::vector<uint32_t> expect;
+    const char* relation;      // "", "eq", "ne", "gt": first two text_match values
+};
+static void synonym_scenarios() {
+    const std::vector<SynonymCase> cases = {
+#include "synonym_cases.inc"
+    };
+    const std::vector<tsgpu::sort_by> sort_fields = {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::numeric, "points", true}};
+    for(auto& c: cases) {
+        tsgpu::Index index((uint32_t) c.docs.size());
+        for(size_t f = 0; f < c.fields.size(); f++) {
+            tsgpu::field_mirror_t m;
+            for(uint32_t d = 0; d < c.docs.size(); d++) m.index_plain_string(d, tsgpu::tokenize_ascii(c.docs[d][f]));
+            CHECK(index.add_field(c.fields[f], m).ok());
+        }
+        std::unordered_map<uint32_t, int64_t> points;
+        for(uint32_t d = 0; d < c.points.size(); d++) points[d] = c.points[d];
+        CHECK(index.add_sort_field("points", points).ok());
+        tsgpu::search_options o = opt(c.num_typos, c.prefix, c.typo_thr);
+        o.synonyms = c.synonyms;
+        o.demote_synonym_match = c.demote;
+        std::vector<tsgpu::KV> kvs;
+        size_t found = 0;
+        CHECK(index.search(tsgpu::tokenize_ascii(c.query), c.fields, sort_fields, c.drop, 250, kvs, found, o).ok());
+        const auto got = keys_of(kvs);
+        if(got != c.expect) { printf("synonym case %s: got", c.name); for(auto k: got) printf(" %u", k); printf("\n"); }
+        CHECK(got == c.expect && found == c.expect.size());
+        const std::string rel = c.relation;
+        if(!rel.empty() && kvs.size() >= 2) {
+            const int64_t a = kvs[0].scores[0], b = kvs[1].scores[0];
+            CHECK(rel == "eq" ? a == b : rel == "ne" ? a != b : a > b);
+        }
+    }
+}
+
 int main(int argc, char** argv) {
     if(tsgpu_device_count() == 0) { printf("no CUDA device: nothing to run (the library has no CPU path)\n"); return 99; }
     posting_list_intersection_basics();
@@ -492,6 +536,7 @@ int main(int argc, char** argv) {
     relevance_scenarios();
     specific_scenarios();
     phrase_scenarios();
+    synonym_scenarios();
     printf("%s (%d failed checks)\n", failures ? "FAILED" : "PASSED", failures);
     return failures;
 }

@@ -128,13 +128,41 @@ class TypoSearcher:
                 break
         return out
 
-    def search(self, q: str):
+    def search(self, q: str, synonyms=(), demote_synonym_match: bool = False):
+        """synonyms: token lists the SynonymIndex resolved for the query (host work; given as input here)."""
         tokens = refflow.tokenize(q)
         self.best: Dict[int, tuple] = {}
         self.all_ids = set()
         self.query_hashes = set()
+        syn_lists = [[t for w in syn for t in refflow.tokenize(w)] if isinstance(syn, (list, tuple)) else refflow.tokenize(syn) for syn in synonyms]
+        # syn_orig_num_tokens (src/index.cpp:3780-3828): -1 without synonyms, else the longest of the query and its synonyms
+        self.syn_orig = max([len(tokens)] + [len(x) for x in syn_lists]) if syn_lists else -1
+        self.orig_num = len(tokens)
+        self.demote = demote_synonym_match
+        self.is_syn = False
+        all_queries = [tokens] + syn_lists
         is_prefix = [self.prefix and i == len(tokens) - 1 for i in range(len(tokens))]
         self.fuzzy(list(zip(tokens, is_prefix)), [])
+        # do_synonym_search (src/index.cpp:6088-6142): every synonym as its own query, no typos, typo_tokens_threshold 0
+        saved = (self.num_typos, self.typo_thr)
+        for syn in syn_lists:
+            self.query_hashes = set()
+            self.is_syn = True
+            self.num_typos, self.typo_thr = 0, 0
+            self.fuzzy([(t, self.prefix and i == len(syn) - 1) for i, t in enumerate(syn)], [])
+        self.num_typos, self.typo_thr = saved
+        self.is_syn = False
+        for qi, toks_q in enumerate(all_queries):
+            self.drop_tokens_rounds(toks_q, qi > 0)
+        order = sorted(self.best.items(), key=lambda kv_: (kv_[1], kv_[0]), reverse=True)
+        return [k for k, _ in order], len(self.all_ids)
+
+    def drop_tokens_rounds(self, tokens, is_synonym_variant):
+        is_prefix = [self.prefix and i == len(tokens) - 1 for i in range(len(tokens))]
+        # the drop-token rounds of a synonym variant run like an ordinary query (syn_orig_num_tokens -1, src/index.cpp:4010)
+        saved_syn = self.syn_orig
+        self.syn_orig = -1
+        self.orig_num = len(tokens)
         n = min(len(tokens), 20)
         if len(self.all_ids) < self.drop_thr:
             n_dropped, dirs_done = 0, 0
@@ -160,11 +188,11 @@ class TypoSearcher:
                         st = n_dropped + 1
                         trunc, dropped = toks[st:n], toks[:st]
                     n_dropped += 1
+                    self.orig_num = len(trunc)
                     self.fuzzy(trunc, [t for t, _ in dropped])
                 else:
                     break
-        order = sorted(self.best.items(), key=lambda kv_: (kv_[1], kv_[0]), reverse=True)
-        return [k for k, _ in order], len(self.all_ids)
+        self.syn_orig = saved_syn
 
     # ---- Index::fuzzy_search_fields
     def fuzzy(self, qtokens, dropped: List[str]):
@@ -239,7 +267,8 @@ class TypoSearcher:
                 continue
             self.query_hashes.add(h)
             rows = [[v.get(t, S.NO_LIST) for v in vocabs] for t in sugg] + [[v.get(t, S.NO_LIST) for v in vocabs] for t in dropped]
-            combos.append(S.Combo(rows, len(sugg), total_cost=total_cost))
+            combos.append(S.Combo(rows, len(sugg), total_cost=total_cost, syn_orig_num_tokens=self.syn_orig, orig_num_tokens=self.orig_num,
+                                  flags=(S.CFLAG_SYNONYM if self.is_syn else 0) | (S.CFLAG_DEMOTE_SYNONYM if self.demote else 0)))
         if not combos:
             return
         query = S.Query(combos, topk=self.K, sort=self.sort, num_query_tokens=len(cands), field_weight=self.weights, flags=self.flags, match_type=self.match_type)

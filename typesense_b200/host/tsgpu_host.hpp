@@ -124,6 +124,10 @@ struct search_options {
     bool prioritize_num_matching_fields = true;
     int text_match_type = TSGPU_MATCH_MAX_SCORE;      // text_match_type_t: max_score | max_weight | sum_score
     std::vector<std::string> exclude_tokens;
+    // synonym variants of the query, already resolved by the SynonymIndex (host work): each runs as a query of its own
+    // (Index::do_synonym_search) and rescales its text match against the root query's token count
+    std::vector<std::vector<std::string>> synonyms;
+    bool demote_synonym_match = false;
     std::vector<std::vector<std::string>> exclude_phrases;   // -"a b c": phrase matches are excluded (Index::handle_exclusion)
     std::vector<std::vector<std::string>> phrases;           // "a b c": results must hold every phrase (Index::do_phrase_search)
     std::vector<uint32_t> query_by_weights;      // empty: 15, 14, ... by field order
@@ -325,7 +329,8 @@ public:
                                       const std::vector<uint32_t>& excluded_result_ids, size_t topster_size,
                                       bool prioritize_exact_match, host_topster_t& topster, size_t& num_found,
                                       bool prioritize_token_position = false, bool prioritize_num_matching_fields = true,
-                                      int text_match_type = TSGPU_MATCH_MAX_SCORE) {
+                                      int text_match_type = TSGPU_MATCH_MAX_SCORE, int syn_orig_num_tokens = -1, int orig_num_tokens = -1,
+                                      bool is_synonym_query = false, bool demote_synonym_match = false) {
         const uint32_t F = (uint32_t) the_fields.size();
         std::vector<uint32_t> fids(F);
         for(uint32_t f = 0; f < F; f++) fids[f] = field_ids.at(the_fields[f]);
@@ -367,6 +372,9 @@ public:
         b.q_sort_type = sort_type; b.q_sort_col = sort_col; b.q_sort_order = sort_order; b.q_sort_missing_first = missing_first;
         b.q_flags = &q_flags; b.q_match_type = &q_match_type; b.q_num_query_tokens = &q_nqt; b.q_field_weight = field_weights.data();
         b.c_tok_off = c_tok_off.data(); b.c_total_cost = c_cost.data(); b.c_n_required = c_nreq.data();
+        const std::vector<int32_t> c_syn(query_suggestions.size(), syn_orig_num_tokens), c_orig(query_suggestions.size(), orig_num_tokens);
+        const std::vector<uint8_t> c_flags(query_suggestions.size(), (uint8_t) ((is_synonym_query ? TSGPU_CFLAG_SYNONYM : 0) | (demote_synonym_match ? TSGPU_CFLAG_DEMOTE_SYNONYM : 0)));
+        b.c_syn_orig_num_tokens = c_syn.data(); b.c_orig_num_tokens = c_orig.data(); b.c_flags = c_flags.data();
         b.t_list = t_list.empty() ? &zero : t_list.data();
         b.filter_off = filter_off; b.filter_ids = filter_ids.empty() ? &zero : filter_ids.data();
         std::vector<KV> kvs(q_topk);
@@ -538,6 +546,8 @@ public:
         std::vector<uint32_t> filter_ids;      // phrase ids (do_phrase_search) restricting the keyword search
         bool filter_by_provided = false;
         std::vector<uint8_t> weights;
+        int syn_orig_num_tokens = -1, orig_num_tokens = -1;     // as passed to fuzzy_search_fields for the running query variant
+        bool is_synonym_query = false;
         explicit search_state(size_t cap): topster(cap) {}
     };
 
@@ -572,7 +582,8 @@ public:
         host_topster_t round(topster_size);
         size_t nf = 0;
         auto op = search_across_fields(suggestions, dropped.size(), costs, the_fields, st.weights, sort_fields, st.filter_ids, st.filter_by_provided, st.excluded, topster_size,
-                                       o.prioritize_exact_match, round, nf, o.prioritize_token_position, o.prioritize_num_matching_fields, o.text_match_type);
+                                       o.prioritize_exact_match, round, nf, o.prioritize_token_position, o.prioritize_num_matching_fields, o.text_match_type,
+                                       st.syn_orig_num_tokens, st.orig_num_tokens, st.is_synonym_query, o.demote_synonym_match);
         if(!op.ok()) return op;
         for(auto& kv: round.sort()) { st.topster.add(kv); st.all_result_ids.insert((uint32_t) kv.key); }
         return Option<bool>(true);
@@ -682,10 +693,47 @@ public:
             // only exclusions: the query is `*` minus the excluded ids (src/index.cpp:3738-3745)
             return search_wildcard(sort_fields, nullptr, st.excluded, topster_size, raw_result_kvs, found);
         }
+        // syn_orig_num_tokens (src/index.cpp:3780-3828): -1 without synonyms, else the longest of the query and its variants
+        int syn_orig = -1;
+        if(!opts.synonyms.empty()) { syn_orig = (int) tokens.size(); for(auto& sy: opts.synonyms) syn_orig = std::max(syn_orig, (int) sy.size()); }
+        st.syn_orig_num_tokens = syn_orig; st.orig_num_tokens = (int) tokens.size();
+        auto as_query = [&](const std::vector<std::string>& toks) {
+            std::vector<query_token> q;
+            for(size_t i = 0; i < toks.size(); i++) q.push_back({toks[i], opts.prefix && i + 1 == toks.size()});
+            return q;
+        };
+        auto op = fuzzy_search_fields(as_query(tokens), {}, the_fields, sort_fields, topster_size, opts, st);
+        if(!op.ok()) return op;
+        // Index::do_synonym_search (src/index.cpp:6088-6142): no typos, typo_tokens_threshold 0, fresh query hashes
+        for(auto& sy: opts.synonyms) {
+            search_options so = opts;
+            so.num_typos = 0; so.typo_tokens_threshold = 0;
+            st.query_hashes.clear();
+            st.is_synonym_query = true;
+            op = fuzzy_search_fields(as_query(sy), {}, the_fields, sort_fields, topster_size, so, st);
+            st.is_synonym_query = false;
+            if(!op.ok()) return op;
+        }
+        // the drop-tokens rounds run over the query and every synonym variant as ordinary queries (syn_orig_num_tokens -1)
+        std::vector<std::vector<std::string>> all_queries = {tokens};
+        all_queries.insert(all_queries.end(), opts.synonyms.begin(), opts.synonyms.end());
+        st.syn_orig_num_tokens = -1;
+        for(auto& qtokens: all_queries) {
+            auto dop = drop_tokens_rounds(qtokens, the_fields, sort_fields, drop_tokens_threshold, topster_size, opts, st);
+            if(!dop.ok()) return dop;
+        }
+        raw_result_kvs = st.topster.sort();
+        found = st.all_result_ids.size();
+        return Option<bool>(true);
+    }
+
+    // the drop-tokens loop of Index::search (src/index.cpp:3920-4017) for one query variant
+    Option<bool> drop_tokens_rounds(const std::vector<std::string>& tokens, const std::vector<std::string>& the_fields,
+                                    const std::vector<sort_by>& sort_fields, size_t drop_tokens_threshold, size_t topster_size,
+                                    const search_options& opts, search_state& st) {
         std::vector<query_token> qt;
         for(size_t i = 0; i < tokens.size(); i++) qt.push_back({tokens[i], opts.prefix && i + 1 == tokens.size()});
-        auto op = fuzzy_search_fields(qt, {}, the_fields, sort_fields, topster_size, opts, st);
-        if(!op.ok()) return op;
+        Option<bool> op(true);
         const size_t n = std::min<size_t>(tokens.size(), 20);
         if(st.all_result_ids.size() < drop_tokens_threshold) {
             size_t num_tokens_dropped = 0, total_dirs_done = 0;
@@ -712,13 +760,12 @@ public:
                         for(size_t i = 0; i < n; i++) { if(i >= start) trunc.push_back(qt[i]); else dropped.push_back(tokens[i]); }
                     }
                     num_tokens_dropped++;
+                    st.orig_num_tokens = (int) trunc.size();
                     op = fuzzy_search_fields(trunc, dropped, the_fields, sort_fields, topster_size, opts, st);
                     if(!op.ok()) return op;
                 } else break;
             }
         }
-        raw_result_kvs = st.topster.sort();
-        found = st.all_result_ids.size();
         return Option<bool>(true);
     }
 
