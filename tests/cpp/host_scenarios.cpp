@@ -526,6 +526,49 @@ static void synonym_scenarios() {
     }
 }
 
+// String filter_by scenarios of test/collection_filtering_test.cpp (table generated from tests/test_filter_scenarios.py)
+struct FilterCheck { const char* field; const char* raw; long count; std::vector<uint32_t> ids; };
+struct FilterCase {
+    const char* source;
+    std::vector<std::string> fields;
+    std::vector<bool> is_array;
+    std::vector<std::vector<std::vector<std::string>>> docs;      // [doc][field][element]
+    std::vector<long> points;
+    std::vector<FilterCheck> checks;
+};
+static void filter_scenarios() {
+    const std::vector<FilterCase> cases = {
+#include "filter_cases.inc"
+    };
+    for(auto& c: cases) {
+        tsgpu::Index index((uint32_t) c.docs.size());
+        for(size_t f = 0; f < c.fields.size(); f++) {
+            tsgpu::field_mirror_t m(c.is_array[f]);
+            for(uint32_t d = 0; d < c.docs.size(); d++) {
+                if(c.is_array[f]) {
+                    std::vector<std::vector<std::string>> elems;
+                    for(auto& e: c.docs[d][f]) elems.push_back(tsgpu::tokenize_ascii(e));
+                    m.index_string_array(d, elems);
+                } else m.index_plain_string(d, tsgpu::tokenize_ascii(c.docs[d][f].empty() ? std::string() : c.docs[d][f][0]));
+            }
+            CHECK(index.add_field(c.fields[f], m).ok());
+        }
+        std::unordered_map<uint32_t, int64_t> points;
+        for(uint32_t d = 0; d < c.points.size(); d++) points[d] = c.points[d];
+        CHECK(index.add_sort_field("points", points).ok());
+        for(auto& k: c.checks) {
+            std::vector<uint32_t> ids;
+            CHECK(index.string_filter_ids(k.field, k.raw, ids).ok());
+            const bool ok = k.count >= 0 ? (long) ids.size() == k.count : ids == k.ids;
+            if(!ok) { printf("filter case %s `%s:%s`: got", c.source, k.field, k.raw); for(auto i: ids) printf(" %u", i); printf("\n"); }
+            CHECK(ok);
+        }
+    }
+    std::vector<uint32_t> ids;
+    tsgpu::string_filter_exp exp;
+    CHECK(!tsgpu::parse_string_filter("tags", "=", exp).ok());        // "Filter value cannot be empty." (FilterOnTextFields :139)
+}
+
 int main(int argc, char** argv) {
     if(tsgpu_device_count() == 0) { printf("no CUDA device: nothing to run (the library has no CPU path)\n"); return 99; }
     posting_list_intersection_basics();
@@ -537,6 +580,7 @@ int main(int argc, char** argv) {
     specific_scenarios();
     phrase_scenarios();
     synonym_scenarios();
+    filter_scenarios();
     printf("%s (%d failed checks)\n", failures ? "FAILED" : "PASSED", failures);
     return failures;
 }

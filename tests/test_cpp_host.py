@@ -44,6 +44,7 @@ def test_specific_cases_table_is_current():
     spec.loader.exec_module(mod)
     assert open(os.path.join(ROOT, "tests", "cpp", "specific_cases.inc")).read() == mod.render(), "run tests/cpp/make_specific_cases.py"
     assert open(os.path.join(ROOT, "tests", "cpp", "synonym_cases.inc")).read() == mod.render_synonyms(), "run tests/cpp/make_specific_cases.py"
+    assert open(os.path.join(ROOT, "tests", "cpp", "filter_cases.inc")).read() == mod.render_filters(), "run tests/cpp/make_specific_cases.py"
 
 
 def test_cpp_host_layer_builds():

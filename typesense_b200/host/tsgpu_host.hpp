@@ -188,6 +188,72 @@ inline std::vector<uint8_t> process_search_field_weights(size_t n_fields, const 
     return w;
 }
 
+// Tokenizer's ASCII rule (src/tokenizer.cpp:232-290): alnum kept and lower-cased, space/newline split, other chars dropped
+inline std::vector<std::string> tokenize_ascii(const std::string& text) {
+    std::vector<std::string> out;
+    std::string cur;
+    for(unsigned char ch: text) {
+        if(ch < 128 && std::isalnum(ch)) cur.push_back((char) std::tolower(ch));
+        else if(ch == ' ' || ch == '\n') { if(!cur.empty()) out.push_back(cur.substr(0, 100)); cur.clear(); }
+    }
+    if(!cur.empty()) out.push_back(cur.substr(0, 100));
+    return out;
+}
+
+// The string branch of filter::parse_filter_string_value... (src/filter.cpp:674-733): `field: v`, `:= v`, `:! v`, `:!= v`,
+// `:"a phrase"`, `:[v1, "a phrase", `v,3`]`.
+struct string_filter_exp {
+    enum comparator_t { CONTAINS, EQUALS, NOT_EQUALS, CONTAINS_PHRASE };
+    std::vector<std::string> values;
+    std::vector<comparator_t> comparators;
+    bool apply_not_equals = false;
+};
+// StringUtils::split_to_values: comma separated, back-ticks keep commas, values trimmed
+inline std::vector<std::string> split_to_values(const std::string& s) {
+    std::vector<std::string> out;
+    std::string cur;
+    bool tick = false;
+    auto flush = [&]() {
+        size_t a = cur.find_first_not_of(' '), b = cur.find_last_not_of(' ');
+        if(a != std::string::npos) out.push_back(cur.substr(a, b - a + 1));
+        cur.clear();
+    };
+    for(char ch: s) {
+        if(ch == '`') tick = !tick;
+        else if(ch == ',' && !tick) flush();
+        else cur.push_back(ch);
+    }
+    flush();
+    return out;
+}
+inline Option<bool> parse_string_filter(const std::string& field_name, const std::string& raw_value, string_filter_exp& exp) {
+    size_t i = 0;
+    string_filter_exp::comparator_t comp = string_filter_exp::CONTAINS;
+    exp = string_filter_exp();
+    if(raw_value.empty()) return Option<bool>(400, "Error with filter field `" + field_name + "`: Filter value cannot be empty.");
+    if(raw_value[0] == '=') { comp = string_filter_exp::EQUALS; i = 1; }
+    else if(raw_value.size() >= 2 && raw_value[0] == '!') {
+        i = 1;
+        if(raw_value[1] == '=') { comp = string_filter_exp::NOT_EQUALS; i = 2; }
+        exp.apply_not_equals = true;
+    }
+    while(i < raw_value.size() && raw_value[i] == ' ') i++;
+    if(i == raw_value.size()) return Option<bool>(400, "Error with filter field `" + field_name + "`: Filter value cannot be empty.");
+    const std::string part = raw_value.substr(i);
+    auto quoted = [](const std::string& v) { return v.size() > 1 && v.front() == '"' && v.back() == '"'; };
+    if(quoted(part)) { exp.values = {part.substr(1, part.size() - 2)}; exp.comparators = {string_filter_exp::CONTAINS_PHRASE}; }
+    else if(part.front() == '[' && part.back() == ']') {
+        auto vals = split_to_values(part.substr(1, part.size() - 2));
+        bool has_phrase = false;
+        for(auto& v: vals) has_phrase = has_phrase || quoted(v);
+        for(auto& v: vals) {
+            if(quoted(v)) { exp.values.push_back(v.substr(1, v.size() - 2)); exp.comparators.push_back(string_filter_exp::CONTAINS_PHRASE); }
+            else { exp.values.push_back(v); exp.comparators.push_back(has_phrase ? string_filter_exp::EQUALS : comp); }
+        }
+    } else { exp.values = {part}; exp.comparators = {comp}; }
+    return Option<bool>(true);
+}
+
 struct sort_by {
     enum type_t { none = TSGPU_SORT_NONE, text_match = TSGPU_SORT_TEXT_MATCH, seq_id = TSGPU_SORT_SEQ_ID, numeric = TSGPU_SORT_NUMERIC,
                   vector_distance = TSGPU_SORT_VECTOR_DISTANCE } type = none;
@@ -444,6 +510,81 @@ public:
             auto op = ids_setop(TSGPU_SET_EXCLUDE, phrase_result_ids, excluded, merged);
             if(!op.ok()) return op;
             phrase_result_ids.swap(merged);
+        }
+        return Option<bool>(true);
+    }
+    // A string `filter_by` clause to its id set: filter_result_iterator_t::init (src/filter_result_iterator.cpp:1739-1905: the
+    // tokens of a value are ANDed, values ORed; `v*` is expanded through the fuzzy search with num_typos 0, the last token
+    // prefix-searched, MAX_SCORE order and max_filter_by_candidates) and ::compute_iterators (:2964-3100: intersect, then
+    // exact / prefix / phrase matches by comparators[0], or_scalar across values), `!` / `!=` complemented against every
+    // seq_id (apply_not_equals :936).
+    Option<bool> string_filter_ids(const std::string& field, const std::string& raw_value, std::vector<uint32_t>& out,
+                                   size_t max_filter_by_candidates = 4) {
+        out.clear();
+        string_filter_exp exp;
+        auto pop = parse_string_filter(field, raw_value, exp);
+        if(!pop.ok()) return pop;
+        const uint32_t f = field_ids.at(field);
+        std::vector<std::vector<std::string>> value_tokens;
+        std::vector<bool> value_is_prefix;
+        for(auto v: exp.values) {
+            const bool is_prefix = v.size() > 1 && v.back() == '*';
+            if(is_prefix) v.pop_back();
+            auto toks = tokenize_ascii(v);
+            if(toks.empty()) return Option<bool>(400, "Error with filter field `" + field + "`: Filter value cannot be empty.");
+            if(!is_prefix) {
+                bool known = true;
+                for(auto& t: toks) known = known && token_id(f, t) != TSGPU_NO_LIST;
+                if(known) { value_tokens.push_back(toks); value_is_prefix.push_back(false); }
+                continue;
+            }
+            search_options o;
+            o.token_order = search_options::MAX_SCORE;
+            o.max_candidates = max_filter_by_candidates;
+            std::set<std::string> unique_tokens;
+            std::vector<std::vector<std::string>> cands;
+            for(size_t ti = 0; ti < toks.size(); ti++) {
+                const bool last = ti + 1 == toks.size();
+                auto c = fuzzy_candidates(f, toks[ti], 0, last, unique_tokens, o, last && toks.size() > 1 ? cands.back()[0] : std::string());
+                if(c.empty()) break;
+                cands.push_back(c);
+            }
+            if(cands.size() != toks.size()) continue;
+            size_t N = 1;
+            for(auto& c: cands) N *= c.size();
+            for(size_t n = 0; n < N && n < max_filter_by_candidates; n++) {      // combination_limit (src/index.cpp:1841)
+                std::vector<std::string> sugg;
+                size_t qn = n;
+                for(auto& c: cands) { sugg.push_back(c[qn % c.size()]); qn /= c.size(); }
+                std::vector<uint32_t> ids;
+                auto op = intersect(field, sugg, ids);
+                if(!op.ok()) return op;
+                if(!ids.empty()) { value_tokens.push_back(sugg); value_is_prefix.push_back(true); }     // a searched_filters entry
+            }
+        }
+        const auto comp0 = exp.comparators[0];
+        const bool eq = comp0 == string_filter_exp::EQUALS || comp0 == string_filter_exp::NOT_EQUALS;
+        for(size_t i = 0; i < value_tokens.size(); i++) {
+            std::vector<uint32_t> ids, matched, merged;
+            auto op = intersect(field, value_tokens[i], ids);
+            if(!op.ok()) return op;
+            if(ids.empty()) continue;
+            if(value_is_prefix[i] && eq) op = get_exact_matches(field, value_tokens[i], ids, matched, true);
+            else if(comp0 == string_filter_exp::CONTAINS_PHRASE) op = get_phrase_matches(field, value_tokens[i], ids, matched);
+            else if(eq) op = get_exact_matches(field, value_tokens[i], ids, matched);
+            else matched = ids;
+            if(!op.ok()) return op;
+            if(matched.empty()) continue;
+            op = ids_setop(TSGPU_SET_OR, out, matched, merged);
+            if(!op.ok()) return op;
+            out.swap(merged);
+        }
+        if(exp.apply_not_equals) {
+            std::vector<uint32_t> all(n_docs), merged;
+            for(uint32_t i = 0; i < n_docs; i++) all[i] = i;
+            auto op = ids_setop(TSGPU_SET_EXCLUDE, all, out, merged);
+            if(!op.ok()) return op;
+            out.swap(merged);
         }
         return Option<bool>(true);
     }
@@ -788,17 +929,5 @@ public:
         return out;
     }
 };
-
-// Tokenizer's ASCII rule (src/tokenizer.cpp:232-290): alnum kept and lower-cased, space/newline split, other chars dropped
-inline std::vector<std::string> tokenize_ascii(const std::string& text) {
-    std::vector<std::string> out;
-    std::string cur;
-    for(unsigned char ch: text) {
-        if(ch < 128 && std::isalnum(ch)) cur.push_back((char) std::tolower(ch));
-        else if(ch == ' ' || ch == '\n') { if(!cur.empty()) out.push_back(cur.substr(0, 100)); cur.clear(); }
-    }
-    if(!cur.empty()) out.push_back(cur.substr(0, 100));
-    return out;
-}
 
 }  // namespace tsgpu
