@@ -273,7 +273,8 @@ def workload_config(args, batch):
             "vector": {"k": 100, "ef": 100, "alpha": 0.3, "M": 16, "data": "clustered unit vectors, latent dim 8, ~2000 per cluster",
                        "graph": "bulk windowed-kNN build (harness), shared with the CPU oracle"},
             "cache": "index working set (>= 30 GB vectors + postings) >> 126 MB L2; a different query batch every step",
-            "parallelism": f"replica x{args.gpus}, queries sharded"}
+            "parallelism": f"replica x{args.gpus}, queries sharded",
+            "kw_scoring": "register-resident (TSGPU_REG_SCORE=1)" if os.environ.get("TSGPU_REG_SCORE") == "1" else "default"}
 
 
 # ------------------------------------------------------------------------------------------------ tsgpu arm

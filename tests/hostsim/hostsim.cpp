@@ -18,6 +18,8 @@ struct HostField {
     tspack::PackedField pk;
     DevField dev;
 };
+int g_reg_score = 0;          // hs_set_reg_score: score like kw_search_kernel<REGSCORE = true>
+long g_reg_score_hits = 0;    // documents x fields scored by that branch
 }
 
 extern "C" {
@@ -31,6 +33,7 @@ size_t hs_keyword_combo(const tsgpu_field* fields, uint32_t n_index_fields, cons
         DevField& d = hf[i].dev;
         d.n_lists = fields[i].n_lists; d.list_off = fields[i].list_off;
         d.is_array = fields[i].is_array ? kFieldIsArray : (tspack::plain_wellformed(fields[i].pos_off, fields[i].positions, fields[i].list_off[fields[i].n_lists]) ? kFieldPlainOk : 0);
+        if((d.is_array & kFieldPlainOk) && tspack::positions_fit_u16(fields[i].positions, fields[i].pos_off[fields[i].list_off[fields[i].n_lists]])) d.is_array |= kFieldPos16;
         d.list_blk_off = hf[i].pk.list_blk_off.data(); d.blk_first = hf[i].pk.blk_first.data();
         d.blk_info = hf[i].pk.blk_info.data(); d.packed = hf[i].pk.packed.data();
         d.pos_off = fields[i].pos_off; d.positions = fields[i].positions;
@@ -117,6 +120,25 @@ size_t hs_keyword_combo(const tsgpu_field* fields, uint32_t n_index_fields, cons
             for(uint32_t f = 0; f < F; f++) {
                 RawTok toks[kMaxTokens]; int nt = 0;
                 const DevField& G = fld(f);
+                if(g_reg_score && n_rows <= (uint32_t) kSmallTokens && (G.is_array & kFieldPos16)) {        // the REGSCORE branch of the kernel
+                    const uint32_t* tp[kSmallTokens];
+                    uint32_t tn[kSmallTokens], present = 0;
+                    for(int r = 0; r < kSmallTokens; r++) {
+                        tp[r] = G.positions; tn[r] = 0;
+                        if((uint32_t) r < n_rows) {
+                            uint32_t h = hit[r * F + f];
+                            if(h != kNone) {
+                                uint64_t p = G.list_off[list_of(r, f)] + h;
+                                tp[r] = G.positions + G.pos_off[p]; tn[r] = (uint32_t) (G.pos_off[p + 1] - G.pos_off[p]); present |= 1u << r;
+                            }
+                        }
+                    }
+                    if(!present) continue;
+                    g_reg_score_hits++;
+                    int64_t fs = score_field_plain_small<kSmallTokens>(P, P.total_cost == 0 && P.num_query_tokens == 1, tp, tn, present);
+                    field_agg_add(agg, P.match_type, fs, b->q_field_weight[(size_t) q * F + f]);
+                    continue;
+                }
                 for(uint32_t r = 0; r < n_rows; r++) {
                     uint32_t h = hit[r * F + f];
                     if(h == kNone) continue;
@@ -198,6 +220,34 @@ int hs_phrase_match_doc(uint32_t k, const uint32_t* tok_off, const uint32_t* raw
     RawTok toks[kMaxTokens];
     for(uint32_t t = 0; t < k; t++) { toks[t].p = raw + tok_off[t]; toks[t].n = tok_off[t + 1] - tok_off[t]; }
     return phrase_match_doc(toks, (int) k) ? 1 : 0;
+}
+
+void hs_set_reg_score(int on) { g_reg_score = on; }
+long hs_reg_score_hits() { return g_reg_score_hits; }
+
+// One plain field, rows 0..n_rows-1 (bit r of `present`: row r matched; its raw offsets are raw[tok_off[r]..tok_off[r+1])):
+// out[0] = score_field_plain() on the matched rows, out[1] = score_field_plain_small() — the two must agree.
+// params = total_cost, num_query_tokens, syn_orig_num_tokens, orig_num_tokens, is_synonym_query, demote_synonym_match,
+//          prioritize_exact_match, prioritize_token_position
+void hs_score_plain_both(uint32_t n_rows, uint32_t present, const uint32_t* tok_off, const uint32_t* raw, const int32_t* params,
+                         int64_t* out) {
+    ScoreParams P;
+    P.total_cost = (uint32_t) params[0]; P.num_query_tokens = (uint32_t) params[1]; P.syn_orig_num_tokens = params[2];
+    P.orig_num_tokens = params[3]; P.is_synonym_query = (uint8_t) params[4]; P.demote_synonym_match = (uint8_t) params[5];
+    P.prioritize_exact_match = (uint8_t) params[6]; P.prioritize_token_position = (uint8_t) params[7];
+    P.prioritize_num_matching_fields = 1; P.match_type = 0;
+    const bool single_exact = P.total_cost == 0 && P.num_query_tokens == 1;
+    RawTok toks[kMaxTokens]; int nt = 0;
+    const uint32_t* tp[kSmallTokens]; uint32_t tn[kSmallTokens];
+    for(int r = 0; r < kSmallTokens; r++) {
+        tp[r] = raw; tn[r] = 0;
+        if((uint32_t) r < n_rows && ((present >> r) & 1u)) {
+            tp[r] = raw + tok_off[r]; tn[r] = tok_off[r + 1] - tok_off[r];
+            toks[nt].p = tp[r]; toks[nt].n = tn[r]; nt++;
+        }
+    }
+    out[0] = score_field_plain(P, single_exact, toks, nt);
+    out[1] = score_field_plain_small<kSmallTokens>(P, single_exact, tp, tn, present);
 }
 
 void hs_sort_scores(const uint8_t* type, const int8_t* order, const uint8_t* missing_first, const int64_t* const* cols,

@@ -43,3 +43,23 @@ def test_no_cpu_fallback():
     rc = L.tsgpu_index_create(10, 0, C.byref(h))
     assert rc == 1   # TSGPU_ERR_NO_DEVICE
     assert b"no CPU fallback" in L.tsgpu_last_error()
+
+
+def test_opt_in_regscore_kernel_adds_no_local_memory_traffic():
+    """SASS of the built library (cuobjdump, no GPU): the opt-in kw_search_kernel<true> exists in its own namespace and has no
+    more local-memory instructions than the default kernel — its register-resident scoring branch neither spills nor indexes
+    a local array (it still carries the default scoring code as the fallback for long queries / array fields)."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_funcs
+    import re
+    fn = sass_funcs.funcs(os.path.join(ROOT, "typesense_b200", "libtsgpu.so"))
+    dflt = [v for k, v in fn.items() if "kw_search_kernelILb0" in k]
+    regs = [v for k, v in fn.items() if "kw_search_kernelILb1" in k and "tsk_rs" in k]
+    assert len(dflt) == 1 and len(regs) == 1
+    cnt = lambda ins, pat: sum(1 for i in ins if re.search(pat, i))
+    assert cnt(regs[0], r"\bLDL") <= cnt(dflt[0], r"\bLDL") and cnt(regs[0], r"\bSTL") <= cnt(dflt[0], r"\bSTL")
+    assert cnt(regs[0], r"\bLDG") > cnt(dflt[0], r"\bLDG")          # the extra branch is really there

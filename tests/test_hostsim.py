@@ -29,6 +29,9 @@ def hs():
     L.hs_keyword_combo.argtypes = [C.POINTER(S.FieldStruct), C.c_uint32, C.POINTER(S.KwBatchStruct), C.c_uint32, C.c_uint32,
                                    S.u32p, S.u64p, C.c_size_t]
     L.hs_phrase_match_doc.argtypes = [C.c_uint32, S.u32p, S.u32p]
+    L.hs_set_reg_score.argtypes = [C.c_int]
+    L.hs_reg_score_hits.restype = C.c_long
+    L.hs_score_plain_both.argtypes = [C.c_uint32, C.c_uint32, S.u32p, S.u32p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
     L.hs_ip_kat_data.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.hs_sort_scores.argtypes = [S.u8p, S.i8p, S.u8p, C.POINTER(C.POINTER(C.c_int64)), C.c_uint32, C.c_int64, C.c_float,
                                  C.POINTER(C.c_int64), C.POINTER(C.c_int)]
@@ -262,3 +265,79 @@ def test_device_functions_reproduce_reference_scenarios(hs):
     coll = trs.refflow.Collection.from_jsonl(os.path.join(trs.GOLD, "documents.jsonl"))
     trs.scenarios(hostsim_backend(hs, coll), coll)
     trs.more_scenarios(hostsim_backend(hs, coll), coll)
+
+
+def test_register_resident_plain_scoring_equals_score_field_plain(hs):
+    """score_field_plain_small() (the opt-in REGSCORE kernel's scoring: no sort, no run-time indexed arrays) against
+    score_field_plain() on random well-formed plain-field documents: 1..4 rows, rows missing from the field, duplicate
+    query tokens, documents whose last token is / is not a query token, phrases in and out of order, every switch that
+    reaches the field score (exact match, token position, synonym rescaling and demotion)."""
+    rng = np.random.default_rng(20260922)
+    out = np.zeros(2, np.int64)
+    n_multi = n_exact = 0
+    for it in range(60000):
+        n_rows = int(rng.integers(1, 5))
+        L = max(n_rows + 1, int(rng.choice([3, 6, 12, 40, 300, 3000, 65535])))
+        universe = np.arange(1, L + 1) if L <= 300 else np.unique(np.concatenate([rng.integers(1, L + 1, 60), [L]]))
+        rows = [[] for _ in range(n_rows)]
+        taken = set()
+        if rng.random() < 0.5:             # the query tokens as a (possibly permuted / gapped) phrase somewhere in the doc
+            gap = int(rng.choice([1, 1, 1, 2, 5, 11, 12]))
+            start = int(rng.integers(1, max(2, L - n_rows * gap)))
+            order = rng.permutation(n_rows) if rng.random() < 0.4 else np.arange(n_rows)
+            for i in range(n_rows):
+                pos = start + i * gap
+                if pos <= min(L, 65535) and pos not in taken:
+                    rows[int(order[i])].append(pos)
+                    taken.add(pos)
+        for pos in universe.tolist():      # every other position belongs to one row or to a token outside the query
+            if pos not in taken and rng.random() < 0.45:
+                rows[int(rng.integers(0, n_rows))].append(pos)
+                taken.add(pos)
+        for r in range(n_rows):            # a matched row holds at least one position
+            if not rows[r]:
+                pos = next(x for x in range(1, 70000) if x not in taken)
+                rows[r].append(pos)
+                taken.add(pos)
+            rows[r].sort()
+        verbatim = rng.random() < 0.08
+        if verbatim:                        # the document IS the query (or the query plus a few more tokens)
+            rows = [[i + 1] for i in range(n_rows)]
+            if rng.random() < 0.3:
+                rows[int(rng.integers(0, n_rows))].append(n_rows + 3)
+        if n_rows >= 2 and rng.random() < 0.15:          # the same token twice in the query: identical lists
+            a, b2 = rng.choice(n_rows, 2, replace=False)
+            rows[int(b2)] = list(rows[int(a)])
+        doc_last = max(max(r) for r in rows)
+        if rng.random() < 0.6:                           # the doc's last token is a query token: trailing 0 on every row holding it
+            for r in rows:
+                if r[-1] == doc_last:
+                    r.append(0)
+        present = (1 << n_rows) - 1 if verbatim else int(rng.integers(1, 1 << n_rows))
+        tok_off = np.zeros(n_rows + 1, np.uint32)
+        tok_off[1:] = np.cumsum([len(r) for r in rows])
+        raw = np.asarray([x for r in rows for x in r], np.uint32)
+        syn = rng.random() < 0.25
+        nq = int(rng.integers(1, 5))
+        params = np.asarray([int(rng.integers(0, 5)), nq, int(rng.choice([-1, 1, 2, 3, 4])) if syn else -1, int(rng.choice([-1, 1, 2, 3])) if syn else -1,
+                             1 if syn else 0, int(rng.integers(0, 2)) if syn else 0, int(rng.integers(0, 2)), int(rng.integers(0, 2))], np.int32)
+        hs.hs_score_plain_both(n_rows, present, ol.p32(tok_off), ol.p32(raw), params.ctypes.data_as(C.POINTER(C.c_int32)),
+                               out.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert out[0] == out[1], (it, rows, present, params.tolist(), out.tolist())
+        n_multi += bin(present).count("1") > 1
+        n_exact += (int(out[0]) >> 12) & 1
+    assert n_multi > 20000 and n_exact > 500, (n_multi, n_exact)
+
+
+def test_reference_scenarios_with_register_resident_scoring(hs, small_collection):
+    """The scenario replays and the random-combination parity above, once more with the REGSCORE branch switched on."""
+    hs.hs_set_reg_score(1)
+    before = hs.hs_reg_score_hits()
+    try:
+        for seed in range(4):
+            test_device_scoring_matches_oracle(hs, small_collection, seed)
+        test_device_scoring_synonym_and_wide_positions(hs)          # positions beyond 65535: the branch must stand aside
+        test_device_functions_reproduce_reference_scenarios(hs)
+    finally:
+        hs.hs_set_reg_score(0)
+    assert hs.hs_reg_score_hits() - before > 2000           # the branch really ran

@@ -1,0 +1,26 @@
+"""The opt-in register-resident scoring kernel (TSGPU_REG_SCORE=1, kw_regscore.cu) against the oracle on the GPU. The switch
+is read once per process, so the keyword parity tests and the reference scenarios are re-run in a child process with it
+set. The file sorts last on purpose: it checks an experimental path and must not stand in front of the others."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_keyword_parity_with_register_resident_scoring():
+    env = dict(os.environ, TSGPU_REG_SCORE="1")
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+           os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_reference_scenarios.py"),
+           os.path.join(ROOT, "tests", "test_typo_scenarios.py"), os.path.join(ROOT, "tests", "test_specific_scenarios.py"),
+           "-k", "keyword or scenarios or edge or large_scale"]
+    if os.environ.get("TSGPU_TEST_DOUBLE") == "1":            # CPU dry run (tests/test_gpu_tests_dryrun.py): leave out what needs a device
+        from test_gpu_tests_dryrun import GPU_ONLY
+        for t in GPU_ONLY:
+            cmd += ["--deselect", t]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0 and " passed" in r.stdout, tail

@@ -196,6 +196,10 @@ constexpr int kQCap = 2 * kThreads;        // pending-match queue slots per CTA
 #ifndef TSGPU_KW_MIN_CTAS
 #define TSGPU_KW_MIN_CTAS 8
 #endif
+// REGSCORE (opt-in, TSGPU_REG_SCORE=1; not yet measured on a GPU): plain fields of combinations with at most kSmallTokens
+// rows are scored by score_field_plain_small(), which keeps the tokens and the Match window in registers instead of the
+// run-time indexed local arrays of score_field_plain(). <false> is the code that was profiled this round.
+template <bool REGSCORE>
 __global__ void __launch_bounds__(kThreads, TSGPU_KW_MIN_CTAS)
 kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ KwParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -298,6 +302,30 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
             }
             for(uint32_t f = 0; f < F; f++) {
                 const DevField& g = ix.fields[P.field_ids[f]];
+                if constexpr (REGSCORE) {
+                    if(cd.n_rows <= (uint32_t) kSmallTokens && (g.is_array & kFieldPos16)) {
+                        const uint32_t* tp[kSmallTokens];
+                        uint32_t tn[kSmallTokens], present = 0;
+#pragma unroll
+                        for(int r = 0; r < kSmallTokens; r++) {
+                            tp[r] = g.positions; tn[r] = 0;
+                            if((uint32_t) r < cd.n_rows) {
+                                const uint32_t j = (uint32_t) r * F + f;
+                                const uint32_t h = q_hp[j * kQCap + src];
+                                if(h != kNone) {
+                                    const unsigned long long p = l_base[j] + h;
+                                    const unsigned long long o0 = __ldg(reinterpret_cast<const unsigned long long*>(g.pos_off) + p);
+                                    const unsigned long long o1 = __ldg(reinterpret_cast<const unsigned long long*>(g.pos_off) + p + 1);
+                                    tp[r] = g.positions + o0; tn[r] = (uint32_t) (o1 - o0); present |= 1u << r;
+                                }
+                            }
+                        }
+                        if(!present) continue;
+                        const int64_t fs = score_field_plain_small<kSmallTokens>(SP, SP.total_cost == 0 && SP.num_query_tokens == 1, tp, tn, present);
+                        field_agg_add(agg, SP.match_type, fs, (int64_t) qd.field_weight[f]);
+                        continue;
+                    }
+                }
                 RawTok toks[kMaxTokens];
                 int nt = 0;
                 for(uint32_t r = 0; r < cd.n_rows; r++) {
@@ -558,6 +586,7 @@ kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ Kw
     }
 }
 
+#ifndef TSGPU_KW_SEARCH_ONLY          // kw_regscore.cu compiles kw_search_kernel alone
 // ---------------------------------------------------------------------------------------------------------------
 // KV record as in include/tsgpu.h (56 bytes)
 struct KVOut {
@@ -1094,5 +1123,7 @@ setop_extract_kernel(const uint32_t* __restrict__ R, uint32_t n_words, const uns
         o++;
     }
 }
+
+#endif  // TSGPU_KW_SEARCH_ONLY
 
 }  // namespace tsk

@@ -32,6 +32,7 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;
 
 constexpr uint32_t kFieldIsArray = 1;       // string[] (in-band array protocol in the offsets)
 constexpr uint32_t kFieldPlainOk = 2;        // plain string field whose offsets were validated as well formed at load
+constexpr uint32_t kFieldPos16 = 4;          // ... and every position fits uint16 (precondition of score_field_plain_small)
 
 struct DevField {
     uint32_t n_lists;

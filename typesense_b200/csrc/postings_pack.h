@@ -108,4 +108,10 @@ inline bool plain_wellformed(const uint64_t* pos_off, const uint32_t* positions,
     return true;
 }
 
+// True when no position exceeds 65535 (Match keeps offsets as uint16: beyond that they wrap).
+inline bool positions_fit_u16(const uint32_t* positions, uint64_t n_positions) {
+    for(uint64_t i = 0; i < n_positions; i++) if(positions[i] > 0xFFFFu) return false;
+    return true;
+}
+
 }  // namespace tspack

@@ -370,6 +370,148 @@ TS_HD_NOINLINE int64_t score_field_plain(const ScoreParams& P, bool single_exact
                                  ((int64_t) proximity << 16) | ((int64_t) verbatim << 12) | ((int64_t) offset_score << 4) | ((int64_t) syn));
 }
 
+// ---- register-resident scoring of a plain field for short queries -------------------------------------------------
+// score_field_plain() keeps its tokens, segments and the Match window in arrays indexed at run time, which nvcc can only
+// place in local memory (the kernel's stack traffic in profiles/). For queries of at most kSmallTokens rows the same
+// computation fits in registers: every per-token array below is indexed by unrolled compile-time constants only.
+//
+// Match::Match (include/match_score.h:129-275) without the sort. Each round the reference sorts its window by offset,
+// descending, and reads from it: the smallest offset (min), the largest (w_off[0]), how many entries lie within
+// WINDOW_SIZE of min, and the sum of the gaps between those entries. The entries within the window are a suffix of the
+// sorted order, so the gaps telescope to (largest in-window offset - min); all four are functions of the MULTISET of
+// offsets. The entry that leaves is the smallest one. Precondition (kFieldPos16, validated when the field is loaded):
+// every position fits uint16, so a token's uint16 positions are strictly increasing and two different tokens never
+// share an offset. Equal offsets then only occur between duplicate query tokens, whose states are interchangeable —
+// whichever of them leaves first, the multiset of offsets of every later round is the same — so the reference's
+// tie order (stable insertion sort) need not be tracked; and "this was the token's last position" can be tested by
+// value exactly as the reference does.
+constexpr int kSmallTokens = 4;
+
+template <int MAXT>
+TS_HD MatchOut match_window_small(const uint32_t* const (&tp)[MAXT], const uint32_t (&tn)[MAXT], uint32_t present, int n_all,
+                                  bool check_exact_match) {
+    MatchOut out;
+    out.words_present = 0; out.distance = 0; out.max_offset = 0; out.exact_match = 0;
+    const uint32_t* cur[MAXT];             // address of the token's current position
+    uint32_t ol[MAXT];                     // current offset | last offset << 16 (both uint16, as Match stores them)
+    uint32_t active = present;
+    int32_t last_token_index = -1;         // inputs of the exact-match test: they do not depend on the walk
+    uint32_t total_offsets = 0;
+#pragma unroll
+    for(int t = 0; t < MAXT; t++) {
+        cur[t] = tp[t]; ol[t] = 0;
+        if((present >> t) & 1u) {
+            const uint32_t n = tn[t];
+            const bool last = tp[t][n - 1] == 0;
+            const uint32_t cnt = n - (last ? 1u : 0u);
+            const uint32_t lp = (uint16_t) ((uint16_t) tp[t][cnt - 1] - 1);
+            ol[t] = (uint32_t) (uint16_t) ((uint16_t) tp[t][0] - 1) | (lp << 16);
+            if(last) last_token_index = (int32_t) lp;
+            total_offsets += cnt;
+        }
+    }
+    const uint32_t tokens_size = (uint32_t) n_all;           // n_all <= MAXT <= WINDOW_SIZE
+    uint32_t wsize = tokens_size;
+    uint32_t best_num_match = 1, best_displacement = kMaxDisplacement;
+    int32_t prev_min_offset = -1;
+    while(wsize > 1) {
+        uint32_t min_offset = 0xFFFFFFFFu, max_off = 0;
+        int tk = 0;
+#pragma unroll
+        for(int t = 0; t < MAXT; t++) {
+            if((active >> t) & 1u) {
+                const uint32_t o = ol[t] & 0xFFFFu;
+                if(o > max_off) max_off = o;
+                if(o < min_offset) { min_offset = o; tk = t; }
+            }
+        }
+        if((int32_t) min_offset < prev_min_offset) break;
+        prev_min_offset = (int32_t) min_offset;
+        uint32_t this_num_match = 0, max_in = min_offset;
+#pragma unroll
+        for(int t = 0; t < MAXT; t++) {
+            const uint32_t o = ol[t] & 0xFFFFu;
+            if(((active >> t) & 1u) && o - min_offset <= (uint32_t) kWindowSize) { this_num_match++; if(o > max_in) max_in = o; }
+        }
+        const uint32_t this_displacement = max_in - min_offset;
+        if((this_num_match > best_num_match) || (this_num_match == best_num_match && this_displacement < best_displacement)) {
+            best_displacement = this_displacement;
+            best_num_match = this_num_match;
+            out.max_offset = max_off < 255 ? max_off : 255;
+        }
+        if(best_num_match == tokens_size && best_displacement == wsize - 1) break;
+        // the smallest entry leaves; its token re-enters with its next position unless that was its last one
+#pragma unroll
+        for(int t = 0; t < MAXT; t++) {
+            if(t == tk) {
+                if((ol[t] & 0xFFFFu) == (ol[t] >> 16)) { active &= ~(1u << t); wsize--; }
+                else { cur[t]++; ol[t] = (ol[t] & 0xFFFF0000u) | (uint32_t) (uint16_t) ((uint16_t) cur[t][0] - 1); }
+            }
+        }
+    }
+    if(best_displacement == kMaxDisplacement) best_displacement = 0;
+    out.words_present = best_num_match & 0xFF;
+    out.distance = best_displacement & 0xFF;
+    if(check_exact_match) {
+        // (the reference returns early once total_offsets > n_all with distance == n_all - 1; the outcome is the same 0)
+        const uint32_t nm1 = (uint32_t) (n_all - 1);
+        if(out.distance <= nm1 && last_token_index == (int32_t) n_all - 1) {
+            if(total_offsets == (uint32_t) n_all && out.distance == nm1) out.exact_match = 1;
+            else if(out.distance < nm1) out.exact_match = 1;
+        }
+    }
+    return out;
+}
+
+// score_field_plain() for rows given as (tp[r], tn[r]) with bit r of `present` set when row r matched in this field.
+template <int MAXT>
+TS_HD int64_t score_field_plain_small(const ScoreParams& P, bool single_exact_query_token, const uint32_t* const (&tp)[MAXT],
+                                      const uint32_t (&tn)[MAXT], uint32_t present) {
+    int n_toks = 0;
+#pragma unroll
+    for(int t = 0; t < MAXT; t++) n_toks += (int) ((present >> t) & 1u);
+    const uint32_t synonym_score = (P.is_synonym_query && P.demote_synonym_match) ? 0 : 1;
+    if(n_toks <= 1) {                      // score_field(), n_toks <= 1, on a plain field
+        const uint32_t* p = tp[0]; uint32_t n = tn[0];
+#pragma unroll
+        for(int t = 1; t < MAXT; t++) if((present >> t) & 1u) { p = tp[t]; n = tn[t]; }
+        const uint32_t tail = p[n - 1];
+        const uint32_t is_verbatim_match = (P.prioritize_exact_match && single_exact_query_token && p[0] == 1 && n == 2 && tail == 0) ? 1 : 0;
+        const bool syn1 = (P.num_query_tokens == 1 && P.is_synonym_query);
+        const uint32_t words_present = syn1 ? (uint32_t) P.syn_orig_num_tokens : 1;
+        const uint32_t distance = syn1 ? (uint32_t) (P.syn_orig_num_tokens - 1) : 0;
+        uint32_t max_offset = 255;
+        if(P.prioritize_token_position) max_offset = tail != 0 ? tail : (n >= 2 ? p[n - 2] : 0);     // get_last_offset()
+        return (int64_t) pack_match_score(words_present & 0xFF, distance & 0xFF, max_offset & 0xFF, is_verbatim_match, P.total_cost,
+                                          words_present, synonym_score);
+    }
+    const MatchOut m = match_window_small<MAXT>(tp, tn, present, n_toks, P.prioritize_exact_match != 0);
+    const uint64_t this_match_score = pack_match_score(m.words_present, m.distance, m.max_offset, m.exact_match, P.total_cost,
+                                                       (uint32_t) n_toks, synonym_score);
+    uint64_t this_words_present = ((this_match_score >> 40) & 0xFF);
+    uint64_t unique_words = ((this_match_score >> 32) & 0xFF);
+    uint64_t typo_score = ((this_match_score >> 24) & 0xFF);
+    uint64_t proximity = ((this_match_score >> 16) & 0xFF);
+    const uint64_t verbatim = ((this_match_score >> 12) & 0xF);
+    uint64_t offset_score = P.prioritize_token_position ? ((this_match_score >> 4) & 0xFF) : 0;
+    const uint64_t syn = ((this_match_score >> 0) & 0xF);
+    if(P.is_synonym_query && P.num_query_tokens == (uint32_t) n_toks) {
+        unique_words = (uint64_t) (int64_t) P.syn_orig_num_tokens;
+        this_words_present = (uint64_t) (int64_t) P.syn_orig_num_tokens;
+    }
+    if(P.is_synonym_query && P.syn_orig_num_tokens > 0 && P.orig_num_tokens > 0) {
+        const double rel_factor = (double) P.orig_num_tokens / (double) P.syn_orig_num_tokens;
+        this_words_present = scale_component(this_words_present, rel_factor);
+        unique_words = scale_component(unique_words, rel_factor);
+        const uint64_t r1 = scale_component(255 - typo_score, rel_factor); typo_score = 255 - r1;
+        const uint64_t r2 = scale_component(100 - proximity, rel_factor); proximity = 100 - r2;
+        const uint64_t r3 = scale_component(255 - offset_score, rel_factor);
+        offset_score = P.prioritize_token_position ? 255 - r3 : 0;
+    }
+    return (int64_t) (uint64_t) (((int64_t) this_words_present << 40) | ((int64_t) unique_words << 32) | ((int64_t) typo_score << 24) |
+                                 ((int64_t) proximity << 16) | ((int64_t) verbatim << 12) | ((int64_t) offset_score << 4) | ((int64_t) syn));
+}
+
 // running reduction of compute_aggregated_score over fields
 struct FieldAgg {
     int64_t best_field_match_score, best_field_weight, sum_field_weighted_score;

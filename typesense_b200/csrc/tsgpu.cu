@@ -20,6 +20,9 @@
 
 using namespace tsk;
 
+// kw_regscore.cu: kw_search_kernel<true> lives in its own translation unit (see there)
+extern "C" cudaError_t tsgpu_launch_kw_search_regscore(const void* index_dev, const void* kw_params, unsigned n_units, size_t smem, cudaStream_t st);
+
 namespace {
 
 thread_local std::string g_err;
@@ -507,8 +510,12 @@ tsgpu_status run_keyword(tsgpu_index* idx, KwPlan& pl, uint32_t kv_stride, KwDev
         P.F = pl.F; P.KP = pl.KP; P.NL = pl.NL;
         for(uint32_t f = 0; f < (uint32_t) kMaxFieldSlots; f++) P.field_ids[f] = pl.field_ids[f];
         const size_t smem = kw_search_smem(pl);
-        CU(cudaFuncSetAttribute(kw_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024)));
-        kw_search_kernel<<<pl.n_units, kThreads, smem, st>>>(idx->ixdev, P);
+        static const bool reg_score = getenv("TSGPU_REG_SCORE") && atoi(getenv("TSGPU_REG_SCORE")) == 1;   // opt-in until measured
+        if(reg_score) CU(tsgpu_launch_kw_search_regscore(&idx->ixdev, &P, pl.n_units, smem, st));          // kw_regscore.cu
+        else {
+            CU(cudaFuncSetAttribute(kw_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024)));
+            kw_search_kernel<false><<<pl.n_units, kThreads, smem, st>>>(idx->ixdev, P);
+        }
         idx->stats.launches_total++;
         CU(cudaGetLastError());
     }
@@ -889,7 +896,10 @@ tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint
         std::vector<uint32_t> h_pos(n_pos ? n_pos : 1);
         CU(cudaMemcpy(h_po.data(), f->pos_off, (n_post + 1) * 8, cudaMemcpyDefault));
         if(n_pos) CU(cudaMemcpy(h_pos.data(), f->positions, n_pos * 4, cudaMemcpyDefault));
-        if(tspack::plain_wellformed(h_po.data(), h_pos.data(), n_post)) fm.dev.is_array |= tsdev::kFieldPlainOk;
+        if(tspack::plain_wellformed(h_po.data(), h_pos.data(), n_post)) {
+            fm.dev.is_array |= tsdev::kFieldPlainOk;
+            if(tspack::positions_fit_u16(h_pos.data(), n_pos)) fm.dev.is_array |= tsdev::kFieldPos16;
+        }
     }
     fm.dev.list_off = (const uint64_t*) fm.d_alloc[0];
     fm.dev.list_blk_off = (const uint32_t*) fm.d_alloc[1];
