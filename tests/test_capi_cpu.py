@@ -59,7 +59,8 @@ def test_opt_in_regscore_kernel_adds_no_local_memory_traffic():
     fn = sass_funcs.funcs(os.path.join(ROOT, "typesense_b200", "libtsgpu.so"))
     dflt = [v for k, v in fn.items() if "kw_search_kernelILb0" in k]
     regs = [v for k, v in fn.items() if "kw_search_kernelILb1" in k and "tsk_rs" in k]
-    assert len(dflt) == 1 and len(regs) == 1
+    assert len(dflt) == 1 and len(regs) == 2                        # <true, false> and the single-field <true, true>
     cnt = lambda ins, pat: sum(1 for i in ins if re.search(pat, i))
-    assert cnt(regs[0], r"\bLDL") <= cnt(dflt[0], r"\bLDL") and cnt(regs[0], r"\bSTL") <= cnt(dflt[0], r"\bSTL")
-    assert cnt(regs[0], r"\bLDG") > cnt(dflt[0], r"\bLDG")          # the extra branch is really there
+    for r in regs:
+        assert cnt(r, r"\bLDL") <= cnt(dflt[0], r"\bLDL") and cnt(r, r"\bSTL") <= cnt(dflt[0], r"\bSTL")
+        assert cnt(r, r"\bLDG") > cnt(dflt[0], r"\bLDG")          # the extra branch is really there

@@ -199,11 +199,13 @@ constexpr int kQCap = 2 * kThreads;        // pending-match queue slots per CTA
 // REGSCORE (opt-in, TSGPU_REG_SCORE=1; not yet measured on a GPU): plain fields of combinations with at most kSmallTokens
 // rows are scored by score_field_plain_small(), which keeps the tokens and the Match window in registers instead of the
 // run-time indexed local arrays of score_field_plain(). <false> is the code that was profiled this round.
-template <bool REGSCORE>
+// ONEFIELD (only instantiated next to REGSCORE): the batch searches a single field, so F is the constant 1 and the
+// per-row / per-field index arithmetic of narrowing, probing and scoring folds away.
+template <bool REGSCORE, bool ONEFIELD = false>
 __global__ void __launch_bounds__(kThreads, TSGPU_KW_MIN_CTAS)
 kw_search_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ KwParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t KP = P.KP, N2 = 2 * KP, NL = P.NL, F = P.F;
+    const uint32_t KP = P.KP, N2 = 2 * KP, NL = P.NL, F = ONEFIELD ? 1u : P.F;
     TopBuf tb;
     tb.s0 = reinterpret_cast<int64_t*>(smem_raw);
     tb.s1 = tb.s0 + N2;

@@ -15,9 +15,9 @@ cudaError_t tsgpu_launch_kw_search_regscore(const void* index_dev, const void* k
     tsk::KwParams P;
     std::memcpy(&ix, index_dev, sizeof ix);
     std::memcpy(&P, kw_params, sizeof P);
-    cudaError_t e = cudaFuncSetAttribute(tsk::kw_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int) std::max<size_t>(smem, 48 * 1024));
+    auto kern = P.F == 1 ? tsk::kw_search_kernel<true, true> : tsk::kw_search_kernel<true, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024));
     if(e != cudaSuccess) return e;
-    tsk::kw_search_kernel<true><<<n_units, tsk::kThreads, smem, st>>>(ix, P);
+    kern<<<n_units, tsk::kThreads, smem, st>>>(ix, P);
     return cudaGetLastError();
 }
