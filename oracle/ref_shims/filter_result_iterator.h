@@ -65,4 +65,10 @@ public:
         return validity ? (seq_id == id ? 1 : 0) : -1;
     }
     void compute_iterators() {}
+    // src/filter_result_iterator.cpp:2273: does the posting list `obj` hold one of the remaining filter ids? Used by
+    // validate_and_add_leaf (src/art.cpp:1019-1023). Defined in oracle/ref_wrap.cpp on top of the reference's own
+    // posting_t::contains_atleast_one.
+    bool contains_atleast_one(const void* obj);
+    const uint32_t* remaining_ids() const { return ids.data() + idx; }
+    size_t remaining_count() const { return ids.size() - idx; }
 };

@@ -25,6 +25,9 @@
 #include "array.h"
 #include "match_score.h"
 #include "thread_local_vars.h"
+#include "art.h"          // through oracle/_ref/stage (see Makefile): the reference's own adaptive radix tree
+#include <set>
+#include <string>
 
 extern "C" {
 
@@ -419,4 +422,83 @@ size_t ref_keyword_combo(const refglue_params* Pp, void** lists,
 
 uint32_t ref_sizeof_params() { return (uint32_t) sizeof(refglue_params); }
 
+// ---- the reference's ART (src/art.cpp, compiled in place): token index + fuzzy / prefix candidate search -------------
+void* ref_art_new() { art_tree* t = new art_tree; art_tree_init(t); return t; }
+void ref_art_free(void* t) { art_tree_destroy((art_tree*) t); delete (art_tree*) t; }
+// one (token, document): what Index::index_field_in_memory does per token of a document (src/index.cpp:877, art_inserts)
+void ref_art_insert(void* t, const char* token, uint32_t seq_id, int64_t score, const uint32_t* offsets, uint32_t n_offsets) {
+    art_document doc(seq_id, score, std::vector<uint32_t>(offsets, offsets + n_offsets));
+    art_insert((art_tree*) t, (const unsigned char*) token, (int) strlen(token) + 1, &doc);
+}
+// art_fuzzy_search_i as Index::fuzzy_search_fields calls it (src/index.cpp:4928-4952): term_len excludes the NUL for a
+// prefix search; `exclude` (newline separated) seeds unique_tokens and receives the new tokens; the matching leaves' tokens
+// are written to out, newline separated, in the order the reference returns them. Returns their count.
+size_t ref_art_fuzzy(void* t, const char* term, int cost, size_t max_words, int token_order, int prefix, int last_token,
+                     const char* prev_token, const uint32_t* filter_ids, size_t n_filter, int has_filter, const char* exclude,
+                     char* out, size_t out_cap) {
+    std::set<std::string> excl;
+    for(const char* p = exclude; p && *p;) { const char* e = strchr(p, '\n'); std::string tok = e ? std::string(p, e) : std::string(p); if(!tok.empty()) excl.insert(tok); if(!e) break; p = e + 1; }
+    filter_result_iterator_t none;
+    filter_result_iterator_t some(filter_ids, n_filter);
+    std::vector<art_leaf*> leaves;
+    const int term_len = prefix ? (int) strlen(term) : (int) strlen(term) + 1;
+    art_fuzzy_search_i((art_tree*) t, (const unsigned char*) term, term_len, cost, cost, max_words,
+                       token_order == 1 ? MAX_SCORE : FREQUENCY, prefix != 0, last_token != 0, std::string(prev_token ? prev_token : ""),
+                       has_filter ? &some : &none, leaves, excl);
+    size_t w = 0;
+    for(auto* l: leaves) {
+        const size_t n = l->key_len - 1;
+        if(w + n + 1 >= out_cap) break;
+        memcpy(out + w, l->key, n); w += n; out[w++] = '\n';
+    }
+    if(out_cap) out[w < out_cap ? w : out_cap - 1] = 0;
+    return leaves.size();
+}
+
+
+// Serialises the tree as it stands in memory (structure, compressed-path bytes and the per-node max_score exactly as the
+// reference's inserts left them) so that an ART mirror can be loaded from it:
+//   inner node: 'N', partial_len u8, partial[8], max_score i64, n_children u16, then per child (ascending byte): byte u8 + record
+//   leaf:       'L', key_len u32, key bytes (with the trailing NUL), max_score i64, num_ids u32
+//   empty tree: 'E'
+// Returns the number of bytes needed; writes only while they fit in cap.
+static void art_export_rec(const art_node* n, std::vector<unsigned char>& o) {
+    auto put = [&](const void* p, size_t k) { const unsigned char* b = (const unsigned char*) p; o.insert(o.end(), b, b + k); };
+    if(((uintptr_t) n) & 1) {
+        const art_leaf* l = (const art_leaf*) (((uintptr_t) n) & ~(uintptr_t) 1);
+        o.push_back('L');
+        uint32_t kl = l->key_len; put(&kl, 4); put(l->key, kl);
+        int64_t ms = l->max_score; put(&ms, 8);
+        uint32_t df = posting_t::num_ids(l->values); put(&df, 4);
+        return;
+    }
+    o.push_back('N');
+    o.push_back(n->partial_len);
+    put(n->partial, MAX_PREFIX_LEN);
+    int64_t ms = n->max_score; put(&ms, 8);
+    std::vector<std::pair<unsigned char, const art_node*>> kids;
+    switch(n->type) {
+        case NODE4:  for(int i = 0; i < n->num_children; i++) kids.push_back({((const art_node4*) n)->keys[i], ((const art_node4*) n)->children[i]}); break;
+        case NODE16: for(int i = 0; i < n->num_children; i++) kids.push_back({((const art_node16*) n)->keys[i], ((const art_node16*) n)->children[i]}); break;
+        case NODE48: for(int b = 0; b < 256; b++) { int ix = ((const art_node48*) n)->keys[b]; if(ix) kids.push_back({(unsigned char) b, ((const art_node48*) n)->children[ix - 1]}); } break;
+        default:     for(int b = 0; b < 256; b++) if(((const art_node256*) n)->children[b]) kids.push_back({(unsigned char) b, ((const art_node256*) n)->children[b]}); break;
+    }
+    uint16_t nk = (uint16_t) kids.size(); put(&nk, 2);
+    for(auto& k: kids) { o.push_back(k.first); art_export_rec(k.second, o); }
+}
+size_t ref_art_export(void* t, unsigned char* buf, size_t cap) {
+    std::vector<unsigned char> o;
+    const art_tree* tr = (const art_tree*) t;
+    if(!tr->root) o.push_back('E'); else art_export_rec(tr->root, o);
+    if(o.size() <= cap) memcpy(buf, o.data(), o.size());
+    return o.size();
+}
+
 }  // extern "C"
+
+// the one member the shim header leaves to this file (src/filter_result_iterator.cpp:2273, materialised-filter case)
+bool filter_result_iterator_t::contains_atleast_one(const void* obj) {
+    if(validity != valid) return false;
+    return posting_t::contains_atleast_one(obj, remaining_ids(), remaining_count());
+}
+

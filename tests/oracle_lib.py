@@ -170,6 +170,15 @@ def ref():
         L.ref_array_index_of.argtypes = [vp, C.c_uint32]
         L.ref_array_index_of.restype = C.c_uint32
         L.ref_array_remove_index.argtypes = [vp, C.c_uint32, C.c_uint32]
+        if hasattr(L, "ref_art_new"):          # the reference's ART (src/art.cpp)
+            L.ref_art_new.restype = vp
+            L.ref_art_free.argtypes = [vp]
+            L.ref_art_insert.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_int64, u32p, C.c_uint32]
+            L.ref_art_export.restype = C.c_size_t
+            L.ref_art_export.argtypes = [vp, C.c_char_p, C.c_size_t]
+            L.ref_art_fuzzy.restype = C.c_size_t
+            L.ref_art_fuzzy.argtypes = [vp, C.c_char_p, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, u32p, C.c_size_t,
+                                        C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
         _ref = L
     return _ref
 

@@ -1,0 +1,207 @@
+"""the ART mirror (typesense_b200/host/art_mirror.hpp) against the reference's own src/art.cpp compiled in
+oracle/_ref. A reference tree is filled with art_insert document by document (as the reference's tests index), exported
+(ref_art_export) and loaded into the mirror; art_fuzzy_search_i and art_mirror_t::fuzzy_search must then return the SAME
+tokens in the SAME order — typos 0..2, prefix and whole-word search, both token orders, max_words truncation, pre-excluded
+tokens, the previous-token restriction and a filter; ties included. A second check covers the mirror BUILT from a
+vocabulary (no live tree): same candidates up to the order of equal-score tokens."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import refflow
+
+ROOT = ol.ROOT
+SO = os.path.join(ROOT, "tests", "cpp", "libartmirror.so")
+
+
+@pytest.fixture(scope="module")
+def am():
+    src = os.path.join(ROOT, "tests", "cpp", "art_mirror_capi.cpp")
+    hdr = os.path.join(ROOT, "typesense_b200", "host", "art_mirror.hpp")
+    if not os.path.exists(SO) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(SO):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", src, "-o", SO])
+    L = C.CDLL(SO)
+    vp = C.c_void_p
+    L.am_load.restype = vp
+    L.am_load.argtypes = [C.c_char_p, C.c_size_t]
+    L.am_build.restype = vp
+    L.am_build.argtypes = [C.c_char_p, C.POINTER(C.c_int64), ol.u32p, C.c_uint32]
+    L.am_free.argtypes = [vp]
+    L.am_bind.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64), ol.u32p]
+    L.am_num_nodes.restype = C.c_size_t
+    L.am_num_nodes.argtypes = [vp]
+    L.am_num_leaves.restype = C.c_size_t
+    L.am_num_leaves.argtypes = [vp]
+    L.am_fuzzy.restype = C.c_size_t
+    L.am_fuzzy.argtypes = [vp, C.c_char_p, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_char_p, ol.u32p, C.c_size_t, C.c_int, C.c_char_p,
+                           C.c_char_p, C.c_size_t]
+    return L
+
+
+def rand_word(rng, alpha, lo, hi):
+    return "".join(rng.choice(list(alpha), int(rng.integers(lo, hi))))
+
+
+def make_collection(rng, trial):
+    alpha = ["abcde", "abcdefghij", "ab", "abcdefghijklmnopqrstuvwxyz"][trial % 4]
+    n_words = int(rng.integers(5, 160)) if trial % 6 != 5 else int(rng.integers(800, 2500))     # large: 48/256-way nodes, deep heaps
+    words = {rand_word(rng, alpha, 1, 8) for _ in range(n_words)}
+    if trial % 3 == 0:            # long shared prefixes: compressed paths beyond the 8 stored bytes
+        stem = rand_word(rng, alpha, 9, 14)
+        words |= {stem + rand_word(rng, alpha, 1, 5) for _ in range(12)} | {stem}
+    words = sorted(words)
+    n_docs = int(rng.integers(5, 80)) if n_words < 800 else int(rng.integers(300, 900))
+    docs = [{"title": " ".join(rng.choice(words, int(rng.integers(1, 9)))), "points": int(rng.integers(0, 40))} for _ in range(n_docs)]
+    return refflow.Collection(docs)
+
+
+def ref_tree(R, coll):
+    t = R.ref_art_new()
+    fl = coll.flat
+    order = np.argsort(fl.ids, kind="stable")               # document by document, as Collection::add does
+    post_list = np.repeat(np.arange(len(fl.list_off) - 1), np.diff(fl.list_off.astype(np.int64)))
+    toks = {l: t_ for t_, l in coll.vocab.items()}
+    for i in order:
+        sid = int(fl.ids[i])
+        offs = np.ascontiguousarray(fl.positions[int(fl.pos_off[i]):int(fl.pos_off[i + 1])], np.uint32)
+        R.ref_art_insert(t, toks[int(post_list[i])].encode(), sid, int(coll.points[sid]), ol.p32(offs), len(offs))
+    return t
+
+
+def export(R, t):
+    n = R.ref_art_export(t, None, 0)
+    buf = C.create_string_buffer(n)
+    assert R.ref_art_export(t, buf, n) == n
+    return buf.raw
+
+
+def bind(am, h, coll):
+    toks = sorted(coll.vocab, key=coll.vocab.get)
+    lo = np.ascontiguousarray(coll.flat.list_off, np.uint64)
+    ids = np.ascontiguousarray(coll.flat.ids, np.uint32)
+    am.am_bind(h, "\n".join(toks).encode(), lo.ctypes.data_as(C.POINTER(C.c_uint64)), ol.p32(ids))
+    return lo, ids          # keep alive
+
+
+def queries(rng, coll, n):
+    vw = list(coll.vocab)
+    alpha = sorted({ch for w in vw for ch in w})
+    for _ in range(n):
+        term = str(rng.choice(vw)) if rng.random() < 0.7 else rand_word(rng, alpha, 1, 9)
+        if rng.random() < 0.5 and len(term) > 1:
+            i = int(rng.integers(0, len(term)))
+            op = int(rng.integers(0, 4))
+            if op == 0:
+                term = term[:i] + term[i + 1:]
+            elif op == 1:
+                term = term[:i] + str(rng.choice(alpha)) + term[i:]
+            elif op == 2:
+                term = term[:i] + str(rng.choice(alpha)) + term[i + 1:]
+            elif i + 1 < len(term):
+                term = term[:i] + term[i + 1] + term[i] + term[i + 2:]
+        if rng.random() < 0.4:
+            term = term[:max(1, int(rng.integers(1, len(term) + 1)))]
+        if not term:
+            continue
+        excl = sorted({str(x) for x in rng.choice(vw, int(rng.integers(1, 4)))}) if rng.random() < 0.3 else []
+        prev = str(rng.choice(vw)) if rng.random() < 0.3 else ""
+        filt = np.unique(rng.integers(0, coll.n_docs, int(rng.integers(1, coll.n_docs)))).astype(np.uint32) if rng.random() < 0.25 else None
+        yield dict(term=term, cost=int(rng.integers(0, 3)), prefix=int(rng.integers(0, 2)), order=int(rng.integers(0, 2)),
+                   max_words=int(rng.choice([1, 2, 4, 10, 100])), excl=excl, prev=prev, filt=filt)
+
+
+def run_ref(R, t, q):
+    buf = C.create_string_buffer(1 << 16)
+    f = q["filt"]
+    R.ref_art_fuzzy(t, q["term"].encode(), q["cost"], q["max_words"], q["order"], q["prefix"], 1 if q["prev"] else 0, q["prev"].encode(),
+                    ol.p32(f) if f is not None else None, 0 if f is None else len(f), 0 if f is None else 1, "\n".join(q["excl"]).encode(), buf, len(buf))
+    return [x for x in buf.value.decode().split("\n") if x]
+
+
+def run_am(am, h, q):
+    buf = C.create_string_buffer(1 << 16)
+    f = q["filt"]
+    am.am_fuzzy(h, q["term"].encode(), q["cost"], q["max_words"], q["order"], q["prefix"], q["prev"].encode(),
+                ol.p32(f) if f is not None else None, 0 if f is None else len(f), 0 if f is None else 1, "\n".join(q["excl"]).encode(), buf, len(buf))
+    return [x for x in buf.value.decode().split("\n") if x]
+
+
+@pytest.mark.skipif(not ol.have_ref() or not hasattr(ol.ref(), "ref_art_new"), reason="oracle/_ref with the reference's art.cpp not built")
+def test_loaded_mirror_returns_the_references_candidates_in_order(am):
+    R = ol.ref()
+    rng = np.random.default_rng(77)
+    n = hits = 0
+    for trial in range(48):
+        coll = make_collection(rng, trial)
+        t = ref_tree(R, coll)
+        blob = export(R, t)
+        h = am.am_load(blob, len(blob))
+        assert h, "export did not parse"
+        assert am.am_num_leaves(h) == len(coll.vocab)
+        keep = bind(am, h, coll)
+        for q in queries(rng, coll, 80):
+            want, got = run_ref(R, t, q), run_am(am, h, q)
+            assert got == want, (trial, {k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in q.items()}, want, got)
+            n += 1
+            hits += len(want)
+        am.am_free(h)
+        R.ref_art_free(t)
+        del keep
+    assert n > 3000 and hits > 4000, (n, hits)
+
+
+@pytest.mark.skipif(not ol.have_ref() or not hasattr(ol.ref(), "ref_art_new"), reason="oracle/_ref with the reference's art.cpp not built")
+def test_reference_fixture_tokens(am):
+    """test/documents.jsonl (the collection_test.cpp fixture): prefix / typo candidates of the scenario queries."""
+    R = ol.ref()
+    coll = refflow.Collection.from_jsonl(os.path.join(ROOT, "tests", "golden", "documents.jsonl"))
+    t = ref_tree(R, coll)
+    blob = export(R, t)
+    h = am.am_load(blob, len(blob))
+    keep = bind(am, h, coll)
+    for term, cost, prefix in [("loox", 1, 0), ("lau", 0, 1), ("launch", 0, 0), ("rocket", 1, 0), ("ro", 0, 1), ("t", 0, 1), ("kind", 1, 1),
+                               ("the", 0, 0), ("laun", 1, 1), ("ex", 0, 1), ("what", 0, 1), ("rokket", 2, 0), ("lauch", 1, 0)]:
+        for order in (0, 1):
+            q = dict(term=term, cost=cost, prefix=prefix, order=order, max_words=4, excl=[], prev="", filt=None)
+            assert run_am(am, h, q) == run_ref(R, t, q), q
+    q = dict(term="loox", cost=1, prefix=0, order=0, max_words=4, excl=[], prev="", filt=None)
+    assert run_ref(R, t, q) == ["look", "loop"]            # QueryWithTypo's candidates, most frequent first
+    am.am_free(h)
+    R.ref_art_free(t)
+    del keep
+
+
+@pytest.mark.skipif(not ol.have_ref() or not hasattr(ol.ref(), "ref_art_new"), reason="oracle/_ref with the reference's art.cpp not built")
+def test_built_mirror_matches_up_to_tie_order(am):
+    """No live tree to export (this repository's harness): the mirror built from the vocabulary finds the same candidates;
+    tokens of equal rank may come in another order (the reference's inner-node scores depend on its insertion history)."""
+    R = ol.ref()
+    rng = np.random.default_rng(5)
+    n = 0
+    for trial in range(20):
+        coll = make_collection(rng, trial)
+        t = ref_tree(R, coll)
+        toks = sorted(coll.vocab, key=coll.vocab.get)
+        fl = coll.flat
+        df = np.diff(fl.list_off.astype(np.int64)).astype(np.uint32)
+        ms = np.asarray([max(int(coll.points[int(i)]) for i in fl.ids[int(fl.list_off[l]):int(fl.list_off[l + 1])]) for l in range(len(toks))], np.int64)
+        h = am.am_build("\n".join(toks).encode(), ms.ctypes.data_as(C.POINTER(C.c_int64)), ol.p32(df), len(toks))
+        keep = bind(am, h, coll)
+        rank = [dict(zip(toks, df.tolist())), dict(zip(toks, ms.tolist()))]
+        for q in queries(rng, coll, 60):
+            q["max_words"] = 100000               # truncation would make membership depend on the tie order
+            want, got = run_ref(R, t, q), run_am(am, h, q)
+            assert sorted(want) == sorted(got), (trial, q, want, got)
+            exact_first = q["cost"] == 0 and q["term"] in coll.vocab and q["term"] not in q["excl"]
+            body = got[1:] if exact_first and got and got[0] == q["term"] else got
+            ranks = [rank[q["order"]][x] for x in body]
+            assert ranks == sorted(ranks, reverse=True), (trial, q, got)
+            n += 1
+        am.am_free(h)
+        R.ref_art_free(t)
+        del keep
+    assert n > 800
