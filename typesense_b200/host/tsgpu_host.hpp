@@ -19,7 +19,7 @@
 //   Index::search drop-tokens loop        src/index.cpp:3920-4017  Index::search(tokens, ...)  (control flow stays on host)
 //   Index::fuzzy_search_fields            src/index.cpp:4784-5109  Index::fuzzy_search_fields (cost combinations, candidate cache)
 //   Index::search_all_candidates          src/index.cpp:1794-1894  Index::search_all_candidates (+ next_suggestion2 costs)
-//   art_fuzzy_search_i                    src/art.cpp:1825         Index::fuzzy_candidates — vocabulary scan standing in for the ART (f-1)
+//   art_fuzzy_search_i                    src/art.cpp:1825         Index::fuzzy_candidates on art_mirror_t (art_mirror.hpp)
 //   Collection::search switches/weights   src/collection.cpp:4210   search_options, process_search_field_weights
 //   Index::tokenize_string_array          src/index.cpp:1357-1393  field_mirror_t::index_string_array
 //
@@ -35,6 +35,7 @@
 #include <vector>
 
 #include "../../include/tsgpu.h"
+#include "art_mirror.hpp"
 
 namespace tsgpu {
 
@@ -271,6 +272,10 @@ class Index {
     // ids (for max_score over the default sorting field)
     struct vocab_t { std::vector<std::string> tokens; std::vector<uint64_t> list_off; std::vector<uint32_t> ids; };
     std::vector<vocab_t> vocabs;
+    // per field: the ART mirror of its vocabulary for (MAX_SCORE, FREQUENCY) leaf scores; rebuilt lazily after a change of
+    // fields or sort columns (a server-side binding loads it from an export of the live art_tree instead, see art_mirror.hpp)
+    mutable std::vector<art_mirror_t> arts;
+    mutable std::vector<bool> arts_ready;
     std::unordered_map<std::string, std::vector<int64_t>> sort_values;
     std::string default_sorting_field;
     std::string err;
@@ -309,6 +314,7 @@ public:
         vocabs[fid].list_off = list_off;
         vocabs[fid].ids = ids;
         token_ids[fid] = std::move(tid);
+        arts_ready.assign(arts_ready.size(), false);
         return Option<uint32_t>(fid);
     }
     // sort_index[field] (spp::sparse_hash_map<uint32, int64>): docs without a value sort as INT64_MIN
@@ -319,6 +325,7 @@ public:
         if(tsgpu_index_load_sort_column(h, dense.data(), &col) != TSGPU_OK) return Option<uint32_t>(500, tsgpu_last_error());
         sort_cols[name] = col;
         sort_values[name] = dense;
+        arts_ready.assign(arts_ready.size(), false);         // leaf max_score comes from the default sorting field
         if(default_sorting_field.empty()) default_sorting_field = name;      // the schema's default_sorting_field
         return Option<uint32_t>(col);
     }
@@ -635,45 +642,47 @@ public:
         if(token.size() < min_len_2typo) return (int) std::min<size_t>(max_cost, 1);
         return (int) std::min<size_t>(max_cost, 2);
     }
-    // Stand-in for art_fuzzy_search_i (src/art.cpp:1825-1894; the ART walk itself is SURVEY §8 f-1): scans the field's
-    // vocabulary for tokens at exactly `cost` edits (or, for a prefix search, with such a prefix), orders them like the
-    // leaves are ordered (document frequency or max_score of the default sorting field, descending), puts the exact
-    // token first at cost 0, skips tokens another field already produced, keeps max_candidates.
-    // With `prev_token` (the last token of a multi-token query) only tokens that share a document with it in this field
-    // qualify — validate_and_add_leaf's or_iterator_t::contains_atleast_one (src/art.cpp:1004-1046).
+    // art_fuzzy_search_i (src/art.cpp:1825-1894) on the field's ART mirror: tokens at exactly `cost` edits (or, for a prefix
+    // search, with such a prefix) as the reference's walk finds them — its pruning heuristics included — best first by
+    // document frequency or by the leaf's max_score (the default sorting field), the exact token first at cost 0, tokens
+    // another field already produced skipped, at most max_candidates. With `prev_token` (the last token of a multi-token
+    // query) only tokens that share a document with it in this field qualify (validate_and_add_leaf, src/art.cpp:1024-1036).
+    // The mirror is built from the vocabulary, so tokens of EQUAL rank may come in another order than from a live tree.
+    const art_mirror_t& art_of(uint32_t fid) const {
+        if(arts.size() <= fid) { arts.resize(fid + 1); arts_ready.resize(fid + 1, false); }
+        if(!arts_ready[fid]) {
+            const vocab_t& v = vocabs[fid];
+            const std::vector<int64_t>* scores = nullptr;
+            auto sv = sort_values.find(default_sorting_field);
+            if(sv != sort_values.end()) scores = &sv->second;
+            std::vector<art_mirror_t::vocab_entry> entries;
+            for(uint32_t l = 0; l < v.tokens.size(); l++) {
+                if(v.list_off[l + 1] == v.list_off[l]) continue;
+                int64_t best = INT64_MIN;
+                if(scores) for(uint64_t i = v.list_off[l]; i < v.list_off[l + 1]; i++) best = std::max(best, (*scores)[v.ids[i]]);
+                entries.push_back({v.tokens[l], best, (uint32_t) (v.list_off[l + 1] - v.list_off[l]), l});
+            }
+            arts[fid].build(entries);
+            arts_ready[fid] = true;
+        }
+        return arts[fid];
+    }
     std::vector<std::string> fuzzy_candidates(uint32_t fid, const std::string& token, int cost, bool prefix_search,
                                               std::set<std::string>& unique_tokens, const search_options& o,
                                               const std::string& prev_token = std::string()) const {
         const vocab_t& v = vocabs[fid];
-        const uint32_t prev_l = prev_token.empty() ? TSGPU_NO_LIST : token_id(fid, prev_token);
-        auto shares_doc = [&](uint32_t l) {
-            uint64_t a = v.list_off[prev_l], ae = v.list_off[prev_l + 1], c = v.list_off[l], ce = v.list_off[l + 1];
-            while(a < ae && c < ce) { if(v.ids[a] == v.ids[c]) return true; if(v.ids[a] < v.ids[c]) a++; else c++; }
+        const art_mirror_t& art = art_of(fid);
+        art_mirror_t::doc_tests docs;
+        docs.share_doc = [&](uint32_t a, uint32_t c) {
+            uint64_t i = v.list_off[a], ie = v.list_off[a + 1], j = v.list_off[c], je = v.list_off[c + 1];
+            while(i < ie && j < je) { if(v.ids[i] == v.ids[j]) return true; if(v.ids[i] < v.ids[j]) i++; else j++; }
             return false;
         };
-        const std::vector<int64_t>* scores = nullptr;
-        auto sv = sort_values.find(default_sorting_field);
-        if(sv != sort_values.end()) scores = &sv->second;
-        struct cand { std::string tok; int64_t rank; };
-        std::vector<cand> found;
-        const bool has_exact = token_ids[fid].count(token) != 0;
-        for(uint32_t l = 0; l < v.tokens.size(); l++) {
-            const std::string& t = v.tokens[l];
-            if((has_exact && t == token) || unique_tokens.count(t) || v.list_off[l + 1] == v.list_off[l]) continue;
-            if(!fuzzy_key_matches(token, t, cost, prefix_search)) continue;
-            if(prev_l != TSGPU_NO_LIST && !shares_doc(l)) continue;
-            int64_t rank = (int64_t) (v.list_off[l + 1] - v.list_off[l]);
-            if(o.token_order == search_options::MAX_SCORE) {
-                rank = INT64_MIN;
-                if(scores) for(uint64_t i = v.list_off[l]; i < v.list_off[l + 1]; i++) rank = std::max(rank, (*scores)[v.ids[i]]);
-            }
-            found.push_back({t, rank});
-        }
-        std::sort(found.begin(), found.end(), [](const cand& a, const cand& c2) { return a.rank != c2.rank ? a.rank > c2.rank : a.tok < c2.tok; });
         std::vector<std::string> out;
-        for(auto& c: found) { out.push_back(c.tok); unique_tokens.insert(c.tok); }
-        if(has_exact && cost == 0 && !unique_tokens.count(token)) { out.insert(out.begin(), token); unique_tokens.insert(token); }
-        if(out.size() > o.max_candidates) out.resize(o.max_candidates);
+        for(uint32_t leaf: art.fuzzy_search(token, cost, o.max_candidates,
+                                            o.token_order == search_options::MAX_SCORE ? art_mirror_t::MAX_SCORE : art_mirror_t::FREQUENCY,
+                                            prefix_search, prev_token, docs, unique_tokens))
+            out.push_back(art.leaves[leaf].key);
         return out;
     }
 
