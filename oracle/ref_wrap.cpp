@@ -433,7 +433,7 @@ void ref_art_insert(void* t, const char* token, uint32_t seq_id, int64_t score, 
 // art_fuzzy_search_i as Index::fuzzy_search_fields calls it (src/index.cpp:4928-4952): term_len excludes the NUL for a
 // prefix search; `exclude` (newline separated) seeds unique_tokens and receives the new tokens; the matching leaves' tokens
 // are written to out, newline separated, in the order the reference returns them. Returns their count.
-size_t ref_art_fuzzy(void* t, const char* term, int cost, size_t max_words, int token_order, int prefix, int last_token,
+size_t ref_art_fuzzy(void* t, const char* term, int min_cost, int max_cost, size_t max_words, int token_order, int prefix, int last_token,
                      const char* prev_token, const uint32_t* filter_ids, size_t n_filter, int has_filter, const char* exclude,
                      char* out, size_t out_cap) {
     std::set<std::string> excl;
@@ -442,7 +442,7 @@ size_t ref_art_fuzzy(void* t, const char* term, int cost, size_t max_words, int 
     filter_result_iterator_t some(filter_ids, n_filter);
     std::vector<art_leaf*> leaves;
     const int term_len = prefix ? (int) strlen(term) : (int) strlen(term) + 1;
-    art_fuzzy_search_i((art_tree*) t, (const unsigned char*) term, term_len, cost, cost, max_words,
+    art_fuzzy_search_i((art_tree*) t, (const unsigned char*) term, term_len, min_cost, max_cost, max_words,
                        token_order == 1 ? MAX_SCORE : FREQUENCY, prefix != 0, last_token != 0, std::string(prev_token ? prev_token : ""),
                        has_filter ? &some : &none, leaves, excl);
     size_t w = 0;

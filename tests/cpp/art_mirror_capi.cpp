@@ -61,7 +61,7 @@ void am_bind(void* hv, const char* tokens_nl, const uint64_t* list_off, const ui
 size_t am_num_nodes(void* hv) { return ((handle_t*) hv)->m.nodes.size(); }
 size_t am_num_leaves(void* hv) { return ((handle_t*) hv)->m.leaves.size(); }
 
-size_t am_fuzzy(void* hv, const char* term, int cost, size_t max_words, int order, int prefix, const char* prev_token,
+size_t am_fuzzy(void* hv, const char* term, int min_cost, int max_cost, size_t max_words, int order, int prefix, const char* prev_token,
                 const uint32_t* filter_ids, size_t n_filter, int has_filter, const char* exclude, char* out, size_t out_cap) {
     auto* h = (handle_t*) hv;
     std::set<std::string> excl;
@@ -71,7 +71,7 @@ size_t am_fuzzy(void* hv, const char* term, int cost, size_t max_words, int orde
     docs.filter_active = has_filter && n_filter > 0;            // an empty filter leaves the iterator invalid: no test
     docs.has_filter_doc = [&](uint32_t l) { return intersects(h->lists[l], filt, nullptr); };
     docs.share_doc = [&](uint32_t a, uint32_t b) { return intersects(h->lists[a], h->lists[b], docs.filter_active ? &filt : nullptr); };
-    auto res = h->m.fuzzy_search(term, cost, max_words, order == 1 ? tsgpu::art_mirror_t::MAX_SCORE : tsgpu::art_mirror_t::FREQUENCY,
+    auto res = h->m.fuzzy_search(term, min_cost, max_cost, max_words, order == 1 ? tsgpu::art_mirror_t::MAX_SCORE : tsgpu::art_mirror_t::FREQUENCY,
                                  prefix != 0, prev_token ? prev_token : "", docs, excl);
     size_t w = 0;
     for(uint32_t li: res) {

@@ -3,7 +3,8 @@
 records the literals so the fixture has a committed generator. Byte copies of the reference's test DATA files (not code) that
 its tests read: topster_record_values.txt = test/resources/record_values.txt (test/topster_test.cpp:60-136);
 documents.jsonl, multi_field_documents.jsonl, float_documents.jsonl = test/*.jsonl (collection_test.cpp,
-collection_sorting_test.cpp fixtures). `cp /root/reference/test/<name> tests/golden/` regenerates them."""
+collection_sorting_test.cpp fixtures); art_skus.txt, art_ill.txt = test/skus.txt, test/ill.txt (test/art_test.cpp:914, :964).
+`cp /root/reference/test/<name> tests/golden/` regenerates them."""
 import json, os
 
 kat = {

@@ -177,7 +177,7 @@ def ref():
             L.ref_art_export.restype = C.c_size_t
             L.ref_art_export.argtypes = [vp, C.c_char_p, C.c_size_t]
             L.ref_art_fuzzy.restype = C.c_size_t
-            L.ref_art_fuzzy.argtypes = [vp, C.c_char_p, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, u32p, C.c_size_t,
+            L.ref_art_fuzzy.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, u32p, C.c_size_t,
                                         C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
         _ref = L
     return _ref

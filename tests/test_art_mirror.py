@@ -37,7 +37,7 @@ def am():
     L.am_num_leaves.restype = C.c_size_t
     L.am_num_leaves.argtypes = [vp]
     L.am_fuzzy.restype = C.c_size_t
-    L.am_fuzzy.argtypes = [vp, C.c_char_p, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_char_p, ol.u32p, C.c_size_t, C.c_int, C.c_char_p,
+    L.am_fuzzy.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_char_p, ol.u32p, C.c_size_t, C.c_int, C.c_char_p,
                            C.c_char_p, C.c_size_t]
     return L
 
@@ -117,7 +117,7 @@ def queries(rng, coll, n):
 def run_ref(R, t, q):
     buf = C.create_string_buffer(1 << 16)
     f = q["filt"]
-    R.ref_art_fuzzy(t, q["term"].encode(), q["cost"], q["max_words"], q["order"], q["prefix"], 1 if q["prev"] else 0, q["prev"].encode(),
+    R.ref_art_fuzzy(t, q["term"].encode(), q.get("min_cost", q["cost"]), q["cost"], q["max_words"], q["order"], q["prefix"], 1 if q["prev"] else 0, q["prev"].encode(),
                     ol.p32(f) if f is not None else None, 0 if f is None else len(f), 0 if f is None else 1, "\n".join(q["excl"]).encode(), buf, len(buf))
     return [x for x in buf.value.decode().split("\n") if x]
 
@@ -125,7 +125,7 @@ def run_ref(R, t, q):
 def run_am(am, h, q):
     buf = C.create_string_buffer(1 << 16)
     f = q["filt"]
-    am.am_fuzzy(h, q["term"].encode(), q["cost"], q["max_words"], q["order"], q["prefix"], q["prev"].encode(),
+    am.am_fuzzy(h, q["term"].encode(), q.get("min_cost", q["cost"]), q["cost"], q["max_words"], q["order"], q["prefix"], q["prev"].encode(),
                 ol.p32(f) if f is not None else None, 0 if f is None else len(f), 0 if f is None else 1, "\n".join(q["excl"]).encode(), buf, len(buf))
     return [x for x in buf.value.decode().split("\n") if x]
 
@@ -205,3 +205,112 @@ def test_built_mirror_matches_up_to_tie_order(am):
         R.ref_art_free(t)
         del keep
     assert n > 800
+
+
+# ---- the reference's own ART tests (test/art_test.cpp) with inline keys or the two small word lists it ships
+def _tree_of(R, keys, scores=None):
+    """art_insert(key, get_document(id)): id = score = position (1-based) unless scores are given (art_test.cpp:18-21)."""
+    t = R.ref_art_new()
+    off = np.zeros(1, np.uint32)
+    for i, k in enumerate(keys):
+        kb = k if isinstance(k, bytes) else k.encode()
+        R.ref_art_insert(t, kb, i + 1 if scores is None else i, (i + 1) if scores is None else scores[i], ol.p32(off), 1)
+    return t
+
+
+def _both(R, am, t, term, lo, hi, max_words, order, prefix):
+    blob = export(R, t)
+    h = am.am_load(blob, len(blob))
+    assert h
+    tb = term if isinstance(term, bytes) else term.encode()
+    out = []
+    for fn, handle in ((R.ref_art_fuzzy, t), (None, h)):
+        buf = C.create_string_buffer(1 << 16)
+        if fn is not None:
+            fn(handle, tb, lo, hi, max_words, order, prefix, 0, b"", None, 0, 0, b"", buf, len(buf))
+        else:
+            am.am_fuzzy(handle, tb, lo, hi, max_words, order, prefix, b"", None, 0, 0, b"", buf, len(buf))
+        out.append([x for x in buf.value.split(b"\n") if x])
+    am.am_free(h)
+    assert out[0] == out[1], (term, lo, hi, out)
+    return [x.decode() for x in out[1]]
+
+
+@pytest.mark.skipif(not ol.have_ref() or not hasattr(ol.ref(), "ref_art_new"), reason="oracle/_ref with the reference's art.cpp not built")
+def test_reference_art_tests(am):
+    R = ol.ref()
+    FREQ, SCORE = 0, 1
+    # test_art_fuzzy_search_single_leaf :579
+    t = _tree_of(R, ["implement"])
+    assert len(_both(R, am, t, "implement", 0, 0, 10, FREQ, 0)) == 1
+    assert len(_both(R, am, t, "implment", 0, 0, 10, FREQ, 0)) == 0
+    assert len(_both(R, am, t, "implment", 0, 1, 10, FREQ, 0)) == 1
+    assert len(_both(R, am, t, "implwnent", 0, 2, 10, FREQ, 0)) == 1
+    R.ref_art_free(t)
+    # test_art_fuzzy_search_single_leaf_prefix :617
+    t = _tree_of(R, ["application"])
+    assert len(_both(R, am, t, "aplication", 0, 1, 10, FREQ, 1)) == 1
+    assert len(_both(R, am, t, "aplication", 0, 2, 10, FREQ, 1)) == 1
+    R.ref_art_free(t)
+    # ..._qlen_greater_than_key :643, ..._non_prefix :661, test_art_prefix_larger_than_key :684
+    t = _tree_of(R, ["storka"])
+    assert _both(R, am, t, "starkbin", 0, 2, 10, FREQ, 1) == []
+    R.ref_art_free(t)
+    t = _tree_of(R, ["spz005"])
+    assert _both(R, am, t, "spz", 0, 1, 10, FREQ, 0) == []
+    assert _both(R, am, t, "spz", 0, 1, 10, FREQ, 1) == ["spz005"]
+    R.ref_art_free(t)
+    t = _tree_of(R, ["arvin"])
+    assert _both(R, am, t, "earrings", 0, 2, 10, FREQ, 0) == []
+    R.ref_art_free(t)
+    # test_art_fuzzy_search_prefix_token_ordering :702 — score = 12 - i; the exact token comes first
+    keys = ["enter", "elephant", "enamel", "ercot", "enyzme", "energy", "epoch", "epyc", "express", "everest", "end", "e"]
+    t = _tree_of(R, keys, scores=[len(keys) - i for i in range(len(keys))])
+    assert _both(R, am, t, "e", 0, 0, 3, SCORE, 1) == ["e", "enter", "elephant"]
+    assert _both(R, am, t, "enter", 1, 1, 3, SCORE, 1) == []
+    R.ref_art_free(t)
+    # test_art_fuzzy_search_unicode_chars :864
+    keys = ["роман", "обладать", "роисхождения", "без", "பஞ்சமம்", "சுதந்திரமாகவே", "அல்லது", "அடிப்படையில்"]
+    t = _tree_of(R, keys)
+    for k in keys:
+        assert _both(R, am, t, k, 0, 0, 10, FREQ, 1) == [k]
+    R.ref_art_free(t)
+    # test_art_fuzzy_search_extra_chars :891, roche_chews :1083, raspberry :1118, highliving :1152, ill_like_tokens2 :1035
+    t = _tree_of(R, ["abbviation"])
+    assert len(_both(R, am, t, "abbreviation", 0, 2, 10, FREQ, 1)) == 1
+    R.ref_art_free(t)
+    t = _tree_of(R, ["roche"])
+    assert _both(R, am, t, "chews", 0, 2, 10, FREQ, 1) == []
+    assert _both(R, am, t, "roche", 0, 0, 10, FREQ, 0) == ["roche"]
+    assert _both(R, am, t, "xxroche", 0, 2, 10, FREQ, 0) == ["roche"]
+    R.ref_art_free(t)
+    t = _tree_of(R, ["raspberry", "raspberries"])
+    assert len(_both(R, am, t, "raspberries", 0, 2, 10, FREQ, 1)) == 2
+    assert len(_both(R, am, t, "raspberry", 0, 2, 10, FREQ, 1)) == 2
+    R.ref_art_free(t)
+    t = _tree_of(R, ["highliving"])
+    assert len(_both(R, am, t, "higghliving", 0, 1, 10, FREQ, 0)) == 1
+    assert len(_both(R, am, t, "higghliving", 0, 2, 10, FREQ, 1)) == 1
+    R.ref_art_free(t)
+    keys = ["input", "illustrations", "illustration"]
+    t = _tree_of(R, keys)
+    for k in keys:
+        assert len(_both(R, am, t, k, 0, 0, 10, FREQ, 1)) == (2 if k == "illustration" else 1)
+        assert _both(R, am, t, k, 0, 0, 10, FREQ, 0) == [k]
+    R.ref_art_free(t)
+    # test_art_search_sku_like_tokens :914 and test_art_search_ill_like_tokens :964 (test/skus.txt, test/ill.txt: byte copies in tests/golden)
+    skus = [l.rstrip("\n") for l in open(os.path.join(ROOT, "tests", "golden", "art_skus.txt"))]
+    t = _tree_of(R, skus)
+    for k in skus:
+        assert _both(R, am, t, k, 0, 0, 10, FREQ, 1) == [k]
+        assert _both(R, am, t, k, 0, 0, 10, FREQ, 0) == [k]
+    R.ref_art_free(t)
+    ill = [l.rstrip("\n") for l in open(os.path.join(ROOT, "tests", "golden", "art_ill.txt"))]
+    counts = {"input": 2, "illustration": 2, "image": 7, "instrument": 2, "in": 10, "info": 2, "inventor": 2, "imageresize": 2, "id": 5,
+              "insect": 2, "ice": 2}
+    t = _tree_of(R, ill)
+    for k in ill:
+        got = _both(R, am, t, k, 0, 0, 10, FREQ, 1)
+        assert len(got) == counts.get(k, 1) and (k in counts or got == [k]), (k, got)
+        assert _both(R, am, t, k, 0, 0, 10, FREQ, 0) == [k]
+    R.ref_art_free(t)

@@ -91,16 +91,21 @@ public:
         std::function<bool(uint32_t)> has_filter_doc;
         std::function<bool(uint32_t, uint32_t)> share_doc;
     };
-    // Leaves (indices into `leaves`) at exactly `cost` edits of `term` — or, for a prefix search, whose key has such a
+    // Leaves (indices into `leaves`) at `cost` edits of `term` — or, for a prefix search, whose key has such a
     // prefix — best first, at most max_words; tokens already in exclude_leaves are skipped and the returned ones added.
     std::vector<uint32_t> fuzzy_search(const std::string& term, int cost, size_t max_words, token_ordering order, bool prefix,
+                                       const std::string& prev_token, const doc_tests& docs, std::set<std::string>& exclude_leaves) const {
+        return fuzzy_search(term, cost, cost, max_words, order, prefix, prev_token, docs, exclude_leaves);
+    }
+    // the general form (the search path always asks for one exact cost; test/art_test.cpp uses ranges)
+    std::vector<uint32_t> fuzzy_search(const std::string& term, int min_cost, int max_cost, size_t max_words, token_ordering order, bool prefix,
                                        const std::string& prev_token, const doc_tests& docs, std::set<std::string>& exclude_leaves) const {
         std::vector<uint32_t> results;
         if(empty) return results;
         search_t s;
         s.q.assign(term.begin(), term.end());
         if(!prefix) s.q.push_back('\0');                           // the key's terminator takes part in a whole-word match
-        s.min_cost = s.max_cost = cost;
+        s.min_cost = min_cost; s.max_cost = max_cost;
         s.prefix = prefix;
         std::vector<int> row0(s.q.size() + 1);
         for(size_t i = 0; i < row0.size(); i++) row0[i] = (int) i;
@@ -112,7 +117,7 @@ public:
         for(int32_t n: s.hits) collect(n, order, max_words, exact_leaf, prev_token, prev_leaf, docs, exclude_leaves, results);
         if(order == FREQUENCY) std::sort(results.begin(), results.end(), [&](uint32_t a, uint32_t b) { return leaves[a].num_ids > leaves[b].num_ids; });
         else std::sort(results.begin(), results.end(), [&](uint32_t a, uint32_t b) { return leaves[a].max_score > leaves[b].max_score; });
-        if(exact_leaf >= 0 && cost == 0 && !exclude_leaves.count(leaves[exact_leaf].key)) {
+        if(exact_leaf >= 0 && min_cost == 0 && !exclude_leaves.count(leaves[exact_leaf].key)) {
             results.insert(results.begin(), (uint32_t) exact_leaf);
             exclude_leaves.insert(leaves[exact_leaf].key);
         }
