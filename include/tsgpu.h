@@ -180,6 +180,38 @@ enum { TSGPU_SET_AND = 0, TSGPU_SET_OR = 1, TSGPU_SET_EXCLUDE = 2 };
 tsgpu_status tsgpu_ids_setop(tsgpu_index* idx, int op, const uint32_t* a, size_t na, const uint32_t* b, size_t nb,
                              uint32_t* out_ids, size_t cap, size_t* out_n);
 
+/* ---- typo / prefix candidate tokens (not measured on a GPU yet) -------------------------------------
+ * A field's token index (art_tree, include/art.h:124-127; one per string field, Index::search_index) as flat arrays:
+ * inner nodes with the first 8 bytes of their compressed path (MAX_PREFIX_LEN), child links ascending by key byte, leaf
+ * keys. typesense_b200/host/art_mirror.hpp builds them from an export of the live tree. */
+typedef struct tsgpu_art {
+    uint32_t n_nodes, n_children, n_leaves;
+    int32_t  root;                      /* >= 0: inner node; < 0: leaf ~root (a one-token index); ignored when n_leaves == 0 */
+    const uint32_t* node_first_child;   /* [n_nodes] -> child_byte / child_ref */
+    const uint16_t* node_n_children;    /* [n_nodes] */
+    const uint8_t*  node_partial_len;   /* [n_nodes] art_node::partial_len */
+    const uint8_t*  node_partial;       /* [n_nodes * 8] art_node::partial */
+    const uint8_t*  child_byte;         /* [n_children] */
+    const int32_t*  child_ref;          /* [n_children] >= 0 inner node, < 0 leaf ~ref */
+    const uint64_t* leaf_key_off;       /* [n_leaves + 1] -> leaf_keys (keys without the terminating NUL) */
+    const uint8_t*  leaf_keys;
+} tsgpu_art;
+
+/* Replaces / extends the mirror of `field` (an id returned by tsgpu_index_load_field). Needs the host's exclusive lock. */
+tsgpu_status tsgpu_index_load_art(tsgpu_index* idx, uint32_t field, const tsgpu_art* art);
+
+/* The tree walk of art_fuzzy_search_i (src/art.cpp:1825-1894: art_fuzzy_recurse :1596-1738 with fuzzy_search_state
+ * :1487-1594), batched: search i looks for keys within [min_cost[i], max_cost[i]] edits of terms[term_off[i]..term_off[i+1])
+ * (prefix[i] != 0: keys having such a prefix) — Index::fuzzy_search_fields issues one such search per (token, cost, field),
+ * src/index.cpp:4949/5004. out_hits[i*cap ..] receives the matching subtrees / leaves (node >= 0, leaf ~ref) in the order
+ * the reference's recursion meets them, out_counts[i] their number. out_flags[i] != 0 means the search must be walked on
+ * the host instead (1: deeper than the device stack, 2: term longer than 31 bytes, 4: more than cap hits). The second half
+ * — art_topk_iter, validate_and_add_leaf, the final sort (a few dozen leaves per search) — is host code:
+ * art_mirror_t::finish. */
+tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, uint32_t n, const uint32_t* term_off, const uint8_t* terms,
+                                  const uint8_t* min_cost, const uint8_t* max_cost, const uint8_t* prefix,
+                                  int32_t* out_hits, uint32_t cap, uint32_t* out_counts, uint8_t* out_flags);
+
 /* search_all_candidates -> search_across_fields -> or_iterator_t::intersect + compute_aggregated_score +
  * compute_sort_scores + Topster::add (src/index.cpp:1794, 5385-5596), batched over queries.
  * out_kv[q*kv_stride ..] = the query's Topster in Topster::sort() order, out_count[q] entries;

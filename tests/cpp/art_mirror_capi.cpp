@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../typesense_b200/host/art_mirror.hpp"
+#include "../../typesense_b200/csrc/art_device.cuh"      // the device walk, compiled for the host
 
 namespace {
 struct handle_t {
@@ -82,5 +83,57 @@ size_t am_fuzzy(void* hv, const char* term, int min_cost, int max_cost, size_t m
     if(out_cap) out[w < out_cap ? w : out_cap - 1] = 0;
     return res.size();
 }
+
+
+// walk_hits on the host mirror (mode 0) or through the device function art_walk() on the flattened arrays (mode 1); refs as int32
+size_t am_walk(void* hv, int mode, const char* term, int min_cost, int max_cost, int prefix, int32_t* out, size_t cap, int* stack_overflow) {
+    auto* h = (handle_t*) hv;
+    *stack_overflow = 0;
+    if(mode == 0) {
+        auto hits = h->m.walk_hits(term, min_cost, max_cost, prefix != 0);
+        for(size_t i = 0; i < hits.size() && i < cap; i++) out[i] = hits[i];
+        return hits.size();
+    }
+    auto f = h->m.flatten();
+    std::vector<tsdev::ArtNodeDev> nodes(h->m.nodes.size());
+    for(size_t i = 0; i < nodes.size(); i++) {
+        nodes[i].first_child = f.node_first_child[i]; nodes[i].n_children = f.node_n_children[i]; nodes[i].partial_len = f.node_partial_len[i];
+        memcpy(nodes[i].partial, &f.node_partial[i * 8], 8); nodes[i].pad = 0;
+    }
+    tsdev::ArtDev A{nodes.data(), h->m.child_byte.data(), h->m.child_ref.data(), f.leaf_key_off.data(), f.leaf_keys.data(), h->m.root, h->m.empty ? 1u : 0u};
+    tsdev::ArtQuery Q;
+    const size_t tl = strlen(term);
+    if(tl + (prefix ? 0 : 1) > (size_t) tsdev::kArtMaxQuery) { *stack_overflow = 2; return 0; }
+    memcpy(Q.q, term, tl);
+    Q.qlen = (int) tl;
+    if(!prefix) Q.q[Q.qlen++] = 0;
+    Q.min_cost = min_cost; Q.max_cost = max_cost; Q.prefix = prefix != 0;
+    std::vector<tsdev::ArtFrame> stack(tsdev::kArtMaxStack);
+    bool so = false;
+    const uint32_t n = tsdev::art_walk(A, Q, out, (uint32_t) cap, stack.data(), &so);
+    *stack_overflow = so ? 1 : 0;
+    return n;
+}
+
+
+// the arrays of tsgpu_art, for handing a mirror to tsgpu_index_load_art from Python: sizes first (out == NULL), then the copy
+// which: 0 node_first_child(u32) 1 node_n_children(u16) 2 node_partial_len(u8) 3 node_partial(u8 x8) 4 child_byte(u8) 5 child_ref(i32)
+//        6 leaf_key_off(u64) 7 leaf_keys(u8); returns the element count
+size_t am_flat(void* hv, int which, void* out) {
+    auto* h = (handle_t*) hv;
+    auto f = h->m.flatten();
+    auto give = [&](const void* p, size_t n, size_t elem) { if(out && n) memcpy(out, p, n * elem); return n; };
+    switch(which) {
+        case 0: return give(f.node_first_child.data(), f.node_first_child.size(), 4);
+        case 1: return give(f.node_n_children.data(), f.node_n_children.size(), 2);
+        case 2: return give(f.node_partial_len.data(), f.node_partial_len.size(), 1);
+        case 3: return give(f.node_partial.data(), f.node_partial.size(), 1);
+        case 4: return give(h->m.child_byte.data(), h->m.child_byte.size(), 1);
+        case 5: return give(h->m.child_ref.data(), h->m.child_ref.size(), 4);
+        case 6: return give(f.leaf_key_off.data(), f.leaf_key_off.size(), 8);
+        default: return give(f.leaf_keys.data(), f.leaf_keys.size(), 1);
+    }
+}
+int32_t am_root(void* hv) { return ((handle_t*) hv)->m.root; }
 
 }

@@ -3,6 +3,7 @@
 // Built and run by tests/test_cpp_host.py on a machine with a GPU; exit code = number of failed checks.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <sstream>
 #include <string>
@@ -75,6 +76,7 @@ static tsgpu::search_options opt(uint32_t num_typos, bool prefix, size_t typo_to
                                  tsgpu::search_options::token_ordering order = tsgpu::search_options::FREQUENCY) {
     tsgpu::search_options o;
     o.num_typos = num_typos; o.prefix = prefix; o.typo_tokens_threshold = typo_tokens_threshold; o.token_order = order;
+    o.device_art_walk = getenv("TSGPU_HOST_DEVICE_ART") != nullptr;      // f-1 opt-in: candidate walks through tsgpu_art_walk_batch
     return o;
 }
 

@@ -10,6 +10,8 @@
 
 #include "../../include/tsgpu.h"
 #include "../../oracle/ts_oracle.h"
+#include "../../typesense_b200/csrc/art_device.cuh"      // art_walk(): the device function, compiled for the host
+#include <map>
 
 static_assert(sizeof(tsgpu_kv) == sizeof(tso_kv), "KV layout");
 static_assert(sizeof(tsgpu_field) == sizeof(tso_field), "field layout");
@@ -151,6 +153,48 @@ tsgpu_status tsgpu_exact_matches(tsgpu_index* idx, uint32_t field, const uint32_
 }
 tsgpu_status tsgpu_prefix_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, const uint32_t* ids, size_t n, uint32_t* out_ids, size_t* out_n) {
     *out_n = tso_prefix_matches(D(idx)->oi, field, lists, k, ids, n, out_ids);
+    return TSGPU_OK;
+}
+// f-1: no oracle exists for the walk other than the reference itself (tests/test_art_mirror.py); the double runs the device
+// function on the host so the Python side of the GPU test executes here too
+namespace {
+struct ArtCopy { std::vector<tsdev::ArtNodeDev> nodes; std::vector<uint8_t> cbyte, keys; std::vector<int32_t> cref; std::vector<uint64_t> koff; int32_t root = 0; bool empty = true; };
+std::map<std::pair<const tsgpu_index*, uint32_t>, ArtCopy> g_arts;
+}
+tsgpu_status tsgpu_index_load_art(tsgpu_index* idx, uint32_t field, const tsgpu_art* a) {
+    ArtCopy c;
+    c.nodes.resize(a->n_nodes);
+    for(uint32_t i = 0; i < a->n_nodes; i++) {
+        c.nodes[i].first_child = a->node_first_child[i]; c.nodes[i].n_children = a->node_n_children[i]; c.nodes[i].partial_len = a->node_partial_len[i];
+        memcpy(c.nodes[i].partial, a->node_partial + (size_t) i * 8, 8); c.nodes[i].pad = 0;
+    }
+    c.cbyte.assign(a->child_byte, a->child_byte + a->n_children);
+    c.cref.assign(a->child_ref, a->child_ref + a->n_children);
+    if(a->n_leaves) { c.koff.assign(a->leaf_key_off, a->leaf_key_off + a->n_leaves + 1); c.keys.assign(a->leaf_keys, a->leaf_keys + c.koff.back()); }
+    else c.koff = {0};
+    c.root = a->root; c.empty = a->n_leaves == 0;
+    g_arts[{idx, field}] = std::move(c);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, uint32_t n, const uint32_t* term_off, const uint8_t* terms, const uint8_t* min_cost,
+                                  const uint8_t* max_cost, const uint8_t* prefix, int32_t* out_hits, uint32_t cap, uint32_t* out_counts, uint8_t* out_flags) {
+    auto it = g_arts.find({idx, field});
+    if(it == g_arts.end()) { g_err = "no ART mirror loaded for this field"; return TSGPU_ERR_INVALID; }
+    const ArtCopy& c = it->second;
+    tsdev::ArtDev A{c.nodes.data(), c.cbyte.data(), c.cref.data(), c.koff.data(), c.keys.data(), c.root, c.empty ? 1u : 0u};
+    std::vector<tsdev::ArtFrame> stack(tsdev::kArtMaxStack);
+    for(uint32_t i = 0; i < n; i++) {
+        const uint32_t len = term_off[i + 1] - term_off[i];
+        if(len + (prefix[i] ? 0u : 1u) > (uint32_t) tsdev::kArtMaxQuery) { out_counts[i] = 0; out_flags[i] = 2; continue; }
+        tsdev::ArtQuery Q;
+        memcpy(Q.q, terms + term_off[i], len);
+        Q.qlen = (int) len;
+        if(!prefix[i]) Q.q[Q.qlen++] = 0;
+        Q.min_cost = min_cost[i]; Q.max_cost = max_cost[i]; Q.prefix = prefix[i] != 0;
+        bool deep = false;
+        out_counts[i] = tsdev::art_walk(A, Q, out_hits + (size_t) i * cap, cap, stack.data(), &deep);
+        out_flags[i] = deep ? 1 : (out_counts[i] > cap ? 4 : 0);
+    }
     return TSGPU_OK;
 }
 tsgpu_status tsgpu_ids_setop(tsgpu_index*, int op, const uint32_t* a, size_t na, const uint32_t* b, size_t nb, uint32_t* out_ids, size_t, size_t* out_n) {

@@ -314,3 +314,31 @@ def test_reference_art_tests(am):
         assert len(got) == counts.get(k, 1) and (k in counts or got == [k]), (k, got)
         assert _both(R, am, t, k, 0, 0, 10, FREQ, 0) == [k]
     R.ref_art_free(t)
+
+
+def test_device_walk_function_equals_the_host_walk(am):
+    """art_walk() of typesense_b200/csrc/art_device.cuh — the explicit-stack, fixed-size-row form the CUDA kernel runs per
+    thread — compiled for the host: same hit list (same subtrees, same order) as art_mirror_t::walk_hits on random
+    vocabularies, typos 0..2 (exact costs and ranges), prefix and whole-word searches."""
+    am.am_walk.restype = C.c_size_t
+    am.am_walk.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_size_t, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(909)
+    n = n_hits = 0
+    cap = 1 << 14
+    a, b = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    so = C.c_int(0)
+    for trial in range(36):
+        coll = make_collection(rng, trial)
+        toks = sorted(coll.vocab, key=coll.vocab.get)
+        df = np.diff(coll.flat.list_off.astype(np.int64)).astype(np.uint32)
+        ms = np.zeros(len(toks), np.int64)
+        h = am.am_build("\n".join(toks).encode(), ms.ctypes.data_as(C.POINTER(C.c_int64)), ol.p32(df), len(toks))
+        for q in queries(rng, coll, 70):
+            lo = q["cost"] if rng.random() < 0.7 else int(rng.integers(0, q["cost"] + 1))
+            na = am.am_walk(h, 0, q["term"].encode(), lo, q["cost"], q["prefix"], a.ctypes.data_as(C.POINTER(C.c_int32)), cap, C.byref(so))
+            nb = am.am_walk(h, 1, q["term"].encode(), lo, q["cost"], q["prefix"], b.ctypes.data_as(C.POINTER(C.c_int32)), cap, C.byref(so))
+            assert so.value == 0 and na == nb and a[:na].tolist() == b[:nb].tolist(), (trial, q["term"], lo, q["cost"], q["prefix"], na, nb)
+            n += 1
+            n_hits += na
+        am.am_free(h)
+    assert n > 2000 and n_hits > 3000, (n, n_hits)

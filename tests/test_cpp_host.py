@@ -35,6 +35,11 @@ def test_cpp_host_scenarios_on_oracle_double():
     r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "documents.jsonl")], capture_output=True, text=True, cwd=ROOT)
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
+    # once more with the candidate walks routed through tsgpu_index_load_art / tsgpu_art_walk_batch (f-1, opt-in): the
+    # double answers them with the device function compiled for the host
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "documents.jsonl")], capture_output=True, text=True, cwd=ROOT,
+                       env=dict(os.environ, TSGPU_HOST_DEVICE_ART="1"))
+    assert r.returncode == 0, r.stdout + r.stderr
 
 
 def test_specific_cases_table_is_current():

@@ -25,7 +25,8 @@ def test_gpu_tests_execute_against_the_oracle_double():
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wno-unused", "-fPIC", "-shared", os.path.join(ROOT, "tests", "cpp", "tsgpu_oracle_double.cpp"),
                            "-o", so, "-L", os.path.join(ROOT, "oracle"), "-l:liboracle.so", f"-Wl,-rpath,{os.path.join(ROOT, 'oracle')}", "-pthread"])
     env = dict(os.environ, TSGPU_TEST_DOUBLE="1", TSGPU_LIB_PATH=so)
-    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-q", "-m", "gpu", "-p", "no:cacheprovider"]
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-q", "-m", "gpu", "-p", "no:cacheprovider",
+           "--runxfail"]          # the opt-in kernels' tests are xfail(strict=False) on the GPU; their Python side must still work here
     for t in GPU_ONLY:
         cmd += ["--deselect", t]
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, env=env, timeout=1500)

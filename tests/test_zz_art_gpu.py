@@ -1,0 +1,83 @@
+"""SURVEY §8 f-1 on the GPU: tsgpu_art_walk_batch (one thread per search, art_kernels.cu) against the host walk of the same
+ART mirror (art_mirror_t::walk_hits, which tests/test_art_mirror.py pins on the reference's compiled art.cpp). The kernel was
+written after round 1's GPU budget was spent and has only run on the CPU (the same art_walk() compiled by g++), so this
+test does not gate the suite yet: it reports XPASS / XFAIL until the kernel has been seen to pass on a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import test_art_mirror as T
+from test_art_mirror import am  # noqa: F401  (fixture)
+
+DTYPES = [np.uint32, np.uint16, np.uint8, np.uint8, np.uint8, np.int32, np.uint64, np.uint8]
+
+
+def flat_arrays(am, h):
+    am.am_flat.restype = C.c_size_t
+    am.am_flat.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    am.am_root.restype = C.c_int32
+    am.am_root.argtypes = [C.c_void_p]
+    out = []
+    for which, dt in enumerate(DTYPES):
+        n = am.am_flat(h, which, None)
+        a = np.zeros(max(n, 1), dt)
+        am.am_flat(h, which, a.ctypes.data)
+        out.append(a[:n])
+    return am.am_root(h), out
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="opt-in f-1 kernel: written without GPU access, first GPU run pending (see DESIGN.md §11.3)")
+def test_art_walk_batch_matches_host_walk(am):
+    from typesense_b200 import capi
+    am.am_walk.restype = C.c_size_t
+    am.am_walk.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_size_t, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(4711)
+    cap = 512
+    buf = np.zeros(1 << 15, np.int32)
+    so = C.c_int(0)
+    total = 0
+    for trial in (0, 1, 3, 5, 9, 11):
+        coll = T.make_collection(rng, trial)
+        toks = sorted(coll.vocab, key=coll.vocab.get)
+        df = np.diff(coll.flat.list_off.astype(np.int64)).astype(np.uint32)
+        ms = np.zeros(len(toks), np.int64)
+        h = am.am_build("\n".join(toks).encode(), ms.ctypes.data_as(C.POINTER(C.c_int64)), T.ol.p32(df), len(toks))
+        root, arrs = flat_arrays(am, h)
+        gi = capi.GpuIndex(coll.n_docs, 0)
+        fid = gi.load_field(coll.flat)
+        gi.load_art(fid, root, *arrs)
+        qs = list(T.queries(rng, coll, 300))
+        hits, flags = gi.art_walk(fid, [q["term"].encode() for q in qs], [q["cost"] for q in qs], [q["cost"] for q in qs],
+                                  [q["prefix"] for q in qs], cap)
+        for q, got, fl in zip(qs, hits, flags):
+            n = am.am_walk(h, 0, q["term"].encode(), q["cost"], q["cost"], q["prefix"], buf.ctypes.data_as(C.POINTER(C.c_int32)), len(buf), C.byref(so))
+            want = buf[:n].tolist()
+            if fl == 4:
+                assert n > cap and got == want[:cap]
+            else:
+                assert fl == 0 and got == want, (trial, q["term"], q["cost"], q["prefix"], fl)
+            total += n
+        long_term = b"x" * 40
+        hits, flags = gi.art_walk(fid, [long_term], [1], [1], [0], cap)
+        assert flags[0] == 2 and hits[0] == []
+        gi.close()
+        am.am_free(h)
+    assert total > 2000
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="opt-in f-1 kernel: written without GPU access, first GPU run pending (see DESIGN.md §11.3)")
+def test_host_layer_scenarios_with_device_walk():
+    """tests/cpp/host_scenarios (the reference's typo / prefix / ranking scenarios through the C++ host layer) with every
+    candidate walk routed through tsgpu_art_walk_batch."""
+    import os
+    import subprocess
+    import test_cpp_host as tch
+    if os.environ.get("TSGPU_TEST_DOUBLE") == "1":
+        pytest.skip("links the real libtsgpu.so")
+    tch.build()
+    r = subprocess.run([tch.BIN, os.path.join(tch.ROOT, "tests", "golden", "documents.jsonl")], capture_output=True, text=True, cwd=tch.ROOT,
+                       env=dict(os.environ, TSGPU_HOST_DEVICE_ART="1"), timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]

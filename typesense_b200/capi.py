@@ -11,7 +11,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from .structs import (FieldStruct, FlatField, HnswGraph, HnswStruct, KV_DTYPE, KwBatch, KwBatchStruct, StatsStruct,
+from .structs import (ArtStruct, FieldStruct, FlatField, HnswGraph, HnswStruct, KV_DTYPE, KwBatch, KwBatchStruct, StatsStruct,
                       VecParamsStruct, f32p, i32p, u32p, u64p)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -21,7 +21,7 @@ EXPORTS = [
     "tsgpu_last_error", "tsgpu_device_count", "tsgpu_index_create", "tsgpu_index_destroy", "tsgpu_index_load_field",
     "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy",
     "tsgpu_intersect", "tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches", "tsgpu_ids_setop", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
-    "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats",
+    "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats", "tsgpu_index_load_art", "tsgpu_art_walk_batch",
 ]
 
 
@@ -61,6 +61,9 @@ def lib():
             getattr(L, n).argtypes = [vp, C.POINTER(KwBatchStruct), C.c_void_p, C.POINTER(VecParamsStruct), C.c_void_p,
                                       C.c_uint32, C.c_void_p, C.c_void_p]
         L.tsgpu_get_stats.argtypes = [vp, C.POINTER(StatsStruct)]
+        L.tsgpu_index_load_art.argtypes = [vp, C.c_uint32, C.POINTER(ArtStruct)]
+        L.tsgpu_art_walk_batch.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                           u32p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -183,6 +186,30 @@ class GpuIndex:
 
     def prefix_matches(self, field: int, lists: Sequence[int], ids: np.ndarray) -> np.ndarray:
         return self._idset(self.L.tsgpu_prefix_matches, field, lists, ids)
+
+    def load_art(self, field: int, root: int, node_first_child, node_n_children, node_partial_len, node_partial, child_byte, child_ref,
+                 leaf_key_off, leaf_keys):
+        """tsgpu_index_load_art: the flat ART mirror of a field (arrays as art_mirror_t::flatten() gives them)."""
+        arrs = [np.ascontiguousarray(node_first_child, np.uint32), np.ascontiguousarray(node_n_children, np.uint16),
+                np.ascontiguousarray(node_partial_len, np.uint8), np.ascontiguousarray(node_partial, np.uint8),
+                np.ascontiguousarray(child_byte, np.uint8), np.ascontiguousarray(child_ref, np.int32),
+                np.ascontiguousarray(leaf_key_off, np.uint64), np.ascontiguousarray(leaf_keys, np.uint8)]
+        a = ArtStruct(len(arrs[0]), len(arrs[4]), len(arrs[6]) - 1, root, *[x.ctypes.data if len(x) else None for x in arrs])
+        _ck(self.L.tsgpu_index_load_art(self.h, field, C.byref(a)))
+
+    def art_walk(self, field: int, terms: Sequence[bytes], min_cost: Sequence[int], max_cost: Sequence[int], prefix: Sequence[int], cap: int = 256):
+        """tsgpu_art_walk_batch -> (hits per search as lists of refs, flags)"""
+        n = len(terms)
+        off = np.zeros(n + 1, np.uint32)
+        off[1:] = np.cumsum([len(t) for t in terms])
+        blob = np.frombuffer(b"".join(terms) + b"\0", np.uint8).copy()
+        mn, mx, pf = (np.ascontiguousarray(x, np.uint8) for x in (min_cost, max_cost, prefix))
+        hits = np.zeros((max(n, 1), cap), np.int32)
+        cnt = np.zeros(max(n, 1), np.uint32)
+        flags = np.zeros(max(n, 1), np.uint8)
+        _ck(self.L.tsgpu_art_walk_batch(self.h, field, n, off.ctypes.data_as(u32p), blob.ctypes.data, mn.ctypes.data, mx.ctypes.data, pf.ctypes.data,
+                                        hits.ctypes.data, cap, cnt.ctypes.data_as(u32p), flags.ctypes.data))
+        return [hits[i, :min(int(cnt[i]), cap)].tolist() for i in range(n)], flags[:n].copy()
 
     def ids_setop(self, op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         """op: 0 and, 1 or, 2 exclude (a minus b)"""

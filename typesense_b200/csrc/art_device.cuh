@@ -1,0 +1,175 @@
+// The walk half of the ART fuzzy / prefix candidate search as __host__ __device__ code: which subtrees
+// of a field's token index hold keys within [min_cost, max_cost] edits of a query token.
+//
+// Replaces (reference file:line):
+//   art_fuzzy_recurse / art_fuzzy_children      src/art.cpp:1596-1738, 1435-1485   -> art_walk()
+//   fuzzy_search_state                          src/art.cpp:1487-1594              -> art_state()
+//   levenshtein_dist                            src/art.cpp:1412-1433              -> art_next_row()
+// The other half (art_topk_iter, validate_and_add_leaf, the final sort: a few dozen leaves per search) stays on the host,
+// typesense_b200/host/art_mirror.hpp::finish — whose own walk() is the readable, recursive statement of this file.
+//
+// Device use: art_walk_kernel (art_kernels.cu) runs one search per thread — a batch is (queries x tokens x typo costs), tens of
+// thousands of independent walks; each is a pointer chase through the flat node arrays, so threads rather than warps are
+// the unit. Host use: tests/hostsim compiles this header with g++ and checks the hit lists against art_mirror_t::walk_hits
+// (itself pinned on the reference's compiled art.cpp). Not measured on a GPU yet (written after round 1's GPU budget).
+//
+// The recursion of the reference becomes an explicit stack: a frame is an inner node whose own bytes have been consumed
+// (the two DP rows children start from, the byte that led here, the depth) plus the next child to visit, largest byte
+// first. A walk cannot run deep: past query length + 4 the cost exceeds every tolerance of art_state().
+#pragma once
+#include <stdint.h>
+
+#ifndef TS_HD                      // as in score_device.cuh (not included: this header stands alone in art_kernels.cu)
+#if defined(__CUDACC__)
+#define TS_HD __host__ __device__ __forceinline__
+#else
+#define TS_HD inline
+#endif
+#endif
+
+namespace tsdev {
+
+constexpr int kArtMaxQuery = 31;       // query bytes incl. the terminator of a whole-word search (one DP column each, + column 0)
+constexpr int kArtMaxStack = 48;
+constexpr int kArtPartialBytes = 8;    // MAX_PREFIX_LEN include/art.h:23
+
+struct ArtNodeDev {
+    uint32_t first_child;
+    uint16_t n_children;
+    uint8_t  partial_len;
+    uint8_t  partial[kArtPartialBytes];
+    uint8_t  pad;
+};
+
+struct ArtDev {
+    const ArtNodeDev* nodes;
+    const uint8_t*  child_byte;
+    const int32_t*  child_ref;         // >= 0 inner node, < 0 leaf ~ref
+    const uint64_t* leaf_key_off;      // keys without terminator, concatenated
+    const uint8_t*  leaf_keys;
+    int32_t root;
+    uint32_t empty;
+};
+
+struct ArtQuery {
+    uint8_t q[kArtMaxQuery + 1];
+    int qlen, min_cost, max_cost;
+    bool prefix;
+};
+
+typedef uint8_t ArtRow[kArtMaxQuery + 1];
+
+TS_HD void art_next_row(int depth, uint8_t p, uint8_t c, const ArtQuery& Q, const uint8_t* prev2, const uint8_t* prev, uint8_t* out) {
+    out[0] = (uint8_t) (prev[0] + 1);
+    for(int col = 1; col <= Q.qlen; col++) {
+        int v = prev[col - 1] + (c == Q.q[col - 1] ? 0 : 1);
+        const int ins = out[col - 1] + 1, del = prev[col] + 1;
+        if(ins < v) v = ins;
+        if(del < v) v = del;
+        if(depth > 1 && col > 1 && c == Q.q[col - 2] && p == Q.q[col - 1]) { const int tr = prev2[col - 2] + 1; if(tr < v) v = tr; }
+        out[col] = (uint8_t) v;
+    }
+}
+
+// +1 accept every key below, 0 read on, -1 give up
+TS_HD int art_state(const ArtQuery& Q, int key_index, uint8_t p, uint8_t c, const uint8_t* row) {
+    const bool key_ends = c == 0;
+    const int key_len = key_ends ? key_index : key_index + 1;
+    const int qlen = Q.qlen;
+    if(key_ends) {
+        if(row[qlen] >= Q.min_cost && row[qlen] <= Q.max_cost) return 1;
+        if(key_len > 5 && qlen > key_len && qlen - key_len <= Q.max_cost && row[key_len] >= Q.min_cost && row[key_len] <= Q.max_cost - 1) return 1;
+        return -1;
+    }
+    const int cost = row[key_len < qlen ? key_len : qlen];
+    if(Q.prefix && key_len >= qlen && cost >= Q.min_cost && cost <= Q.max_cost) return 1;
+    if(cost <= Q.max_cost) return 0;
+    if(cost == 2 || cost == 3) {
+        if((key_index + 1 < qlen && Q.q[key_index + 1] == c) || (key_index > 0 && Q.q[key_index - 1] == c)) return 0;
+    }
+    if(cost == 3 || cost == 4) {
+        if(key_index + 2 < qlen && Q.q[key_index + 1] == p && Q.q[key_index + 2] == c) return 0;
+        if(key_index > 1 && Q.q[key_index - 2] == c) return 0;
+    }
+    return -1;
+}
+
+struct ArtFrame {
+    ArtRow prev2, prev;
+    int32_t ref;
+    int16_t depth;
+    uint16_t next_child;       // children [0, next_child) are still to visit, from the top
+    uint8_t c;
+};
+
+// Writes the matching refs (walk order) to hits[0..cap) and returns how many there are (may exceed cap: caller's overflow).
+// *stack_overflow is set when the walk needed more than kArtMaxStack frames (the caller falls back to the host walk).
+TS_HD uint32_t art_walk(const ArtDev& A, const ArtQuery& Q, int32_t* hits, uint32_t cap, ArtFrame* stack, bool* stack_overflow) {
+    uint32_t n_hits = 0;
+    *stack_overflow = false;
+    if(A.empty) return 0;
+    int sp = 0;
+    ArtRow rows[3];
+    // enter(): consume the byte leading to `ref` (unless it is the root), then the node's own bytes; a leaf is decided here, an
+    // undecided inner node becomes a frame
+    int32_t ref = A.root;
+    uint8_t p = 0, c = 0;
+    int depth = A.root < 0 ? 0 : -1;
+    if(A.root < 0) { const uint64_t o = A.leaf_key_off[~A.root]; c = A.leaf_key_off[~A.root + 1] > o ? A.leaf_keys[o] : 0; }
+    for(int i = 0; i <= Q.qlen; i++) { rows[0][i] = (uint8_t) i; rows[1][i] = (uint8_t) i; }
+    bool have = true;
+    while(true) {
+        if(!have) {
+            if(sp == 0) break;
+            ArtFrame& f = stack[sp - 1];
+            if(f.next_child == 0) { sp--; continue; }
+            const ArtNodeDev& pn = A.nodes[f.ref];
+            const uint32_t k = pn.first_child + --f.next_child;
+            ref = A.child_ref[k];
+            p = f.c; c = A.child_byte[k]; depth = f.depth;
+            for(int i = 0; i <= Q.qlen; i++) { rows[0][i] = f.prev2[i]; rows[1][i] = f.prev[i]; }
+        }
+        have = false;
+        int i2 = 0, i1 = 1, i0 = 2;
+        bool decided = false;
+        // one key byte: returns false when the branch is decided
+#define ART_STEP(BYTE, ADVANCE)                                                                          \
+        {                                                                                                \
+            const uint8_t byte_ = (BYTE);                                                                \
+            if(ADVANCE) { art_next_row(depth, p, byte_, Q, rows[i2], rows[i1], rows[i0]); const int t_ = i2; i2 = i1; i1 = i0; i0 = t_; } \
+            const int a_ = art_state(Q, depth, p, byte_, rows[i1]);                                      \
+            if(a_ == 1) { if(n_hits < cap) hits[n_hits] = ref; n_hits++; }                               \
+            if(a_ != 0) decided = true; else { p = byte_; depth++; }                                     \
+        }
+        if(depth == -1) depth = 0;
+        else ART_STEP(c, !(Q.prefix && c == 0))
+        if(decided) continue;
+        if(ref < 0) {
+            const uint64_t o = A.leaf_key_off[~ref];
+            const int klen = (int) (A.leaf_key_off[~ref + 1] - o) + 1;            // with the terminator
+            const int iter_len = klen < Q.qlen + Q.max_cost ? klen : Q.qlen + Q.max_cost;
+            if(depth >= iter_len) {
+                if(art_state(Q, depth, 0, 0, rows[i1]) == 1) { if(n_hits < cap) hits[n_hits] = ref; n_hits++; }
+                continue;
+            }
+            while(depth < iter_len && !decided) {
+                c = depth < klen - 1 ? A.leaf_keys[o + depth] : 0;
+                ART_STEP(c, !(Q.prefix && c == 0))
+            }
+            continue;
+        }
+        const ArtNodeDev& n = A.nodes[ref];
+        int seen = n.partial_len < kArtPartialBytes ? n.partial_len : kArtPartialBytes;
+        for(int i = 0; i < seen && !decided; i++) { c = n.partial[i]; ART_STEP(c, true) }
+        while(!decided && seen < (int) n.partial_len && depth < Q.qlen) { c = Q.q[depth]; ART_STEP(c, true) seen++; }
+        if(decided) continue;
+#undef ART_STEP
+        if(sp == kArtMaxStack) { *stack_overflow = true; return n_hits; }
+        ArtFrame& f = stack[sp++];
+        for(int i = 0; i <= Q.qlen; i++) { f.prev2[i] = rows[i2][i]; f.prev[i] = rows[i1][i]; }
+        f.ref = ref; f.depth = (int16_t) depth; f.next_child = n.n_children; f.c = c;
+    }
+    return n_hits;
+}
+
+}  // namespace tsdev

@@ -1,0 +1,173 @@
+// tsgpu_index_load_art / tsgpu_art_walk_batch (include/tsgpu.h): the device side of the typo / prefix
+// candidate search — one thread per (token, cost) search walks the flat ART mirror with art_walk() (art_device.cuh).
+// A translation unit of its own, like kw_regscore.cu: the kernels of tsgpu.cu that were measured this round keep their
+// code byte for byte. Written after round 1's GPU budget was spent: checked on the CPU only (tests/test_art_mirror.py runs
+// art_walk() compiled for the host against the host walk and the reference's art.cpp); tests/test_zz_art_gpu.py is its
+// first run on a GPU.
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/tsgpu.h"
+#include "art_device.cuh"
+
+// tsgpu.cu
+extern "C" int tsgpu_index_device_(const tsgpu_index* idx);
+extern "C" tsgpu_status tsgpu_fail_(tsgpu_status s, const char* msg);
+
+namespace {
+
+using namespace tsdev;
+
+struct ArtState {
+    std::vector<void*> alloc;
+    ArtDev dev{};
+};
+std::mutex g_mu;
+std::unordered_map<const tsgpu_index*, std::unordered_map<uint32_t, ArtState>> g_art;
+
+void release(ArtState& s) { for(void* p: s.alloc) cudaFree(p); s.alloc.clear(); }
+
+#define CUA(call)                                                                                                  \
+    do {                                                                                                           \
+        cudaError_t e__ = (call);                                                                                  \
+        if(e__ != cudaSuccess) return tsgpu_fail_(TSGPU_ERR_CUDA, (std::string(#call) + ": " + cudaGetErrorString(e__)).c_str()); \
+    } while(0)
+
+__global__ void __launch_bounds__(64)
+art_walk_kernel(const ArtDev A, uint32_t n, const uint32_t* __restrict__ term_off, const uint8_t* __restrict__ terms,
+                const uint8_t* __restrict__ min_cost, const uint8_t* __restrict__ max_cost, const uint8_t* __restrict__ prefix,
+                int32_t* __restrict__ out_hits, uint32_t cap, uint32_t* __restrict__ out_counts, uint8_t* __restrict__ out_flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const uint32_t o = term_off[i], len = term_off[i + 1] - o;
+    const bool pre = prefix[i] != 0;
+    if(len + (pre ? 0u : 1u) > (uint32_t) kArtMaxQuery) { out_counts[i] = 0; out_flags[i] = 2; return; }
+    ArtQuery Q;
+    for(uint32_t k = 0; k < len; k++) Q.q[k] = terms[o + k];
+    Q.qlen = (int) len;
+    if(!pre) Q.q[Q.qlen++] = 0;                 // the key's terminator takes part in a whole-word match
+    Q.min_cost = min_cost[i]; Q.max_cost = max_cost[i]; Q.prefix = pre;
+    ArtFrame stack[kArtMaxStack];
+    bool deep = false;
+    const uint32_t cnt = art_walk(A, Q, out_hits + (size_t) i * cap, cap, stack, &deep);
+    out_counts[i] = cnt;
+    out_flags[i] = deep ? 1 : (cnt > cap ? 4 : 0);
+}
+
+}  // namespace
+
+// called by tsgpu_index_destroy
+extern "C" __attribute__((visibility("hidden"))) void tsgpu_art_release_(const tsgpu_index* idx) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_art.find(idx);
+    if(it == g_art.end()) return;
+    for(auto& f: it->second) release(f.second);
+    g_art.erase(it);
+}
+
+extern "C" tsgpu_status tsgpu_index_load_art(tsgpu_index* idx, uint32_t field, const tsgpu_art* a) {
+    if(!idx || !a) return tsgpu_fail_(TSGPU_ERR_INVALID, "null argument");
+    if(a->n_leaves && (!a->leaf_key_off || !a->leaf_keys)) return tsgpu_fail_(TSGPU_ERR_INVALID, "tsgpu_art: leaf arrays missing");
+    if(a->n_nodes && (!a->node_first_child || !a->node_n_children || !a->node_partial_len || !a->node_partial || !a->child_byte || !a->child_ref))
+        return tsgpu_fail_(TSGPU_ERR_INVALID, "tsgpu_art: node arrays missing");
+    CUA(cudaSetDevice(tsgpu_index_device_(idx)));
+    // validate the links once, so the kernel can follow them blindly
+    std::vector<uint32_t> first(a->n_nodes);
+    std::vector<uint16_t> nch(a->n_nodes);
+    std::vector<uint8_t> plen(a->n_nodes), part((size_t) a->n_nodes * kArtPartialBytes), cbyte(a->n_children);
+    std::vector<int32_t> cref(a->n_children);
+    std::vector<uint64_t> koff((size_t) a->n_leaves + 1);
+    if(a->n_nodes) {
+        CUA(cudaMemcpy(first.data(), a->node_first_child, first.size() * 4, cudaMemcpyDefault));
+        CUA(cudaMemcpy(nch.data(), a->node_n_children, nch.size() * 2, cudaMemcpyDefault));
+        CUA(cudaMemcpy(plen.data(), a->node_partial_len, plen.size(), cudaMemcpyDefault));
+        CUA(cudaMemcpy(part.data(), a->node_partial, part.size(), cudaMemcpyDefault));
+    }
+    if(a->n_children) {
+        CUA(cudaMemcpy(cbyte.data(), a->child_byte, cbyte.size(), cudaMemcpyDefault));
+        CUA(cudaMemcpy(cref.data(), a->child_ref, cref.size() * 4, cudaMemcpyDefault));
+    }
+    if(a->n_leaves) CUA(cudaMemcpy(koff.data(), a->leaf_key_off, koff.size() * 8, cudaMemcpyDefault));
+    auto ref_ok = [&](int32_t r) { return r >= 0 ? (uint32_t) r < a->n_nodes : (uint32_t) ~r < a->n_leaves; };
+    if(a->n_leaves && !ref_ok(a->root)) return tsgpu_fail_(TSGPU_ERR_INVALID, "tsgpu_art: root out of range");
+    for(uint32_t i = 0; i < a->n_nodes; i++)
+        if((uint64_t) first[i] + nch[i] > a->n_children) return tsgpu_fail_(TSGPU_ERR_INVALID, "tsgpu_art: child range out of bounds");
+    for(uint32_t i = 0; i < a->n_children; i++) if(!ref_ok(cref[i])) return tsgpu_fail_(TSGPU_ERR_INVALID, "tsgpu_art: child ref out of range");
+    for(uint32_t i = 0; i < a->n_leaves; i++) if(koff[i + 1] < koff[i]) return tsgpu_fail_(TSGPU_ERR_INVALID, "tsgpu_art: key offsets not ascending");
+    std::vector<uint8_t> keys(a->n_leaves ? koff[a->n_leaves] : 0);
+    if(!keys.empty()) CUA(cudaMemcpy(keys.data(), a->leaf_keys, keys.size(), cudaMemcpyDefault));
+    std::vector<ArtNodeDev> nodes(a->n_nodes);
+    for(uint32_t i = 0; i < a->n_nodes; i++) {
+        nodes[i].first_child = first[i]; nodes[i].n_children = nch[i]; nodes[i].partial_len = plen[i]; nodes[i].pad = 0;
+        for(int k = 0; k < kArtPartialBytes; k++) nodes[i].partial[k] = part[(size_t) i * kArtPartialBytes + k];
+    }
+    ArtState st;
+    auto up = [&](const void* src, size_t bytes, const void** dst) -> cudaError_t {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, bytes ? bytes : 16);
+        if(e != cudaSuccess) return e;
+        st.alloc.push_back(d);
+        *dst = d;
+        return bytes ? cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    cudaError_t e = up(nodes.data(), nodes.size() * sizeof(ArtNodeDev), (const void**) &st.dev.nodes);
+    if(e == cudaSuccess) e = up(cbyte.data(), cbyte.size(), (const void**) &st.dev.child_byte);
+    if(e == cudaSuccess) e = up(cref.data(), cref.size() * 4, (const void**) &st.dev.child_ref);
+    if(e == cudaSuccess) e = up(koff.data(), koff.size() * 8, (const void**) &st.dev.leaf_key_off);
+    if(e == cudaSuccess) e = up(keys.data(), keys.size(), (const void**) &st.dev.leaf_keys);
+    if(e != cudaSuccess) { release(st); return tsgpu_fail_(TSGPU_ERR_CUDA, cudaGetErrorString(e)); }
+    st.dev.root = a->root;
+    st.dev.empty = a->n_leaves == 0 ? 1u : 0u;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto& slot = g_art[idx][field];
+    release(slot);
+    slot = st;
+    return TSGPU_OK;
+}
+
+extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, uint32_t n, const uint32_t* term_off, const uint8_t* terms,
+                                             const uint8_t* min_cost, const uint8_t* max_cost, const uint8_t* prefix,
+                                             int32_t* out_hits, uint32_t cap, uint32_t* out_counts, uint8_t* out_flags) {
+    if(!idx) return tsgpu_fail_(TSGPU_ERR_INVALID, "null index");
+    if(n == 0) return TSGPU_OK;
+    if(!term_off || !terms || !min_cost || !max_cost || !prefix || !out_hits || !out_counts || !out_flags || cap == 0)
+        return tsgpu_fail_(TSGPU_ERR_INVALID, "null argument");
+    CUA(cudaSetDevice(tsgpu_index_device_(idx)));
+    ArtDev A;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_art.find(idx);
+        if(it == g_art.end() || !it->second.count(field)) return tsgpu_fail_(TSGPU_ERR_INVALID, "no ART mirror loaded for this field");
+        A = it->second[field].dev;
+    }
+    std::vector<uint32_t> h_off((size_t) n + 1);
+    CUA(cudaMemcpy(h_off.data(), term_off, h_off.size() * 4, cudaMemcpyDefault));
+    for(uint32_t i = 0; i < n; i++) if(h_off[i + 1] < h_off[i]) return tsgpu_fail_(TSGPU_ERR_INVALID, "term offsets not ascending");
+    const size_t n_bytes = h_off[n];
+    auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t o_off = 0, o_terms = al((size_t) (n + 1) * 4), o_min = al(o_terms + n_bytes + 1), o_max = al(o_min + n), o_pre = al(o_max + n);
+    const size_t o_cnt = al(o_pre + n), o_flag = al(o_cnt + (size_t) n * 4), o_hits = al(o_flag + n), total = o_hits + (size_t) n * cap * 4;
+    unsigned char* d = nullptr;
+    CUA(cudaMalloc(&d, total));
+    cudaError_t e = cudaMemcpy(d + o_off, h_off.data(), h_off.size() * 4, cudaMemcpyHostToDevice);
+    if(e == cudaSuccess && n_bytes) e = cudaMemcpy(d + o_terms, terms, n_bytes, cudaMemcpyDefault);
+    if(e == cudaSuccess) e = cudaMemcpy(d + o_min, min_cost, n, cudaMemcpyDefault);
+    if(e == cudaSuccess) e = cudaMemcpy(d + o_max, max_cost, n, cudaMemcpyDefault);
+    if(e == cudaSuccess) e = cudaMemcpy(d + o_pre, prefix, n, cudaMemcpyDefault);
+    if(e == cudaSuccess) {
+        art_walk_kernel<<<(n + 63) / 64, 64>>>(A, n, (const uint32_t*) (d + o_off), d + o_terms, d + o_min, d + o_max, d + o_pre,
+                                               (int32_t*) (d + o_hits), cap, (uint32_t*) (d + o_cnt), d + o_flag);
+        e = cudaGetLastError();
+    }
+    if(e == cudaSuccess) e = cudaDeviceSynchronize();
+    if(e == cudaSuccess) e = cudaMemcpy(out_counts, d + o_cnt, (size_t) n * 4, cudaMemcpyDefault);
+    if(e == cudaSuccess) e = cudaMemcpy(out_flags, d + o_flag, n, cudaMemcpyDefault);
+    if(e == cudaSuccess) e = cudaMemcpy(out_hits, d + o_hits, (size_t) n * cap * 4, cudaMemcpyDefault);
+    cudaFree(d);
+    if(e != cudaSuccess) return tsgpu_fail_(TSGPU_ERR_CUDA, cudaGetErrorString(e));
+    return TSGPU_OK;
+}

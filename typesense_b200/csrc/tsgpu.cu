@@ -20,6 +20,8 @@
 
 using namespace tsk;
 
+// art_kernels.cu keeps its state outside tsgpu_index; it frees it through this hook
+extern "C" void tsgpu_art_release_(const tsgpu_index* idx);
 // kw_regscore.cu: kw_search_kernel<true> lives in its own translation unit (see there)
 extern "C" cudaError_t tsgpu_launch_kw_search_regscore(const void* index_dev, const void* kw_params, unsigned n_units, size_t smem, cudaStream_t st);
 
@@ -785,6 +787,9 @@ tsgpu_status run_vector_stage(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan&
 extern "C" {
 
 const char* tsgpu_last_error(void) { return g_err.c_str(); }
+// for the other translation units of the library (art_kernels.cu)
+extern "C" __attribute__((visibility("hidden"))) int tsgpu_index_device_(const tsgpu_index* idx) { return idx->device; }
+extern "C" __attribute__((visibility("hidden"))) tsgpu_status tsgpu_fail_(tsgpu_status s, const char* msg) { return fail(s, msg); }
 
 int tsgpu_device_count(void) {
     int n = 0;
@@ -826,6 +831,7 @@ tsgpu_status tsgpu_index_create(uint32_t n_docs, int device, tsgpu_index** out) 
 void tsgpu_index_destroy(tsgpu_index* idx) {
     if(!idx) return;
     cudaSetDevice(idx->device);
+    tsgpu_art_release_(idx);
     cudaStreamSynchronize(idx->stream);
     for(auto& f: idx->fields) for(void* p: f.d_alloc) if(p) cudaFree(p);
     for(auto* c: idx->sort_cols) cudaFree(c);

@@ -83,6 +83,27 @@ public:
         return it == by_key.end() ? -1 : (int32_t) it->second;
     }
 
+    // the arrays of tsgpu_art (include/tsgpu.h) that are not already members: per-node columns and the key arena
+    struct flat_t {
+        std::vector<uint32_t> node_first_child;
+        std::vector<uint16_t> node_n_children;
+        std::vector<uint8_t> node_partial_len, node_partial;          // node_partial: kPartialBytes per node
+        std::vector<uint64_t> leaf_key_off;
+        std::vector<uint8_t> leaf_keys;
+    };
+    flat_t flatten() const {
+        flat_t f;
+        for(auto& n: nodes) {
+            f.node_first_child.push_back(n.first_child);
+            f.node_n_children.push_back((uint16_t) n.n_children);
+            f.node_partial_len.push_back(n.partial_len);
+            f.node_partial.insert(f.node_partial.end(), n.partial, n.partial + kPartialBytes);
+        }
+        f.leaf_key_off.push_back(0);
+        for(auto& l: leaves) { f.leaf_keys.insert(f.leaf_keys.end(), l.key.begin(), l.key.end()); f.leaf_key_off.push_back(f.leaf_keys.size()); }
+        return f;
+    }
+
     // ---- search ------------------------------------------------------------------------------------------------------
     // has_filter_doc(list): the posting list holds a document of the active filter (only consulted when filter_active);
     // share_doc(a, b): lists a and b hold a common document (that also passes the filter when one is active).
@@ -100,9 +121,15 @@ public:
     // the general form (the search path always asks for one exact cost; test/art_test.cpp uses ranges)
     std::vector<uint32_t> fuzzy_search(const std::string& term, int min_cost, int max_cost, size_t max_words, token_ordering order, bool prefix,
                                        const std::string& prev_token, const doc_tests& docs, std::set<std::string>& exclude_leaves) const {
-        std::vector<uint32_t> results;
-        if(empty) return results;
+        return finish(term, min_cost, max_words, order, prev_token, docs, exclude_leaves, walk_hits(term, min_cost, max_cost, prefix));
+    }
+
+    // The two halves of fuzzy_search. walk_hits: the subtrees / leaves whose keys match, in the order the walk meets them
+    // (the part that touches the whole tree — tsgpu_art_walk_batch computes the same list on the device for a batch of
+    // searches). finish: best leaves of those subtrees, sorted, exact token first, truncated.
+    std::vector<int32_t> walk_hits(const std::string& term, int min_cost, int max_cost, bool prefix) const {
         search_t s;
+        if(empty) return s.hits;
         s.q.assign(term.begin(), term.end());
         if(!prefix) s.q.push_back('\0');                           // the key's terminator takes part in a whole-word match
         s.min_cost = min_cost; s.max_cost = max_cost;
@@ -111,10 +138,15 @@ public:
         for(size_t i = 0; i < row0.size(); i++) row0[i] = (int) i;
         if(root < 0) walk(s, 0, (uint8_t) leaves[~root].key.c_str()[0], root, 0, row0, row0);
         else walk(s, 0, 0, root, -1, row0, row0);
-
+        return s.hits;
+    }
+    std::vector<uint32_t> finish(const std::string& term, int min_cost, size_t max_words, token_ordering order, const std::string& prev_token,
+                                 const doc_tests& docs, std::set<std::string>& exclude_leaves, const std::vector<int32_t>& hits) const {
+        std::vector<uint32_t> results;
+        if(empty) return results;
         const int32_t exact_leaf = find(term);
         const int32_t prev_leaf = find(prev_token);
-        for(int32_t n: s.hits) collect(n, order, max_words, exact_leaf, prev_token, prev_leaf, docs, exclude_leaves, results);
+        for(int32_t n: hits) collect(n, order, max_words, exact_leaf, prev_token, prev_leaf, docs, exclude_leaves, results);
         if(order == FREQUENCY) std::sort(results.begin(), results.end(), [&](uint32_t a, uint32_t b) { return leaves[a].num_ids > leaves[b].num_ids; });
         else std::sort(results.begin(), results.end(), [&](uint32_t a, uint32_t b) { return leaves[a].max_score > leaves[b].max_score; });
         if(exact_leaf >= 0 && min_cost == 0 && !exclude_leaves.count(leaves[exact_leaf].key)) {

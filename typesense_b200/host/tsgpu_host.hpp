@@ -143,6 +143,9 @@ struct search_options {
     // directions when the query has at most `drop_both_sides_token_limit` tokens
     enum drop_mode_t { right_to_left, left_to_right, both_sides } drop_tokens_mode = right_to_left;
     size_t drop_both_sides_token_limit = 0;
+    // f-1 (opt-in, not yet measured on a GPU): let the device do the tree walk of every candidate search
+    // (tsgpu_art_walk_batch); the few matching subtrees come back and art_mirror_t::finish picks the leaves on the host
+    bool device_art_walk = false;
 };
 
 // Incremental optimal-string-alignment rows as src/art.cpp:1412-1433 computes them while it walks a key: rows[i][col] =
@@ -276,6 +279,7 @@ class Index {
     // fields or sort columns (a server-side binding loads it from an export of the live art_tree instead, see art_mirror.hpp)
     mutable std::vector<art_mirror_t> arts;
     mutable std::vector<bool> arts_ready;
+    mutable std::vector<bool> arts_on_device;
     std::unordered_map<std::string, std::vector<int64_t>> sort_values;
     std::string default_sorting_field;
     std::string err;
@@ -649,7 +653,7 @@ public:
     // query) only tokens that share a document with it in this field qualify (validate_and_add_leaf, src/art.cpp:1024-1036).
     // The mirror is built from the vocabulary, so tokens of EQUAL rank may come in another order than from a live tree.
     const art_mirror_t& art_of(uint32_t fid) const {
-        if(arts.size() <= fid) { arts.resize(fid + 1); arts_ready.resize(fid + 1, false); }
+        if(arts.size() <= fid) { arts.resize(fid + 1); arts_ready.resize(fid + 1, false); arts_on_device.resize(fid + 1, false); }
         if(!arts_ready[fid]) {
             const vocab_t& v = vocabs[fid];
             const std::vector<int64_t>* scores = nullptr;
@@ -664,6 +668,7 @@ public:
             }
             arts[fid].build(entries);
             arts_ready[fid] = true;
+            arts_on_device[fid] = false;
         }
         return arts[fid];
     }
@@ -678,10 +683,33 @@ public:
             while(i < ie && j < je) { if(v.ids[i] == v.ids[j]) return true; if(v.ids[i] < v.ids[j]) i++; else j++; }
             return false;
         };
+        std::vector<int32_t> hits;
+        bool walked = false;
+        if(o.device_art_walk && !art.empty) {
+            if(!arts_on_device[fid]) {
+                const auto f = art.flatten();
+                tsgpu_art a{(uint32_t) art.nodes.size(), (uint32_t) art.child_byte.size(), (uint32_t) art.leaves.size(), art.root,
+                            f.node_first_child.data(), f.node_n_children.data(), f.node_partial_len.data(), f.node_partial.data(),
+                            art.child_byte.data(), art.child_ref.data(), f.leaf_key_off.data(), f.leaf_keys.data()};
+                arts_on_device[fid] = tsgpu_index_load_art(h, fid, &a) == TSGPU_OK;
+            }
+            if(arts_on_device[fid]) {
+                const uint32_t cap = 1024, off[2] = {0, (uint32_t) token.size()};
+                const uint8_t c8 = (uint8_t) cost, p8 = prefix_search ? 1 : 0;
+                uint32_t cnt = 0;
+                uint8_t flag = 0;
+                hits.resize(cap);
+                if(tsgpu_art_walk_batch(h, fid, 1, off, (const uint8_t*) token.data(), &c8, &c8, &p8, hits.data(), cap, &cnt, &flag) == TSGPU_OK && flag == 0) {
+                    hits.resize(cnt);
+                    walked = true;
+                }
+            }
+        }
+        if(!walked) hits = art.walk_hits(token, cost, cost, prefix_search);        // also the fallback for flagged searches
         std::vector<std::string> out;
-        for(uint32_t leaf: art.fuzzy_search(token, cost, o.max_candidates,
-                                            o.token_order == search_options::MAX_SCORE ? art_mirror_t::MAX_SCORE : art_mirror_t::FREQUENCY,
-                                            prefix_search, prev_token, docs, unique_tokens))
+        for(uint32_t leaf: art.finish(token, cost, o.max_candidates,
+                                      o.token_order == search_options::MAX_SCORE ? art_mirror_t::MAX_SCORE : art_mirror_t::FREQUENCY,
+                                      prev_token, docs, unique_tokens, hits))
             out.push_back(art.leaves[leaf].key);
         return out;
     }

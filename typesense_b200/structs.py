@@ -60,6 +60,13 @@ class VecParamsStruct(C.Structure):
                 ("distance_threshold", C.c_float), ("alpha", C.c_float), ("fetch_size", C.c_uint32)]
 
 
+class ArtStruct(C.Structure):
+    """tsgpu_art (include/tsgpu.h)"""
+    _fields_ = [("n_nodes", C.c_uint32), ("n_children", C.c_uint32), ("n_leaves", C.c_uint32), ("root", C.c_int32),
+                ("node_first_child", C.c_void_p), ("node_n_children", C.c_void_p), ("node_partial_len", C.c_void_p), ("node_partial", C.c_void_p),
+                ("child_byte", C.c_void_p), ("child_ref", C.c_void_p), ("leaf_key_off", C.c_void_p), ("leaf_keys", C.c_void_p)]
+
+
 class StatsStruct(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_kernels", C.c_float), ("ms_keyword", C.c_float), ("ms_knn", C.c_float),
                 ("ms_fuse", C.c_float), ("launches_total", C.c_uint64), ("kw_driver_ids", C.c_uint64),
