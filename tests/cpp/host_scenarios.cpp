@@ -583,6 +583,14 @@ int main(int argc, char** argv) {
     phrase_scenarios();
     synonym_scenarios();
     filter_scenarios();
+    {
+        const auto& ws = tsgpu::Index::art_walk_stats();
+        if(getenv("TSGPU_HOST_DEVICE_ART")) {
+            printf("device ART walks: %llu launches, %llu searches, %llu served from them, %llu host fallbacks\n", (unsigned long long) ws.launches,
+                   (unsigned long long) ws.searches, (unsigned long long) ws.served, (unsigned long long) ws.host_fallbacks);
+            CHECK(ws.launches > 50 && ws.served > 200 && ws.searches > ws.launches);     // batched, and really used
+        } else CHECK(ws.launches == 0);
+    }
     printf("%s (%d failed checks)\n", failures ? "FAILED" : "PASSED", failures);
     return failures;
 }

@@ -30,6 +30,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <tuple>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -280,6 +281,12 @@ class Index {
     mutable std::vector<art_mirror_t> arts;
     mutable std::vector<bool> arts_ready;
     mutable std::vector<bool> arts_on_device;
+    // device_art_walk: hit lists fetched ahead by prefetch_walks, keyed by (field, prefix search, cost, token)
+    mutable std::map<std::tuple<uint32_t, bool, int, std::string>, std::vector<int32_t>> walk_cache;
+public:
+    struct art_walk_stats_t { uint64_t launches = 0, searches = 0, served = 0, host_fallbacks = 0; };
+    static art_walk_stats_t& art_walk_stats() { static art_walk_stats_t s; return s; }     // process-wide, for tests and tuning
+private:
     std::unordered_map<std::string, std::vector<int64_t>> sort_values;
     std::string default_sorting_field;
     std::string err;
@@ -669,8 +676,58 @@ public:
             arts[fid].build(entries);
             arts_ready[fid] = true;
             arts_on_device[fid] = false;
+            walk_cache.clear();
         }
         return arts[fid];
+    }
+    struct query_token { std::string value; bool is_prefix_searched; };
+    // One tsgpu_art_walk_batch for a list of (token, cost, prefix) searches on one field; the hit lists land in walk_cache.
+    // A walk depends on nothing but these three — not on the tokens already taken, the previous token or a filter, which
+    // only enter art_mirror_t::finish — so walks may be fetched ahead of the control flow that may or may not need them.
+    struct walk_request { std::string token; int cost; bool prefix; };
+    void device_walks(uint32_t fid, const std::vector<walk_request>& reqs) const {
+        const art_mirror_t& art = art_of(fid);
+        if(art.empty || reqs.empty()) return;
+        if(!arts_on_device[fid]) {
+            const auto f = art.flatten();
+            tsgpu_art a{(uint32_t) art.nodes.size(), (uint32_t) art.child_byte.size(), (uint32_t) art.leaves.size(), art.root,
+                        f.node_first_child.data(), f.node_n_children.data(), f.node_partial_len.data(), f.node_partial.data(),
+                        art.child_byte.data(), art.child_ref.data(), f.leaf_key_off.data(), f.leaf_keys.data()};
+            arts_on_device[fid] = tsgpu_index_load_art(h, fid, &a) == TSGPU_OK;
+            if(!arts_on_device[fid]) return;
+        }
+        const uint32_t n = (uint32_t) reqs.size(), cap = 1024;
+        std::vector<uint32_t> off(1, 0), cnt(n);
+        std::vector<uint8_t> terms, cost8, pre8, flags(n);
+        for(auto& r: reqs) {
+            terms.insert(terms.end(), r.token.begin(), r.token.end());
+            off.push_back((uint32_t) terms.size());
+            cost8.push_back((uint8_t) r.cost); pre8.push_back(r.prefix ? 1 : 0);
+        }
+        terms.push_back(0);
+        std::vector<int32_t> hits((size_t) n * cap);
+        if(tsgpu_art_walk_batch(h, fid, n, off.data(), terms.data(), cost8.data(), cost8.data(), pre8.data(), hits.data(), cap, cnt.data(), flags.data()) != TSGPU_OK)
+            return;
+        art_walk_stats().launches++; art_walk_stats().searches += n;
+        for(uint32_t i = 0; i < n; i++)
+            if(flags[i] == 0)            // flagged searches stay out of the cache: fuzzy_candidates walks them on the host
+                walk_cache[std::make_tuple(fid, reqs[i].prefix, reqs[i].cost, reqs[i].token)] =
+                    std::vector<int32_t>(hits.begin() + (size_t) i * cap, hits.begin() + (size_t) i * cap + cnt[i]);
+    }
+    // Every walk fuzzy_search_fields could ask for — each token at each cost its length allows, in each searched field — in
+    // one launch per field ("lets all cost combinations be speculated in one launch").
+    void prefetch_walks(const std::vector<query_token>& query_tokens, const std::vector<std::string>& the_fields, const search_options& o) const {
+        for(auto& fn: the_fields) {
+            const uint32_t fid = field_ids.at(fn);
+            std::vector<walk_request> reqs;
+            for(auto& t: query_tokens) {
+                const int max_cost = std::min<int>((int) o.num_typos, get_bounded_typo_cost(2, t.value, o.min_len_1typo, o.min_len_2typo));
+                const bool prefix_search = o.prefix && t.is_prefix_searched;
+                for(int c = 0; c <= max_cost; c++)
+                    if(!walk_cache.count(std::make_tuple(fid, prefix_search, c, t.value))) reqs.push_back({t.value, c, prefix_search});
+            }
+            device_walks(fid, reqs);
+        }
     }
     std::vector<std::string> fuzzy_candidates(uint32_t fid, const std::string& token, int cost, bool prefix_search,
                                               std::set<std::string>& unique_tokens, const search_options& o,
@@ -686,24 +743,13 @@ public:
         std::vector<int32_t> hits;
         bool walked = false;
         if(o.device_art_walk && !art.empty) {
-            if(!arts_on_device[fid]) {
-                const auto f = art.flatten();
-                tsgpu_art a{(uint32_t) art.nodes.size(), (uint32_t) art.child_byte.size(), (uint32_t) art.leaves.size(), art.root,
-                            f.node_first_child.data(), f.node_n_children.data(), f.node_partial_len.data(), f.node_partial.data(),
-                            art.child_byte.data(), art.child_ref.data(), f.leaf_key_off.data(), f.leaf_keys.data()};
-                arts_on_device[fid] = tsgpu_index_load_art(h, fid, &a) == TSGPU_OK;
+            auto hit = walk_cache.find(std::make_tuple(fid, prefix_search, cost, token));
+            if(hit == walk_cache.end()) {             // not speculated by prefetch_walks: fetch this one search
+                device_walks(fid, {{token, cost, prefix_search}});
+                hit = walk_cache.find(std::make_tuple(fid, prefix_search, cost, token));
             }
-            if(arts_on_device[fid]) {
-                const uint32_t cap = 1024, off[2] = {0, (uint32_t) token.size()};
-                const uint8_t c8 = (uint8_t) cost, p8 = prefix_search ? 1 : 0;
-                uint32_t cnt = 0;
-                uint8_t flag = 0;
-                hits.resize(cap);
-                if(tsgpu_art_walk_batch(h, fid, 1, off, (const uint8_t*) token.data(), &c8, &c8, &p8, hits.data(), cap, &cnt, &flag) == TSGPU_OK && flag == 0) {
-                    hits.resize(cnt);
-                    walked = true;
-                }
-            }
+            if(hit != walk_cache.end()) { hits = hit->second; walked = true; art_walk_stats().served++; }
+            else art_walk_stats().host_fallbacks++;
         }
         if(!walked) hits = art.walk_hits(token, cost, cost, prefix_search);        // also the fallback for flagged searches
         std::vector<std::string> out;
@@ -714,7 +760,6 @@ public:
         return out;
     }
 
-    struct query_token { std::string value; bool is_prefix_searched; };
     struct tok_candidates { query_token token; int cost; std::vector<std::string> candidates; };
     struct search_state {              // what Index::search threads through its rounds
         host_topster_t topster;
@@ -773,6 +818,7 @@ public:
                                      const std::vector<std::string>& the_fields, const std::vector<sort_by>& sort_fields,
                                      size_t topster_size, const search_options& o, search_state& st) {
         if(query_tokens.empty()) return Option<bool>(true);
+        if(o.device_art_walk) prefetch_walks(query_tokens, the_fields, o);
         std::vector<std::vector<int>> token_to_costs;
         for(auto& t: query_tokens) {
             std::vector<int> all;
