@@ -84,12 +84,13 @@ TS_HD int art_state(const ArtQuery& Q, int key_index, uint8_t p, uint8_t c, cons
     const int cost = row[key_len < qlen ? key_len : qlen];
     if(Q.prefix && key_len >= qlen && cost >= Q.min_cost && cost <= Q.max_cost) return 1;
     if(cost <= Q.max_cost) return 0;
+    // query bytes behind the query's end read as 0 (the reference reads them unguarded, src/art.cpp:1557, 1587): never a key byte
     if(cost == 2 || cost == 3) {
-        if((key_index + 1 < qlen && Q.q[key_index + 1] == c) || (key_index > 0 && Q.q[key_index - 1] == c)) return 0;
+        if((key_index + 1 < qlen && Q.q[key_index + 1] == c) || (key_index > 0 && key_index - 1 < qlen && Q.q[key_index - 1] == c)) return 0;
     }
     if(cost == 3 || cost == 4) {
         if(key_index + 2 < qlen && Q.q[key_index + 1] == p && Q.q[key_index + 2] == c) return 0;
-        if(key_index > 1 && Q.q[key_index - 2] == c) return 0;
+        if(key_index > 1 && key_index - 2 < qlen && Q.q[key_index - 2] == c) return 0;
     }
     return -1;
 }

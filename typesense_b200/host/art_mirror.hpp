@@ -265,7 +265,9 @@ private:
         const int cost = row[std::min(key_len, qlen)];
         if(s.prefix && key_len >= qlen && within(cost, s.max_cost)) return 1;
         if(cost <= s.max_cost) return 0;
-        auto qat = [&](int i) { return s.q[(size_t) i]; };
+        // The reference reads query[key_index - 1] / [key_index - 2] without a bound (src/art.cpp:1557, 1587); once the key is
+        // longer than the query that is the terminator or memory behind it. Defined here as 0, which never equals a key byte.
+        auto qat = [&](int i) -> uint8_t { return i >= 0 && i < qlen ? s.q[(size_t) i] : 0; };
         if(cost == 2 || cost == 3) {
             if((key_index + 1 < qlen && qat(key_index + 1) == c) || (key_index > 0 && qat(key_index - 1) == c)) return 0;
         }
