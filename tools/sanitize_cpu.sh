@@ -1,7 +1,7 @@
 #!/bin/bash
 # AddressSanitizer + UBSan over everything of the product that can execute without a GPU: the __host__ __device__ functions
 # (scoring, block probe, ART walk) compiled for the host, the ART mirror, and the C++ host layer on the test double.
-# usage: tools/sanitize_cpu.sh   (from the repo root; ~2 min)
+# usage: tools/sanitize_cpu.sh   (from the repo root; ~3 min)
 set -e
 cd "$(dirname "$0")/.."
 SAN="-std=c++17 -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer"
@@ -19,4 +19,11 @@ g++ $SAN -fPIC -shared -x c++ tests/hostsim/hostsim.cpp -o tests/hostsim/libhost
 LD_PRELOAD="$(g++ -print-file-name=libasan.so) $(g++ -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0:verify_asan_link_order=0 \
     python -m pytest tests/test_hostsim.py -x -q -p no:cacheprovider | tail -1
 [ -f $OUT/keep.so ] && cp $OUT/keep.so tests/hostsim/libhostsim.so && touch tests/hostsim/libhostsim.so
+echo "== the CPU oracle itself (the checker) under the reference KATs and scenario replays"
+cp oracle/liboracle.so $OUT/oracle_keep.so
+g++ $SAN -fPIC -Wno-unused -pthread -mavx2 -mfma -shared oracle/ts_oracle.cpp -o oracle/liboracle.so
+LD_PRELOAD="$(g++ -print-file-name=libasan.so) $(g++ -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0:verify_asan_link_order=0 \
+    python -m pytest tests/test_oracle_ref.py tests/test_reference_scenarios.py tests/test_hybrid_reference_kat.py tests/test_filter_scenarios.py \
+    tests/test_sorting_scenarios.py tests/test_typo_scenarios.py tests/test_synonym_scenarios.py -x -q -m "not gpu" -p no:cacheprovider | tail -1
+cp $OUT/oracle_keep.so oracle/liboracle.so && touch oracle/liboracle.so
 rm -rf $OUT
