@@ -385,7 +385,10 @@ TS_HD_NOINLINE int64_t score_field_plain(const ScoreParams& P, bool single_exact
 // whichever of them leaves first, the multiset of offsets of every later round is the same — so the reference's
 // tie order (stable insertion sort) need not be tracked; and "this was the token's last position" can be tested by
 // value exactly as the reference does.
-constexpr int kSmallTokens = 4;
+#ifndef TSGPU_SMALL_TOKENS
+#define TSGPU_SMALL_TOKENS 4            // -DTSGPU_SMALL_TOKENS=3: leaner loops, 4-row combinations fall back to score_field_plain()
+#endif
+constexpr int kSmallTokens = TSGPU_SMALL_TOKENS;
 
 template <int MAXT>
 TS_HD MatchOut match_window_small(const uint32_t* const (&tp)[MAXT], const uint32_t (&tn)[MAXT], uint32_t present, int n_all,
