@@ -26,10 +26,25 @@ struct ArtState {
     std::vector<void*> alloc;
     ArtDev dev{};
 };
-std::mutex g_mu;
-std::unordered_map<const tsgpu_index*, std::unordered_map<uint32_t, ArtState>> g_art;
+// per tsgpu_index: the fields' mirrors, a stream of its own and a grow-only staging buffer; walk calls on one index serialise
+struct ArtIndexState {
+    std::unordered_map<uint32_t, ArtState> fields;
+    cudaStream_t stream = nullptr;
+    unsigned char* scratch = nullptr;
+    size_t scratch_cap = 0;
+    std::mutex call_mu;
+};
+std::mutex g_mu;                                                       // guards the table itself
+std::unordered_map<const tsgpu_index*, ArtIndexState*> g_art;
 
 void release(ArtState& s) { for(void* p: s.alloc) cudaFree(p); s.alloc.clear(); }
+ArtIndexState* state_of(const tsgpu_index* idx, bool create) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_art.find(idx);
+    if(it != g_art.end()) return it->second;
+    if(!create) return nullptr;
+    return g_art[idx] = new ArtIndexState;
+}
 
 #define CUA(call)                                                                                                  \
     do {                                                                                                           \
@@ -62,11 +77,18 @@ art_walk_kernel(const ArtDev A, uint32_t n, const uint32_t* __restrict__ term_of
 
 // called by tsgpu_index_destroy
 extern "C" __attribute__((visibility("hidden"))) void tsgpu_art_release_(const tsgpu_index* idx) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_art.find(idx);
-    if(it == g_art.end()) return;
-    for(auto& f: it->second) release(f.second);
-    g_art.erase(it);
+    ArtIndexState* st = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_art.find(idx);
+        if(it == g_art.end()) return;
+        st = it->second;
+        g_art.erase(it);
+    }
+    for(auto& f: st->fields) release(f.second);
+    if(st->scratch) cudaFree(st->scratch);
+    if(st->stream) cudaStreamDestroy(st->stream);
+    delete st;
 }
 
 extern "C" tsgpu_status tsgpu_index_load_art(tsgpu_index* idx, uint32_t field, const tsgpu_art* a) {
@@ -122,8 +144,9 @@ extern "C" tsgpu_status tsgpu_index_load_art(tsgpu_index* idx, uint32_t field, c
     if(e != cudaSuccess) { release(st); return tsgpu_fail_(TSGPU_ERR_CUDA, cudaGetErrorString(e)); }
     st.dev.root = a->root;
     st.dev.empty = a->n_leaves == 0 ? 1u : 0u;
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto& slot = g_art[idx][field];
+    ArtIndexState* is = state_of(idx, true);
+    std::lock_guard<std::mutex> lk(is->call_mu);
+    auto& slot = is->fields[field];
     release(slot);
     slot = st;
     return TSGPU_OK;
@@ -137,13 +160,12 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
     if(!term_off || !terms || !min_cost || !max_cost || !prefix || !out_hits || !out_counts || !out_flags || cap == 0)
         return tsgpu_fail_(TSGPU_ERR_INVALID, "null argument");
     CUA(cudaSetDevice(tsgpu_index_device_(idx)));
-    ArtDev A;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        auto it = g_art.find(idx);
-        if(it == g_art.end() || !it->second.count(field)) return tsgpu_fail_(TSGPU_ERR_INVALID, "no ART mirror loaded for this field");
-        A = it->second[field].dev;
-    }
+    ArtIndexState* is = state_of(idx, false);
+    if(!is) return tsgpu_fail_(TSGPU_ERR_INVALID, "no ART mirror loaded for this index");
+    std::lock_guard<std::mutex> lk(is->call_mu);
+    auto fit = is->fields.find(field);
+    if(fit == is->fields.end()) return tsgpu_fail_(TSGPU_ERR_INVALID, "no ART mirror loaded for this field");
+    const ArtDev A = fit->second.dev;
     std::vector<uint32_t> h_off((size_t) n + 1);
     CUA(cudaMemcpy(h_off.data(), term_off, h_off.size() * 4, cudaMemcpyDefault));
     for(uint32_t i = 0; i < n; i++) if(h_off[i + 1] < h_off[i]) return tsgpu_fail_(TSGPU_ERR_INVALID, "term offsets not ascending");
@@ -151,23 +173,26 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
     auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
     const size_t o_off = 0, o_terms = al((size_t) (n + 1) * 4), o_min = al(o_terms + n_bytes + 1), o_max = al(o_min + n), o_pre = al(o_max + n);
     const size_t o_cnt = al(o_pre + n), o_flag = al(o_cnt + (size_t) n * 4), o_hits = al(o_flag + n), total = o_hits + (size_t) n * cap * 4;
-    unsigned char* d = nullptr;
-    CUA(cudaMalloc(&d, total));
-    cudaError_t e = cudaMemcpy(d + o_off, h_off.data(), h_off.size() * 4, cudaMemcpyHostToDevice);
-    if(e == cudaSuccess && n_bytes) e = cudaMemcpy(d + o_terms, terms, n_bytes, cudaMemcpyDefault);
-    if(e == cudaSuccess) e = cudaMemcpy(d + o_min, min_cost, n, cudaMemcpyDefault);
-    if(e == cudaSuccess) e = cudaMemcpy(d + o_max, max_cost, n, cudaMemcpyDefault);
-    if(e == cudaSuccess) e = cudaMemcpy(d + o_pre, prefix, n, cudaMemcpyDefault);
-    if(e == cudaSuccess) {
-        art_walk_kernel<<<(n + 63) / 64, 64>>>(A, n, (const uint32_t*) (d + o_off), d + o_terms, d + o_min, d + o_max, d + o_pre,
-                                               (int32_t*) (d + o_hits), cap, (uint32_t*) (d + o_cnt), d + o_flag);
-        e = cudaGetLastError();
+    if(!is->stream) CUA(cudaStreamCreateWithFlags(&is->stream, cudaStreamNonBlocking));
+    if(total > is->scratch_cap) {
+        if(is->scratch) cudaFree(is->scratch);
+        is->scratch = nullptr; is->scratch_cap = 0;
+        CUA(cudaMalloc(&is->scratch, total + total / 4));
+        is->scratch_cap = total + total / 4;
     }
-    if(e == cudaSuccess) e = cudaDeviceSynchronize();
-    if(e == cudaSuccess) e = cudaMemcpy(out_counts, d + o_cnt, (size_t) n * 4, cudaMemcpyDefault);
-    if(e == cudaSuccess) e = cudaMemcpy(out_flags, d + o_flag, n, cudaMemcpyDefault);
-    if(e == cudaSuccess) e = cudaMemcpy(out_hits, d + o_hits, (size_t) n * cap * 4, cudaMemcpyDefault);
-    cudaFree(d);
-    if(e != cudaSuccess) return tsgpu_fail_(TSGPU_ERR_CUDA, cudaGetErrorString(e));
+    unsigned char* d = is->scratch;
+    cudaStream_t st = is->stream;
+    CUA(cudaMemcpyAsync(d + o_off, h_off.data(), h_off.size() * 4, cudaMemcpyHostToDevice, st));
+    if(n_bytes) CUA(cudaMemcpyAsync(d + o_terms, terms, n_bytes, cudaMemcpyDefault, st));
+    CUA(cudaMemcpyAsync(d + o_min, min_cost, n, cudaMemcpyDefault, st));
+    CUA(cudaMemcpyAsync(d + o_max, max_cost, n, cudaMemcpyDefault, st));
+    CUA(cudaMemcpyAsync(d + o_pre, prefix, n, cudaMemcpyDefault, st));
+    art_walk_kernel<<<(n + 63) / 64, 64, 0, st>>>(A, n, (const uint32_t*) (d + o_off), d + o_terms, d + o_min, d + o_max, d + o_pre,
+                                                  (int32_t*) (d + o_hits), cap, (uint32_t*) (d + o_cnt), d + o_flag);
+    CUA(cudaGetLastError());
+    CUA(cudaMemcpyAsync(out_counts, d + o_cnt, (size_t) n * 4, cudaMemcpyDefault, st));
+    CUA(cudaMemcpyAsync(out_flags, d + o_flag, n, cudaMemcpyDefault, st));
+    CUA(cudaMemcpyAsync(out_hits, d + o_hits, (size_t) n * cap * 4, cudaMemcpyDefault, st));
+    CUA(cudaStreamSynchronize(st));              // h_off and the caller's buffers are done with
     return TSGPU_OK;
 }
