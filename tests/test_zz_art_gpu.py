@@ -29,7 +29,23 @@ def flat_arrays(am, h):
 
 @pytest.mark.gpu
 @pytest.mark.xfail(strict=False, reason="opt-in f-1 kernel: written without GPU access, first GPU run pending (see DESIGN.md §11.3)")
-def test_art_walk_batch_matches_host_walk(am):
+def test_art_walk_batch_matches_host_walk():
+    """Runs the check below in a child process: a kernel that has never run may fault, and a poisoned CUDA context must not
+    reach the fixtures of the tests that gate the suite."""
+    import os
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider",
+                        "-k", "child_art_walk"], env=dict(os.environ, TSGPU_ART_CHILD="1"), capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and " passed" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+@pytest.mark.gpu
+def test_child_art_walk_batch_matches_host_walk(am):
+    import os
+    if os.environ.get("TSGPU_ART_CHILD") != "1":
+        pytest.skip("runs inside test_art_walk_batch_matches_host_walk's child process")
     from typesense_b200 import capi
     am.am_walk.restype = C.c_size_t
     am.am_walk.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_size_t, C.POINTER(C.c_int)]
