@@ -160,6 +160,28 @@ static void collection_scenarios(const std::string& jsonl) {
             CHECK(ids == c.expect);
             if(c.found >= 0) CHECK((long) found == c.found);
         }
+        // the same searches as ONE multi_search (src/core_api.cpp:1080): identical answers; with the device walk switched on all of
+        // their candidate walks are fetched ahead in one launch
+        {
+            std::vector<tsgpu::Index::search_request> reqs;
+            for(auto& c: cases) reqs.push_back({tsgpu::tokenize_ascii(c.q), {"title"}, sort_fields, c.drop, 250, c.o});
+            index.clear_walk_cache();
+            const auto before = tsgpu::Index::art_walk_stats();
+            auto resps = index.multi_search(reqs);
+            if(getenv("TSGPU_HOST_DEVICE_ART")) {      // 15 searches, one field: one launch up front carries (nearly) all walks
+                const auto& after = tsgpu::Index::art_walk_stats();
+                printf("multi_search: %llu launches for %llu walks\n", (unsigned long long) (after.launches - before.launches),
+                       (unsigned long long) (after.searches - before.searches));
+                CHECK(after.searches - before.searches >= 20 && after.launches - before.launches <= 2);
+            }
+            for(size_t i = 0; i < cases.size(); i++) {
+                CHECK(resps[i].status.ok());
+                auto ids = ids_of(resps[i].raw_result_kvs);
+                if(ids.size() > cases[i].per_page) ids.resize(cases[i].per_page);
+                CHECK(ids == cases[i].expect);
+                if(cases[i].found >= 0) CHECK((long) resps[i].found == cases[i].found);
+            }
+        }
         CHECK(index.search(tsgpu::tokenize_ascii("redundant"), {"title"}, sort_fields, 10, 250, kvs, found, opt(2, true, 0)).ok());
         CHECK(kvs.size() == 1 && found == 1);
         CHECK(index.search(tsgpu::tokenize_ascii("redundant"), {"title"}, sort_fields, 10, 250, kvs, found, opt(2, true, 10)).ok());

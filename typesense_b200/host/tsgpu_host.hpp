@@ -286,6 +286,7 @@ class Index {
 public:
     struct art_walk_stats_t { uint64_t launches = 0, searches = 0, served = 0, host_fallbacks = 0; };
     static art_walk_stats_t& art_walk_stats() { static art_walk_stats_t s; return s; }     // process-wide, for tests and tuning
+    void clear_walk_cache() { walk_cache.clear(); }
 private:
     std::unordered_map<std::string, std::vector<int64_t>> sort_values;
     std::string default_sorting_field;
@@ -949,6 +950,46 @@ public:
         raw_result_kvs = st.topster.sort();
         found = st.all_result_ids.size();
         return Option<bool>(true);
+    }
+
+    // The searches of one multi_search (src/core_api.cpp:1080-1131 runs them one after the other). With device_art_walk every
+    // candidate walk any of them can ask for — each token of each request (and of its synonym variants) at each cost its
+    // length allows — is fetched first: one tsgpu_art_walk_batch per field for the whole request list.
+    struct search_request {
+        std::vector<std::string> tokens, the_fields;
+        std::vector<sort_by> sort_fields;
+        size_t drop_tokens_threshold = 1, topster_size = 250;
+        search_options opts;
+    };
+    struct search_response { Option<bool> status{true}; std::vector<KV> raw_result_kvs; size_t found = 0; };
+    std::vector<search_response> multi_search(const std::vector<search_request>& requests) {
+        std::map<uint32_t, std::vector<walk_request>> per_field;
+        std::set<std::tuple<uint32_t, bool, int, std::string>> asked;
+        for(auto& r: requests) {
+            if(!r.opts.device_art_walk) continue;
+            std::vector<std::vector<std::string>> variants = {r.tokens};
+            variants.insert(variants.end(), r.opts.synonyms.begin(), r.opts.synonyms.end());
+            for(size_t v = 0; v < variants.size(); v++) for(size_t i = 0; i < variants[v].size(); i++) {
+                const std::string& t = variants[v][i];
+                const bool prefix_search = r.opts.prefix && i + 1 == variants[v].size();
+                const int max_cost = v ? 0 : std::min<int>((int) r.opts.num_typos, get_bounded_typo_cost(2, t, r.opts.min_len_1typo, r.opts.min_len_2typo));
+                for(auto& fn: r.the_fields) {
+                    const uint32_t fid = field_ids.at(fn);
+                    for(int c = 0; c <= max_cost; c++) {
+                        const auto key = std::make_tuple(fid, prefix_search, c, t);
+                        if(walk_cache.count(key) || !asked.insert(key).second) continue;
+                        per_field[fid].push_back({t, c, prefix_search});
+                    }
+                }
+            }
+        }
+        for(auto& pf: per_field) device_walks(pf.first, pf.second);
+        std::vector<search_response> out(requests.size());
+        for(size_t i = 0; i < requests.size(); i++) {
+            const auto& r = requests[i];
+            out[i].status = search(r.tokens, r.the_fields, r.sort_fields, r.drop_tokens_threshold, r.topster_size, out[i].raw_result_kvs, out[i].found, r.opts);
+        }
+        return out;
     }
 
     // the drop-tokens loop of Index::search (src/index.cpp:3920-4017) for one query variant
