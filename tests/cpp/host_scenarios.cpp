@@ -167,7 +167,19 @@ static void collection_scenarios(const std::string& jsonl) {
             for(auto& c: cases) reqs.push_back({tsgpu::tokenize_ascii(c.q), {"title"}, sort_fields, c.drop, 250, c.o});
             index.clear_walk_cache();
             const auto before = tsgpu::Index::art_walk_stats();
-            auto resps = index.multi_search(reqs);
+            const uint64_t calls0 = tsgpu::Index::kw_device_calls();
+            auto seq = index.multi_search(reqs, /*in_lockstep=*/false);
+            const uint64_t calls_seq = tsgpu::Index::kw_device_calls() - calls0;
+            auto resps = index.multi_search(reqs);                        // lock-step: pending queries of all searches share a device call
+            const uint64_t calls_lock = tsgpu::Index::kw_device_calls() - calls0 - calls_seq;
+            printf("multi_search of %zu searches: %llu keyword device calls one by one, %llu in lock-step\n", reqs.size(),
+                   (unsigned long long) calls_seq, (unsigned long long) calls_lock);
+            CHECK(calls_lock * 3 <= calls_seq && seq.size() == resps.size());
+            for(size_t i = 0; i < seq.size(); i++) {
+                CHECK(seq[i].found == resps[i].found && ids_of(seq[i].raw_result_kvs) == ids_of(resps[i].raw_result_kvs));
+                for(size_t k = 0; k < seq[i].raw_result_kvs.size() && k < resps[i].raw_result_kvs.size(); k++)
+                    CHECK(seq[i].raw_result_kvs[k].scores[0] == resps[i].raw_result_kvs[k].scores[0]);
+            }
             if(getenv("TSGPU_HOST_DEVICE_ART")) {      // 15 searches, one field: one launch up front carries (nearly) all walks
                 const auto& after = tsgpu::Index::art_walk_stats();
                 printf("multi_search: %llu launches for %llu walks\n", (unsigned long long) (after.launches - before.launches),

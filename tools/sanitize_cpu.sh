@@ -13,6 +13,10 @@ echo "== C++ host layer on the oracle double (host walk, then device-walk marsha
 g++ $SAN -Wno-unused tests/cpp/host_scenarios.cpp tests/cpp/tsgpu_oracle_double.cpp -o $OUT/hs -L oracle -l:liboracle.so -Wl,-rpath,$PWD/oracle -pthread
 ASAN_OPTIONS=detect_leaks=0 $OUT/hs tests/golden/documents.jsonl | tail -1
 TSGPU_HOST_DEVICE_ART=1 ASAN_OPTIONS=detect_leaks=0 $OUT/hs tests/golden/documents.jsonl | tail -1
+echo "== ThreadSanitizer: the lock-step multi_search of the C++ host layer"
+g++ -std=c++17 -O1 -g -fsanitize=thread -fno-omit-frame-pointer -Wno-unused tests/cpp/host_scenarios.cpp tests/cpp/tsgpu_oracle_double.cpp -o $OUT/hs_tsan \
+    -L oracle -l:liboracle.so -Wl,-rpath,$PWD/oracle -pthread
+TSGPU_HOST_DEVICE_ART=1 $OUT/hs_tsan tests/golden/documents.jsonl 2>&1 | grep -E "WARNING: ThreadSanitizer|PASSED|FAIL" | sort | uniq -c
 echo "== device scoring / probing functions through tests/test_hostsim.py"
 cp tests/hostsim/libhostsim.so $OUT/keep.so 2>/dev/null || true
 g++ $SAN -fPIC -shared -x c++ tests/hostsim/hostsim.cpp -o tests/hostsim/libhostsim.so

@@ -28,6 +28,9 @@
 #include <algorithm>
 #include <cstdint>
 #include <map>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
 #include <set>
 #include <string>
 #include <tuple>
@@ -416,59 +419,153 @@ public:
                                       bool prioritize_token_position = false, bool prioritize_num_matching_fields = true,
                                       int text_match_type = TSGPU_MATCH_MAX_SCORE, int syn_orig_num_tokens = -1, int orig_num_tokens = -1,
                                       bool is_synonym_query = false, bool demote_synonym_match = false) {
+        kw_query q;
         const uint32_t F = (uint32_t) the_fields.size();
-        std::vector<uint32_t> fids(F);
-        for(uint32_t f = 0; f < F; f++) fids[f] = field_ids.at(the_fields[f]);
-        std::vector<uint32_t> c_tok_off{0}, t_list, c_cost;
-        std::vector<uint8_t> c_nreq;
+        q.fids.resize(F);
+        for(uint32_t f = 0; f < F; f++) q.fids[f] = field_ids.at(the_fields[f]);
+        q.c_tok_off = {0};
         size_t n_query_tokens = 0;
         for(size_t c = 0; c < query_suggestions.size(); c++) {
             const auto& toks = query_suggestions[c];
-            for(auto& t: toks) for(uint32_t f = 0; f < F; f++) t_list.push_back(token_id(fids[f], t));
-            c_tok_off.push_back(c_tok_off.back() + (uint32_t) toks.size());
-            c_nreq.push_back((uint8_t) (toks.size() - n_dropped));
-            c_cost.push_back(c < total_costs.size() ? total_costs[c] : 0);
+            for(auto& t: toks) for(uint32_t f = 0; f < F; f++) q.t_list.push_back(token_id(q.fids[f], t));
+            q.c_tok_off.push_back(q.c_tok_off.back() + (uint32_t) toks.size());
+            q.c_nreq.push_back((uint8_t) (toks.size() - n_dropped));
+            q.c_cost.push_back(c < total_costs.size() ? total_costs[c] : 0);
             n_query_tokens = toks.size() - n_dropped;
         }
-        uint32_t q_combo_off[2] = {0, (uint32_t) query_suggestions.size()};
-        int32_t q_filter = filter_by_provided ? 0 : -1;
-        uint32_t q_excl_off[2] = {0, (uint32_t) excluded_result_ids.size()};
-        uint32_t q_topk = (uint32_t) std::min<size_t>(topster_size, TSGPU_MAX_TOPK);
-        uint8_t sort_type[3] = {0, 0, 0}, missing_first[3] = {0, 0, 0};
-        int32_t sort_col[3] = {-1, -1, -1};
-        int8_t sort_order[3] = {1, 1, 1};
+        q.has_filter = filter_by_provided;
+        q.filter_ids = filter_ids;
+        q.excl = excluded_result_ids;
+        q.topk = (uint32_t) std::min<size_t>(topster_size, TSGPU_MAX_TOPK);
         for(size_t i = 0; i < sort_fields.size() && i < 3; i++) {
-            sort_type[i] = (uint8_t) sort_fields[i].type;
-            sort_order[i] = sort_fields[i].desc ? 1 : -1;
-            missing_first[i] = sort_fields[i].missing_first;
-            if(sort_fields[i].type == sort_by::numeric) sort_col[i] = (int32_t) sort_cols.at(sort_fields[i].name);
+            q.sort_type[i] = (uint8_t) sort_fields[i].type;
+            q.sort_order[i] = sort_fields[i].desc ? 1 : -1;
+            q.missing_first[i] = sort_fields[i].missing_first;
+            if(sort_fields[i].type == sort_by::numeric) q.sort_col[i] = (int32_t) sort_cols.at(sort_fields[i].name);
         }
-        uint8_t q_flags = (uint8_t) ((prioritize_exact_match ? TSGPU_FLAG_PRIORITIZE_EXACT_MATCH : 0) |
-                                     (prioritize_token_position ? TSGPU_FLAG_PRIORITIZE_TOKEN_POSITION : 0) |
-                                     (prioritize_num_matching_fields ? TSGPU_FLAG_PRIORITIZE_NUM_MATCHING_FIELDS : 0));
-        uint8_t q_match_type = (uint8_t) text_match_type;
-        uint8_t q_nqt = (uint8_t) n_query_tokens;
-        uint64_t filter_off[2] = {0, filter_ids.size()};
-        const uint32_t zero = 0;
-        tsgpu_kw_batch b{};
-        b.n_queries = 1; b.n_combos = (uint32_t) query_suggestions.size(); b.n_fields = F; b.n_filters = filter_by_provided ? 1 : 0;
-        b.field_ids = fids.data(); b.q_combo_off = q_combo_off; b.q_filter = &q_filter; b.q_excl_off = q_excl_off;
-        b.excl_ids = excluded_result_ids.empty() ? &zero : excluded_result_ids.data(); b.q_topk = &q_topk;
-        b.q_sort_type = sort_type; b.q_sort_col = sort_col; b.q_sort_order = sort_order; b.q_sort_missing_first = missing_first;
-        b.q_flags = &q_flags; b.q_match_type = &q_match_type; b.q_num_query_tokens = &q_nqt; b.q_field_weight = field_weights.data();
-        b.c_tok_off = c_tok_off.data(); b.c_total_cost = c_cost.data(); b.c_n_required = c_nreq.data();
-        const std::vector<int32_t> c_syn(query_suggestions.size(), syn_orig_num_tokens), c_orig(query_suggestions.size(), orig_num_tokens);
-        const std::vector<uint8_t> c_flags(query_suggestions.size(), (uint8_t) ((is_synonym_query ? TSGPU_CFLAG_SYNONYM : 0) | (demote_synonym_match ? TSGPU_CFLAG_DEMOTE_SYNONYM : 0)));
-        b.c_syn_orig_num_tokens = c_syn.data(); b.c_orig_num_tokens = c_orig.data(); b.c_flags = c_flags.data();
-        b.t_list = t_list.empty() ? &zero : t_list.data();
-        b.filter_off = filter_off; b.filter_ids = filter_ids.empty() ? &zero : filter_ids.data();
-        std::vector<KV> kvs(q_topk);
-        uint32_t count = 0, found = 0;
-        if(tsgpu_keyword_search_batch(h, &b, kvs.data(), q_topk, &count, &found) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
-        for(uint32_t i = 0; i < count; i++) topster.add(kvs[i]);
-        num_found = found;
+        q.flags = (uint8_t) ((prioritize_exact_match ? TSGPU_FLAG_PRIORITIZE_EXACT_MATCH : 0) |
+                             (prioritize_token_position ? TSGPU_FLAG_PRIORITIZE_TOKEN_POSITION : 0) |
+                             (prioritize_num_matching_fields ? TSGPU_FLAG_PRIORITIZE_NUM_MATCHING_FIELDS : 0));
+        q.match_type = (uint8_t) text_match_type;
+        q.nqt = (uint8_t) n_query_tokens;
+        q.field_weights = field_weights;
+        q.c_syn.assign(query_suggestions.size(), syn_orig_num_tokens);
+        q.c_orig.assign(query_suggestions.size(), orig_num_tokens);
+        q.c_flags.assign(query_suggestions.size(), (uint8_t) ((is_synonym_query ? TSGPU_CFLAG_SYNONYM : 0) | (demote_synonym_match ? TSGPU_CFLAG_DEMOTE_SYNONYM : 0)));
+        // one device call for this query alone — or, inside multi_search, for this query together with the pending query of every
+        // other search of the request list
+        if(lockstep()) lockstep()->submit_and_wait(q);
+        else { std::vector<kw_query*> one{&q}; run_kw_batch(one); }
+        if(!q.status.ok()) return q.status;
+        for(uint32_t i = 0; i < q.count; i++) topster.add(q.kvs[i]);
+        num_found = q.found;
         return Option<bool>(true);
     }
+
+    // One Index::search_all_candidates call's worth of input (one "query" of tsgpu_kw_batch) and its answer.
+    struct kw_query {
+        std::vector<uint32_t> fids, c_tok_off, t_list, c_cost, filter_ids, excl;
+        std::vector<uint8_t> c_nreq, c_flags, field_weights;
+        std::vector<int32_t> c_syn, c_orig;
+        bool has_filter = false;
+        uint32_t topk = 250;
+        uint8_t sort_type[3] = {0, 0, 0}, missing_first[3] = {0, 0, 0}, flags = 0, match_type = 0, nqt = 0;
+        int32_t sort_col[3] = {-1, -1, -1};
+        int8_t sort_order[3] = {1, 1, 1};
+        // out
+        Option<bool> status{true};
+        std::vector<KV> kvs;
+        uint32_t count = 0, found = 0;
+        bool done = false;
+    };
+    // tsgpu_keyword_search_batch for several queries over the same searched fields: their arrays concatenated, one launch sequence
+    void run_kw_batch(const std::vector<kw_query*>& qs) {
+        const uint32_t nq = (uint32_t) qs.size(), F = (uint32_t) qs[0]->fids.size();
+        std::vector<uint32_t> q_combo_off{0}, q_excl_off{0}, excl, q_topk, c_tok_off{0}, t_list, c_cost;
+        std::vector<int32_t> q_filter, sort_col, c_syn, c_orig;
+        std::vector<uint8_t> sort_type, missing_first, q_flags, q_match_type, q_nqt, q_weights, c_nreq, c_flags;
+        std::vector<int8_t> sort_order;
+        std::vector<uint64_t> filter_off{0};
+        std::vector<uint32_t> filter_ids;
+        uint32_t n_filters = 0, stride = 1;
+        for(auto* q: qs) {
+            const uint32_t nc = (uint32_t) q->c_nreq.size();
+            q_combo_off.push_back(q_combo_off.back() + nc);
+            if(q->has_filter) { q_filter.push_back((int32_t) n_filters++); filter_ids.insert(filter_ids.end(), q->filter_ids.begin(), q->filter_ids.end()); filter_off.push_back(filter_ids.size()); }
+            else q_filter.push_back(-1);
+            excl.insert(excl.end(), q->excl.begin(), q->excl.end());
+            q_excl_off.push_back((uint32_t) excl.size());
+            q_topk.push_back(q->topk);
+            stride = std::max(stride, q->topk);
+            for(int i = 0; i < 3; i++) { sort_type.push_back(q->sort_type[i]); sort_col.push_back(q->sort_col[i]); sort_order.push_back(q->sort_order[i]); missing_first.push_back(q->missing_first[i]); }
+            q_flags.push_back(q->flags); q_match_type.push_back(q->match_type); q_nqt.push_back(q->nqt);
+            for(uint32_t f = 0; f < F; f++) q_weights.push_back(f < q->field_weights.size() ? q->field_weights[f] : 0);
+            const uint32_t row0 = c_tok_off.back();
+            for(uint32_t c = 0; c < nc; c++) c_tok_off.push_back(row0 + q->c_tok_off[c + 1]);
+            t_list.insert(t_list.end(), q->t_list.begin(), q->t_list.end());
+            c_cost.insert(c_cost.end(), q->c_cost.begin(), q->c_cost.end());
+            c_nreq.insert(c_nreq.end(), q->c_nreq.begin(), q->c_nreq.end());
+            c_flags.insert(c_flags.end(), q->c_flags.begin(), q->c_flags.end());
+            c_syn.insert(c_syn.end(), q->c_syn.begin(), q->c_syn.end());
+            c_orig.insert(c_orig.end(), q->c_orig.begin(), q->c_orig.end());
+        }
+        const uint32_t zero = 0;
+        tsgpu_kw_batch b{};
+        b.n_queries = nq; b.n_combos = q_combo_off.back(); b.n_fields = F; b.n_filters = n_filters;
+        b.field_ids = qs[0]->fids.data(); b.q_combo_off = q_combo_off.data(); b.q_filter = q_filter.data(); b.q_excl_off = q_excl_off.data();
+        b.excl_ids = excl.empty() ? &zero : excl.data(); b.q_topk = q_topk.data();
+        b.q_sort_type = sort_type.data(); b.q_sort_col = sort_col.data(); b.q_sort_order = sort_order.data(); b.q_sort_missing_first = missing_first.data();
+        b.q_flags = q_flags.data(); b.q_match_type = q_match_type.data(); b.q_num_query_tokens = q_nqt.data(); b.q_field_weight = q_weights.data();
+        b.c_tok_off = c_tok_off.data(); b.c_total_cost = c_cost.empty() ? &zero : c_cost.data(); b.c_n_required = c_nreq.empty() ? (const uint8_t*) &zero : c_nreq.data();
+        b.c_syn_orig_num_tokens = c_syn.empty() ? (const int32_t*) &zero : c_syn.data(); b.c_orig_num_tokens = c_orig.empty() ? (const int32_t*) &zero : c_orig.data();
+        b.c_flags = c_flags.empty() ? (const uint8_t*) &zero : c_flags.data();
+        b.t_list = t_list.empty() ? &zero : t_list.data();
+        b.filter_off = filter_off.data(); b.filter_ids = filter_ids.empty() ? &zero : filter_ids.data();
+        std::vector<KV> kvs((size_t) nq * stride);
+        std::vector<uint32_t> count(nq), found(nq);
+        kw_device_calls()++;
+        if(tsgpu_keyword_search_batch(h, &b, kvs.data(), stride, count.data(), found.data()) != TSGPU_OK) {
+            const Option<bool> err(500, tsgpu_last_error());
+            for(auto* q: qs) { q->status = err; q->done = true; }
+            return;
+        }
+        for(uint32_t i = 0; i < nq; i++) {
+            qs[i]->kvs.assign(kvs.begin() + (size_t) i * stride, kvs.begin() + (size_t) i * stride + count[i]);
+            qs[i]->count = count[i]; qs[i]->found = found[i]; qs[i]->done = true;
+        }
+    }
+    static uint64_t& kw_device_calls() { static uint64_t n = 0; return n; }        // tsgpu_keyword_search_batch calls made (tests, tuning)
+
+    // multi_search in lock-step (the batching shim of SURVEY 8b, src/core_api.cpp:1080-1131): every search of the request list
+    // runs its unchanged control flow (typo combinations, restarts, drop-token rounds) on a thread of its own, but only ONE of
+    // them executes at any time — a thread gives the baton away only where it needs a keyword device call. When every search
+    // still running is waiting there, their pending queries go to the device as one batch (grouped by searched fields) and
+    // all resume. Device calls per request list: the longest search's number of rounds instead of the sum over searches.
+    struct lockstep_t {
+        Index* ix;
+        std::mutex baton;
+        std::condition_variable cv;
+        size_t active = 0;
+        std::vector<kw_query*> waiting;
+        explicit lockstep_t(Index* ix): ix(ix) {}
+        void flush() {                                   // caller holds the baton
+            std::map<std::vector<uint32_t>, std::vector<kw_query*>> groups;
+            for(auto* q: waiting) groups[q->fids].push_back(q);
+            waiting.clear();
+            for(auto& g: groups) ix->run_kw_batch(g.second);
+            cv.notify_all();
+        }
+        void submit_and_wait(kw_query& q) {              // caller holds the baton (as every running search does)
+            waiting.push_back(&q);
+            if(waiting.size() == active) flush();
+            else {
+                std::unique_lock<std::mutex> lk(baton, std::adopt_lock);
+                cv.wait(lk, [&] { return q.done; });
+                lk.release();                            // keep holding the baton after waking up
+            }
+        }
+    };
+    static lockstep_t*& lockstep() { static thread_local lockstep_t* l = nullptr; return l; }
 
     // ids of `field` holding the tokens as a phrase (a single token: its posting list); false when a token is unknown
     Option<bool> phrase_ids_of(const std::string& field, const std::vector<std::string>& phrase, std::vector<uint32_t>& out, bool& all_known) {
@@ -962,7 +1059,7 @@ public:
         search_options opts;
     };
     struct search_response { Option<bool> status{true}; std::vector<KV> raw_result_kvs; size_t found = 0; };
-    std::vector<search_response> multi_search(const std::vector<search_request>& requests) {
+    std::vector<search_response> multi_search(const std::vector<search_request>& requests, bool in_lockstep = true, size_t max_threads = 64) {
         std::map<uint32_t, std::vector<walk_request>> per_field;
         std::set<std::tuple<uint32_t, bool, int, std::string>> asked;
         for(auto& r: requests) {
@@ -985,9 +1082,26 @@ public:
         }
         for(auto& pf: per_field) device_walks(pf.first, pf.second);
         std::vector<search_response> out(requests.size());
-        for(size_t i = 0; i < requests.size(); i++) {
+        auto run_one = [&](size_t i) {
             const auto& r = requests[i];
             out[i].status = search(r.tokens, r.the_fields, r.sort_fields, r.drop_tokens_threshold, r.topster_size, out[i].raw_result_kvs, out[i].found, r.opts);
+        };
+        if(!in_lockstep || requests.size() < 2) { for(size_t i = 0; i < requests.size(); i++) run_one(i); return out; }
+        for(size_t base = 0; base < requests.size(); base += max_threads) {          // see lockstep_t: one thread runs at a time
+            const size_t n = std::min(max_threads, requests.size() - base);
+            lockstep_t ls(this);
+            ls.active = n;
+            std::vector<std::thread> threads;
+            for(size_t k = 0; k < n; k++) threads.emplace_back([&, k] {
+                ls.baton.lock();
+                lockstep() = &ls;
+                run_one(base + k);
+                lockstep() = nullptr;
+                ls.active--;
+                if(!ls.waiting.empty() && ls.waiting.size() == ls.active) ls.flush();
+                ls.baton.unlock();
+            });
+            for(auto& t: threads) t.join();
         }
         return out;
     }
