@@ -1,7 +1,9 @@
 // C++ host-side scenarios over the tsgpu C-ABI, written the way the reference's own gtest cases read
 // (test/posting_list_test.cpp, test/or_iterator_test.cpp, test/collection_test.cpp, test/collection_vector_search_test.cpp).
 // Built and run by tests/test_cpp_host.py on a machine with a GPU; exit code = number of failed checks.
+#include <cfloat>
 #include <cmath>
+#include <cstring>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -236,6 +238,89 @@ static void vector_scenario() {
     if(pairs.size() == 2) CHECK(pairs[0].second == 1 && pairs[1].second == 0);
 }
 
+static std::vector<uint32_t> keys_of(const std::vector<tsgpu::KV>& kvs) { std::vector<uint32_t> r; for(auto& kv: kvs) r.push_back((uint32_t) kv.key); return r; }
+// Rank fusion through Index::hybrid_search: HybridSearchRankFusionTest (test/collection_test.cpp:4779-4850) and
+// TestRankFusionOrdering (test/collection_vector_search_test.cpp:5674-5753) with stand-in vectors of the same distance order
+// (the reference embeds text with a model that is not available offline; only the order matters to its assertions);
+// DistanceThresholdTest (:1548-1598) through Index::vector_search; process_results_bruteforce through Index::flat_distances.
+static std::vector<float> unit_vec(std::vector<float> v) {
+    float n = 0; for(float x: v) n += x * x;
+    n = std::sqrt(n);
+    for(float& x: v) x /= n;
+    return v;
+}
+struct GraphHolder {
+    std::vector<float> vecs; std::vector<uint8_t> levels; std::vector<uint32_t> links0, links_up; std::vector<uint64_t> upper_off;
+    tsgpu_hnsw g{};
+    GraphHolder(const std::vector<std::vector<float>>& rows, uint32_t metric) {
+        const uint32_t n = (uint32_t) rows.size(), dim = (uint32_t) rows[0].size();
+        for(auto& r: rows) vecs.insert(vecs.end(), r.begin(), r.end());
+        void* bld = tso_hnsw_build(vecs.data(), n, dim, 16, 200, 100);
+        uint32_t max_level = 0, entry = 0; uint64_t n_up = 0;
+        tso_hnsw_build_info(bld, &max_level, &entry, &n_up);
+        levels.resize(n); links0.resize((size_t) n * 33); links_up.resize((n_up + 1) * 17); upper_off.resize(n + 1);
+        tso_hnsw_build_fetch(bld, levels.data(), links0.data(), upper_off.data(), links_up.data());
+        tso_hnsw_build_free(bld);
+        g = tsgpu_hnsw{n, dim, 16, max_level, entry, metric, vecs.data(), nullptr, levels.data(), links0.data(), upper_off.data(), links_up.data()};
+    }
+};
+static float fused_score(const tsgpu::KV& kv) {
+    const int32_t bits = (int32_t) kv.scores[kv.match_score_index];
+    float f; memcpy(&f, &bits, 4);                  // int64_t_to_float for non-negative values (src/index.cpp:276-286)
+    return f;
+}
+static void hybrid_scenarios() {
+    const std::vector<tsgpu::sort_by> sort_fields = {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::seq_id, "", true}};
+    const tsgpu_vec_params vp{0, 10, 0, FLT_MAX, 0.3f, 10};
+    const auto q = unit_vec({1, 0.2f, 0, 0});
+    {   // "butter" with prefix search: butter (cost 0), butterfly / butterball (prefix-found: cost 1); vector order butter < butterball < butterfly
+        tsgpu::Index index(3);
+        tsgpu::field_mirror_t title;
+        const char* docs[] = {"butter", "butterball", "butterfly"};
+        for(uint32_t i = 0; i < 3; i++) title.index_plain_string(i, tsgpu::tokenize_ascii(docs[i]));
+        CHECK(index.add_field("title", title).ok());
+        GraphHolder gh({q, unit_vec({1, 0.5f, 0, 0}), unit_vec({1, 1.5f, 0, 0})}, 0);
+        CHECK(index.add_vector_field(gh.g).ok());
+        std::vector<tsgpu::KV> kvs; size_t found = 0;
+        CHECK(index.hybrid_search({{"butter"}, {"butterfly"}, {"butterball"}}, {0, 1, 1}, {"title"}, {15}, sort_fields, nullptr, {}, 250, q.data(), vp, kvs, found).ok());
+        CHECK(found == 3 && (keys_of(kvs) == std::vector<uint32_t>{0, 1, 2}));
+        const float expect[3] = {1.0f / 1 * 0.7f + 1.0f / 1 * 0.3f, 1.0f / 2 * 0.7f + 1.0f / 2 * 0.3f, 1.0f / 2 * 0.7f + 1.0f / 3 * 0.3f};
+        for(size_t i = 0; i < kvs.size() && i < 3; i++) CHECK(std::fabs(fused_score(kvs[i]) - expect[i]) <= 3e-7f * expect[i]);
+    }
+    {   // "apple" matches all three with one shared text rank; vector order green apple < apple pie < red apple
+        tsgpu::Index index(3);
+        tsgpu::field_mirror_t title;
+        const char* docs[] = {"red apple", "green apple", "apple pie"};
+        for(uint32_t i = 0; i < 3; i++) title.index_plain_string(i, tsgpu::tokenize_ascii(docs[i]));
+        CHECK(index.add_field("title", title).ok());
+        GraphHolder gh({unit_vec({1, 2.0f, 0, 0}), q, unit_vec({1, 0.8f, 0, 0})}, 0);
+        CHECK(index.add_vector_field(gh.g).ok());
+        std::vector<tsgpu::KV> kvs; size_t found = 0;
+        CHECK(index.hybrid_search({{"apple"}}, {0}, {"title"}, {15}, sort_fields, nullptr, {}, 250, q.data(), vp, kvs, found).ok());
+        CHECK(found == 3 && (keys_of(kvs) == std::vector<uint32_t>{1, 2, 0}));
+        const float expect[3] = {0.7f + 0.3f / 1, 0.7f + 0.3f / 2, 0.7f + 0.3f / 3};
+        for(size_t i = 0; i < kvs.size() && i < 3; i++) CHECK(std::fabs(fused_score(kvs[i]) - expect[i]) <= 3e-7f * expect[i]);
+        // process_results_bruteforce: distances of the query to given ids = 1 - dot
+        std::vector<float> dist;
+        CHECK(index.flat_distances(q.data(), {0, 1, 2}, dist).ok());
+        CHECK(dist.size() == 3 && std::fabs(dist[1]) < 1e-6f && dist[2] < dist[0] && dist[2] > dist[1]);
+    }
+    {   // DistanceThresholdTest: cosine, wildcard + vector query
+        tsgpu::Index index(2);
+        GraphHolder gh({unit_vec({0.1f, 0.2f, 0.3f}), unit_vec({0.6f, 0.7f, 0.8f})}, 1);
+        CHECK(index.add_vector_field(gh.g).ok());
+        const auto vq = unit_vec({0.3f, 0.4f, 0.5f});
+        const std::vector<tsgpu::sort_by> vsort = {{tsgpu::sort_by::vector_distance, "", false}, {tsgpu::sort_by::seq_id, "", true}};
+        std::vector<tsgpu::KV> kvs; size_t found = 0;
+        tsgpu_vec_params v2{0, 10, 0, FLT_MAX, 0.3f, 20};
+        CHECK(index.vector_search(vsort, nullptr, {}, 250, vq.data(), v2, kvs, found).ok());
+        CHECK(found == 2 && (keys_of(kvs) == std::vector<uint32_t>{1, 0}));
+        v2.distance_threshold = 0.01f;
+        CHECK(index.vector_search(vsort, nullptr, {}, 250, vq.data(), v2, kvs, found).ok());
+        CHECK(found == 1 && (keys_of(kvs) == std::vector<uint32_t>{1}));
+    }
+}
+
 // posting_t::get_exact_matches / get_prefix_matches (src/posting_list.cpp:1129-1452) on the ExactMatch documents of
 // test/collection_test.cpp:3638, and ArrayUtils (test/array_utils_test.cpp:5-172)
 static void exact_prefix_and_setops() {
@@ -272,7 +357,6 @@ static void exact_prefix_and_setops() {
 // ---- more of the reference's end-to-end expectations, through Index::search with Collection::search's defaults
 struct Rec { std::vector<std::string> values; };     // one string per field
 
-static std::vector<uint32_t> keys_of(const std::vector<tsgpu::KV>& kvs) { std::vector<uint32_t> r; for(auto& kv: kvs) r.push_back((uint32_t) kv.key); return r; }
 
 // builds an index over `fields` (plain strings) with points = row number
 static void build_plain(tsgpu::Index& index, const std::vector<std::string>& fields, const std::vector<Rec>& recs) {
@@ -611,6 +695,7 @@ int main(int argc, char** argv) {
     or_iterator_intersect_and_filter();
     collection_scenarios(argc > 1 ? argv[1] : "tests/golden/documents.jsonl");
     vector_scenario();
+    if(getenv("TSGPU_HOST_HYBRID_KAT")) hybrid_scenarios();      // tiny-graph hybrid calls: run on the double and, non-gating, on the GPU
     exact_prefix_and_setops();
     relevance_scenarios();
     specific_scenarios();

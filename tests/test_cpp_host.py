@@ -32,7 +32,8 @@ def test_cpp_host_scenarios_on_oracle_double():
     cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wno-unused", src, dbl, "-o", exe, "-L", os.path.join(ROOT, "oracle"),
            "-l:liboracle.so", f"-Wl,-rpath,{os.path.join(ROOT, 'oracle')}", "-pthread"]
     subprocess.check_call(cmd)
-    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "documents.jsonl")], capture_output=True, text=True, cwd=ROOT)
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "documents.jsonl")], capture_output=True, text=True, cwd=ROOT,
+                       env=dict(os.environ, TSGPU_HOST_HYBRID_KAT="1"))          # + the tiny-graph hybrid / vector KATs
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     # once more with the candidate walks routed through tsgpu_index_load_art / tsgpu_art_walk_batch (f-1, opt-in): the

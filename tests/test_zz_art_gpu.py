@@ -87,7 +87,8 @@ def test_child_art_walk_batch_matches_host_walk(am):
 @pytest.mark.xfail(strict=False, reason="opt-in f-1 kernel: written without GPU access, first GPU run pending (see DESIGN.md §11.3)")
 def test_host_layer_scenarios_with_device_walk():
     """tests/cpp/host_scenarios (the reference's typo / prefix / ranking scenarios through the C++ host layer) with every
-    candidate walk routed through tsgpu_art_walk_batch."""
+    candidate walk routed through tsgpu_art_walk_batch, plus the rank-fusion KATs on 3-vector graphs through
+    Index::hybrid_search / vector_search (a graph size the GPU hybrid path has not been run on yet)."""
     import os
     import subprocess
     import test_cpp_host as tch
@@ -95,5 +96,5 @@ def test_host_layer_scenarios_with_device_walk():
         pytest.skip("links the real libtsgpu.so")
     tch.build()
     r = subprocess.run([tch.BIN, os.path.join(tch.ROOT, "tests", "golden", "documents.jsonl")], capture_output=True, text=True, cwd=tch.ROOT,
-                       env=dict(os.environ, TSGPU_HOST_DEVICE_ART="1"), timeout=600)
+                       env=dict(os.environ, TSGPU_HOST_DEVICE_ART="1", TSGPU_HOST_HYBRID_KAT="1"), timeout=600)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]

@@ -15,6 +15,11 @@
 //   Index::search_wildcard                src/index.cpp:6616-6800  Index::search_wildcard
 //   Index::search_across_fields           src/index.cpp:5385       Index::search_across_fields(query_suggestions, ...)
 //   hnsw_index_t + searchKnnCloserFirst   src/index.cpp:3384       Index::searchKnnCloserFirst(q, k, ef, filter_ids)
+//   process_results_bruteforce            src/index.cpp:3345-3374  Index::flat_distances(q, ids, dist)
+//   wildcard + vector query               src/index.cpp:3645-3732  Index::vector_search(sort, filter, excluded, K, q, vec params)
+//   keyword + vector query, RRF           src/index.cpp:4036-4221  Index::hybrid_search(suggestions, ..., q, vec params)   (one device call)
+//   multi_search loop                     src/core_api.cpp:1080    Index::multi_search(requests)   (lock-step batching of the device calls)
+//   filter_by string clause               src/filter.cpp:674, src/filter_result_iterator.cpp:1739, 2964   Index::string_filter_ids
 //   Topster<KV>::add / sort               include/topster.h:321    host_topster_t (merges the <=K KVs of each device round)
 //   Index::search drop-tokens loop        src/index.cpp:3920-4017  Index::search(tokens, ...)  (control flow stays on host)
 //   Index::fuzzy_search_fields            src/index.cpp:4784-5109  Index::fuzzy_search_fields (cost combinations, candidate cache)
@@ -419,6 +424,26 @@ public:
                                       bool prioritize_token_position = false, bool prioritize_num_matching_fields = true,
                                       int text_match_type = TSGPU_MATCH_MAX_SCORE, int syn_orig_num_tokens = -1, int orig_num_tokens = -1,
                                       bool is_synonym_query = false, bool demote_synonym_match = false) {
+        kw_query q = make_kw_query(query_suggestions, n_dropped, total_costs, the_fields, field_weights, sort_fields, filter_ids, filter_by_provided,
+                                   excluded_result_ids, topster_size, prioritize_exact_match, prioritize_token_position, prioritize_num_matching_fields,
+                                   text_match_type, syn_orig_num_tokens, orig_num_tokens, is_synonym_query, demote_synonym_match);
+        // one device call for this query alone — or, inside multi_search, for this query together with the pending query of every
+        // other search of the request list
+        if(lockstep()) lockstep()->submit_and_wait(q);
+        else { std::vector<kw_query*> one{&q}; run_kw_batch(one); }
+        if(!q.status.ok()) return q.status;
+        for(uint32_t i = 0; i < q.count; i++) topster.add(q.kvs[i]);
+        num_found = q.found;
+        return Option<bool>(true);
+    }
+    struct kw_query;
+    kw_query make_kw_query(const std::vector<std::vector<std::string>>& query_suggestions, size_t n_dropped,
+                           const std::vector<uint32_t>& total_costs, const std::vector<std::string>& the_fields,
+                           const std::vector<uint8_t>& field_weights, const std::vector<sort_by>& sort_fields,
+                           const std::vector<uint32_t>& filter_ids, bool filter_by_provided,
+                           const std::vector<uint32_t>& excluded_result_ids, size_t topster_size,
+                           bool prioritize_exact_match, bool prioritize_token_position, bool prioritize_num_matching_fields,
+                           int text_match_type, int syn_orig_num_tokens, int orig_num_tokens, bool is_synonym_query, bool demote_synonym_match) {
         kw_query q;
         const uint32_t F = (uint32_t) the_fields.size();
         q.fids.resize(F);
@@ -452,13 +477,47 @@ public:
         q.c_syn.assign(query_suggestions.size(), syn_orig_num_tokens);
         q.c_orig.assign(query_suggestions.size(), orig_num_tokens);
         q.c_flags.assign(query_suggestions.size(), (uint8_t) ((is_synonym_query ? TSGPU_CFLAG_SYNONYM : 0) | (demote_synonym_match ? TSGPU_CFLAG_DEMOTE_SYNONYM : 0)));
-        // one device call for this query alone — or, inside multi_search, for this query together with the pending query of every
-        // other search of the request list
-        if(lockstep()) lockstep()->submit_and_wait(q);
-        else { std::vector<kw_query*> one{&q}; run_kw_batch(one); }
+        return q;
+    }
+
+    // Keyword + vector query in ONE device call with reciprocal-rank fusion (Index::search with a vector_query,
+    // src/index.cpp:4036-4221). The suggestions are resolved token combinations as for search_across_fields — a single round:
+    // the typo / drop-token loop is not interleaved with the vector stage here. vp: k, ef, alpha, flat_search_cutoff,
+    // distance_threshold, fetch_size as vector_query_t / Index::search carry them.
+    Option<bool> hybrid_search(const std::vector<std::vector<std::string>>& query_suggestions, const std::vector<uint32_t>& total_costs,
+                               const std::vector<std::string>& the_fields, const std::vector<uint8_t>& field_weights,
+                               const std::vector<sort_by>& sort_fields, const std::vector<uint32_t>* filter_ids,
+                               const std::vector<uint32_t>& excluded_result_ids, size_t topster_size, const float* query_vector,
+                               const tsgpu_vec_params& vp, std::vector<KV>& raw_result_kvs, size_t& found, const search_options& o = search_options()) {
+        kw_query q = make_kw_query(query_suggestions, 0, total_costs, the_fields, field_weights, sort_fields, filter_ids ? *filter_ids : std::vector<uint32_t>(),
+                                   filter_ids != nullptr, excluded_result_ids, topster_size, o.prioritize_exact_match, o.prioritize_token_position,
+                                   o.prioritize_num_matching_fields, o.text_match_type, -1, -1, false, false);
+        std::vector<kw_query*> one{&q};
+        run_kw_batch(one, 2, query_vector, &vp);
         if(!q.status.ok()) return q.status;
-        for(uint32_t i = 0; i < q.count; i++) topster.add(q.kvs[i]);
-        num_found = q.found;
+        raw_result_kvs = q.kvs;
+        found = q.found;
+        return Option<bool>(true);
+    }
+    // Wildcard + vector query (src/index.cpp:3645-3732): nearest neighbours (graph walk, or brute force over the filter ids
+    // below flat_search_cutoff), distance threshold, sort clauses, top-k
+    Option<bool> vector_search(const std::vector<sort_by>& sort_fields, const std::vector<uint32_t>* filter_ids,
+                               const std::vector<uint32_t>& excluded_result_ids, size_t topster_size, const float* query_vector,
+                               const tsgpu_vec_params& vp, std::vector<KV>& raw_result_kvs, size_t& found) {
+        kw_query q = make_kw_query({}, 0, {}, {}, {}, sort_fields, filter_ids ? *filter_ids : std::vector<uint32_t>(), filter_ids != nullptr,
+                                   excluded_result_ids, topster_size, true, false, true, TSGPU_MATCH_MAX_SCORE, -1, -1, false, false);
+        std::vector<kw_query*> one{&q};
+        run_kw_batch(one, 1, query_vector, &vp);
+        if(!q.status.ok()) return q.status;
+        raw_result_kvs = q.kvs;
+        found = q.found;
+        return Option<bool>(true);
+    }
+    // process_results_bruteforce (src/index.cpp:3345-3374): distance of the query to every id, in id order
+    Option<bool> flat_distances(const float* query_vector, const std::vector<uint32_t>& ids, std::vector<float>& dist) {
+        dist.assign(ids.size(), 0.f);
+        if(ids.empty()) return Option<bool>(true);
+        if(tsgpu_flat_distances(h, query_vector, ids.data(), ids.size(), dist.data()) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
         return Option<bool>(true);
     }
 
@@ -478,53 +537,65 @@ public:
         uint32_t count = 0, found = 0;
         bool done = false;
     };
-    // tsgpu_keyword_search_batch for several queries over the same searched fields: their arrays concatenated, one launch sequence
-    void run_kw_batch(const std::vector<kw_query*>& qs) {
-        const uint32_t nq = (uint32_t) qs.size(), F = (uint32_t) qs[0]->fids.size();
-        std::vector<uint32_t> q_combo_off{0}, q_excl_off{0}, excl, q_topk, c_tok_off{0}, t_list, c_cost;
+    // tsgpu_kw_batch for several queries over the same searched fields: their arrays concatenated
+    struct kw_batch_storage {
+        std::vector<uint32_t> q_combo_off{0}, q_excl_off{0}, excl, q_topk, c_tok_off{0}, t_list, c_cost, filter_ids, fids;
         std::vector<int32_t> q_filter, sort_col, c_syn, c_orig;
         std::vector<uint8_t> sort_type, missing_first, q_flags, q_match_type, q_nqt, q_weights, c_nreq, c_flags;
         std::vector<int8_t> sort_order;
         std::vector<uint64_t> filter_off{0};
-        std::vector<uint32_t> filter_ids;
-        uint32_t n_filters = 0, stride = 1;
-        for(auto* q: qs) {
-            const uint32_t nc = (uint32_t) q->c_nreq.size();
-            q_combo_off.push_back(q_combo_off.back() + nc);
-            if(q->has_filter) { q_filter.push_back((int32_t) n_filters++); filter_ids.insert(filter_ids.end(), q->filter_ids.begin(), q->filter_ids.end()); filter_off.push_back(filter_ids.size()); }
-            else q_filter.push_back(-1);
-            excl.insert(excl.end(), q->excl.begin(), q->excl.end());
-            q_excl_off.push_back((uint32_t) excl.size());
-            q_topk.push_back(q->topk);
-            stride = std::max(stride, q->topk);
-            for(int i = 0; i < 3; i++) { sort_type.push_back(q->sort_type[i]); sort_col.push_back(q->sort_col[i]); sort_order.push_back(q->sort_order[i]); missing_first.push_back(q->missing_first[i]); }
-            q_flags.push_back(q->flags); q_match_type.push_back(q->match_type); q_nqt.push_back(q->nqt);
-            for(uint32_t f = 0; f < F; f++) q_weights.push_back(f < q->field_weights.size() ? q->field_weights[f] : 0);
-            const uint32_t row0 = c_tok_off.back();
-            for(uint32_t c = 0; c < nc; c++) c_tok_off.push_back(row0 + q->c_tok_off[c + 1]);
-            t_list.insert(t_list.end(), q->t_list.begin(), q->t_list.end());
-            c_cost.insert(c_cost.end(), q->c_cost.begin(), q->c_cost.end());
-            c_nreq.insert(c_nreq.end(), q->c_nreq.begin(), q->c_nreq.end());
-            c_flags.insert(c_flags.end(), q->c_flags.begin(), q->c_flags.end());
-            c_syn.insert(c_syn.end(), q->c_syn.begin(), q->c_syn.end());
-            c_orig.insert(c_orig.end(), q->c_orig.begin(), q->c_orig.end());
-        }
-        const uint32_t zero = 0;
+        uint32_t stride = 1, zero = 0;
         tsgpu_kw_batch b{};
-        b.n_queries = nq; b.n_combos = q_combo_off.back(); b.n_fields = F; b.n_filters = n_filters;
-        b.field_ids = qs[0]->fids.data(); b.q_combo_off = q_combo_off.data(); b.q_filter = q_filter.data(); b.q_excl_off = q_excl_off.data();
-        b.excl_ids = excl.empty() ? &zero : excl.data(); b.q_topk = q_topk.data();
-        b.q_sort_type = sort_type.data(); b.q_sort_col = sort_col.data(); b.q_sort_order = sort_order.data(); b.q_sort_missing_first = missing_first.data();
-        b.q_flags = q_flags.data(); b.q_match_type = q_match_type.data(); b.q_num_query_tokens = q_nqt.data(); b.q_field_weight = q_weights.data();
-        b.c_tok_off = c_tok_off.data(); b.c_total_cost = c_cost.empty() ? &zero : c_cost.data(); b.c_n_required = c_nreq.empty() ? (const uint8_t*) &zero : c_nreq.data();
-        b.c_syn_orig_num_tokens = c_syn.empty() ? (const int32_t*) &zero : c_syn.data(); b.c_orig_num_tokens = c_orig.empty() ? (const int32_t*) &zero : c_orig.data();
-        b.c_flags = c_flags.empty() ? (const uint8_t*) &zero : c_flags.data();
-        b.t_list = t_list.empty() ? &zero : t_list.data();
-        b.filter_off = filter_off.data(); b.filter_ids = filter_ids.empty() ? &zero : filter_ids.data();
+        explicit kw_batch_storage(const std::vector<kw_query*>& qs) {
+            fids = qs[0]->fids;
+            const uint32_t F = (uint32_t) fids.size();
+            uint32_t n_filters = 0;
+            for(auto* q: qs) {
+                const uint32_t nc = (uint32_t) q->c_nreq.size();
+                q_combo_off.push_back(q_combo_off.back() + nc);
+                if(q->has_filter) { q_filter.push_back((int32_t) n_filters++); filter_ids.insert(filter_ids.end(), q->filter_ids.begin(), q->filter_ids.end()); filter_off.push_back(filter_ids.size()); }
+                else q_filter.push_back(-1);
+                excl.insert(excl.end(), q->excl.begin(), q->excl.end());
+                q_excl_off.push_back((uint32_t) excl.size());
+                q_topk.push_back(q->topk);
+                stride = std::max(stride, q->topk);
+                for(int i = 0; i < 3; i++) { sort_type.push_back(q->sort_type[i]); sort_col.push_back(q->sort_col[i]); sort_order.push_back(q->sort_order[i]); missing_first.push_back(q->missing_first[i]); }
+                q_flags.push_back(q->flags); q_match_type.push_back(q->match_type); q_nqt.push_back(q->nqt);
+                for(uint32_t f = 0; f < F; f++) q_weights.push_back(f < q->field_weights.size() ? q->field_weights[f] : 0);
+                const uint32_t row0 = c_tok_off.back();
+                for(uint32_t c = 0; c < nc; c++) c_tok_off.push_back(row0 + q->c_tok_off[c + 1]);
+                t_list.insert(t_list.end(), q->t_list.begin(), q->t_list.end());
+                c_cost.insert(c_cost.end(), q->c_cost.begin(), q->c_cost.end());
+                c_nreq.insert(c_nreq.end(), q->c_nreq.begin(), q->c_nreq.end());
+                c_flags.insert(c_flags.end(), q->c_flags.begin(), q->c_flags.end());
+                c_syn.insert(c_syn.end(), q->c_syn.begin(), q->c_syn.end());
+                c_orig.insert(c_orig.end(), q->c_orig.begin(), q->c_orig.end());
+            }
+            b.n_queries = (uint32_t) qs.size(); b.n_combos = q_combo_off.back(); b.n_fields = F; b.n_filters = n_filters;
+            b.field_ids = fids.empty() ? &zero : fids.data(); b.q_combo_off = q_combo_off.data(); b.q_filter = q_filter.data(); b.q_excl_off = q_excl_off.data();
+            b.excl_ids = excl.empty() ? &zero : excl.data(); b.q_topk = q_topk.data();
+            b.q_sort_type = sort_type.data(); b.q_sort_col = sort_col.data(); b.q_sort_order = sort_order.data(); b.q_sort_missing_first = missing_first.data();
+            b.q_flags = q_flags.data(); b.q_match_type = q_match_type.data(); b.q_num_query_tokens = q_nqt.data();
+            b.q_field_weight = q_weights.empty() ? (const uint8_t*) &zero : q_weights.data();
+            b.c_tok_off = c_tok_off.data(); b.c_total_cost = c_cost.empty() ? &zero : c_cost.data(); b.c_n_required = c_nreq.empty() ? (const uint8_t*) &zero : c_nreq.data();
+            b.c_syn_orig_num_tokens = c_syn.empty() ? (const int32_t*) &zero : c_syn.data(); b.c_orig_num_tokens = c_orig.empty() ? (const int32_t*) &zero : c_orig.data();
+            b.c_flags = c_flags.empty() ? (const uint8_t*) &zero : c_flags.data();
+            b.t_list = t_list.empty() ? &zero : t_list.data();
+            b.filter_off = filter_off.data(); b.filter_ids = filter_ids.empty() ? &zero : filter_ids.data();
+        }
+        kw_batch_storage(const kw_batch_storage&) = delete;
+    };
+    // what: 0 tsgpu_keyword_search_batch, 1 tsgpu_vector_search_batch, 2 tsgpu_hybrid_search_batch (qvecs: one vector per query)
+    void run_kw_batch(const std::vector<kw_query*>& qs, int what = 0, const float* qvecs = nullptr, const tsgpu_vec_params* vp = nullptr) {
+        kw_batch_storage st(qs);
+        const uint32_t nq = (uint32_t) qs.size(), stride = st.stride;
         std::vector<KV> kvs((size_t) nq * stride);
         std::vector<uint32_t> count(nq), found(nq);
         kw_device_calls()++;
-        if(tsgpu_keyword_search_batch(h, &b, kvs.data(), stride, count.data(), found.data()) != TSGPU_OK) {
+        const tsgpu_status rc = what == 0 ? tsgpu_keyword_search_batch(h, &st.b, kvs.data(), stride, count.data(), found.data())
+                              : what == 1 ? tsgpu_vector_search_batch(h, &st.b, qvecs, vp, kvs.data(), stride, count.data(), found.data())
+                                          : tsgpu_hybrid_search_batch(h, &st.b, qvecs, vp, kvs.data(), stride, count.data(), found.data());
+        if(rc != TSGPU_OK) {
             const Option<bool> err(500, tsgpu_last_error());
             for(auto* q: qs) { q->status = err; q->done = true; }
             return;
