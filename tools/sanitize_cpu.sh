@@ -11,8 +11,8 @@ echo "== ART mirror + art_walk() (random vocabularies)"
 g++ $SAN tests/cpp/art_sanitize_driver.cpp tests/cpp/art_mirror_capi.cpp -o $OUT/art && ASAN_OPTIONS=detect_leaks=1 $OUT/art
 echo "== C++ host layer on the oracle double (host walk, then device-walk marshalling)"
 g++ $SAN -Wno-unused tests/cpp/host_scenarios.cpp tests/cpp/tsgpu_oracle_double.cpp -o $OUT/hs -L oracle -l:liboracle.so -Wl,-rpath,$PWD/oracle -pthread
-ASAN_OPTIONS=detect_leaks=0 $OUT/hs tests/golden/documents.jsonl | tail -1
-TSGPU_HOST_DEVICE_ART=1 ASAN_OPTIONS=detect_leaks=0 $OUT/hs tests/golden/documents.jsonl | tail -1
+TSGPU_HOST_HYBRID_KAT=1 ASAN_OPTIONS=detect_leaks=0 $OUT/hs tests/golden/documents.jsonl | tail -1
+TSGPU_HOST_HYBRID_KAT=1 TSGPU_HOST_DEVICE_ART=1 ASAN_OPTIONS=detect_leaks=0 $OUT/hs tests/golden/documents.jsonl | tail -1
 echo "== ThreadSanitizer: the lock-step multi_search of the C++ host layer"
 g++ -std=c++17 -O1 -g -fsanitize=thread -fno-omit-frame-pointer -Wno-unused tests/cpp/host_scenarios.cpp tests/cpp/tsgpu_oracle_double.cpp -o $OUT/hs_tsan \
     -L oracle -l:liboracle.so -Wl,-rpath,$PWD/oracle -pthread
