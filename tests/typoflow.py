@@ -5,8 +5,11 @@ refflow's backends so the reference's typo and prefix scenarios (test/collection
   Index::next_suggestion2        src/index.cpp:7204-7248   total_cost = sum(2*typo + prefix-found)
   Index::get_bounded_typo_cost   src/index.cpp:6923-6951
   drop-tokens loop               src/index.cpp:3920-4017
-Candidate generation is the reference's ART walk (src/art.cpp: art_fuzzy_search_i, SURVEY §8 f-1, not built); here a
-brute-force scan of the (tiny) test vocabulary stands in for it: optimal-string-alignment distance exactly equal to the
+Candidate generation is the reference's ART walk (src/art.cpp: art_fuzzy_search_i). The faithful
+implementation is typesense_b200/host/art_mirror.hpp (pinned on the reference's compiled art.cpp, tests/test_art_mirror.py)
+and is what the C++ host layer uses; THIS Python harness keeps a brute-force scan of the (tiny) test vocabulary, which
+agrees with the walk on every replayed scenario but accepts a superset in corner cases the walk's pruning rules skip
+(DESIGN.md §11.3): optimal-string-alignment distance exactly equal to the
 cost, prefix rule of fuzzy_search_state, leaves ordered by frequency / max_score (ties: token order), the exact leaf
 first, at most max_candidates; fields are scanned in query_by order with one shared set of already-produced tokens. For the
 last token of a multi-token query the reference first looks only at the fields that hold the previous token (most
