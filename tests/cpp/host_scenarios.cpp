@@ -174,6 +174,12 @@ static void collection_scenarios(const std::string& jsonl) {
             const uint64_t calls_seq = tsgpu::Index::kw_device_calls() - calls0;
             auto resps = index.multi_search(reqs);                        // lock-step: pending queries of all searches share a device call
             const uint64_t calls_lock = tsgpu::Index::kw_device_calls() - calls0 - calls_seq;
+            {   // a request naming an unknown field fails alone; the others of the list are answered
+                auto bad = reqs;
+                bad[1].the_fields = {"no_such_field"};
+                auto r2 = index.multi_search(bad);
+                CHECK(!r2[1].status.ok() && r2[0].status.ok() && r2[2].status.ok() && ids_of(r2[0].raw_result_kvs) == ids_of(resps[0].raw_result_kvs));
+            }
             printf("multi_search of %zu searches: %llu keyword device calls one by one, %llu in lock-step\n", reqs.size(),
                    (unsigned long long) calls_seq, (unsigned long long) calls_lock);
             CHECK(calls_lock * 3 <= calls_seq && seq.size() == resps.size());

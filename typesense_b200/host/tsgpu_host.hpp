@@ -32,6 +32,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <exception>
 #include <map>
 #include <thread>
 #include <mutex>
@@ -1142,7 +1143,9 @@ public:
                 const bool prefix_search = r.opts.prefix && i + 1 == variants[v].size();
                 const int max_cost = v ? 0 : std::min<int>((int) r.opts.num_typos, get_bounded_typo_cost(2, t, r.opts.min_len_1typo, r.opts.min_len_2typo));
                 for(auto& fn: r.the_fields) {
-                    const uint32_t fid = field_ids.at(fn);
+                    auto fit = field_ids.find(fn);
+                    if(fit == field_ids.end()) continue;            // the search itself will report the unknown field
+                    const uint32_t fid = fit->second;
                     for(int c = 0; c <= max_cost; c++) {
                         const auto key = std::make_tuple(fid, prefix_search, c, t);
                         if(walk_cache.count(key) || !asked.insert(key).second) continue;
@@ -1155,7 +1158,8 @@ public:
         std::vector<search_response> out(requests.size());
         auto run_one = [&](size_t i) {
             const auto& r = requests[i];
-            out[i].status = search(r.tokens, r.the_fields, r.sort_fields, r.drop_tokens_threshold, r.topster_size, out[i].raw_result_kvs, out[i].found, r.opts);
+            try { out[i].status = search(r.tokens, r.the_fields, r.sort_fields, r.drop_tokens_threshold, r.topster_size, out[i].raw_result_kvs, out[i].found, r.opts); }
+            catch(const std::exception& e) { out[i].status = Option<bool>(400, e.what()); }        // e.g. an unknown field name: this request alone fails
         };
         if(!in_lockstep || requests.size() < 2) { for(size_t i = 0; i < requests.size(); i++) run_one(i); return out; }
         for(size_t base = 0; base < requests.size(); base += max_threads) {          // see lockstep_t: one thread runs at a time
