@@ -1,0 +1,98 @@
+#!/usr/bin/env python3
+"""CPU timing of the typo / prefix candidate search on a synthetic vocabulary: the reference's own
+art_fuzzy_search_i (src/art.cpp compiled in oracle/_ref) next to this repository's art_mirror_t (host walk + finish, and the walk
+alone — the part tsgpu_art_walk_batch moves to the device). One core. Says how much host time a 4096-query batch's candidate
+generation costs next to the 37 ms the device spends on the batch.   usage: tools/bench_art_cpu.py [n_tokens] > profiles/…json"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib as ol          # noqa: E402
+import test_art_mirror as T     # noqa: E402
+
+
+def main():
+    n_tokens = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
+    rng = np.random.default_rng(1)
+    alpha = np.array(list("abcdefghijklmnopqrstuvwxyz"))
+    lens = rng.integers(3, 11, n_tokens * 2)
+    toks = sorted({"".join(rng.choice(alpha, int(l))) for l in lens})[:n_tokens]
+    n = len(toks)
+    df = np.minimum(1 + (n / (1 + rng.permutation(n))).astype(np.int64), 5000).astype(np.uint32)       # Zipf-like document counts
+    ms = rng.integers(0, 1000, n).astype(np.int64)
+    L = C.CDLL(T.SO)
+    vp = C.c_void_p
+    L.am_build.restype = vp
+    L.am_build.argtypes = [C.c_char_p, C.POINTER(C.c_int64), ol.u32p, C.c_uint32]
+    L.am_walk.restype = C.c_size_t
+    L.am_walk.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_size_t, C.POINTER(C.c_int)]
+    L.am_fuzzy.restype = C.c_size_t
+    L.am_fuzzy.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_char_p, ol.u32p, C.c_size_t, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
+    L.am_bind.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64), ol.u32p]
+    t0 = time.time()
+    h = L.am_build("\n".join(toks).encode(), ms.ctypes.data_as(C.POINTER(C.c_int64)), ol.p32(df), n)
+    lo = np.arange(n + 1, dtype=np.uint64)
+    ids = np.arange(n, dtype=np.uint32)
+    L.am_bind(h, "\n".join(toks).encode(), lo.ctypes.data_as(C.POINTER(C.c_uint64)), ol.p32(ids))
+    t_build = time.time() - t0
+    R = ol.ref()
+    t0 = time.time()
+    rt = R.ref_art_new()
+    off = np.zeros(1, np.uint32)
+    for i, t in enumerate(toks):                     # one document per token is enough for the walk; frequency order uses num_ids = 1
+        R.ref_art_insert(rt, t.encode(), i, int(ms[i]), ol.p32(off), 1)
+    t_ref_build = time.time() - t0
+
+    def queries(kind, m):
+        out = []
+        for _ in range(m):
+            w = toks[int(rng.integers(0, n))]
+            if kind == "prefix0":
+                out.append((w[:max(2, len(w) // 2)], 0, 1))
+            elif kind == "typo1":
+                i = int(rng.integers(0, len(w)))
+                out.append((w[:i] + str(rng.choice(alpha)) + w[i + 1:], 1, 0))
+            else:
+                i, j = sorted(rng.integers(0, len(w), 2).tolist())
+                w2 = w[:i] + str(rng.choice(alpha)) + w[i + 1:]
+                out.append((w2[:j] + w2[j + 1:] if len(w2) > 3 else w2, 2, 0))
+        return out
+
+    res = {"tokens": n, "build_s": {"art_mirror_build": round(t_build, 2), "reference_art_insert": round(t_ref_build, 2)}, "per_search_us": {}}
+    hits = np.zeros(1 << 16, np.int32)
+    so = C.c_int(0)
+    buf = C.create_string_buffer(1 << 16)
+    for kind in ("prefix0", "typo1", "typo2"):
+        qs = queries(kind, 300)
+        t0 = time.perf_counter()
+        for term, cost, pre in qs:
+            R.ref_art_fuzzy(rt, term.encode(), cost, cost, 4, 1, pre, 0, b"", None, 0, 0, b"", buf, len(buf))
+        t_ref = (time.perf_counter() - t0) / len(qs) * 1e6
+        t0 = time.perf_counter()
+        for term, cost, pre in qs:
+            L.am_fuzzy(h, term.encode(), cost, cost, 4, 1, pre, b"", None, 0, 0, b"", buf, len(buf))
+        t_am = (time.perf_counter() - t0) / len(qs) * 1e6
+        t0 = time.perf_counter()
+        nh = 0
+        for term, cost, pre in qs:
+            nh += L.am_walk(h, 0, term.encode(), cost, cost, pre, hits.ctypes.data_as(C.POINTER(C.c_int32)), len(hits), C.byref(so))
+        t_walk = (time.perf_counter() - t0) / len(qs) * 1e6
+        res["per_search_us"][kind] = {"reference_art_fuzzy_search_i": round(t_ref, 1), "art_mirror_fuzzy_search": round(t_am, 1),
+                                      "art_mirror_walk_only": round(t_walk, 1), "hits_per_search": round(nh / len(qs), 1)}
+    p = res["per_search_us"]
+    per_query = p["prefix0"]["reference_art_fuzzy_search_i"] + 2 * (p["typo1"]["reference_art_fuzzy_search_i"] + p["typo2"]["reference_art_fuzzy_search_i"])
+    res["note"] = ("one core, max_candidates 4, MAX_SCORE order. A 3-token query that exhausts its typo budget asks for about 1 prefix search and 2 x (cost 1 + cost 2) "
+                   "searches on top of the exact lookups: ~%.0f us of reference walk per query, %.0f ms per 4096-query batch on one core — next to 37 ms of device "
+                   "time for the batch's scoring" % (per_query, per_query * 4096 / 1e3))
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -134,8 +134,9 @@ public:
         if(!prefix) s.q.push_back('\0');                           // the key's terminator takes part in a whole-word match
         s.min_cost = min_cost; s.max_cost = max_cost;
         s.prefix = prefix;
-        std::vector<int> row0(s.q.size() + 1);
-        for(size_t i = 0; i < row0.size(); i++) row0[i] = (int) i;
+        if(s.q.size() + 1 > (size_t) kMaxCols) return s.hits;      // cannot happen for indexed tokens (cut at 100 bytes)
+        int row0[kMaxCols];
+        for(size_t i = 0; i <= s.q.size(); i++) row0[i] = (int) i;
         if(root < 0) walk(s, 0, (uint8_t) leaves[~root].key.c_str()[0], root, 0, row0, row0);
         else walk(s, 0, 0, root, -1, row0, row0);
         return s.hits;
@@ -238,8 +239,7 @@ private:
 
     // optimal-string-alignment distance, one more key byte `c` (previous byte `p`): prev2 / prev are the rows of the two
     // shorter key prefixes
-    static void next_row(int depth, uint8_t p, uint8_t c, const std::vector<uint8_t>& q, const std::vector<int>& prev2,
-                         const std::vector<int>& prev, std::vector<int>& out) {
+    static void next_row(int depth, uint8_t p, uint8_t c, const std::vector<uint8_t>& q, const int* prev2, const int* prev, int* out) {
         out[0] = prev[0] + 1;
         for(size_t col = 1; col <= q.size(); col++) {
             const int subst = prev[col - 1] + (c == q[col - 1] ? 0 : 1);
@@ -251,7 +251,7 @@ private:
     // +1: every key below is a candidate; 0: read on; -1: give this branch up. Not a plain distance test: a cost that is
     // momentarily too high is tolerated when the next / previous query bytes explain it, and a prefix search accepts as soon
     // as the whole query has been consumed within bounds.
-    static int search_state(const search_t& s, int key_index, uint8_t p, uint8_t c, const std::vector<int>& row) {
+    static int search_state(const search_t& s, int key_index, uint8_t p, uint8_t c, const int* row) {
         const int qlen = (int) s.q.size();
         const bool key_ends = c == 0;
         const int key_len = key_ends ? key_index : key_index + 1;
@@ -279,8 +279,12 @@ private:
     }
 
     // depth -1: `ref` is the root and no byte has led to it. Children are visited from the largest byte down.
-    void walk(search_t& s, uint8_t p, uint8_t c, int32_t ref, int depth, const std::vector<int>& in_prev2, const std::vector<int>& in_prev) const {
-        std::vector<int> rows[3] = {in_prev2, in_prev, std::vector<int>(in_prev.size())};
+    static constexpr int kMaxCols = 104;               // query bytes (tokens are cut at 100) + terminator + column 0
+    void walk(search_t& s, uint8_t p, uint8_t c, int32_t ref, int depth, const int* in_prev2, const int* in_prev) const {
+        int rows[3][kMaxCols];                          // on the stack: a walk visits thousands of nodes
+        const size_t cols = s.q.size() + 1;
+        std::memcpy(rows[0], in_prev2, cols * sizeof(int));
+        std::memcpy(rows[1], in_prev, cols * sizeof(int));
         int i2 = 0, i1 = 1, i0 = 2;                     // rows[i1] is the row of the bytes read so far
         auto feed = [&](uint8_t byte, bool advance) -> int {
             if(advance) { next_row(depth, p, byte, s.q, rows[i2], rows[i1], rows[i0]); const int t = i2; i2 = i1; i1 = i0; i0 = t; }
