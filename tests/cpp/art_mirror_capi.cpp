@@ -136,4 +136,6 @@ size_t am_flat(void* hv, int which, void* out) {
 }
 int32_t am_root(void* hv) { return ((handle_t*) hv)->m.root; }
 
+unsigned long long am_last_visited() { return tsgpu::art_mirror_t::last_walk_visited(); }
+
 }

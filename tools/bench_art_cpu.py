@@ -36,6 +36,7 @@ def main():
     L.am_fuzzy.restype = C.c_size_t
     L.am_fuzzy.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_char_p, ol.u32p, C.c_size_t, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
     L.am_bind.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64), ol.u32p]
+    L.am_last_visited.restype = C.c_ulonglong
     t0 = time.time()
     h = L.am_build("\n".join(toks).encode(), ms.ctypes.data_as(C.POINTER(C.c_int64)), ol.p32(df), n)
     lo = np.arange(n + 1, dtype=np.uint64)
@@ -80,12 +81,13 @@ def main():
             L.am_fuzzy(h, term.encode(), cost, cost, 4, 1, pre, b"", None, 0, 0, b"", buf, len(buf))
         t_am = (time.perf_counter() - t0) / len(qs) * 1e6
         t0 = time.perf_counter()
-        nh = 0
+        nh = nv = 0
         for term, cost, pre in qs:
             nh += L.am_walk(h, 0, term.encode(), cost, cost, pre, hits.ctypes.data_as(C.POINTER(C.c_int32)), len(hits), C.byref(so))
+            nv += L.am_last_visited()
         t_walk = (time.perf_counter() - t0) / len(qs) * 1e6
         res["per_search_us"][kind] = {"reference_art_fuzzy_search_i": round(t_ref, 1), "art_mirror_fuzzy_search": round(t_am, 1),
-                                      "art_mirror_walk_only": round(t_walk, 1), "hits_per_search": round(nh / len(qs), 1)}
+                                      "art_mirror_walk_only": round(t_walk, 1), "hits_per_search": round(nh / len(qs), 1), "nodes_visited_per_search": round(nv / len(qs))}
     p = res["per_search_us"]
     per_query = p["prefix0"]["reference_art_fuzzy_search_i"] + 2 * (p["typo1"]["reference_art_fuzzy_search_i"] + p["typo2"]["reference_art_fuzzy_search_i"])
     res["note"] = ("one core, max_candidates 4, MAX_SCORE order. A 3-token query that exhausts its typo budget asks for about 1 prefix search and 2 x (cost 1 + cost 2) "

@@ -77,6 +77,7 @@ public:
     // list id of every leaf, for mirrors loaded from an export
     void bind_lists(const std::function<uint32_t(const std::string&)>& list_of) { for(auto& l: leaves) l.list = list_of(l.key); }
 
+    static uint64_t& last_walk_visited() { static thread_local uint64_t v = 0; return v; }      // size of the last walk_hits() (tuning)
     // art_search: the leaf whose key equals `token`, or -1
     int32_t find(const std::string& token) const {
         auto it = by_key.find(token);
@@ -139,6 +140,7 @@ public:
         for(size_t i = 0; i <= s.q.size(); i++) row0[i] = (int) i;
         if(root < 0) walk(s, 0, (uint8_t) leaves[~root].key.c_str()[0], root, 0, row0, row0);
         else walk(s, 0, 0, root, -1, row0, row0);
+        last_walk_visited() = s.visited;
         return s.hits;
     }
     std::vector<uint32_t> finish(const std::string& term, int min_cost, size_t max_words, token_ordering order, const std::string& prev_token,
@@ -235,6 +237,7 @@ private:
         int min_cost, max_cost;
         bool prefix;
         std::vector<int32_t> hits;                // subtrees (or single leaves) every key of which is a candidate
+        uint64_t visited = 0;                     // nodes and leaves the walk entered
     };
 
     // optimal-string-alignment distance, one more key byte `c` (previous byte `p`): prev2 / prev are the rows of the two
@@ -281,6 +284,7 @@ private:
     // depth -1: `ref` is the root and no byte has led to it. Children are visited from the largest byte down.
     static constexpr int kMaxCols = 104;               // query bytes (tokens are cut at 100) + terminator + column 0
     void walk(search_t& s, uint8_t p, uint8_t c, int32_t ref, int depth, const int* in_prev2, const int* in_prev) const {
+        s.visited++;
         int rows[3][kMaxCols];                          // on the stack: a walk visits thousands of nodes
         const size_t cols = s.q.size() + 1;
         std::memcpy(rows[0], in_prev2, cols * sizeof(int));
