@@ -195,6 +195,8 @@ typedef struct tsgpu_art {
     const int32_t*  child_ref;          /* [n_children] >= 0 inner node, < 0 leaf ~ref */
     const uint64_t* leaf_key_off;       /* [n_leaves + 1] -> leaf_keys (keys without the terminating NUL) */
     const uint8_t*  leaf_keys;
+    const uint32_t* node_rank;          /* [n_nodes], [n_leaves]: position in the pre-order of the tree with children from the largest */
+    const uint32_t* leaf_rank;          /* byte down (the order art_fuzzy_recurse visits); NULL: computed at load */
 } tsgpu_art;
 
 /* Replaces / extends the mirror of `field` (an id returned by tsgpu_index_load_field). Needs the host's exclusive lock. */

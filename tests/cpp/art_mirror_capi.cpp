@@ -136,6 +136,46 @@ size_t am_flat(void* hv, int which, void* out) {
 }
 int32_t am_root(void* hv) { return ((handle_t*) hv)->m.root; }
 
+// mode 2 of the walk: breadth-first over the flattened arrays with art_enter(), level by level as the frontier kernel will do it,
+// hits sorted by pre-order rank at the end; returns the hit count, *levels and *peak the number of levels and the largest frontier
+size_t am_walk_frontier(void* hv, const char* term, int min_cost, int max_cost, int prefix, int32_t* out, size_t cap, int* levels, size_t* peak) {
+    auto* h = (handle_t*) hv;
+    auto f = h->m.flatten();
+    std::vector<tsdev::ArtNodeDev> nodes(h->m.nodes.size());
+    for(size_t i = 0; i < nodes.size(); i++) {
+        nodes[i].first_child = f.node_first_child[i]; nodes[i].n_children = f.node_n_children[i]; nodes[i].partial_len = f.node_partial_len[i];
+        memcpy(nodes[i].partial, &f.node_partial[i * 8], 8); nodes[i].pad = 0;
+    }
+    tsdev::ArtDev A{nodes.data(), h->m.child_byte.data(), h->m.child_ref.data(), f.leaf_key_off.data(), f.leaf_keys.data(), h->m.root, h->m.empty ? 1u : 0u};
+    tsdev::ArtQuery Q;
+    const size_t tl = strlen(term);
+    *levels = 0; *peak = 0;
+    if(tl + (prefix ? 0 : 1) > (size_t) tsdev::kArtMaxQuery || h->m.empty) return 0;
+    memcpy(Q.q, term, tl);
+    Q.qlen = (int) tl;
+    if(!prefix) Q.q[Q.qlen++] = 0;
+    Q.min_cost = min_cost; Q.max_cost = max_cost; Q.prefix = prefix != 0;
+    const auto ranks = h->m.preorder_ranks();
+    std::vector<tsdev::ArtItem> cur(1), next;
+    tsdev::art_root_item(A, Q, cur[0]);
+    std::vector<int32_t> hits;
+    while(!cur.empty()) {
+        (*levels)++;
+        *peak = std::max(*peak, cur.size());
+        next.clear();
+        for(auto& it: cur) {                               // on the device: one thread / warp per item
+            bool hit = false;
+            const bool descend = tsdev::art_enter(A, Q, it, &hit);
+            if(hit) hits.push_back(it.ref);
+            if(descend) for(uint32_t k = 0; k < nodes[it.ref].n_children; k++) { next.emplace_back(); tsdev::art_child_item(A, Q, it, k, next.back()); }
+        }
+        cur.swap(next);
+    }
+    auto rank = [&](int32_t r) { return r < 0 ? ranks.leaf[~r] : ranks.node[r]; };
+    std::sort(hits.begin(), hits.end(), [&](int32_t a, int32_t b) { return rank(a) < rank(b); });
+    for(size_t i = 0; i < hits.size() && i < cap; i++) out[i] = hits[i];
+    return hits.size();
+}
 unsigned long long am_last_visited() { return tsgpu::art_mirror_t::last_walk_visited(); }
 
 }

@@ -342,3 +342,34 @@ def test_device_walk_function_equals_the_host_walk(am):
             n_hits += na
         am.am_free(h)
     assert n > 2000 and n_hits > 3000, (n, n_hits)
+
+
+def test_frontier_walk_with_preorder_ranks_equals_the_recursion(am):
+    """The breadth-first form (art_enter() per frontier item, level by level — the shape of the parallel device walk) finds the
+    same hits, and sorting them by the tree's static pre-order rank gives the recursion's order."""
+    am.am_walk.restype = C.c_size_t
+    am.am_walk.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_size_t, C.POINTER(C.c_int)]
+    am.am_walk_frontier.restype = C.c_size_t
+    am.am_walk_frontier.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+    rng = np.random.default_rng(31337)
+    cap = 1 << 14
+    a, b = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    so, lv, pk = C.c_int(0), C.c_int(0), C.c_size_t(0)
+    n = n_hits = max_levels = 0
+    for trial in range(30):
+        coll = make_collection(rng, trial)
+        toks = sorted(coll.vocab, key=coll.vocab.get)
+        df = np.diff(coll.flat.list_off.astype(np.int64)).astype(np.uint32)
+        ms = np.zeros(len(toks), np.int64)
+        h = am.am_build("\n".join(toks).encode(), ms.ctypes.data_as(C.POINTER(C.c_int64)), ol.p32(df), len(toks))
+        for q in queries(rng, coll, 60):
+            if len(q["term"]) + (0 if q["prefix"] else 1) > 31:
+                continue
+            na = am.am_walk(h, 0, q["term"].encode(), q["cost"], q["cost"], q["prefix"], a.ctypes.data_as(C.POINTER(C.c_int32)), cap, C.byref(so))
+            nb = am.am_walk_frontier(h, q["term"].encode(), q["cost"], q["cost"], q["prefix"], b.ctypes.data_as(C.POINTER(C.c_int32)), cap, C.byref(lv), C.byref(pk))
+            assert na == nb and a[:na].tolist() == b[:nb].tolist(), (trial, q["term"], q["cost"], q["prefix"])
+            n += 1
+            n_hits += na
+            max_levels = max(max_levels, lv.value)
+        am.am_free(h)
+    assert n > 1500 and n_hits > 2000 and max_levels >= 4, (n, n_hits, max_levels)

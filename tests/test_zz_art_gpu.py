@@ -29,14 +29,19 @@ def flat_arrays(am, h):
 
 @pytest.mark.gpu
 @pytest.mark.xfail(strict=False, reason="opt-in f-1 kernel: written without GPU access, first GPU run pending (see DESIGN.md §11.3)")
-def test_art_walk_batch_matches_host_walk():
+@pytest.mark.parametrize("mode", ["dfs", "frontier"])
+def test_art_walk_batch_matches_host_walk(mode):
     """Runs the check below in a child process: a kernel that has never run may fault, and a poisoned CUDA context must not
-    reach the fixtures of the tests that gate the suite."""
+    reach the fixtures of the tests that gate the suite. dfs: one thread per search (art_walk_kernel); frontier: one thread per
+    node visit, level by level, hits sorted back by pre-order rank (art_frontier_kernel; small chunks so several are needed)."""
     import os
     import subprocess
     import sys
+    env = dict(os.environ, TSGPU_ART_CHILD="1")
+    if mode == "frontier":
+        env.update(TSGPU_ART_MODE="frontier", TSGPU_ART_CHUNK="64")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider",
-                        "-k", "child_art_walk"], env=dict(os.environ, TSGPU_ART_CHILD="1"), capture_output=True, text=True, timeout=600,
+                        "-k", "child_art_walk"], env=env, capture_output=True, text=True, timeout=600,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and " passed" in r.stdout, (r.stdout + r.stderr)[-3000:]
 

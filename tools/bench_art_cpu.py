@@ -37,6 +37,8 @@ def main():
     L.am_fuzzy.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_char_p, ol.u32p, C.c_size_t, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
     L.am_bind.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64), ol.u32p]
     L.am_last_visited.restype = C.c_ulonglong
+    L.am_walk_frontier.restype = C.c_size_t
+    L.am_walk_frontier.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
     t0 = time.time()
     h = L.am_build("\n".join(toks).encode(), ms.ctypes.data_as(C.POINTER(C.c_int64)), ol.p32(df), n)
     lo = np.arange(n + 1, dtype=np.uint64)
@@ -86,6 +88,15 @@ def main():
             nh += L.am_walk(h, 0, term.encode(), cost, cost, pre, hits.ctypes.data_as(C.POINTER(C.c_int32)), len(hits), C.byref(so))
             nv += L.am_last_visited()
         t_walk = (time.perf_counter() - t0) / len(qs) * 1e6
+        lv, pk = C.c_int(0), C.c_size_t(0)
+        levels = peaks = 0
+        for term, cost, pre in qs[:60]:
+            if len(term) + (0 if pre else 1) > 31:
+                continue
+            L.am_walk_frontier(h, term.encode(), cost, cost, pre, hits.ctypes.data_as(C.POINTER(C.c_int32)), len(hits), C.byref(lv), C.byref(pk))
+            levels = max(levels, lv.value)
+            peaks = max(peaks, pk.value)
+        res.setdefault("frontier_form", {})[kind] = {"levels_max": levels, "largest_frontier_items": peaks}
         res["per_search_us"][kind] = {"reference_art_fuzzy_search_i": round(t_ref, 1), "art_mirror_fuzzy_search": round(t_am, 1),
                                       "art_mirror_walk_only": round(t_walk, 1), "hits_per_search": round(nh / len(qs), 1), "nodes_visited_per_search": round(nv / len(qs))}
     p = res["per_search_us"]

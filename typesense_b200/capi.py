@@ -194,7 +194,7 @@ class GpuIndex:
                 np.ascontiguousarray(node_partial_len, np.uint8), np.ascontiguousarray(node_partial, np.uint8),
                 np.ascontiguousarray(child_byte, np.uint8), np.ascontiguousarray(child_ref, np.int32),
                 np.ascontiguousarray(leaf_key_off, np.uint64), np.ascontiguousarray(leaf_keys, np.uint8)]
-        a = ArtStruct(len(arrs[0]), len(arrs[4]), len(arrs[6]) - 1, root, *[x.ctypes.data if len(x) else None for x in arrs])
+        a = ArtStruct(len(arrs[0]), len(arrs[4]), len(arrs[6]) - 1, root, *[x.ctypes.data if len(x) else None for x in arrs], None, None)
         _ck(self.L.tsgpu_index_load_art(self.h, field, C.byref(a)))
 
     def art_walk(self, field: int, terms: Sequence[bytes], min_cost: Sequence[int], max_cost: Sequence[int], prefix: Sequence[int], cap: int = 256):

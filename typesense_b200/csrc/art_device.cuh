@@ -95,12 +95,81 @@ TS_HD int art_state(const ArtQuery& Q, int key_index, uint8_t p, uint8_t c, cons
     return -1;
 }
 
-struct ArtFrame {
+// One visit: `ref` is about to be entered through key byte c (previous byte p) at `depth` with the two DP rows of the
+// path so far (depth -1: the root, no byte leads to it).
+struct ArtItem {
     ArtRow prev2, prev;
     int32_t ref;
     int16_t depth;
+    uint8_t p, c;
+};
+
+// Consumes the byte leading to the item's node and the node's own bytes (its compressed path, or a leaf's remaining key).
+// Returns true when the node's children have to be visited: the item then holds the state they start from (rows, depth, and
+// c = the last byte read, their `p`). *hit: every key below item.ref is a candidate (the walk does not descend further).
+TS_HD bool art_enter(const ArtDev& A, const ArtQuery& Q, ArtItem& it, bool* hit) {
+    ArtRow rows[3];
+    for(int i = 0; i <= Q.qlen; i++) { rows[0][i] = it.prev2[i]; rows[1][i] = it.prev[i]; }
+    int i2 = 0, i1 = 1, i0 = 2;
+    int depth = it.depth;
+    uint8_t p = it.p, c = it.c;
+    const int32_t ref = it.ref;
+    bool decided = false;
+    *hit = false;
+#define ART_STEP(BYTE, ADVANCE)                                                                          \
+    {                                                                                                    \
+        const uint8_t byte_ = (BYTE);                                                                    \
+        if(ADVANCE) { art_next_row(depth, p, byte_, Q, rows[i2], rows[i1], rows[i0]); const int t_ = i2; i2 = i1; i1 = i0; i0 = t_; } \
+        const int a_ = art_state(Q, depth, p, byte_, rows[i1]);                                          \
+        if(a_ == 1) *hit = true;                                                                         \
+        if(a_ != 0) decided = true; else { p = byte_; depth++; }                                         \
+    }
+    if(depth == -1) depth = 0;
+    else ART_STEP(c, !(Q.prefix && c == 0))
+    if(decided) return false;
+    if(ref < 0) {
+        const uint64_t o = A.leaf_key_off[~ref];
+        const int klen = (int) (A.leaf_key_off[~ref + 1] - o) + 1;            // with the terminator
+        const int iter_len = klen < Q.qlen + Q.max_cost ? klen : Q.qlen + Q.max_cost;
+        if(depth >= iter_len) { *hit = art_state(Q, depth, 0, 0, rows[i1]) == 1; return false; }
+        while(depth < iter_len && !decided) {
+            c = depth < klen - 1 ? A.leaf_keys[o + depth] : 0;
+            ART_STEP(c, !(Q.prefix && c == 0))
+        }
+        return false;
+    }
+    const ArtNodeDev& n = A.nodes[ref];
+    int seen = n.partial_len < kArtPartialBytes ? n.partial_len : kArtPartialBytes;
+    for(int i = 0; i < seen && !decided; i++) { c = n.partial[i]; ART_STEP(c, true) }
+    // only the first kArtPartialBytes of a compressed path are stored: the rest is assumed to agree with the query
+    while(!decided && seen < (int) n.partial_len && depth < Q.qlen) { c = Q.q[depth]; ART_STEP(c, true) seen++; }
+#undef ART_STEP
+    if(decided) return false;
+    for(int i = 0; i <= Q.qlen; i++) { it.prev2[i] = rows[i2][i]; it.prev[i] = rows[i1][i]; }
+    it.depth = (int16_t) depth; it.c = c;
+    return true;
+}
+
+TS_HD void art_root_item(const ArtDev& A, const ArtQuery& Q, ArtItem& it) {
+    it.ref = A.root; it.p = 0; it.c = 0; it.depth = -1;
+    if(A.root < 0) {              // a one-key index: the root is that leaf and its first byte is read like any other
+        const uint64_t o = A.leaf_key_off[~A.root];
+        it.c = A.leaf_key_off[~A.root + 1] > o ? A.leaf_keys[o] : 0;
+        it.depth = 0;
+    }
+    for(int i = 0; i <= Q.qlen; i++) { it.prev2[i] = (uint8_t) i; it.prev[i] = (uint8_t) i; }
+}
+// the item of child k of an entered inner node
+TS_HD void art_child_item(const ArtDev& A, const ArtQuery& Q, const ArtItem& parent, uint32_t k, ArtItem& ch) {
+    const ArtNodeDev& n = A.nodes[parent.ref];
+    ch.ref = A.child_ref[n.first_child + k]; ch.c = A.child_byte[n.first_child + k]; ch.p = parent.c; ch.depth = parent.depth;
+    for(int i = 0; i <= Q.qlen; i++) { ch.prev2[i] = parent.prev2[i]; ch.prev[i] = parent.prev[i]; }
+}
+
+// Depth-first driver (one thread does a whole search): a frame is an entered inner node and the next child to visit.
+struct ArtFrame {
+    ArtItem at;
     uint16_t next_child;       // children [0, next_child) are still to visit, from the top
-    uint8_t c;
 };
 
 // Writes the matching refs (walk order) to hits[0..cap) and returns how many there are (may exceed cap: caller's overflow).
@@ -110,67 +179,33 @@ TS_HD uint32_t art_walk(const ArtDev& A, const ArtQuery& Q, int32_t* hits, uint3
     *stack_overflow = false;
     if(A.empty) return 0;
     int sp = 0;
-    ArtRow rows[3];
-    // enter(): consume the byte leading to `ref` (unless it is the root), then the node's own bytes; a leaf is decided here, an
-    // undecided inner node becomes a frame
-    int32_t ref = A.root;
-    uint8_t p = 0, c = 0;
-    int depth = A.root < 0 ? 0 : -1;
-    if(A.root < 0) { const uint64_t o = A.leaf_key_off[~A.root]; c = A.leaf_key_off[~A.root + 1] > o ? A.leaf_keys[o] : 0; }
-    for(int i = 0; i <= Q.qlen; i++) { rows[0][i] = (uint8_t) i; rows[1][i] = (uint8_t) i; }
+    ArtItem it;
+    art_root_item(A, Q, it);
     bool have = true;
     while(true) {
         if(!have) {
             if(sp == 0) break;
             ArtFrame& f = stack[sp - 1];
             if(f.next_child == 0) { sp--; continue; }
-            const ArtNodeDev& pn = A.nodes[f.ref];
-            const uint32_t k = pn.first_child + --f.next_child;
-            ref = A.child_ref[k];
-            p = f.c; c = A.child_byte[k]; depth = f.depth;
-            for(int i = 0; i <= Q.qlen; i++) { rows[0][i] = f.prev2[i]; rows[1][i] = f.prev[i]; }
+            art_child_item(A, Q, f.at, --f.next_child, it);
         }
         have = false;
-        int i2 = 0, i1 = 1, i0 = 2;
-        bool decided = false;
-        // one key byte: returns false when the branch is decided
-#define ART_STEP(BYTE, ADVANCE)                                                                          \
-        {                                                                                                \
-            const uint8_t byte_ = (BYTE);                                                                \
-            if(ADVANCE) { art_next_row(depth, p, byte_, Q, rows[i2], rows[i1], rows[i0]); const int t_ = i2; i2 = i1; i1 = i0; i0 = t_; } \
-            const int a_ = art_state(Q, depth, p, byte_, rows[i1]);                                      \
-            if(a_ == 1) { if(n_hits < cap) hits[n_hits] = ref; n_hits++; }                               \
-            if(a_ != 0) decided = true; else { p = byte_; depth++; }                                     \
-        }
-        if(depth == -1) depth = 0;
-        else ART_STEP(c, !(Q.prefix && c == 0))
-        if(decided) continue;
-        if(ref < 0) {
-            const uint64_t o = A.leaf_key_off[~ref];
-            const int klen = (int) (A.leaf_key_off[~ref + 1] - o) + 1;            // with the terminator
-            const int iter_len = klen < Q.qlen + Q.max_cost ? klen : Q.qlen + Q.max_cost;
-            if(depth >= iter_len) {
-                if(art_state(Q, depth, 0, 0, rows[i1]) == 1) { if(n_hits < cap) hits[n_hits] = ref; n_hits++; }
-                continue;
-            }
-            while(depth < iter_len && !decided) {
-                c = depth < klen - 1 ? A.leaf_keys[o + depth] : 0;
-                ART_STEP(c, !(Q.prefix && c == 0))
-            }
-            continue;
-        }
-        const ArtNodeDev& n = A.nodes[ref];
-        int seen = n.partial_len < kArtPartialBytes ? n.partial_len : kArtPartialBytes;
-        for(int i = 0; i < seen && !decided; i++) { c = n.partial[i]; ART_STEP(c, true) }
-        while(!decided && seen < (int) n.partial_len && depth < Q.qlen) { c = Q.q[depth]; ART_STEP(c, true) seen++; }
-        if(decided) continue;
-#undef ART_STEP
+        bool hit = false;
+        const bool descend = art_enter(A, Q, it, &hit);
+        if(hit) { if(n_hits < cap) hits[n_hits] = it.ref; n_hits++; }
+        if(!descend) continue;
         if(sp == kArtMaxStack) { *stack_overflow = true; return n_hits; }
-        ArtFrame& f = stack[sp++];
-        for(int i = 0; i <= Q.qlen; i++) { f.prev2[i] = rows[i2][i]; f.prev[i] = rows[i1][i]; }
-        f.ref = ref; f.depth = (int16_t) depth; f.next_child = n.n_children; f.c = c;
+        stack[sp].at = it;
+        stack[sp].next_child = A.nodes[it.ref].n_children;
+        sp++;
     }
     return n_hits;
 }
+
+// Breadth-first driver, one level: every item of `in` is entered; hits go to (hit_search, hit_ref), the children of the nodes
+// that have to be descended into become the next level's items. The device form gives one thread (later: one warp) per item and
+// appends with atomic counters; this serial form is what tests/ run on the host. Hits come out in no particular order: the
+// reference's order is the pre-order of the tree with children descending, a static rank per node (art_mirror_t::preorder_ranks).
+struct ArtWorkItem { ArtItem at; uint32_t search; };
 
 }  // namespace tsdev

@@ -6,6 +6,9 @@
 // first run on a GPU.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -25,6 +28,7 @@ using namespace tsdev;
 struct ArtState {
     std::vector<void*> alloc;
     ArtDev dev{};
+    std::vector<uint32_t> node_rank, leaf_rank;          // pre-order ranks (host side): restore the recursion's hit order
 };
 // per tsgpu_index: the fields' mirrors, a stream of its own and a grow-only staging buffer; walk calls on one index serialise
 struct ArtIndexState {
@@ -71,6 +75,48 @@ art_walk_kernel(const ArtDev A, uint32_t n, const uint32_t* __restrict__ term_of
     const uint32_t cnt = art_walk(A, Q, out_hits + (size_t) i * cap, cap, stack, &deep);
     out_counts[i] = cnt;
     out_flags[i] = deep ? 1 : (cnt > cap ? 4 : 0);
+}
+
+// ---- frontier form: the node visit is the unit of parallelism -----------------------------------------------------------
+// Level by level: every item of the current frontier (search, node about to be entered, its two DP rows) is entered by one
+// thread; accepted subtrees go to the hit list, the children of nodes to descend into are appended to the next frontier.
+struct Hit { uint32_t search; int32_t ref; };
+
+__global__ void art_frontier_init_kernel(const ArtDev A, const ArtQuery* __restrict__ queries, const uint32_t* __restrict__ search_ids, uint32_t n,
+                                         ArtWorkItem* __restrict__ items) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    ArtWorkItem w;
+    w.search = search_ids[i];
+    art_root_item(A, queries[w.search], w.at);
+    items[i] = w;
+}
+
+__global__ void __launch_bounds__(128)
+art_frontier_kernel(const ArtDev A, const ArtQuery* __restrict__ queries, const ArtWorkItem* __restrict__ in, uint32_t n_in,
+                    ArtWorkItem* __restrict__ out, uint32_t out_cap, uint32_t* __restrict__ counters /* 0 next items, 1 hits, 2 overflow */,
+                    Hit* __restrict__ hits, uint32_t hit_cap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n_in) return;
+    ArtWorkItem w = in[i];
+    const ArtQuery Q = queries[w.search];
+    bool hit = false;
+    const bool descend = art_enter(A, Q, w.at, &hit);
+    if(hit) {
+        const uint32_t pos = atomicAdd(counters + 1, 1u);
+        if(pos < hit_cap) hits[pos] = Hit{w.search, w.at.ref}; else atomicOr(counters + 2, 1u);
+    }
+    if(descend) {
+        const uint32_t nch = A.nodes[w.at.ref].n_children;
+        const uint32_t base = atomicAdd(counters + 0, nch);
+        if(base + nch > out_cap) { atomicOr(counters + 2, 2u); return; }
+        for(uint32_t k = 0; k < nch; k++) {
+            ArtWorkItem ch;
+            ch.search = w.search;
+            art_child_item(A, Q, w.at, k, ch.at);
+            out[base + k] = ch;
+        }
+    }
 }
 
 }  // namespace
@@ -144,6 +190,23 @@ extern "C" tsgpu_status tsgpu_index_load_art(tsgpu_index* idx, uint32_t field, c
     if(e != cudaSuccess) { release(st); return tsgpu_fail_(TSGPU_ERR_CUDA, cudaGetErrorString(e)); }
     st.dev.root = a->root;
     st.dev.empty = a->n_leaves == 0 ? 1u : 0u;
+    st.node_rank.assign(a->n_nodes, 0);
+    st.leaf_rank.assign(a->n_leaves, 0);
+    if(a->node_rank && a->leaf_rank) {
+        if(a->n_nodes) cudaMemcpy(st.node_rank.data(), a->node_rank, (size_t) a->n_nodes * 4, cudaMemcpyDefault);
+        if(a->n_leaves) cudaMemcpy(st.leaf_rank.data(), a->leaf_rank, (size_t) a->n_leaves * 4, cudaMemcpyDefault);
+    } else if(a->n_leaves) {                  // pre-order with children from the largest byte down
+        uint32_t next = 0;
+        std::vector<int32_t> stack{a->root};
+        while(!stack.empty()) {
+            const int32_t r = stack.back();
+            stack.pop_back();
+            if(r < 0) { st.leaf_rank[~r] = next++; continue; }
+            st.node_rank[r] = next++;
+            if(next > a->n_nodes + a->n_leaves) { release(st); return tsgpu_fail_(TSGPU_ERR_INVALID, "tsgpu_art: the links do not form a tree"); }
+            for(uint32_t k = 0; k < nch[r]; k++) stack.push_back(cref[first[r] + k]);
+        }
+    }
     ArtIndexState* is = state_of(idx, true);
     std::lock_guard<std::mutex> lk(is->call_mu);
     auto& slot = is->fields[field];
@@ -166,6 +229,93 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
     auto fit = is->fields.find(field);
     if(fit == is->fields.end()) return tsgpu_fail_(TSGPU_ERR_INVALID, "no ART mirror loaded for this field");
     const ArtDev A = fit->second.dev;
+    static const bool frontier_mode = getenv("TSGPU_ART_MODE") && std::string(getenv("TSGPU_ART_MODE")) == "frontier";
+    if(frontier_mode) {
+        // ---- breadth-first: chunks of searches, one launch per tree level, hits sorted back into the recursion's order on the host
+        const ArtState& AS = fit->second;
+        std::vector<uint32_t> h_off((size_t) n + 1);
+        CUA(cudaMemcpy(h_off.data(), term_off, h_off.size() * 4, cudaMemcpyDefault));
+        for(uint32_t i = 0; i < n; i++) if(h_off[i + 1] < h_off[i]) return tsgpu_fail_(TSGPU_ERR_INVALID, "term offsets not ascending");
+        std::vector<uint8_t> h_terms(h_off[n] + 1), h_min(n), h_max(n), h_pre(n);
+        if(h_off[n]) CUA(cudaMemcpy(h_terms.data(), terms, h_off[n], cudaMemcpyDefault));
+        CUA(cudaMemcpy(h_min.data(), min_cost, n, cudaMemcpyDefault));
+        CUA(cudaMemcpy(h_max.data(), max_cost, n, cudaMemcpyDefault));
+        CUA(cudaMemcpy(h_pre.data(), prefix, n, cudaMemcpyDefault));
+        std::vector<ArtQuery> hq(n);
+        std::vector<uint8_t> flags(n, 0);
+        std::vector<uint32_t> counts(n, 0);
+        std::vector<int32_t> out((size_t) n * cap, 0);
+        for(uint32_t i = 0; i < n; i++) {
+            const uint32_t len = h_off[i + 1] - h_off[i];
+            ArtQuery& Q = hq[i];
+            memset(&Q, 0, sizeof Q);
+            if(len + (h_pre[i] ? 0u : 1u) > (uint32_t) kArtMaxQuery) { flags[i] = 2; continue; }
+            memcpy(Q.q, h_terms.data() + h_off[i], len);
+            Q.qlen = (int) len;
+            if(!h_pre[i]) Q.q[Q.qlen++] = 0;
+            Q.min_cost = h_min[i]; Q.max_cost = h_max[i]; Q.prefix = h_pre[i] != 0;
+        }
+        const uint32_t chunk = (uint32_t) std::max(1, getenv("TSGPU_ART_CHUNK") ? atoi(getenv("TSGPU_ART_CHUNK")) : 256);
+        const uint32_t item_cap = (uint32_t) std::max(1024, getenv("TSGPU_ART_ITEMS") ? atoi(getenv("TSGPU_ART_ITEMS")) : (4 << 20));
+        const uint32_t hit_cap = std::max<uint32_t>(item_cap, chunk * cap);
+        auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+        const size_t o_q = 0, o_ids = al((size_t) n * sizeof(ArtQuery)), o_cnt = al(o_ids + (size_t) chunk * 4), o_a = al(o_cnt + 16);
+        const size_t o_b = al(o_a + (size_t) item_cap * sizeof(ArtWorkItem)), o_hits = al(o_b + (size_t) item_cap * sizeof(ArtWorkItem));
+        const size_t total = o_hits + (size_t) hit_cap * sizeof(Hit);
+        if(!is->stream) CUA(cudaStreamCreateWithFlags(&is->stream, cudaStreamNonBlocking));
+        if(total > is->scratch_cap) {
+            if(is->scratch) cudaFree(is->scratch);
+            is->scratch = nullptr; is->scratch_cap = 0;
+            CUA(cudaMalloc(&is->scratch, total));
+            is->scratch_cap = total;
+        }
+        unsigned char* d = is->scratch;
+        cudaStream_t st = is->stream;
+        CUA(cudaMemcpyAsync(d + o_q, hq.data(), (size_t) n * sizeof(ArtQuery), cudaMemcpyHostToDevice, st));
+        ArtWorkItem* bufs[2] = {(ArtWorkItem*) (d + o_a), (ArtWorkItem*) (d + o_b)};
+        uint32_t* d_cnt = (uint32_t*) (d + o_cnt);
+        std::vector<Hit> h_hits;
+        auto rank_of = [&](int32_t r) { return r < 0 ? AS.leaf_rank[~r] : AS.node_rank[r]; };
+        for(uint32_t base = 0; base < n; base += chunk) {
+            std::vector<uint32_t> ids;
+            for(uint32_t i = base; i < std::min(n, base + chunk); i++) if(flags[i] == 0) ids.push_back(i);
+            if(ids.empty()) continue;
+            CUA(cudaMemcpyAsync(d + o_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, st));
+            CUA(cudaMemsetAsync(d_cnt, 0, 16, st));
+            art_frontier_init_kernel<<<((uint32_t) ids.size() + 127) / 128, 128, 0, st>>>(A, (const ArtQuery*) (d + o_q), (const uint32_t*) (d + o_ids),
+                                                                                           (uint32_t) ids.size(), bufs[0]);
+            CUA(cudaGetLastError());
+            uint32_t n_cur = (uint32_t) ids.size(), h_cnt[4] = {0, 0, 0, 0};
+            int cur = 0;
+            bool overflow = false;
+            for(int level = 0; n_cur && level < 256; level++) {
+                CUA(cudaMemsetAsync(d_cnt, 0, 4, st));                    // next-frontier counter only: hits accumulate over the levels
+                art_frontier_kernel<<<(n_cur + 127) / 128, 128, 0, st>>>(A, (const ArtQuery*) (d + o_q), bufs[cur], n_cur, bufs[cur ^ 1], item_cap, d_cnt,
+                                                                         (Hit*) (d + o_hits), hit_cap);
+                CUA(cudaGetLastError());
+                CUA(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));
+                CUA(cudaStreamSynchronize(st));
+                if(h_cnt[2]) { overflow = true; break; }
+                n_cur = h_cnt[0];
+                cur ^= 1;
+            }
+            if(overflow || n_cur) { for(uint32_t i: ids) flags[i] = 4; continue; }       // the host walks this chunk's searches
+            h_hits.resize(h_cnt[1]);
+            if(h_cnt[1]) CUA(cudaMemcpyAsync(h_hits.data(), d + o_hits, (size_t) h_cnt[1] * sizeof(Hit), cudaMemcpyDeviceToHost, st));
+            CUA(cudaStreamSynchronize(st));
+            std::sort(h_hits.begin(), h_hits.end(), [&](const Hit& x, const Hit& y) { return x.search != y.search ? x.search < y.search : rank_of(x.ref) < rank_of(y.ref); });
+            for(const Hit& hh: h_hits) {
+                uint32_t& c = counts[hh.search];
+                if(c < cap) out[(size_t) hh.search * cap + c] = hh.ref;
+                c++;
+            }
+            for(uint32_t i: ids) if(counts[i] > cap) flags[i] = 4;
+        }
+        CUA(cudaMemcpy(out_counts, counts.data(), (size_t) n * 4, cudaMemcpyDefault));
+        CUA(cudaMemcpy(out_flags, flags.data(), n, cudaMemcpyDefault));
+        CUA(cudaMemcpy(out_hits, out.data(), (size_t) n * cap * 4, cudaMemcpyDefault));
+        return TSGPU_OK;
+    }
     std::vector<uint32_t> h_off((size_t) n + 1);
     CUA(cudaMemcpy(h_off.data(), term_off, h_off.size() * 4, cudaMemcpyDefault));
     for(uint32_t i = 0; i < n; i++) if(h_off[i + 1] < h_off[i]) return tsgpu_fail_(TSGPU_ERR_INVALID, "term offsets not ascending");

@@ -105,6 +105,28 @@ public:
         return f;
     }
 
+    // Position of every node / leaf in the order the reference's recursion visits the tree (pre-order, children from the largest
+    // byte down). The hits of any search, in any order, sorted by this rank are the hits in the reference's order — what a
+    // breadth-first (frontier-parallel) device walk needs to hand back the same list as the depth-first one.
+    struct ranks_t { std::vector<uint32_t> node, leaf; };
+    ranks_t preorder_ranks() const {
+        ranks_t r;
+        r.node.assign(nodes.size(), 0);
+        r.leaf.assign(leaves.size(), 0);
+        if(empty) return r;
+        uint32_t next = 0;
+        std::vector<int32_t> stack{root};
+        while(!stack.empty()) {
+            const int32_t ref = stack.back();
+            stack.pop_back();
+            if(ref < 0) { r.leaf[~ref] = next++; continue; }
+            r.node[ref] = next++;
+            const node_t& n = nodes[ref];
+            for(uint32_t k = 0; k < n.n_children; k++) stack.push_back(child_ref[n.first_child + k]);      // popped largest byte first
+        }
+        return r;
+    }
+
     // ---- search ------------------------------------------------------------------------------------------------------
     // has_filter_doc(list): the posting list holds a document of the active filter (only consulted when filter_active);
     // share_doc(a, b): lists a and b hold a common document (that also passes the filter when one is active).

@@ -862,7 +862,7 @@ public:
             const auto f = art.flatten();
             tsgpu_art a{(uint32_t) art.nodes.size(), (uint32_t) art.child_byte.size(), (uint32_t) art.leaves.size(), art.root,
                         f.node_first_child.data(), f.node_n_children.data(), f.node_partial_len.data(), f.node_partial.data(),
-                        art.child_byte.data(), art.child_ref.data(), f.leaf_key_off.data(), f.leaf_keys.data()};
+                        art.child_byte.data(), art.child_ref.data(), f.leaf_key_off.data(), f.leaf_keys.data(), nullptr, nullptr};
             arts_on_device[fid] = tsgpu_index_load_art(h, fid, &a) == TSGPU_OK;
             if(!arts_on_device[fid]) return;
         }

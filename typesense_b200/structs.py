@@ -64,7 +64,8 @@ class ArtStruct(C.Structure):
     """tsgpu_art (include/tsgpu.h)"""
     _fields_ = [("n_nodes", C.c_uint32), ("n_children", C.c_uint32), ("n_leaves", C.c_uint32), ("root", C.c_int32),
                 ("node_first_child", C.c_void_p), ("node_n_children", C.c_void_p), ("node_partial_len", C.c_void_p), ("node_partial", C.c_void_p),
-                ("child_byte", C.c_void_p), ("child_ref", C.c_void_p), ("leaf_key_off", C.c_void_p), ("leaf_keys", C.c_void_p)]
+                ("child_byte", C.c_void_p), ("child_ref", C.c_void_p), ("leaf_key_off", C.c_void_p), ("leaf_keys", C.c_void_p),
+                ("node_rank", C.c_void_p), ("leaf_rank", C.c_void_p)]
 
 
 class StatsStruct(C.Structure):
