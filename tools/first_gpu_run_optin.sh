@@ -24,4 +24,8 @@ for n in ("default", "regscore"):
 PY
 TSGPU_REG_SCORE=1 ncu --set full --clock-control none --import-source on -k regex:kw_search_kernel -s 1 -c 1 -o $OUT/optin_prof_kw_regscore -f \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2> $OUT/optin_ncu.log
+# 4. f-1: the candidate walk on the device, both forms, next to profiles/r01d_art_cpu.json
+python tools/bench_art_gpu.py > $OUT/optin_art_dfs.json 2> $OUT/optin_art_dfs.err
+TSGPU_ART_MODE=frontier python tools/bench_art_gpu.py > $OUT/optin_art_frontier.json 2> $OUT/optin_art_frontier.err
+tail -1 $OUT/optin_art_dfs.json; tail -1 $OUT/optin_art_frontier.json
 ls -la $OUT | grep optin
