@@ -85,6 +85,29 @@ size_t am_fuzzy(void* hv, const char* term, int min_cost, int max_cost, size_t m
 }
 
 
+// am_fuzzy that also hands back the exclude set as the search left it (it grows by every leaf the search collected, also those
+// the final truncation dropped — exactly what the reference's unique_tokens sees)
+size_t am_fuzzy_ex(void* hv, const char* term, int min_cost, int max_cost, size_t max_words, int order, int prefix, const char* prev_token,
+                   const char* exclude, char* out, size_t out_cap, char* exclude_out, size_t exclude_cap) {
+    auto* h = (handle_t*) hv;
+    std::set<std::string> excl;
+    for(auto& t: split_nl(exclude)) if(!t.empty()) excl.insert(t);
+    tsgpu::art_mirror_t::doc_tests docs;
+    docs.share_doc = [&](uint32_t a, uint32_t b) { return intersects(h->lists[a], h->lists[b], nullptr); };
+    auto res = h->m.fuzzy_search(term, min_cost, max_cost, max_words, order == 1 ? tsgpu::art_mirror_t::MAX_SCORE : tsgpu::art_mirror_t::FREQUENCY,
+                                 prefix != 0, prev_token ? prev_token : "", docs, excl);
+    auto put = [](const std::vector<std::string>& v, char* dst, size_t cap) {
+        size_t w = 0;
+        for(auto& k: v) { if(w + k.size() + 1 >= cap) break; memcpy(dst + w, k.data(), k.size()); w += k.size(); dst[w++] = '\n'; }
+        if(cap) dst[w < cap ? w : cap - 1] = 0;
+    };
+    std::vector<std::string> keys;
+    for(uint32_t li: res) keys.push_back(h->m.leaves[li].key);
+    put(keys, out, out_cap);
+    put(std::vector<std::string>(excl.begin(), excl.end()), exclude_out, exclude_cap);
+    return res.size();
+}
+
 // walk_hits on the host mirror (mode 0) or through the device function art_walk() on the flattened arrays (mode 1); refs as int32
 size_t am_walk(void* hv, int mode, const char* term, int min_cost, int max_cost, int prefix, int32_t* out, size_t cap, int* stack_overflow) {
     auto* h = (handle_t*) hv;

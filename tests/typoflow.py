@@ -5,11 +5,12 @@ refflow's backends so the reference's typo and prefix scenarios (test/collection
   Index::next_suggestion2        src/index.cpp:7204-7248   total_cost = sum(2*typo + prefix-found)
   Index::get_bounded_typo_cost   src/index.cpp:6923-6951
   drop-tokens loop               src/index.cpp:3920-4017
-Candidate generation is the reference's ART walk (src/art.cpp: art_fuzzy_search_i). The faithful
-implementation is typesense_b200/host/art_mirror.hpp (pinned on the reference's compiled art.cpp, tests/test_art_mirror.py)
-and is what the C++ host layer uses; THIS Python harness keeps a brute-force scan of the (tiny) test vocabulary, which
-agrees with the walk on every replayed scenario but accepts a superset in corner cases the walk's pruning rules skip
-(DESIGN.md §11.3): optimal-string-alignment distance exactly equal to the
+Candidate generation is the reference's ART walk (src/art.cpp: art_fuzzy_search_i): field_candidates() calls
+typesense_b200/host/art_mirror.hpp (pinned on the reference's compiled art.cpp, tests/test_art_mirror.py; the same code the
+C++ host layer uses) through tests/cpp/libartmirror.so. field_candidates_scan() is the earlier stand-in, kept for
+comparison — a brute-force scan of the vocabulary that agrees with the walk on every replayed scenario but accepts a
+superset in corner cases the walk's pruning rules skip:
+optimal-string-alignment distance exactly equal to the
 cost, prefix rule of fuzzy_search_state, leaves ordered by frequency / max_score (ties: token order), the exact leaf
 first, at most max_candidates; fields are scanned in query_by order with one shared set of already-produced tokens. For the
 last token of a multi-token query the reference first looks only at the fields that hold the previous token (most
@@ -25,6 +26,33 @@ import refflow
 from typesense_b200 import structs as S
 
 FREQUENCY, MAX_SCORE = 0, 1
+
+_ART = None
+
+
+def art_lib():
+    """tests/cpp/libartmirror.so: C entry points around typesense_b200/host/art_mirror.hpp (built on demand with g++)."""
+    global _ART
+    if _ART is None:
+        import ctypes as C
+        import os
+        import subprocess
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        so = os.path.join(root, "tests", "cpp", "libartmirror.so")
+        deps = [os.path.join(root, "tests", "cpp", "art_mirror_capi.cpp"), os.path.join(root, "typesense_b200", "host", "art_mirror.hpp"),
+                os.path.join(root, "typesense_b200", "csrc", "art_device.cuh")]
+        if not os.path.exists(so) or max(os.path.getmtime(d) for d in deps) > os.path.getmtime(so):
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", deps[0], "-o", so])
+        L = C.CDLL(so)
+        L.am_build.restype = C.c_void_p
+        L.am_build.argtypes = [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_uint32), C.c_uint32]
+        L.am_bind.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.am_free.argtypes = [C.c_void_p]
+        L.am_fuzzy_ex.restype = C.c_size_t
+        L.am_fuzzy_ex.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t,
+                                  C.c_char_p, C.c_size_t]
+        _ART = L
+    return _ART
 
 
 def osa_rows(term: str, key: str):
@@ -91,7 +119,48 @@ class TypoSearcher:
         fl, l = self.coll.flats[f], self.coll.vocabs[f][t]
         return fl.ids[int(fl.list_off[l]):int(fl.list_off[l + 1])]
 
+    def __del__(self):
+        for h, *_ in getattr(self, "_arts", {}).values():
+            try:
+                art_lib().am_free(h)
+            except Exception:
+                pass
+
+    def art_of(self, f: int):
+        """the field's ART mirror (built from the vocabulary: max_score = best points of the token's documents)"""
+        import ctypes as C
+        if not hasattr(self, "_arts"):
+            self._arts = {}
+        if f not in self._arts:
+            L = art_lib()
+            vocab, fl = self.coll.vocabs[f], self.coll.flats[f]
+            toks = sorted(vocab, key=vocab.get)
+            df = np.ascontiguousarray(np.diff(fl.list_off.astype(np.int64)), np.uint32)
+            ms = np.asarray([self.max_score[f][t] for t in toks], np.int64)
+            blob = "\n".join(toks).encode()
+            h = L.am_build(blob, ms.ctypes.data_as(C.POINTER(C.c_int64)), df.ctypes.data_as(C.POINTER(C.c_uint32)), len(toks))
+            lo = np.ascontiguousarray(fl.list_off, np.uint64)
+            ids = np.ascontiguousarray(fl.ids, np.uint32)
+            L.am_bind(h, blob, lo.ctypes.data_as(C.POINTER(C.c_uint64)), ids.ctypes.data_as(C.POINTER(C.c_uint32)))
+            self._arts[f] = (h, lo, ids, blob)
+        return self._arts[f][0]
+
     def field_candidates(self, f: int, token: str, cost: int, prefix_search: bool, unique_tokens: set, prev_token: str = "") -> List[str]:
+        """art_fuzzy_search_i on the field's ART mirror (typesense_b200/host/art_mirror.hpp, pinned on the reference's compiled
+        art.cpp): the candidates, and unique_tokens grown by every leaf the search collected."""
+        import ctypes as C
+        if not self.coll.vocabs[f] or any(ord(ch) > 127 or ch == "\n" for ch in token):
+            return self.field_candidates_scan(f, token, cost, prefix_search, unique_tokens, prev_token)
+        L = art_lib()
+        out, excl = C.create_string_buffer(1 << 16), C.create_string_buffer(1 << 18)
+        L.am_fuzzy_ex(self.art_of(f), token.encode(), cost, cost, self.max_cand, 1 if self.token_order == MAX_SCORE else 0, 1 if prefix_search else 0,
+                      (prev_token or "").encode(), "\n".join(sorted(unique_tokens)).encode(), out, len(out), excl, len(excl))
+        unique_tokens.clear()
+        unique_tokens.update(x for x in excl.value.decode().split("\n") if x)
+        return [x for x in out.value.decode().split("\n") if x]
+
+    def field_candidates_scan(self, f: int, token: str, cost: int, prefix_search: bool, unique_tokens: set, prev_token: str = "") -> List[str]:
+        """The earlier stand-in, kept for comparison: a brute-force scan of the vocabulary with a plain distance test."""
         vocab = self.coll.vocabs[f]
         rank = self.freq[f] if self.token_order == FREQUENCY else self.max_score[f]
         exact = token if token in vocab else None
