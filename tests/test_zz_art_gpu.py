@@ -41,7 +41,7 @@ def test_art_walk_batch_matches_host_walk(mode):
     if mode == "frontier":
         env.update(TSGPU_ART_MODE="frontier", TSGPU_ART_CHUNK="64")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider",
-                        "-k", "child_art_walk"], env=env, capture_output=True, text=True, timeout=600,
+                        "-k", "child_art_walk"], env=env, capture_output=True, text=True, timeout=300,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and " passed" in r.stdout, (r.stdout + r.stderr)[-3000:]
 
@@ -101,5 +101,5 @@ def test_host_layer_scenarios_with_device_walk():
         pytest.skip("links the real libtsgpu.so")
     tch.build()
     r = subprocess.run([tch.BIN, os.path.join(tch.ROOT, "tests", "golden", "documents.jsonl")], capture_output=True, text=True, cwd=tch.ROOT,
-                       env=dict(os.environ, TSGPU_HOST_DEVICE_ART="1", TSGPU_HOST_HYBRID_KAT="1"), timeout=600)
+                       env=dict(os.environ, TSGPU_HOST_DEVICE_ART="1", TSGPU_HOST_HYBRID_KAT="1"), timeout=300)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]

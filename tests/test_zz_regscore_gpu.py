@@ -23,6 +23,6 @@ def test_keyword_parity_with_register_resident_scoring():
         from test_gpu_tests_dryrun import GPU_ONLY
         for t in GPU_ONLY:
             cmd += ["--deselect", t]
-    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=480)
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0 and " passed" in r.stdout, tail
