@@ -64,7 +64,15 @@ def test_child_art_walk_batch_matches_host_walk(am):
         toks = sorted(coll.vocab, key=coll.vocab.get)
         df = np.diff(coll.flat.list_off.astype(np.int64)).astype(np.uint32)
         ms = np.zeros(len(toks), np.int64)
-        h = am.am_build("\n".join(toks).encode(), ms.ctypes.data_as(C.POINTER(C.c_int64)), T.ol.p32(df), len(toks))
+        if trial % 2 and T.ol.have_ref() and hasattr(T.ol.ref(), "ref_art_new"):      # a mirror LOADED from the reference's live tree
+            R = T.ol.ref()
+            rt = T.ref_tree(R, coll)
+            blob = T.export(R, rt)
+            R.ref_art_free(rt)
+            h = am.am_load(blob, len(blob))
+            assert h
+        else:
+            h = am.am_build("\n".join(toks).encode(), ms.ctypes.data_as(C.POINTER(C.c_int64)), T.ol.p32(df), len(toks))
         root, arrs = flat_arrays(am, h)
         gi = capi.GpuIndex(coll.n_docs, 0)
         fid = gi.load_field(coll.flat)
