@@ -168,7 +168,7 @@ static void collection_scenarios(const std::string& jsonl) {
             std::vector<tsgpu::Index::search_request> reqs;
             for(auto& c: cases) reqs.push_back({tsgpu::tokenize_ascii(c.q), {"title"}, sort_fields, c.drop, 250, c.o});
             index.clear_walk_cache();
-            const auto before = tsgpu::Index::art_walk_stats();
+            const uint64_t launches0 = tsgpu::Index::art_walk_stats().launches, searches0 = tsgpu::Index::art_walk_stats().searches;
             const uint64_t calls0 = tsgpu::Index::kw_device_calls();
             auto seq = index.multi_search(reqs, /*in_lockstep=*/false);
             const uint64_t calls_seq = tsgpu::Index::kw_device_calls() - calls0;
@@ -190,9 +190,9 @@ static void collection_scenarios(const std::string& jsonl) {
             }
             if(getenv("TSGPU_HOST_DEVICE_ART")) {      // 15 searches, one field: one launch up front carries (nearly) all walks
                 const auto& after = tsgpu::Index::art_walk_stats();
-                printf("multi_search: %llu launches for %llu walks\n", (unsigned long long) (after.launches - before.launches),
-                       (unsigned long long) (after.searches - before.searches));
-                CHECK(after.searches - before.searches >= 20 && after.launches - before.launches <= 2);
+                printf("multi_search: %llu launches for %llu walks\n", (unsigned long long) (after.launches - launches0),
+                       (unsigned long long) (after.searches - searches0));
+                CHECK(after.searches - searches0 >= 20 && after.launches - launches0 <= 2);
             }
             for(size_t i = 0; i < cases.size(); i++) {
                 CHECK(resps[i].status.ok());

@@ -31,6 +31,7 @@
 // Header-only; needs only libtsgpu.so. There is no CPU implementation behind these calls.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <exception>
 #include <map>
@@ -293,7 +294,7 @@ class Index {
     // device_art_walk: hit lists fetched ahead by prefetch_walks, keyed by (field, prefix search, cost, token)
     mutable std::map<std::tuple<uint32_t, bool, int, std::string>, std::vector<int32_t>> walk_cache;
 public:
-    struct art_walk_stats_t { uint64_t launches = 0, searches = 0, served = 0, host_fallbacks = 0; };
+    struct art_walk_stats_t { std::atomic<uint64_t> launches{0}, searches{0}, served{0}, host_fallbacks{0}; };
     static art_walk_stats_t& art_walk_stats() { static art_walk_stats_t s; return s; }     // process-wide, for tests and tuning
     void clear_walk_cache() { walk_cache.clear(); }
 private:
@@ -606,7 +607,7 @@ public:
             qs[i]->count = count[i]; qs[i]->found = found[i]; qs[i]->done = true;
         }
     }
-    static uint64_t& kw_device_calls() { static uint64_t n = 0; return n; }        // tsgpu_keyword_search_batch calls made (tests, tuning)
+    static std::atomic<uint64_t>& kw_device_calls() { static std::atomic<uint64_t> n{0}; return n; }        // tsgpu_keyword_search_batch calls made (tests, tuning)
 
     // multi_search in lock-step (the batching shim of SURVEY 8b, src/core_api.cpp:1080-1131): every search of the request list
     // runs its unchanged control flow (typo combinations, restarts, drop-token rounds) on a thread of its own, but only ONE of
