@@ -9,6 +9,7 @@
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../typesense_b200/host/tsgpu_host.hpp"
@@ -201,6 +202,24 @@ static void collection_scenarios(const std::string& jsonl) {
                 CHECK(ids == cases[i].expect);
                 if(cases[i].found >= 0) CHECK((long) resps[i].found == cases[i].found);
             }
+        }
+        {   // concurrent searches on one Index, as the reference's request threads do (each holds only the shared lock)
+            index.clear_walk_cache();
+            std::vector<std::thread> threads;
+            std::vector<int> ok(4, 0);
+            for(int t = 0; t < 4; t++) threads.emplace_back([&, t] {
+                int good = 0;
+                for(int rep = 0; rep < 3; rep++) for(size_t i = t; i < cases.size(); i += 2) {
+                    std::vector<tsgpu::KV> kv2; size_t f2 = 0;
+                    if(!index.search(tsgpu::tokenize_ascii(cases[i].q), {"title"}, sort_fields, cases[i].drop, 250, kv2, f2, cases[i].o).ok()) continue;
+                    auto ids = ids_of(kv2);
+                    if(ids.size() > cases[i].per_page) ids.resize(cases[i].per_page);
+                    good += ids == cases[i].expect;
+                }
+                ok[t] = good;
+            });
+            for(auto& th: threads) th.join();
+            for(int t = 0; t < 4; t++) CHECK(ok[t] == 3 * (int) ((cases.size() - t + 1) / 2));
         }
         CHECK(index.search(tsgpu::tokenize_ascii("redundant"), {"title"}, sort_fields, 10, 250, kvs, found, opt(2, true, 0)).ok());
         CHECK(kvs.size() == 1 && found == 1);

@@ -289,14 +289,14 @@ class Index {
     // per field: the ART mirror of its vocabulary for (MAX_SCORE, FREQUENCY) leaf scores; rebuilt lazily after a change of
     // fields or sort columns (a server-side binding loads it from an export of the live art_tree instead, see art_mirror.hpp)
     mutable std::vector<art_mirror_t> arts;
-    mutable std::vector<bool> arts_ready;
-    mutable std::vector<bool> arts_on_device;
+    mutable std::vector<char> arts_ready, arts_on_device;      // char, not bool: flags of different fields are touched independently
+    mutable std::mutex cache_mu;                             // searches may run concurrently on one Index (as on the reference's): guards the lazy caches
     // device_art_walk: hit lists fetched ahead by prefetch_walks, keyed by (field, prefix search, cost, token)
     mutable std::map<std::tuple<uint32_t, bool, int, std::string>, std::vector<int32_t>> walk_cache;
 public:
     struct art_walk_stats_t { std::atomic<uint64_t> launches{0}, searches{0}, served{0}, host_fallbacks{0}; };
     static art_walk_stats_t& art_walk_stats() { static art_walk_stats_t s; return s; }     // process-wide, for tests and tuning
-    void clear_walk_cache() { walk_cache.clear(); }
+    void clear_walk_cache() { std::lock_guard<std::mutex> lk(cache_mu); walk_cache.clear(); }
 private:
     std::unordered_map<std::string, std::vector<int64_t>> sort_values;
     std::string default_sorting_field;
@@ -336,7 +336,8 @@ public:
         vocabs[fid].list_off = list_off;
         vocabs[fid].ids = ids;
         token_ids[fid] = std::move(tid);
-        arts_ready.assign(arts_ready.size(), false);
+        if(arts.size() <= fid) { arts.resize(fid + 1); arts_ready.resize(fid + 1, 0); arts_on_device.resize(fid + 1, 0); }   // sized here, under the host's exclusive lock
+        arts_ready.assign(arts_ready.size(), 0);
         return Option<uint32_t>(fid);
     }
     // sort_index[field] (spp::sparse_hash_map<uint32, int64>): docs without a value sort as INT64_MIN
@@ -347,7 +348,7 @@ public:
         if(tsgpu_index_load_sort_column(h, dense.data(), &col) != TSGPU_OK) return Option<uint32_t>(500, tsgpu_last_error());
         sort_cols[name] = col;
         sort_values[name] = dense;
-        arts_ready.assign(arts_ready.size(), false);         // leaf max_score comes from the default sorting field
+        arts_ready.assign(arts_ready.size(), 0);             // leaf max_score comes from the default sorting field
         if(default_sorting_field.empty()) default_sorting_field = name;      // the schema's default_sorting_field
         return Option<uint32_t>(col);
     }
@@ -831,7 +832,7 @@ public:
     // query) only tokens that share a document with it in this field qualify (validate_and_add_leaf, src/art.cpp:1024-1036).
     // The mirror is built from the vocabulary, so tokens of EQUAL rank may come in another order than from a live tree.
     const art_mirror_t& art_of(uint32_t fid) const {
-        if(arts.size() <= fid) { arts.resize(fid + 1); arts_ready.resize(fid + 1, false); arts_on_device.resize(fid + 1, false); }
+        std::lock_guard<std::mutex> lk(cache_mu);
         if(!arts_ready[fid]) {
             const vocab_t& v = vocabs[fid];
             const std::vector<int64_t>* scores = nullptr;
@@ -845,13 +846,22 @@ public:
                 entries.push_back({v.tokens[l], best, (uint32_t) (v.list_off[l + 1] - v.list_off[l]), l});
             }
             arts[fid].build(entries);
-            arts_ready[fid] = true;
-            arts_on_device[fid] = false;
+            arts_ready[fid] = 1;
+            arts_on_device[fid] = 0;
             walk_cache.clear();
         }
         return arts[fid];
     }
     struct query_token { std::string value; bool is_prefix_searched; };
+    using walk_key = std::tuple<uint32_t, bool, int, std::string>;
+    bool has_walk(const walk_key& k) const { std::lock_guard<std::mutex> lk(cache_mu); return walk_cache.count(k) != 0; }
+    bool cached_walk(const walk_key& k, std::vector<int32_t>& hits) const {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        auto it = walk_cache.find(k);
+        if(it == walk_cache.end()) return false;
+        hits = it->second;
+        return true;
+    }
     // One tsgpu_art_walk_batch for a list of (token, cost, prefix) searches on one field; the hit lists land in walk_cache.
     // A walk depends on nothing but these three — not on the tokens already taken, the previous token or a filter, which
     // only enter art_mirror_t::finish — so walks may be fetched ahead of the control flow that may or may not need them.
@@ -859,14 +869,16 @@ public:
     void device_walks(uint32_t fid, const std::vector<walk_request>& reqs) const {
         const art_mirror_t& art = art_of(fid);
         if(art.empty || reqs.empty()) return;
+        std::unique_lock<std::mutex> up(cache_mu);
         if(!arts_on_device[fid]) {
             const auto f = art.flatten();
             tsgpu_art a{(uint32_t) art.nodes.size(), (uint32_t) art.child_byte.size(), (uint32_t) art.leaves.size(), art.root,
                         f.node_first_child.data(), f.node_n_children.data(), f.node_partial_len.data(), f.node_partial.data(),
                         art.child_byte.data(), art.child_ref.data(), f.leaf_key_off.data(), f.leaf_keys.data(), nullptr, nullptr};
-            arts_on_device[fid] = tsgpu_index_load_art(h, fid, &a) == TSGPU_OK;
+            arts_on_device[fid] = tsgpu_index_load_art(h, fid, &a) == TSGPU_OK ? 1 : 0;
             if(!arts_on_device[fid]) return;
         }
+        up.unlock();
         const uint32_t n = (uint32_t) reqs.size(), cap = 1024;
         std::vector<uint32_t> off(1, 0), cnt(n);
         std::vector<uint8_t> terms, cost8, pre8, flags(n);
@@ -880,6 +892,7 @@ public:
         if(tsgpu_art_walk_batch(h, fid, n, off.data(), terms.data(), cost8.data(), cost8.data(), pre8.data(), hits.data(), cap, cnt.data(), flags.data()) != TSGPU_OK)
             return;
         art_walk_stats().launches++; art_walk_stats().searches += n;
+        std::lock_guard<std::mutex> lk(cache_mu);
         for(uint32_t i = 0; i < n; i++)
             if(flags[i] == 0)            // flagged searches stay out of the cache: fuzzy_candidates walks them on the host
                 walk_cache[std::make_tuple(fid, reqs[i].prefix, reqs[i].cost, reqs[i].token)] =
@@ -895,7 +908,7 @@ public:
                 const int max_cost = std::min<int>((int) o.num_typos, get_bounded_typo_cost(2, t.value, o.min_len_1typo, o.min_len_2typo));
                 const bool prefix_search = o.prefix && t.is_prefix_searched;
                 for(int c = 0; c <= max_cost; c++)
-                    if(!walk_cache.count(std::make_tuple(fid, prefix_search, c, t.value))) reqs.push_back({t.value, c, prefix_search});
+                    if(!has_walk(std::make_tuple(fid, prefix_search, c, t.value))) reqs.push_back({t.value, c, prefix_search});
             }
             device_walks(fid, reqs);
         }
@@ -914,13 +927,13 @@ public:
         std::vector<int32_t> hits;
         bool walked = false;
         if(o.device_art_walk && !art.empty) {
-            auto hit = walk_cache.find(std::make_tuple(fid, prefix_search, cost, token));
-            if(hit == walk_cache.end()) {             // not speculated by prefetch_walks: fetch this one search
+            const walk_key key = std::make_tuple(fid, prefix_search, cost, token);
+            walked = cached_walk(key, hits);
+            if(!walked) {                             // not speculated by prefetch_walks: fetch this one search
                 device_walks(fid, {{token, cost, prefix_search}});
-                hit = walk_cache.find(std::make_tuple(fid, prefix_search, cost, token));
+                walked = cached_walk(key, hits);
             }
-            if(hit != walk_cache.end()) { hits = hit->second; walked = true; art_walk_stats().served++; }
-            else art_walk_stats().host_fallbacks++;
+            if(walked) art_walk_stats().served++; else art_walk_stats().host_fallbacks++;
         }
         if(!walked) hits = art.walk_hits(token, cost, cost, prefix_search);        // also the fallback for flagged searches
         std::vector<std::string> out;
@@ -1149,7 +1162,7 @@ public:
                     const uint32_t fid = fit->second;
                     for(int c = 0; c <= max_cost; c++) {
                         const auto key = std::make_tuple(fid, prefix_search, c, t);
-                        if(walk_cache.count(key) || !asked.insert(key).second) continue;
+                        if(has_walk(key) || !asked.insert(key).second) continue;
                         per_field[fid].push_back({t, c, prefix_search});
                     }
                 }
