@@ -1,7 +1,5 @@
 """SURVEY §8 f-1 on the GPU: tsgpu_art_walk_batch (one thread per search, art_kernels.cu) against the host walk of the same
-ART mirror (art_mirror_t::walk_hits, which tests/test_art_mirror.py pins on the reference's compiled art.cpp). The kernel was
-written after round 1's GPU budget was spent and has only run on the CPU (the same art_walk() compiled by g++), so this
-test does not gate the suite yet: it reports XPASS / XFAIL until the kernel has been seen to pass on a B200."""
+ART mirror (art_mirror_t::walk_hits, which tests/test_art_mirror.py pins on the reference's compiled art.cpp). It passed on the driver's B200 in round 1 and gates since round 2."""
 import ctypes as C
 
 import numpy as np
@@ -28,7 +26,6 @@ def flat_arrays(am, h):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="opt-in f-1 kernel: written without GPU access, first GPU run pending (see DESIGN.md §11.3)")
 @pytest.mark.parametrize("mode", ["dfs", "frontier"])
 def test_art_walk_batch_matches_host_walk(mode):
     """Runs the check below in a child process: a kernel that has never run may fault, and a poisoned CUDA context must not
@@ -97,7 +94,6 @@ def test_child_art_walk_batch_matches_host_walk(am):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="opt-in f-1 kernel: written without GPU access, first GPU run pending (see DESIGN.md §11.3)")
 def test_host_layer_scenarios_with_device_walk():
     """tests/cpp/host_scenarios (the reference's typo / prefix / ranking scenarios through the C++ host layer) with every
     candidate walk routed through tsgpu_art_walk_batch, plus the rank-fusion KATs on 3-vector graphs through

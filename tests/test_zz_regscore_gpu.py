@@ -1,7 +1,6 @@
 """The opt-in register-resident scoring kernel (TSGPU_REG_SCORE=1, kw_regscore.cu) against the oracle on the GPU. The switch
 is read once per process, so the keyword parity tests and the reference scenarios are re-run in a child process with it
-set. The file sorts last on purpose: it checks an experimental path and must not stand in front of the others; and since the
-kernel has never run on a GPU it does not gate the suite yet (XPASS / XFAIL) — the default kernel's tests do."""
+set. The file sorts last on purpose: it checks an experimental path and must not stand in front of the others; it passed on the driver's B200 in round 1 and gates since round 2."""
 import os
 import subprocess
 import sys
@@ -12,7 +11,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="opt-in kernel (TSGPU_REG_SCORE=1): written without GPU access, first GPU run pending (see DESIGN.md §11.1)")
 def test_keyword_parity_with_register_resident_scoring():
     env = dict(os.environ, TSGPU_REG_SCORE="1")
     cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
