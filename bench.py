@@ -274,7 +274,7 @@ def workload_config(args, batch):
                        "graph": "bulk windowed-kNN build (harness), shared with the CPU oracle"},
             "cache": "index working set (>= 30 GB vectors + postings) >> 126 MB L2; a different query batch every step",
             "parallelism": f"replica x{args.gpus}, queries sharded",
-            "kw_scoring": "register-resident (TSGPU_REG_SCORE=1)" if os.environ.get("TSGPU_REG_SCORE") == "1" else "default"}
+            "kw_scoring": "r01 local-array scorer (TSGPU_REG_SCORE=0)" if os.environ.get("TSGPU_REG_SCORE") == "0" else "register-resident (default)"}
 
 
 # ------------------------------------------------------------------------------------------------ tsgpu arm

@@ -512,7 +512,7 @@ tsgpu_status run_keyword(tsgpu_index* idx, KwPlan& pl, uint32_t kv_stride, KwDev
         P.F = pl.F; P.KP = pl.KP; P.NL = pl.NL;
         for(uint32_t f = 0; f < (uint32_t) kMaxFieldSlots; f++) P.field_ids[f] = pl.field_ids[f];
         const size_t smem = kw_search_smem(pl);
-        static const bool reg_score = getenv("TSGPU_REG_SCORE") && atoi(getenv("TSGPU_REG_SCORE")) == 1;   // opt-in until measured
+        static const bool reg_score = !(getenv("TSGPU_REG_SCORE") && atoi(getenv("TSGPU_REG_SCORE")) == 0);   // default since r02: 29.4 -> 19.4 ms per 4096 queries (profiles/r02a_*); =0 selects the r01 kernel for A/B
         if(reg_score) CU(tsgpu_launch_kw_search_regscore(&idx->ixdev, &P, pl.n_units, smem, st));          // kw_regscore.cu
         else {
             CU(cudaFuncSetAttribute(kw_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024)));
