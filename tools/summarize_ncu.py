@@ -44,8 +44,9 @@ def main():
                 if w in d:
                     lines.append(f"| {w} | {d[w]} | {u.get(w, '')} |")
             try:
-                tr = float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"])
-                lines.append(f"| dram traffic (read+write) | {tr:.3f} | {u.get('dram__bytes_read.sum','')} |")
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+                tr = sum(float(d[k].replace(",", "")) * scale[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                lines.append(f"| dram traffic (read+write) | {tr / 1e9:.3f} | Gbyte |")
             except Exception:
                 pass
             lines.append("")
