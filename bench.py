@@ -364,6 +364,7 @@ def run_tsgpu(args, rank, world, local_rank):
     # events on the library's stream) with the overlap switched off. Not part of `value`.
     os.environ["TSGPU_KNN_OVERLAP_BLOCKS"] = "0"
     sts_iso = [step(args.warmup + i, True) for i in range(min(args.steps, 4))]
+    knn_work = gi.knn_work(nq) if hybrid else None
     os.environ.pop("TSGPU_KNN_OVERLAP_BLOCKS", None)
     launches_per_region = (launches * args.steps) // (args.steps + args.warmup)
     # latency of a small multi_search (64 queries, host buffers in and out), the p50/p99 half of BASELINE.json's metric
@@ -427,6 +428,13 @@ def run_tsgpu(args, rank, world, local_rank):
                                        "knn": ms_knn, "total": statistics.mean(s["ms_total"] for s in sts_iso)}
         extra["work_per_step"] = {k: float(statistics.mean(s_[k] for s_ in sts_iso)) for k in
                                   ("kw_driver_ids", "kw_probe_ids", "kw_matches", "knn_dist", "knn_expanded", "knn_spec_hits")}
+        if knn_work is not None and len(knn_work):
+            ex = np.sort(knn_work[:, 0])
+            filt = (gbatches[(args.warmup + min(args.steps, 4) - 1) % n_b][0].q_filter != -1)[:len(knn_work)]
+            extra["knn_walks"] = {"expanded_mean": float(ex.mean()), "expanded_p50": int(ex[len(ex) // 2]), "expanded_p99": int(ex[int(0.99 * (len(ex) - 1))]),
+                                  "expanded_max": int(ex[-1]), "expanded_mean_filtered": float(knn_work[filt, 0].mean()) if filt.any() else None,
+                                  "expanded_mean_unfiltered": float(knn_work[~filt, 0].mean()) if (~filt).any() else None,
+                                  "dist_max": int(knn_work[:, 1].max())}
         if traffic:
             extra["roofline_traffic_source"] = traffic.get("source")
         if want_cpu:

@@ -144,6 +144,22 @@ tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint
 tsgpu_status tsgpu_index_load_sort_column(tsgpu_index* idx, const int64_t* vals, uint32_t* out_col);
 /* Mirror hnsw_index_t (vectors + graph). Pointers may be host or device memory. */
 tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g);
+/* Build the vector index ON THE DEVICE: hnswlib's addPoint (the loop of Index::batch_memory_index, src/index.cpp:1003-1054,
+ * which the reference runs on 4 host threads) as batched rounds — see csrc/hnsw_build.cuh. label == row index. Levels are
+ * drawn exactly as hnswlib draws them (std::default_random_engine(seed)); with max_batch == 1 the graph equals the
+ * single-threaded hnswlib build link for link; larger batches relax the insertion order the way hnswlib's own
+ * multi-threaded build does, deterministically. M in 2..16. `vectors` may be host or device memory; with
+ * keep_device_vectors != 0 a device buffer is used in place (the caller keeps it alive for the index's lifetime). */
+tsgpu_status tsgpu_index_build_hnsw(tsgpu_index* idx, const float* vectors, uint32_t n, uint32_t dim, uint32_t M,
+                                    uint32_t ef_construction, uint32_t seed, uint32_t metric, uint32_t max_batch,
+                                    int keep_device_vectors);
+/* Shape of the loaded / built graph; build_counters[5] (may be null) = distance evaluations of the construction searches,
+ * expansions, heuristic distance evaluations, rows re-selected, rounds of the last tsgpu_index_build_hnsw. */
+tsgpu_status tsgpu_index_hnsw_info(tsgpu_index* idx, uint32_t* n_nodes, uint32_t* dim, uint32_t* M, uint32_t* max_level,
+                                   uint32_t* entry_point, uint64_t* n_upper_records, uint64_t* build_counters);
+/* Copy the graph out (what a snapshot would persist; what the parity oracle walks). Destinations may be host or device
+ * memory, any may be null: levels[n], links0[n*(2M+1)], upper_off[n+1], links_up[n_upper_records*(M+1)]. */
+tsgpu_status tsgpu_index_export_hnsw(tsgpu_index* idx, uint8_t* levels, uint32_t* links0, uint64_t* upper_off, uint32_t* links_up);
 /* Persistent filter (a mirrored filter leaf / cached filter result): sorted seq_ids -> device bitmap. */
 tsgpu_status tsgpu_filter_create(tsgpu_index* idx, const uint32_t* ids, size_t n, int32_t* out_handle);
 tsgpu_status tsgpu_filter_destroy(tsgpu_index* idx, int32_t handle);
@@ -269,8 +285,12 @@ typedef struct {
     float    ms_kw_merge;        // kw_merge_kernel levels + kw_final_kernel + found_popcount_kernel
     float    ms_host_plan;       /* host wall time of batch planning (build_kw_plan) inside the call; the GPU idles meanwhile */
     uint64_t knn_spec_hits;      /* expansions whose node was the one the walk had prefetched for (speculation hit) */
+    uint64_t knn_tier2_walks;    /* graph walks whose visited set outgrew shared memory (continued in the HBM tier) */
+    uint64_t knn_retried;        /* graph walks that outgrew their slot's scratch and were re-run alone with a full-size slot */
 } tsgpu_stats;
 tsgpu_status tsgpu_get_stats(tsgpu_index* idx, tsgpu_stats* out);
+/* Instrumentation: per graph walk of the last HNSW launch, out[2q] = expanded nodes, out[2q+1] = distance evaluations. */
+tsgpu_status tsgpu_debug_knn_work(tsgpu_index* idx, uint32_t* out, uint32_t cap_queries, uint32_t* out_n);
 
 #ifdef __cplusplus
 }

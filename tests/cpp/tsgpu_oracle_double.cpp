@@ -245,6 +245,12 @@ tsgpu_status tsgpu_filter_destroy(tsgpu_index* idx, int32_t handle) {
     return TSGPU_OK;
 }
 tsgpu_status tsgpu_get_stats(tsgpu_index*, tsgpu_stats* out) { memset(out, 0, sizeof(*out)); return TSGPU_OK; }
+tsgpu_status tsgpu_index_build_hnsw(tsgpu_index*, const float*, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, int) {
+    g_err = "the test double has no device build"; return TSGPU_ERR_NO_DEVICE;
+}
+tsgpu_status tsgpu_index_hnsw_info(tsgpu_index*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint64_t*, uint64_t*) { g_err = "the test double has no device build"; return TSGPU_ERR_NO_DEVICE; }
+tsgpu_status tsgpu_index_export_hnsw(tsgpu_index*, uint8_t*, uint32_t*, uint64_t*, uint32_t*) { g_err = "the test double has no device build"; return TSGPU_ERR_NO_DEVICE; }
+tsgpu_status tsgpu_debug_knn_work(tsgpu_index*, uint32_t*, uint32_t, uint32_t* out_n) { *out_n = 0; return TSGPU_OK; }
 tsgpu_status tsgpu_knn_batch(tsgpu_index* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef, const int32_t* q_filter, uint32_t,
                              const uint64_t* filter_off, const uint32_t* filter_ids, float* out_dist, uint32_t* out_labels, uint32_t* out_n) {
     Double* d = D(idx);

@@ -242,6 +242,34 @@ def test_knn_generic_dim_and_reference_kat():
     gi.close()
 
 
+def test_knn_selective_filters_long_walks():
+    """Selective filters make hnswlib visit most of the graph before `ef` allowed results exist (the functor gates only the
+    result heap): the visited set leaves shared memory (tier 2) and, with a handful of allowed ids, outgrows the per-slot
+    scratch — those walks are handed to the retry launch and must still return the oracle's answer, without disturbing the
+    other queries of the batch (one long walk used to fail the whole call)."""
+    import torch
+    n, dim = 90000, 32
+    vec = synth.make_vectors_clustered(n, dim, 45, seed=5, device="cuda", spread=0.5, latent=8, center_latent=8)[0]
+    lv, l0, uo, lu, ml, ep = synth.build_graph_bulk(vec, 16, 100)
+    g = S.HnswGraph(vec.cpu().numpy(), lv.cpu().numpy(), l0.cpu().numpy().astype(np.uint32), uo.cpu().numpy().astype(np.uint64),
+                    lu.cpu().numpy().astype(np.uint32), 16, ml, ep)
+    gi = capi.GpuIndex(n, 0)
+    gi.load_hnsw(g)
+    oi = ol.OracleIndex(n, [], [], g)
+    rng = np.random.default_rng(8)
+    qv = synth.make_vectors_clustered(48, dim, 45, seed=77, device="cpu", spread=0.5, latent=8, center_latent=8, centers_seed=5)[0].numpy()
+    filters = [np.unique(rng.integers(0, n, 25)).astype(np.uint32),            # ~25 allowed ids: the walk covers the graph (retry)
+               np.unique(rng.integers(0, n, n // 40)).astype(np.uint32),       # 2.5 %: thousands of visited nodes (tier 2)
+               np.arange(0, n, 2, dtype=np.uint32)]
+    qf = (np.arange(len(qv)) % 4 - 1).astype(np.int32)                         # -1 (none), 0, 1, 2
+    d, l, cnt = gi.knn(qv, 10, 30, qf, filters)
+    st = gi.stats()
+    od, olab, ocnt, _ = oi.knn(qv, 10, 30, qf, filters)
+    assert cnt.tolist() == ocnt.tolist() and l.tolist() == olab.tolist() and (d == od).all()
+    assert st["knn_tier2_walks"] > 0 and st["knn_retried"] > 0, st
+    gi.close()
+
+
 def _vec_queries(rng, fd, n, filters, sort, with_combos):
     toks = synth.sample_queries(fd, n, 2, int(rng.integers(0, 1 << 30)))
     qs = []

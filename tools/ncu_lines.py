@@ -25,9 +25,15 @@ def main():
     base = int(inst[0][0], 16)
     d = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, capture_output=True)
-    cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-    sass = subprocess.run(["nvdisasm", "-g", os.path.join(d, cubin)], capture_output=True, text=True).stdout.splitlines()
-    start = next(i for i, l in enumerate(sass) if l.startswith(".text.") and sect in l)
+    sass, start = None, None
+    for cubin in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):          # one cubin per translation unit
+        cand = subprocess.run(["nvdisasm", "-g", os.path.join(d, cubin)], capture_output=True, text=True).stdout.splitlines()
+        hit = [i for i, l in enumerate(cand) if l.startswith(".text.") and sect in l]
+        if hit:
+            sass, start = cand, hit[0]
+            break
+    if sass is None:
+        sys.exit(f"no .text section matching {sect} in {so}")
     off2line = {}
     cur = ("?", 0)
     for l in sass[start + 1:]:

@@ -19,9 +19,9 @@ LIB_PATH = os.environ.get("TSGPU_LIB_PATH") or os.path.join(HERE, "libtsgpu.so")
 
 EXPORTS = [
     "tsgpu_last_error", "tsgpu_device_count", "tsgpu_index_create", "tsgpu_index_destroy", "tsgpu_index_load_field",
-    "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy",
+    "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_index_build_hnsw", "tsgpu_index_hnsw_info", "tsgpu_index_export_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy",
     "tsgpu_intersect", "tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches", "tsgpu_ids_setop", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
-    "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats", "tsgpu_index_load_art", "tsgpu_art_walk_batch",
+    "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats", "tsgpu_debug_knn_work", "tsgpu_index_load_art", "tsgpu_art_walk_batch",
 ]
 
 
@@ -46,6 +46,9 @@ def lib():
         L.tsgpu_index_load_field.argtypes = [vp, C.POINTER(FieldStruct), u32p]
         L.tsgpu_index_load_sort_column.argtypes = [vp, C.c_void_p, u32p]
         L.tsgpu_index_load_hnsw.argtypes = [vp, C.POINTER(HnswStruct)]
+        L.tsgpu_index_build_hnsw.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.tsgpu_index_hnsw_info.argtypes = [vp, u32p, u32p, u32p, u32p, u32p, u64p, u64p]
+        L.tsgpu_index_export_hnsw.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.tsgpu_filter_create.argtypes = [vp, C.c_void_p, C.c_size_t, i32p]
         L.tsgpu_filter_destroy.argtypes = [vp, C.c_int32]
         L.tsgpu_intersect.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -61,6 +64,7 @@ def lib():
             getattr(L, n).argtypes = [vp, C.POINTER(KwBatchStruct), C.c_void_p, C.POINTER(VecParamsStruct), C.c_void_p,
                                       C.c_uint32, C.c_void_p, C.c_void_p]
         L.tsgpu_get_stats.argtypes = [vp, C.POINTER(StatsStruct)]
+        L.tsgpu_debug_knn_work.argtypes = [vp, C.c_void_p, C.c_uint32, u32p]
         L.tsgpu_index_load_art.argtypes = [vp, C.c_uint32, C.POINTER(ArtStruct)]
         L.tsgpu_art_walk_batch.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                            u32p, C.c_void_p]
@@ -147,6 +151,38 @@ class GpuIndex:
         s.upper_off = C.cast(_addr(upper_off), u64p)
         s.links_up = C.cast(_addr(links_up), u32p)
         _ck(self.L.tsgpu_index_load_hnsw(self.h, C.byref(s)))
+
+    def build_hnsw(self, vectors, M=16, ef_construction=200, seed=100, metric=0, max_batch=4096, keep_device_vectors=False) -> dict:
+        """tsgpu_index_build_hnsw: hnswlib's addPoint as batched rounds on the device. `vectors`: numpy [n, dim] f32 or a CUDA
+        tensor. Returns the graph's shape and the build counters."""
+        if isinstance(vectors, np.ndarray):
+            vectors = np.ascontiguousarray(vectors, np.float32)
+        n, dim = int(vectors.shape[0]), int(vectors.shape[1])
+        _ck(self.L.tsgpu_index_build_hnsw(self.h, _addr(vectors), n, dim, M, ef_construction, seed, metric, max_batch, 1 if keep_device_vectors else 0))
+        if keep_device_vectors:
+            self._keep_vectors = vectors
+        return self.hnsw_info()
+
+    def hnsw_info(self) -> dict:
+        v = [C.c_uint32(0) for _ in range(5)]
+        nup = C.c_uint64(0)
+        bc = (C.c_uint64 * 5)()
+        _ck(self.L.tsgpu_index_hnsw_info(self.h, *[C.byref(x) for x in v], C.byref(nup), bc))
+        return {"n": v[0].value, "dim": v[1].value, "M": v[2].value, "max_level": v[3].value, "entry_point": v[4].value, "n_upper": nup.value,
+                "build": {"search_dist": bc[0], "expanded": bc[1], "heuristic_dist": bc[2], "rows_reselected": bc[3], "rounds": bc[4]}}
+
+    def export_hnsw(self, vectors: np.ndarray, metric: int = 0) -> HnswGraph:
+        """The device graph as host arrays (the form the oracle walks)."""
+        i = self.hnsw_info()
+        n, M = i["n"], i["M"]
+        levels = np.zeros(max(n, 1), np.uint8)[:n]
+        links0 = np.zeros(n * (2 * M + 1), np.uint32)
+        upper_off = np.zeros(n + 1, np.uint64)
+        links_up = np.zeros(max(i["n_upper"] * (M + 1), 1), np.uint32)
+        _ck(self.L.tsgpu_index_export_hnsw(self.h, levels.ctypes.data if n else None, links0.ctypes.data if n else None, upper_off.ctypes.data,
+                                           links_up.ctypes.data))
+        return HnswGraph(np.ascontiguousarray(vectors, np.float32), levels, links0, upper_off, links_up[:i["n_upper"] * (M + 1)] if i["n_upper"] else links_up,
+                         M, i["max_level"], i["entry_point"], metric)
 
     def filter_create(self, ids) -> int:
         if isinstance(ids, np.ndarray):
@@ -285,6 +321,13 @@ class GpuIndex:
         out = np.zeros(max(len(ids), 1), np.float32)
         _ck(self.L.tsgpu_flat_distances(self.h, q.ctypes.data, ids.ctypes.data, len(ids), out.ctypes.data))
         return out[:len(ids)]
+
+    def knn_work(self, nq: int) -> np.ndarray:
+        """[(expanded nodes, distance evaluations)] of every graph walk of the last call (instrumentation)."""
+        out = np.zeros((nq, 2), np.uint32)
+        n = C.c_uint32(0)
+        _ck(self.L.tsgpu_debug_knn_work(self.h, out.ctypes.data, nq, C.byref(n)))
+        return out[:n.value]
 
     def stats(self) -> dict:
         s = StatsStruct()

@@ -13,7 +13,7 @@
 //     512-byte warp loads, two neighbours (2*d/128 LDG.128 per lane) in flight before the first FMA;
 //   - dot products use the fixed "W128" order (element e -> accumulator e mod 128 by FMA, 4->1 per lane, xor
 //     butterfly), the same order the oracle uses, so CPU and GPU take identical branches on the same graph;
-//   - visited set = one bit per node in a per-warp global bitmap (atomicOr), undone from a visit log afterwards;
+//   - visited set = a two-tier hash set: shared memory first, a per-slot HBM table for long walks (see vis_insert);
 //   - result heap (size ef) in shared memory, candidate heap in a per-warp global arena (L2-resident);
 //     both are binary heaps of u64 keys (order-preserving float bits << 32 | id) reproducing std::priority_queue<
 //     pair<float,id>> order exactly;
@@ -30,7 +30,9 @@ namespace tsv {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr int kKnnThreads = 128;            // 4 warps = 4 queries per CTA
-constexpr uint32_t kCandSmem = 512;         // candidate-heap entries kept in shared memory per warp (rest spills to HBM)
+constexpr uint32_t kCandSmem = 256;         // candidate-heap entries kept in shared memory per warp (rest spills to HBM)
+constexpr uint32_t kVisSmem = 2048;         // visited set, tier 1: open-addressing slots in shared memory per warp (power of two)
+constexpr uint32_t kVisSmemLimit = 1536;    // ... filled to 75 %, then tier 2 (a per-slot table in HBM) takes the new keys
 
 struct HnswDev {
     uint32_t n_nodes, dim, M, max_level, entry_point, metric;
@@ -49,19 +51,22 @@ struct KnnParams {
     const uint32_t* const* q_excl;            // [nq] or nullptr
     const uint32_t* q_n_excl;
     const uint8_t* q_skip;                    // [nq] 1 = query not run (e.g. goes to the flat path) or nullptr
+    const uint32_t* q_order;                  // [n_order] queries in hand-out order (longest walks first) or nullptr = 0..nq-1
+    uint32_t n_order;
+    const uint32_t* n_order_dev;              // when set, the number of tickets is read from device memory (retry launch)
     float* out_dist;               // [nq*k]
     uint32_t* out_labels;          // [nq*k]
     uint32_t* out_n;               // [nq]
     // per-warp-slot scratch
-    uint32_t* visited;             // [n_slots * vis_words]
-    uint32_t vis_words;
-    uint32_t* vis_log;             // [n_slots * log_cap]
-    uint32_t log_cap;
+    uint32_t* vis2;                // [n_slots * vis2_slots] tier 2 of the visited set, all-zero between queries
+    uint32_t vis2_slots;           // power of two
     unsigned long long* cand;      // [n_slots * cand_cap]
     uint32_t cand_cap;
     uint32_t* counter;             // query ticket
-    unsigned long long* stats;     // [0] n_dist, [1] n_expanded
-    int* error;                    // set to 1 on candidate-heap overflow
+    unsigned long long* stats;     // [0] n_dist, [1] n_expanded, [2] speculation hits, [3] walks that used tier 2
+    uint32_t* retry_n;             // walks that outgrew the per-slot scratch: re-run by the host with a full-size slot
+    uint32_t* retry_list;          // [nq]
+    uint32_t* q_work;              // [2*nq] expansions, distance evaluations of each walk (instrumentation; may be nullptr)
 };
 
 __device__ __forceinline__ uint32_t ord_f32(float f) {          // order-preserving float -> u32
@@ -205,6 +210,48 @@ __device__ __forceinline__ bool allowed(const HnswDev& g, const uint32_t* fbm, c
     return (__ldg(fbm + (label >> 5)) >> (label & 31)) & 1;
 }
 
+// ---- visited set (hnswlib's VisitedList) as a two-tier hash set. Round 1 kept one bit per node in a per-warp bitmap in
+// HBM: at 10 M nodes that is 1.25 MB per walk, 3.7 GB over the resident walks, so every test-and-set was a DRAM sector
+// read + write-back (6.7 GB of the 32.7 GB the kernel moved per launch, profiles/r01c) and a DRAM round trip on the
+// critical path of every expansion. A walk touches ~1.3 K nodes, so the set fits in shared memory: tier 1 is an
+// open-addressing table of kVisSmem keys per warp (shared-memory CAS, no HBM traffic at all); walks that outgrow it
+// (selective filters) continue in a per-slot table in HBM. Membership is exact, so the walk is unchanged.
+__device__ __forceinline__ uint32_t vis_hash(uint32_t x) { x *= 0x9E3779B1u; return x ^ (x >> 15); }
+
+// test-and-set of `node`; lanes of a warp call it together with distinct nodes. use2: tier 1 is frozen (read-only),
+// new keys go to tier 2. Returns true when the node was not in the set.
+__device__ __forceinline__ bool vis_insert(uint32_t* t1, uint32_t* t2, uint32_t mask2, uint32_t node, bool use2) {
+    const uint32_t key = node + 1;
+    const uint32_t h = vis_hash(node);
+    uint32_t i = h & (kVisSmem - 1);
+    if(!use2) {
+        for(;;) {
+            const uint32_t old = atomicCAS(t1 + i, 0u, key);
+            if(old == 0) return true;
+            if(old == key) return false;
+            i = (i + 1) & (kVisSmem - 1);
+        }
+    }
+    for(;;) { const uint32_t v = t1[i]; if(v == key) return false; if(v == 0) break; i = (i + 1) & (kVisSmem - 1); }
+    uint32_t j = (h >> 7) & mask2;
+    for(;;) {
+        const uint32_t old = atomicCAS(t2 + j, 0u, key);
+        if(old == 0) return true;
+        if(old == key) return false;
+        j = (j + 1) & mask2;
+    }
+}
+// read-only membership (speculation hints)
+__device__ __forceinline__ bool vis_contains(const uint32_t* t1, const uint32_t* t2, uint32_t mask2, uint32_t node, bool t2_used) {
+    const uint32_t key = node + 1;
+    const uint32_t h = vis_hash(node);
+    uint32_t i = h & (kVisSmem - 1);
+    for(;;) { const uint32_t v = t1[i]; if(v == key) return true; if(v == 0) break; i = (i + 1) & (kVisSmem - 1); }
+    if(!t2_used) return false;
+    uint32_t j = (h >> 7) & mask2;
+    for(;;) { const uint32_t v = __ldcg(t2 + j); if(v == key) return true; if(v == 0) return false; j = (j + 1) & mask2; }
+}
+
 // One query per warp. Measured on the 10 M x 768 workload: 96 registers / 5 CTAs per SM walks 4096 queries in 10.7 ms,
 // the 72-register build (7 CTAs per SM, a warp for every query) needs 12.4 ms — the extra residency does not pay for the
 // serialised loads the tighter register budget forces, because the batch time is set by the slowest walks.
@@ -220,23 +267,27 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
     const uint32_t ef = P.ef > P.k ? P.ef : P.k;           // Typesense fork: effective ef = max(ef, k)
     const uint32_t dim = g.dim;
     const uint32_t dim_pad = (dim + 3) & ~3u;
-    // shared: per warp [ef+1] u64 result heap, then (generic path) the query vector
-    // shared per warp: [ef+1] u64 result heap + [kCandSmem] u64 first tier of the candidate heap; then (generic path) q
-    const size_t per_warp = (size_t) (ef + 1) + kCandSmem;
+    // shared per warp: [ef+1] u64 result heap + [kCandSmem] u64 first tier of the candidate heap + [kVisSmem] u32 visited
+    // tier 1; then (generic path) the query vectors
+    const size_t per_warp = (size_t) (ef + 1) + kCandSmem + kVisSmem / 2;          // in u64 units
     unsigned long long* res = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t) warp * per_warp;
     unsigned long long* cand_s = res + (ef + 1);
+    uint32_t* vis1 = reinterpret_cast<uint32_t*>(cand_s + kCandSmem);
     float* qs = reinterpret_cast<float*>(reinterpret_cast<unsigned long long*>(smem_raw) + (size_t) (kKnnThreads / 32) * per_warp) + (size_t) warp * dim_pad;
-    uint32_t* vis = P.visited + (size_t) slot * P.vis_words;
-    uint32_t* vlog = P.vis_log + (size_t) slot * P.log_cap;
+    uint32_t* vis2 = P.vis2 + (size_t) slot * P.vis2_slots;
+    const uint32_t mask2 = P.vis2_slots - 1;
+    const uint32_t limit2 = P.vis2_slots - (P.vis2_slots >> 2);
     unsigned long long* cand = P.cand + (size_t) slot * P.cand_cap;
     const uint32_t L0 = 2 * g.M + 1, LU = g.M + 1;
-    unsigned long long n_dist_acc = 0, n_exp_acc = 0, n_hit_acc = 0;
+    const uint32_t n_tickets = P.n_order_dev ? __ldcg(P.n_order_dev) : (P.q_order ? P.n_order : P.nq);
+    unsigned long long n_dist_acc = 0, n_exp_acc = 0, n_hit_acc = 0, n_t2_acc = 0;
 
     for(;;) {
         uint32_t qi = 0;
         if(lane == 0) qi = atomicAdd(P.counter, 1u);
         qi = __shfl_sync(0xffffffffu, qi, 0);
-        if(qi >= P.nq) break;
+        if(qi >= n_tickets) break;
+        if(P.q_order) qi = __ldg(P.q_order + qi);
         if(P.q_skip && P.q_skip[qi]) { if(lane == 0) P.out_n[qi] = 0; continue; }
         const float* qv = P.queries + (size_t) qi * dim;
         QReg<NCH> q;
@@ -251,6 +302,7 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
         const uint32_t* excl = P.q_excl ? P.q_excl[qi] : nullptr;
         const uint32_t n_excl = P.q_n_excl ? P.q_n_excl[qi] : 0;
         if(g.n_nodes == 0 || g.entry_point == kNone) { if(lane == 0) P.out_n[qi] = 0; continue; }
+        for(uint32_t i = lane; i < kVisSmem; i += 32) vis1[i] = 0;
 
         // ---- greedy descent through the upper layers (searchKnn)
         uint32_t cur = g.entry_point;
@@ -277,9 +329,12 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
         }
 
         // ---- best-first search of the base layer (searchBaseLayerST, non-"bare bone" branch)
-        uint32_t n_res = 0, n_cand = 0, n_cs = 0, n_cg = 0, n_log = 0;     // n_cand = n_cs (shared tier) + n_cg (HBM tier)
-        bool log_overflow = false;
+        uint32_t n_res = 0, n_cand = 0, n_cs = 0, n_cg = 0;     // n_cand = n_cs (shared tier) + n_cg (HBM tier)
+        const unsigned long long exp0 = n_exp_acc, dist0 = n_dist_acc;
+        uint32_t n_v1 = 0, n_v2 = 0;                             // visited keys per tier (warp-uniform)
+        bool overflow = false;                                   // the walk outgrew this slot's scratch (warp-uniform)
         float lowerBound;
+        __syncwarp();
         {
             const bool ok = allowed(g, fbm, excl, n_excl, cur);
             if(ok) {
@@ -291,15 +346,15 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
                 lowerBound = FLT_MAX;
                 if(lane == 0) heap_push_min(cand_s, n_cs, cand_key(FLT_MAX, cur));
             }
-            if(lane == 0) { atomicOr(vis + (cur >> 5), 1u << (cur & 31)); vlog[0] = cur; }
-            n_log = 1;
+            if(lane == 0) vis_insert(vis1, vis2, mask2, cur, false);
+            n_v1 = 1;
             n_res = __shfl_sync(0xffffffffu, n_res, 0);
             n_cand = 1;
             __syncwarp();
         }
         uint32_t prev_spec = kNone, prev_nb2 = kNone, prev_size2 = 0;
         for(;;) {
-            if(n_cand == 0) break;
+            if(n_cand == 0 || overflow) break;
             // global minimum = the smaller of the two tiers' tops
             unsigned long long top = 0;
             int from_g = 0;
@@ -322,9 +377,9 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
             const uint32_t size = reuse ? prev_size2 : __ldg(rec);
             const uint32_t nb_first = reuse ? prev_nb2 : ((lane + 1 < L0) ? __ldg(rec + 1 + lane) : kNone);
             // Speculation (hints only, no effect on results): the new top of the shared-memory tier is the most likely next
-            // expansion. Its link row rides along with this node's, its visited words with this node's atomics, and the
-            // vectors of its unvisited neighbours are started towards L2 before this node's distances are computed — so
-            // the next expansion finds links, visited words and vectors in L2 instead of paying three DRAM round trips.
+            // expansion. Its link row rides along with this node's, and the vectors of its unvisited neighbours are started
+            // towards L2 before this node's distances are computed — so the next expansion finds links and vectors in L2
+            // instead of paying two DRAM round trips.
             uint32_t spec = kNone, nb2 = kNone, size2 = 0;
             if(lane == 0 && n_cs) spec = ~(uint32_t) cand_s[0];
             spec = __shfl_sync(0xffffffffu, spec, 0);
@@ -339,25 +394,16 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
             for(uint32_t base = 0; base < size; base += 32) {
                 const uint32_t j = base + lane;
                 nb = (j < size) ? (base == 0 ? nb_first : __ldg(rec + 1 + j)) : kNone;
-                fresh = false;
-                if(nb != kNone) {
-                    const uint32_t old = atomicOr(vis + (nb >> 5), 1u << (nb & 31));
-                    fresh = !((old >> (nb & 31)) & 1);
-                }
-                uint32_t w2 = 0xFFFFFFFFu;
-                if(base == 0 && lane < size2 && nb2 < g.n_nodes) w2 = __ldcg(vis + (nb2 >> 5)) >> (nb2 & 31);
+                const bool use2 = n_v1 + 32 > kVisSmemLimit;          // warp-uniform: tier 1 frozen once it may pass 75 %
+                if(use2 && n_v2 + 32 > limit2) { overflow = true; break; }
+                fresh = (nb != kNone) && vis_insert(vis1, vis2, mask2, nb, use2);
                 uint32_t mask = __ballot_sync(0xffffffffu, fresh);
-                if(!(w2 & 1u)) {
+                if(use2) n_v2 += __popc(mask); else n_v1 += __popc(mask);
+                __syncwarp();
+                if(base == 0 && lane < size2 && nb2 < g.n_nodes && !vis_contains(vis1, vis2, mask2, nb2, n_v2 != 0)) {
                     const char* vp = reinterpret_cast<const char*>(g.vectors + (size_t) nb2 * dim);
                     for(uint32_t o = 0; o < dim * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(vp + o));
                 }
-                // visit log for the bitmap undo
-                if(fresh) {
-                    const uint32_t pos = n_log + __popc(mask & ((1u << lane) - 1u));
-                    if(pos < P.log_cap) vlog[pos] = nb;
-                }
-                n_log += __popc(mask);
-                if(n_log > P.log_cap) log_overflow = true;
                 // every fresh neighbour's vector will be read below, two at a time: start all of them towards L2 now so only
                 // the first pair pays the full DRAM (and page-walk) latency
                 if(fresh && __popc(mask) > 2) {
@@ -378,6 +424,7 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
                     d0 = 1.0f - d0; d1 = 1.0f - d1;
                     n_dist_acc += j1 >= 0 ? 2 : 1;
                     // admission replayed in neighbour order (lane 0 owns the heaps)
+                    uint32_t ovf = 0;
                     if(lane == 0) {
 #pragma unroll
                         for(int t = 0; t < 2; t++) {
@@ -393,7 +440,7 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
                                 }
                                 if(n_cs < kCandSmem) heap_push_min(cand_s, n_cs, cand_key(d, c));
                                 else if(n_cg < P.cand_cap) heap_push_min(cand, n_cg, cand_key(d, c));
-                                else *P.error = 1;
+                                else ovf = 1;
                                 if(ok) {       // push, then pop while over ef (hnswlib) == replace the maximum when already full
                                     if(n_res < ef) heap_push_max(res, n_res, res_key(d, c));
                                     else heap_replace_max(res, n_res, res_key(d, c));
@@ -405,14 +452,20 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
                     lowerBound = __shfl_sync(0xffffffffu, lowerBound, 0);
                     n_res = __shfl_sync(0xffffffffu, n_res, 0);
                     n_cand = __shfl_sync(0xffffffffu, n_cs + n_cg, 0);
+                    if(__shfl_sync(0xffffffffu, ovf, 0)) { overflow = true; break; }
                 }
+                if(overflow) break;
             }
             prev_spec = spec; prev_nb2 = nb2; prev_size2 = size2;
             __syncwarp();
         }
 
-        // ---- emit: keep the k closest, closest first (searchKnnCloserFirst)
-        if(lane == 0) {
+        if(overflow) {
+            // hand the query back: the host re-runs it alone with a slot sized for the whole graph (the other queries of the
+            // batch are unaffected)
+            if(lane == 0) { const uint32_t r = atomicAdd(P.retry_n, 1u); P.retry_list[r] = qi; P.out_n[qi] = 0; }
+        } else if(lane == 0) {
+            // ---- emit: keep the k closest, closest first (searchKnnCloserFirst)
             while(n_res > P.k) heap_pop_max(res, n_res);
             const uint32_t n = n_res;
             P.out_n[qi] = n;
@@ -424,16 +477,335 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
                 P.out_labels[(size_t) qi * P.k + i] = g.labels ? g.labels[node] : node;
             }
         }
+        if(lane == 0 && P.q_work) { P.q_work[2 * qi] = (uint32_t) (n_exp_acc - exp0); P.q_work[2 * qi + 1] = (uint32_t) (n_dist_acc - dist0); }
         __syncwarp();
-        // ---- undo the visited bits
-        if(!log_overflow) {
-            for(uint32_t i = lane; i < n_log; i += 32) { const uint32_t nd = vlog[i]; vis[nd >> 5] = 0; }
-        } else {
-            for(uint32_t i = lane; i < P.vis_words; i += 32) vis[i] = 0;
+        // ---- tier 2 goes back to all-zero for the slot's next walk
+        if(n_v2) {
+            n_t2_acc++;
+            uint4* z = reinterpret_cast<uint4*>(vis2);
+            for(uint32_t i = lane; i < (P.vis2_slots >> 2); i += 32) z[i] = make_uint4(0, 0, 0, 0);
         }
         __syncwarp();
     }
-    if(lane == 0) { atomicAdd(P.stats + 0, n_dist_acc); atomicAdd(P.stats + 1, n_exp_acc); atomicAdd(P.stats + 2, n_hit_acc); }
+    if(lane == 0) { atomicAdd(P.stats + 0, n_dist_acc); atomicAdd(P.stats + 1, n_exp_acc); atomicAdd(P.stats + 2, n_hit_acc); atomicAdd(P.stats + 3, n_t2_acc); }
+}
+
+// ===============================================================================================================
+// hnsw_walk_kernel — the same search with its two priority queues held ACROSS THE WARP'S REGISTERS instead of as binary
+// heaps that one lane maintains in shared / global memory. Why: profiles/r02b showed the heap kernel executing ~1150 warp
+// instructions per expanded node, most of them single-lane heap sifts (dependent shared-memory chains; dependent
+// GLOBAL-memory chains once a filtered walk's candidate set has outgrown its shared tier), at ~10 cycles each with 5 warps
+// per scheduler — and the batch time is the latency of the longest walks (2048 filtered walks of ~1000 expansions on 2960
+// warp slots: no second wave to hide behind), so instructions on one walk's critical path are what the kernel time is made of.
+//   result set R   the ef (<= 128) closest allowed nodes as ONE sorted array, element e in lane e / 4, register e % 4
+//                  (keys ord(dist) << 32 | id, ascending): admission is a warp-wide compare + shift (~25 instructions, no
+//                  memory), lowerBound is a shuffle
+//   candidates C   the 64 smallest candidate keys sorted the same way (2 per lane) + an UNSORTED pool in HBM for the rest.
+//                  Invariant: every pool key >= every buffered key, so the buffer's front is the global minimum. A key below
+//                  the buffer's last goes into the buffer (the evicted last goes to the pool, one store); others are
+//                  appended to the pool. Only when the buffer runs empty is the pool read: its 64 smallest are selected by
+//                  one streaming pass (swap-insert) — every ~64 expansions at most, so no global load sits on an
+//                  expansion's critical path.
+// Pop order, admission order and every comparison are those of hnswlib's two std::priority_queues, so results are unchanged
+// (same GPU parity tests). Used when max(ef, k) <= 128 and 2M <= 32 (Typesense defaults: ef 10..100s, M 16); the heap kernel
+// above stays as the general path.
+constexpr unsigned long long kKeyInf = ~0ull;
+
+template <int S> struct WArr { unsigned long long a[S]; };
+
+template <int S>
+__device__ __forceinline__ void warr_clear(WArr<S>& w) {
+#pragma unroll
+    for(int i = 0; i < S; i++) w.a[i] = kKeyInf;
+}
+// insert k (unique, < +inf) keeping ascending order; returns what fell off the end (+inf while the array is not full)
+template <int S>
+__device__ __forceinline__ unsigned long long warr_insert(WArr<S>& w, unsigned long long k, uint32_t lane) {
+    const unsigned long long last = w.a[S - 1];
+    unsigned long long x = __shfl_up_sync(0xffffffffu, last, 1);          // the element just before my block
+    if(lane == 0) x = 0;
+    const unsigned long long evicted = __shfl_sync(0xffffffffu, last, 31);
+    if(k < last) {                                                        // my block changes
+        if(k < x) {                                                       // k landed in an earlier lane: shift right, x comes in
+#pragma unroll
+            for(int i = S - 1; i > 0; i--) w.a[i] = w.a[i - 1];
+            w.a[0] = x;
+        } else {                                                          // k lands here, my last falls to the next lane
+            unsigned long long carry = k;
+#pragma unroll
+            for(int i = 0; i < S; i++) { const unsigned long long t = w.a[i]; const bool sw = carry < t; w.a[i] = sw ? carry : t; carry = sw ? t : carry; }
+        }
+    }
+    return evicted;
+}
+template <int S>
+__device__ __forceinline__ unsigned long long warr_front(const WArr<S>& w) { return __shfl_sync(0xffffffffu, w.a[0], 0); }
+template <int S>
+__device__ __forceinline__ void warr_pop_front(WArr<S>& w, uint32_t lane) {
+    unsigned long long nx = __shfl_down_sync(0xffffffffu, w.a[0], 1);
+    if(lane == 31) nx = kKeyInf;
+#pragma unroll
+    for(int i = 0; i < S - 1; i++) w.a[i] = w.a[i + 1];
+    w.a[S - 1] = nx;
+}
+template <int S>
+__device__ __forceinline__ unsigned long long warr_get(const WArr<S>& w, uint32_t e) {       // e warp-uniform
+    unsigned long long v = w.a[0];
+#pragma unroll
+    for(int i = 1; i < S; i++) if((e % S) == (uint32_t) i) v = w.a[i];
+    return __shfl_sync(0xffffffffu, v, e / S);
+}
+template <int S>
+__device__ __forceinline__ void warr_set_inf(WArr<S>& w, uint32_t e, uint32_t lane) {
+    if(lane == e / S) {
+#pragma unroll
+        for(int i = 0; i < S; i++) if((e % S) == (uint32_t) i) w.a[i] = kKeyInf;
+    }
+}
+
+constexpr int kResPerLane = 4;           // R: 128 entries
+constexpr int kBufPerLane = 2;           // C buffer: 64 entries
+constexpr uint32_t kBufCap = 32 * kBufPerLane;
+
+#ifndef TSGPU_WALK_MIN_CTAS
+#define TSGPU_WALK_MIN_CTAS 4
+#endif
+template <int NCH>
+__global__ void __launch_bounds__(kKnnThreads, TSGPU_WALK_MIN_CTAS)
+hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t slot = blockIdx.x * (kKnnThreads / 32) + warp;
+    const uint32_t ef = P.ef > P.k ? P.ef : P.k;           // <= 128 (host checks)
+    const uint32_t dim = g.dim;
+    const uint32_t dim_pad = (dim + 3) & ~3u;
+    // shared per warp: [kVisSmem] u32 visited tier 1; then (generic path) the query vectors
+    uint32_t* vis1 = reinterpret_cast<uint32_t*>(smem_raw) + (size_t) warp * kVisSmem;
+    float* qs = reinterpret_cast<float*>(reinterpret_cast<uint32_t*>(smem_raw) + (size_t) (kKnnThreads / 32) * kVisSmem) + (size_t) warp * dim_pad;
+    uint32_t* vis2 = P.vis2 + (size_t) slot * P.vis2_slots;
+    const uint32_t mask2 = P.vis2_slots - 1;
+    const uint32_t limit2 = P.vis2_slots - (P.vis2_slots >> 2);
+    unsigned long long* pool = P.cand + (size_t) slot * P.cand_cap;
+    const uint32_t L0 = 2 * g.M + 1, LU = g.M + 1;
+    const uint32_t n_tickets = P.n_order_dev ? __ldcg(P.n_order_dev) : (P.q_order ? P.n_order : P.nq);
+    unsigned long long n_dist_acc = 0, n_exp_acc = 0, n_hit_acc = 0, n_t2_acc = 0;
+
+    for(;;) {
+        uint32_t qi = 0;
+        if(lane == 0) qi = atomicAdd(P.counter, 1u);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if(qi >= n_tickets) break;
+        if(P.q_order) qi = __ldg(P.q_order + qi);
+        if(P.q_skip && P.q_skip[qi]) { if(lane == 0) P.out_n[qi] = 0; continue; }
+        const float* qv = P.queries + (size_t) qi * dim;
+        QReg<NCH> q;
+        if(NCH > 0) {
+#pragma unroll
+            for(int s = 0; s < NCH; s++) q.v[s] = __ldg(reinterpret_cast<const float4*>(qv + s * 128) + lane);
+        } else {
+            for(uint32_t e = lane; e < dim; e += 32) qs[e] = qv[e];
+            __syncwarp();
+        }
+        const uint32_t* fbm = P.q_filter_bitmap ? P.q_filter_bitmap[qi] : nullptr;
+        const uint32_t* excl = P.q_excl ? P.q_excl[qi] : nullptr;
+        const uint32_t n_excl = P.q_n_excl ? P.q_n_excl[qi] : 0;
+        if(g.n_nodes == 0 || g.entry_point == kNone) { if(lane == 0) P.out_n[qi] = 0; continue; }
+        for(uint32_t i = lane; i < kVisSmem; i += 32) vis1[i] = 0;
+        const unsigned long long exp0 = n_exp_acc, dist0 = n_dist_acc;
+
+        // ---- greedy descent through the upper layers (searchKnn)
+        uint32_t cur = g.entry_point;
+        float curdist = 1.0f - dot_one<NCH>(q, qs, g.vectors + (size_t) cur * dim, dim, lane);
+        n_dist_acc++;
+        for(int level = (int) g.max_level; level > 0; level--) {
+            bool changed = true;
+            while(changed) {
+                changed = false;
+                const uint32_t* rec = g.links_up + (g.upper_off[cur] + (unsigned long long) (level - 1)) * LU;
+                const uint32_t size = __ldg(rec);
+                const uint32_t nb = (lane < size) ? __ldg(rec + 1 + lane) : kNone;     // M <= 32
+                for(uint32_t i = 0; i < size; i += 2) {
+                    const uint32_t c0 = __shfl_sync(0xffffffffu, nb, i);
+                    const uint32_t c1 = (i + 1 < size) ? __shfl_sync(0xffffffffu, nb, i + 1) : c0;
+                    float d0, d1;
+                    dot_two<NCH>(q, qs, g.vectors + (size_t) c0 * dim, g.vectors + (size_t) c1 * dim, dim, lane, d0, d1);
+                    d0 = 1.0f - d0; d1 = 1.0f - d1;
+                    n_dist_acc += (i + 1 < size) ? 2 : 1;
+                    if(d0 < curdist) { curdist = d0; cur = c0; changed = true; }
+                    if(i + 1 < size && d1 < curdist) { curdist = d1; cur = c1; changed = true; }
+                }
+            }
+        }
+
+        // ---- best-first search of the base layer (searchBaseLayerST, non-"bare bone" branch)
+        WArr<kResPerLane> R; warr_clear(R);
+        WArr<kBufPerLane> B; warr_clear(B);
+        uint32_t n_res = 0, n_b = 0, n_p = 0;                   // result count, buffered / pooled candidates (warp-uniform)
+        uint32_t n_v1 = 0, n_v2 = 0;
+        bool overflow = false;
+        float lowerBound;
+        __syncwarp();
+        {
+            const bool ok = allowed(g, fbm, excl, n_excl, cur);
+            if(ok) {
+                const float d = curdist;      // same value hnswlib recomputes for the entry point
+                n_dist_acc++;
+                lowerBound = d;
+                warr_insert(R, res_key(d, cur), lane); n_res = 1;
+                warr_insert(B, cand_key(d, cur), lane); n_b = 1;
+            } else {
+                lowerBound = FLT_MAX;
+                warr_insert(B, cand_key(FLT_MAX, cur), lane); n_b = 1;
+            }
+            if(lane == 0) vis_insert(vis1, vis2, mask2, cur, false);
+            n_v1 = 1;
+            __syncwarp();
+        }
+        uint32_t prev_spec = kNone, prev_nb2 = kNone, prev_size2 = 0;
+        for(;;) {
+            if(overflow) break;
+            if(n_b == 0) {
+                if(n_p == 0) break;
+                // ---- refill: the kBufCap smallest pool keys move to the buffer. The pool's tail seeds the buffer, then one
+                // streaming pass swaps every key below the buffer's last with that last (so the pool keeps its size minus the
+                // seed and never holds gaps).
+                const uint32_t seed = n_p < kBufCap ? n_p : kBufCap;
+                n_p -= seed;
+                for(uint32_t i = 0; i < seed; i += 32) {
+                    const unsigned long long k = (i + lane < seed) ? pool[n_p + i + lane] : kKeyInf;
+                    uint32_t m = __ballot_sync(0xffffffffu, k != kKeyInf);
+                    while(m) { const int src = __ffs(m) - 1; m &= m - 1; warr_insert(B, __shfl_sync(0xffffffffu, k, src), lane); }
+                }
+                n_b = seed;
+                if(seed == kBufCap) {
+                    for(uint32_t i = 0; i < n_p; i += 32) {
+                        unsigned long long k = (i + lane < n_p) ? pool[i + lane] : kKeyInf;
+                        unsigned long long bl = __shfl_sync(0xffffffffu, B.a[kBufPerLane - 1], 31);
+                        uint32_t m = __ballot_sync(0xffffffffu, k < bl);
+                        bool mine = false;
+                        while(m) {
+                            const int src = __ffs(m) - 1; m &= m - 1;
+                            const unsigned long long ks = __shfl_sync(0xffffffffu, k, src);
+                            bl = __shfl_sync(0xffffffffu, B.a[kBufPerLane - 1], 31);
+                            if(ks < bl) {                                   // still below the (shrinking) last
+                                const unsigned long long ev = warr_insert(B, ks, lane);
+                                if((int) lane == src) { k = ev; mine = true; }
+                            }
+                        }
+                        if(mine) pool[i + lane] = k;
+                    }
+                }
+                __syncwarp();
+            }
+            const unsigned long long top = warr_front(B);
+            const float cdist = unord_f32((uint32_t) (top >> 32));
+            if(cdist > lowerBound && n_res == ef) break;
+            const uint32_t cnode = ~(uint32_t) top;
+            warr_pop_front(B, lane); n_b--;
+            n_exp_acc++;
+
+            const uint32_t* rec = g.links0 + (size_t) cnode * L0;
+            // a right guess already holds this node's link row in registers
+            const bool reuse = cnode == prev_spec;
+            n_hit_acc += reuse ? 1 : 0;
+            const uint32_t size = reuse ? prev_size2 : __ldg(rec);
+            const uint32_t nb = reuse ? prev_nb2 : ((lane + 1 < L0) ? __ldg(rec + 1 + lane) : kNone);
+            // Speculation (hints only): the buffer's new front is the most likely next expansion — fetch its link row now
+            // and start the vectors of its unvisited neighbours towards L2.
+            uint32_t spec = kNone, nb2 = kNone, size2 = 0;
+            if(n_b) spec = ~(uint32_t) warr_front(B);
+            if(spec != kNone) {
+                const uint32_t* rec2 = g.links0 + (size_t) spec * L0;
+                size2 = __ldg(rec2);
+                nb2 = (lane + 1 < L0) ? __ldg(rec2 + 1 + lane) : kNone;
+            }
+            const bool use2 = n_v1 + 32 > kVisSmemLimit;          // warp-uniform: tier 1 frozen once it may pass 75 %
+            if(use2 && n_v2 + 32 > limit2) { overflow = true; break; }
+            const bool fresh = (lane < size) && vis_insert(vis1, vis2, mask2, nb, use2);
+            uint32_t mask = __ballot_sync(0xffffffffu, fresh);
+            if(use2) n_v2 += __popc(mask); else n_v1 += __popc(mask);
+            // the filter functor of every fresh neighbour at once (one bitmap word per lane), ahead of the vector loads
+            const bool ok_mine = fresh && allowed(g, fbm, excl, n_excl, nb);
+            const uint32_t ok_mask = __ballot_sync(0xffffffffu, ok_mine);
+            if(fresh && __popc(mask) > 2) {
+                const char* vp = reinterpret_cast<const char*>(g.vectors + (size_t) nb * dim);
+                for(uint32_t o = 0; o < dim * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(vp + o));
+            }
+            if(lane < size2 && nb2 < g.n_nodes && !vis_contains(vis1, vis2, mask2, nb2, n_v2 != 0)) {
+                const char* vp = reinterpret_cast<const char*>(g.vectors + (size_t) nb2 * dim);
+                for(uint32_t o = 0; o < dim * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(vp + o));
+            }
+            while(mask) {
+                const int j0 = __ffs(mask) - 1; mask &= mask - 1;
+                int j1 = -1;
+                if(mask) { j1 = __ffs(mask) - 1; mask &= mask - 1; }
+                const uint32_t c0 = __shfl_sync(0xffffffffu, nb, j0);
+                const uint32_t c1 = j1 >= 0 ? __shfl_sync(0xffffffffu, nb, j1) : c0;
+                float d0, d1;
+                dot_two<NCH>(q, qs, g.vectors + (size_t) c0 * dim, g.vectors + (size_t) c1 * dim, dim, lane, d0, d1);
+                d0 = 1.0f - d0; d1 = 1.0f - d1;
+                n_dist_acc += j1 >= 0 ? 2 : 1;
+                // admission in neighbour order (every value below is warp-uniform)
+#pragma unroll
+                for(int t = 0; t < 2; t++) {
+                    if(t == 1 && j1 < 0) break;
+                    const float d = t ? d1 : d0;
+                    const uint32_t c = t ? c1 : c0;
+                    const bool ok = (ok_mask >> (t ? j1 : j0)) & 1;
+                    if(n_res < ef || lowerBound > d) {
+                        if(lane == 0) {   // the link row of a pushed candidate will be needed when it is expanded: start pulling it into L2
+                            const char* lp = reinterpret_cast<const char*>(g.links0 + (size_t) c * L0);
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(lp));
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(lp + 128));
+                        }
+                        const unsigned long long ck = cand_key(d, c);
+                        // buffer unless a pooled key might be smaller: below the buffer's last, or nothing pooled and room left
+                        const unsigned long long bl = n_b ? warr_get(B, n_b - 1) : 0ull;
+                        if((n_p == 0 && n_b < kBufCap) || ck < bl) {
+                            const unsigned long long ev = warr_insert(B, ck, lane);
+                            if(n_b < kBufCap) n_b++;
+                            else { if(n_p < P.cand_cap) { if(lane == 0) pool[n_p] = ev; n_p++; } else overflow = true; }
+                        } else { if(n_p < P.cand_cap) { if(lane == 0) pool[n_p] = ck; n_p++; } else overflow = true; }
+                        if(ok) {       // push, then pop while over ef (hnswlib) == the insert drops the last when already full
+                            warr_insert(R, res_key(d, c), lane);
+                            if(n_res < ef) n_res++; else warr_set_inf(R, ef, lane);
+                        }
+                        if(n_res) lowerBound = unord_f32((uint32_t) (warr_get(R, n_res - 1) >> 32));
+                    }
+                }
+                if(overflow) break;
+            }
+            prev_spec = spec; prev_nb2 = nb2; prev_size2 = size2;
+            __syncwarp();
+        }
+
+        if(overflow) {
+            if(lane == 0) { const uint32_t r = atomicAdd(P.retry_n, 1u); P.retry_list[r] = qi; P.out_n[qi] = 0; }
+        } else {
+            // ---- emit: the k closest, closest first (searchKnnCloserFirst): R is already in that order
+            const uint32_t n = n_res < P.k ? n_res : P.k;
+            if(lane == 0) P.out_n[qi] = n;
+#pragma unroll
+            for(int i = 0; i < kResPerLane; i++) {
+                const uint32_t e = lane * kResPerLane + i;
+                if(e < n) {
+                    const unsigned long long t = R.a[i];
+                    const uint32_t node = (uint32_t) t;
+                    P.out_dist[(size_t) qi * P.k + e] = unord_f32((uint32_t) (t >> 32));
+                    P.out_labels[(size_t) qi * P.k + e] = g.labels ? g.labels[node] : node;
+                }
+            }
+        }
+        if(lane == 0 && P.q_work) { P.q_work[2 * qi] = (uint32_t) (n_exp_acc - exp0); P.q_work[2 * qi + 1] = (uint32_t) (n_dist_acc - dist0); }
+        __syncwarp();
+        if(n_v2) {
+            n_t2_acc++;
+            uint4* z = reinterpret_cast<uint4*>(vis2);
+            for(uint32_t i = lane; i < (P.vis2_slots >> 2); i += 32) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+    }
+    if(lane == 0) { atomicAdd(P.stats + 0, n_dist_acc); atomicAdd(P.stats + 1, n_exp_acc); atomicAdd(P.stats + 2, n_hit_acc); atomicAdd(P.stats + 3, n_t2_acc); }
 }
 
 // process_results_bruteforce: one warp per (query, id)

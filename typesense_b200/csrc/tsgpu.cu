@@ -9,13 +9,16 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <cmath>
 #include <mutex>
+#include <random>
 #include <string>
 #include <vector>
 
 #include "../../include/tsgpu.h"
 #include "fuse_kernels.cuh"
 #include "knn_kernels.cuh"
+#include "hnsw_build.cuh"
 #include "postings_pack.h"
 
 using namespace tsk;
@@ -109,6 +112,8 @@ struct tsgpu_index {
     cudaStream_t vs = nullptr;           // stream the vector stage is issued on for the current call
     cudaEvent_t evA = nullptr, evB = nullptr;
     unsigned knn_blocks_per_sm = 7;
+    unsigned long long build_stats[4] = {0, 0, 0, 0}; size_t build_rounds = 0;   // counters of the last tsgpu_index_build_hnsw
+    uint32_t* knn_work_dev = nullptr; uint32_t knn_work_n = 0;   // per-walk counters of the last HNSW launch (tsgpu_debug_knn_work)
     unsigned char* knn_misc_dev = nullptr;    // counters of the last HNSW launch (read after the final sync)
     std::vector<unsigned char> knn_tables;   // host copies that must outlive the async uploads
     std::vector<uint8_t> tmp_is_flat; std::vector<unsigned long long> tmp_foff;
@@ -122,9 +127,9 @@ struct tsgpu_index {
     std::vector<Filter> filters;
     int n_sms = 148;
     // scratch
-    DevBuf d_stage, d_pool, d_small, d_bitmaps, d_found_bm, d_out, d_knn_vis, d_knn_log, d_knn_cand, d_knn_out, d_isect, d_kw_out;
+    DevBuf d_stage, d_pool, d_small, d_bitmaps, d_found_bm, d_out, d_knn_vis, d_knn_retry_vis, d_knn_retry_cand, d_knn_cand, d_knn_out, d_isect, d_kw_out;
     PinBuf h_stage;
-    size_t knn_slots = 0, knn_vis_words = 0;
+    size_t knn_slots = 0;
     bool found_dirty = false;            // d_found_bm is all-zero between calls unless a call died before its popcount pass
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     tsgpu_stats stats{};
@@ -564,40 +569,80 @@ void launch_hnsw(tsgpu_index* idx, const tsv::KnnParams& P, unsigned grid, size_
     tsv::hnsw_search_kernel<NCH><<<grid, tsv::kKnnThreads, smem, idx->vs>>>(idx->hnsw, P);
 }
 
-// d_queries: [nq*dim] on device. q_bitmap/q_excl/q_nexcl/q_skip: host vectors (uploaded here). Results in d_knn_out.
+template <int NCH>
+void launch_walk(tsgpu_index* idx, const tsv::KnnParams& P, unsigned grid, size_t smem) {
+    cudaFuncSetAttribute(tsv::hnsw_walk_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024));
+    tsv::hnsw_walk_kernel<NCH><<<grid, tsv::kKnnThreads, smem, idx->vs>>>(idx->hnsw, P);
+}
+
+// d_queries: [nq*dim] on device. q_bitmap/q_excl/q_nexcl/q_skip: host vectors (uploaded here). q_cost: optional per-query
+// walk-length estimate (larger = longer; queries are handed out longest first so the batch does not end on a few long walks
+// that started last). Results in d_knn_out.
 tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef,
                      const std::vector<const uint32_t*>& q_bitmap, const std::vector<const uint32_t*>& q_excl,
-                     const std::vector<uint32_t>& q_nexcl, const std::vector<uint8_t>& q_skip, KnnDeviceOut& out) {
+                     const std::vector<uint32_t>& q_nexcl, const std::vector<uint8_t>& q_skip, const std::vector<float>& q_cost,
+                     KnnDeviceOut& out) {
     cudaStream_t st = idx->vs;
     if(!idx->has_hnsw) return fail(TSGPU_ERR_INVALID, "no vector index loaded");
     if(k == 0) return fail(TSGPU_ERR_INVALID, "k must be > 0");
     const uint32_t efe = std::max(ef, k);
     if(efe > 4096) return fail(TSGPU_ERR_CAPACITY, "max(ef,k) must be <= 4096");
     const tsv::HnswDev& g = idx->hnsw;
-    // persistent warps: 4 per CTA
-    const unsigned max_blocks = (unsigned) idx->n_sms * idx->knn_blocks_per_sm;   // 7 = register-limited residency (72 regs x 128 threads)
+    // persistent warps: 4 per CTA; residency is bounded by shared memory (result heap + candidate tier + visited tier 1)
+    // register-resident queues (hnsw_walk_kernel) when they fit: max(ef,k) <= 128 and a link row per warp; TSGPU_KNN_HEAP=1
+    // forces the general heap kernel (A/B runs)
+    static const bool force_heap = getenv("TSGPU_KNN_HEAP") && atoi(getenv("TSGPU_KNN_HEAP")) == 1;
+    const bool walk = !force_heap && efe <= 32 * tsv::kResPerLane && 2 * g.M <= 32;
+    const size_t per_warp_smem = walk ? (size_t) tsv::kVisSmem * 4 : ((size_t) efe + 1 + tsv::kCandSmem) * 8 + (size_t) tsv::kVisSmem * 4;
+    const uint32_t dim = g.dim;
+    const int nch = (dim % 128 == 0 && dim / 128 <= 8 && dim / 128 != 5 && dim / 128 != 7) ? (int) (dim / 128) : 0;
+    const size_t q_bytes = nch ? 0 : (size_t) 4 * ((dim + 3) & ~3u) * 4;
+    const size_t smem = 4 * per_warp_smem + q_bytes;
+    if(smem > 200 * 1024) return fail(TSGPU_ERR_CAPACITY, "max(ef,k) / dim too large for the per-query shared-memory heaps");
+    const unsigned smem_blocks = (unsigned) std::max<size_t>(1, (size_t) (227 * 1024) / (smem + 1024));
+    const unsigned max_blocks = (unsigned) idx->n_sms * std::min(std::min(idx->knn_blocks_per_sm, smem_blocks), walk ? (unsigned) TSGPU_WALK_MIN_CTAS : 64u);
     const unsigned grid = std::max(1u, std::min(max_blocks, (nq + 3) / 4));
     const size_t slots = (size_t) grid * 4;
-    const size_t vis_words = ((size_t) g.n_nodes + 31) / 32;
-    // per-warp scratch: with a selective filter hnswlib pushes every visited node into the candidate set until `ef`
-    // allowed results exist, so the heap must hold ~visited-count entries; 256 Ki keys (2 MiB) per warp slot
-    const uint32_t log_cap = 65536, cand_cap = std::min<uint32_t>(262144, std::max<uint32_t>(1024, g.n_nodes + 1));
-    if(slots * vis_words > idx->knn_slots * idx->knn_vis_words || vis_words != idx->knn_vis_words) {
+    // per-warp scratch in HBM: tier 2 of the visited set (64 Ki keys: walks of up to 48 K visited nodes) and the overflow of
+    // the candidate heap (with a selective filter hnswlib pushes every visited node until `ef` allowed results exist).
+    // A walk that outgrows either is handed to the retry launch below, whose slots are sized for the whole graph.
+    const uint32_t vis2_slots = 1u << 16, cand_cap = std::min<uint32_t>(1u << 16, std::max<uint32_t>(1024, g.n_nodes + 1));
+    if(slots > idx->knn_slots) {
         idx->d_knn_vis.release();
-        CU(idx->d_knn_vis.reserve(slots * vis_words * 4));
+        CU(idx->d_knn_vis.reserve(slots * (size_t) vis2_slots * 4));
         CU(cudaMemsetAsync(idx->d_knn_vis.p, 0, idx->d_knn_vis.cap, st));
-        idx->knn_slots = slots; idx->knn_vis_words = vis_words;
+        idx->knn_slots = slots;
     }
-    CU(idx->d_knn_log.reserve(slots * log_cap * 4));
     CU(idx->d_knn_cand.reserve(slots * (size_t) cand_cap * 8));
+    // retry slots (one CTA): visited tier 2 with >= 2 n slots, candidate arena n + 1
+    const uint32_t big_vis = pow2_ceil(std::max<uint32_t>(1u << 17, 2 * g.n_nodes + 64)), big_cand = g.n_nodes + 1;
+    {
+        const size_t need = (size_t) 16 * big_vis * 4;
+        if(need > idx->d_knn_retry_vis.cap) {
+            idx->d_knn_retry_vis.release();
+            CU(idx->d_knn_retry_vis.reserve(need));
+            CU(cudaMemsetAsync(idx->d_knn_retry_vis.p, 0, idx->d_knn_retry_vis.cap, st));
+        }
+        CU(idx->d_knn_retry_cand.reserve((size_t) 16 * big_cand * 8));
+    }
+    // hand-out order: longest expected walks first
+    std::vector<uint32_t> order;
+    if(!q_cost.empty()) {
+        order.resize(nq);
+        for(uint32_t q = 0; q < nq; q++) order[q] = q;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b2) { return q_cost[a] > q_cost[b2]; });
+    }
     // outputs + per-query pointer tables
     Stager sg;
     const size_t o_bm = sg.add(q_bitmap.empty() ? nullptr : q_bitmap.data(), (size_t) nq * 8);
     const size_t o_ex = sg.add(q_excl.empty() ? nullptr : q_excl.data(), (size_t) nq * 8);
     const size_t o_ne = sg.add(q_nexcl.empty() ? nullptr : q_nexcl.data(), (size_t) nq * 4);
     const size_t o_sk = sg.add(q_skip.empty() ? nullptr : q_skip.data(), (size_t) nq);
-    const size_t o_misc = sg.reserve(64);
-    memset(sg.host.data() + o_misc, 0, 64);
+    const size_t o_or = sg.add(order.empty() ? nullptr : order.data(), (size_t) nq * 4);
+    const size_t o_rl = sg.reserve((size_t) nq * 4 + 64);          // retry list
+    const size_t o_wk = sg.reserve((size_t) nq * 8);               // per-walk work counters
+    const size_t o_misc = sg.reserve(128);
+    memset(sg.host.data() + o_misc, 0, 128);
     idx->knn_tables.swap(sg.host);                 // keep the pageable source alive until the call ends
     const size_t tbl_bytes = idx->knn_tables.size();
     const size_t out_bytes = (size_t) nq * k * 8 + (size_t) nq * 4;
@@ -612,47 +657,68 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     out.labels = reinterpret_cast<uint32_t*>(ob + (size_t) nq * k * 4);
     out.n = reinterpret_cast<uint32_t*>(ob + (size_t) nq * k * 8);
     out.stride = k;
+    // misc layout: [0] ticket, [4] retry ticket, [8..40) stats u64 x4, [40] retry_n, [44] retry_n of the retry launch (unused)
     tsv::KnnParams P{};
     P.queries = d_queries; P.nq = nq; P.k = k; P.ef = ef;
     P.q_filter_bitmap = q_bitmap.empty() ? nullptr : reinterpret_cast<const uint32_t* const*>(base + o_bm);
     P.q_excl = q_excl.empty() ? nullptr : reinterpret_cast<const uint32_t* const*>(base + o_ex);
     P.q_n_excl = q_nexcl.empty() ? nullptr : reinterpret_cast<const uint32_t*>(base + o_ne);
     P.q_skip = q_skip.empty() ? nullptr : reinterpret_cast<const uint8_t*>(base + o_sk);
+    P.q_order = order.empty() ? nullptr : reinterpret_cast<const uint32_t*>(base + o_or);
+    P.n_order = nq; P.n_order_dev = nullptr;
     P.out_dist = out.dist; P.out_labels = out.labels; P.out_n = out.n;
-    P.visited = idx->d_knn_vis.as<uint32_t>(); P.vis_words = (uint32_t) vis_words;
-    P.vis_log = idx->d_knn_log.as<uint32_t>(); P.log_cap = log_cap;
+    P.vis2 = idx->d_knn_vis.as<uint32_t>(); P.vis2_slots = vis2_slots;
     P.cand = idx->d_knn_cand.as<unsigned long long>(); P.cand_cap = cand_cap;
     P.counter = reinterpret_cast<uint32_t*>(base + o_misc);
     P.stats = reinterpret_cast<unsigned long long*>(base + o_misc + 8);
-    P.error = reinterpret_cast<int*>(base + o_misc + 32);
-    const uint32_t dim = g.dim;
-    const int nch = (dim % 128 == 0) ? (int) (dim / 128) : 0;
-    const size_t heap_bytes = (size_t) 4 * ((size_t) efe + 1 + tsv::kCandSmem) * 8;
-    const size_t q_bytes = (size_t) 4 * ((dim + 3) & ~3u) * 4;
+    P.retry_n = reinterpret_cast<uint32_t*>(base + o_misc + 40);
+    P.retry_list = reinterpret_cast<uint32_t*>(base + o_rl);
+    P.q_work = reinterpret_cast<uint32_t*>(base + o_wk);
+    idx->knn_work_dev = P.q_work; idx->knn_work_n = nq;
+    // the retry launch: the same kernel over the queries the first one handed back, one CTA whose four slots can hold a
+    // walk over the whole graph. It reads its ticket count from device memory, so it is issued unconditionally (no host
+    // round trip between the two) and ends at once when nothing was handed back.
+    tsv::KnnParams R = P;
+    R.q_order = P.retry_list; R.n_order = 0; R.n_order_dev = P.retry_n; R.q_skip = nullptr;
+    R.vis2 = idx->d_knn_retry_vis.as<uint32_t>(); R.vis2_slots = big_vis;
+    R.cand = idx->d_knn_retry_cand.as<unsigned long long>(); R.cand_cap = big_cand;
+    R.counter = reinterpret_cast<uint32_t*>(base + o_misc + 4);
+    R.retry_n = reinterpret_cast<uint32_t*>(base + o_misc + 44);
+    R.retry_list = reinterpret_cast<uint32_t*>(base + o_rl + (size_t) nq * 4);    // cannot be reached: nothing outgrows a full-size slot
     CU(cudaEventRecord(idx->ev[3], st));
-    switch(nch) {
-        case 1: launch_hnsw<1>(idx, P, grid, heap_bytes); break;
-        case 2: launch_hnsw<2>(idx, P, grid, heap_bytes); break;
-        case 3: launch_hnsw<3>(idx, P, grid, heap_bytes); break;
-        case 4: launch_hnsw<4>(idx, P, grid, heap_bytes); break;
-        case 6: launch_hnsw<6>(idx, P, grid, heap_bytes); break;
-        case 8: launch_hnsw<8>(idx, P, grid, heap_bytes); break;
-        default: launch_hnsw<0>(idx, P, grid, heap_bytes + q_bytes); break;
+    if(walk) switch(nch) {
+        case 1: launch_walk<1>(idx, P, grid, smem); launch_walk<1>(idx, R, 4, smem); break;
+        case 2: launch_walk<2>(idx, P, grid, smem); launch_walk<2>(idx, R, 4, smem); break;
+        case 3: launch_walk<3>(idx, P, grid, smem); launch_walk<3>(idx, R, 4, smem); break;
+        case 4: launch_walk<4>(idx, P, grid, smem); launch_walk<4>(idx, R, 4, smem); break;
+        case 6: launch_walk<6>(idx, P, grid, smem); launch_walk<6>(idx, R, 4, smem); break;
+        case 8: launch_walk<8>(idx, P, grid, smem); launch_walk<8>(idx, R, 4, smem); break;
+        default: launch_walk<0>(idx, P, grid, smem); launch_walk<0>(idx, R, 4, smem); break;
     }
-    idx->stats.launches_total++;
+    else switch(nch) {
+        case 1: launch_hnsw<1>(idx, P, grid, smem); launch_hnsw<1>(idx, R, 1, smem); break;
+        case 2: launch_hnsw<2>(idx, P, grid, smem); launch_hnsw<2>(idx, R, 1, smem); break;
+        case 3: launch_hnsw<3>(idx, P, grid, smem); launch_hnsw<3>(idx, R, 1, smem); break;
+        case 4: launch_hnsw<4>(idx, P, grid, smem); launch_hnsw<4>(idx, R, 1, smem); break;
+        case 6: launch_hnsw<6>(idx, P, grid, smem); launch_hnsw<6>(idx, R, 1, smem); break;
+        case 8: launch_hnsw<8>(idx, P, grid, smem); launch_hnsw<8>(idx, R, 1, smem); break;
+        default: launch_hnsw<0>(idx, P, grid, smem); launch_hnsw<0>(idx, R, 1, smem); break;
+    }
+    idx->stats.launches_total += 2;
     CU(cudaGetLastError());
     CU(cudaEventRecord(idx->ev[4], st));
-    idx->knn_misc_dev = base + o_misc;        // counters + overflow flag are read by finish_knn() after the final sync
+    idx->knn_misc_dev = base + o_misc;        // counters are read by finish_knn() after the final sync
     return TSGPU_OK;
 }
 
 tsgpu_status finish_knn(tsgpu_index* idx) {
     if(!idx->knn_misc_dev) return TSGPU_OK;
-    unsigned long long hst[4];
-    CU(cudaMemcpy(hst, idx->knn_misc_dev + 8, 32, cudaMemcpyDeviceToHost));
+    unsigned long long hst[5];
+    CU(cudaMemcpy(hst, idx->knn_misc_dev + 8, 40, cudaMemcpyDeviceToHost));
     idx->knn_misc_dev = nullptr;
     idx->stats.knn_dist += hst[0]; idx->stats.knn_expanded += hst[1]; idx->stats.knn_spec_hits += hst[2];
-    if((int) hst[3]) return fail(TSGPU_ERR_CAPACITY, "HNSW candidate heap overflow (more than 262144 live candidates in one query)");
+    idx->stats.knn_tier2_walks += hst[3];
+    idx->stats.knn_retried += (uint32_t) hst[4];
     return TSGPU_OK;
 }
 
@@ -778,7 +844,11 @@ tsgpu_status run_vector_stage(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan&
     // before searching in that case — mark such queries as skipped
     std::vector<uint8_t> skip(is_flat);
     for(uint32_t q = 0; q < nq; q++) if(pl.qd[q].filter_empty) skip[q] = 1;
-    return run_knn(idx, reinterpret_cast<const float*>(base + o_q), nq, k, vp->ef, pl.q_bitmap, pl.q_excl_dev, nexcl, skip, vs.knn);
+    // expected walk length: a filter of selectivity s makes hnswlib visit ~1/s times as many nodes before `ef` allowed results exist
+    std::vector<float> cost(nq, 1.0f);
+    for(uint32_t q = 0; q < nq; q++)
+        if(b->q_filter[q] != -1 && pl.q_filter_n[q]) cost[q] = std::min(1e6f, (float) idx->n_docs / (float) pl.q_filter_n[q]);
+    return run_knn(idx, reinterpret_cast<const float*>(base + o_q), nq, k, vp->ef, pl.q_bitmap, pl.q_excl_dev, nexcl, skip, cost, vs.knn);
 }
 
 }  // namespace
@@ -838,7 +908,7 @@ void tsgpu_index_destroy(tsgpu_index* idx) {
     for(void* p: idx->hnsw_alloc) cudaFree(p);
     for(auto& f: idx->filters) { if(f.d_bitmap) cudaFree(f.d_bitmap); if(f.d_ids) cudaFree(f.d_ids); }
     DevBuf* bufs[] = {&idx->d_stage, &idx->d_pool, &idx->d_small, &idx->d_bitmaps, &idx->d_found_bm, &idx->d_out, &idx->d_knn_vis,
-                      &idx->d_knn_log, &idx->d_knn_cand, &idx->d_knn_out, &idx->d_isect, &idx->d_kw_out};
+                      &idx->d_knn_retry_vis, &idx->d_knn_retry_cand, &idx->d_knn_cand, &idx->d_knn_out, &idx->d_isect, &idx->d_kw_out};
     for(auto* b: bufs) b->release();
     idx->h_stage.release();
     for(auto& e: idx->ev) if(e) cudaEventDestroy(e);
@@ -974,6 +1044,8 @@ tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g) {
     idx->has_hnsw = true;
     return TSGPU_OK;
 }
+
+#include "hnsw_build_host.inc"
 
 tsgpu_status tsgpu_filter_create(tsgpu_index* idx, const uint32_t* ids, size_t n, int32_t* out_handle) {
     tsgpu_status s = check_device(idx); if(s) return s;
@@ -1232,7 +1304,18 @@ tsgpu_status tsgpu_knn_batch(tsgpu_index* idx, const float* queries, uint32_t nq
     }
     KnnDeviceOut o{};
     idx->vs = idx->stream; idx->knn_blocks_per_sm = 7;
-    s = run_knn(idx, reinterpret_cast<const float*>(base), nq, k, ef, q_bitmap, {}, {}, {}, o); if(s) return s;
+    std::vector<float> cost;
+    if(q_filter) {
+        cost.assign(nq, 1.0f);
+        for(uint32_t q = 0; q < nq; q++) {
+            const int32_t fs = q_filter[q];
+            size_t n = 0;
+            if(fs >= 0) n = (size_t) (filter_off[fs + 1] - filter_off[fs]);
+            else if(fs <= -2) n = idx->filters[(size_t) (-(fs + 2))].n;
+            if(fs != -1 && n) cost[q] = std::min(1e6f, (float) idx->n_docs / (float) n);
+        }
+    }
+    s = run_knn(idx, reinterpret_cast<const float*>(base), nq, k, ef, q_bitmap, {}, {}, {}, cost, o); if(s) return s;
     CU(cudaMemcpyAsync(out_dist, o.dist, (size_t) nq * k * 4, cudaMemcpyDefault, st));
     CU(cudaMemcpyAsync(out_labels, o.labels, (size_t) nq * k * 4, cudaMemcpyDefault, st));
     CU(cudaMemcpyAsync(out_n, o.n, (size_t) nq * 4, cudaMemcpyDefault, st));
@@ -1385,6 +1468,17 @@ tsgpu_status tsgpu_vector_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b
 tsgpu_status tsgpu_hybrid_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const float* qvecs, const tsgpu_vec_params* vp,
                                        tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
     return vec_or_hybrid(idx, b, qvecs, vp, out_kv, kv_stride, out_count, out_found, true);
+}
+
+/* instrumentation: (expansions, distance evaluations) of every graph walk of the last call that ran the HNSW kernel */
+tsgpu_status tsgpu_debug_knn_work(tsgpu_index* idx, uint32_t* out, uint32_t cap_queries, uint32_t* out_n) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!out || !out_n) return fail(TSGPU_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    const uint32_t n = std::min(cap_queries, idx->knn_work_dev ? idx->knn_work_n : 0u);
+    if(n) CU(cudaMemcpy(out, idx->knn_work_dev, (size_t) n * 8, cudaMemcpyDeviceToHost));
+    *out_n = n;
+    return TSGPU_OK;
 }
 
 tsgpu_status tsgpu_get_stats(tsgpu_index* idx, tsgpu_stats* out) {
