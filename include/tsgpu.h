@@ -170,6 +170,10 @@ tsgpu_status tsgpu_filter_destroy(tsgpu_index* idx, int32_t handle);
 tsgpu_status tsgpu_intersect(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k,
                              uint32_t* out_ids, size_t cap, size_t* out_n);
 
+/* posting_t::contains_atleast_one / posting_list_t::contains_atleast_one (src/posting.cpp:365, src/posting_list.cpp:1090-1112;
+ * call sites src/index.cpp:6519, src/art.cpp:992): *out = 1 when any of the ascending `ids` is in the list. */
+tsgpu_status tsgpu_contains_atleast_one(tsgpu_index* idx, uint32_t field, uint32_t list, const uint32_t* ids, size_t n, int* out);
+
 /* posting_t::get_phrase_matches (src/posting_list.cpp:1791; call site src/index.cpp:5960): of the ascending `ids`,
  * keep those where the k lists' tokens occur as a consecutive sequence. */
 tsgpu_status tsgpu_phrase_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k,

@@ -807,6 +807,19 @@ void parallel_for(uint32_t n, uint32_t n_threads, Fn fn) {
 // ============================================================================ C API
 extern "C" {
 
+int tso_contains_atleast_one(const uint32_t* list, size_t n_list, const uint32_t* target_ids, size_t n_targets) {
+    // posting_list_t::contains_atleast_one (src/posting_list.cpp:1090-1112): two ascending sequences, the smaller head advances
+    // (the list side by skip_to, here a gallop)
+    size_t li = 0, ti = 0;
+    while(ti < n_targets && li < n_list) {
+        const uint32_t id = list[li];
+        if(id == target_ids[ti]) return 1;
+        if(id > target_ids[ti]) { while(ti < n_targets && target_ids[ti] < id) ti++; }
+        else li = gallop_to(list, li, n_list, target_ids[ti]);
+    }
+    return 0;
+}
+
 size_t tso_intersect(uint32_t k, const uint32_t* const* lists, const size_t* lens, uint32_t* out, size_t cap) {
     // posting_list_t::intersect (src/posting_list.cpp:708-756)
     if(k == 0) return 0;

@@ -102,6 +102,8 @@ typedef struct {
 } tso_hnsw;
 
 /* ---- posting lists on flat arrays */
+/* posting_list_t::contains_atleast_one (src/posting_list.cpp:1090-1112) on an ascending id list */
+int tso_contains_atleast_one(const uint32_t* list, size_t n_list, const uint32_t* target_ids, size_t n_targets);
 size_t tso_intersect(uint32_t k, const uint32_t* const* lists, const size_t* lens, uint32_t* out, size_t cap);
 size_t tso_merge(uint32_t k, const uint32_t* const* lists, const size_t* lens, uint32_t* out, size_t cap);
 size_t tso_and_scalar(const uint32_t* a, size_t na, const uint32_t* b, size_t nb, uint32_t* out);

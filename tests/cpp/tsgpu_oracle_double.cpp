@@ -143,6 +143,11 @@ tsgpu_status tsgpu_intersect(tsgpu_index* idx, uint32_t field, const uint32_t* l
     *out_n = tso_intersect(k, ptr.data(), len.data(), out_ids, cap);
     return TSGPU_OK;
 }
+tsgpu_status tsgpu_contains_atleast_one(tsgpu_index* idx, uint32_t field, uint32_t list, const uint32_t* ids, size_t n, int* out) {
+    const FieldCopy& f = *D(idx)->fields[field];
+    *out = tso_contains_atleast_one(f.ids.data() + f.list_off[list], (size_t) (f.list_off[list + 1] - f.list_off[list]), ids, n);
+    return TSGPU_OK;
+}
 tsgpu_status tsgpu_phrase_matches(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, const uint32_t* ids, size_t n, uint32_t* out_ids, size_t* out_n) {
     *out_n = tso_phrase_matches(D(idx)->oi, field, lists, k, ids, n, out_ids);
     return TSGPU_OK;

@@ -40,6 +40,7 @@ def oracle():
         L = C.CDLL(ORACLE_SO)
         L.tso_intersect.restype = C.c_size_t
         L.tso_merge.restype = C.c_size_t
+        L.tso_contains_atleast_one.argtypes = [u32p, C.c_size_t, u32p, C.c_size_t]
         for n in ("tso_and_scalar", "tso_or_scalar", "tso_exclude_scalar"):
             getattr(L, n).restype = C.c_size_t
             getattr(L, n).argtypes = [u32p, C.c_size_t, u32p, C.c_size_t, u32p]

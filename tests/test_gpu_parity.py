@@ -124,6 +124,30 @@ def test_intersect_and_phrase(coll):
                 assert gi.phrase_matches(fi, lists.tolist(), ids).tolist() == out[:n].tolist()
 
 
+def test_contains_atleast_one(coll):
+    """posting_t::contains_atleast_one: the reference's own cases (test/posting_list_test.cpp:823-859) on a loaded field, then
+    random target sets against the oracle (pinned on the reference's compiled code in tests/test_oracle_ref.py)."""
+    from test_oracle_ref import CONTAINS_KAT
+    lists = [np.asarray(k[0], np.uint32) for k in CONTAINS_KAT[:1]] + [np.asarray(CONTAINS_KAT[3][0], np.uint32)]
+    flat = S.FlatField.from_postings([[(int(d), [1, 0]) for d in l] for l in lists], False)
+    gk = capi.GpuIndex(4000, 0)
+    fid = gk.load_field(flat)
+    for lst, targets, expect in CONTAINS_KAT:
+        li = 0 if len(lst) > 100 else 1
+        assert gk.contains_atleast_one(fid, li, targets) == expect
+    gk.close()
+    n_docs, fds, flats, pts, gi, oi = coll
+    rng = np.random.default_rng(3)
+    L = ol.oracle()
+    for f, flat in enumerate(flats):
+        df = np.diff(flat.list_off.astype(np.int64))
+        for _ in range(60):
+            l = int(rng.choice(np.nonzero(df > 0)[0]))
+            tg = np.unique(rng.integers(0, n_docs, int(rng.integers(1, 50)))).astype(np.uint32)
+            a = np.ascontiguousarray(flat.ids[int(flat.list_off[l]):int(flat.list_off[l + 1])])
+            assert gi.contains_atleast_one(f, l, tg) == bool(L.tso_contains_atleast_one(ol.p32(a), len(a), ol.p32(tg), len(tg)))
+
+
 def test_exact_and_prefix_matches(coll):
     """tsgpu_exact_matches / tsgpu_prefix_matches vs the oracle (itself pinned on the reference's compiled code)."""
     from test_hostsim import idset_cases

@@ -499,3 +499,35 @@ def test_kat_array_utils():
             out = np.zeros(len(a) + len(b) + 1, np.uint32)
             n = getattr(lib, pre + names[case["op"]])(ol.p32(a0), len(a), ol.p32(b0), len(b), ol.p32(out))
             assert out[:n].tolist() == case["expect"], (pre, case["src"])
+
+
+# test/posting_list_test.cpp:823-859 (PostingListContainsAtleastOne): the literal cases, then random lists against the
+# reference's compiled posting_list_t::contains_atleast_one
+CONTAINS_KAT = [
+    (list(range(20, 1000)), [200, 300], True), (list(range(20, 1000)), [200, 3000], True), (list(range(20, 1000)), [2000, 3000], False),
+    (list(range(10, 20)), list(range(5, 1000)), True), (list(range(10, 20)), list(range(25, 1000)), False),
+]
+
+
+def _tso_contains(lst, targets):
+    a, b = np.asarray(lst, np.uint32), np.asarray(targets, np.uint32)
+    return bool(ol.oracle().tso_contains_atleast_one(ol.p32(a), len(a), ol.p32(b), len(b)))
+
+
+@pytest.mark.parametrize("lst,targets,expect", CONTAINS_KAT)
+def test_kat_contains_atleast_one(lst, targets, expect):
+    assert _tso_contains(lst, targets) == expect
+    if ol.have_ref():
+        pls = ref_lists([lst], block=100 if len(lst) > 100 else 2)
+        t = np.asarray(targets, np.uint32)
+        assert bool(ol.ref().ref_plist_contains_atleast_one(pls[0].h, ol.p32(t), len(t))) == expect
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
+def test_ref_contains_atleast_one_random():
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        lst = np.unique(rng.integers(0, 3000, int(rng.integers(1, 400)))).tolist()
+        tg = np.unique(rng.integers(0, 3000, int(rng.integers(1, 60)))).astype(np.uint32)
+        pls = ref_lists([lst], block=int(rng.choice([2, 16, 256])))
+        assert _tso_contains(lst, tg) == bool(ol.ref().ref_plist_contains_atleast_one(pls[0].h, ol.p32(tg), len(tg)))

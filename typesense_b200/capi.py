@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("TSGPU_LIB_PATH") or os.path.join(HERE, "libtsgpu.so")
 EXPORTS = [
     "tsgpu_last_error", "tsgpu_device_count", "tsgpu_index_create", "tsgpu_index_destroy", "tsgpu_index_load_field",
     "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_index_build_hnsw", "tsgpu_index_hnsw_info", "tsgpu_index_export_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy",
-    "tsgpu_intersect", "tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches", "tsgpu_ids_setop", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
+    "tsgpu_intersect", "tsgpu_contains_atleast_one", "tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches", "tsgpu_ids_setop", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
     "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats", "tsgpu_debug_knn_work", "tsgpu_index_load_art", "tsgpu_art_walk_batch",
 ]
 
@@ -52,6 +52,7 @@ def lib():
         L.tsgpu_filter_create.argtypes = [vp, C.c_void_p, C.c_size_t, i32p]
         L.tsgpu_filter_destroy.argtypes = [vp, C.c_int32]
         L.tsgpu_intersect.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.tsgpu_contains_atleast_one.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, C.c_size_t, C.POINTER(C.c_int)]
         L.tsgpu_ids_setop.argtypes = [vp, C.c_int, u32p, C.c_size_t, u32p, C.c_size_t, u32p, C.c_size_t, C.POINTER(C.c_size_t)]
         for n in ("tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches"):
             getattr(L, n).argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, C.c_size_t, u32p, C.POINTER(C.c_size_t)]
@@ -193,6 +194,12 @@ class GpuIndex:
         return out.value
 
     # ---- search
+    def contains_atleast_one(self, field: int, lst: int, ids) -> bool:
+        a = np.ascontiguousarray(ids, np.uint32)
+        out = C.c_int(0)
+        _ck(self.L.tsgpu_contains_atleast_one(self.h, field, lst, a.ctypes.data_as(u32p), len(a), C.byref(out)))
+        return bool(out.value)
+
     def intersect(self, field: int, lists: Sequence[int], cap: int) -> np.ndarray:
         ls = np.asarray(lists, np.uint32)
         out = np.zeros(max(cap, 1), np.uint32)

@@ -1039,6 +1039,19 @@ isect_tiles_kernel(const __grid_constant__ IndexDev ix, const __grid_constant__ 
     if(tid == 0) P.tile_cnt[tile] = total;
 }
 
+// posting_list_t::contains_atleast_one (src/posting_list.cpp:1090-1112; compact form src/posting.cpp:215): is any of the
+// ascending target ids a member of list l? One probe per target id (skip index + packed block, or the dense bitmap).
+__global__ void __launch_bounds__(256)
+contains_any_kernel(const __grid_constant__ IndexDev ix, uint32_t field, uint32_t l, const uint32_t* __restrict__ ids, size_t n, int* __restrict__ out) {
+    const DevField& g = ix.fields[field];
+    const uint32_t b0 = g.list_blk_off[l], b1 = g.list_blk_off[l + 1];
+    bool hit = false;
+    if(b1 > b0)
+        for(size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n && !hit; i += (size_t) gridDim.x * blockDim.x)
+            hit = probe_list(g, l, b0, b1 - 1, ids[i]) != kNone;
+    if(__any_sync(0xffffffffu, hit) && (threadIdx.x & 31) == 0) atomicExch(out, 1);
+}
+
 // single-CTA exclusive scan of tile counts (n_tiles <= a few hundred thousand)
 __global__ void __launch_bounds__(1024)
 scan_tiles_kernel(const uint32_t* __restrict__ cnt, uint32_t n, unsigned long long* __restrict__ off, unsigned long long* total) {

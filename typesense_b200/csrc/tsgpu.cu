@@ -1137,6 +1137,33 @@ static tsgpu_status isect_common(tsgpu_index* idx, uint32_t field, const uint32_
     return end_call(idx, true, false);
 }
 
+tsgpu_status tsgpu_contains_atleast_one(tsgpu_index* idx, uint32_t field, uint32_t list, const uint32_t* ids, size_t n, int* out) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!out || (n && !ids)) return fail(TSGPU_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if(field >= idx->fields.size()) return fail(TSGPU_ERR_INVALID, "field id out of range");
+    if(list >= idx->fields[field].dev.n_lists) return fail(TSGPU_ERR_INVALID, "list out of range");
+    begin_call(idx);
+    *out = 0;
+    if(n == 0) return end_call(idx, false, false);
+    cudaStream_t st = idx->stream;
+    CU(idx->d_isect.reserve(n * 4 + 512));
+    unsigned char* base = idx->d_isect.as<unsigned char>();
+    CU(cudaMemsetAsync(base, 0, 256, st));
+    CU(cudaMemcpyAsync(base + 256, ids, n * 4, cudaMemcpyDefault, st));
+    idx->stats.h2d_bytes += n * 4;
+    const unsigned grid = (unsigned) std::min<size_t>((n + 255) / 256, (size_t) idx->n_sms * 8);
+    CU(cudaEventRecord(idx->ev[1], st));
+    contains_any_kernel<<<grid, 256, 0, st>>>(idx->ixdev, field, list, reinterpret_cast<const uint32_t*>(base + 256), n, reinterpret_cast<int*>(base));
+    idx->stats.launches_total++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(idx->ev[6], st));
+    CU(cudaEventRecord(idx->ev[2], st));
+    CU(cudaMemcpyAsync(out, base, 4, cudaMemcpyDeviceToHost, st));
+    idx->stats.d2h_bytes += 4;
+    return end_call(idx, true, false);
+}
+
 tsgpu_status tsgpu_intersect(tsgpu_index* idx, uint32_t field, const uint32_t* lists, uint32_t k, uint32_t* out_ids,
                              size_t cap, size_t* out_n) {
     return isect_common(idx, field, lists, k, nullptr, 0, 0, out_ids, cap, out_n);
