@@ -268,6 +268,43 @@ tsgpu_status tsgpu_hybrid_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b
                                        const tsgpu_vec_params* vp, tsgpu_kv* out_kv, uint32_t kv_stride,
                                        uint32_t* out_count, uint32_t* out_found);
 
+/* The tail of a keyword + vector query whose keyword stage has already run (Index::search reaches the vector query only
+ * after fuzzy_search_fields and the drop-token rounds, src/index.cpp:4036): kw_kv[q*kw_stride ..] holds query q's final
+ * keyword Topster in Topster::sort() order (kw_count[q] <= q_topk[q] entries), kw_found[q] its all_result_ids_len and
+ * kw_searched[q] its searched_queries.size(); the batch's combinations are every combination the rounds executed (they are
+ * only probed to tell vector results that are keyword matches from new ids). Runs the vector stage and the rank fusion as
+ * tsgpu_hybrid_search_batch does. */
+tsgpu_status tsgpu_hybrid_fuse_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const tsgpu_kv* kw_kv, uint32_t kw_stride,
+                                     const uint32_t* kw_count, const uint32_t* kw_found, const uint32_t* kw_searched,
+                                     const float* qvecs, const tsgpu_vec_params* vp, tsgpu_kv* out_kv, uint32_t kv_stride,
+                                     uint32_t* out_count, uint32_t* out_found);
+
+/* ---- facets ---------------------------------------------------------------------------------------- */
+/* tsgpu_kw_batch::q_flags bit: keep the query's all_result_ids (the id_buff / vec_search_ids union of src/index.cpp:5081-5090,
+ * 4215-4219) on the device after a keyword / hybrid search, as one bit per doc — the `out_all_ids` of SURVEY 8(b). */
+#define TSGPU_QFLAG_KEEP_ALL_IDS 0x80u
+/* Mirror of one facet field: facet_index_t's seq_id -> facet ids (src/facet_index.cpp:27-90; ids are the dense counter the
+ * reference assigns per distinct value; a binding densifies numeric facets the same way). Host or device pointers. */
+typedef struct {
+    uint32_t n_values;           /* ids are 0 .. n_values-1 */
+    const uint64_t* doc_off;     /* [n_docs+1] */
+    const uint32_t* value_ids;   /* per doc in stored order: array_pos = index inside the doc's slice */
+} tsgpu_facet;
+typedef struct { uint32_t value_id, count, doc_id, array_pos; } tsgpu_facet_count;
+tsgpu_status tsgpu_index_load_facet(tsgpu_index* idx, const tsgpu_facet* f, uint32_t* out_facet);
+/* Index::do_facets, hash-index branch (src/index.cpp:1674-1780) over ascending `result_ids` (host or device), then the
+ * (count, id)-descending order of Collection::search (include/collection.h:552): writes the top_n (<= 1024) entries,
+ * *out_n = entries written, *out_distinct = values with a count. sample_mod > 1: `estimate_facets`, every sample_mod-th id.
+ * doc_id / array_pos: of the largest result id holding the value (one sequential do_facets pass). */
+tsgpu_status tsgpu_facet_counts(tsgpu_index* idx, uint32_t facet, const uint32_t* result_ids, size_t n, uint32_t sample_mod,
+                                uint32_t top_n, tsgpu_facet_count* out, uint32_t* out_n, uint32_t* out_distinct);
+/* The same over the all_result_ids the LAST keyword / hybrid search kept (TSGPU_QFLAG_KEEP_ALL_IDS), every query of that
+ * batch at once: out[q*top_n ..], out_n[q], out_distinct[q] (0 for queries that did not keep their ids). */
+tsgpu_status tsgpu_facet_counts_last(tsgpu_index* idx, uint32_t facet, uint32_t top_n, tsgpu_facet_count* out, uint32_t* out_n,
+                                     uint32_t* out_distinct);
+/* all_result_ids of query q of the last search (ascending; needs TSGPU_QFLAG_KEEP_ALL_IDS). */
+tsgpu_status tsgpu_all_result_ids_last(tsgpu_index* idx, uint32_t q, uint32_t* out_ids, size_t cap, size_t* out_n);
+
 /* ---- instrumentation ------------------------------------------------------------------------------------------ */
 /* Device-time breakdown of the last search call on this index (CUDA events on the library's stream), kernel launch
  * count since index creation, and algorithmic work counters of the last call. */

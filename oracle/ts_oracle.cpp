@@ -807,6 +807,37 @@ void parallel_for(uint32_t n, uint32_t n_threads, Fn fn) {
 // ============================================================================ C API
 extern "C" {
 
+size_t tso_facet_counts(uint32_t n_docs, uint32_t n_values, const uint64_t* doc_off, const uint32_t* value_ids,
+                        const uint32_t* result_ids, size_t n, uint32_t sample_mod, tso_facet_count* out, size_t cap, uint32_t* out_distinct) {
+    // Index::do_facets, hash-index branch (src/index.cpp:1674-1780) over ONE batch of ascending result ids, plain facet (no
+    // range / facet query / group-by): per doc the distinct facet ids it holds; count += 1, doc_id = this doc, array_pos =
+    // position of the id in the doc's list; `estimate_facets` keeps every sample_mod-th result (i % mod == 0). Then
+    // Collection::search's order: (count, id) descending (include/collection.h:552-554).
+    std::vector<uint32_t> cnt(n_values, 0), doc(n_values, 0), pos(n_values, 0);
+    for(size_t i = 0; i < n; i++) {
+        if(sample_mod > 1 && (i % sample_mod) != 0) continue;
+        const uint32_t d = result_ids[i];
+        if(d >= n_docs) continue;
+        const uint64_t o0 = doc_off[d], o1 = doc_off[d + 1];
+        for(uint64_t j = o0; j < o1; j++) {
+            const uint32_t v = value_ids[j];
+            if(v >= n_values) continue;
+            bool dup = false;
+            for(uint64_t k = o0; k < j && !dup; k++) dup = value_ids[k] == v;
+            if(dup) continue;
+            cnt[v]++; doc[v] = d; pos[v] = (uint32_t) (j - o0);
+        }
+    }
+    std::vector<tso_facet_count> all;
+    for(uint32_t v = 0; v < n_values; v++) if(cnt[v]) all.push_back({v, cnt[v], doc[v], pos[v]});
+    std::sort(all.begin(), all.end(), [](const tso_facet_count& a, const tso_facet_count& b) {
+        return a.count != b.count ? a.count > b.count : a.value_id > b.value_id; });
+    if(out_distinct) *out_distinct = (uint32_t) all.size();
+    const size_t m = std::min(cap, all.size());
+    for(size_t i = 0; i < m; i++) out[i] = all[i];
+    return m;
+}
+
 int tso_contains_atleast_one(const uint32_t* list, size_t n_list, const uint32_t* target_ids, size_t n_targets) {
     // posting_list_t::contains_atleast_one (src/posting_list.cpp:1090-1112): two ascending sequences, the smaller head advances
     // (the list side by skip_to, here a gallop)

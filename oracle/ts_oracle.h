@@ -102,6 +102,10 @@ typedef struct {
 } tso_hnsw;
 
 /* ---- posting lists on flat arrays */
+/* Index::do_facets hash-index branch (src/index.cpp:1674-1780) + Collection::search's (count, id) order; returns entries written */
+typedef struct { uint32_t value_id, count, doc_id, array_pos; } tso_facet_count;
+size_t tso_facet_counts(uint32_t n_docs, uint32_t n_values, const uint64_t* doc_off, const uint32_t* value_ids,
+                        const uint32_t* result_ids, size_t n, uint32_t sample_mod, tso_facet_count* out, size_t cap, uint32_t* out_distinct);
 /* posting_list_t::contains_atleast_one (src/posting_list.cpp:1090-1112) on an ascending id list */
 int tso_contains_atleast_one(const uint32_t* list, size_t n_list, const uint32_t* target_ids, size_t n_targets);
 size_t tso_intersect(uint32_t k, const uint32_t* const* lists, const size_t* lens, uint32_t* out, size_t cap);
@@ -193,6 +197,9 @@ int tso_hybrid_search_batch(void* idx, const tso_kw_batch* b, const float* qvecs
                             uint32_t n_threads);
 /* pure vector search batch (wildcard q + vector_query): sort clauses / filter / exclusion from the kw batch
  * (combos unused) */
+int tso_hybrid_fuse_batch(void* idx, const tso_kw_batch* b, const tso_kv* kw_kv, uint32_t kw_stride, const uint32_t* kw_count, const uint32_t* kw_found,
+                          const uint32_t* kw_searched, const float* qvecs, const tso_vec_params* vp, tso_kv* out_kv, uint32_t kv_stride,
+                          uint32_t* out_count, uint32_t* out_found, uint32_t n_threads);
 int tso_vector_search_batch(void* idx, const tso_kw_batch* b, const float* qvecs, const tso_vec_params* vp,
                             tso_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found,
                             uint32_t n_threads);

@@ -195,6 +195,30 @@ static void collection_scenarios(const std::string& jsonl) {
                        (unsigned long long) (after.searches - searches0));
                 CHECK(after.searches - searches0 >= 20 && after.launches - launches0 <= 2);
             }
+            {   // the same list once more through the replay-batched multi_search (no thread per request; device walks fetched
+                // lazily, one batch per pass): identical answers, and as few keyword device calls as the longest search has rounds
+                std::vector<tsgpu::Index::batched_request> breqs;
+                for(auto& r: reqs) { tsgpu::Index::batched_request b; b.r = r; breqs.push_back(b); }
+                index.clear_walk_cache();
+                tsgpu::Index::batched_stats bst;
+                tsgpu::Index::batched_stats bst_any;
+                for(size_t threads: {size_t(1), size_t(4)}) {
+                    auto br = index.multi_search_batched(breqs, threads, threads == 1 ? &bst : &bst_any);
+                    CHECK(br.size() == seq.size());
+                    for(size_t i = 0; i < seq.size() && i < br.size(); i++) {
+                        CHECK(br[i].status.ok() && br[i].found == seq[i].found && ids_of(br[i].raw_result_kvs) == ids_of(seq[i].raw_result_kvs));
+                        for(size_t k = 0; k < seq[i].raw_result_kvs.size() && k < br[i].raw_result_kvs.size(); k++)
+                            CHECK(seq[i].raw_result_kvs[k].scores[0] == br[i].raw_result_kvs[k].scores[0]);
+                    }
+                }
+                printf("multi_search_batched: %zu passes, %zu keyword batches for %zu queries, %zu walk batches for %zu walks (%zu on the host)\n",
+                       bst.passes, bst.kw_batches, bst.kw_queries, bst.walk_batches, bst.walks, bst.host_walk_fallbacks);
+                CHECK(bst.kw_batches * 2 <= calls_seq);          // lazily fetched walks put the searches out of step by a pass or two
+                auto bad = breqs;
+                bad[1].r.the_fields = {"no_such_field"};
+                auto r3 = index.multi_search_batched(bad, 2);
+                CHECK(!r3[1].status.ok() && r3[0].status.ok() && ids_of(r3[0].raw_result_kvs) == ids_of(resps[0].raw_result_kvs));
+            }
             for(size_t i = 0; i < cases.size(); i++) {
                 CHECK(resps[i].status.ok());
                 auto ids = ids_of(resps[i].raw_result_kvs);

@@ -4,6 +4,8 @@
 // is linked only into the CPU build of that one test program, and is never part of libtsgpu.so: the product has no CPU
 // path. Layouts of tsgpu_* and tso_* structs are identical by construction (tests/oracle_lib.py passes one ctypes
 // struct to both), which the static_asserts below re-check.
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -55,12 +57,17 @@ static const tso_kw_batch* rewrite(const Double* d, const tsgpu_kw_batch* in, Re
         r.filter_off.push_back(r.filter_ids.size());
     }
     r.q_filter.assign(in->q_filter, in->q_filter + in->n_queries);
+    std::map<int32_t, int32_t> slot_of;                   // one inline slot per distinct handle
     for(uint32_t q = 0; q < in->n_queries; q++) {
         if(in->q_filter[q] > -2) continue;
-        const auto& ids = d->filters[(size_t) (-(in->q_filter[q] + 2))];
-        r.filter_ids.insert(r.filter_ids.end(), ids.begin(), ids.end());
-        r.filter_off.push_back(r.filter_ids.size());
-        r.q_filter[q] = (int32_t) r.filter_off.size() - 2;
+        auto it = slot_of.find(in->q_filter[q]);
+        if(it == slot_of.end()) {
+            const auto& ids = d->filters[(size_t) (-(in->q_filter[q] + 2))];
+            r.filter_ids.insert(r.filter_ids.end(), ids.begin(), ids.end());
+            r.filter_off.push_back(r.filter_ids.size());
+            it = slot_of.emplace(in->q_filter[q], (int32_t) r.filter_off.size() - 2).first;
+        }
+        r.q_filter[q] = it->second;
     }
     if(r.filter_ids.empty()) r.filter_ids.push_back(0);
     r.b.n_filters = (uint32_t) r.filter_off.size() - 1;
@@ -68,6 +75,8 @@ static const tso_kw_batch* rewrite(const Double* d, const tsgpu_kw_batch* in, Re
     return &r.b;
 }
 thread_local std::string g_err;
+// oracle threads per batch call: 1 for the scenario tests; bench.py's CPU arm sets TSGPU_DOUBLE_THREADS to the host's core count
+uint32_t n_thr() { static const uint32_t n = getenv("TSGPU_DOUBLE_THREADS") ? (uint32_t) std::max(1, atoi(getenv("TSGPU_DOUBLE_THREADS"))) : 1u; return n; }
 Double* D(tsgpu_index* p) { return reinterpret_cast<Double*>(p); }
 }
 
@@ -208,26 +217,36 @@ tsgpu_status tsgpu_ids_setop(tsgpu_index*, int op, const uint32_t* a, size_t na,
 }
 tsgpu_status tsgpu_keyword_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
     Rewritten r;
-    tso_keyword_search_batch(D(idx)->oi, rewrite(D(idx), b, r), reinterpret_cast<tso_kv*>(out_kv), kv_stride, out_count, out_found, 1);
+    tso_keyword_search_batch(D(idx)->oi, rewrite(D(idx), b, r), reinterpret_cast<tso_kv*>(out_kv), kv_stride, out_count, out_found, n_thr());
     return TSGPU_OK;
 }
 tsgpu_status tsgpu_wildcard_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
     Rewritten r;
-    tso_wildcard_search_batch(D(idx)->oi, rewrite(D(idx), b, r), reinterpret_cast<tso_kv*>(out_kv), kv_stride, out_count, out_found, 1);
+    tso_wildcard_search_batch(D(idx)->oi, rewrite(D(idx), b, r), reinterpret_cast<tso_kv*>(out_kv), kv_stride, out_count, out_found, n_thr());
     return TSGPU_OK;
 }
 tsgpu_status tsgpu_vector_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const float* qvecs, const tsgpu_vec_params* vp, tsgpu_kv* out_kv,
                                        uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
     Rewritten r;
     if(tso_vector_search_batch(D(idx)->oi, rewrite(D(idx), b, r), qvecs, reinterpret_cast<const tso_vec_params*>(vp), reinterpret_cast<tso_kv*>(out_kv),
-                               kv_stride, out_count, out_found, 1) != 0) { g_err = "no vector index loaded"; return TSGPU_ERR_INVALID; }
+                               kv_stride, out_count, out_found, n_thr()) != 0) { g_err = "no vector index loaded"; return TSGPU_ERR_INVALID; }
     return TSGPU_OK;
 }
 tsgpu_status tsgpu_hybrid_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const float* qvecs, const tsgpu_vec_params* vp, tsgpu_kv* out_kv,
                                        uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
     Rewritten r;
     if(tso_hybrid_search_batch(D(idx)->oi, rewrite(D(idx), b, r), qvecs, reinterpret_cast<const tso_vec_params*>(vp), reinterpret_cast<tso_kv*>(out_kv),
-                               kv_stride, out_count, out_found, 1) != 0) { g_err = "no vector index loaded"; return TSGPU_ERR_INVALID; }
+                               kv_stride, out_count, out_found, n_thr()) != 0) { g_err = "no vector index loaded"; return TSGPU_ERR_INVALID; }
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_hybrid_fuse_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const tsgpu_kv* kw_kv, uint32_t kw_stride, const uint32_t* kw_count,
+                                     const uint32_t* kw_found, const uint32_t* kw_searched, const float* qvecs, const tsgpu_vec_params* vp,
+                                     tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
+    Rewritten r;
+    if(tso_hybrid_fuse_batch(D(idx)->oi, rewrite(D(idx), b, r), reinterpret_cast<const tso_kv*>(kw_kv), kw_stride, kw_count, kw_found, kw_searched, qvecs,
+                             reinterpret_cast<const tso_vec_params*>(vp), reinterpret_cast<tso_kv*>(out_kv), kv_stride, out_count, out_found, n_thr()) != 0) {
+        g_err = "no vector index loaded"; return TSGPU_ERR_INVALID;
+    }
     return TSGPU_OK;
 }
 tsgpu_status tsgpu_flat_distances(tsgpu_index* idx, const float* query, const uint32_t* ids, size_t n, float* out_dist) {
@@ -255,13 +274,35 @@ tsgpu_status tsgpu_index_build_hnsw(tsgpu_index*, const float*, uint32_t, uint32
 }
 tsgpu_status tsgpu_index_hnsw_info(tsgpu_index*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint64_t*, uint64_t*) { g_err = "the test double has no device build"; return TSGPU_ERR_NO_DEVICE; }
 tsgpu_status tsgpu_index_export_hnsw(tsgpu_index*, uint8_t*, uint32_t*, uint64_t*, uint32_t*) { g_err = "the test double has no device build"; return TSGPU_ERR_NO_DEVICE; }
+namespace { struct FacetCopy { uint32_t n_values; std::vector<uint64_t> off; std::vector<uint32_t> vals; }; std::vector<FacetCopy*> g_facets; }
+tsgpu_status tsgpu_index_load_facet(tsgpu_index* idx, const tsgpu_facet* f, uint32_t* out_facet) {
+    const size_t n = D(idx)->n_docs;
+    FacetCopy* c = new FacetCopy;
+    c->n_values = f->n_values;
+    c->off.assign(f->doc_off, f->doc_off + n + 1);
+    c->vals.assign(f->value_ids, f->value_ids + c->off[n]);
+    if(c->vals.empty()) c->vals.push_back(0);
+    *out_facet = (uint32_t) g_facets.size();
+    g_facets.push_back(c);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_facet_counts(tsgpu_index* idx, uint32_t facet, const uint32_t* result_ids, size_t n, uint32_t sample_mod, uint32_t top_n,
+                                tsgpu_facet_count* out, uint32_t* out_n, uint32_t* out_distinct) {
+    static_assert(sizeof(tsgpu_facet_count) == sizeof(tso_facet_count), "facet count layout");
+    const FacetCopy& c = *g_facets[facet];
+    *out_n = (uint32_t) tso_facet_counts(D(idx)->n_docs, c.n_values, c.off.data(), c.vals.data(), result_ids, n, sample_mod,
+                                         reinterpret_cast<tso_facet_count*>(out), top_n, out_distinct);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_facet_counts_last(tsgpu_index*, uint32_t, uint32_t, tsgpu_facet_count*, uint32_t*, uint32_t*) { g_err = "the test double keeps no all_result_ids"; return TSGPU_ERR_NO_DEVICE; }
+tsgpu_status tsgpu_all_result_ids_last(tsgpu_index*, uint32_t, uint32_t*, size_t, size_t*) { g_err = "the test double keeps no all_result_ids"; return TSGPU_ERR_NO_DEVICE; }
 tsgpu_status tsgpu_debug_knn_work(tsgpu_index*, uint32_t*, uint32_t, uint32_t* out_n) { *out_n = 0; return TSGPU_OK; }
 tsgpu_status tsgpu_knn_batch(tsgpu_index* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef, const int32_t* q_filter, uint32_t,
                              const uint64_t* filter_off, const uint32_t* filter_ids, float* out_dist, uint32_t* out_labels, uint32_t* out_n) {
     Double* d = D(idx);
     if(!d->has_g) { g_err = "no vector index loaded"; return TSGPU_ERR_INVALID; }
     uint64_t stats[2] = {0, 0};
-    tso_hnsw_search_batch(&d->g, queries, nq, k, ef, q_filter, filter_off, filter_ids, out_dist, out_labels, out_n, stats, 1);
+    tso_hnsw_search_batch(&d->g, queries, nq, k, ef, q_filter, filter_off, filter_ids, out_dist, out_labels, out_n, stats, n_thr());
     return TSGPU_OK;
 }
 

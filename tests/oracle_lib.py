@@ -41,6 +41,8 @@ def oracle():
         L.tso_intersect.restype = C.c_size_t
         L.tso_merge.restype = C.c_size_t
         L.tso_contains_atleast_one.argtypes = [u32p, C.c_size_t, u32p, C.c_size_t]
+        L.tso_facet_counts.restype = C.c_size_t
+        L.tso_facet_counts.argtypes = [C.c_uint32, C.c_uint32, u64p, u32p, u32p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_size_t, u32p]
         for n in ("tso_and_scalar", "tso_or_scalar", "tso_exclude_scalar"):
             getattr(L, n).restype = C.c_size_t
             getattr(L, n).argtypes = [u32p, C.c_size_t, u32p, C.c_size_t, u32p]
@@ -316,3 +318,14 @@ def ref_plists_of(field: FlatField, lists: Sequence[int], block_max: int = 256) 
         pl.L.ref_plist_bulk(pl.h, p32(ids), p32(oi), p32(offs), len(ids))
         out.append(pl)
     return out
+
+
+def facet_counts(n_docs: int, n_values: int, doc_off: np.ndarray, value_ids: np.ndarray, ids, cap: int, sample_mod: int = 0):
+    """tso_facet_counts: (entries as the FACET_DTYPE of typesense_b200.capi, distinct values with a count)."""
+    from typesense_b200.capi import FACET_DTYPE
+    a = np.ascontiguousarray(ids, np.uint32)
+    out = np.zeros(max(cap, 1), FACET_DTYPE)
+    dis = C.c_uint32(0)
+    n = oracle().tso_facet_counts(n_docs, n_values, doc_off.ctypes.data_as(u64p), value_ids.ctypes.data_as(u32p), a.ctypes.data_as(u32p), len(a), sample_mod,
+                                  out.ctypes.data, cap, C.byref(dis))
+    return out[:n], dis.value

@@ -21,8 +21,12 @@ EXPORTS = [
     "tsgpu_last_error", "tsgpu_device_count", "tsgpu_index_create", "tsgpu_index_destroy", "tsgpu_index_load_field",
     "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_index_build_hnsw", "tsgpu_index_hnsw_info", "tsgpu_index_export_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy",
     "tsgpu_intersect", "tsgpu_contains_atleast_one", "tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches", "tsgpu_ids_setop", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
-    "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats", "tsgpu_debug_knn_work", "tsgpu_index_load_art", "tsgpu_art_walk_batch",
+    "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats", "tsgpu_debug_knn_work", "tsgpu_index_load_facet", "tsgpu_facet_counts", "tsgpu_facet_counts_last", "tsgpu_all_result_ids_last", "tsgpu_index_load_art", "tsgpu_art_walk_batch",
 ]
+
+
+FACET_DTYPE = np.dtype([("value_id", np.uint32), ("count", np.uint32), ("doc_id", np.uint32), ("array_pos", np.uint32)])
+QFLAG_KEEP_ALL_IDS = 0x80
 
 
 class TsgpuError(RuntimeError):
@@ -65,6 +69,10 @@ def lib():
             getattr(L, n).argtypes = [vp, C.POINTER(KwBatchStruct), C.c_void_p, C.POINTER(VecParamsStruct), C.c_void_p,
                                       C.c_uint32, C.c_void_p, C.c_void_p]
         L.tsgpu_get_stats.argtypes = [vp, C.POINTER(StatsStruct)]
+        L.tsgpu_index_load_facet.argtypes = [vp, C.c_void_p, u32p]
+        L.tsgpu_facet_counts.argtypes = [vp, C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, u32p, u32p]
+        L.tsgpu_facet_counts_last.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tsgpu_all_result_ids_last.argtypes = [vp, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.tsgpu_debug_knn_work.argtypes = [vp, C.c_void_p, C.c_uint32, u32p]
         L.tsgpu_index_load_art.argtypes = [vp, C.c_uint32, C.POINTER(ArtStruct)]
         L.tsgpu_art_walk_batch.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
@@ -328,6 +336,35 @@ class GpuIndex:
         out = np.zeros(max(len(ids), 1), np.float32)
         _ck(self.L.tsgpu_flat_distances(self.h, q.ctypes.data, ids.ctypes.data, len(ids), out.ctypes.data))
         return out[:len(ids)]
+
+    # ---- facets (SURVEY 8 f-3)
+    def load_facet(self, n_values: int, doc_off, value_ids) -> int:
+        class _F(C.Structure):
+            _fields_ = [("n_values", C.c_uint32), ("doc_off", C.c_void_p), ("value_ids", C.c_void_p)]
+        self._facet_keep = getattr(self, "_facet_keep", []) + [(doc_off, value_ids)]
+        f = _F(n_values, _addr(doc_off), _addr(value_ids))
+        out = C.c_uint32(0)
+        _ck(self.L.tsgpu_index_load_facet(self.h, C.byref(f), C.byref(out)))
+        return out.value
+
+    def facet_counts(self, facet: int, ids, top_n: int, sample_mod: int = 0):
+        a = np.ascontiguousarray(ids, np.uint32)
+        out = np.zeros(top_n, FACET_DTYPE)
+        n, dis = C.c_uint32(0), C.c_uint32(0)
+        _ck(self.L.tsgpu_facet_counts(self.h, facet, a.ctypes.data if len(a) else None, len(a), sample_mod, top_n, out.ctypes.data, C.byref(n), C.byref(dis)))
+        return out[:n.value], dis.value
+
+    def facet_counts_last(self, facet: int, nq: int, top_n: int):
+        out = np.zeros((nq, top_n), FACET_DTYPE)
+        n, dis = np.zeros(nq, np.uint32), np.zeros(nq, np.uint32)
+        _ck(self.L.tsgpu_facet_counts_last(self.h, facet, top_n, out.ctypes.data, n.ctypes.data, dis.ctypes.data))
+        return out, n, dis
+
+    def all_result_ids_last(self, q: int, cap: int) -> np.ndarray:
+        out = np.zeros(max(cap, 1), np.uint32)
+        n = C.c_size_t(0)
+        _ck(self.L.tsgpu_all_result_ids_last(self.h, q, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value]
 
     def knn_work(self, nq: int) -> np.ndarray:
         """[(expanded nodes, distance evaluations)] of every graph walk of the last call (instrumentation)."""

@@ -254,6 +254,8 @@ hybrid_fuse_kernel(const __grid_constant__ HybridParams P) {
             if(pass && qd.filter_bitmap) pass = (qd.filter_bitmap[seq_id >> 5] >> (seq_id & 31)) & 1;
             if(pass) {
                 fl = 1;
+                // all_result_ids |= vec_search_ids (src/index.cpp:4197, 4215-4219) when the query keeps its id set
+                if(qd.keep_all && qd.found_bitmap) atomicOr(qd.found_bitmap + (seq_id >> 5), 1u << (seq_id & 31));
                 const double vec_part = (1.0 / (double) (v_rank[vi] + 1)) * (double) VECTOR_SEARCH_WEIGHT;
                 int64_t sc[3];
                 v_msi[vi] = (int8_t) compute_sort_scores(SS, seq_id, float_to_int64(__double2float_rn(vec_part)), v_dist[vi], sc);
@@ -279,6 +281,7 @@ hybrid_fuse_kernel(const __grid_constant__ HybridParams P) {
             else {
                 if(qd.filter_bitmap && !((qd.filter_bitmap[seq_id >> 5] >> (seq_id & 31)) & 1)) continue;
                 if(qd.filter_empty) continue;
+                if(lane == 0 && qd.keep_all && qd.found_bitmap) atomicOr(qd.found_bitmap + (seq_id >> 5), 1u << (seq_id & 31));
             }
             // topster->map.find(seq_id)
             uint32_t found_pos = kNone;

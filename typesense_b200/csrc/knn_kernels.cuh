@@ -66,6 +66,7 @@ struct KnnParams {
     unsigned long long* stats;     // [0] n_dist, [1] n_expanded, [2] speculation hits, [3] walks that used tier 2
     uint32_t* retry_n;             // walks that outgrew the per-slot scratch: re-run by the host with a full-size slot
     uint32_t* retry_list;          // [nq]
+    uint32_t vis_cache;            // register-queue kernel: entries of the shared-memory visited cache per walk (power of two)
     uint32_t* q_work;              // [2*nq] expansions, distance evaluations of each walk (instrumentation; may be nullptr)
 };
 
@@ -550,38 +551,94 @@ __device__ __forceinline__ void warr_pop_front(WArr<S>& w, uint32_t lane) {
 }
 template <int S>
 __device__ __forceinline__ unsigned long long warr_get(const WArr<S>& w, uint32_t e) {       // e warp-uniform
+    const uint32_t r = e % S;
     unsigned long long v = w.a[0];
-#pragma unroll
-    for(int i = 1; i < S; i++) if((e % S) == (uint32_t) i) v = w.a[i];
+    if(S > 1 && r == 1) v = w.a[S > 1 ? 1 : 0];
+    if(S > 2 && r == 2) v = w.a[S > 2 ? 2 : 0];
+    if(S > 3 && r == 3) v = w.a[S > 3 ? 3 : 0];
     return __shfl_sync(0xffffffffu, v, e / S);
 }
 template <int S>
 __device__ __forceinline__ void warr_set_inf(WArr<S>& w, uint32_t e, uint32_t lane) {
-    if(lane == e / S) {
-#pragma unroll
-        for(int i = 0; i < S; i++) if((e % S) == (uint32_t) i) w.a[i] = kKeyInf;
-    }
+    const bool me = lane == e / S;
+    const uint32_t r = e % S;
+    if(me && r == 0) w.a[0] = kKeyInf;
+    if(S > 1 && me && r == 1) w.a[S > 1 ? 1 : 0] = kKeyInf;
+    if(S > 2 && me && r == 2) w.a[S > 2 ? 2 : 0] = kKeyInf;
+    if(S > 3 && me && r == 3) w.a[S > 3 ? 3 : 0] = kKeyInf;
 }
+static_assert(true, "WArr accessors are written out for S <= 4");
 
 constexpr int kResPerLane = 4;           // R: 128 entries
-constexpr int kBufPerLane = 2;           // C buffer: 64 entries
+constexpr int kBufPerLane = 4;           // C buffer: 128 entries
 constexpr uint32_t kBufCap = 32 * kBufPerLane;
+constexpr int kWalkWarps = 2;            // walks (warps) per CTA
+constexpr int kStageRows = 4;            // default: neighbour rows in flight per walk (shared-memory ring filled by cp.async.bulk)
+constexpr uint32_t kVisCache = 2048;     // default: direct-mapped cache of recently visited nodes per walk (shared memory)
+
+// ---- mbarrier + bulk async copy (TMA engine, 1-D): rows land in shared memory without passing through registers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Visited set of the register-queue kernel: the authoritative set is an open-addressing table in HBM (one per warp slot,
+// all-zero between walks); in front of it a direct-mapped cache of recently visited nodes in shared memory answers most of
+// the "already visited" tests (9 of 10 neighbours of an expanded node have been seen, almost always recently) with one
+// shared-memory load. Only cache misses — the fresh neighbours plus a few evicted ones — go to the table: one compare-
+// and-swap each, in parallel across the lanes. Exact by construction (the table decides), any size of walk.
+__device__ __forceinline__ bool vis_test_and_set(uint32_t* cache, uint32_t cmask, uint32_t* table, uint32_t mask2, uint32_t node) {
+    const uint32_t key = node + 1;
+    const uint32_t h = vis_hash(node);
+    uint32_t* c = cache + (h & cmask);
+    if(*c == key) return false;
+    bool fresh = false;
+    uint32_t j = (h >> 11) & mask2;
+    for(;;) {
+        const uint32_t old = atomicCAS(table + j, 0u, key);
+        if(old == 0) { fresh = true; break; }
+        if(old == key) break;
+        j = (j + 1) & mask2;
+    }
+    *c = key;
+    return fresh;
+}
 
 #ifndef TSGPU_WALK_MIN_CTAS
-#define TSGPU_WALK_MIN_CTAS 4
+#define TSGPU_WALK_MIN_CTAS 5
 #endif
-template <int NCH>
-__global__ void __launch_bounds__(kKnnThreads, TSGPU_WALK_MIN_CTAS)
+// NCH = dim / 128 (dim a multiple of 128: rows are staged by bulk copies of dim * 4 bytes); other dimensions take the heap kernel.
+template <int NCH, int RS>
+__global__ void __launch_bounds__(32 * kWalkWarps, RS == 2 ? 2 * TSGPU_WALK_MIN_CTAS : TSGPU_WALK_MIN_CTAS)
 hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t slot = blockIdx.x * (kKnnThreads / 32) + warp;
+    const uint32_t slot = blockIdx.x * kWalkWarps + warp;
     const uint32_t ef = P.ef > P.k ? P.ef : P.k;           // <= 128 (host checks)
-    const uint32_t dim = g.dim;
-    const uint32_t dim_pad = (dim + 3) & ~3u;
-    // shared per warp: [kVisSmem] u32 visited tier 1; then (generic path) the query vectors
-    uint32_t* vis1 = reinterpret_cast<uint32_t*>(smem_raw) + (size_t) warp * kVisSmem;
-    float* qs = reinterpret_cast<float*>(reinterpret_cast<uint32_t*>(smem_raw) + (size_t) (kKnnThreads / 32) * kVisSmem) + (size_t) warp * dim_pad;
+    constexpr uint32_t dim = NCH * 128, row_bytes = dim * 4;
+    // shared per CTA: [kWalkWarps] mbarriers (128 B), then per warp: [RS] rows, [kVisCache] u32
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw);
+    float* ring = reinterpret_cast<float*>(smem_raw + 128) + (size_t) warp * RS * dim;
+    const uint32_t n_cache = P.vis_cache, cmask = n_cache - 1;          // power of two
+    uint32_t* cache = reinterpret_cast<uint32_t*>(smem_raw + 128 + (size_t) kWalkWarps * RS * row_bytes) + (size_t) warp * n_cache;
+    const uint32_t bar = smem_u32(bars + warp), ring_s = smem_u32(ring);
+    uint32_t parity = 0;
+    if(lane == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
     uint32_t* vis2 = P.vis2 + (size_t) slot * P.vis2_slots;
     const uint32_t mask2 = P.vis2_slots - 1;
     const uint32_t limit2 = P.vis2_slots - (P.vis2_slots >> 2);
@@ -589,6 +646,7 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
     const uint32_t L0 = 2 * g.M + 1, LU = g.M + 1;
     const uint32_t n_tickets = P.n_order_dev ? __ldcg(P.n_order_dev) : (P.q_order ? P.n_order : P.nq);
     unsigned long long n_dist_acc = 0, n_exp_acc = 0, n_hit_acc = 0, n_t2_acc = 0;
+    float* const qs = nullptr;
 
     for(;;) {
         uint32_t qi = 0;
@@ -599,18 +657,13 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
         if(P.q_skip && P.q_skip[qi]) { if(lane == 0) P.out_n[qi] = 0; continue; }
         const float* qv = P.queries + (size_t) qi * dim;
         QReg<NCH> q;
-        if(NCH > 0) {
 #pragma unroll
-            for(int s = 0; s < NCH; s++) q.v[s] = __ldg(reinterpret_cast<const float4*>(qv + s * 128) + lane);
-        } else {
-            for(uint32_t e = lane; e < dim; e += 32) qs[e] = qv[e];
-            __syncwarp();
-        }
+        for(int s = 0; s < NCH; s++) q.v[s] = __ldg(reinterpret_cast<const float4*>(qv + s * 128) + lane);
         const uint32_t* fbm = P.q_filter_bitmap ? P.q_filter_bitmap[qi] : nullptr;
         const uint32_t* excl = P.q_excl ? P.q_excl[qi] : nullptr;
         const uint32_t n_excl = P.q_n_excl ? P.q_n_excl[qi] : 0;
         if(g.n_nodes == 0 || g.entry_point == kNone) { if(lane == 0) P.out_n[qi] = 0; continue; }
-        for(uint32_t i = lane; i < kVisSmem; i += 32) vis1[i] = 0;
+        for(uint32_t i = lane; i < n_cache; i += 32) cache[i] = 0;
         const unsigned long long exp0 = n_exp_acc, dist0 = n_dist_acc;
 
         // ---- greedy descent through the upper layers (searchKnn)
@@ -641,7 +694,7 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
         WArr<kResPerLane> R; warr_clear(R);
         WArr<kBufPerLane> B; warr_clear(B);
         uint32_t n_res = 0, n_b = 0, n_p = 0;                   // result count, buffered / pooled candidates (warp-uniform)
-        uint32_t n_v1 = 0, n_v2 = 0;
+        uint32_t n_vis = 0;                                      // keys in the visited table
         bool overflow = false;
         float lowerBound;
         __syncwarp();
@@ -657,8 +710,8 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
                 lowerBound = FLT_MAX;
                 warr_insert(B, cand_key(FLT_MAX, cur), lane); n_b = 1;
             }
-            if(lane == 0) vis_insert(vis1, vis2, mask2, cur, false);
-            n_v1 = 1;
+            if(lane == 0) vis_test_and_set(cache, cmask, vis2, mask2, cur);
+            n_vis = 1;
             __syncwarp();
         }
         uint32_t prev_spec = kNone, prev_nb2 = kNone, prev_size2 = 0;
@@ -710,8 +763,7 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
             n_hit_acc += reuse ? 1 : 0;
             const uint32_t size = reuse ? prev_size2 : __ldg(rec);
             const uint32_t nb = reuse ? prev_nb2 : ((lane + 1 < L0) ? __ldg(rec + 1 + lane) : kNone);
-            // Speculation (hints only): the buffer's new front is the most likely next expansion — fetch its link row now
-            // and start the vectors of its unvisited neighbours towards L2.
+            // the buffer's new front is the most likely next expansion: its link row rides along (a hint, no effect on results)
             uint32_t spec = kNone, nb2 = kNone, size2 = 0;
             if(n_b) spec = ~(uint32_t) warr_front(B);
             if(spec != kNone) {
@@ -719,58 +771,79 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
                 size2 = __ldg(rec2);
                 nb2 = (lane + 1 < L0) ? __ldg(rec2 + 1 + lane) : kNone;
             }
-            const bool use2 = n_v1 + 32 > kVisSmemLimit;          // warp-uniform: tier 1 frozen once it may pass 75 %
-            if(use2 && n_v2 + 32 > limit2) { overflow = true; break; }
-            const bool fresh = (lane < size) && vis_insert(vis1, vis2, mask2, nb, use2);
+            if(n_vis + 32 > limit2) { overflow = true; break; }
+            const bool fresh = (lane < size) && vis_test_and_set(cache, cmask, vis2, mask2, nb);
             uint32_t mask = __ballot_sync(0xffffffffu, fresh);
-            if(use2) n_v2 += __popc(mask); else n_v1 += __popc(mask);
-            // the filter functor of every fresh neighbour at once (one bitmap word per lane), ahead of the vector loads
+            n_vis += __popc(mask);
+            // the filter functor of every fresh neighbour at once (one bitmap word per lane), ahead of the vector copies
             const bool ok_mine = fresh && allowed(g, fbm, excl, n_excl, nb);
             const uint32_t ok_mask = __ballot_sync(0xffffffffu, ok_mine);
-            if(fresh && __popc(mask) > 2) {
-                const char* vp = reinterpret_cast<const char*>(g.vectors + (size_t) nb * dim);
-                for(uint32_t o = 0; o < dim * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(vp + o));
-            }
-            if(lane < size2 && nb2 < g.n_nodes && !vis_contains(vis1, vis2, mask2, nb2, n_v2 != 0)) {
-                const char* vp = reinterpret_cast<const char*>(g.vectors + (size_t) nb2 * dim);
-                for(uint32_t o = 0; o < dim * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(vp + o));
-            }
+            n_dist_acc += __popc(mask);
             while(mask) {
-                const int j0 = __ffs(mask) - 1; mask &= mask - 1;
-                int j1 = -1;
-                if(mask) { j1 = __ffs(mask) - 1; mask &= mask - 1; }
-                const uint32_t c0 = __shfl_sync(0xffffffffu, nb, j0);
-                const uint32_t c1 = j1 >= 0 ? __shfl_sync(0xffffffffu, nb, j1) : c0;
-                float d0, d1;
-                dot_two<NCH>(q, qs, g.vectors + (size_t) c0 * dim, g.vectors + (size_t) c1 * dim, dim, lane, d0, d1);
-                d0 = 1.0f - d0; d1 = 1.0f - d1;
-                n_dist_acc += j1 >= 0 ? 2 : 1;
-                // admission in neighbour order (every value below is warp-uniform)
+                // ---- up to RS fresh neighbours at a time: their rows are copied into the ring by the bulk-copy engine,
+                // all in flight together, completion counted in bytes on the warp's mbarrier
+                uint32_t grp = 0, cnt = 0;
+                while(mask && cnt < (uint32_t) RS) { grp |= mask & (0u - mask); mask &= mask - 1; cnt++; }
+                __syncwarp();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the ring's previous readers are done
+                if(lane == 0) mbar_expect_tx(bar, cnt * row_bytes);
+                __syncwarp();
+                if((grp >> lane) & 1u) {
+                    const uint32_t rs = __popc(grp & ((1u << lane) - 1u));
+                    bulk_g2s(ring_s + rs * row_bytes, g.vectors + (size_t) nb * dim, row_bytes, bar);
+                }
+                {
+                    uint32_t spins = 0;
+                    while(!mbar_try_wait(bar, parity)) { if(++spins > (1u << 28)) { __trap(); } }
+                    parity ^= 1u;
+                }
+                float dres[RS];
+                {
+                    float acc[RS][4];
 #pragma unroll
-                for(int t = 0; t < 2; t++) {
-                    if(t == 1 && j1 < 0) break;
-                    const float d = t ? d1 : d0;
-                    const uint32_t c = t ? c1 : c0;
-                    const bool ok = (ok_mask >> (t ? j1 : j0)) & 1;
-                    if(n_res < ef || lowerBound > d) {
-                        if(lane == 0) {   // the link row of a pushed candidate will be needed when it is expanded: start pulling it into L2
-                            const char* lp = reinterpret_cast<const char*>(g.links0 + (size_t) c * L0);
-                            asm volatile("prefetch.global.L2 [%0];" :: "l"(lp));
-                            asm volatile("prefetch.global.L2 [%0];" :: "l"(lp + 128));
+                    for(int r = 0; r < RS; r++) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+#pragma unroll
+                    for(int sgm = 0; sgm < NCH; sgm++) {
+#pragma unroll
+                        for(int r = 0; r < RS; r++) {
+                            if((uint32_t) r < cnt) {
+                                const float4 x = reinterpret_cast<const float4*>(ring + (size_t) r * dim + sgm * 128)[lane];
+                                acc[r][0] = __fmaf_rn(q.v[sgm].x, x.x, acc[r][0]); acc[r][1] = __fmaf_rn(q.v[sgm].y, x.y, acc[r][1]);
+                                acc[r][2] = __fmaf_rn(q.v[sgm].z, x.z, acc[r][2]); acc[r][3] = __fmaf_rn(q.v[sgm].w, x.w, acc[r][3]);
+                            }
                         }
-                        const unsigned long long ck = cand_key(d, c);
-                        // buffer unless a pooled key might be smaller: below the buffer's last, or nothing pooled and room left
-                        const unsigned long long bl = n_b ? warr_get(B, n_b - 1) : 0ull;
-                        if((n_p == 0 && n_b < kBufCap) || ck < bl) {
-                            const unsigned long long ev = warr_insert(B, ck, lane);
-                            if(n_b < kBufCap) n_b++;
-                            else { if(n_p < P.cand_cap) { if(lane == 0) pool[n_p] = ev; n_p++; } else overflow = true; }
-                        } else { if(n_p < P.cand_cap) { if(lane == 0) pool[n_p] = ck; n_p++; } else overflow = true; }
-                        if(ok) {       // push, then pop while over ef (hnswlib) == the insert drops the last when already full
-                            warr_insert(R, res_key(d, c), lane);
-                            if(n_res < ef) n_res++; else warr_set_inf(R, ef, lane);
+                    }
+#pragma unroll
+                    for(int r = 0; r < RS; r++) dres[r] = 1.0f - warp_tree(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                }
+                // ---- admission in neighbour order (every value below is warp-uniform)
+#pragma unroll
+                for(int r = 0; r < RS; r++) {
+                    if((uint32_t) r < cnt && !overflow) {
+                        const int src = __ffs(grp) - 1; grp &= grp - 1;
+                        const float d = dres[r];
+                        const uint32_t c = __shfl_sync(0xffffffffu, nb, src);
+                        const bool ok = (ok_mask >> src) & 1u;
+                        if(n_res < ef || lowerBound > d) {
+                            if(lane == 0) {   // the link row of a pushed candidate will be needed when it is expanded: start pulling it into L2
+                                const char* lp = reinterpret_cast<const char*>(g.links0 + (size_t) c * L0);
+                                asm volatile("prefetch.global.L2 [%0];" :: "l"(lp));
+                                asm volatile("prefetch.global.L2 [%0];" :: "l"(lp + 128));
+                            }
+                            const unsigned long long ck = cand_key(d, c);
+                            // buffer unless a pooled key might be smaller: below the buffer's last, or nothing pooled and room left
+                            const unsigned long long bl = n_b ? warr_get(B, n_b - 1) : 0ull;
+                            if((n_p == 0 && n_b < kBufCap) || ck < bl) {
+                                const unsigned long long ev = warr_insert(B, ck, lane);
+                                if(n_b < kBufCap) n_b++;
+                                else { if(n_p < P.cand_cap) { if(lane == 0) pool[n_p] = ev; n_p++; } else overflow = true; }
+                            } else { if(n_p < P.cand_cap) { if(lane == 0) pool[n_p] = ck; n_p++; } else overflow = true; }
+                            if(ok) {       // push, then pop while over ef (hnswlib) == the insert drops the last when already full
+                                warr_insert(R, res_key(d, c), lane);
+                                if(n_res < ef) n_res++; else warr_set_inf(R, ef, lane);
+                            }
+                            if(n_res) lowerBound = unord_f32((uint32_t) (warr_get(R, n_res - 1) >> 32));
                         }
-                        if(n_res) lowerBound = unord_f32((uint32_t) (warr_get(R, n_res - 1) >> 32));
                     }
                 }
                 if(overflow) break;
@@ -798,8 +871,9 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
         }
         if(lane == 0 && P.q_work) { P.q_work[2 * qi] = (uint32_t) (n_exp_acc - exp0); P.q_work[2 * qi + 1] = (uint32_t) (n_dist_acc - dist0); }
         __syncwarp();
-        if(n_v2) {
-            n_t2_acc++;
+        // ---- the table goes back to all-zero for the slot's next walk
+        {
+            if(n_vis > kVisSmemLimit) n_t2_acc++;
             uint4* z = reinterpret_cast<uint4*>(vis2);
             for(uint32_t i = lane; i < (P.vis2_slots >> 2); i += 32) z[i] = make_uint4(0, 0, 0, 0);
         }

@@ -57,7 +57,8 @@ struct QDesc {
     uint8_t  flags, match_type, num_query_tokens;
     uint8_t  field_weight[kMaxFieldSlots];
     uint8_t  filter_empty;             // filter given but matches no doc (src/index.cpp:4823-4826)
-    uint8_t  pad[3];
+    uint8_t  keep_all;                 // found_bitmap is the query's all_result_ids and outlives the call (facets, export)
+    uint8_t  pad[2];
 };
 
 struct CDesc {
@@ -926,7 +927,7 @@ wc_unit_kernel(const __grid_constant__ WcParams P) {
 // counted, so the bitmaps are all-zero again for the next call and no memset pass is needed. out_found[q] was zeroed by
 // kw_final_kernel.
 __global__ void __launch_bounds__(256)
-found_popcount_kernel(const QDesc* qd, const uint32_t* multi_q, uint32_t n_vec, uint32_t* out_found) {
+found_popcount_kernel(const QDesc* qd, const uint32_t* multi_q, uint32_t n_vec, uint32_t* out_found, int clear) {
     const uint32_t q = multi_q[blockIdx.x];
     uint4* bm = reinterpret_cast<uint4*>(qd[q].found_bitmap);
     const uint32_t per = (n_vec + gridDim.y - 1) / gridDim.y;
@@ -936,7 +937,7 @@ found_popcount_kernel(const QDesc* qd, const uint32_t* multi_q, uint32_t n_vec, 
         const uint4 w = bm[i];
         if(w.x | w.y | w.z | w.w) {
             c += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
-            bm[i] = make_uint4(0, 0, 0, 0);
+            if(clear) bm[i] = make_uint4(0, 0, 0, 0);
         }
     }
     for(int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);

@@ -19,6 +19,7 @@
 #include "fuse_kernels.cuh"
 #include "knn_kernels.cuh"
 #include "hnsw_build.cuh"
+#include "facet_kernels.cuh"
 #include "postings_pack.h"
 
 using namespace tsk;
@@ -125,6 +126,10 @@ struct tsgpu_index {
     tsv::HnswDev hnsw{};
     std::vector<void*> hnsw_alloc;
     std::vector<Filter> filters;
+    struct FacetMirror { tsfc::FacetDev dev{}; void* d_off = nullptr; void* d_vals = nullptr; };
+    std::vector<FacetMirror> facets;
+    std::vector<const uint32_t*> keep_bitmaps;      // per query of the last search: its all_result_ids bitmap (device) or nullptr
+    DevBuf d_keep_bm, d_facet;
     int n_sms = 148;
     // scratch
     DevBuf d_stage, d_pool, d_small, d_bitmaps, d_found_bm, d_out, d_knn_vis, d_knn_retry_vis, d_knn_retry_cand, d_knn_cand, d_knn_out, d_isect, d_kw_out;
@@ -155,7 +160,9 @@ struct KwPlan {
     std::vector<QDesc> qd;
     std::vector<CDesc> cd;
     std::vector<UDesc> ud;
-    std::vector<uint32_t> multi_q;        // queries whose found count needs the union bitmap
+    std::vector<uint32_t> multi_q;        // queries whose found count needs the union bitmap (cleared after counting)
+    std::vector<uint32_t> multi_keep_q;   // ... and whose bitmap is kept (all_result_ids for facets / export)
+    std::vector<uint32_t> keep_q;         // every query that keeps its all_result_ids bitmap
     std::vector<std::vector<MDesc>> levels;   // intermediate merge levels (only queries with many units)
     std::vector<MDesc*> d_levels;
     uint32_t n_units_total = 0;           // level-0 units + merge outputs
@@ -163,7 +170,7 @@ struct KwPlan {
     std::vector<uint32_t> q_nids;         // wildcard: ids per query
     size_t pool_slots = 0;
     // device views (valid after upload)
-    QDesc* d_qd = nullptr; CDesc* d_cd = nullptr; UDesc* d_ud = nullptr; uint32_t* d_multi_q = nullptr;
+    QDesc* d_qd = nullptr; CDesc* d_cd = nullptr; UDesc* d_ud = nullptr; uint32_t* d_multi_q = nullptr; uint32_t* d_multi_keep_q = nullptr;
     uint32_t* d_unit_cnt = nullptr; uint32_t* d_combo_matches = nullptr; unsigned long long* d_stats = nullptr;
     long long* d_q_thr = nullptr;
     std::vector<const uint32_t*> q_bitmap;   // per query filter bitmap (device) or nullptr
@@ -290,7 +297,8 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
                 qd.sort_col[i] = idx->sort_cols[col];
             }
         }
-        qd.flags = b->q_flags[q]; qd.match_type = b->q_match_type[q]; qd.num_query_tokens = b->q_num_query_tokens[q];
+        qd.flags = b->q_flags[q] & 0x7F; qd.match_type = b->q_match_type[q]; qd.num_query_tokens = b->q_num_query_tokens[q];
+        qd.keep_all = (b->q_flags[q] & TSGPU_QFLAG_KEEP_ALL_IDS) ? 1 : 0;
         for(uint32_t f = 0; f < (uint32_t) kMaxFieldSlots; f++) qd.field_weight[f] = f < F ? b->q_field_weight[(size_t) q * F + f] : 0;
         qd.n_excl = b->q_excl_off[q + 1] - b->q_excl_off[q];
         qd.combo_begin = with_combos ? b->q_combo_off[q] : 0;
@@ -329,7 +337,8 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
         }
         qd.unit_end = (uint32_t) pl.ud.size();
         q_units0.push_back({qd.unit_begin, qd.unit_end});
-        if(combos_with_tiles > 1) pl.multi_q.push_back(q);
+        if(qd.keep_all && !wildcard) { pl.keep_q.push_back(q); if(combos_with_tiles > 1) pl.multi_keep_q.push_back(q); }
+        else if(combos_with_tiles > 1) pl.multi_q.push_back(q);
         const int32_t fs = b->q_filter[q];
         if(fs >= 0 && (uint32_t) fs >= b->n_filters) return fail(TSGPU_ERR_INVALID, "inline filter slot out of range");
         if(fs <= -2) {
@@ -394,6 +403,11 @@ tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& p
         idx->found_dirty = true;
     }
     uint32_t* fbm = idx->d_found_bm.as<uint32_t>();
+    idx->keep_bitmaps.assign(nq, nullptr);
+    if(!pl.keep_q.empty()) {               // all_result_ids that outlive the call: their own buffer, zeroed per call
+        CU(idx->d_keep_bm.reserve(pl.keep_q.size() * fwords * 4));
+        CU(cudaMemsetAsync(idx->d_keep_bm.p, 0, pl.keep_q.size() * fwords * 4, st));
+    }
     Stager sg;
     const size_t n_excl_total = b->q_excl_off[nq];
     const size_t o_excl = sg.add(b->excl_ids, n_excl_total * 4);
@@ -404,6 +418,7 @@ tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& p
     const size_t o_cd = sg.reserve(pl.cd.size() * sizeof(CDesc));
     const size_t o_ud = sg.reserve(pl.ud.size() * sizeof(UDesc));
     const size_t o_mq = sg.reserve(pl.multi_q.size() * 4);
+    const size_t o_mk = sg.reserve(pl.multi_keep_q.size() * 4);
     std::vector<size_t> o_lv;
     for(auto& lv: pl.levels) o_lv.push_back(sg.add(lv.data(), lv.size() * sizeof(MDesc)));
     const size_t o_cnt = sg.reserve(((size_t) pl.n_units_total + pl.nc + 8) * 4 + 64);
@@ -433,10 +448,15 @@ tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& p
         qd.found_bitmap = nullptr;
     }
     for(size_t i = 0; i < pl.multi_q.size(); i++) pl.qd[pl.multi_q[i]].found_bitmap = fbm + i * fwords;
+    for(size_t i = 0; i < pl.keep_q.size(); i++) {
+        pl.qd[pl.keep_q[i]].found_bitmap = idx->d_keep_bm.as<uint32_t>() + i * fwords;
+        idx->keep_bitmaps[pl.keep_q[i]] = pl.qd[pl.keep_q[i]].found_bitmap;
+    }
     memcpy(sg.host.data() + o_qd, pl.qd.data(), pl.qd.size() * sizeof(QDesc));
     memcpy(sg.host.data() + o_cd, pl.cd.data(), pl.cd.size() * sizeof(CDesc));
     memcpy(sg.host.data() + o_ud, pl.ud.data(), pl.ud.size() * sizeof(UDesc));
     memcpy(sg.host.data() + o_mq, pl.multi_q.data(), pl.multi_q.size() * 4);
+    memcpy(sg.host.data() + o_mk, pl.multi_keep_q.data(), pl.multi_keep_q.size() * 4);
     memset(sg.host.data() + o_cnt, 0, ((size_t) pl.n_units_total + pl.nc + 8) * 4 + 64);
     for(uint32_t q = 0; q < nq; q++) reinterpret_cast<long long*>(sg.host.data() + o_thr)[q] = INT64_MIN;
     CU(idx->h_stage.reserve(sg.host.size()));
@@ -447,6 +467,7 @@ tsgpu_status upload_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan& p
     pl.d_cd = reinterpret_cast<CDesc*>(dbase + o_cd);
     pl.d_ud = reinterpret_cast<UDesc*>(dbase + o_ud);
     pl.d_multi_q = reinterpret_cast<uint32_t*>(dbase + o_mq);
+    pl.d_multi_keep_q = reinterpret_cast<uint32_t*>(dbase + o_mk);
     pl.d_levels.clear();
     for(size_t o: o_lv) pl.d_levels.push_back(reinterpret_cast<MDesc*>(dbase + o));
     unsigned char* cnt = dbase + ((o_cnt + 63) & ~size_t(63));
@@ -550,10 +571,16 @@ tsgpu_status run_keyword(tsgpu_index* idx, KwPlan& pl, uint32_t kv_stride, KwDev
         CU(cudaGetLastError());
         if(!pl.multi_q.empty()) {
             const uint32_t n_vec = (uint32_t) (((((size_t) idx->n_docs + 31) / 32) + 3) / 4);
-            found_popcount_kernel<<<dim3((unsigned) pl.multi_q.size(), 4), 256, 0, st>>>(pl.d_qd, pl.d_multi_q, n_vec, out.found);
+            found_popcount_kernel<<<dim3((unsigned) pl.multi_q.size(), 4), 256, 0, st>>>(pl.d_qd, pl.d_multi_q, n_vec, out.found, 1);
             idx->stats.launches_total++;
             CU(cudaGetLastError());
             idx->found_dirty = false;
+        }
+        if(!pl.multi_keep_q.empty()) {         // same count, bitmap left in place
+            const uint32_t n_vec = (uint32_t) (((((size_t) idx->n_docs + 31) / 32) + 3) / 4);
+            found_popcount_kernel<<<dim3((unsigned) pl.multi_keep_q.size(), 4), 256, 0, st>>>(pl.d_qd, pl.d_multi_keep_q, n_vec, out.found, 0);
+            idx->stats.launches_total++;
+            CU(cudaGetLastError());
         }
     }
     CU(cudaEventRecord(idx->ev[2], st));
@@ -570,9 +597,14 @@ void launch_hnsw(tsgpu_index* idx, const tsv::KnnParams& P, unsigned grid, size_
 }
 
 template <int NCH>
-void launch_walk(tsgpu_index* idx, const tsv::KnnParams& P, unsigned grid, size_t smem) {
-    cudaFuncSetAttribute(tsv::hnsw_walk_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024));
-    tsv::hnsw_walk_kernel<NCH><<<grid, tsv::kKnnThreads, smem, idx->vs>>>(idx->hnsw, P);
+void launch_walk(tsgpu_index* idx, const tsv::KnnParams& P, unsigned grid, size_t smem, int rs) {
+    if(NCH == 6 && rs == 2) {            // the 768-d build also exists with a two-row ring (more walks resident per SM)
+        cudaFuncSetAttribute(tsv::hnsw_walk_kernel<NCH == 6 ? 6 : 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024));
+        tsv::hnsw_walk_kernel<NCH == 6 ? 6 : 1, 2><<<grid, 32 * tsv::kWalkWarps, smem, idx->vs>>>(idx->hnsw, P);
+        return;
+    }
+    cudaFuncSetAttribute(tsv::hnsw_walk_kernel<NCH, tsv::kStageRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024));
+    tsv::hnsw_walk_kernel<NCH, tsv::kStageRows><<<grid, 32 * tsv::kWalkWarps, smem, idx->vs>>>(idx->hnsw, P);
 }
 
 // d_queries: [nq*dim] on device. q_bitmap/q_excl/q_nexcl/q_skip: host vectors (uploaded here). q_cost: optional per-query
@@ -592,17 +624,27 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     // register-resident queues (hnsw_walk_kernel) when they fit: max(ef,k) <= 128 and a link row per warp; TSGPU_KNN_HEAP=1
     // forces the general heap kernel (A/B runs)
     static const bool force_heap = getenv("TSGPU_KNN_HEAP") && atoi(getenv("TSGPU_KNN_HEAP")) == 1;
-    const bool walk = !force_heap && efe <= 32 * tsv::kResPerLane && 2 * g.M <= 32;
-    const size_t per_warp_smem = walk ? (size_t) tsv::kVisSmem * 4 : ((size_t) efe + 1 + tsv::kCandSmem) * 8 + (size_t) tsv::kVisSmem * 4;
     const uint32_t dim = g.dim;
     const int nch = (dim % 128 == 0 && dim / 128 <= 8 && dim / 128 != 5 && dim / 128 != 7) ? (int) (dim / 128) : 0;
+    const bool walk = !force_heap && efe <= 32 * tsv::kResPerLane && 2 * g.M <= 32 && nch > 0;
+    const unsigned wpc = walk ? (unsigned) tsv::kWalkWarps : 4u;                       // walks (warps) per CTA
+    // tuning knobs of the register-queue kernel (defaults are the measured best): rows staged per walk, visited-
+    // cache entries per walk, CTAs per SM
+    static const int env_rs = getenv("TSGPU_WALK_ROWS") ? atoi(getenv("TSGPU_WALK_ROWS")) : 0;
+    static const int env_cache = getenv("TSGPU_WALK_CACHE") ? atoi(getenv("TSGPU_WALK_CACHE")) : 0;
+    static const int env_ctas = getenv("TSGPU_WALK_CTAS") ? atoi(getenv("TSGPU_WALK_CTAS")) : 0;
+    const int rs = (env_rs == 2 && nch == 6) ? 2 : tsv::kStageRows;
+    const uint32_t vis_cache = env_cache >= 64 ? pow2_ceil((uint32_t) env_cache) : tsv::kVisCache;
+    const size_t per_warp_smem = walk ? (size_t) rs * dim * 4 + (size_t) vis_cache * 4
+                                      : ((size_t) efe + 1 + tsv::kCandSmem) * 8 + (size_t) tsv::kVisSmem * 4;
     const size_t q_bytes = nch ? 0 : (size_t) 4 * ((dim + 3) & ~3u) * 4;
-    const size_t smem = 4 * per_warp_smem + q_bytes;
+    const size_t smem = wpc * per_warp_smem + q_bytes + (walk ? 128 : 0);
     if(smem > 200 * 1024) return fail(TSGPU_ERR_CAPACITY, "max(ef,k) / dim too large for the per-query shared-memory heaps");
     const unsigned smem_blocks = (unsigned) std::max<size_t>(1, (size_t) (227 * 1024) / (smem + 1024));
-    const unsigned max_blocks = (unsigned) idx->n_sms * std::min(std::min(idx->knn_blocks_per_sm, smem_blocks), walk ? (unsigned) TSGPU_WALK_MIN_CTAS : 64u);
-    const unsigned grid = std::max(1u, std::min(max_blocks, (nq + 3) / 4));
-    const size_t slots = (size_t) grid * 4;
+    const unsigned max_blocks = walk ? (unsigned) idx->n_sms * std::min(smem_blocks, (unsigned) (env_ctas > 0 ? env_ctas : (rs == 2 ? 2 : 1) * TSGPU_WALK_MIN_CTAS))
+                                     : (unsigned) idx->n_sms * std::min(idx->knn_blocks_per_sm, smem_blocks);
+    const unsigned grid = std::max(1u, std::min(max_blocks, (nq + wpc - 1) / wpc));
+    const size_t slots = (size_t) grid * wpc;
     // per-warp scratch in HBM: tier 2 of the visited set (64 Ki keys: walks of up to 48 K visited nodes) and the overflow of
     // the candidate heap (with a selective filter hnswlib pushes every visited node until `ef` allowed results exist).
     // A walk that outgrows either is handed to the retry launch below, whose slots are sized for the whole graph.
@@ -674,6 +716,7 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     P.retry_n = reinterpret_cast<uint32_t*>(base + o_misc + 40);
     P.retry_list = reinterpret_cast<uint32_t*>(base + o_rl);
     P.q_work = reinterpret_cast<uint32_t*>(base + o_wk);
+    P.vis_cache = vis_cache;
     idx->knn_work_dev = P.q_work; idx->knn_work_n = nq;
     // the retry launch: the same kernel over the queries the first one handed back, one CTA whose four slots can hold a
     // walk over the whole graph. It reads its ticket count from device memory, so it is issued unconditionally (no host
@@ -687,13 +730,13 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     R.retry_list = reinterpret_cast<uint32_t*>(base + o_rl + (size_t) nq * 4);    // cannot be reached: nothing outgrows a full-size slot
     CU(cudaEventRecord(idx->ev[3], st));
     if(walk) switch(nch) {
-        case 1: launch_walk<1>(idx, P, grid, smem); launch_walk<1>(idx, R, 4, smem); break;
-        case 2: launch_walk<2>(idx, P, grid, smem); launch_walk<2>(idx, R, 4, smem); break;
-        case 3: launch_walk<3>(idx, P, grid, smem); launch_walk<3>(idx, R, 4, smem); break;
-        case 4: launch_walk<4>(idx, P, grid, smem); launch_walk<4>(idx, R, 4, smem); break;
-        case 6: launch_walk<6>(idx, P, grid, smem); launch_walk<6>(idx, R, 4, smem); break;
-        case 8: launch_walk<8>(idx, P, grid, smem); launch_walk<8>(idx, R, 4, smem); break;
-        default: launch_walk<0>(idx, P, grid, smem); launch_walk<0>(idx, R, 4, smem); break;
+        case 1: launch_walk<1>(idx, P, grid, smem, rs); launch_walk<1>(idx, R, 4, smem, rs); break;
+        case 2: launch_walk<2>(idx, P, grid, smem, rs); launch_walk<2>(idx, R, 4, smem, rs); break;
+        case 3: launch_walk<3>(idx, P, grid, smem, rs); launch_walk<3>(idx, R, 4, smem, rs); break;
+        case 4: launch_walk<4>(idx, P, grid, smem, rs); launch_walk<4>(idx, R, 4, smem, rs); break;
+        case 6: launch_walk<6>(idx, P, grid, smem, rs); launch_walk<6>(idx, R, 4, smem, rs); break;
+        case 8: launch_walk<8>(idx, P, grid, smem, rs); launch_walk<8>(idx, R, 4, smem, rs); break;
+        default: launch_walk<1>(idx, P, grid, smem, rs); launch_walk<1>(idx, R, 4, smem, rs); break;
     }
     else switch(nch) {
         case 1: launch_hnsw<1>(idx, P, grid, smem); launch_hnsw<1>(idx, R, 1, smem); break;
@@ -907,6 +950,8 @@ void tsgpu_index_destroy(tsgpu_index* idx) {
     for(auto* c: idx->sort_cols) cudaFree(c);
     for(void* p: idx->hnsw_alloc) cudaFree(p);
     for(auto& f: idx->filters) { if(f.d_bitmap) cudaFree(f.d_bitmap); if(f.d_ids) cudaFree(f.d_ids); }
+    for(auto& fm: idx->facets) { if(fm.d_off) cudaFree(fm.d_off); if(fm.d_vals) cudaFree(fm.d_vals); }
+    idx->d_keep_bm.release(); idx->d_facet.release();
     DevBuf* bufs[] = {&idx->d_stage, &idx->d_pool, &idx->d_small, &idx->d_bitmaps, &idx->d_found_bm, &idx->d_out, &idx->d_knn_vis,
                       &idx->d_knn_retry_vis, &idx->d_knn_retry_cand, &idx->d_knn_cand, &idx->d_knn_out, &idx->d_isect, &idx->d_kw_out};
     for(auto* b: bufs) b->release();
@@ -1046,6 +1091,7 @@ tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g) {
 }
 
 #include "hnsw_build_host.inc"
+#include "facet_host.inc"
 
 tsgpu_status tsgpu_filter_create(tsgpu_index* idx, const uint32_t* ids, size_t n, int32_t* out_handle) {
     tsgpu_status s = check_device(idx); if(s) return s;
@@ -1384,8 +1430,12 @@ tsgpu_status tsgpu_flat_distances(tsgpu_index* idx, const float* query, const ui
     return end_call(idx, false, true);
 }
 
+// keyword results handed in by the caller instead of computed here (tsgpu_hybrid_fuse_batch)
+struct GivenKw { const tsgpu_kv* kv; uint32_t stride; const uint32_t* count; const uint32_t* found; const uint32_t* searched; };
+
 static tsgpu_status vec_or_hybrid(tsgpu_index* idx, const tsgpu_kw_batch* b, const float* qvecs, const tsgpu_vec_params* vp,
-                                  tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found, bool hybrid) {
+                                  tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found, bool hybrid,
+                                  const GivenKw* given = nullptr) {
     tsgpu_status s = check_device(idx); if(s) return s;
     if(!b || !qvecs || !vp || !out_kv || !out_count || !out_found || kv_stride == 0) return fail(TSGPU_ERR_INVALID, "null argument");
     if(!idx->has_hnsw) return fail(TSGPU_ERR_INVALID, "no vector index loaded");
@@ -1422,11 +1472,25 @@ static tsgpu_status vec_or_hybrid(tsgpu_index* idx, const tsgpu_kw_batch* b, con
     // graph-walk CTAs then take the slots that free up (kw_search's tail, the small merge / final grids) and finish alone.
     // The other order lets the latency-bound walk hold half the register file while it uses a fifth of the memory system.
     static const bool kw_first = !(getenv("TSGPU_KW_FIRST") && atoi(getenv("TSGPU_KW_FIRST")) == 0);
-    if(hybrid && kw_first) { s = run_keyword(idx, pl, std::max(kv_stride, pl.KMAX), kwo); if(s) return s; }
+    if(given) {
+        // the keyword stage already ran (several rounds of it, on the host's schedule): its final Topster content comes in
+        const size_t kvb = (size_t) nq * given->stride * sizeof(KVOut);
+        CU(idx->d_kw_out.reserve(kvb + (size_t) nq * 12 + 64));
+        kwo.kv = idx->d_kw_out.as<KVOut>();
+        kwo.count = reinterpret_cast<uint32_t*>(idx->d_kw_out.as<unsigned char>() + ((kvb + 15) & ~size_t(15)));
+        kwo.found = kwo.count + nq; kwo.searched = kwo.found + nq; kwo.stride = given->stride;
+        CU(cudaMemcpyAsync(kwo.kv, given->kv, kvb, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(kwo.count, given->count, (size_t) nq * 4, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(kwo.found, given->found, (size_t) nq * 4, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(kwo.searched, given->searched, (size_t) nq * 4, cudaMemcpyDefault, st));
+        idx->stats.h2d_bytes += kvb + (size_t) nq * 12;
+        CU(cudaEventRecord(idx->ev[1], st)); CU(cudaEventRecord(idx->ev[6], st)); CU(cudaEventRecord(idx->ev[2], st));
+    }
+    else if(hybrid && kw_first) { s = run_keyword(idx, pl, std::max(kv_stride, pl.KMAX), kwo); if(s) return s; }
     s = run_vector_stage(idx, b, pl, qvecs, vp, k, vs); if(s) return s;
     if(hybrid) {
         CU(cudaEventRecord(idx->evB, idx->stream2));
-        if(!kw_first) { s = run_keyword(idx, pl, std::max(kv_stride, pl.KMAX), kwo); if(s) return s; }
+        if(!kw_first && !given) { s = run_keyword(idx, pl, std::max(kv_stride, pl.KMAX), kwo); if(s) return s; }
         CU(cudaStreamWaitEvent(st, idx->evB, 0));
     }
     // final assembly
@@ -1483,7 +1547,7 @@ static tsgpu_status vec_or_hybrid(tsgpu_index* idx, const tsgpu_kw_batch* b, con
     idx->stats.ms_fuse = ms; idx->stats.ms_kernels += ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if(s) return s;
-    if(hybrid) return fetch_kw_stats(idx, pl);
+    if(hybrid && !given) return fetch_kw_stats(idx, pl);
     return TSGPU_OK;
 }
 
@@ -1506,6 +1570,15 @@ tsgpu_status tsgpu_debug_knn_work(tsgpu_index* idx, uint32_t* out, uint32_t cap_
     if(n) CU(cudaMemcpy(out, idx->knn_work_dev, (size_t) n * 8, cudaMemcpyDeviceToHost));
     *out_n = n;
     return TSGPU_OK;
+}
+
+tsgpu_status tsgpu_hybrid_fuse_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const tsgpu_kv* kw_kv, uint32_t kw_stride, const uint32_t* kw_count,
+                                     const uint32_t* kw_found, const uint32_t* kw_searched, const float* qvecs, const tsgpu_vec_params* vp,
+                                     tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {
+    if(!kw_kv || !kw_count || !kw_found || !kw_searched || kw_stride == 0) return fail(TSGPU_ERR_INVALID, "null argument");
+    if(b) for(uint32_t q = 0; q < b->n_queries; q++) if(kw_count[q] > kw_stride || kw_count[q] > b->q_topk[q]) return fail(TSGPU_ERR_INVALID, "kw_count exceeds kw_stride / topk");
+    const GivenKw g{kw_kv, kw_stride, kw_count, kw_found, kw_searched};
+    return vec_or_hybrid(idx, b, qvecs, vp, out_kv, kv_stride, out_count, out_found, true, &g);
 }
 
 tsgpu_status tsgpu_get_stats(tsgpu_index* idx, tsgpu_stats* out) {

@@ -299,6 +299,7 @@ public:
     void clear_walk_cache() { std::lock_guard<std::mutex> lk(cache_mu); walk_cache.clear(); }
 private:
     std::unordered_map<std::string, std::vector<int64_t>> sort_values;
+    std::map<int32_t, std::vector<uint64_t>> host_filters;        // persistent filters: handle -> one bit per doc
     std::string default_sorting_field;
     std::string err;
 public:
@@ -340,6 +341,42 @@ public:
         arts_ready.assign(arts_ready.size(), 0);
         return Option<uint32_t>(fid);
     }
+    // The same mirror from arrays that already are in the flat form tsgpu_index_load_field takes (list l = tokens[l]; lists in any
+    // order; ids ascending inside a list): what a binding that walks the live art_tree / posting lists hands over, and what a
+    // 10 M-document collection needs (the per-token std::map of field_mirror_t is a test convenience).
+    Option<uint32_t> add_field_flat(const std::string& name, std::vector<std::string> tokens, std::vector<uint64_t> list_off, std::vector<uint32_t> ids,
+                                    const uint64_t* pos_off, const uint32_t* positions, bool is_array = false) {
+        if(tokens.size() + 1 != list_off.size()) return Option<uint32_t>(400, "list_off must have one entry per token plus one");
+        tsgpu_field tf{(uint32_t) tokens.size(), is_array ? 1u : 0u, list_off.data(), ids.data(), pos_off, positions};
+        uint32_t fid = 0;
+        if(tsgpu_index_load_field(h, &tf, &fid) != TSGPU_OK) return Option<uint32_t>(500, tsgpu_last_error());
+        field_ids[name] = fid;
+        if(token_ids.size() <= fid) token_ids.resize(fid + 1);
+        if(vocabs.size() <= fid) vocabs.resize(fid + 1);
+        token_ids[fid].clear();
+        token_ids[fid].reserve(tokens.size());
+        for(uint32_t l = 0; l < tokens.size(); l++) token_ids[fid][tokens[l]] = l;
+        vocabs[fid].tokens = std::move(tokens);
+        vocabs[fid].list_off = std::move(list_off);
+        vocabs[fid].ids = std::move(ids);
+        if(arts.size() <= fid) { arts.resize(fid + 1); arts_ready.resize(fid + 1, 0); arts_on_device.resize(fid + 1, 0); }
+        arts_ready.assign(arts_ready.size(), 0);
+        return Option<uint32_t>(fid);
+    }
+    // A filter_by result kept on the device (tsgpu_filter_create) with its host-side bit set: searches name it by handle, the
+    // device applies it, and the host uses the bits where the reference consults the filter while it picks candidate tokens
+    // (validate_and_add_leaf: a token must hold a document of the filter, src/art.cpp:1016-1036).
+    Option<int32_t> add_filter(const std::vector<uint32_t>& sorted_ids) {
+        int32_t handle = 0;
+        if(tsgpu_filter_create(h, sorted_ids.empty() ? nullptr : sorted_ids.data(), sorted_ids.size(), &handle) != TSGPU_OK) return Option<int32_t>(500, tsgpu_last_error());
+        std::vector<uint64_t> bits(((size_t) n_docs + 63) / 64, 0);
+        for(uint32_t id: sorted_ids) if(id < n_docs) bits[id >> 6] |= 1ull << (id & 63);
+        std::lock_guard<std::mutex> lk(cache_mu);
+        host_filters[handle] = std::move(bits);
+        return Option<int32_t>(handle);
+    }
+    tsgpu_index* handle() const { return h; }
+
     // sort_index[field] (spp::sparse_hash_map<uint32, int64>): docs without a value sort as INT64_MIN
     Option<uint32_t> add_sort_field(const std::string& name, const std::unordered_map<uint32_t, int64_t>& values) {
         std::vector<int64_t> dense(n_docs, INT64_MIN);
@@ -350,6 +387,15 @@ public:
         sort_values[name] = dense;
         arts_ready.assign(arts_ready.size(), 0);             // leaf max_score comes from the default sorting field
         if(default_sorting_field.empty()) default_sorting_field = name;      // the schema's default_sorting_field
+        return Option<uint32_t>(col);
+    }
+    Option<uint32_t> add_sort_field_dense(const std::string& name, const int64_t* dense_values) {      // [n_docs], INT64_MIN = no value
+        uint32_t col = 0;
+        if(tsgpu_index_load_sort_column(h, dense_values, &col) != TSGPU_OK) return Option<uint32_t>(500, tsgpu_last_error());
+        sort_cols[name] = col;
+        sort_values[name].assign(dense_values, dense_values + n_docs);
+        arts_ready.assign(arts_ready.size(), 0);
+        if(default_sorting_field.empty()) default_sorting_field = name;
         return Option<uint32_t>(col);
     }
     Option<bool> add_vector_field(const tsgpu_hnsw& g) {
@@ -432,7 +478,15 @@ public:
                                    text_match_type, syn_orig_num_tokens, orig_num_tokens, is_synonym_query, demote_synonym_match);
         // one device call for this query alone — or, inside multi_search, for this query together with the pending query of every
         // other search of the request list
-        if(lockstep()) lockstep()->submit_and_wait(q);
+        if(replay_t* r = replay()) {
+            q.filter_handle = r->filter_handle;
+            if(r->filter_handle <= -2) { q.has_filter = false; q.filter_ids.clear(); }
+            if(r->next < r->answers.size()) {                    // this round was answered in an earlier pass
+                const kw_query& a = r->answers[r->next++];
+                q.status = a.status; q.kvs = a.kvs; q.count = a.count; q.found = a.found; q.done = true;
+            } else { r->pending = std::move(q); r->has_pending = true; throw replay_suspend(); }
+        }
+        else if(lockstep()) lockstep()->submit_and_wait(q);
         else { std::vector<kw_query*> one{&q}; run_kw_batch(one); }
         if(!q.status.ok()) return q.status;
         for(uint32_t i = 0; i < q.count; i++) topster.add(q.kvs[i]);
@@ -530,6 +584,7 @@ public:
         std::vector<uint8_t> c_nreq, c_flags, field_weights;
         std::vector<int32_t> c_syn, c_orig;
         bool has_filter = false;
+        int32_t filter_handle = -1;          // <= -2: a persistent device filter (tsgpu_filter_create) instead of inline ids
         uint32_t topk = 250;
         uint8_t sort_type[3] = {0, 0, 0}, missing_first[3] = {0, 0, 0}, flags = 0, match_type = 0, nqt = 0;
         int32_t sort_col[3] = {-1, -1, -1};
@@ -556,7 +611,8 @@ public:
             for(auto* q: qs) {
                 const uint32_t nc = (uint32_t) q->c_nreq.size();
                 q_combo_off.push_back(q_combo_off.back() + nc);
-                if(q->has_filter) { q_filter.push_back((int32_t) n_filters++); filter_ids.insert(filter_ids.end(), q->filter_ids.begin(), q->filter_ids.end()); filter_off.push_back(filter_ids.size()); }
+                if(q->filter_handle <= -2) q_filter.push_back(q->filter_handle);
+                else if(q->has_filter) { q_filter.push_back((int32_t) n_filters++); filter_ids.insert(filter_ids.end(), q->filter_ids.begin(), q->filter_ids.end()); filter_off.push_back(filter_ids.size()); }
                 else q_filter.push_back(-1);
                 excl.insert(excl.end(), q->excl.begin(), q->excl.end());
                 q_excl_off.push_back((uint32_t) excl.size());
@@ -640,6 +696,26 @@ public:
         }
     };
     static lockstep_t*& lockstep() { static thread_local lockstep_t* l = nullptr; return l; }
+
+    struct walk_request { std::string token; int cost; bool prefix; };
+    // multi_search without a thread per request: REPLAY. A request's search is a deterministic function of its inputs and of
+    // the device's answers, so it can simply be run again: a pass runs every unfinished search from its start on a small pool
+    // of worker threads; where a search needs a device answer it does not have yet (a keyword round, a candidate walk) it
+    // records the question and unwinds (replay_suspend). After the pass all recorded questions go to the device as ONE walk
+    // batch per field and ONE keyword batch per searched-field set; the next pass replays the recorded answers and runs on.
+    // Passes needed = the longest search's number of device rounds (+1 per walk round); host work per pass is the
+    // (cheap) control flow of the searches still running. No baton, no 4096 threads.
+    struct replay_suspend {};
+    struct replay_t {
+        std::vector<kw_query> answers;       // this request's answered keyword rounds, in call order
+        size_t next = 0;
+        kw_query pending;
+        bool has_pending = false;
+        std::vector<std::pair<uint32_t, walk_request>> pending_walks;
+        int32_t filter_handle = -1;
+        kw_query executed;                   // every combination the request's rounds ran (the hybrid tail probes them)
+    };
+    static replay_t*& replay() { static thread_local replay_t* r = nullptr; return r; }
 
     // ids of `field` holding the tokens as a phrase (a single token: its posting list); false when a token is unknown
     Option<bool> phrase_ids_of(const std::string& field, const std::vector<std::string>& phrase, std::vector<uint32_t>& out, bool& all_known) {
@@ -865,7 +941,6 @@ public:
     // One tsgpu_art_walk_batch for a list of (token, cost, prefix) searches on one field; the hit lists land in walk_cache.
     // A walk depends on nothing but these three — not on the tokens already taken, the previous token or a filter, which
     // only enter art_mirror_t::finish — so walks may be fetched ahead of the control flow that may or may not need them.
-    struct walk_request { std::string token; int cost; bool prefix; };
     void device_walks(uint32_t fid, const std::vector<walk_request>& reqs) const {
         const art_mirror_t& art = art_of(fid);
         if(art.empty || reqs.empty()) return;
@@ -919,16 +994,27 @@ public:
         const vocab_t& v = vocabs[fid];
         const art_mirror_t& art = art_of(fid);
         art_mirror_t::doc_tests docs;
+        const std::vector<uint64_t>* fbits = nullptr;              // the request's persistent filter (multi_search), if any
+        if(replay_t* r = replay()) if(r->filter_handle <= -2) { auto it = host_filters.find(r->filter_handle); if(it != host_filters.end()) fbits = &it->second; }
+        auto in_filter = [&](uint32_t id) { return !fbits || (((*fbits)[id >> 6] >> (id & 63)) & 1ull); };
+        if(fbits) {
+            docs.filter_active = true;
+            docs.has_filter_doc = [&](uint32_t l) { for(uint64_t i = v.list_off[l]; i < v.list_off[l + 1]; i++) if(in_filter(v.ids[i])) return true; return false; };
+        }
         docs.share_doc = [&](uint32_t a, uint32_t c) {
             uint64_t i = v.list_off[a], ie = v.list_off[a + 1], j = v.list_off[c], je = v.list_off[c + 1];
-            while(i < ie && j < je) { if(v.ids[i] == v.ids[j]) return true; if(v.ids[i] < v.ids[j]) i++; else j++; }
+            while(i < ie && j < je) { if(v.ids[i] == v.ids[j]) { if(in_filter(v.ids[i])) return true; i++; j++; } else if(v.ids[i] < v.ids[j]) i++; else j++; }
             return false;
         };
         std::vector<int32_t> hits;
         bool walked = false;
-        if(o.device_art_walk && !art.empty) {
+        if(o.device_art_walk && !art.empty && !(replay() && cost == 0)) {      // batched multi_search: a cost-0 walk is one descent, cheaper on the host
             const walk_key key = std::make_tuple(fid, prefix_search, cost, token);
             walked = cached_walk(key, hits);
+            if(!walked && replay()) {                 // batched multi_search: ask for it and come back in the next pass
+                replay()->pending_walks.push_back({fid, {token, cost, prefix_search}});
+                throw replay_suspend();
+            }
             if(!walked) {                             // not speculated by prefetch_walks: fetch this one search
                 device_walks(fid, {{token, cost, prefix_search}});
                 walked = cached_walk(key, hits);
@@ -952,6 +1038,8 @@ public:
         std::vector<uint32_t> excluded;
         std::vector<uint32_t> filter_ids;      // phrase ids (do_phrase_search) restricting the keyword search
         bool filter_by_provided = false;
+        int32_t filter_handle = -1;            // persistent filter of the request (multi_search): the device applies it, the host tests leaves with it
+        size_t rounds_with_results = 0, found_of_round = 0;     // device `found` of the keyword rounds (exact when one round matched)
         std::vector<uint8_t> weights;
         int syn_orig_num_tokens = -1, orig_num_tokens = -1;     // as passed to fuzzy_search_fields for the running query variant
         bool is_synonym_query = false;
@@ -993,6 +1081,7 @@ public:
                                        st.syn_orig_num_tokens, st.orig_num_tokens, st.is_synonym_query, o.demote_synonym_match);
         if(!op.ok()) return op;
         for(auto& kv: round.sort()) { st.topster.add(kv); st.all_result_ids.insert((uint32_t) kv.key); }
+        if(nf) { st.rounds_with_results++; st.found_of_round = nf; }
         return Option<bool>(true);
     }
 
@@ -1002,7 +1091,7 @@ public:
                                      const std::vector<std::string>& the_fields, const std::vector<sort_by>& sort_fields,
                                      size_t topster_size, const search_options& o, search_state& st) {
         if(query_tokens.empty()) return Option<bool>(true);
-        if(o.device_art_walk) prefetch_walks(query_tokens, the_fields, o);
+        if(o.device_art_walk && !replay()) prefetch_walks(query_tokens, the_fields, o);
         std::vector<std::vector<int>> token_to_costs;
         for(auto& t: query_tokens) {
             std::vector<int> all;
@@ -1131,7 +1220,9 @@ public:
             if(!dop.ok()) return dop;
         }
         raw_result_kvs = st.topster.sort();
-        found = st.all_result_ids.size();
+        // all_result_ids_len: the device counts a round's matches exactly; the union over SEVERAL matching rounds is only known
+        // through the ids the Topsters kept (a lower bound, exact below the Topster size)
+        found = st.rounds_with_results == 1 ? st.found_of_round : st.all_result_ids.size();
         return Option<bool>(true);
     }
 
@@ -1193,6 +1284,158 @@ public:
             for(auto& t: threads) t.join();
         }
         return out;
+    }
+
+    // ---- batched multi_search (replay; see replay_t). A request may carry a persistent filter (add_filter) and a vector query:
+    // the keyword flow runs to its end first — exactly as Index::search does before it looks at the vector query
+    // (src/index.cpp:4036) — then every hybrid request's final keyword Topster goes, together, through ONE
+    // tsgpu_hybrid_fuse_batch (graph walk + reciprocal rank fusion on the device).
+    struct batched_request {
+        search_request r;
+        int32_t filter_handle = -1;
+        const float* query_vector = nullptr;     // nullptr: keyword only
+        tsgpu_vec_params vp{0, 10, 0, 3.4028234663852886e38f, 0.3f, 10};
+    };
+    struct batched_stats { size_t passes = 0, kw_batches = 0, kw_queries = 0, walk_batches = 0, walks = 0, host_walk_fallbacks = 0, fuse_queries = 0; };
+    std::vector<search_response> multi_search_batched(const std::vector<batched_request>& requests, size_t n_threads = 0, batched_stats* stats = nullptr) {
+        const size_t n = requests.size();
+        std::vector<search_response> out(n);
+        std::vector<replay_t> rs(n);
+        std::vector<char> done(n, 0);
+        std::vector<size_t> active(n);
+        for(size_t i = 0; i < n; i++) { active[i] = i; rs[i].filter_handle = requests[i].filter_handle; }
+        if(n_threads == 0) n_threads = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), 32));
+        batched_stats bs;
+        auto run_one = [&](size_t i) {
+            replay_t& r = rs[i];
+            r.next = 0; r.has_pending = false; r.pending_walks.clear();
+            replay() = &r;
+            const auto& q = requests[i].r;
+            try {
+                out[i].status = search(q.tokens, q.the_fields, q.sort_fields, q.drop_tokens_threshold, q.topster_size, out[i].raw_result_kvs, out[i].found, q.opts);
+                done[i] = 1;
+            }
+            catch(const replay_suspend&) {}
+            catch(const std::exception& e) { out[i].status = Option<bool>(400, e.what()); done[i] = 1; }
+            replay() = nullptr;
+        };
+        while(!active.empty()) {
+            bs.passes++;
+            // ---- one pass over the unfinished searches
+            std::atomic<size_t> cursor{0};
+            auto worker = [&] { for(;;) { const size_t k = cursor.fetch_add(1); if(k >= active.size()) break; run_one(active[k]); } };
+            const size_t nt = std::min(n_threads, active.size());
+            if(nt <= 1) worker();
+            else { std::vector<std::thread> th; for(size_t t = 0; t < nt; t++) th.emplace_back(worker); for(auto& t: th) t.join(); }
+            // ---- candidate walks asked for in this pass: one device batch per field
+            std::map<uint32_t, std::vector<walk_request>> per_field;
+            std::set<walk_key> asked;
+            for(size_t i: active) for(auto& pw: rs[i].pending_walks) {
+                const walk_key key = std::make_tuple(pw.first, pw.second.prefix, pw.second.cost, pw.second.token);
+                if(!has_walk(key) && asked.insert(key).second) per_field[pw.first].push_back(pw.second);
+            }
+            for(auto& pf: per_field) {
+                device_walks(pf.first, pf.second);
+                bs.walk_batches++; bs.walks += pf.second.size();
+                for(auto& w: pf.second) {                      // a search the device flagged (long term, deep stack): the host walk answers it
+                    const walk_key key = std::make_tuple(pf.first, w.prefix, w.cost, w.token);
+                    if(has_walk(key)) continue;
+                    auto hits = art_of(pf.first).walk_hits(w.token, w.cost, w.cost, w.prefix);
+                    std::lock_guard<std::mutex> lk(cache_mu);
+                    walk_cache[key] = std::move(hits);
+                    bs.host_walk_fallbacks++;
+                }
+            }
+            // ---- keyword rounds asked for in this pass: one device batch per searched-field set
+            std::map<std::vector<uint32_t>, std::vector<size_t>> groups;
+            for(size_t i: active) if(rs[i].has_pending) groups[rs[i].pending.fids].push_back(i);
+            for(auto& g: groups) {
+                std::vector<kw_query*> qs;
+                for(size_t i: g.second) qs.push_back(&rs[i].pending);
+                run_kw_batch(qs);
+                bs.kw_batches++; bs.kw_queries += qs.size();
+                for(size_t i: g.second) {
+                    replay_t& r = rs[i];
+                    append_combos(r.executed, r.pending);
+                    r.answers.push_back(std::move(r.pending));
+                    r.has_pending = false;
+                }
+            }
+            std::vector<size_t> still;
+            for(size_t i: active) if(!done[i]) still.push_back(i);
+            active.swap(still);
+        }
+        // ---- hybrid tail: vector stage + rank fusion for every request that carries a vector query
+        std::vector<size_t> hyb;
+        for(size_t i = 0; i < n; i++) if(requests[i].query_vector && out[i].status.ok()) hyb.push_back(i);
+        std::map<std::vector<uint32_t>, std::vector<size_t>> hgroups;        // same searched fields, same vector parameters per call
+        for(size_t i: hyb) {
+            std::vector<uint32_t> key = rs[i].executed.fids;
+            if(key.empty()) for(auto& fn: requests[i].r.the_fields) key.push_back(field_ids.at(fn));
+            hgroups[key].push_back(i);
+        }
+        for(auto& g: hgroups) {
+            const auto& ids = g.second;
+            const size_t m = ids.size();
+            uint32_t dim = 0;
+            tsgpu_index_hnsw_info(h, nullptr, &dim, nullptr, nullptr, nullptr, nullptr, nullptr);
+            std::vector<kw_query> qv(m);
+            std::vector<kw_query*> qs(m);
+            uint32_t stride_in = 1;
+            for(size_t k = 0; k < m; k++) {
+                const size_t i = ids[k];
+                const auto& rq = requests[i].r;
+                const std::vector<uint8_t> w = process_search_field_weights(rq.the_fields.size(), rq.opts.query_by_weights);
+                qv[k] = make_kw_query({}, 0, {}, rq.the_fields, w, rq.sort_fields, {}, false, {}, rq.topster_size, rq.opts.prioritize_exact_match,
+                                      rq.opts.prioritize_token_position, rq.opts.prioritize_num_matching_fields, rq.opts.text_match_type, -1, -1, false, false);
+                append_combos(qv[k], rs[i].executed);
+                qv[k].nqt = (uint8_t) rq.tokens.size();
+                qv[k].filter_handle = requests[i].filter_handle;
+                qs[k] = &qv[k];
+                stride_in = std::max<uint32_t>(stride_in, (uint32_t) out[i].raw_result_kvs.size());
+            }
+            kw_batch_storage st(qs);
+            std::vector<KV> kw((size_t) m * stride_in);
+            std::vector<uint32_t> kw_count(m), kw_found(m), kw_searched(m);
+            std::vector<float> vecs((size_t) m * dim);
+            for(size_t k = 0; k < m; k++) {
+                const size_t i = ids[k];
+                std::copy(out[i].raw_result_kvs.begin(), out[i].raw_result_kvs.end(), kw.begin() + k * stride_in);
+                kw_count[k] = (uint32_t) out[i].raw_result_kvs.size(); kw_found[k] = (uint32_t) out[i].found;
+                kw_searched[k] = (uint32_t) rs[i].executed.c_nreq.size();
+                std::copy(requests[i].query_vector, requests[i].query_vector + dim, vecs.begin() + k * dim);
+            }
+            const uint32_t stride = st.stride;
+            std::vector<KV> okv((size_t) m * stride);
+            std::vector<uint32_t> ocount(m), ofound(m);
+            const tsgpu_vec_params vp = requests[ids[0]].vp;
+            if(tsgpu_hybrid_fuse_batch(h, &st.b, kw.data(), stride_in, kw_count.data(), kw_found.data(), kw_searched.data(), vecs.data(), &vp,
+                                       okv.data(), stride, ocount.data(), ofound.data()) != TSGPU_OK) {
+                const Option<bool> e(500, tsgpu_last_error());
+                for(size_t i: ids) out[i].status = e;
+                continue;
+            }
+            bs.fuse_queries += m;
+            for(size_t k = 0; k < m; k++) {
+                out[ids[k]].raw_result_kvs.assign(okv.begin() + k * stride, okv.begin() + k * stride + ocount[k]);
+                out[ids[k]].found = ofound[k];
+            }
+        }
+        if(stats) *stats = bs;
+        return out;
+    }
+    // the combinations of `src` appended to `dst` (same searched fields)
+    static void append_combos(kw_query& dst, const kw_query& src) {
+        if(dst.fids.empty()) dst.fids = src.fids;
+        if(dst.c_tok_off.empty()) dst.c_tok_off = {0};
+        const uint32_t row0 = dst.c_tok_off.back();
+        for(size_t c = 0; c + 1 < src.c_tok_off.size(); c++) dst.c_tok_off.push_back(row0 + src.c_tok_off[c + 1]);
+        dst.t_list.insert(dst.t_list.end(), src.t_list.begin(), src.t_list.end());
+        dst.c_cost.insert(dst.c_cost.end(), src.c_cost.begin(), src.c_cost.end());
+        dst.c_nreq.insert(dst.c_nreq.end(), src.c_nreq.begin(), src.c_nreq.end());
+        dst.c_flags.insert(dst.c_flags.end(), src.c_flags.begin(), src.c_flags.end());
+        dst.c_syn.insert(dst.c_syn.end(), src.c_syn.begin(), src.c_syn.end());
+        dst.c_orig.insert(dst.c_orig.end(), src.c_orig.begin(), src.c_orig.end());
     }
 
     // the drop-tokens loop of Index::search (src/index.cpp:3920-4017) for one query variant
