@@ -142,6 +142,7 @@ def build_workload(args, device, rank, need_host_copy):
     g = torch.Generator(device="cpu"); g.manual_seed(17)
     w.cat = torch.randint(0, 10, (args.docs,), generator=g).numpy().astype(np.int32)
     w.filters = [np.nonzero(w.cat == c)[0].astype(np.uint32) for c in range(10)]
+    w.words = synth.vocab_words(args.vocab)               # token rank -> its string (the host layer searches strings)
     log(f"rank{rank}: postings {len(fd.flat.ids)/1e6:.1f}M in {time.time()-t0:.1f}s")
     w.graph_host = None
     w.vec_dev = None
@@ -251,41 +252,40 @@ def attach_vector_index(args, w, gi, rank, need_host_copy):
     return host
 
 
+TYPO_FRACTION = 0.30
+
+
 def make_batches(args, w, n_batches, rank):
-    """Resolved query batches (what the host hands over after tokenising + candidate generation)."""
-    from typesense_b200 import structs as S, synth
-    import torch
+    """Query batches in both forms. STRINGS (what a client sends, what the end-to-end leg and the CPU arm search): three tokens of
+    a random document, in 30 % of the queries one token misspelt by one substituted letter (never a vocabulary word itself), half of
+    the queries with `cat:=c`, plus a query vector. RESOLVED (what the device-resident leg times: the C-ABI's input after the host's
+    tokenising and candidate search): the same queries as one combination of the corrected tokens, total_cost 2 where a typo was
+    fixed — the combination the reference's fuzzy_search_fields arrives at for these strings."""
+    from typesense_b200 import hostapi, structs as S, synth
     rng = np.random.default_rng(1000 + rank)
     out = []
-    df = np.diff(w.fd.flat.list_off.astype(np.int64))
+    taken = set(w.words)
+    sort = ((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_NUMERIC, 0, 1, 0), (S.SORT_NONE, -1, 1, 0))
     for bi in range(n_batches):
         toks = synth.sample_queries(w.fd, args.batch, 3, int(rng.integers(0, 1 << 30)))
-        qs = []
+        qs, strings, filt = [], [], np.full(args.batch, -1, np.int32)
         for i in range(args.batch):
             row = [int(t) for t in toks[i]]
-            combos = [S.Combo([[t] for t in row], 3)]
-            if rng.random() < 0.30:
-                # typo on one term: the host's fuzzy lookup returns up to max_candidates=4 tokens at cost 1; the
-                # original term is one of them, the others are vocabulary neighbours (other words of similar rank)
+            words = [w.words[t] for t in row]
+            cost = 0
+            if rng.random() < TYPO_FRACTION:
                 j = int(rng.integers(0, 3))
-                cands = [row[j]]
-                while len(cands) < 4:
-                    c = int(np.clip(row[j] + rng.integers(-50, 51), 0, args.vocab - 1))
-                    if c not in cands and df[c] > 0:
-                        cands.append(c)
-                combos = []
-                for c in cands:
-                    r2 = list(row); r2[j] = c
-                    combos.append(S.Combo([[t] for t in r2], 3, total_cost=2))
-            q = S.Query(combos, topk=250, num_query_tokens=3,
-                        sort=((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_NUMERIC, 0, 1, 0), (S.SORT_NONE, -1, 1, 0)))
+                words[j] = synth.misspell(words[j], rng, taken)
+                cost = 2                                  # next_suggestion2: 2 * typo cost of the corrected token
+            q = S.Query([S.Combo([[t] for t in row], 3, total_cost=cost)], topk=250, num_query_tokens=3, sort=sort)
             if i % 2 == 1:
                 q.filter = int(rng.integers(0, 10))
-            qs.append(q)
+                filt[i] = q.filter
+            qs.append(q); strings.append(words)
         b = S.KwBatch(qs, [0], w.filters)
         qv = (synth.make_vectors_clustered(args.batch, args.dim, w.n_clusters, seed=4321 + 97 * rank + bi, centers_seed=1234, spread=0.35)[0].numpy()
               if args.workload != "keyword10m" else None)
-        out.append((b, qv))
+        out.append((b, qv, {"strings": strings, "packed": hostapi.pack_queries(strings), "filter": filt}))
     return out
 
 
@@ -296,12 +296,45 @@ def kw_algorithmic_bytes(b, flat, matches):
     return int(4 * df[lists].sum() + matches * (3 * (8 + 4 * 1.3) + 8) + 36 * 250 * b.n_queries)
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
+# ------------------------------------------------------------------------------------------------ the CPU path
+HOST_OPTIONS = dict(num_typos=2, prefix=1, max_candidates=4, typo_tokens_threshold=1, drop_tokens_threshold=1, topster_size=250,
+                    vec_k=0, vec_ef=10, vec_flat_search_cutoff=0, vec_fetch_size=100, vec_alpha=0.3)
+
+
+def build_cpu_host(args, w, cores):
+    """The reference's CPU path for this workload: the SAME C++ host layer (tokens -> ART candidate search -> typo / prefix /
+    drop-token control flow of Index::search -> rank fusion) with every C-ABI call answered by the CPU oracle (the port of
+    posting-list intersection, scoring, Topster, HNSW walk: oracle/), one query per thread on all host cores. ART walks run on the
+    host (the mirror's walk, pinned on the reference's compiled art.cpp)."""
+    import hostlib
+    from typesense_b200 import hostapi
+    os.environ["TSGPU_DOUBLE_THREADS"] = str(cores)            # read once by the double when it is loaded
+    t0 = time.time()
+    hc = hostapi.HostIndex(w.n_docs, 0, hostlib.build_host_cpu())
+    hc.add_field_flat("title", w.words, w.fd.flat)
+    hc.add_sort_column("points", w.points)
+    handles = [hc.add_filter(f) for f in w.filters]
+    if w.graph_host is not None:
+        hc.device_index().load_hnsw(w.graph_host)
+    log(f"CPU arm: host layer over the oracle double ready in {time.time()-t0:.1f}s")
+    return hc, handles
+
+
+def cpu_search(args, hc, handles, batch, n, cores, out=None):
+    from typesense_b200 import hostapi
+    b, qv, qs = batch
+    blob, tok_off, q_off = qs["packed"]
+    packed = (blob, tok_off, q_off[:n + 1])
+    qf = np.asarray([handles[f] if f >= 0 else -1 for f in qs["filter"][:n]], np.int32)
+    opt = hostapi.Options(device_art_walk=0, n_threads=cores, **HOST_OPTIONS)
+    hybrid = args.workload != "keyword10m"
+    return hc.multi_search("title", "points", None, 100, qf, qv[:n] if hybrid else None, opt, packed=packed, out=out)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     import oracle_lib as ol
-    from typesense_b200 import structs as S
     import torch
     ol.build_oracle()
     device = "cuda" if torch.cuda.is_available() else "cpu"
@@ -318,40 +351,44 @@ def run_reference(args, rank, world):
             lv, l0, uo, lu, ml, ep = w.graph_dev
             w.graph_host = HnswGraph(w.vec_dev.numpy(), lv.numpy(), l0.numpy().astype(np.uint32), uo.numpy().astype(np.uint64),
                                      lu.numpy().astype(np.uint32), 16, ml, ep)
-    oi = ol.OracleIndex(w.n_docs, [w.fd.flat], [w.points], w.graph_host)
-    batches = make_batches(args, w, min(args.steps + args.warmup, 4), 0)
+            w.vec_dev = None
     cores = os.cpu_count() or 1
+    hc, handles = build_cpu_host(args, w, cores)
+    batches = make_batches(args, w, min(args.steps + args.warmup, 4), 0)
     S_n = min(args.cpu_sample, args.batch)
-    vp = S.vec_params(k=0, ef=10, alpha=0.3, fetch_size=100)
 
     def step(i):
-        b, qv = batches[i % len(batches)]
-        bh = b.head(S_n)
-        if args.workload == "keyword10m":
-            oi.keyword_search(bh, 100, cores)
-        else:
-            oi.hybrid_search(bh, qv[:S_n], vp, 100, cores)
+        return cpu_search(args, hc, handles, batches[i % len(batches)], S_n, cores)
     for i in range(args.warmup):
         step(i)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        step(args.warmup + i)
+        st = step(args.warmup + i)[3]
     dt = time.perf_counter() - t0
     qps = S_n * args.steps / dt
     out = {"impl": "reference", "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": SCALING,
            "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic",
            "config": workload_config(args, args.batch),
            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                            "sample": f"{S_n} queries of the batch per step, {args.steps} steps"},
+                            "sample": f"{S_n} queries of the batch per step, {args.steps} steps, query strings through the C++ host layer over the CPU oracle",
+                            "host_rounds_last_step": st},
            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)
+    hc.close()
+
+
+SCALING = "strong"
 
 
 def workload_config(args, batch):
     return {"workload": args.workload, "docs": args.docs, "vocab": args.vocab, "dim": args.dim, "batch": batch,
-            "terms": 3, "typo_candidate_queries": 0.30, "filtered_queries": 0.5, "topster": 250, "hits": 100,
+            "terms": 3, "typo": {"executed": True, "misspelt_queries": TYPO_FRACTION, "num_typos": 2, "prefix": True, "max_candidates": 4,
+                                 "typo_tokens_threshold": 1, "drop_tokens_threshold": 1,
+                                 "where": "e2e and the CPU arm: query STRINGS through the C++ host layer (ART candidate search + Index::search control flow); "
+                                          "value: the same queries in resolved form through the C-ABI"},
+            "filtered_queries": 0.5, "topster": 250, "hits": 100,
             "vector": {"k": 100, "ef_param": 10, "ef_effective": 100, "alpha": 0.3, "M": 16, "ef_construction": GRAPH_PARAMS["ef_construction"],
                        "data": "clustered unit vectors, latent dim 8, ~2000 per cluster",
                        "graph": (_GRAPH_NOTE[0] or "tsgpu_index_build_hnsw (device build of all vectors)") + "; the CPU arm walks the exported copy"},

@@ -279,6 +279,18 @@ tsgpu_status tsgpu_hybrid_fuse_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, 
                                      const float* qvecs, const tsgpu_vec_params* vp, tsgpu_kv* out_kv, uint32_t kv_stride,
                                      uint32_t* out_count, uint32_t* out_found);
 
+/* ---- multi-GPU --------------------------------------------------------------------------------------- */
+/* A multi_search batch shards over queries: one process per GPU, a full replica each, rank r answers its contiguous slice,
+ * and the ONLY exchange is the gather of the slices' result records on the rank that answers the request
+ * (src/core_api.cpp:1080-1131 spread over ranks). The exchange runs inside the library: NCCL over NVLink, bound at run time
+ * (dlopen of libnccl.so.2; override with TSGPU_NCCL_LIB), device to device on the index's stream. */
+tsgpu_status tsgpu_comm_unique_id(void* out128);                      /* ncclGetUniqueId: create on one rank, hand to the others */
+tsgpu_status tsgpu_comm_init(tsgpu_index* idx, int rank, int world, const void* id128);
+tsgpu_status tsgpu_comm_destroy(tsgpu_index* idx);
+/* every rank sends `bytes` from src (host or device); on `root`, dst (host or device) receives world * bytes in rank order */
+tsgpu_status tsgpu_comm_gather(tsgpu_index* idx, const void* src, size_t bytes, void* dst, int root);
+tsgpu_status tsgpu_comm_last_ms(tsgpu_index* idx, float* out_ms);     /* device time of the last gather on this rank */
+
 /* ---- facets ---------------------------------------------------------------------------------------- */
 /* tsgpu_kw_batch::q_flags bit: keep the query's all_result_ids (the id_buff / vec_search_ids union of src/index.cpp:5081-5090,
  * 4215-4219) on the device after a keyword / hybrid search, as one bit per doc — the `out_all_ids` of SURVEY 8(b). */
@@ -328,6 +340,9 @@ typedef struct {
     uint64_t knn_spec_hits;      /* expansions whose node was the one the walk had prefetched for (speculation hit) */
     uint64_t knn_tier2_walks;    /* graph walks whose visited set outgrew shared memory (continued in the HBM tier) */
     uint64_t knn_retried;        /* graph walks that outgrew their slot's scratch and were re-run alone with a full-size slot */
+    uint64_t h2d_total;          /* host->device / device->host bytes since index creation (every call; h2d_bytes / d2h_bytes: last call) */
+    uint64_t d2h_total;
+    uint64_t calls_total;        /* C-ABI search calls since index creation */
 } tsgpu_stats;
 tsgpu_status tsgpu_get_stats(tsgpu_index* idx, tsgpu_stats* out);
 /* Instrumentation: per graph walk of the last HNSW launch, out[2q] = expanded nodes, out[2q+1] = distance evaluations. */

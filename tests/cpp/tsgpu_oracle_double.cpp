@@ -272,7 +272,19 @@ tsgpu_status tsgpu_get_stats(tsgpu_index*, tsgpu_stats* out) { memset(out, 0, si
 tsgpu_status tsgpu_index_build_hnsw(tsgpu_index*, const float*, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, int) {
     g_err = "the test double has no device build"; return TSGPU_ERR_NO_DEVICE;
 }
-tsgpu_status tsgpu_index_hnsw_info(tsgpu_index*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint64_t*, uint64_t*) { g_err = "the test double has no device build"; return TSGPU_ERR_NO_DEVICE; }
+tsgpu_status tsgpu_index_hnsw_info(tsgpu_index* idx, uint32_t* n_nodes, uint32_t* dim, uint32_t* M, uint32_t* max_level, uint32_t* entry_point,
+                                   uint64_t* n_upper_records, uint64_t* build_counters) {
+    Double* d = D(idx);
+    if(!d->has_g) { g_err = "no vector index loaded"; return TSGPU_ERR_INVALID; }
+    if(n_nodes) *n_nodes = d->g.n_nodes;
+    if(dim) *dim = d->g.dim;
+    if(M) *M = d->g.M;
+    if(max_level) *max_level = d->g.max_level;
+    if(entry_point) *entry_point = d->g.entry_point;
+    if(n_upper_records) *n_upper_records = d->g.n_nodes ? d->upper_off[d->g.n_nodes] : 0;
+    if(build_counters) for(int i = 0; i < 5; i++) build_counters[i] = 0;
+    return TSGPU_OK;
+}
 tsgpu_status tsgpu_index_export_hnsw(tsgpu_index*, uint8_t*, uint32_t*, uint64_t*, uint32_t*) { g_err = "the test double has no device build"; return TSGPU_ERR_NO_DEVICE; }
 namespace { struct FacetCopy { uint32_t n_values; std::vector<uint64_t> off; std::vector<uint32_t> vals; }; std::vector<FacetCopy*> g_facets; }
 tsgpu_status tsgpu_index_load_facet(tsgpu_index* idx, const tsgpu_facet* f, uint32_t* out_facet) {

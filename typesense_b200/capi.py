@@ -109,10 +109,21 @@ class GpuIndex:
         self.n_docs = n_docs
         self._keep = []
 
+    @classmethod
+    def from_handle(cls, handle, n_docs: int, library=None) -> "GpuIndex":
+        """A view over an index somebody else owns (the C++ host layer's): same calls, never destroyed from here."""
+        g = cls.__new__(cls)
+        g.L = library if library is not None else lib()
+        g.h = C.c_void_p(handle)
+        g.n_docs = n_docs
+        g._keep = []
+        g._borrowed = True
+        return g
+
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "_borrowed", False):
             self.L.tsgpu_index_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:

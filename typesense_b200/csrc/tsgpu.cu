@@ -3,6 +3,7 @@
 // descriptors, launches kernels on one stream and copies results out. There is no CPU compute path: every entry point
 // fails with TSGPU_ERR_NO_DEVICE when no CUDA device is usable.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -129,7 +130,8 @@ struct tsgpu_index {
     struct FacetMirror { tsfc::FacetDev dev{}; void* d_off = nullptr; void* d_vals = nullptr; };
     std::vector<FacetMirror> facets;
     std::vector<const uint32_t*> keep_bitmaps;      // per query of the last search: its all_result_ids bitmap (device) or nullptr
-    DevBuf d_keep_bm, d_facet;
+    DevBuf d_keep_bm, d_facet, d_comm;
+    void* comm = nullptr; int comm_rank = 0, comm_world = 1; float last_comm_ms = 0;       // ncclComm_t of tsgpu_comm_init
     int n_sms = 148;
     // scratch
     DevBuf d_stage, d_pool, d_small, d_bitmaps, d_found_bm, d_out, d_knn_vis, d_knn_retry_vis, d_knn_retry_cand, d_knn_cand, d_knn_out, d_isect, d_kw_out;
@@ -792,8 +794,10 @@ tsgpu_status run_flat(tsgpu_index* idx, const tsv::FlatParams& P, unsigned long 
 
 void begin_call(tsgpu_index* idx) {
     const uint64_t launches = idx->stats.launches_total;
+    const uint64_t h2d = idx->stats.h2d_total + idx->stats.h2d_bytes, d2h = idx->stats.d2h_total + idx->stats.d2h_bytes, calls = idx->stats.calls_total + 1;
     idx->stats = tsgpu_stats{};
     idx->stats.launches_total = launches;
+    idx->stats.h2d_total = h2d; idx->stats.d2h_total = d2h; idx->stats.calls_total = calls;      // totals up to (not including) this call
     cudaEventRecord(idx->ev[0], idx->stream);
 }
 
@@ -951,7 +955,8 @@ void tsgpu_index_destroy(tsgpu_index* idx) {
     for(void* p: idx->hnsw_alloc) cudaFree(p);
     for(auto& f: idx->filters) { if(f.d_bitmap) cudaFree(f.d_bitmap); if(f.d_ids) cudaFree(f.d_ids); }
     for(auto& fm: idx->facets) { if(fm.d_off) cudaFree(fm.d_off); if(fm.d_vals) cudaFree(fm.d_vals); }
-    idx->d_keep_bm.release(); idx->d_facet.release();
+    idx->d_keep_bm.release(); idx->d_facet.release(); idx->d_comm.release();
+    if(idx->comm) { tsgpu_comm_destroy(idx); }
     DevBuf* bufs[] = {&idx->d_stage, &idx->d_pool, &idx->d_small, &idx->d_bitmaps, &idx->d_found_bm, &idx->d_out, &idx->d_knn_vis,
                       &idx->d_knn_retry_vis, &idx->d_knn_retry_cand, &idx->d_knn_cand, &idx->d_knn_out, &idx->d_isect, &idx->d_kw_out};
     for(auto* b: bufs) b->release();
@@ -1092,6 +1097,7 @@ tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g) {
 
 #include "hnsw_build_host.inc"
 #include "facet_host.inc"
+#include "comm_host.inc"
 
 tsgpu_status tsgpu_filter_create(tsgpu_index* idx, const uint32_t* ids, size_t n, int32_t* out_handle) {
     tsgpu_status s = check_device(idx); if(s) return s;

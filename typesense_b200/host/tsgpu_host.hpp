@@ -1378,7 +1378,11 @@ public:
             const auto& ids = g.second;
             const size_t m = ids.size();
             uint32_t dim = 0;
-            tsgpu_index_hnsw_info(h, nullptr, &dim, nullptr, nullptr, nullptr, nullptr, nullptr);
+            if(tsgpu_index_hnsw_info(h, nullptr, &dim, nullptr, nullptr, nullptr, nullptr, nullptr) != TSGPU_OK || dim == 0) {
+                const Option<bool> e(400, "a vector query needs a vector index");
+                for(size_t i: ids) out[i].status = e;
+                continue;
+            }
             std::vector<kw_query> qv(m);
             std::vector<kw_query*> qs(m);
             uint32_t stride_in = 1;

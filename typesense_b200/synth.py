@@ -266,3 +266,40 @@ def build_graph_bulk(vec: torch.Tensor, M: int = 16, seed: int = 100, max_level_
         links_up[rec, 1:] = rows.to(torch.int32)
     entry = int(torch.nonzero(levels == max_level).flatten()[0])
     return (levels.to(torch.uint8), links0.reshape(-1), upper_off, links_up.reshape(-1), max_level, entry)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Vocabulary strings for the token ids (rank r -> a 7-letter word; a bijection, so no two ranks share a word, and scrambled so
+# that neighbouring ranks are not lexical neighbours). 26^7 = 8e9 words for <= 2^21 tokens: as in a natural vocabulary an
+# edit-distance-1 neighbour of a word is almost never a word itself, so a misspelt query token has one or two candidates.
+_W_LEN, _W_MOD = 7, 26 ** 7
+
+
+def vocab_word(rank: int) -> bytes:
+    x = (rank * 2654435761 + 97) % _W_MOD          # odd multiplier, gcd(2654435761, 26^7) == 1: a bijection on [0, 26^7)
+    out = bytearray(_W_LEN)
+    for i in range(_W_LEN):
+        out[_W_LEN - 1 - i] = 97 + x % 26
+        x //= 26
+    return bytes(out)
+
+
+def vocab_words(vocab: int):
+    x = (np.arange(vocab, dtype=np.uint64) * np.uint64(2654435761) + np.uint64(97)) % np.uint64(_W_MOD)
+    m = np.zeros((vocab, _W_LEN), np.uint8)
+    for i in range(_W_LEN):
+        m[:, _W_LEN - 1 - i] = (x % np.uint64(26)).astype(np.uint8) + 97
+        x //= np.uint64(26)
+    return [bytes(r) for r in m]
+
+
+def misspell(word: bytes, rng, taken=None) -> bytes:
+    """One substituted letter (an edit-distance-1 typo), never itself a vocabulary word when `taken` (a set) is given."""
+    while True:
+        i = int(rng.integers(0, len(word)))
+        c = 97 + int(rng.integers(0, 26))
+        if c == word[i]:
+            continue
+        w = word[:i] + bytes([c]) + word[i + 1:]
+        if taken is None or w not in taken:
+            return w
