@@ -308,6 +308,11 @@ tsgpu_status tsgpu_facet_counts(tsgpu_index* idx, uint32_t facet, const uint32_t
 }
 tsgpu_status tsgpu_facet_counts_last(tsgpu_index*, uint32_t, uint32_t, tsgpu_facet_count*, uint32_t*, uint32_t*) { g_err = "the test double keeps no all_result_ids"; return TSGPU_ERR_NO_DEVICE; }
 tsgpu_status tsgpu_all_result_ids_last(tsgpu_index*, uint32_t, uint32_t*, size_t, size_t*) { g_err = "the test double keeps no all_result_ids"; return TSGPU_ERR_NO_DEVICE; }
+tsgpu_status tsgpu_comm_unique_id(void*) { g_err = "the test double has no communicator"; return TSGPU_ERR_NO_DEVICE; }
+tsgpu_status tsgpu_comm_init(tsgpu_index*, int, int, const void*) { g_err = "the test double has no communicator"; return TSGPU_ERR_NO_DEVICE; }
+tsgpu_status tsgpu_comm_destroy(tsgpu_index*) { return TSGPU_OK; }
+tsgpu_status tsgpu_comm_gather(tsgpu_index*, const void*, size_t, void*, int) { g_err = "the test double has no communicator"; return TSGPU_ERR_NO_DEVICE; }
+tsgpu_status tsgpu_comm_last_ms(tsgpu_index*, float* out) { *out = 0; return TSGPU_OK; }
 tsgpu_status tsgpu_debug_knn_work(tsgpu_index*, uint32_t*, uint32_t, uint32_t* out_n) { *out_n = 0; return TSGPU_OK; }
 tsgpu_status tsgpu_knn_batch(tsgpu_index* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef, const int32_t* q_filter, uint32_t,
                              const uint64_t* filter_off, const uint32_t* filter_ids, float* out_dist, uint32_t* out_labels, uint32_t* out_n) {

@@ -21,7 +21,7 @@ EXPORTS = [
     "tsgpu_last_error", "tsgpu_device_count", "tsgpu_index_create", "tsgpu_index_destroy", "tsgpu_index_load_field",
     "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_index_build_hnsw", "tsgpu_index_hnsw_info", "tsgpu_index_export_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy",
     "tsgpu_intersect", "tsgpu_contains_atleast_one", "tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches", "tsgpu_ids_setop", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
-    "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats", "tsgpu_debug_knn_work", "tsgpu_index_load_facet", "tsgpu_facet_counts", "tsgpu_facet_counts_last", "tsgpu_all_result_ids_last", "tsgpu_index_load_art", "tsgpu_art_walk_batch",
+    "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats", "tsgpu_debug_knn_work", "tsgpu_comm_unique_id", "tsgpu_comm_init", "tsgpu_comm_destroy", "tsgpu_comm_gather", "tsgpu_comm_last_ms", "tsgpu_hybrid_fuse_batch", "tsgpu_index_load_facet", "tsgpu_facet_counts", "tsgpu_facet_counts_last", "tsgpu_all_result_ids_last", "tsgpu_index_load_art", "tsgpu_art_walk_batch",
 ]
 
 
@@ -42,7 +42,14 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise TsgpuError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                              "(there is no CPU fallback)")
-        L = C.CDLL(LIB_PATH)
+        _lib = declare(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def declare(L):
+    """Argument types of every tsgpu_* entry point on a loaded library (libtsgpu.so itself, or one that re-exports it: the C++
+    host layer's wrapper, the test double)."""
+    if True:
         vp = C.c_void_p
         L.tsgpu_last_error.restype = C.c_char_p
         L.tsgpu_index_create.argtypes = [C.c_uint32, C.c_int, C.POINTER(vp)]
@@ -69,6 +76,11 @@ def lib():
             getattr(L, n).argtypes = [vp, C.POINTER(KwBatchStruct), C.c_void_p, C.POINTER(VecParamsStruct), C.c_void_p,
                                       C.c_uint32, C.c_void_p, C.c_void_p]
         L.tsgpu_get_stats.argtypes = [vp, C.POINTER(StatsStruct)]
+        L.tsgpu_comm_unique_id.argtypes = [C.c_void_p]
+        L.tsgpu_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]
+        L.tsgpu_comm_destroy.argtypes = [vp]
+        L.tsgpu_comm_gather.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+        L.tsgpu_comm_last_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.tsgpu_index_load_facet.argtypes = [vp, C.c_void_p, u32p]
         L.tsgpu_facet_counts.argtypes = [vp, C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, u32p, u32p]
         L.tsgpu_facet_counts_last.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -77,8 +89,7 @@ def lib():
         L.tsgpu_index_load_art.argtypes = [vp, C.c_uint32, C.POINTER(ArtStruct)]
         L.tsgpu_art_walk_batch.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                            u32p, C.c_void_p]
-        _lib = L
-    return _lib
+    return L
 
 
 def _ck(rc: int):
@@ -347,6 +358,28 @@ class GpuIndex:
         out = np.zeros(max(len(ids), 1), np.float32)
         _ck(self.L.tsgpu_flat_distances(self.h, q.ctypes.data, ids.ctypes.data, len(ids), out.ctypes.data))
         return out[:len(ids)]
+
+    # ---- multi-GPU: the library's own NCCL exchange
+    def comm_unique_id(self) -> np.ndarray:
+        out = np.zeros(128, np.uint8)
+        _ck(self.L.tsgpu_comm_unique_id(out.ctypes.data))
+        return out
+
+    def comm_init(self, rank: int, world: int, ident: np.ndarray):
+        a = np.ascontiguousarray(ident, np.uint8)
+        _ck(self.L.tsgpu_comm_init(self.h, rank, world, a.ctypes.data))
+
+    def comm_destroy(self):
+        _ck(self.L.tsgpu_comm_destroy(self.h))
+
+    def comm_gather(self, src, nbytes: int, dst, root: int = 0):
+        """src / dst: numpy arrays or torch tensors (host, pinned or device); dst is only read on `root`."""
+        _ck(self.L.tsgpu_comm_gather(self.h, _addr(src), nbytes, _addr(dst) if dst is not None else None, root))
+
+    def comm_last_ms(self) -> float:
+        v = C.c_float(0)
+        _ck(self.L.tsgpu_comm_last_ms(self.h, C.byref(v)))
+        return v.value
 
     # ---- facets (SURVEY 8 f-3)
     def load_facet(self, n_values: int, doc_off, value_ids) -> int:

@@ -59,7 +59,7 @@ def pack_strings(strings: Sequence[bytes]):
 class HostIndex:
     def __init__(self, n_docs: int, device: int = 0, lib_path: Optional[str] = None):
         path = lib_path or build_gpu_lib()
-        self.L = C.CDLL(path)
+        self.L = capi.declare(C.CDLL(path))          # re-exports the tsgpu_* entry points it links
         L = self.L
         L.tshost_last_error.restype = C.c_char_p
         L.tshost_create.restype = C.c_void_p

@@ -158,6 +158,7 @@ class KwBatch:
         F = len(field_ids)
         nq = len(queries)
         self.n_queries, self.n_fields = nq, F
+        self.queries = list(queries)
         self.field_ids = np.asarray(field_ids, np.uint32)
         q_combo_off = [0]
         q_excl_off = [0]
