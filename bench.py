@@ -459,7 +459,7 @@ def run_tsgpu(args, rank, world, local_rank):
     all_pin = torch.zeros(world * max_nl * rec, dtype=torch.uint8).pin_memory() if (world > 1 and rank == 0) else None
     host_kv = np.zeros((max_nl, stride), S.KV_DTYPE)
     host_cnt = np.zeros(max_nl, np.uint32); host_fnd = np.zeros(max_nl, np.uint32)
-    host_opt = hostapi.Options(device_art_walk=1, n_threads=min(os.cpu_count() or 1, 32), **HOST_OPTIONS)
+    host_opt = hostapi.Options(device_art_walk=1, n_threads=min(os.cpu_count() or 1, 64), **HOST_OPTIONS)
     comm_ms = []
 
     def step(i, mode):
@@ -603,7 +603,8 @@ def run_tsgpu(args, rank, world, local_rank):
         if traffic:
             extra["roofline_traffic_source"] = traffic.get("source")
         extra["host_rounds_per_step"] = {k: float(statistics.mean(s_[k] for s_ in sts_e2e)) for k in
-                                         ("passes", "kw_batches", "kw_queries", "walk_batches", "walks", "host_walk_fallbacks", "fuse_queries")}
+                                         ("passes", "kw_batches", "kw_queries", "walk_batches", "walks", "host_walk_fallbacks", "fuse_queries",
+                                          "ms_host_passes", "ms_kw_calls", "ms_walk_calls", "ms_fuse_calls")}
         if getattr(w, "build_info", None):
             extra["hnsw_build"] = w.build_info
         if want_cpu:

@@ -263,6 +263,13 @@ tsgpu_status tsgpu_vector_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b
                                        const tsgpu_vec_params* vp, tsgpu_kv* out_kv, uint32_t kv_stride,
                                        uint32_t* out_count, uint32_t* out_found);
 
+/* The scoring half of Index::do_phrase_search for a phrase-ONLY query (src/index.cpp:6019-6082): query q's result ids are its
+ * inline filter (the phrase matches, already ANDed with filter_by and minus exclusions), id_scores[i] — aligned with the
+ * batch's filter_ids — the match score of each (the reference's `100000 + field weight` for the first 10000 matches of a field,
+ * 0 beyond); every id goes through compute_sort_scores into the Topster. found = number of ids. */
+tsgpu_status tsgpu_scored_ids_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const int64_t* id_scores, tsgpu_kv* out_kv,
+                                           uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found);
+
 /* Keyword + vector query with reciprocal-rank fusion (src/index.cpp:4036-4221). */
 tsgpu_status tsgpu_hybrid_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const float* qvecs,
                                        const tsgpu_vec_params* vp, tsgpu_kv* out_kv, uint32_t kv_stride,

@@ -962,8 +962,19 @@ int tso_keyword_search_batch(void* idx, const tso_kw_batch* b, tso_kv* out_kv, u
     return 0;
 }
 
+static int wildcard_common(void* idx, const tso_kw_batch* b, const int64_t* id_scores, tso_kv* out_kv, uint32_t kv_stride,
+                           uint32_t* out_count, uint32_t* out_found, uint32_t n_threads);
 int tso_wildcard_search_batch(void* idx, const tso_kw_batch* b, tso_kv* out_kv, uint32_t kv_stride,
                               uint32_t* out_count, uint32_t* out_found, uint32_t n_threads) {
+    return wildcard_common(idx, b, nullptr, out_kv, kv_stride, out_count, out_found, n_threads);
+}
+// Index::do_phrase_search's Topster loop for a phrase-only query (src/index.cpp:6039-6076): ids with their phrase match scores
+int tso_scored_ids_search_batch(void* idx, const tso_kw_batch* b, const int64_t* id_scores, tso_kv* out_kv, uint32_t kv_stride,
+                                uint32_t* out_count, uint32_t* out_found, uint32_t n_threads) {
+    return wildcard_common(idx, b, id_scores, out_kv, kv_stride, out_count, out_found, n_threads);
+}
+static int wildcard_common(void* idx, const tso_kw_batch* b, const int64_t* id_scores, tso_kv* out_kv, uint32_t kv_stride,
+                           uint32_t* out_count, uint32_t* out_found, uint32_t n_threads) {
     const Index& ix = *(Index*) idx;
     parallel_for(b->n_queries, n_threads, [&](uint32_t q) {
         Topster t(std::max<uint32_t>(1, b->q_topk[q]));
@@ -979,7 +990,8 @@ int tso_wildcard_search_batch(void* idx, const tso_kw_batch* b, tso_kv* out_kv, 
             if(n_excl && std::binary_search(excl, excl + n_excl, seq_id)) continue;      // get_n_ids skips excluded ids
             tso_kv kv{};
             int64_t msi = -1;
-            compute_sort_scores(ix, S, seq_id, 100, kv.scores, msi, 0);                  // src/index.cpp:6727-6729
+            const int64_t ms = (id_scores && filt) ? id_scores[(filt - b->filter_ids) + i] : 100;
+            compute_sort_scores(ix, S, seq_id, ms, kv.scores, msi, 0);                   // src/index.cpp:6727-6729 / 6045-6053
             kv.key = seq_id; kv.distinct_key = seq_id; kv.query_index = 0;
             kv.match_score_index = (int8_t) msi;
             kv.vector_distance = -1.0f;

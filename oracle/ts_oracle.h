@@ -141,6 +141,8 @@ int tso_keyword_search_batch(void* idx, const tso_kw_batch* b, tso_kv* out_kv, u
  * has no filter) minus the exclusion list gets sort scores with text-match value 100 and goes into the Topster.
  * Combinations of the batch are ignored. query_index is left 0 (the reference reads searched_queries.size() from worker
  * threads while the enqueuing thread is still appending to it, i.e. it is not deterministic there). */
+int tso_scored_ids_search_batch(void* idx, const tso_kw_batch* b, const int64_t* id_scores, tso_kv* out_kv, uint32_t kv_stride,
+                                uint32_t* out_count, uint32_t* out_found, uint32_t n_threads);
 int tso_wildcard_search_batch(void* idx, const tso_kw_batch* b, tso_kv* out_kv, uint32_t kv_stride,
                               uint32_t* out_count, uint32_t* out_found, uint32_t n_threads);
 

@@ -552,7 +552,7 @@ static void relevance_scenarios() {
 }
 
 // PhraseSearch, test/collection_specific_test.cpp:2504-2622 — the cases that combine phrases with tokens or exclusions
-// (phrase-only queries get do_phrase_search's own score and are not mirrored by the host layer)
+// and the phrase-only queries with do_phrase_search's own score
 static void phrase_scenarios() {
     tsgpu::Index index(3);
     tsgpu::field_mirror_t m;
@@ -587,10 +587,22 @@ static void phrase_scenarios() {
         CHECK(index.search({}, {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
         CHECK(kvs.size() == 3);
     }
-    {   // phrase-only queries are refused, not approximated
+    {   // phrase-only queries (test/collection_specific_test.cpp:2535-2545): do_phrase_search's own scoring, 100000 + field weight
         tsgpu::search_options o = opt(0, false);
-        o.phrases = {P({"down", "there", "by"})};
-        CHECK(!index.search({}, {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
+        o.phrases = {P({"down", "there", "by"})};                      // " down there by "
+        CHECK(index.search({}, {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{1}) && found == 1);
+        CHECK(kvs.size() == 1 && kvs[0].scores[0] == 100000 + 15 && kvs[0].match_score_index == 0);
+        o.phrases = {P({"by", "the"})};                                // "by the" -train
+        o.exclude_tokens = {"train"};
+        CHECK(index.search({}, {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{0}) && found == 1);
+        o.exclude_tokens.clear();                                      // "by the": both documents, same score, the later id first
+        CHECK(index.search({}, {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
+        CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 0}) && found == 2);
+        o.phrases = {P({"by", "the", "dinosaur"})};                    // a phrase with an unknown token: nothing
+        CHECK(index.search({}, {"title"}, sort_fields, 10, 250, kvs, found, o).ok());
+        CHECK(kvs.empty() && found == 0);
     }
 }
 

@@ -239,6 +239,11 @@ tsgpu_status tsgpu_hybrid_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b
                                kv_stride, out_count, out_found, n_thr()) != 0) { g_err = "no vector index loaded"; return TSGPU_ERR_INVALID; }
     return TSGPU_OK;
 }
+tsgpu_status tsgpu_scored_ids_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const int64_t* id_scores, tsgpu_kv* out_kv, uint32_t kv_stride,
+                                           uint32_t* out_count, uint32_t* out_found) {
+    tso_scored_ids_search_batch(D(idx)->oi, reinterpret_cast<const tso_kw_batch*>(b), id_scores, reinterpret_cast<tso_kv*>(out_kv), kv_stride, out_count, out_found, n_thr());
+    return TSGPU_OK;
+}
 tsgpu_status tsgpu_hybrid_fuse_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const tsgpu_kv* kw_kv, uint32_t kw_stride, const uint32_t* kw_count,
                                      const uint32_t* kw_found, const uint32_t* kw_searched, const float* qvecs, const tsgpu_vec_params* vp,
                                      tsgpu_kv* out_kv, uint32_t kv_stride, uint32_t* out_count, uint32_t* out_found) {

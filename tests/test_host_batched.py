@@ -54,6 +54,7 @@ def run_and_check(lib_path, device_walk):
     qv = synth.make_vectors_clustered(len(qs), vec.shape[1], 12, seed=77, spread=0.5, latent=6, center_latent=6, centers_seed=3)[0].numpy()
     opt = hostapi.Options(device_art_walk=1 if device_walk else 0, n_threads=3, vec_fetch_size=100)
     kv, cnt, found, st = hi.multi_search("title", "points", qs, 250, np.asarray([handles[f] if f >= 0 else -1 for f in qf], np.int32), qv, opt)
+    st_first = dict(st)
     assert st["fuse_queries"] == len(qs) and st["kw_queries"] >= len(qs)
     # the resolved form: one combination of the (corrected) tokens per query
     sort = ((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_NUMERIC, 0, 1, 0), (S.SORT_NONE, -1, 1, 0))
@@ -83,7 +84,7 @@ def run_and_check(lib_path, device_walk):
     for i in range(len(qs)):
         assert cnt[i] == ocnt[i] and found[i] == ofound[i] and kv["key"][i, :cnt[i]].tolist() == okv["key"][i, :ocnt[i]].tolist(), i
     hi.close()
-    return st
+    return st_first
 
 
 def test_batched_multi_search_on_the_oracle_double():

@@ -832,6 +832,7 @@ struct WcParams {
     const UDesc* ud;                   // ud.combo == query index
     const uint32_t* const* q_ids;      // [nq] device id arrays or nullptr (= identity)
     const uint32_t* q_nids;            // [nq]
+    const int64_t* const* q_scores;    // [nq] per-id match scores aligned with q_ids (do_phrase_search) or nullptr = the wildcard's 100
     int64_t* pool_s0; int64_t* pool_s1; int64_t* pool_s2;
     uint32_t* pool_key; uint16_t* pool_cmb;
     uint32_t* unit_cnt; uint32_t* combo_matches;
@@ -874,7 +875,8 @@ wc_unit_kernel(const __grid_constant__ WcParams P) {
         }
         const bool matched = keep;
         if(keep) {
-            compute_sort_scores(SS, id, 100, 0.0f, sc);                       // src/index.cpp:6727-6729
+            const int64_t ms = (P.q_scores && P.q_scores[q]) ? __ldg(P.q_scores[q] + i) : 100;      // src/index.cpp:6727-6729; phrase-only: :6045
+            compute_sort_scores(SS, id, ms, 0.0f, sc);
             const long long gthr = *reinterpret_cast<volatile long long*>(gthr_p);
             keep = sc[0] >= gthr;
             if(keep && s_have_thr) keep = kv_greater(sc[0], sc[1], sc[2], id, thr[0], thr[1], thr[2], thr_key);

@@ -170,6 +170,9 @@ struct KwPlan {
     uint32_t n_units_total = 0;           // level-0 units + merge outputs
     bool wildcard = false;                // units walk the filter ids (Index::search_wildcard) instead of posting lists
     std::vector<uint32_t> q_nids;         // wildcard: ids per query
+    std::vector<unsigned long long> q_inline_off;   // wildcard: offset of the query's ids inside the batch's inline filter ids (~0: not inline)
+    size_t n_inline_ids = 0;
+    const int64_t* id_scores = nullptr;   // scored id sets (host or device, aligned with the batch's inline filter ids) or nullptr
     size_t pool_slots = 0;
     // device views (valid after upload)
     QDesc* d_qd = nullptr; CDesc* d_cd = nullptr; UDesc* d_ud = nullptr; uint32_t* d_multi_q = nullptr; uint32_t* d_multi_keep_q = nullptr;
@@ -327,6 +330,8 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
             if(wfs >= 0 && (uint32_t) wfs < b->n_filters) n_ids = b->filter_off[wfs + 1] - b->filter_off[wfs];
             else if(wfs <= -2 && (size_t) (-(wfs + 2)) < idx->filters.size()) n_ids = idx->filters[(size_t) (-(wfs + 2))].n;
             pl.q_nids.push_back((uint32_t) n_ids);
+            pl.q_inline_off.push_back((wfs >= 0 && (uint32_t) wfs < b->n_filters) ? (unsigned long long) b->filter_off[wfs] : ~0ull);
+            pl.n_inline_ids = b->n_filters ? (size_t) b->filter_off[b->n_filters] : 0;
             qd.combo_begin = q; qd.combo_end = q + 1;
             const uint32_t tiles = (uint32_t) ((n_ids + kThreads - 1) / kThreads), wtpu = 64;
             for(uint32_t t = 0; t < tiles; t += wtpu) {
@@ -515,7 +520,9 @@ tsgpu_status run_keyword(tsgpu_index* idx, KwPlan& pl, uint32_t kv_stride, KwDev
         // per-query id arrays
         std::vector<const uint32_t*> qids(nq);
         for(uint32_t q = 0; q < nq; q++) qids[q] = pl.q_filter_ids[q];
-        const size_t tb = (size_t) nq * 12 + 64;
+        const size_t n_sc = pl.id_scores ? pl.n_inline_ids : 0;
+        const size_t o_sp = ((size_t) nq * 12 + 63) & ~size_t(63), o_sc = o_sp + (size_t) nq * 8;
+        const size_t tb = o_sc + n_sc * 8 + 64;
         CU(idx->d_small.reserve(tb));
         unsigned char* sb = idx->d_small.as<unsigned char>();
         CU(cudaMemcpy(sb, qids.data(), (size_t) nq * 8, cudaMemcpyHostToDevice));
@@ -524,6 +531,15 @@ tsgpu_status run_keyword(tsgpu_index* idx, KwPlan& pl, uint32_t kv_stride, KwDev
         WcParams P{};
         P.qd = pl.d_qd; P.ud = pl.d_ud;
         P.q_ids = reinterpret_cast<const uint32_t* const*>(sb); P.q_nids = reinterpret_cast<const uint32_t*>(sb + (size_t) nq * 8);
+        P.q_scores = nullptr;
+        if(pl.id_scores) {                       // per-id match scores ride next to the ids they belong to
+            CU(cudaMemcpy(sb + o_sc, pl.id_scores, n_sc * 8, cudaMemcpyDefault));
+            std::vector<const int64_t*> qsc(nq, nullptr);
+            for(uint32_t q = 0; q < nq; q++) if(pl.q_inline_off[q] != ~0ull) qsc[q] = reinterpret_cast<const int64_t*>(sb + o_sc) + pl.q_inline_off[q];
+            CU(cudaMemcpy(sb + o_sp, qsc.data(), (size_t) nq * 8, cudaMemcpyHostToDevice));
+            P.q_scores = reinterpret_cast<const int64_t* const*>(sb + o_sp);
+            idx->stats.h2d_bytes += n_sc * 8 + (size_t) nq * 8;
+        }
         P.pool_s0 = p0; P.pool_s1 = p1; P.pool_s2 = p2; P.pool_key = pk; P.pool_cmb = pc;
         P.unit_cnt = pl.d_unit_cnt; P.combo_matches = pl.d_combo_matches; P.q_thr = pl.d_q_thr; P.KP = pl.KP;
         const size_t smem = (size_t) 2 * pl.KP * 28;
@@ -1310,13 +1326,29 @@ tsgpu_status tsgpu_keyword_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* 
     return fetch_kw_stats(idx, pl);
 }
 
+static tsgpu_status wildcard_common(tsgpu_index* idx, const tsgpu_kw_batch* b, const int64_t* id_scores, tsgpu_kv* out_kv, uint32_t kv_stride,
+                                    uint32_t* out_count, uint32_t* out_found);
+
 tsgpu_status tsgpu_wildcard_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, tsgpu_kv* out_kv, uint32_t kv_stride,
                                          uint32_t* out_count, uint32_t* out_found) {
+    return wildcard_common(idx, b, nullptr, out_kv, kv_stride, out_count, out_found);
+}
+
+tsgpu_status tsgpu_scored_ids_search_batch(tsgpu_index* idx, const tsgpu_kw_batch* b, const int64_t* id_scores, tsgpu_kv* out_kv, uint32_t kv_stride,
+                                           uint32_t* out_count, uint32_t* out_found) {
+    if(!id_scores) return fail(TSGPU_ERR_INVALID, "null id_scores");
+    if(b) for(uint32_t q = 0; q < b->n_queries; q++) if(b->q_filter[q] < 0) return fail(TSGPU_ERR_INVALID, "every query needs its id set as an inline filter");
+    return wildcard_common(idx, b, id_scores, out_kv, kv_stride, out_count, out_found);
+}
+
+static tsgpu_status wildcard_common(tsgpu_index* idx, const tsgpu_kw_batch* b, const int64_t* id_scores, tsgpu_kv* out_kv, uint32_t kv_stride,
+                                    uint32_t* out_count, uint32_t* out_found) {
     tsgpu_status s = check_device(idx); if(s) return s;
     if(!b || !out_kv || !out_count || !out_found || kv_stride == 0) return fail(TSGPU_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(idx->mu);
     begin_call(idx);
     KwPlan pl;
+    pl.id_scores = id_scores;
     { const auto t0 = std::chrono::steady_clock::now();
       s = build_kw_plan(idx, b, false, pl, true);
       idx->stats.ms_host_plan = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }

@@ -32,6 +32,7 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <exception>
 #include <map>
@@ -714,6 +715,10 @@ public:
         std::vector<std::pair<uint32_t, walk_request>> pending_walks;
         int32_t filter_handle = -1;
         kw_query executed;                   // every combination the request's rounds ran (the hybrid tail probes them)
+        // candidate searches already answered in an earlier pass, in call order: (tokens returned, the exclusion set afterwards).
+        // A replayed search asks the same questions in the same order, so pass k only pays for the questions that are new.
+        std::vector<std::pair<std::vector<std::string>, std::set<std::string>>> cand_log;
+        size_t cand_next = 0;
     };
     static replay_t*& replay() { static thread_local replay_t* r = nullptr; return r; }
 
@@ -777,6 +782,58 @@ public:
             if(!op.ok()) return op;
             phrase_result_ids.swap(merged);
         }
+        return Option<bool>(true);
+    }
+    struct search_state;
+    // A query made of phrases only (Index::do_phrase_search with is_wildcard_query, src/index.cpp:5925-6082): per field the ids
+    // holding every phrase; the first 10000 of a field score 100000 + the field's weight (the best field wins), later ones 0;
+    // fields are ORed, exclusions removed, and every id goes through compute_sort_scores into the Topster — on the device
+    // (tsgpu_scored_ids_search_batch).
+    Option<bool> phrase_only_search(const std::vector<std::string>& the_fields, const std::vector<sort_by>& sort_fields, size_t topster_size,
+                                    const search_options& o, const search_state& st, std::vector<KV>& raw_result_kvs, size_t& found) {
+        std::map<uint32_t, int64_t> phrase_match_id_scores;
+        std::vector<uint32_t> result;
+        for(size_t fi = 0; fi < the_fields.size(); fi++) {
+            std::vector<uint32_t> acc;
+            bool have = false;
+            for(auto& ph: o.phrases) {
+                std::vector<uint32_t> ids, merged;
+                bool known = true;
+                auto op = phrase_ids_of(the_fields[fi], ph, ids, known);
+                if(!op.ok()) return op;
+                if(!known || ids.empty()) continue;
+                if(!have) { acc = ids; have = true; }
+                else { op = ids_setop(TSGPU_SET_AND, ids, acc, merged); if(!op.ok()) return op; acc.swap(merged); }
+            }
+            if(acc.empty()) continue;
+            const int64_t this_field_score = 100000 + (int64_t) (fi < st.weights.size() ? st.weights[fi] : 0);
+            for(size_t pi = 0; pi < std::min<size_t>(10000, acc.size()); pi++) {
+                int64_t& sc = phrase_match_id_scores[acc[pi]];
+                sc = std::max(sc, this_field_score);
+            }
+            std::vector<uint32_t> merged;
+            auto op = ids_setop(TSGPU_SET_OR, result, acc, merged);
+            if(!op.ok()) return op;
+            result.swap(merged);
+        }
+        if(!st.excluded.empty() && !result.empty()) {
+            std::vector<uint32_t> merged;
+            auto op = ids_setop(TSGPU_SET_EXCLUDE, result, st.excluded, merged);
+            if(!op.ok()) return op;
+            result.swap(merged);
+        }
+        raw_result_kvs.clear(); found = 0;
+        if(result.empty()) return Option<bool>(true);
+        std::vector<int64_t> scores(result.size(), 0);
+        for(size_t i = 0; i < result.size(); i++) { auto it = phrase_match_id_scores.find(result[i]); if(it != phrase_match_id_scores.end()) scores[i] = it->second; }
+        kw_query q = make_kw_query({}, 0, {}, {}, {}, sort_fields, result, true, {}, topster_size, true, false, true, TSGPU_MATCH_MAX_SCORE, -1, -1, false, false);
+        std::vector<kw_query*> one{&q};
+        kw_batch_storage bst(one);
+        std::vector<KV> kvs(bst.stride);
+        uint32_t count = 0, nf = 0;
+        if(tsgpu_scored_ids_search_batch(h, &bst.b, scores.data(), kvs.data(), bst.stride, &count, &nf) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
+        raw_result_kvs.assign(kvs.begin(), kvs.begin() + count);
+        found = nf;
         return Option<bool>(true);
     }
     // A string `filter_by` clause to its id set: filter_result_iterator_t::init (src/filter_result_iterator.cpp:1739-1905: the
@@ -991,6 +1048,11 @@ public:
     std::vector<std::string> fuzzy_candidates(uint32_t fid, const std::string& token, int cost, bool prefix_search,
                                               std::set<std::string>& unique_tokens, const search_options& o,
                                               const std::string& prev_token = std::string()) const {
+        if(replay_t* r = replay()) if(r->cand_next < r->cand_log.size()) {        // answered in an earlier pass
+            const auto& e = r->cand_log[r->cand_next++];
+            unique_tokens = e.second;
+            return e.first;
+        }
         const vocab_t& v = vocabs[fid];
         const art_mirror_t& art = art_of(fid);
         art_mirror_t::doc_tests docs;
@@ -1001,9 +1063,21 @@ public:
             docs.filter_active = true;
             docs.has_filter_doc = [&](uint32_t l) { for(uint64_t i = v.list_off[l]; i < v.list_off[l + 1]; i++) if(in_filter(v.ids[i])) return true; return false; };
         }
-        docs.share_doc = [&](uint32_t a, uint32_t c) {
+        docs.share_doc = [&](uint32_t a, uint32_t c) {             // two ascending lists: the smaller head gallops (posting_list_t::contains_atleast_one's skip_to)
+            const uint32_t* ids = v.ids.data();
             uint64_t i = v.list_off[a], ie = v.list_off[a + 1], j = v.list_off[c], je = v.list_off[c + 1];
-            while(i < ie && j < je) { if(v.ids[i] == v.ids[j]) { if(in_filter(v.ids[i])) return true; i++; j++; } else if(v.ids[i] < v.ids[j]) i++; else j++; }
+            auto gallop = [&](uint64_t lo, uint64_t hi, uint32_t target) {          // first position in [lo, hi) with ids[pos] >= target
+                uint64_t step = 1, p = lo;
+                while(p + step < hi && ids[p + step] < target) { p += step; step <<= 1; }
+                uint64_t l = p, h = std::min(hi, p + step + 1);
+                while(l < h) { const uint64_t m = (l + h) >> 1; if(ids[m] < target) l = m + 1; else h = m; }
+                return l;
+            };
+            while(i < ie && j < je) {
+                if(ids[i] == ids[j]) { if(in_filter(ids[i])) return true; i++; j++; }
+                else if(ids[i] < ids[j]) i = gallop(i, ie, ids[j]);
+                else j = gallop(j, je, ids[i]);
+            }
             return false;
         };
         std::vector<int32_t> hits;
@@ -1027,6 +1101,7 @@ public:
                                       o.token_order == search_options::MAX_SCORE ? art_mirror_t::MAX_SCORE : art_mirror_t::FREQUENCY,
                                       prev_token, docs, unique_tokens, hits))
             out.push_back(art.leaves[leaf].key);
+        if(replay_t* r = replay()) { r->cand_log.emplace_back(out, unique_tokens); r->cand_next++; }
         return out;
     }
 
@@ -1184,7 +1259,7 @@ public:
             auto pop = phrase_filter_ids(the_fields, opts, st.excluded, st.filter_ids);
             if(!pop.ok()) return pop;
             st.filter_by_provided = true;
-            if(tokens.empty()) return Option<bool>(400, "phrase-only queries are scored by do_phrase_search's 100000 + weight rule, which this layer does not mirror");
+            if(tokens.empty()) return phrase_only_search(the_fields, sort_fields, topster_size, opts, st, raw_result_kvs, found);
         }
         if(tokens.empty()) {
             // only exclusions: the query is `*` minus the excluded ids (src/index.cpp:3738-3745)
@@ -1296,7 +1371,8 @@ public:
         const float* query_vector = nullptr;     // nullptr: keyword only
         tsgpu_vec_params vp{0, 10, 0, 3.4028234663852886e38f, 0.3f, 10};
     };
-    struct batched_stats { size_t passes = 0, kw_batches = 0, kw_queries = 0, walk_batches = 0, walks = 0, host_walk_fallbacks = 0, fuse_queries = 0; };
+    struct batched_stats { size_t passes = 0, kw_batches = 0, kw_queries = 0, walk_batches = 0, walks = 0, host_walk_fallbacks = 0, fuse_queries = 0;
+                           double ms_host_passes = 0, ms_kw_calls = 0, ms_walk_calls = 0, ms_fuse_calls = 0; };
     std::vector<search_response> multi_search_batched(const std::vector<batched_request>& requests, size_t n_threads = 0, batched_stats* stats = nullptr) {
         const size_t n = requests.size();
         std::vector<search_response> out(n);
@@ -1304,11 +1380,11 @@ public:
         std::vector<char> done(n, 0);
         std::vector<size_t> active(n);
         for(size_t i = 0; i < n; i++) { active[i] = i; rs[i].filter_handle = requests[i].filter_handle; }
-        if(n_threads == 0) n_threads = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), 32));
+        if(n_threads == 0) n_threads = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), 64));
         batched_stats bs;
         auto run_one = [&](size_t i) {
             replay_t& r = rs[i];
-            r.next = 0; r.has_pending = false; r.pending_walks.clear();
+            r.next = 0; r.cand_next = 0; r.has_pending = false; r.pending_walks.clear();
             replay() = &r;
             const auto& q = requests[i].r;
             try {
@@ -1319,14 +1395,19 @@ public:
             catch(const std::exception& e) { out[i].status = Option<bool>(400, e.what()); done[i] = 1; }
             replay() = nullptr;
         };
+        using clk = std::chrono::steady_clock;
+        auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
         while(!active.empty()) {
             bs.passes++;
+            auto tp = clk::now();
             // ---- one pass over the unfinished searches
             std::atomic<size_t> cursor{0};
             auto worker = [&] { for(;;) { const size_t k = cursor.fetch_add(1); if(k >= active.size()) break; run_one(active[k]); } };
             const size_t nt = std::min(n_threads, active.size());
             if(nt <= 1) worker();
             else { std::vector<std::thread> th; for(size_t t = 0; t < nt; t++) th.emplace_back(worker); for(auto& t: th) t.join(); }
+            bs.ms_host_passes += ms_since(tp);
+            tp = clk::now();
             // ---- candidate walks asked for in this pass: one device batch per field
             std::map<uint32_t, std::vector<walk_request>> per_field;
             std::set<walk_key> asked;
@@ -1346,6 +1427,8 @@ public:
                     bs.host_walk_fallbacks++;
                 }
             }
+            bs.ms_walk_calls += ms_since(tp);
+            tp = clk::now();
             // ---- keyword rounds asked for in this pass: one device batch per searched-field set
             std::map<std::vector<uint32_t>, std::vector<size_t>> groups;
             for(size_t i: active) if(rs[i].has_pending) groups[rs[i].pending.fids].push_back(i);
@@ -1361,11 +1444,13 @@ public:
                     r.has_pending = false;
                 }
             }
+            bs.ms_kw_calls += ms_since(tp);
             std::vector<size_t> still;
             for(size_t i: active) if(!done[i]) still.push_back(i);
             active.swap(still);
         }
         // ---- hybrid tail: vector stage + rank fusion for every request that carries a vector query
+        auto tfuse = clk::now();
         std::vector<size_t> hyb;
         for(size_t i = 0; i < n; i++) if(requests[i].query_vector && out[i].status.ok()) hyb.push_back(i);
         std::map<std::vector<uint32_t>, std::vector<size_t>> hgroups;        // same searched fields, same vector parameters per call
@@ -1425,6 +1510,7 @@ public:
                 out[ids[k]].found = ofound[k];
             }
         }
+        bs.ms_fuse_calls = ms_since(tfuse);
         if(stats) *stats = bs;
         return out;
     }

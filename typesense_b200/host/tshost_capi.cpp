@@ -54,7 +54,7 @@ typedef struct {
     uint32_t vec_k, vec_ef, vec_flat_search_cutoff, vec_fetch_size;
     float vec_alpha, vec_distance_threshold;
 } tshost_options;
-typedef struct { uint64_t passes, kw_batches, kw_queries, walk_batches, walks, host_walk_fallbacks, fuse_queries; } tshost_stats;
+typedef struct { uint64_t passes, kw_batches, kw_queries, walk_batches, walks, host_walk_fallbacks, fuse_queries; double ms_host_passes, ms_kw_calls, ms_walk_calls, ms_fuse_calls; } tshost_stats;
 
 // nq requests over one searched field; request i's tokens are tokens[q_off[i] .. q_off[i+1]), token t = blob[tok_off[t] .. tok_off[t+1]).
 // q_filter[i]: a handle from tshost_add_filter or -1. qvecs: nq * dim floats (hybrid) or NULL (keyword only).
@@ -90,7 +90,7 @@ int tshost_multi_search(void* h, const char* field, const char* sort_field, uint
         std::memcpy(out_kv + (size_t) i * stride, resp[i].raw_result_kvs.data(), (size_t) n * sizeof(tsgpu_kv));
         out_count[i] = n; out_found[i] = (uint32_t) resp[i].found;
     }
-    if(out_stats) *out_stats = tshost_stats{bs.passes, bs.kw_batches, bs.kw_queries, bs.walk_batches, bs.walks, bs.host_walk_fallbacks, bs.fuse_queries};
+    if(out_stats) *out_stats = tshost_stats{bs.passes, bs.kw_batches, bs.kw_queries, bs.walk_batches, bs.walks, bs.host_walk_fallbacks, bs.fuse_queries, bs.ms_host_passes, bs.ms_kw_calls, bs.ms_walk_calls, bs.ms_fuse_calls};
     return rc;
 }
 

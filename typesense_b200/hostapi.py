@@ -47,7 +47,8 @@ class Options(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("passes", "kw_batches", "kw_queries", "walk_batches", "walks", "host_walk_fallbacks", "fuse_queries")]
+    _fields_ = ([(n, C.c_uint64) for n in ("passes", "kw_batches", "kw_queries", "walk_batches", "walks", "host_walk_fallbacks", "fuse_queries")] +
+                [(n, C.c_double) for n in ("ms_host_passes", "ms_kw_calls", "ms_walk_calls", "ms_fuse_calls")])
 
 
 def pack_strings(strings: Sequence[bytes]):
