@@ -65,7 +65,11 @@ typedef struct {
 
 enum { TSGPU_SORT_NONE = 0, TSGPU_SORT_TEXT_MATCH = 1, TSGPU_SORT_SEQ_ID = 2, TSGPU_SORT_NUMERIC = 3, TSGPU_SORT_VECTOR_DISTANCE = 4 };
 enum { TSGPU_MATCH_MAX_SCORE = 0, TSGPU_MATCH_MAX_WEIGHT = 1, TSGPU_MATCH_SUM_SCORE = 2 };   /* text_match_type_t */
-enum { TSGPU_FLAG_PRIORITIZE_EXACT_MATCH = 1, TSGPU_FLAG_PRIORITIZE_TOKEN_POSITION = 2, TSGPU_FLAG_PRIORITIZE_NUM_MATCHING_FIELDS = 4 };
+enum { TSGPU_FLAG_PRIORITIZE_EXACT_MATCH = 1, TSGPU_FLAG_PRIORITIZE_TOKEN_POSITION = 2, TSGPU_FLAG_PRIORITIZE_NUM_MATCHING_FIELDS = 4,
+       /* hybrid calls: `rerank_hybrid_matches` — Index::compute_aux_scores (src/index.cpp:8793-8923) after the fusion: a result found only by
+        * the vector query gets the text match score of the query's FIRST combination (its literal tokens; absent tokens are skipped), one found only
+        * by keywords gets its vector distance, then every result is re-scored 1/keyword_rank * (1-alpha) + 1/semantic_rank * alpha */
+       TSGPU_FLAG_RERANK_HYBRID_MATCHES = 0x40 };
 enum { TSGPU_CFLAG_SYNONYM = 1, TSGPU_CFLAG_DEMOTE_SYNONYM = 2 };
 
 /* A batch of keyword searches. Query q is ONE Index::search_all_candidates call (src/index.cpp:1794-1894): a list

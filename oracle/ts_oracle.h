@@ -47,7 +47,8 @@ typedef struct {
 
 enum { TSO_SORT_NONE = 0, TSO_SORT_TEXT_MATCH = 1, TSO_SORT_SEQ_ID = 2, TSO_SORT_NUMERIC = 3, TSO_SORT_VECTOR_DISTANCE = 4 };
 enum { TSO_MATCH_MAX_SCORE = 0, TSO_MATCH_MAX_WEIGHT = 1, TSO_MATCH_SUM_SCORE = 2 };
-enum { TSO_FLAG_PRIORITIZE_EXACT_MATCH = 1, TSO_FLAG_PRIORITIZE_TOKEN_POSITION = 2, TSO_FLAG_PRIORITIZE_NUM_MATCHING_FIELDS = 4 };
+enum { TSO_FLAG_PRIORITIZE_EXACT_MATCH = 1, TSO_FLAG_PRIORITIZE_TOKEN_POSITION = 2, TSO_FLAG_PRIORITIZE_NUM_MATCHING_FIELDS = 4,
+       TSO_FLAG_RERANK_HYBRID_MATCHES = 0x40 /* hybrid calls: Index::compute_aux_scores after the fusion */ };
 enum { TSO_CFLAG_SYNONYM = 1, TSO_CFLAG_DEMOTE_SYNONYM = 2 };
 
 /* A batch of keyword searches; query q = one Index::search_all_candidates call (src/index.cpp:1794), i.e. a list of

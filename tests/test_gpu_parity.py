@@ -335,6 +335,15 @@ def test_hybrid_search_matches_oracle(vec_coll):
         kv, cnt, found = gi.hybrid_search(b, qv, vp, 256)
         okv, ocnt, ofound = oi.hybrid_search(b, qv, vp, 256)
         assert_kv_equal(kv, cnt, found, okv, ocnt, ofound)
+    # rerank_hybrid_matches: Index::compute_aux_scores after the fusion (vector-only results get a text score, keyword-only ones a
+    # distance, everything is re-ranked and re-scored), on half of the queries, both metrics of field count
+    b3 = _vec_queries(rng, fd, 60, filters, sort, True)
+    for i in range(0, b3.n_queries, 2):
+        b3.q_flags[i] |= 0x40
+    for vp in [S.vec_params(k=0, ef=10, alpha=0.3, fetch_size=10), S.vec_params(k=30, ef=40, alpha=0.8, fetch_size=10)]:
+        kv, cnt, found = gi.hybrid_search(b3, qv[:60], vp, 256)
+        okv, ocnt, ofound = oi.hybrid_search(b3, qv[:60], vp, 256)
+        assert_kv_equal(kv, cnt, found, okv, ocnt, ofound)
     # sort clause with _vector_distance as tie-breaker and a full Topster (the add()-on-sorted-array path)
     sort2 = ((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_VECTOR_DISTANCE, -1, -1, 0), (S.SORT_SEQ_ID, -1, 1, 0))
     b2 = _vec_queries(rng, fd, 40, [], sort2, True)

@@ -113,3 +113,47 @@ def test_hybrid_flat_cutoff_reference_kat_oracle():
     b = S.KwBatch([q], [0], [np.arange(4, dtype=np.uint32)])
     kv, cnt, found = oi.hybrid_search(b, unit(rng.normal(size=8))[None, :].copy(), S.vec_params(k=0, ef=10, alpha=0.3, flat_search_cutoff=100, fetch_size=10), 256)
     assert int(cnt[0]) == 4 and int(found[0]) == 4 and sorted(int(kv["key"][0, i]) for i in range(4)) == [0, 1, 2, 3]
+
+
+def test_rerank_hybrid_matches_scores_follow_the_two_rankings():
+    """Index::compute_aux_scores (src/index.cpp:8793-8923; no reference test sets rerank_hybrid_matches): after it every result carries a text match
+    score and a distance, and its score is 1/keyword_rank * (1 - alpha) + 1/semantic_rank * alpha with the keyword ranking by (text_match_score, key)
+    descending and the semantic one by distance, stable on the keyword order. Recomputed here from the returned records."""
+    import struct
+    from typesense_b200 import synth
+    n, dim = 3000, 16
+    fd = synth.make_string_field(n, 60, 3, 8, seed=2)
+    vec = synth.make_vectors(n, dim, 4).numpy()
+    g = ol.hnsw_build(vec, 8, 40, 100)
+    oi = ol.OracleIndex(n, [fd.flat], [], g)
+    toks = synth.sample_queries(fd, 12, 2, 6)
+    qs = []
+    for row in toks:
+        q = S.Query([S.Combo([[int(t)] for t in row], 2)], topk=40, sort=SORT, num_query_tokens=2)
+        q.flags = FLAGS | S.FLAG_RERANK_HYBRID_MATCHES
+        qs.append(q)
+    qv = synth.make_vectors(12, dim, 8).numpy()
+    alpha = 0.3
+    kv, cnt, found = oi.hybrid_search(S.KwBatch(qs, [0]), qv, S.vec_params(k=20, ef=30, alpha=alpha, fetch_size=10), 64)
+
+    def f2i(x):
+        i = struct.unpack("<i", struct.pack("<f", np.float32(x)))[0]
+        return i ^ 0x7FFFFFFF if i < 0 else i
+    checked = 0
+    for q in range(len(qs)):
+        c = int(cnt[q])
+        if c < 3:
+            continue
+        recs = [(int(kv["text_match_score"][q, i]), int(kv["key"][q, i]), float(kv["vector_distance"][q, i]), int(kv["scores"][q, i, 0])) for i in range(c)]
+        assert all(r[2] != -1.0 for r in recs) and any(r[0] != 0 for r in recs)
+        kw = sorted(recs, key=lambda r: (-r[0], -r[1]))
+        krank = {r[1]: i + 1 for i, r in enumerate(kw)}
+        sem = sorted(kw, key=lambda r: r[2])                       # Python's sort is stable, like std::stable_sort
+        srank = {r[1]: i + 1 for i, r in enumerate(sem)}
+        for r in recs:
+            a = float(np.float32(alpha))                           # vector_query.alpha is a float; the expression is evaluated in double
+            expect = f2i(np.float32((1.0 / krank[r[1]]) * (1.0 - a) + (1.0 / srank[r[1]]) * a))
+            assert r[3] == expect, (q, r, krank[r[1]], srank[r[1]])
+            checked += 1
+        assert [r[3] for r in recs] == sorted([r[3] for r in recs], reverse=True)
+    assert checked > 50

@@ -35,8 +35,10 @@ def test_art_walk_batch_matches_host_walk(mode):
     import subprocess
     import sys
     env = dict(os.environ, TSGPU_ART_CHILD="1")
-    if mode == "frontier":
-        env.update(TSGPU_ART_MODE="frontier", TSGPU_ART_CHUNK="64")
+    if mode == "frontier":        # the default since round 2; tiny chunks and item buffers so that several chunks and the split-on-overflow path run
+        env.update(TSGPU_ART_MODE="frontier", TSGPU_ART_CHUNK="64", TSGPU_ART_CHUNK2="16", TSGPU_ART_ITEMS="4096")
+    else:
+        env.update(TSGPU_ART_MODE="dfs")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider",
                         "-k", "child_art_walk"], env=env, capture_output=True, text=True, timeout=300,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

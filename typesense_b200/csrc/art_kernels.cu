@@ -229,7 +229,10 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
     auto fit = is->fields.find(field);
     if(fit == is->fields.end()) return tsgpu_fail_(TSGPU_ERR_INVALID, "no ART mirror loaded for this field");
     const ArtDev A = fit->second.dev;
-    static const bool frontier_mode = getenv("TSGPU_ART_MODE") && std::string(getenv("TSGPU_ART_MODE")) == "frontier";
+    // default: the frontier form (one thread per node visit). Measured (profiles/r02a_art_gpu_*.json, 200 K tokens, 4096 searches): one thread per
+    // search ("dfs") needs 74 us per 2-typo search and, being one serial chain of dependent loads per search, ~0.7 ms per search when a
+    // multi_search only has a few hundred walks to do (profiles/r02j); the frontier form spreads each search over the machine.
+    static const bool frontier_mode = !(getenv("TSGPU_ART_MODE") && std::string(getenv("TSGPU_ART_MODE")) == "dfs");
     if(frontier_mode) {
         // ---- breadth-first: chunks of searches, one launch per tree level, hits sorted back into the recursion's order on the host
         const ArtState& AS = fit->second;
@@ -255,11 +258,14 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
             if(!h_pre[i]) Q.q[Q.qlen++] = 0;
             Q.min_cost = h_min[i]; Q.max_cost = h_max[i]; Q.prefix = h_pre[i] != 0;
         }
-        const uint32_t chunk = (uint32_t) std::max(1, getenv("TSGPU_ART_CHUNK") ? atoi(getenv("TSGPU_ART_CHUNK")) : 256);
-        const uint32_t item_cap = (uint32_t) std::max(1024, getenv("TSGPU_ART_ITEMS") ? atoi(getenv("TSGPU_ART_ITEMS")) : (4 << 20));
-        const uint32_t hit_cap = std::max<uint32_t>(item_cap, chunk * cap);
+        // searches per chunk: a 2-typo search over a large vocabulary has frontiers of 10^5 items, a 1-typo search of 10^3-10^4; a chunk
+        // that overflows the item buffers is split in two and run again (a single search that does not fit goes back to the host walk)
+        const uint32_t chunk = (uint32_t) std::max(1, getenv("TSGPU_ART_CHUNK") ? atoi(getenv("TSGPU_ART_CHUNK")) : 1024);
+        const uint32_t chunk2 = (uint32_t) std::max(1, getenv("TSGPU_ART_CHUNK2") ? atoi(getenv("TSGPU_ART_CHUNK2")) : 64);
+        const uint32_t item_cap = (uint32_t) std::max(1024, getenv("TSGPU_ART_ITEMS") ? atoi(getenv("TSGPU_ART_ITEMS")) : (16 << 20));
+        const uint32_t hit_cap = std::max<uint32_t>(item_cap, std::max(chunk, chunk2) * cap);
         auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
-        const size_t o_q = 0, o_ids = al((size_t) n * sizeof(ArtQuery)), o_cnt = al(o_ids + (size_t) chunk * 4), o_a = al(o_cnt + 16);
+        const size_t o_q = 0, o_ids = al((size_t) n * sizeof(ArtQuery)), o_cnt = al(o_ids + (size_t) std::max(chunk, chunk2) * 4), o_a = al(o_cnt + 16);
         const size_t o_b = al(o_a + (size_t) item_cap * sizeof(ArtWorkItem)), o_hits = al(o_b + (size_t) item_cap * sizeof(ArtWorkItem));
         const size_t total = o_hits + (size_t) hit_cap * sizeof(Hit);
         if(!is->stream) CUA(cudaStreamCreateWithFlags(&is->stream, cudaStreamNonBlocking));
@@ -276,9 +282,16 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
         uint32_t* d_cnt = (uint32_t*) (d + o_cnt);
         std::vector<Hit> h_hits;
         auto rank_of = [&](int32_t r) { return r < 0 ? AS.leaf_rank[~r] : AS.node_rank[r]; };
-        for(uint32_t base = 0; base < n; base += chunk) {
-            std::vector<uint32_t> ids;
-            for(uint32_t i = base; i < std::min(n, base + chunk); i++) if(flags[i] == 0) ids.push_back(i);
+        std::vector<std::vector<uint32_t>> work;               // chunks still to run (a stack)
+        {
+            std::vector<uint32_t> light, heavy;
+            for(uint32_t i = 0; i < n; i++) if(flags[i] == 0) (h_max[i] >= 2 ? heavy : light).push_back(i);
+            for(size_t b0 = 0; b0 < heavy.size(); b0 += chunk2) work.emplace_back(heavy.begin() + b0, heavy.begin() + std::min(heavy.size(), b0 + chunk2));
+            for(size_t b0 = 0; b0 < light.size(); b0 += chunk) work.emplace_back(light.begin() + b0, light.begin() + std::min(light.size(), b0 + chunk));
+        }
+        while(!work.empty()) {
+            std::vector<uint32_t> ids = std::move(work.back());
+            work.pop_back();
             if(ids.empty()) continue;
             CUA(cudaMemcpyAsync(d + o_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, st));
             CUA(cudaMemsetAsync(d_cnt, 0, 16, st));
@@ -299,7 +312,14 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
                 n_cur = h_cnt[0];
                 cur ^= 1;
             }
-            if(overflow || n_cur) { for(uint32_t i: ids) flags[i] = 4; continue; }       // the host walks this chunk's searches
+            if(overflow || n_cur) {
+                if(ids.size() > 1) {                                  // too many items for the buffers: two half chunks
+                    const size_t half = ids.size() / 2;
+                    work.emplace_back(ids.begin(), ids.begin() + half);
+                    work.emplace_back(ids.begin() + half, ids.end());
+                } else flags[ids[0]] = 4;                             // the host walks this search
+                continue;
+            }
             h_hits.resize(h_cnt[1]);
             if(h_cnt[1]) CUA(cudaMemcpyAsync(h_hits.data(), d + o_hits, (size_t) h_cnt[1] * sizeof(Hit), cudaMemcpyDeviceToHost, st));
             CUA(cudaStreamSynchronize(st));

@@ -126,6 +126,10 @@ struct HybridParams {
     uint32_t kv_stride;
     uint32_t KMAX;               // max topk in batch (shared memory sizing)
     uint32_t VMAX;               // max knn results per query (<= 1024)
+    // rerank_hybrid_matches (Index::compute_aux_scores): the query vectors and the vector index for the keyword-only results' distances
+    const float* queries;        // [nq * dim]
+    const float* vectors;        // [n_nodes * dim]
+    uint32_t dim, n_nodes;
 };
 
 __device__ __forceinline__ bool kvo_greater(const KVOut& a, const KVOut& b) {
@@ -152,6 +156,43 @@ __device__ bool is_keyword_match(const HybridParams& P, const QDesc& qd, uint32_
         if(all) return true;
     }
     return false;
+}
+
+// compute_aggregated_score for ONE doc over the tokens of the query's first combination (every token optional, total_cost 0):
+// what compute_aux_scores gives a result that only the vector query found (src/index.cpp:8801-8845)
+__device__ int64_t aux_text_score(const HybridParams& P, const QDesc& qd, uint32_t doc) {
+    if(qd.combo_end == qd.combo_begin) return 0;
+    const CDesc& cd = P.cd[qd.combo_begin];
+    ScoreParams SP;
+    SP.total_cost = 0; SP.num_query_tokens = cd.n_rows; SP.syn_orig_num_tokens = -1; SP.orig_num_tokens = (int32_t) cd.n_rows;
+    SP.is_synonym_query = 0; SP.demote_synonym_match = 0;
+    SP.prioritize_exact_match = qd.flags & 1; SP.prioritize_token_position = (qd.flags >> 1) & 1; SP.prioritize_num_matching_fields = (qd.flags >> 2) & 1;
+    SP.match_type = qd.match_type;
+    FieldAgg agg; field_agg_init(agg);
+    uint32_t found_rows = 0, query_len = 0;
+    for(uint32_t f = 0; f < P.F; f++) {
+        const DevField& g = P.ix.fields[P.field_ids[f]];
+        RawTok toks[kMaxTokens];
+        int nt = 0;
+        for(uint32_t r = 0; r < cd.n_rows; r++) {
+            const uint32_t l = cd.lists[r * P.F + f];
+            if(l == kNone) continue;
+            const uint32_t b0 = g.list_blk_off[l], b1 = g.list_blk_off[l + 1];
+            if(b1 == b0) continue;
+            const uint32_t h = probe_list(g, l, b0, b1 - 1, doc);
+            if(h == kNone) continue;
+            const unsigned long long p = g.list_off[l] + h;
+            const unsigned long long o0 = g.pos_off[p], o1 = g.pos_off[p + 1];
+            toks[nt].p = g.positions + o0; toks[nt].n = (uint32_t) (o1 - o0); nt++;
+            found_rows |= 1u << r;
+        }
+        if(nt == 0) continue;
+        const bool single_exact = (SP.total_cost == 0 && SP.num_query_tokens == 1);
+        const int64_t fs = score_field(SP, (g.is_array & kFieldIsArray) != 0, single_exact, toks, nt);
+        field_agg_add(agg, SP.match_type, fs, (int64_t) qd.field_weight[f]);
+    }
+    query_len = __popc(found_rows);
+    return (int64_t) field_agg_finish(agg, SP, query_len);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -355,6 +396,58 @@ hybrid_fuse_kernel(const __grid_constant__ HybridParams P) {
         if(lane == 0) { s_size = size; s_vec_only_new = vec_new; }
     }
     __syncthreads();
+
+    // ---- rerank_hybrid_matches: Index::compute_aux_scores (src/index.cpp:8793-8923) on the fused Topster
+    if((qd.rerank) && s_size) {
+        const uint32_t n = s_size;                       // data slots 0 .. n-1 hold the entries (slots are handed out in order)
+        for(uint32_t i = tid; i < n; i += kThreads) {    // results only the vector query found: their text match score
+            KVOut& kv = data[i];
+            if(kv.text_match_score == 0) kv.text_match_score = aux_text_score(P, qd, (uint32_t) kv.key);
+        }
+        {   // results only the keyword query found: their vector distance (one warp per result, W128 order as everywhere)
+            const uint32_t lane2 = tid & 31, warp2 = tid >> 5;
+            const float* qv = P.queries + (size_t) q * P.dim;
+            for(uint32_t i = warp2; i < n; i += kThreads / 32) {
+                const bool need = data[i].vector_distance == -1.0f && data[i].text_match_score != 0 && (uint32_t) data[i].key < P.n_nodes;
+                if(!need) continue;                        // warp-uniform
+                const float* v = P.vectors + (size_t) (uint32_t) data[i].key * P.dim;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for(uint32_t sgm = 0; sgm * 128 < P.dim; sgm++) {
+                    const uint32_t e = sgm * 128 + 4 * lane2;
+                    if(e + 0 < P.dim) a0 = __fmaf_rn(qv[e + 0], __ldg(v + e + 0), a0);
+                    if(e + 1 < P.dim) a1 = __fmaf_rn(qv[e + 1], __ldg(v + e + 1), a1);
+                    if(e + 2 < P.dim) a2 = __fmaf_rn(qv[e + 2], __ldg(v + e + 2), a2);
+                    if(e + 3 < P.dim) a3 = __fmaf_rn(qv[e + 3], __ldg(v + e + 3), a3);
+                }
+                float t = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+                for(int off = 16; off >= 1; off >>= 1) t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, off));
+                if(lane2 == 0) data[i].vector_distance = 1.0f - t;
+            }
+        }
+        __syncthreads();
+        // ranks: keyword rank by (text_match_score, key) descending; semantic rank by distance ascending, stable on the keyword order
+        const double alpha = (double) P.vp.alpha;
+        for(uint32_t i = tid; i < n; i += kThreads) {
+            const int64_t ti = data[i].text_match_score; const uint32_t ki = (uint32_t) data[i].key; const float di = data[i].vector_distance;
+            uint32_t kr = 1;
+            for(uint32_t j = 0; j < n; j++) { const int64_t tj = data[j].text_match_score; if(tj > ti || (tj == ti && (uint32_t) data[j].key > ki)) kr++; }
+            uint32_t sr = 1;
+            for(uint32_t j = 0; j < n; j++) {
+                if(j == i) continue;
+                const float dj = data[j].vector_distance;
+                if(dj < di) sr++;
+                else if(dj == di) { const int64_t tj = data[j].text_match_score; if(tj > ti || (tj == ti && (uint32_t) data[j].key > ki)) sr++; }
+            }
+            data[i].distinct_key = (uint64_t) float_to_int64(__double2float_rn((1.0 / (double) kr) * (1.0 - alpha) + (1.0 / (double) sr) * alpha));   // parked until every rank is known
+        }
+        __syncthreads();
+        for(uint32_t i = tid; i < n; i += kThreads) {
+            const int m = data[i].match_score_index;
+            if(m >= 0 && m <= 2) data[i].scores[m] = (int64_t) data[i].distinct_key;
+            data[i].distinct_key = data[i].key;
+        }
+        __syncthreads();
+    }
 
     // ---- final topster->sort(): stable_sort by KV order (total order: keys are unique)
     const uint32_t size = s_size;

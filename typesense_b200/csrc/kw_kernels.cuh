@@ -58,7 +58,8 @@ struct QDesc {
     uint8_t  field_weight[kMaxFieldSlots];
     uint8_t  filter_empty;             // filter given but matches no doc (src/index.cpp:4823-4826)
     uint8_t  keep_all;                 // found_bitmap is the query's all_result_ids and outlives the call (facets, export)
-    uint8_t  pad[2];
+    uint8_t  rerank;                   // hybrid calls: compute_aux_scores after the fusion (rerank_hybrid_matches)
+    uint8_t  pad[1];
 };
 
 struct CDesc {

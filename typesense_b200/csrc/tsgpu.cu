@@ -302,7 +302,7 @@ tsgpu_status build_kw_plan(tsgpu_index* idx, const tsgpu_kw_batch* b, bool with_
                 qd.sort_col[i] = idx->sort_cols[col];
             }
         }
-        qd.flags = b->q_flags[q] & 0x7F; qd.match_type = b->q_match_type[q]; qd.num_query_tokens = b->q_num_query_tokens[q];
+        qd.flags = b->q_flags[q] & 0x3F; qd.rerank = (b->q_flags[q] & TSGPU_FLAG_RERANK_HYBRID_MATCHES) ? 1 : 0; qd.match_type = b->q_match_type[q]; qd.num_query_tokens = b->q_num_query_tokens[q];
         qd.keep_all = (b->q_flags[q] & TSGPU_QFLAG_KEEP_ALL_IDS) ? 1 : 0;
         for(uint32_t f = 0; f < (uint32_t) kMaxFieldSlots; f++) qd.field_weight[f] = f < F ? b->q_field_weight[(size_t) q * F + f] : 0;
         qd.n_excl = b->q_excl_off[q + 1] - b->q_excl_off[q];
@@ -849,6 +849,7 @@ struct VecStage {
     KnnDeviceOut knn{};
     const float* flat_dist = nullptr; const uint32_t* flat_ids = nullptr; const unsigned long long* flat_off = nullptr;
     const uint8_t* d_is_flat = nullptr;
+    const float* d_queries = nullptr;
     bool any_flat = false;
     uint32_t k = 0;
 };
@@ -888,6 +889,7 @@ tsgpu_status run_vector_stage(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan&
             CU(cudaMemcpyAsync(base + o_fi + foff[q] * 4, pl.q_filter_ids[q], pl.q_filter_n[q] * 4, cudaMemcpyDeviceToDevice, st));
     }
     vs.d_is_flat = base + o_if;
+    vs.d_queries = reinterpret_cast<const float*>(base + o_q);
     vs.flat_off = reinterpret_cast<const unsigned long long*>(base + o_fo);
     vs.flat_ids = reinterpret_cast<const uint32_t*>(base + o_fi);
     vs.flat_dist = reinterpret_cast<const float*>(base + o_fd);
@@ -1566,6 +1568,7 @@ static tsgpu_status vec_or_hybrid(tsgpu_index* idx, const tsgpu_kw_batch* b, con
         P.vp = dvp;
         P.out_kv = d_kv; P.out_count = d_cnt; P.out_found = d_found; P.kv_stride = kv_stride;
         P.KMAX = pl.KMAX; P.VMAX = k;
+        P.queries = vs.d_queries; P.vectors = idx->hnsw.vectors; P.dim = idx->hnsw.dim; P.n_nodes = idx->hnsw.n_nodes;
         const uint32_t KP2 = pow2_ceil(pl.KMAX), VP2 = pow2_ceil(k);
         const size_t smem = (size_t) pl.KMAX * sizeof(KVOut) + (size_t) (KP2 + 2) * 2 + (size_t) VP2 * (12 + 24 + 2) + 48;
         CU(cudaFuncSetAttribute(tsf::hybrid_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024)));

@@ -18,6 +18,7 @@ MAX_TOKENS = 16
 SORT_NONE, SORT_TEXT_MATCH, SORT_SEQ_ID, SORT_NUMERIC, SORT_VECTOR_DISTANCE = 0, 1, 2, 3, 4
 MATCH_MAX_SCORE, MATCH_MAX_WEIGHT, MATCH_SUM_SCORE = 0, 1, 2
 FLAG_PRIORITIZE_EXACT_MATCH, FLAG_PRIORITIZE_TOKEN_POSITION, FLAG_PRIORITIZE_NUM_MATCHING_FIELDS = 1, 2, 4
+FLAG_RERANK_HYBRID_MATCHES, FLAG_KEEP_ALL_IDS = 0x40, 0x80
 CFLAG_SYNONYM, CFLAG_DEMOTE_SYNONYM = 1, 2
 
 u8p, u16p, u32p, u64p = (C.POINTER(C.c_uint8), C.POINTER(C.c_uint16), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64))
