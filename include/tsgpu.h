@@ -167,6 +167,16 @@ tsgpu_status tsgpu_index_export_hnsw(tsgpu_index* idx, uint8_t* levels, uint32_t
 /* Persistent filter (a mirrored filter leaf / cached filter result): sorted seq_ids -> device bitmap. */
 tsgpu_status tsgpu_filter_create(tsgpu_index* idx, const uint32_t* ids, size_t n, int32_t* out_handle);
 tsgpu_status tsgpu_filter_destroy(tsgpu_index* idx, int32_t handle);
+/* filter_by evaluated ON THE DEVICE: the result never visits the host.
+ * A numeric / bool leaf (filter_result_iterator_t over num_tree_t, src/filter_result_iterator.cpp:1507-1700, src/num_tree.cpp): one pass
+ * over the mirrored column `sort_col` (tsgpu_index_load_sort_column; floats as float_to_int64_t, bools as 0 / 1). Docs without a value
+ * match no comparator; TSGPU_CMP_NE is "every doc but the equal ones" (apply_not_equals). RANGE = [v1, v2] (`field:[v1..v2]`). */
+enum { TSGPU_CMP_EQ = 0, TSGPU_CMP_NE = 1, TSGPU_CMP_LT = 2, TSGPU_CMP_LE = 3, TSGPU_CMP_GT = 4, TSGPU_CMP_GE = 5, TSGPU_CMP_RANGE = 6 };
+tsgpu_status tsgpu_filter_numeric(tsgpu_index* idx, uint32_t sort_col, int op, int64_t v1, int64_t v2, int32_t* out_handle, size_t* out_n);
+/* The tree's inner nodes on two persistent filters: op = TSGPU_SET_AND / TSGPU_SET_OR / TSGPU_SET_EXCLUDE (a AND NOT b); string leaves come from
+ * tsgpu_exact_matches / tsgpu_prefix_matches / tsgpu_phrase_matches + tsgpu_filter_create. */
+tsgpu_status tsgpu_filter_combine(tsgpu_index* idx, int op, int32_t a, int32_t b, int32_t* out_handle, size_t* out_n);
+tsgpu_status tsgpu_filter_ids(tsgpu_index* idx, int32_t handle, uint32_t* out_ids, size_t cap, size_t* out_n);
 
 /* ---- search -------------------------------------------------------------------------------------------------- */
 /* posting_list_t::intersect / posting_t::intersect (src/posting_list.cpp:708, src/posting.cpp:388): k-way AND of

@@ -266,6 +266,56 @@ tsgpu_status tsgpu_filter_create(tsgpu_index* idx, const uint32_t* ids, size_t n
     *out_handle = -((int32_t) d->filters.size() - 1 + 2);
     return TSGPU_OK;
 }
+// filter_by leaves / tree answered on the host (the comparators of src/num_tree.cpp over the dense column)
+tsgpu_status tsgpu_filter_numeric(tsgpu_index* idx, uint32_t col, int op, int64_t v1, int64_t v2, int32_t* out_handle, size_t* out_n) {
+    Double* d = D(idx);
+    if(col >= d->cols.size()) { g_err = "column out of range"; return TSGPU_ERR_INVALID; }
+    const std::vector<int64_t>& c = *d->cols[col];
+    std::vector<uint32_t> ids;
+    for(uint32_t i = 0; i < d->n_docs; i++) {
+        const int64_t v = c[i];
+        const bool has = v != INT64_MIN;
+        bool m;
+        switch(op) {
+            case 0: m = has && v == v1; break;
+            case 1: m = !(has && v == v1); break;
+            case 2: m = has && v < v1; break;
+            case 3: m = has && v <= v1; break;
+            case 4: m = has && v > v1; break;
+            case 5: m = has && v >= v1; break;
+            default: m = has && v >= v1 && v <= v2; break;
+        }
+        if(m) ids.push_back(i);
+    }
+    if(out_n) *out_n = ids.size();
+    d->filters.push_back(std::move(ids));
+    *out_handle = -((int32_t) d->filters.size() - 1 + 2);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_filter_combine(tsgpu_index* idx, int op, int32_t a, int32_t b, int32_t* out_handle, size_t* out_n) {
+    Double* d = D(idx);
+    const size_t ia = (size_t) (-(a + 2)), ib = (size_t) (-(b + 2));
+    if(a > -2 || b > -2 || ia >= d->filters.size() || ib >= d->filters.size()) { g_err = "unknown filter handle"; return TSGPU_ERR_INVALID; }
+    const auto& A = d->filters[ia]; const auto& B = d->filters[ib];
+    std::vector<uint32_t> out(A.size() + B.size() + 1);
+    size_t n = op == 0 ? tso_and_scalar(A.data(), A.size(), B.data(), B.size(), out.data())
+             : op == 1 ? tso_or_scalar(A.data(), A.size(), B.data(), B.size(), out.data())
+                       : tso_exclude_scalar(A.data(), A.size(), B.data(), B.size(), out.data());
+    out.resize(n);
+    if(out_n) *out_n = n;
+    d->filters.push_back(std::move(out));
+    *out_handle = -((int32_t) d->filters.size() - 1 + 2);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_filter_ids(tsgpu_index* idx, int32_t handle, uint32_t* out_ids, size_t cap, size_t* out_n) {
+    Double* d = D(idx);
+    const size_t h = (size_t) (-(handle + 2));
+    if(handle > -2 || h >= d->filters.size()) { g_err = "bad filter handle"; return TSGPU_ERR_INVALID; }
+    *out_n = d->filters[h].size();
+    if(*out_n > cap) { g_err = "output buffer too small"; return TSGPU_ERR_CAPACITY; }
+    std::copy(d->filters[h].begin(), d->filters[h].end(), out_ids);
+    return TSGPU_OK;
+}
 tsgpu_status tsgpu_filter_destroy(tsgpu_index* idx, int32_t handle) {
     Double* d = D(idx);
     const size_t h = (size_t) (-(handle + 2));

@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("TSGPU_LIB_PATH") or os.path.join(HERE, "libtsgpu.so")
 
 EXPORTS = [
     "tsgpu_last_error", "tsgpu_device_count", "tsgpu_index_create", "tsgpu_index_destroy", "tsgpu_index_load_field",
-    "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_index_build_hnsw", "tsgpu_index_hnsw_info", "tsgpu_index_export_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy",
+    "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_index_build_hnsw", "tsgpu_index_hnsw_info", "tsgpu_index_export_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy", "tsgpu_filter_numeric", "tsgpu_filter_combine", "tsgpu_filter_ids", "tsgpu_scored_ids_search_batch",
     "tsgpu_intersect", "tsgpu_contains_atleast_one", "tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches", "tsgpu_ids_setop", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
     "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats", "tsgpu_debug_knn_work", "tsgpu_comm_unique_id", "tsgpu_comm_init", "tsgpu_comm_destroy", "tsgpu_comm_gather", "tsgpu_comm_last_ms", "tsgpu_hybrid_fuse_batch", "tsgpu_index_load_facet", "tsgpu_facet_counts", "tsgpu_facet_counts_last", "tsgpu_all_result_ids_last", "tsgpu_index_load_art", "tsgpu_art_walk_batch",
 ]
@@ -62,6 +62,10 @@ def declare(L):
         L.tsgpu_index_export_hnsw.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.tsgpu_filter_create.argtypes = [vp, C.c_void_p, C.c_size_t, i32p]
         L.tsgpu_filter_destroy.argtypes = [vp, C.c_int32]
+        L.tsgpu_filter_numeric.argtypes = [vp, C.c_uint32, C.c_int, C.c_int64, C.c_int64, i32p, C.POINTER(C.c_size_t)]
+        L.tsgpu_filter_combine.argtypes = [vp, C.c_int, C.c_int32, C.c_int32, i32p, C.POINTER(C.c_size_t)]
+        L.tsgpu_filter_ids.argtypes = [vp, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.tsgpu_scored_ids_search_batch.argtypes = [vp, C.POINTER(KwBatchStruct), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.tsgpu_intersect.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.tsgpu_contains_atleast_one.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, C.c_size_t, C.POINTER(C.c_int)]
         L.tsgpu_ids_setop.argtypes = [vp, C.c_int, u32p, C.c_size_t, u32p, C.c_size_t, u32p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -222,6 +226,26 @@ class GpuIndex:
         out = C.c_int32(0)
         _ck(self.L.tsgpu_filter_create(self.h, _addr(ids) if n else None, n, C.byref(out)))
         return out.value
+
+    # ---- filter_by on the device
+    CMP = {"=": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5, "range": 6}
+
+    def filter_numeric(self, col: int, op: str, v1: int, v2: int = 0):
+        """A numeric / bool leaf evaluated over the mirrored column: (handle, number of docs)."""
+        h, n = C.c_int32(0), C.c_size_t(0)
+        _ck(self.L.tsgpu_filter_numeric(self.h, col, self.CMP[op], int(v1), int(v2), C.byref(h), C.byref(n)))
+        return h.value, n.value
+
+    def filter_combine(self, op: int, a: int, b: int):
+        h, n = C.c_int32(0), C.c_size_t(0)
+        _ck(self.L.tsgpu_filter_combine(self.h, op, a, b, C.byref(h), C.byref(n)))
+        return h.value, n.value
+
+    def filter_ids(self, handle: int, cap: int) -> np.ndarray:
+        out = np.zeros(max(cap, 1), np.uint32)
+        n = C.c_size_t(0)
+        _ck(self.L.tsgpu_filter_ids(self.h, handle, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value]
 
     # ---- search
     def contains_atleast_one(self, field: int, lst: int, ids) -> bool:

@@ -1056,6 +1056,46 @@ contains_any_kernel(const __grid_constant__ IndexDev ix, uint32_t field, uint32_
     if(__any_sync(0xffffffffu, hit) && (threadIdx.x & 31) == 0) atomicExch(out, 1);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// filter_by evaluated on the device. A numeric / bool leaf (filter_result_iterator_t over num_tree_t,
+// src/filter_result_iterator.cpp:1507-1700, src/num_tree.cpp:35-250) is one pass over the field's dense column: 32 docs per
+// thread word, straight into the filter bitmap in HBM — no id list crosses the host. A doc without a value (INT64_MIN, it is not
+// in the reference's tree) matches no comparator; `!=` is "every doc minus the equal ones" (apply_not_equals), so it does
+// match docs without a value, as in the reference.
+enum { kCmpEq = 0, kCmpNe = 1, kCmpLt = 2, kCmpLe = 3, kCmpGt = 4, kCmpGe = 5, kCmpRange = 6 };
+__global__ void __launch_bounds__(256)
+filter_numeric_kernel(const int64_t* __restrict__ col, uint32_t n_docs, int op, int64_t v1, int64_t v2, uint32_t* __restrict__ bitmap) {
+    const uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t base = wi << 5;
+    if(base >= n_docs) return;
+    uint32_t w = 0;
+    const uint32_t n = min(32u, n_docs - base);
+    for(uint32_t k = 0; k < n; k++) {
+        const int64_t v = __ldg(col + base + k);
+        const bool has = v != INT64_MIN;
+        bool m;
+        switch(op) {
+            case kCmpEq: m = has && v == v1; break;
+            case kCmpNe: m = !(has && v == v1); break;
+            case kCmpLt: m = has && v < v1; break;
+            case kCmpLe: m = has && v <= v1; break;
+            case kCmpGt: m = has && v > v1; break;
+            case kCmpGe: m = has && v >= v1; break;
+            default: m = has && v >= v1 && v <= v2; break;
+        }
+        w |= (m ? 1u : 0u) << k;
+    }
+    bitmap[wi] = w;
+}
+// the AND / OR / AND-NOT nodes of the filter tree (filter_result_iterator_t::and_filter_iterators / or_filter_iterators) on bitmaps
+__global__ void __launch_bounds__(256)
+filter_combine_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t n_words, int op, uint32_t* __restrict__ out) {
+    const uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if(wi >= n_words) return;
+    const uint32_t x = a[wi], y = b[wi];
+    out[wi] = op == 0 ? (x & y) : op == 1 ? (x | y) : (x & ~y);
+}
+
 // single-CTA exclusive scan of tile counts (n_tiles <= a few hundred thousand)
 __global__ void __launch_bounds__(1024)
 scan_tiles_kernel(const uint32_t* __restrict__ cnt, uint32_t n, unsigned long long* __restrict__ off, unsigned long long* total) {

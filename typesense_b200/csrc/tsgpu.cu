@@ -1138,6 +1138,98 @@ tsgpu_status tsgpu_filter_create(tsgpu_index* idx, const uint32_t* ids, size_t n
     return TSGPU_OK;
 }
 
+// a bitmap already on the device -> a persistent filter (its ascending id list is extracted from the bits: the flat vector path
+// and the wildcard search read ids)
+static tsgpu_status filter_from_bitmap(tsgpu_index* idx, uint32_t* d_bitmap, int32_t* out_handle, size_t* out_n) {
+    cudaStream_t st = idx->stream;
+    const uint32_t n_words = (uint32_t) (((size_t) idx->n_docs + 31) / 32);
+    const uint32_t n_tiles = (n_words + kThreads - 1) / kThreads;
+    const size_t o_off = ((size_t) n_tiles * 4 + 255) & ~size_t(255);
+    const size_t o_tot = o_off + (size_t) n_tiles * 8;
+    CU(idx->d_isect.reserve(o_tot + 64));
+    unsigned char* base = idx->d_isect.as<unsigned char>();
+    setop_count_kernel<<<n_tiles, kThreads, 0, st>>>(d_bitmap, d_bitmap, n_words, 0, reinterpret_cast<uint32_t*>(base));
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<uint32_t*>(base), n_tiles, reinterpret_cast<unsigned long long*>(base + o_off),
+                                          reinterpret_cast<unsigned long long*>(base + o_tot));
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, base + o_tot, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    Filter f;
+    f.d_bitmap = d_bitmap;
+    CU(cudaMalloc(&f.d_ids, std::max<size_t>((size_t) total, 4) * 4));
+    setop_extract_kernel<<<n_tiles, kThreads, 0, st>>>(d_bitmap, n_words, reinterpret_cast<unsigned long long*>(base + o_off), f.d_ids, (size_t) total);
+    idx->stats.launches_total += 3;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    f.n = (size_t) total; f.live = true;
+    idx->filters.push_back(f);
+    *out_handle = -((int32_t) idx->filters.size() - 1) - 2;
+    if(out_n) *out_n = (size_t) total;
+    return TSGPU_OK;
+}
+
+tsgpu_status tsgpu_filter_numeric(tsgpu_index* idx, uint32_t sort_col, int op, int64_t v1, int64_t v2, int32_t* out_handle, size_t* out_n) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!out_handle) return fail(TSGPU_ERR_INVALID, "null argument");
+    if(op < 0 || op > 6) return fail(TSGPU_ERR_INVALID, "unknown comparator");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if(sort_col >= idx->sort_cols.size()) return fail(TSGPU_ERR_INVALID, "column out of range");
+    begin_call(idx);
+    const size_t words = ((size_t) idx->n_docs + 31) / 32;
+    uint32_t* bm = nullptr;
+    CU(cudaMalloc(&bm, std::max<size_t>((words + 3) & ~size_t(3), 4) * 4));
+    CU(cudaMemsetAsync(bm, 0, std::max<size_t>((words + 3) & ~size_t(3), 4) * 4, idx->stream));
+    CU(cudaEventRecord(idx->ev[1], idx->stream));
+    if(words) filter_numeric_kernel<<<(unsigned) ((words + 255) / 256), 256, 0, idx->stream>>>(idx->sort_cols[sort_col], idx->n_docs, op, v1, v2, bm);
+    idx->stats.launches_total++;
+    CU(cudaGetLastError());
+    s = filter_from_bitmap(idx, bm, out_handle, out_n);
+    if(s) { cudaFree(bm); return s; }
+    CU(cudaEventRecord(idx->ev[6], idx->stream)); CU(cudaEventRecord(idx->ev[2], idx->stream));
+    return end_call(idx, true, false);
+}
+
+tsgpu_status tsgpu_filter_combine(tsgpu_index* idx, int op, int32_t a, int32_t b, int32_t* out_handle, size_t* out_n) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!out_handle) return fail(TSGPU_ERR_INVALID, "null argument");
+    if(op < TSGPU_SET_AND || op > TSGPU_SET_EXCLUDE) return fail(TSGPU_ERR_INVALID, "unknown set operation");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    auto get = [&](int32_t h) -> const Filter* {
+        if(h > -2) return nullptr;
+        const size_t i = (size_t) (-(h + 2));
+        return (i < idx->filters.size() && idx->filters[i].live) ? &idx->filters[i] : nullptr;
+    };
+    const Filter* fa = get(a); const Filter* fb = get(b);
+    if(!fa || !fb) return fail(TSGPU_ERR_INVALID, "unknown filter handle");
+    begin_call(idx);
+    const size_t words = ((size_t) idx->n_docs + 31) / 32;
+    uint32_t* bm = nullptr;
+    CU(cudaMalloc(&bm, std::max<size_t>((words + 3) & ~size_t(3), 4) * 4));
+    CU(cudaMemsetAsync(bm, 0, std::max<size_t>((words + 3) & ~size_t(3), 4) * 4, idx->stream));
+    CU(cudaEventRecord(idx->ev[1], idx->stream));
+    if(words) filter_combine_kernel<<<(unsigned) ((words + 255) / 256), 256, 0, idx->stream>>>(fa->d_bitmap, fb->d_bitmap, (uint32_t) words, op, bm);
+    idx->stats.launches_total++;
+    CU(cudaGetLastError());
+    s = filter_from_bitmap(idx, bm, out_handle, out_n);
+    if(s) { cudaFree(bm); return s; }
+    CU(cudaEventRecord(idx->ev[6], idx->stream)); CU(cudaEventRecord(idx->ev[2], idx->stream));
+    return end_call(idx, true, false);
+}
+
+/* ids of a persistent filter (ascending), e.g. to hand a device-evaluated filter to host-side code */
+tsgpu_status tsgpu_filter_ids(tsgpu_index* idx, int32_t handle, uint32_t* out_ids, size_t cap, size_t* out_n) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!out_n) return fail(TSGPU_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if(handle > -2) return fail(TSGPU_ERR_INVALID, "bad filter handle");
+    const size_t h = (size_t) (-(handle + 2));
+    if(h >= idx->filters.size() || !idx->filters[h].live) return fail(TSGPU_ERR_INVALID, "bad filter handle");
+    *out_n = idx->filters[h].n;
+    if(idx->filters[h].n > cap) return fail(TSGPU_ERR_CAPACITY, "output buffer too small");
+    if(idx->filters[h].n) CU(cudaMemcpy(out_ids, idx->filters[h].d_ids, idx->filters[h].n * 4, cudaMemcpyDefault));
+    return TSGPU_OK;
+}
+
 tsgpu_status tsgpu_filter_destroy(tsgpu_index* idx, int32_t handle) {
     tsgpu_status s = check_device(idx); if(s) return s;
     std::lock_guard<std::mutex> lk(idx->mu);
