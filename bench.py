@@ -71,6 +71,8 @@ def parse():
     ap.add_argument("--recall-queries", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", default="hnsw", choices=["hnsw", "bulk"], help="hnsw: built by tsgpu_index_build_hnsw; bulk: r01's harness stand-in")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the secondary BASELINE.json configurations (other_configs)")
+    ap.add_argument("--e2e-depth", type=int, default=2, help="multi_search calls in flight in the end-to-end leg (1 = strictly one after the other)")
     ap.add_argument("--no-graph-cache", action="store_true", help="always rebuild the HNSW graph (default: reuse /tmp/tsgpu_bench_cache)")
     ap.add_argument("--exp-sorted-vectors", action="store_true",
                     help="experiment only: store vectors in cluster order (seq_id locality) to measure what row locality is worth")
@@ -397,6 +399,81 @@ def workload_config(args, batch):
             "kw_scoring": "r01 local-array scorer (TSGPU_REG_SCORE=0)" if os.environ.get("TSGPU_REG_SCORE") == "0" else "register-resident (default)"}
 
 
+# ------------------------------------------------------------------------------------------------ secondary configurations
+def other_configs(args, w, hi, gi, sl, qv_pin, host_opt, hbm_peak):
+    """BASELINE.json's other configurations, measured on the same box next to the headline (rank 0, N = 1, outside its timed
+    regions): parity for each is in tests/; these are the timings.
+      configs[0]  3-way posting-list AND in the reference's own DISABLED_BenchmarkIntersection shape (tools/bench_intersect.py)
+      configs[1]  10 M-doc 3-term keyword search with typo tolerance, Topster 250 -> 100 hits: query strings through the host layer
+      configs[2]  HNSW k=100 (ef 10 -> effective 100), inner product, batch 1024, no filter — on THIS index (10 M x 768; the named one is 5 M)
+      configs[4]-shaped  faceted keyword search: all_result_ids kept on the device + facet counts over a 50 K-value facet (1-5 values per doc)"""
+    import torch
+    from typesense_b200 import capi, hostapi, synth, structs as S
+    out = {}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_intersect
+        out["intersect_3way_100k"] = bench_intersect.run(cpu_reps=5)
+    except Exception as e:
+        out["intersect_3way_100k"] = {"error": str(e)[:200]}
+    try:        # configs[1]: keyword + typo through the host layer
+        sb, _, packed, qf = sl[0]
+        nl = sb.n_queries
+        kvb = (np.zeros((nl, 100), S.KV_DTYPE), np.zeros(nl, np.uint32), np.zeros(nl, np.uint32))
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            _, _, _, st = hi.multi_search("title", "points", None, 100, qf, None, host_opt, packed=packed, out=kvb)
+            ts.append(time.perf_counter() - t0)
+        out["keyword10m_typo"] = {"queries": nl, "ms_per_batch": 1000 * min(ts), "queries_per_s": nl / min(ts), "host_rounds": st,
+                                  "path": "query strings (30 % misspelt, half filtered) -> host layer -> device; keyword only"}
+    except Exception as e:
+        out["keyword10m_typo"] = {"error": str(e)[:200]}
+    try:        # configs[2]: pure kNN
+        nqv = min(1024, qv_pin[0].shape[0])
+        qv = qv_pin[0].numpy()[:nqv]
+        gi.knn(qv, 100, 10)
+        ts, sts = [], []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            gi.knn(qv, 100, 10)
+            ts.append(time.perf_counter() - t0)
+            sts.append(gi.stats())
+        st = sts[-1]
+        algo = st["knn_dist"] * 4 * w.dim + st["knn_expanded"] * 4 * 33
+        out["hnsw_knn_batch1024"] = {"queries": nqv, "nodes": w.n_docs, "ms_per_batch": 1000 * min(ts), "queries_per_s": nqv / min(ts), "kernel_ms": st["ms_knn"],
+                                     "dist_per_query": st["knn_dist"] / nqv, "expanded_per_query": st["knn_expanded"] / nqv,
+                                     "roofline_frac": algo / (st["ms_knn"] * 1e-3) / 1e9 / hbm_peak if st["ms_knn"] > 0 else None}
+    except Exception as e:
+        out["hnsw_knn_batch1024"] = {"error": str(e)[:200]}
+    try:        # configs[4]-shaped: facets over all_result_ids
+        n_values = 50000
+        rng = np.random.default_rng(99)
+        per = rng.integers(1, 6, w.n_docs)
+        off = np.zeros(w.n_docs + 1, np.uint64); off[1:] = np.cumsum(per)
+        cdf = np.cumsum(np.arange(1, n_values + 1, dtype=np.float64) ** -1.07); cdf /= cdf[-1]
+        vals = np.minimum(np.searchsorted(cdf, rng.random(int(off[-1]))), n_values - 1).astype(np.uint32)
+        fac = gi.load_facet(n_values, off, vals)
+        sb = sl[0][0]
+        nf = min(512, sb.n_queries)                         # 512 faceted queries per call: 512 x 1.25 MB of all_result_ids bitmaps, 512 x 50 K histograms
+        hb = sb.head(nf)
+        flags0 = hb.q_flags.copy()
+        hb.q_flags = hb.q_flags.copy(); hb.q_flags[:nf] |= capi.QFLAG_KEEP_ALL_IDS
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            gi.keyword_search(hb, 100)
+            t1 = time.perf_counter()
+            fc, fn, fdis = gi.facet_counts_last(fac, nf, 10)
+            ts.append((t1 - t0, time.perf_counter() - t1, gi.stats()["ms_total"]))
+        best = min(ts, key=lambda x: x[0] + x[1])
+        out["faceted_keyword"] = {"queries": nf, "facet_values": n_values, "values_per_doc": "1-5", "search_ms": 1000 * best[0], "facet_ms": 1000 * best[1],
+                                  "facet_device_ms": best[2], "queries_per_s": nf / (best[0] + best[1]), "mean_distinct_values": float(fdis.mean())}
+    except Exception as e:
+        out["faceted_keyword"] = {"error": str(e)[:200]}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ tsgpu arm
 def run_tsgpu(args, rank, world, local_rank):
     """One process per GPU, a full replica each. STRONG scaling (BASELINE config 4 literally): every step is ONE multi_search batch
@@ -457,8 +534,9 @@ def run_tsgpu(args, rank, world, local_rank):
     qv_pin = [torch.from_numpy(np.ascontiguousarray(x[1])).pin_memory() for x in sl] if hybrid else [None] * n_b
     all_dev = torch.zeros(world * max_nl * rec, dtype=torch.uint8, device=device) if (world > 1 and rank == 0) else None
     all_pin = torch.zeros(world * max_nl * rec, dtype=torch.uint8).pin_memory() if (world > 1 and rank == 0) else None
-    host_kv = np.zeros((max_nl, stride), S.KV_DTYPE)
-    host_cnt = np.zeros(max_nl, np.uint32); host_fnd = np.zeros(max_nl, np.uint32)
+    E2E_DEPTH = max(1, args.e2e_depth)              # multi_search calls in flight in the end-to-end leg (client threads of a server)
+    host_bufs = [(np.zeros((max_nl, stride), S.KV_DTYPE), np.zeros(max_nl, np.uint32), np.zeros(max_nl, np.uint32)) for _ in range(E2E_DEPTH)]
+    host_kv, host_cnt, host_fnd = host_bufs[0]
     host_opt = hostapi.Options(device_art_walk=1, n_threads=min(os.cpu_count() or 1, 64), **HOST_OPTIONS)
     comm_ms = []
 
@@ -505,6 +583,45 @@ def run_tsgpu(args, rank, world, local_rank):
             dt = float(t.item())
         return dt, sts
 
+    def timed_e2e():
+        """The end-to-end leg: K multi_search calls of query strings through the host layer, E2E_DEPTH of them in flight (a server's
+        request threads: while one call's device round runs, another call's host pass does; the library serialises device calls).
+        Every call's results land in host buffers; with several ranks each call is followed, in call order, by the NCCL gather."""
+        import concurrent.futures as cf
+
+        def run(i, slot):
+            j = i % n_b
+            sb, _, packed, qf = sl[j]
+            t1 = time.perf_counter()
+            kvb, cb, fb = host_bufs[slot]
+            _, _, _, hst = hi.multi_search("title", "points", None, stride, qf, qv_pin[j].numpy() if hybrid else None, host_opt, packed=packed,
+                                           out=(kvb[:nl], cb[:nl], fb[:nl]))
+            hst["wall_ms"] = 1000 * (time.perf_counter() - t1)
+            return hst
+        for i in range(args.warmup):
+            step(i, 2)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sts, futs, nxt = [], {}, 0
+        with cf.ThreadPoolExecutor(E2E_DEPTH) as pool:
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                while nxt < args.steps and nxt < i + E2E_DEPTH:
+                    futs[nxt] = pool.submit(run, args.warmup + nxt, nxt % E2E_DEPTH)
+                    nxt += 1
+                sts.append(futs.pop(i).result())
+                if world > 1:
+                    gi.comm_gather(host_bufs[i % E2E_DEPTH][0], max_nl * rec, all_pin, 0)
+                    comm_ms.append(gi.comm_last_ms())
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, sts
+
     def xfer():
         s_ = gi.stats()
         return s_["h2d_total"] + s_["h2d_bytes"], s_["d2h_total"] + s_["d2h_bytes"], s_["calls_total"]
@@ -517,7 +634,7 @@ def run_tsgpu(args, rank, world, local_rank):
     launches = gi.stats()["launches_total"] - launches0
     dt_pin, sts_pin = timed(1)
     x0 = xfer()
-    dt_e2e, sts_e2e = timed(2)
+    dt_e2e, sts_e2e = timed_e2e()
     x1 = xfer()
     clocks = sampler.stop() if rank == 0 else None
     e2e_steps = args.steps + args.warmup
@@ -592,7 +709,7 @@ def run_tsgpu(args, rank, world, local_rank):
         extra["device_ms_isolated"] = {"kw_search": ms_kw, "kw_merge": statistics.mean(s["ms_kw_merge"] for s in sts_iso),
                                        "knn": ms_knn, "total": statistics.mean(s["ms_total"] for s in sts_iso)}
         extra["work_per_step"] = {k: float(statistics.mean(s_[k] for s_ in sts_iso)) for k in
-                                  ("kw_driver_ids", "kw_probe_ids", "kw_matches", "knn_dist", "knn_expanded", "knn_spec_hits")}
+                                  ("kw_driver_ids", "kw_probe_ids", "kw_matches", "knn_dist", "knn_expanded", "knn_spec_hits", "knn_table_probes")}
         if knn_work is not None and len(knn_work):
             ex = np.sort(knn_work[:, 0])
             filt = (sl[(args.warmup + min(args.steps, 4) - 1) % n_b][0].q_filter != -1)[:len(knn_work)]
@@ -634,6 +751,8 @@ def run_tsgpu(args, rank, world, local_rank):
             extra["parity_resolved_vs_cpu"] = {"queries": S_n, "identical_topk": same2,
                                                "note": "differences = queries whose resolved single combination is not where the reference's flow ends (no match under the filter -> typo / drop-token rounds)"}
             hc.close()
+        if world == 1 and not args.no_other_configs:
+            extra["other_configs"] = other_configs(args, w, hi, gi, sl, qv_pin, host_opt, hbm_peak)
         if hybrid and w.recall_exact is not None:
             R = len(w.recall_q)
             d, l, n = gi.knn(w.recall_q, 100, 100)
@@ -650,7 +769,7 @@ def run_tsgpu(args, rank, world, local_rank):
                "dtype": "u32+f32", "data": "synthetic", "config": workload_config(args, nq),
                "e2e": {"value": e2e, "unit": "queries/s", "ms_per_step": 1000 * dt_e2e / args.steps,
                        "h2d_bytes_per_step": int((x1[0] - x0[0]) / e2e_steps), "d2h_bytes_per_step": int((x1[1] - x0[1]) / e2e_steps),
-                       "device_calls_per_step": (x1[2] - x0[2]) / e2e_steps,
+                       "device_calls_per_step": (x1[2] - x0[2]) / e2e_steps, "calls_in_flight": E2E_DEPTH,
                        "path": "query strings -> C++ host layer (libtshost.so: tokens, ART candidate walks on the device, typo / prefix / drop-token control flow) -> "
                                "C-ABI rounds with host buffers -> tsgpu_hybrid_fuse_batch; rank 0's slice per step" + (" + NCCL gather" if world > 1 else "")},
                "e2e_resolved": {"value": nq * args.steps / dt_pin, "unit": "queries/s", "ms_per_step": 1000 * dt_pin / args.steps,

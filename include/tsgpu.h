@@ -364,6 +364,7 @@ typedef struct {
     uint64_t h2d_total;          /* host->device / device->host bytes since index creation (every call; h2d_bytes / d2h_bytes: last call) */
     uint64_t d2h_total;
     uint64_t calls_total;        /* C-ABI search calls since index creation */
+    uint64_t knn_table_probes;   /* neighbour tests of the graph walks that missed the shared-memory visited cache (went to the HBM table) */
 } tsgpu_stats;
 tsgpu_status tsgpu_get_stats(tsgpu_index* idx, tsgpu_stats* out);
 /* Instrumentation: per graph walk of the last HNSW launch, out[2q] = expanded nodes, out[2q+1] = distance evaluations. */

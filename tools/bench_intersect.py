@@ -31,7 +31,7 @@ def best_of(fn, reps):
     return min(ts), r
 
 
-def main():
+def run(cpu_reps=20):
     rng = np.random.default_rng(42)
     n_range = 1_000_000
     lists = [np.unique(rng.integers(0, n_range, n)).astype(np.uint32) for n in (100_000, 50_000, 25_000)]
@@ -43,7 +43,7 @@ def main():
     ptrs = (S.u32p * 3)(*[ol.p32(a) for a in lists])
     lens = (C.c_size_t * 3)(*[len(a) for a in lists])
     res = np.zeros(len(lists[2]), np.uint32)
-    t, n = best_of(lambda: L.tso_intersect(3, ptrs, lens, ol.p32(res), len(res)), 20)
+    t, n = best_of(lambda: L.tso_intersect(3, ptrs, lens, ol.p32(res), len(res)), cpu_reps)
     expect = res[:n].copy()
     out["port_us"] = 1e6 * t
     out["result_len"] = int(n)
@@ -82,7 +82,11 @@ def main():
         out["tsgpu_device_ms"] = st["ms_total"]
         out["tsgpu_algorithmic_GBps"] = algo_bytes / t / 1e9
         gi.close()
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    print(json.dumps(run()))
 
 
 if __name__ == "__main__":

@@ -600,11 +600,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // the "already visited" tests (9 of 10 neighbours of an expanded node have been seen, almost always recently) with one
 // shared-memory load. Only cache misses — the fresh neighbours plus a few evicted ones — go to the table: one compare-
 // and-swap each, in parallel across the lanes. Exact by construction (the table decides), any size of walk.
-__device__ __forceinline__ bool vis_test_and_set(uint32_t* cache, uint32_t cmask, uint32_t* table, uint32_t mask2, uint32_t node) {
+__device__ __forceinline__ bool vis_test_and_set(uint32_t* cache, uint32_t cmask, uint32_t* table, uint32_t mask2, uint32_t node, bool* went_to_table = nullptr) {
     const uint32_t key = node + 1;
     const uint32_t h = vis_hash(node);
     uint32_t* c = cache + (h & cmask);
     if(*c == key) return false;
+    if(went_to_table) *went_to_table = true;
     bool fresh = false;
     uint32_t j = (h >> 11) & mask2;
     for(;;) {
@@ -622,7 +623,7 @@ __device__ __forceinline__ bool vis_test_and_set(uint32_t* cache, uint32_t cmask
 #endif
 // NCH = dim / 128 (dim a multiple of 128: rows are staged by bulk copies of dim * 4 bytes); other dimensions take the heap kernel.
 template <int NCH, int RS>
-__global__ void __launch_bounds__(32 * kWalkWarps, RS == 2 ? 2 * TSGPU_WALK_MIN_CTAS : TSGPU_WALK_MIN_CTAS)
+__global__ void __launch_bounds__(32 * kWalkWarps, RS == 2 ? 2 * TSGPU_WALK_MIN_CTAS : (RS == 8 ? 2 : TSGPU_WALK_MIN_CTAS))
 hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -645,7 +646,7 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
     unsigned long long* pool = P.cand + (size_t) slot * P.cand_cap;
     const uint32_t L0 = 2 * g.M + 1, LU = g.M + 1;
     const uint32_t n_tickets = P.n_order_dev ? __ldcg(P.n_order_dev) : (P.q_order ? P.n_order : P.nq);
-    unsigned long long n_dist_acc = 0, n_exp_acc = 0, n_hit_acc = 0, n_t2_acc = 0;
+    unsigned long long n_dist_acc = 0, n_exp_acc = 0, n_hit_acc = 0, n_t2_acc = 0, n_tab_acc = 0;
     float* const qs = nullptr;
 
     for(;;) {
@@ -772,9 +773,11 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
                 nb2 = (lane + 1 < L0) ? __ldg(rec2 + 1 + lane) : kNone;
             }
             if(n_vis + 32 > limit2) { overflow = true; break; }
-            const bool fresh = (lane < size) && vis_test_and_set(cache, cmask, vis2, mask2, nb);
+            bool to_table = false;
+            const bool fresh = (lane < size) && vis_test_and_set(cache, cmask, vis2, mask2, nb, &to_table);
             uint32_t mask = __ballot_sync(0xffffffffu, fresh);
             n_vis += __popc(mask);
+            n_tab_acc += __popc(__ballot_sync(0xffffffffu, to_table));
             // the filter functor of every fresh neighbour at once (one bitmap word per lane), ahead of the vector copies
             const bool ok_mine = fresh && allowed(g, fbm, excl, n_excl, nb);
             const uint32_t ok_mask = __ballot_sync(0xffffffffu, ok_mine);
@@ -879,7 +882,7 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
         }
         __syncwarp();
     }
-    if(lane == 0) { atomicAdd(P.stats + 0, n_dist_acc); atomicAdd(P.stats + 1, n_exp_acc); atomicAdd(P.stats + 2, n_hit_acc); atomicAdd(P.stats + 3, n_t2_acc); }
+    if(lane == 0) { atomicAdd(P.stats + 0, n_dist_acc); atomicAdd(P.stats + 1, n_exp_acc); atomicAdd(P.stats + 2, n_hit_acc); atomicAdd(P.stats + 3, n_t2_acc); atomicAdd(P.stats + 5, n_tab_acc); }
 }
 
 // process_results_bruteforce: one warp per (query, id)

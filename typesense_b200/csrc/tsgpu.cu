@@ -616,6 +616,11 @@ void launch_hnsw(tsgpu_index* idx, const tsv::KnnParams& P, unsigned grid, size_
 
 template <int NCH>
 void launch_walk(tsgpu_index* idx, const tsv::KnnParams& P, unsigned grid, size_t smem, int rs) {
+    if(NCH == 6 && rs == 8) {            // ... and with an eight-row ring (few, long walks: everything a node's expansion needs in one round trip)
+        cudaFuncSetAttribute(tsv::hnsw_walk_kernel<NCH == 6 ? 6 : 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024));
+        tsv::hnsw_walk_kernel<NCH == 6 ? 6 : 1, 8><<<grid, 32 * tsv::kWalkWarps, smem, idx->vs>>>(idx->hnsw, P);
+        return;
+    }
     if(NCH == 6 && rs == 2) {            // the 768-d build also exists with a two-row ring (more walks resident per SM)
         cudaFuncSetAttribute(tsv::hnsw_walk_kernel<NCH == 6 ? 6 : 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024));
         tsv::hnsw_walk_kernel<NCH == 6 ? 6 : 1, 2><<<grid, 32 * tsv::kWalkWarps, smem, idx->vs>>>(idx->hnsw, P);
@@ -651,7 +656,7 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     static const int env_rs = getenv("TSGPU_WALK_ROWS") ? atoi(getenv("TSGPU_WALK_ROWS")) : 0;
     static const int env_cache = getenv("TSGPU_WALK_CACHE") ? atoi(getenv("TSGPU_WALK_CACHE")) : 0;
     static const int env_ctas = getenv("TSGPU_WALK_CTAS") ? atoi(getenv("TSGPU_WALK_CTAS")) : 0;
-    const int rs = (env_rs == 2 && nch == 6) ? 2 : tsv::kStageRows;
+    const int rs = ((env_rs == 2 || env_rs == 8) && nch == 6) ? env_rs : tsv::kStageRows;
     const uint32_t vis_cache = env_cache >= 64 ? pow2_ceil((uint32_t) env_cache) : tsv::kVisCache;
     const size_t per_warp_smem = walk ? (size_t) rs * dim * 4 + (size_t) vis_cache * 4
                                       : ((size_t) efe + 1 + tsv::kCandSmem) * 8 + (size_t) tsv::kVisSmem * 4;
@@ -717,7 +722,7 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     out.labels = reinterpret_cast<uint32_t*>(ob + (size_t) nq * k * 4);
     out.n = reinterpret_cast<uint32_t*>(ob + (size_t) nq * k * 8);
     out.stride = k;
-    // misc layout: [0] ticket, [4] retry ticket, [8..40) stats u64 x4, [40] retry_n, [44] retry_n of the retry launch (unused)
+    // misc layout: [0] ticket, [4] retry ticket, [8..40) stats u64 x4, [40] retry_n, [44] retry_n of the retry launch (unused), [48] stats[5]: visited-table probes
     tsv::KnnParams P{};
     P.queries = d_queries; P.nq = nq; P.k = k; P.ef = ef;
     P.q_filter_bitmap = q_bitmap.empty() ? nullptr : reinterpret_cast<const uint32_t* const*>(base + o_bm);
@@ -774,8 +779,9 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
 
 tsgpu_status finish_knn(tsgpu_index* idx) {
     if(!idx->knn_misc_dev) return TSGPU_OK;
-    unsigned long long hst[5];
-    CU(cudaMemcpy(hst, idx->knn_misc_dev + 8, 40, cudaMemcpyDeviceToHost));
+    unsigned long long hst[6];
+    CU(cudaMemcpy(hst, idx->knn_misc_dev + 8, 48, cudaMemcpyDeviceToHost));
+    idx->stats.knn_table_probes += hst[5];
     idx->knn_misc_dev = nullptr;
     idx->stats.knn_dist += hst[0]; idx->stats.knn_expanded += hst[1]; idx->stats.knn_spec_hits += hst[2];
     idx->stats.knn_tier2_walks += hst[3];

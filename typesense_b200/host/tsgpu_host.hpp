@@ -1369,6 +1369,7 @@ public:
         search_request r;
         int32_t filter_handle = -1;
         const float* query_vector = nullptr;     // nullptr: keyword only
+        size_t hits = 0;                         // results the caller will read (0: the whole Topster); bounds what the hybrid tail copies back
         tsgpu_vec_params vp{0, 10, 0, 3.4028234663852886e38f, 0.3f, 10};
     };
     struct batched_stats { size_t passes = 0, kw_batches = 0, kw_queries = 0, walk_batches = 0, walks = 0, host_walk_fallbacks = 0, fuse_queries = 0;
@@ -1494,7 +1495,8 @@ public:
                 kw_searched[k] = (uint32_t) rs[i].executed.c_nreq.size();
                 std::copy(requests[i].query_vector, requests[i].query_vector + dim, vecs.begin() + k * dim);
             }
-            const uint32_t stride = st.stride;
+            uint32_t stride = 1;
+            for(size_t i: ids) stride = std::max<uint32_t>(stride, (uint32_t) std::min<size_t>(requests[i].hits ? requests[i].hits : requests[i].r.topster_size, st.stride));
             std::vector<KV> okv((size_t) m * stride);
             std::vector<uint32_t> ocount(m), ofound(m);
             const tsgpu_vec_params vp = requests[ids[0]].vp;

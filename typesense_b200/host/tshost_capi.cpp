@@ -76,6 +76,7 @@ int tshost_multi_search(void* h, const char* field, const char* sort_field, uint
         r.opts.num_typos = o->num_typos; r.opts.prefix = o->prefix != 0; r.opts.max_candidates = o->max_candidates;
         r.opts.typo_tokens_threshold = o->typo_tokens_threshold; r.opts.device_art_walk = o->device_art_walk != 0;
         reqs[i].filter_handle = q_filter ? q_filter[i] : -1;
+        reqs[i].hits = stride;
         if(qvecs) {
             reqs[i].query_vector = qvecs + (size_t) i * dim;
             reqs[i].vp = tsgpu_vec_params{o->vec_k, o->vec_ef, o->vec_flat_search_cutoff, o->vec_distance_threshold, o->vec_alpha, o->vec_fetch_size};

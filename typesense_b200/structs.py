@@ -76,7 +76,7 @@ class StatsStruct(C.Structure):
                 ("knn_expanded", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("ms_kw_search", C.c_float), ("ms_kw_merge", C.c_float), ("ms_host_plan", C.c_float), ("knn_spec_hits", C.c_uint64),
                 ("knn_tier2_walks", C.c_uint64), ("knn_retried", C.c_uint64), ("h2d_total", C.c_uint64), ("d2h_total", C.c_uint64),
-                ("calls_total", C.c_uint64)]
+                ("calls_total", C.c_uint64), ("knn_table_probes", C.c_uint64)]
 
 
 def _ptr(a: Optional[np.ndarray], typ):
