@@ -72,7 +72,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", default="hnsw", choices=["hnsw", "bulk"], help="hnsw: built by tsgpu_index_build_hnsw; bulk: r01's harness stand-in")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the secondary BASELINE.json configurations (other_configs)")
-    ap.add_argument("--e2e-depth", type=int, default=2, help="multi_search calls in flight in the end-to-end leg (1 = strictly one after the other)")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="multi_search calls in flight in the end-to-end leg (1 = strictly one after the other)")
     ap.add_argument("--no-graph-cache", action="store_true", help="always rebuild the HNSW graph (default: reuse /tmp/tsgpu_bench_cache)")
     ap.add_argument("--exp-sorted-vectors", action="store_true",
                     help="experiment only: store vectors in cluster order (seq_id locality) to measure what row locality is worth")
@@ -784,7 +784,7 @@ def run_tsgpu(args, rank, world, local_rank):
                              "small": {"queries": min(64, nl), "p50": pct(ls, 0.5), "p99": pct(ls, 0.99), "calls": len(ls)}}
         if world > 1 and comm_ms:
             out["collective"] = {"what": "tsgpu_comm_gather (in-library NCCL send/recv group, device to device) of the slices' KV records to rank 0",
-                                 "bytes_per_rank": max_nl * rec, "ms_mean_rank0": float(statistics.mean(comm_ms))}
+                                 "bytes_per_rank": max_nl * rec, "ms_median_rank0": float(statistics.median(comm_ms)), "ms_max_rank0": float(max(comm_ms)), "calls": len(comm_ms)}
         out.update(extra)
         emit(out)
     if world > 1:

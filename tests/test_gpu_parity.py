@@ -228,6 +228,37 @@ def test_knn_matches_oracle(vec_coll):
     assert cnt.tolist() == ocnt.tolist() and l.tolist() == olab.tolist() and (d == od).all()
 
 
+def test_hnsw_load_rejects_malformed_graph_and_keeps_the_old_one(vec_coll):
+    """tsgpu_index_load_hnsw validates what the walk kernels follow blindly (ids, counts, offsets) and swaps only on success."""
+    import copy
+    n, dim, vec, g, fd, pts, gi, oi = vec_coll
+    qv = synth.make_vectors(16, dim, 5).numpy()
+    before = gi.knn(qv, 10, 20)
+    L0 = 2 * g.M + 1
+
+    def broken(mut):
+        b = copy.copy(g)
+        for f in ("links0", "upper_off", "links_up", "levels"):
+            setattr(b, f, getattr(g, f).copy())
+        mut(b)
+        return b
+
+    def bad_id(b): b.links0[5 * L0 + 1] = n + 7
+    def bad_count(b): b.links0[9 * L0] = 2 * g.M + 1
+    def bad_levels(b): b.levels[int(np.argmax(g.levels == 0))] = 1
+    def bad_entry(b): b.entry_point = n
+    def bad_entry_level(b): b.entry_point = int(np.argmax(g.levels == 0))
+    def bad_upper(b):
+        assert len(b.links_up)
+        b.links_up[1] = n
+
+    for mut in (bad_id, bad_count, bad_levels, bad_entry, bad_entry_level, bad_upper):
+        with pytest.raises(capi.TsgpuError):
+            gi.load_hnsw(broken(mut))
+        after = gi.knn(qv, 10, 20)
+        assert all((a == b).all() for a, b in zip(before, after)), mut.__name__
+
+
 def test_knn_generic_dim_and_reference_kat():
     from test_oracle_ref import KAT
     k = KAT["vector_cosine"]

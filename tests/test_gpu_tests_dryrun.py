@@ -18,6 +18,7 @@ GPU_ONLY = [
     "tests/test_gpu_parity.py::test_edge_cases",                                  # asserts the library's capacity errors
     "tests/test_facets.py::test_gpu_all_result_ids_and_facets_of_a_search_batch",  # all_result_ids live in device memory
     "tests/test_gpu_parity.py::test_knn_selective_filters_long_walks",            # builds its graph on the device, asserts device counters
+    "tests/test_gpu_parity.py::test_hnsw_load_rejects_malformed_graph_and_keeps_the_old_one",   # asserts the library's load-time validation
 ]
 
 

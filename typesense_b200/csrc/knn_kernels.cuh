@@ -67,6 +67,7 @@ struct KnnParams {
     uint32_t* retry_n;             // walks that outgrew the per-slot scratch: re-run by the host with a full-size slot
     uint32_t* retry_list;          // [nq]
     uint32_t vis_cache;            // register-queue kernel: entries of the shared-memory visited cache per walk (power of two)
+    uint32_t walk_prefetch;        // register-queue kernel: L2 hints for the likely next expansion (bit 0 table line, 1 rows, 2 filter word)
     uint32_t* q_work;              // [2*nq] expansions, distance evaluations of each walk (instrumentation; may be nullptr)
 };
 
@@ -501,12 +502,15 @@ hnsw_search_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ Kn
 //   result set R   the ef (<= 128) closest allowed nodes as ONE sorted array, element e in lane e / 4, register e % 4
 //                  (keys ord(dist) << 32 | id, ascending): admission is a warp-wide compare + shift (~25 instructions, no
 //                  memory), lowerBound is a shuffle
-//   candidates C   the 64 smallest candidate keys sorted the same way (2 per lane) + an UNSORTED pool in HBM for the rest.
-//                  Invariant: every pool key >= every buffered key, so the buffer's front is the global minimum. A key below
-//                  the buffer's last goes into the buffer (the evicted last goes to the pool, one store); others are
-//                  appended to the pool. Only when the buffer runs empty is the pool read: its 64 smallest are selected by
-//                  one streaming pass (swap-insert) — every ~64 expansions at most, so no global load sits on an
-//                  expansion's critical path.
+//   candidates C   the 128 smallest candidate keys sorted the same way (the "buffer") + two UNSORTED pools in HBM for the
+//                  rest: "near" (keys below a pivot pv) and "far" (keys >= pv). Invariant: buffer <= near < pv <= far, so
+//                  the buffer's front is the global minimum. A key below the buffer's last goes into the buffer (the
+//                  evicted last goes to the near pool, one store); others are appended to the pool their side of pv says.
+//                  Only when the buffer runs empty are the pools read: the near pool — split first around a sampled pivot
+//                  when it holds more than kNearMax keys; replaced by the far pool when empty — gives up its 128 smallest
+//                  through a sorting network (sort each 128-key chunk, merge against the buffer, write the upper half
+//                  back): ~30 instructions per popped key. (The first version scanned ONE pool with a serial insert per
+//                  qualifying key: 26 % of the kernel's instructions on filtered walks, profiles/r02g.)
 // Pop order, admission order and every comparison are those of hnswlib's two std::priority_queues, so results are unchanged
 // (same GPU parity tests). Used when max(ef, k) <= 128 and 2M <= 32 (Typesense defaults: ef 10..100s, M 16); the heap kernel
 // above stays as the general path.
@@ -569,9 +573,68 @@ __device__ __forceinline__ void warr_set_inf(WArr<S>& w, uint32_t e, uint32_t la
 }
 static_assert(true, "WArr accessors are written out for S <= 4");
 
+// ---- 128 keys (4 per lane) as a sorting network: bitonic stages over the element index e = lane * 4 + register.
+// Strides below 4 stay inside a lane; larger ones are one xor-shuffle per register. Used by the candidate buffer's refill,
+// which takes the 128 smallest of a few hundred pooled keys by sort + merge instead of one serial insert per key.
+__device__ __forceinline__ void key_cx(unsigned long long& a, unsigned long long& b, bool asc) {      // afterwards a <= b iff asc
+    const bool sw = (a > b) == asc;
+    const unsigned long long t = a;
+    a = sw ? b : a; b = sw ? t : b;
+}
+template <uint32_t K, uint32_t J>
+__device__ __forceinline__ void warr_stage(WArr<4>& w, uint32_t lane) {
+    if constexpr (J >= 4) {
+        constexpr uint32_t LJ = J >> 2;
+        const bool lower = (lane & LJ) == 0;
+        const bool asc = ((lane << 2) & K) == 0;             // K >= 8 here: the direction is a lane bit
+        const bool take_min = lower == asc;
+#pragma unroll
+        for(int r = 0; r < 4; r++) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, w.a[r], LJ);
+            const bool less = w.a[r] < o;
+            w.a[r] = (less == take_min) ? w.a[r] : o;
+        }
+    } else if constexpr (J == 2) {
+        const bool asc = ((lane << 2) & K) == 0;             // K >= 4
+        key_cx(w.a[0], w.a[2], asc); key_cx(w.a[1], w.a[3], asc);
+    } else {
+        if constexpr (K == 2) { key_cx(w.a[0], w.a[1], true); key_cx(w.a[2], w.a[3], false); }
+        else { const bool asc = ((lane << 2) & K) == 0; key_cx(w.a[0], w.a[1], asc); key_cx(w.a[2], w.a[3], asc); }
+    }
+}
+template <uint32_t K, uint32_t J>
+__device__ __forceinline__ void warr_merge_from(WArr<4>& w, uint32_t lane) {       // stages (K, J), (K, J/2), ... (K, 1)
+    warr_stage<K, J>(w, lane);
+    if constexpr (J > 1) warr_merge_from<K, J / 2>(w, lane);
+}
+template <uint32_t K>
+__device__ __forceinline__ void warr_sort_from(WArr<4>& w, uint32_t lane) {        // blocks of K, then 2K, ... 128
+    warr_merge_from<K, K / 2>(w, lane);
+    if constexpr (K < 128) warr_sort_from<K * 2>(w, lane);
+}
+// any order -> ascending (element e in lane e / 4, register e % 4: the layout of warr_insert / warr_front)
+__device__ __forceinline__ void warr_sort128(WArr<4>& w, uint32_t lane) { warr_sort_from<2>(w, lane); }
+// a bitonic sequence -> ascending
+__device__ __forceinline__ void warr_bmerge128(WArr<4>& w, uint32_t lane) { warr_merge_from<128, 64>(w, lane); }
+// b, c ascending -> b = the 128 smallest of both, ascending; c = the 128 others as a bitonic sequence
+__device__ __forceinline__ void warr_keep_low(WArr<4>& b, WArr<4>& c, uint32_t lane) {
+    unsigned long long o[4];
+#pragma unroll
+    for(int r = 0; r < 4; r++) o[r] = __shfl_sync(0xffffffffu, c.a[3 - r], 31 - lane);      // c reversed
+#pragma unroll
+    for(int r = 0; r < 4; r++) {
+        const bool less = b.a[r] < o[r];
+        c.a[r] = less ? o[r] : b.a[r];
+        b.a[r] = less ? b.a[r] : o[r];
+    }
+    warr_bmerge128(b, lane);
+}
+
 constexpr int kResPerLane = 4;           // R: 128 entries
 constexpr int kBufPerLane = 4;           // C buffer: 128 entries
 constexpr uint32_t kBufCap = 32 * kBufPerLane;
+constexpr uint32_t kNearMax = 1024;       // a near pool above this is split before the buffer refills from it ...
+constexpr uint32_t kNearTarget = 512;     // ... with a pivot aimed at leaving this many keys
 constexpr int kWalkWarps = 2;            // walks (warps) per CTA
 constexpr int kStageRows = 4;            // default: neighbour rows in flight per walk (shared-memory ring filled by cp.async.bulk)
 constexpr uint32_t kVisCache = 2048;     // default: direct-mapped cache of recently visited nodes per walk (shared memory)
@@ -643,7 +706,9 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
     uint32_t* vis2 = P.vis2 + (size_t) slot * P.vis2_slots;
     const uint32_t mask2 = P.vis2_slots - 1;
     const uint32_t limit2 = P.vis2_slots - (P.vis2_slots >> 2);
-    unsigned long long* pool = P.cand + (size_t) slot * P.cand_cap;
+    // candidate pools of this slot: two halves, "near" (keys below the pivot) and "far" (the rest); they trade places
+    unsigned long long* const pool0 = P.cand + (size_t) slot * P.cand_cap;
+    const uint32_t pool_half = P.cand_cap >> 1;
     const uint32_t L0 = 2 * g.M + 1, LU = g.M + 1;
     const uint32_t n_tickets = P.n_order_dev ? __ldcg(P.n_order_dev) : (P.q_order ? P.n_order : P.nq);
     unsigned long long n_dist_acc = 0, n_exp_acc = 0, n_hit_acc = 0, n_t2_acc = 0, n_tab_acc = 0;
@@ -694,7 +759,12 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
         // ---- best-first search of the base layer (searchBaseLayerST, non-"bare bone" branch)
         WArr<kResPerLane> R; warr_clear(R);
         WArr<kBufPerLane> B; warr_clear(B);
-        uint32_t n_res = 0, n_b = 0, n_p = 0;                   // result count, buffered / pooled candidates (warp-uniform)
+        uint32_t n_res = 0, n_b = 0;                            // result count, buffered candidates (warp-uniform, like all below)
+        unsigned long long* nearp = pool0;                       // pooled candidates: keys < pv ...
+        unsigned long long* farp = pool0 + pool_half;            // ... and keys >= pv, both unsorted
+        uint32_t n_near = 0, n_far = 0;
+        unsigned long long pv = kKeyInf;
+        unsigned long long b_last = 0;                           // the buffer's largest key (0 when empty)
         uint32_t n_vis = 0;                                      // keys in the visited table
         bool overflow = false;
         float lowerBound;
@@ -706,10 +776,10 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
                 n_dist_acc++;
                 lowerBound = d;
                 warr_insert(R, res_key(d, cur), lane); n_res = 1;
-                warr_insert(B, cand_key(d, cur), lane); n_b = 1;
+                warr_insert(B, cand_key(d, cur), lane); n_b = 1; b_last = cand_key(d, cur);
             } else {
                 lowerBound = FLT_MAX;
-                warr_insert(B, cand_key(FLT_MAX, cur), lane); n_b = 1;
+                warr_insert(B, cand_key(FLT_MAX, cur), lane); n_b = 1; b_last = cand_key(FLT_MAX, cur);
             }
             if(lane == 0) vis_test_and_set(cache, cmask, vis2, mask2, cur);
             n_vis = 1;
@@ -719,35 +789,79 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
         for(;;) {
             if(overflow) break;
             if(n_b == 0) {
-                if(n_p == 0) break;
-                // ---- refill: the kBufCap smallest pool keys move to the buffer. The pool's tail seeds the buffer, then one
-                // streaming pass swaps every key below the buffer's last with that last (so the pool keeps its size minus the
-                // seed and never holds gaps).
-                const uint32_t seed = n_p < kBufCap ? n_p : kBufCap;
-                n_p -= seed;
-                for(uint32_t i = 0; i < seed; i += 32) {
-                    const unsigned long long k = (i + lane < seed) ? pool[n_p + i + lane] : kKeyInf;
-                    uint32_t m = __ballot_sync(0xffffffffu, k != kKeyInf);
-                    while(m) { const int src = __ffs(m) - 1; m &= m - 1; warr_insert(B, __shfl_sync(0xffffffffu, k, src), lane); }
+                if(n_near == 0) {
+                    if(n_far == 0) break;
+                    unsigned long long* t = nearp; nearp = farp; farp = t;           // the far pool becomes the near one
+                    n_near = n_far; n_far = 0; pv = kKeyInf;
                 }
-                n_b = seed;
-                if(seed == kBufCap) {
-                    for(uint32_t i = 0; i < n_p; i += 32) {
-                        unsigned long long k = (i + lane < n_p) ? pool[i + lane] : kKeyInf;
-                        unsigned long long bl = __shfl_sync(0xffffffffu, B.a[kBufPerLane - 1], 31);
-                        uint32_t m = __ballot_sync(0xffffffffu, k < bl);
-                        bool mine = false;
-                        while(m) {
-                            const int src = __ffs(m) - 1; m &= m - 1;
-                            const unsigned long long ks = __shfl_sync(0xffffffffu, k, src);
-                            bl = __shfl_sync(0xffffffffu, B.a[kBufPerLane - 1], 31);
-                            if(ks < bl) {                                   // still below the (shrinking) last
-                                const unsigned long long ev = warr_insert(B, ks, lane);
-                                if((int) lane == src) { k = ev; mine = true; }
-                            }
+                __syncwarp();
+                if(n_near > kNearMax) {
+                    // ---- split: a pivot from a 32-key sample (the rank-q sample, q chosen for ~kNearTarget keys below it);
+                    // keys below stay (compacted in place), the others move to the far pool. Any pivot is correct — the
+                    // invariant is only near < pv <= far — a lucky or unlucky one just changes how soon the next split comes.
+                    const uint32_t n = n_near;
+                    const unsigned long long sk = nearp[(unsigned long long) lane * n >> 5];
+                    uint32_t rank = 0;
+#pragma unroll 8
+                    for(int o = 0; o < 32; o++) rank += __shfl_sync(0xffffffffu, sk, o) < sk ? 1u : 0u;
+                    uint32_t q = (32u * kNearTarget + (n >> 1)) / n;
+                    q = q < 1 ? 1 : (q > 16 ? 16 : q);
+                    const unsigned long long pivot = __shfl_sync(0xffffffffu, sk, __ffs(__ballot_sync(0xffffffffu, rank == q)) - 1);
+                    uint32_t w = 0;
+                    const uint32_t lt = (1u << lane) - 1u;
+                    for(uint32_t base = 0; base < n; base += 32) {
+                        const bool valid = base + lane < n;
+                        const unsigned long long k = valid ? nearp[base + lane] : kKeyInf;
+                        const uint32_t mb = __ballot_sync(0xffffffffu, valid && k < pivot);
+                        const uint32_t ma = __ballot_sync(0xffffffffu, valid && k >= pivot);
+                        if(n_far + __popc(ma) > pool_half) { overflow = true; break; }
+                        if(valid) {
+                            if(k < pivot) nearp[w + __popc(mb & lt)] = k;
+                            else farp[n_far + __popc(ma & lt)] = k;
                         }
-                        if(mine) pool[i + lane] = k;
+                        w += __popc(mb); n_far += __popc(ma);
                     }
+                    if(overflow) break;
+                    n_near = w; pv = pivot;
+                    __syncwarp();
+                }
+                // ---- refill: the buffer takes the 128 smallest near keys. The pool's tail is sorted into the buffer, then
+                // every 128-key chunk of the rest is sorted and merged against it: the lower half stays in registers, the
+                // upper half goes back where the chunk came from (so the pool never holds gaps). ~1 K instructions per chunk,
+                // where one serial insert per qualifying key cost 30-40 K per refill on a filtered walk's pool.
+                {
+                    uint32_t n = n_near;
+                    const uint32_t seed = n < kBufCap ? n : kBufCap;
+                    n -= seed;
+#pragma unroll
+                    for(int r = 0; r < 4; r++) { const uint32_t e = r * 32 + lane; B.a[r] = e < seed ? nearp[n + e] : kKeyInf; }
+                    WArr<4> C; warr_clear(C);
+                    if(n) {
+#pragma unroll
+                        for(int r = 0; r < 4; r++) { const uint32_t e = r * 32 + lane; C.a[r] = e < n ? nearp[e] : kKeyInf; }
+                    }
+                    warr_sort128(B, lane);
+                    n_b = seed;
+                    for(uint32_t base = 0; base < n; base += 128) {
+                        const uint32_t m = n - base < 128 ? n - base : 128;
+                        WArr<4> N;                                        // the next chunk's loads ride under this chunk's sort
+                        const uint32_t nb_ = base + 128;
+#pragma unroll
+                        for(int r = 0; r < 4; r++) { const uint32_t e = nb_ + r * 32 + lane; N.a[r] = e < n ? nearp[e] : kKeyInf; }
+                        warr_sort128(C, lane);
+                        warr_keep_low(B, C, lane);
+                        if(m == 128) {
+#pragma unroll
+                            for(int r = 0; r < 4; r++) nearp[base + r * 32 + lane] = C.a[r];
+                        } else {                                          // a partial chunk: its m real keys first
+                            warr_bmerge128(C, lane);
+#pragma unroll
+                            for(int r = 0; r < 4; r++) { const uint32_t e = lane * 4 + r; if(e < m) nearp[base + e] = C.a[r]; }
+                        }
+                        C = N;
+                    }
+                    n_near = n;
+                    b_last = warr_get(B, n_b - 1);
                 }
                 __syncwarp();
             }
@@ -756,6 +870,7 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
             if(cdist > lowerBound && n_res == ef) break;
             const uint32_t cnode = ~(uint32_t) top;
             warr_pop_front(B, lane); n_b--;
+            if(n_b == 0) b_last = 0;
             n_exp_acc++;
 
             const uint32_t* rec = g.links0 + (size_t) cnode * L0;
@@ -773,15 +888,33 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
                 nb2 = (lane + 1 < L0) ? __ldg(rec2 + 1 + lane) : kNone;
             }
             if(n_vis + 32 > limit2) { overflow = true; break; }
+            // the filter functor of every neighbour at once (one bitmap word per lane): its load is issued ahead of the visited
+            // test, whose table probe is the longer wait, and is only looked at for the fresh ones
+            const bool ok_any = (lane < size) && allowed(g, fbm, excl, n_excl, nb);
             bool to_table = false;
             const bool fresh = (lane < size) && vis_test_and_set(cache, cmask, vis2, mask2, nb, &to_table);
             uint32_t mask = __ballot_sync(0xffffffffu, fresh);
             n_vis += __popc(mask);
             n_tab_acc += __popc(__ballot_sync(0xffffffffu, to_table));
-            // the filter functor of every fresh neighbour at once (one bitmap word per lane), ahead of the vector copies
-            const bool ok_mine = fresh && allowed(g, fbm, excl, n_excl, nb);
-            const uint32_t ok_mask = __ballot_sync(0xffffffffu, ok_mine);
+            const uint32_t ok_mask = __ballot_sync(0xffffffffu, fresh && ok_any);
             n_dist_acc += __popc(mask);
+            // Hints for the likely next expansion (no effect on results): the neighbours of the buffer's front that the visited
+            // cache does not recognise will most probably be probed in the table and have their rows fetched one iteration
+            // from now — start the table line, the row (one bulk L2 prefetch per row) and the filter word towards L2 while this
+            // expansion's rows are in flight. P.walk_prefetch: bit 0 table line, bit 1 row, bit 2 filter word.
+            bool hinted = P.walk_prefetch == 0;
+            auto hint_next = [&]() {
+                hinted = true;
+                if(spec != kNone && lane < size2) {
+                    const uint32_t h2 = vis_hash(nb2);
+                    if(cache[h2 & cmask] != nb2 + 1) {
+                        if(P.walk_prefetch & 1u) asm volatile("prefetch.global.L2 [%0];" :: "l"(vis2 + ((h2 >> 11) & mask2)));
+                        if(P.walk_prefetch & 2u) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(g.vectors + (size_t) nb2 * dim), "r"(row_bytes) : "memory");
+                        if((P.walk_prefetch & 4u) && fbm && !g.labels) asm volatile("prefetch.global.L2 [%0];" :: "l"(fbm + (nb2 >> 5)));
+                    }
+                }
+            };
+            if(!mask && !hinted) hint_next();
             while(mask) {
                 // ---- up to RS fresh neighbours at a time: their rows are copied into the ring by the bulk-copy engine,
                 // all in flight together, completion counted in bytes on the warp's mbarrier
@@ -795,6 +928,7 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
                     const uint32_t rs = __popc(grp & ((1u << lane) - 1u));
                     bulk_g2s(ring_s + rs * row_bytes, g.vectors + (size_t) nb * dim, row_bytes, bar);
                 }
+                if(!hinted) hint_next();
                 {
                     uint32_t spins = 0;
                     while(!mbar_try_wait(bar, parity)) { if(++spins > (1u << 28)) { __trap(); } }
@@ -835,17 +969,22 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
                             }
                             const unsigned long long ck = cand_key(d, c);
                             // buffer unless a pooled key might be smaller: below the buffer's last, or nothing pooled and room left
-                            const unsigned long long bl = n_b ? warr_get(B, n_b - 1) : 0ull;
-                            if((n_p == 0 && n_b < kBufCap) || ck < bl) {
-                                const unsigned long long ev = warr_insert(B, ck, lane);
-                                if(n_b < kBufCap) n_b++;
-                                else { if(n_p < P.cand_cap) { if(lane == 0) pool[n_p] = ev; n_p++; } else overflow = true; }
-                            } else { if(n_p < P.cand_cap) { if(lane == 0) pool[n_p] = ck; n_p++; } else overflow = true; }
+                            if(ck >= pv) { if(n_far < pool_half) { if(lane == 0) farp[n_far] = ck; n_far++; } else overflow = true; }
+                            else {
+                                if((n_near == 0 && n_b < kBufCap) || ck < b_last) {
+                                    const unsigned long long ev = warr_insert(B, ck, lane);
+                                    if(n_b < kBufCap) { n_b++; b_last = ck > b_last ? ck : b_last; }
+                                    else {
+                                        b_last = __shfl_sync(0xffffffffu, B.a[kBufPerLane - 1], 31);
+                                        if(n_near < pool_half) { if(lane == 0) nearp[n_near] = ev; n_near++; } else overflow = true;
+                                    }
+                                } else { if(n_near < pool_half) { if(lane == 0) nearp[n_near] = ck; n_near++; } else overflow = true; }
+                            }
                             if(ok) {       // push, then pop while over ef (hnswlib) == the insert drops the last when already full
                                 warr_insert(R, res_key(d, c), lane);
                                 if(n_res < ef) n_res++; else warr_set_inf(R, ef, lane);
+                                lowerBound = unord_f32((uint32_t) (warr_get(R, n_res - 1) >> 32));
                             }
-                            if(n_res) lowerBound = unord_f32((uint32_t) (warr_get(R, n_res - 1) >> 32));
                         }
                     }
                 }
@@ -926,6 +1065,33 @@ flat_distance_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ 
         float d = 0.f;
         if(id < g.n_nodes) d = 1.0f - dot_one<NCH>(q, qs, g.vectors + (size_t) id * dim, dim, lane);
         if(lane == 0) P.out_dist[i] = d;
+    }
+}
+
+
+// Load-time check of an exported graph (the search kernels follow links and offsets without bounds tests): first violation
+// class wins. 1/2: level-0 count / id, 3: levels vs upper_off, 4/5: upper count / id, 6: level > max_level, 7: entry point level.
+__global__ void __launch_bounds__(256)
+hnsw_validate_kernel(const HnswDev g, unsigned long long n_up, uint32_t* __restrict__ bad) {
+    const uint32_t L0 = 2 * g.M + 1, LU = g.M + 1;
+    for(size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < g.n_nodes; i += (size_t) gridDim.x * blockDim.x) {
+        uint32_t err = 0;
+        const uint32_t* l0 = g.links0 + i * L0;
+        const uint32_t c0 = l0[0];
+        if(c0 > 2 * g.M) err = 1;
+        else for(uint32_t j = 0; j < c0; j++) if(l0[1 + j] >= g.n_nodes) { err = 2; break; }
+        const unsigned long long u0 = g.upper_off[i], u1 = g.upper_off[i + 1];
+        const uint32_t lv = g.levels[i];
+        if(!err && (u1 < u0 || u1 - u0 != lv || u1 > n_up)) err = 3;
+        if(!err && lv > g.max_level) err = 6;
+        if(!err && i == g.entry_point && lv != g.max_level) err = 7;
+        if(!err) for(unsigned long long r = u0; r < u1 && !err; r++) {
+            const uint32_t* lu = g.links_up + r * LU;
+            const uint32_t c = lu[0];
+            if(c > g.M) { err = 4; break; }
+            for(uint32_t j = 0; j < c; j++) if(lu[1 + j] >= g.n_nodes) { err = 5; break; }
+        }
+        if(err) atomicCAS(bad, 0u, err);
     }
 }
 

@@ -671,7 +671,7 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     // per-warp scratch in HBM: tier 2 of the visited set (64 Ki keys: walks of up to 48 K visited nodes) and the overflow of
     // the candidate heap (with a selective filter hnswlib pushes every visited node until `ef` allowed results exist).
     // A walk that outgrows either is handed to the retry launch below, whose slots are sized for the whole graph.
-    const uint32_t vis2_slots = 1u << 16, cand_cap = std::min<uint32_t>(1u << 16, std::max<uint32_t>(1024, g.n_nodes + 1));
+    const uint32_t vis2_slots = 1u << 16, cand_cap = std::min<uint32_t>(1u << 16, std::max<uint32_t>(1024, 2 * (g.n_nodes + 1)));    // two pools (near / far) of half each
     if(slots > idx->knn_slots) {
         idx->d_knn_vis.release();
         CU(idx->d_knn_vis.reserve(slots * (size_t) vis2_slots * 4));
@@ -680,7 +680,7 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     }
     CU(idx->d_knn_cand.reserve(slots * (size_t) cand_cap * 8));
     // retry slots (one CTA): visited tier 2 with >= 2 n slots, candidate arena n + 1
-    const uint32_t big_vis = pow2_ceil(std::max<uint32_t>(1u << 17, 2 * g.n_nodes + 64)), big_cand = g.n_nodes + 1;
+    const uint32_t big_vis = pow2_ceil(std::max<uint32_t>(1u << 17, 2 * g.n_nodes + 64)), big_cand = 2 * (g.n_nodes + 1);        // every node is pushed at most once, and either pool may hold them all
     {
         const size_t need = (size_t) 16 * big_vis * 4;
         if(need > idx->d_knn_retry_vis.cap) {
@@ -740,6 +740,8 @@ tsgpu_status run_knn(tsgpu_index* idx, const float* d_queries, uint32_t nq, uint
     P.retry_list = reinterpret_cast<uint32_t*>(base + o_rl);
     P.q_work = reinterpret_cast<uint32_t*>(base + o_wk);
     P.vis_cache = vis_cache;
+    static const int env_pf = getenv("TSGPU_WALK_PREFETCH") ? atoi(getenv("TSGPU_WALK_PREFETCH")) : 5;
+    P.walk_prefetch = (uint32_t) env_pf & 7u;
     idx->knn_work_dev = P.q_work; idx->knn_work_n = nq;
     // the retry launch: the same kernel over the queries the first one handed back, one CTA whose four slots can hold a
     // walk over the whole graph. It reads its ticket count from device memory, so it is issued unconditionally (no host
@@ -1085,21 +1087,27 @@ tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g) {
     if(!g) return fail(TSGPU_ERR_INVALID, "null graph");
     if(g->M == 0 || g->M > 32) return fail(TSGPU_ERR_CAPACITY, "M must be 1..32");
     std::lock_guard<std::mutex> lk(idx->mu);
-    for(void* p: idx->hnsw_alloc) cudaFree(p);
-    idx->hnsw_alloc.clear();
+    // Upload into allocations of their own, check what the kernels will follow blindly, and only then replace the graph the
+    // index holds: a failed load (out of memory, a malformed export) leaves the previous graph in place.
     const size_t n = g->n_nodes;
+    std::vector<void*> fresh;
+    struct Guard { std::vector<void*>& v; bool keep = false; ~Guard() { if(!keep) for(void* p: v) cudaFree(p); } } guard{fresh};
     auto up = [&](const void* src, size_t bytes, const void** dst) -> cudaError_t {
         void* d = nullptr;
         cudaError_t e = cudaMalloc(&d, bytes ? bytes : 16);
         if(e != cudaSuccess) return e;
-        idx->hnsw_alloc.push_back(d);
+        fresh.push_back(d);
         *dst = d;
         return bytes ? cudaMemcpy(d, src, bytes, cudaMemcpyDefault) : cudaSuccess;
     };
     tsv::HnswDev h{};
     h.n_nodes = g->n_nodes; h.dim = g->dim; h.M = g->M; h.max_level = g->max_level; h.entry_point = g->entry_point; h.metric = g->metric;
+    if(n && g->entry_point >= n) return fail(TSGPU_ERR_INVALID, "hnsw: entry point outside the graph");
+    if(n && (!g->vectors || !g->levels || !g->links0 || !g->upper_off)) return fail(TSGPU_ERR_INVALID, "hnsw: null array");
     uint64_t n_up = 0;
     if(n) CU(cudaMemcpy(&n_up, g->upper_off + n, 8, cudaMemcpyDefault));
+    if(n_up > (uint64_t) n * 64) return fail(TSGPU_ERR_INVALID, "hnsw: upper_off[n] is not a record count");
+    if(n_up && !g->links_up) return fail(TSGPU_ERR_INVALID, "hnsw: null array");
     const void* p = nullptr;
     CU(up(g->vectors, n * g->dim * 4, &p)); h.vectors = (const float*) p;
     if(g->labels) { CU(up(g->labels, n * 4, &p)); h.labels = (const uint32_t*) p; } else h.labels = nullptr;
@@ -1107,6 +1115,24 @@ tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g) {
     CU(up(g->links0, n * (2 * (size_t) g->M + 1) * 4, &p)); h.links0 = (const uint32_t*) p;
     CU(up(g->upper_off, (n + 1) * 8, &p)); h.upper_off = (const unsigned long long*) p;
     CU(up(g->links_up, n_up * ((size_t) g->M + 1) * 4, &p)); h.links_up = (const uint32_t*) p;
+    if(n) {
+        uint32_t* d_bad = nullptr;
+        CU(cudaMalloc(&d_bad, 4));
+        fresh.push_back(d_bad);
+        CU(cudaMemsetAsync(d_bad, 0, 4, idx->stream));
+        tsv::hnsw_validate_kernel<<<(unsigned) std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, idx->stream>>>(h, n_up, d_bad);
+        CU(cudaGetLastError());
+        uint32_t bad = 0;
+        CU(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, idx->stream));
+        CU(cudaStreamSynchronize(idx->stream));
+        if(bad) {
+            static const char* const what[] = {"", "hnsw: a level-0 link count exceeds 2M", "hnsw: a level-0 link points outside the graph", "hnsw: levels[] and upper_off[] disagree",
+                                               "hnsw: an upper-level link count exceeds M", "hnsw: an upper-level link points outside the graph", "hnsw: a node's level exceeds max_level",
+                                               "hnsw: the entry point is not on the top level"};
+            return fail(TSGPU_ERR_INVALID, what[bad < 8 ? bad : 1]);
+        }
+        cudaFree(d_bad); fresh.pop_back();
+    }
     if(h.labels) {   // identity labels are the common case: detect and drop the indirection
         std::vector<uint32_t> hl(n);
         CU(cudaMemcpy(hl.data(), h.labels, n * 4, cudaMemcpyDeviceToHost));
@@ -1114,6 +1140,9 @@ tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g) {
         for(size_t i = 0; i < n && ident; i++) ident = hl[i] == i;
         if(ident) h.labels = nullptr;
     }
+    guard.keep = true;
+    for(void* q: idx->hnsw_alloc) cudaFree(q);
+    idx->hnsw_alloc = std::move(fresh);
     idx->hnsw = h;
     idx->has_hnsw = true;
     return TSGPU_OK;

@@ -298,6 +298,10 @@ public:
     struct art_walk_stats_t { std::atomic<uint64_t> launches{0}, searches{0}, served{0}, host_fallbacks{0}; };
     static art_walk_stats_t& art_walk_stats() { static art_walk_stats_t s; return s; }     // process-wide, for tests and tuning
     void clear_walk_cache() { std::lock_guard<std::mutex> lk(cache_mu); walk_cache.clear(); }
+    // The cache is bounded: once it holds walk_cache_limit hit lists it is emptied before the next batch of walks is stored
+    // (a miss is never an error — the walk is fetched again, or answered by the host walk). Walks of one multi_search are
+    // stored together, so a request list always finds the walks of its own pass.
+    size_t walk_cache_limit = size_t(1) << 16;
 private:
     std::unordered_map<std::string, std::vector<int64_t>> sort_values;
     std::map<int32_t, std::vector<uint64_t>> host_filters;        // persistent filters: handle -> one bit per doc
@@ -713,6 +717,7 @@ public:
         kw_query pending;
         bool has_pending = false;
         std::vector<std::pair<uint32_t, walk_request>> pending_walks;
+        std::map<std::tuple<uint32_t, bool, int, std::string>, std::vector<int32_t>>* walk_scope = nullptr;   // the request list's own walk results
         int32_t filter_handle = -1;
         kw_query executed;                   // every combination the request's rounds ran (the hybrid tail probes them)
         // candidate searches already answered in an earlier pass, in call order: (tokens returned, the exclusion set afterwards).
@@ -987,18 +992,22 @@ public:
     }
     struct query_token { std::string value; bool is_prefix_searched; };
     using walk_key = std::tuple<uint32_t, bool, int, std::string>;
-    bool has_walk(const walk_key& k) const { std::lock_guard<std::mutex> lk(cache_mu); return walk_cache.count(k) != 0; }
-    bool cached_walk(const walk_key& k, std::vector<int32_t>& hits) const {
+    // `scope`: the walk results of one multi_search_batched call (they live and die with the call: nothing is carried from one
+    // request list to the next); without it, the Index-wide cache that prefetch_walks fills for single searches.
+    using walk_map = std::map<walk_key, std::vector<int32_t>>;
+    bool has_walk(const walk_key& k, const walk_map* scope = nullptr) const { std::lock_guard<std::mutex> lk(cache_mu); return (scope ? *scope : walk_cache).count(k) != 0; }
+    bool cached_walk(const walk_key& k, std::vector<int32_t>& hits, const walk_map* scope = nullptr) const {
         std::lock_guard<std::mutex> lk(cache_mu);
-        auto it = walk_cache.find(k);
-        if(it == walk_cache.end()) return false;
+        const walk_map& wc = scope ? *scope : walk_cache;
+        auto it = wc.find(k);
+        if(it == wc.end()) return false;
         hits = it->second;
         return true;
     }
     // One tsgpu_art_walk_batch for a list of (token, cost, prefix) searches on one field; the hit lists land in walk_cache.
     // A walk depends on nothing but these three — not on the tokens already taken, the previous token or a filter, which
     // only enter art_mirror_t::finish — so walks may be fetched ahead of the control flow that may or may not need them.
-    void device_walks(uint32_t fid, const std::vector<walk_request>& reqs) const {
+    void device_walks(uint32_t fid, const std::vector<walk_request>& reqs, walk_map* scope = nullptr) const {
         const art_mirror_t& art = art_of(fid);
         if(art.empty || reqs.empty()) return;
         std::unique_lock<std::mutex> up(cache_mu);
@@ -1025,9 +1034,11 @@ public:
             return;
         art_walk_stats().launches++; art_walk_stats().searches += n;
         std::lock_guard<std::mutex> lk(cache_mu);
+        if(!scope && walk_cache.size() + n > walk_cache_limit) walk_cache.clear();
+        walk_map& wc = scope ? *scope : walk_cache;
         for(uint32_t i = 0; i < n; i++)
             if(flags[i] == 0)            // flagged searches stay out of the cache: fuzzy_candidates walks them on the host
-                walk_cache[std::make_tuple(fid, reqs[i].prefix, reqs[i].cost, reqs[i].token)] =
+                wc[std::make_tuple(fid, reqs[i].prefix, reqs[i].cost, reqs[i].token)] =
                     std::vector<int32_t>(hits.begin() + (size_t) i * cap, hits.begin() + (size_t) i * cap + cnt[i]);
     }
     // Every walk fuzzy_search_fields could ask for — each token at each cost its length allows, in each searched field — in
@@ -1084,7 +1095,7 @@ public:
         bool walked = false;
         if(o.device_art_walk && !art.empty && !(replay() && cost == 0)) {      // batched multi_search: a cost-0 walk is one descent, cheaper on the host
             const walk_key key = std::make_tuple(fid, prefix_search, cost, token);
-            walked = cached_walk(key, hits);
+            walked = cached_walk(key, hits, replay() ? replay()->walk_scope : nullptr);
             if(!walked && replay()) {                 // batched multi_search: ask for it and come back in the next pass
                 replay()->pending_walks.push_back({fid, {token, cost, prefix_search}});
                 throw replay_suspend();
@@ -1380,7 +1391,8 @@ public:
         std::vector<replay_t> rs(n);
         std::vector<char> done(n, 0);
         std::vector<size_t> active(n);
-        for(size_t i = 0; i < n; i++) { active[i] = i; rs[i].filter_handle = requests[i].filter_handle; }
+        walk_map call_walks;                     // candidate walks of this request list (scoped to the call)
+        for(size_t i = 0; i < n; i++) { active[i] = i; rs[i].filter_handle = requests[i].filter_handle; rs[i].walk_scope = &call_walks; }
         if(n_threads == 0) n_threads = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), 64));
         batched_stats bs;
         auto run_one = [&](size_t i) {
@@ -1414,17 +1426,17 @@ public:
             std::set<walk_key> asked;
             for(size_t i: active) for(auto& pw: rs[i].pending_walks) {
                 const walk_key key = std::make_tuple(pw.first, pw.second.prefix, pw.second.cost, pw.second.token);
-                if(!has_walk(key) && asked.insert(key).second) per_field[pw.first].push_back(pw.second);
+                if(!has_walk(key, &call_walks) && asked.insert(key).second) per_field[pw.first].push_back(pw.second);
             }
             for(auto& pf: per_field) {
-                device_walks(pf.first, pf.second);
+                device_walks(pf.first, pf.second, &call_walks);
                 bs.walk_batches++; bs.walks += pf.second.size();
                 for(auto& w: pf.second) {                      // a search the device flagged (long term, deep stack): the host walk answers it
                     const walk_key key = std::make_tuple(pf.first, w.prefix, w.cost, w.token);
-                    if(has_walk(key)) continue;
+                    if(has_walk(key, &call_walks)) continue;
                     auto hits = art_of(pf.first).walk_hits(w.token, w.cost, w.cost, w.prefix);
                     std::lock_guard<std::mutex> lk(cache_mu);
-                    walk_cache[key] = std::move(hits);
+                    call_walks[key] = std::move(hits);
                     bs.host_walk_fallbacks++;
                 }
             }
