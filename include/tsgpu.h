@@ -157,6 +157,16 @@ tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g);
 tsgpu_status tsgpu_index_build_hnsw(tsgpu_index* idx, const float* vectors, uint32_t n, uint32_t dim, uint32_t M,
                                     uint32_t ef_construction, uint32_t seed, uint32_t metric, uint32_t max_batch,
                                     int keep_device_vectors);
+/* SURVEY 8 f-4 (vector half): hnswlib's addPoint for `n_add` MORE vectors (labels n .. n + n_add - 1, n = current node count)
+ * into the graph the index holds, built here or loaded (src/index.cpp:1052, the same call the reference makes for every new
+ * document). The existing nodes keep their links except where a new node's reverse links change them, exactly as in a
+ * sequential addPoint; levels continue the generator sequence of `seed`. Needs identity labels, M in 2..16. With
+ * max_batch == 1, build(n1) + append(n2) equals build(n1 + n2) link for link. */
+tsgpu_status tsgpu_index_append_hnsw(tsgpu_index* idx, const float* vectors, uint32_t n_add, uint32_t ef_construction, uint32_t seed, uint32_t max_batch);
+/* hnswlib's markDelete / unmarkDelete (src/index.cpp:7423 on document removal): a deleted label is never returned by a search
+ * but is still traversed. `labels`: host memory. Loading or rebuilding a graph clears all marks. (hnswlib's slot reuse for
+ * replace_deleted inserts is not mirrored: appended vectors always get new labels.) */
+tsgpu_status tsgpu_index_mark_deleted(tsgpu_index* idx, const uint32_t* labels, size_t n, int deleted);
 /* Shape of the loaded / built graph; build_counters[5] (may be null) = distance evaluations of the construction searches,
  * expansions, heuristic distance evaluations, rows re-selected, rounds of the last tsgpu_index_build_hnsw. */
 tsgpu_status tsgpu_index_hnsw_info(tsgpu_index* idx, uint32_t* n_nodes, uint32_t* dim, uint32_t* M, uint32_t* max_level,

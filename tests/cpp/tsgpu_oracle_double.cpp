@@ -340,6 +340,8 @@ tsgpu_status tsgpu_index_hnsw_info(tsgpu_index* idx, uint32_t* n_nodes, uint32_t
     if(build_counters) for(int i = 0; i < 5; i++) build_counters[i] = 0;
     return TSGPU_OK;
 }
+tsgpu_status tsgpu_index_append_hnsw(tsgpu_index*, const float*, uint32_t, uint32_t, uint32_t, uint32_t) { g_err = "the test double has no device build"; return TSGPU_ERR_NO_DEVICE; }
+tsgpu_status tsgpu_index_mark_deleted(tsgpu_index*, const uint32_t*, size_t, int) { g_err = "the test double has no deletion marks"; return TSGPU_ERR_NO_DEVICE; }
 tsgpu_status tsgpu_index_export_hnsw(tsgpu_index*, uint8_t*, uint32_t*, uint64_t*, uint32_t*) { g_err = "the test double has no device build"; return TSGPU_ERR_NO_DEVICE; }
 namespace { struct FacetCopy { uint32_t n_values; std::vector<uint64_t> off; std::vector<uint32_t> vals; }; std::vector<FacetCopy*> g_facets; }
 tsgpu_status tsgpu_index_load_facet(tsgpu_index* idx, const tsgpu_facet* f, uint32_t* out_facet) {

@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("TSGPU_LIB_PATH") or os.path.join(HERE, "libtsgpu.so")
 
 EXPORTS = [
     "tsgpu_last_error", "tsgpu_device_count", "tsgpu_index_create", "tsgpu_index_destroy", "tsgpu_index_load_field",
-    "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_index_build_hnsw", "tsgpu_index_hnsw_info", "tsgpu_index_export_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy", "tsgpu_filter_numeric", "tsgpu_filter_combine", "tsgpu_filter_ids", "tsgpu_scored_ids_search_batch",
+    "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_index_build_hnsw", "tsgpu_index_append_hnsw", "tsgpu_index_mark_deleted", "tsgpu_index_hnsw_info", "tsgpu_index_export_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy", "tsgpu_filter_numeric", "tsgpu_filter_combine", "tsgpu_filter_ids", "tsgpu_scored_ids_search_batch",
     "tsgpu_intersect", "tsgpu_contains_atleast_one", "tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches", "tsgpu_ids_setop", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
     "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats", "tsgpu_debug_knn_work", "tsgpu_comm_unique_id", "tsgpu_comm_init", "tsgpu_comm_destroy", "tsgpu_comm_gather", "tsgpu_comm_last_ms", "tsgpu_hybrid_fuse_batch", "tsgpu_index_load_facet", "tsgpu_facet_counts", "tsgpu_facet_counts_last", "tsgpu_all_result_ids_last", "tsgpu_index_load_art", "tsgpu_art_walk_batch",
 ]
@@ -58,6 +58,8 @@ def declare(L):
         L.tsgpu_index_load_sort_column.argtypes = [vp, C.c_void_p, u32p]
         L.tsgpu_index_load_hnsw.argtypes = [vp, C.POINTER(HnswStruct)]
         L.tsgpu_index_build_hnsw.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.tsgpu_index_append_hnsw.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.tsgpu_index_mark_deleted.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_int]
         L.tsgpu_index_hnsw_info.argtypes = [vp, u32p, u32p, u32p, u32p, u32p, u64p, u64p]
         L.tsgpu_index_export_hnsw.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.tsgpu_filter_create.argtypes = [vp, C.c_void_p, C.c_size_t, i32p]
@@ -197,6 +199,18 @@ class GpuIndex:
         if keep_device_vectors:
             self._keep_vectors = vectors
         return self.hnsw_info()
+
+    def append_hnsw(self, vectors, ef_construction=200, seed=100, max_batch=4096) -> dict:
+        """tsgpu_index_append_hnsw: addPoint for more vectors into the graph the index holds (labels continue)."""
+        if isinstance(vectors, np.ndarray):
+            vectors = np.ascontiguousarray(vectors, np.float32)
+        _ck(self.L.tsgpu_index_append_hnsw(self.h, _addr(vectors), int(vectors.shape[0]), ef_construction, seed, max_batch))
+        return self.hnsw_info()
+
+    def mark_deleted(self, labels, deleted=True):
+        """tsgpu_index_mark_deleted: hnswlib's markDelete / unmarkDelete."""
+        l = np.ascontiguousarray(labels, np.uint32)
+        _ck(self.L.tsgpu_index_mark_deleted(self.h, l.ctypes.data, len(l), 1 if deleted else 0))
 
     def hnsw_info(self) -> dict:
         v = [C.c_uint32(0) for _ in range(5)]

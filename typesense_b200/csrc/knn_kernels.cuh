@@ -42,6 +42,7 @@ struct HnswDev {
     const uint32_t* links0;        // [n*(2M+1)]
     const unsigned long long* upper_off;
     const uint32_t* links_up;
+    const uint32_t* deleted;       // one bit per label: hnswlib's markDelete (never a result, still traversed); nullptr = none
 };
 
 struct KnnParams {
@@ -201,13 +202,15 @@ __device__ __forceinline__ void heap_pop_min(unsigned long long* h, uint32_t& n)
 __device__ __forceinline__ unsigned long long res_key(float d, uint32_t id) { return ((unsigned long long) ord_f32(d) << 32) | id; }
 __device__ __forceinline__ unsigned long long cand_key(float d, uint32_t id) { return ((unsigned long long) ord_f32(d) << 32) | (uint32_t) ~id; }
 
+__device__ __forceinline__ bool is_excluded(const uint32_t* excl, uint32_t n_excl, uint32_t label) {
+    uint32_t lo = 0, hi = n_excl;
+    while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(excl[mid] < label) lo = mid + 1; else hi = mid; }
+    return lo < n_excl && excl[lo] == label;
+}
 __device__ __forceinline__ bool allowed(const HnswDev& g, const uint32_t* fbm, const uint32_t* excl, uint32_t n_excl, uint32_t node) {
     const uint32_t label = g.labels ? __ldg(g.labels + node) : node;
-    if(n_excl) {
-        uint32_t lo = 0, hi = n_excl;
-        while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(excl[mid] < label) lo = mid + 1; else hi = mid; }
-        if(lo < n_excl && excl[lo] == label) return false;
-    }
+    if(g.deleted && ((__ldg(g.deleted + (label >> 5)) >> (label & 31)) & 1u)) return false;       // isMarkedDeleted
+    if(n_excl && is_excluded(excl, n_excl, label)) return false;
     if(!fbm) return true;
     return (__ldg(fbm + (label >> 5)) >> (label & 31)) & 1;
 }
@@ -888,15 +891,24 @@ hnsw_walk_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ KnnP
                 nb2 = (lane + 1 < L0) ? __ldg(rec2 + 1 + lane) : kNone;
             }
             if(n_vis + 32 > limit2) { overflow = true; break; }
-            // the filter functor of every neighbour at once (one bitmap word per lane): its load is issued ahead of the visited
-            // test, whose table probe is the longer wait, and is only looked at for the fresh ones
-            const bool ok_any = (lane < size) && allowed(g, fbm, excl, n_excl, nb);
+            // the filter functor of every neighbour at once (one bitmap word per lane): the load is issued ahead of the visited
+            // test, whose table probe is the longer wait, and its result is only looked at afterwards, for the fresh ones
+            uint32_t fw = 0xffffffffu, dw = 0u;                  // only the LOADS go first; the bits are looked at after the table's answer
+            if(lane < size && !g.labels) {
+                if(fbm) fw = __ldg(fbm + (nb >> 5));
+                if(g.deleted) dw = __ldg(g.deleted + (nb >> 5));
+            }
             bool to_table = false;
             const bool fresh = (lane < size) && vis_test_and_set(cache, cmask, vis2, mask2, nb, &to_table);
             uint32_t mask = __ballot_sync(0xffffffffu, fresh);
             n_vis += __popc(mask);
             n_tab_acc += __popc(__ballot_sync(0xffffffffu, to_table));
-            const uint32_t ok_mask = __ballot_sync(0xffffffffu, fresh && ok_any);
+            bool ok_mine = false;
+            if(fresh) {
+                if(g.labels) ok_mine = allowed(g, fbm, excl, n_excl, nb);
+                else ok_mine = ((fw >> (nb & 31)) & 1u) && !((dw >> (nb & 31)) & 1u) && !(n_excl && is_excluded(excl, n_excl, nb));
+            }
+            const uint32_t ok_mask = __ballot_sync(0xffffffffu, ok_mine);
             n_dist_acc += __popc(mask);
             // Hints for the likely next expansion (no effect on results): the neighbours of the buffer's front that the visited
             // cache does not recognise will most probably be probed in the table and have their rows fetched one iteration
@@ -1093,6 +1105,15 @@ hnsw_validate_kernel(const HnswDev g, unsigned long long n_up, uint32_t* __restr
         }
         if(err) atomicCAS(bad, 0u, err);
     }
+}
+
+
+__global__ void __launch_bounds__(256)
+mark_deleted_kernel(const uint32_t* __restrict__ labels, size_t n, uint32_t* __restrict__ bitmap, bool set) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const uint32_t l = labels[i];
+    if(set) atomicOr(bitmap + (l >> 5), 1u << (l & 31)); else atomicAnd(bitmap + (l >> 5), ~(1u << (l & 31)));
 }
 
 }  // namespace tsv

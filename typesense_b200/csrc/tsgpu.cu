@@ -126,6 +126,7 @@ struct tsgpu_index {
     bool has_hnsw = false;
     tsv::HnswDev hnsw{};
     std::vector<void*> hnsw_alloc;
+    uint32_t* d_deleted = nullptr; size_t deleted_words = 0;     // markDelete bitmap over labels (lives with the index, survives appends)
     std::vector<Filter> filters;
     struct FacetMirror { tsfc::FacetDev dev{}; void* d_off = nullptr; void* d_vals = nullptr; };
     std::vector<FacetMirror> facets;
@@ -979,6 +980,7 @@ void tsgpu_index_destroy(tsgpu_index* idx) {
     for(auto& f: idx->fields) for(void* p: f.d_alloc) if(p) cudaFree(p);
     for(auto* c: idx->sort_cols) cudaFree(c);
     for(void* p: idx->hnsw_alloc) cudaFree(p);
+    if(idx->d_deleted) cudaFree(idx->d_deleted);
     for(auto& f: idx->filters) { if(f.d_bitmap) cudaFree(f.d_bitmap); if(f.d_ids) cudaFree(f.d_ids); }
     for(auto& fm: idx->facets) { if(fm.d_off) cudaFree(fm.d_off); if(fm.d_vals) cudaFree(fm.d_vals); }
     idx->d_keep_bm.release(); idx->d_facet.release(); idx->d_comm.release();
@@ -1139,6 +1141,10 @@ tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g) {
         bool ident = true;
         for(size_t i = 0; i < n && ident; i++) ident = hl[i] == i;
         if(ident) h.labels = nullptr;
+    }
+    if(idx->d_deleted) {                         // a newly loaded graph starts with nothing deleted
+        CU(cudaMemsetAsync(idx->d_deleted, 0, idx->deleted_words * 4, idx->stream));
+        CU(cudaStreamSynchronize(idx->stream));
     }
     guard.keep = true;
     for(void* q: idx->hnsw_alloc) cudaFree(q);

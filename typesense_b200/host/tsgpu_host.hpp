@@ -407,6 +407,21 @@ public:
         if(tsgpu_index_load_hnsw(h, &g) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
         return Option<bool>(true);
     }
+    // The write side of hnsw_index_t (src/index.cpp:1003-1054, 7423): the vecdex->addPoint loop of a batch of new documents
+    // (labels = the next seq_ids) and vecdex->markDelete on removal. build_vector_field replaces the whole graph.
+    Option<bool> build_vector_field(const float* vectors, uint32_t n, uint32_t dim, uint32_t M = 16, uint32_t ef_construction = 200,
+                                    uint32_t seed = 100, uint32_t metric = 0, uint32_t max_batch = 4096) {
+        if(tsgpu_index_build_hnsw(h, vectors, n, dim, M, ef_construction, seed, metric, max_batch, 0) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
+        return Option<bool>(true);
+    }
+    Option<bool> add_vectors(const float* vectors, uint32_t n_add, uint32_t ef_construction = 200, uint32_t seed = 100, uint32_t max_batch = 4096) {
+        if(tsgpu_index_append_hnsw(h, vectors, n_add, ef_construction, seed, max_batch) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
+        return Option<bool>(true);
+    }
+    Option<bool> remove_vectors(const std::vector<uint32_t>& seq_ids, bool deleted = true) {
+        if(tsgpu_index_mark_deleted(h, seq_ids.data(), seq_ids.size(), deleted ? 1 : 0) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
+        return Option<bool>(true);
+    }
 
     uint32_t token_id(uint32_t field, const std::string& tok) const {
         auto it = token_ids[field].find(tok);
