@@ -72,7 +72,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", default="hnsw", choices=["hnsw", "bulk"], help="hnsw: built by tsgpu_index_build_hnsw; bulk: r01's harness stand-in")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the secondary BASELINE.json configurations (other_configs)")
-    ap.add_argument("--e2e-depth", type=int, default=4, help="multi_search calls in flight in the end-to-end leg (1 = strictly one after the other)")
+    ap.add_argument("--e2e-threads", type=int, default=32, help="host threads of one multi_search call's control-flow passes (capped at the core count)")
+    ap.add_argument("--e2e-depth", type=int, default=8, help="multi_search calls in flight in the end-to-end leg (1 = strictly one after the other)")
     ap.add_argument("--no-graph-cache", action="store_true", help="always rebuild the HNSW graph (default: reuse /tmp/tsgpu_bench_cache)")
     ap.add_argument("--exp-sorted-vectors", action="store_true",
                     help="experiment only: store vectors in cluster order (seq_id locality) to measure what row locality is worth")
@@ -537,7 +538,7 @@ def run_tsgpu(args, rank, world, local_rank):
     E2E_DEPTH = max(1, args.e2e_depth)              # multi_search calls in flight in the end-to-end leg (client threads of a server)
     host_bufs = [(np.zeros((max_nl, stride), S.KV_DTYPE), np.zeros(max_nl, np.uint32), np.zeros(max_nl, np.uint32)) for _ in range(E2E_DEPTH)]
     host_kv, host_cnt, host_fnd = host_bufs[0]
-    host_opt = hostapi.Options(device_art_walk=1, n_threads=min(os.cpu_count() or 1, 64), **HOST_OPTIONS)
+    host_opt = hostapi.Options(device_art_walk=1, n_threads=max(1, min(os.cpu_count() or 1, args.e2e_threads)), **HOST_OPTIONS)
     comm_ms = []
 
     def step(i, mode):
@@ -769,7 +770,7 @@ def run_tsgpu(args, rank, world, local_rank):
                "dtype": "u32+f32", "data": "synthetic", "config": workload_config(args, nq),
                "e2e": {"value": e2e, "unit": "queries/s", "ms_per_step": 1000 * dt_e2e / args.steps,
                        "h2d_bytes_per_step": int((x1[0] - x0[0]) / e2e_steps), "d2h_bytes_per_step": int((x1[1] - x0[1]) / e2e_steps),
-                       "device_calls_per_step": (x1[2] - x0[2]) / e2e_steps, "calls_in_flight": E2E_DEPTH,
+                       "device_calls_per_step": (x1[2] - x0[2]) / e2e_steps, "calls_in_flight": E2E_DEPTH, "host_threads_per_call": int(host_opt.n_threads),
                        "path": "query strings -> C++ host layer (libtshost.so: tokens, ART candidate walks on the device, typo / prefix / drop-token control flow) -> "
                                "C-ABI rounds with host buffers -> tsgpu_hybrid_fuse_batch; rank 0's slice per step" + (" + NCCL gather" if world > 1 else "")},
                "e2e_resolved": {"value": nq * args.steps / dt_pin, "unit": "queries/s", "ms_per_step": 1000 * dt_pin / args.steps,

@@ -188,7 +188,7 @@ size_t am_walk_frontier(void* hv, const char* term, int min_cost, int max_cost, 
         next.clear();
         for(auto& it: cur) {                               // on the device: one thread / warp per item
             bool hit = false;
-            const bool descend = tsdev::art_enter(A, Q, it, &hit);
+            const bool descend = tsdev::art_enter_fast(A, Q, it, &hit);      // the form the frontier kernel calls (register rows for short queries)
             if(hit) hits.push_back(it.ref);
             if(descend) for(uint32_t k = 0; k < nodes[it.ref].n_children; k++) { next.emplace_back(); tsdev::art_child_item(A, Q, it, k, next.back()); }
         }

@@ -150,6 +150,159 @@ TS_HD bool art_enter(const ArtDev& A, const ArtQuery& Q, ArtItem& it, bool* hit)
     return true;
 }
 
+// art_enter() for query tokens of at most QL bytes with every DP row in REGISTERS: arrays of compile-time size, every loop
+// unrolled to QL with the column test as a predicate, the three rows rotated by copies (moves the compiler renames away),
+// dynamic row reads as select chains, a leaf's remaining key bytes loaded together before the first of them is used
+// (independent loads instead of one dependent byte load per step). Same arithmetic, same rules, same results as art_enter():
+// the frontier kernel's items spend their time here, and the general form keeps rows[3][32] in local memory behind run-time
+// indices (profiles/r02s: 31 % of the end-to-end bench's kernel time was art_frontier_kernel).
+template <int QL>
+TS_HD uint8_t art_pick(const uint8_t (&row)[QL + 1], int idx) {
+    uint8_t v = row[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int i = 1; i <= QL; i++) v = (i == idx) ? row[i] : v;
+    return v;
+}
+template <int QL>
+TS_HD int art_state_t(const ArtQuery& Q, const uint8_t (&qq)[QL + 3], int key_index, uint8_t p, uint8_t c, const uint8_t (&row)[QL + 1]) {
+    // qq[i + 1] = Q.q[i] for 0 <= i < qlen, 0 elsewhere (so that index -1 .. QL + 1 can be read)
+    const bool key_ends = c == 0;
+    const int key_len = key_ends ? key_index : key_index + 1;
+    const int qlen = Q.qlen;
+    if(key_ends) {
+        const uint8_t rq = art_pick<QL>(row, qlen);
+        if(rq >= Q.min_cost && rq <= Q.max_cost) return 1;
+        if(key_len > 5 && qlen > key_len && qlen - key_len <= Q.max_cost) {
+            const uint8_t rk = art_pick<QL>(row, key_len);
+            if(rk >= Q.min_cost && rk <= Q.max_cost - 1) return 1;
+        }
+        return -1;
+    }
+    const int cost = art_pick<QL>(row, key_len < qlen ? key_len : qlen);
+    if(Q.prefix && key_len >= qlen && cost >= Q.min_cost && cost <= Q.max_cost) return 1;
+    if(cost <= Q.max_cost) return 0;
+    auto qat = [&](int i) -> uint8_t {          // Q.q[i] for i in [-1, QL + 1], 0 outside the query
+        uint8_t v = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int j = 0; j < QL + 3; j++) v = (j == i + 1) ? qq[j] : v;
+        return v;
+    };
+    if(cost == 2 || cost == 3) {
+        if((key_index + 1 < qlen && qat(key_index + 1) == c) || (key_index > 0 && key_index - 1 < qlen && qat(key_index - 1) == c)) return 0;
+    }
+    if(cost == 3 || cost == 4) {
+        if(key_index + 2 < qlen && qat(key_index + 1) == p && qat(key_index + 2) == c) return 0;
+        if(key_index > 1 && key_index - 2 < qlen && qat(key_index - 2) == c) return 0;
+    }
+    return -1;
+}
+
+template <int QL>
+TS_HD bool art_enter_t(const ArtDev& A, const ArtQuery& Q, ArtItem& it, bool* hit) {
+    const int qlen = Q.qlen;                    // <= QL (caller's dispatch)
+    uint8_t r2[QL + 1], r1[QL + 1], r0[QL + 1], qq[QL + 3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int i = 0; i <= QL; i++) { r2[i] = it.prev2[i]; r1[i] = it.prev[i]; r0[i] = 0; }
+    qq[0] = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int i = 0; i < QL + 2; i++) qq[i + 1] = (i < qlen) ? Q.q[i] : (uint8_t) 0;
+    int depth = it.depth;
+    uint8_t p = it.p, c = it.c;
+    const int32_t ref = it.ref;
+    bool decided = false;
+    *hit = false;
+    auto step = [&](uint8_t byte_, bool advance) {
+        if(advance) {
+            // art_next_row(depth, p, byte_, Q, r2, r1, r0)
+            r0[0] = (uint8_t) (r1[0] + 1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for(int col = 1; col <= QL; col++) {
+                if(col <= qlen) {
+                    int v = r1[col - 1] + (byte_ == qq[col] ? 0 : 1);
+                    const int ins = r0[col - 1] + 1, del = r1[col] + 1;
+                    if(ins < v) v = ins;
+                    if(del < v) v = del;
+                    if(col > 1) { if(depth > 1 && byte_ == qq[col - 1] && p == qq[col]) { const int tr = r2[col - 2] + 1; if(tr < v) v = tr; } }
+                    r0[col] = (uint8_t) v;
+                }
+            }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for(int i = 0; i <= QL; i++) { r2[i] = r1[i]; r1[i] = r0[i]; }
+        }
+        const int a_ = art_state_t<QL>(Q, qq, depth, p, byte_, r1);
+        if(a_ == 1) *hit = true;
+        if(a_ != 0) decided = true; else { p = byte_; depth++; }
+    };
+    if(depth == -1) depth = 0;
+    else step(c, !(Q.prefix && c == 0));
+    if(decided) return false;
+    if(ref < 0) {
+        const uint64_t o = A.leaf_key_off[~ref];
+        const int klen = (int) (A.leaf_key_off[~ref + 1] - o) + 1;            // with the terminator
+        const int iter_len = klen < qlen + Q.max_cost ? klen : qlen + Q.max_cost;
+        if(depth >= iter_len) { *hit = art_state_t<QL>(Q, qq, depth, 0, 0, r1) == 1; return false; }
+        // the bytes this loop can read: key positions depth .. iter_len - 1, at most QL + 3 of them from `depth`
+        constexpr int KB = QL + 4;
+        uint8_t kb[KB];
+        const int d0 = depth;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int j = 0; j < KB; j++) { const int pos = d0 + j; kb[j] = (pos < iter_len && pos < klen - 1) ? A.leaf_keys[o + pos] : (uint8_t) 0; }
+        if(iter_len - d0 > KB) {                 // cannot happen for max_cost <= 3 (iter_len <= qlen + max_cost); keep the general loop for safety
+            while(depth < iter_len && !decided) { c = depth < klen - 1 ? A.leaf_keys[o + depth] : 0; step(c, !(Q.prefix && c == 0)); }
+            return false;
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int j = 0; j < KB; j++) {
+            if(d0 + j < iter_len && !decided && depth == d0 + j) { c = kb[j]; step(c, !(Q.prefix && c == 0)); }
+        }
+        return false;
+    }
+    const ArtNodeDev& n = A.nodes[ref];
+    const int plen = n.partial_len;
+    int seen = plen < kArtPartialBytes ? plen : kArtPartialBytes;
+    uint8_t pb[kArtPartialBytes];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int i = 0; i < kArtPartialBytes; i++) pb[i] = n.partial[i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int i = 0; i < kArtPartialBytes; i++) { if(i < seen && !decided) { c = pb[i]; step(c, true); } }
+    // only the first kArtPartialBytes of a compressed path are stored: the rest is assumed to agree with the query
+    while(!decided && seen < plen && depth < qlen) { c = Q.q[depth]; step(c, true); seen++; }
+    if(decided) return false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int i = 0; i <= QL; i++) { it.prev2[i] = r2[i]; it.prev[i] = r1[i]; }
+    it.depth = (int16_t) depth; it.c = c;
+    return true;
+}
+
+// dispatch on the query's length
+TS_HD bool art_enter_fast(const ArtDev& A, const ArtQuery& Q, ArtItem& it, bool* hit) {
+    if(Q.qlen <= 10) return art_enter_t<10>(A, Q, it, hit);
+    if(Q.qlen <= 16) return art_enter_t<16>(A, Q, it, hit);
+    return art_enter(A, Q, it, hit);
+}
+
 TS_HD void art_root_item(const ArtDev& A, const ArtQuery& Q, ArtItem& it) {
     it.ref = A.root; it.p = 0; it.c = 0; it.depth = -1;
     if(A.root < 0) {              // a one-key index: the root is that leaf and its first byte is read like any other

@@ -99,9 +99,9 @@ art_frontier_kernel(const ArtDev A, const ArtQuery* __restrict__ queries, const 
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n_in) return;
     ArtWorkItem w = in[i];
-    const ArtQuery Q = queries[w.search];
+    const ArtQuery& Q = queries[w.search];
     bool hit = false;
-    const bool descend = art_enter(A, Q, w.at, &hit);
+    const bool descend = art_enter_fast(A, Q, w.at, &hit);
     if(hit) {
         const uint32_t pos = atomicAdd(counters + 1, 1u);
         if(pos < hit_cap) hits[pos] = Hit{w.search, w.at.ref}; else atomicOr(counters + 2, 1u);
@@ -110,11 +110,12 @@ art_frontier_kernel(const ArtDev A, const ArtQuery* __restrict__ queries, const 
         const uint32_t nch = A.nodes[w.at.ref].n_children;
         const uint32_t base = atomicAdd(counters + 0, nch);
         if(base + nch > out_cap) { atomicOr(counters + 2, 2u); return; }
+        const uint32_t first = A.nodes[w.at.ref].first_child;
+        w.at.p = w.at.c;                          // art_child_item(): a child is its parent's state + the byte and link that lead to it
         for(uint32_t k = 0; k < nch; k++) {
-            ArtWorkItem ch;
-            ch.search = w.search;
-            art_child_item(A, Q, w.at, k, ch.at);
-            out[base + k] = ch;
+            w.at.ref = A.child_ref[first + k];
+            w.at.c = A.child_byte[first + k];
+            out[base + k] = w;
         }
     }
 }

@@ -40,6 +40,7 @@
 #include <mutex>
 #include <condition_variable>
 #include <set>
+#include <stdexcept>
 #include <string>
 #include <tuple>
 #include <unordered_map>
@@ -291,6 +292,7 @@ class Index {
     // fields or sort columns (a server-side binding loads it from an export of the live art_tree instead, see art_mirror.hpp)
     mutable std::vector<art_mirror_t> arts;
     mutable std::vector<char> arts_ready, arts_on_device;      // char, not bool: flags of different fields are touched independently
+    mutable std::mutex art_upload_mu;                        // serialises tsgpu_index_load_art uploads only
     mutable std::mutex cache_mu;                             // searches may run concurrently on one Index (as on the reference's): guards the lazy caches
     // device_art_walk: hit lists fetched ahead by prefetch_walks, keyed by (field, prefix search, cost, token)
     mutable std::map<std::tuple<uint32_t, bool, int, std::string>, std::vector<int32_t>> walk_cache;
@@ -1025,16 +1027,22 @@ public:
     void device_walks(uint32_t fid, const std::vector<walk_request>& reqs, walk_map* scope = nullptr) const {
         const art_mirror_t& art = art_of(fid);
         if(art.empty || reqs.empty()) return;
-        std::unique_lock<std::mutex> up(cache_mu);
-        if(!arts_on_device[fid]) {
-            const auto f = art.flatten();
-            tsgpu_art a{(uint32_t) art.nodes.size(), (uint32_t) art.child_byte.size(), (uint32_t) art.leaves.size(), art.root,
-                        f.node_first_child.data(), f.node_n_children.data(), f.node_partial_len.data(), f.node_partial.data(),
-                        art.child_byte.data(), art.child_ref.data(), f.leaf_key_off.data(), f.leaf_keys.data(), nullptr, nullptr};
-            arts_on_device[fid] = tsgpu_index_load_art(h, fid, &a) == TSGPU_OK ? 1 : 0;
-            if(!arts_on_device[fid]) return;
+        bool on_dev;
+        { std::lock_guard<std::mutex> lk(cache_mu); on_dev = arts_on_device[fid] != 0; }
+        if(!on_dev) {            // the upload (a device allocation + copies) runs under a mutex of its own: searches that only read the caches go on
+            std::lock_guard<std::mutex> ul(art_upload_mu);
+            { std::lock_guard<std::mutex> lk(cache_mu); on_dev = arts_on_device[fid] != 0; }
+            if(!on_dev) {
+                const auto f = art.flatten();
+                tsgpu_art a{(uint32_t) art.nodes.size(), (uint32_t) art.child_byte.size(), (uint32_t) art.leaves.size(), art.root,
+                            f.node_first_child.data(), f.node_n_children.data(), f.node_partial_len.data(), f.node_partial.data(),
+                            art.child_byte.data(), art.child_ref.data(), f.leaf_key_off.data(), f.leaf_keys.data(), nullptr, nullptr};
+                const bool ok = tsgpu_index_load_art(h, fid, &a) == TSGPU_OK;
+                std::lock_guard<std::mutex> lk(cache_mu);
+                arts_on_device[fid] = ok ? 1 : 0;
+                if(!ok) return;
+            }
         }
-        up.unlock();
         const uint32_t n = (uint32_t) reqs.size(), cap = 1024;
         std::vector<uint32_t> off(1, 0), cnt(n);
         std::vector<uint8_t> terms, cost8, pre8, flags(n);
@@ -1611,8 +1619,7 @@ public:
         std::vector<std::pair<float, size_t>> out;
         if(tsgpu_knn_batch(h, query, 1, (uint32_t) k, (uint32_t) ef, &slot, filter_ids ? 1 : 0, off,
                            filter_ids && !filter_ids->empty() ? filter_ids->data() : &zero, dist.data(), labels.data(), &n) != TSGPU_OK) {
-            err = tsgpu_last_error();
-            return out;
+            throw std::runtime_error(tsgpu_last_error());          // hnswlib's own error convention (caught at src/index.cpp:3354-3359)
         }
         for(uint32_t i = 0; i < n; i++) out.emplace_back(dist[i], (size_t) labels[i]);
         return out;
