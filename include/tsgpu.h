@@ -133,7 +133,12 @@ typedef struct {
     float    distance_threshold; /* FLT_MAX default */
     float    alpha;              /* 0.3 default */
     uint32_t fetch_size;
+    uint32_t flags;              /* TSGPU_VEC_* (0 = the reference's fp32 loop everywhere: bit-equal distances) */
 } tsgpu_vec_params;
+/* Flat-path queries (filter below flat_search_cutoff) of one call that share a filter are scanned together on the tensor cores
+ * (see tsgpu_flat_distances_batch): same ids, distances within ~1e-6 absolute of the fp32 loop instead of bit-equal — so two
+ * candidates whose distances differ by less than that may swap ranks. Opt-in for that reason. */
+#define TSGPU_VEC_FLAT_TENSOR 1u
 
 const char* tsgpu_last_error(void);
 int tsgpu_device_count(void);
@@ -280,6 +285,14 @@ tsgpu_status tsgpu_knn_batch(tsgpu_index* idx, const float* queries, uint32_t nq
 
 /* process_results_bruteforce (src/index.cpp:3345-3374): distance of the query to every id, in id order. */
 tsgpu_status tsgpu_flat_distances(tsgpu_index* idx, const float* query, const uint32_t* ids, size_t n, float* out_dist);
+/* The same for nq queries that share ONE candidate set (the requests of a multi_search that carry the same filter_by, each below
+ * flat_search_cutoff): out_dist[q*n + i] = distance(query q, ids[i]). The loop of src/index.cpp:3345-3374 over (query, id) pairs is
+ * the contraction [n x dim] . [dim x nq]: it runs on the tensor cores (tcgen05.mma kind::tf32, 3-term split of the fp32 operands,
+ * fp32 accumulation in TMEM; csrc/flat_tc.cu) when dim is a multiple of 32, else pair by pair like tsgpu_flat_distances. Distances
+ * agree with the fp32 loop to ~1e-6 absolute (gate: 1e-4 relative), not bit for bit. queries / ids / out_dist: host or device memory.
+ * tsgpu_vector_search_batch / tsgpu_hybrid_search_batch route their flat-path queries through the same kernel when >= 8 of them
+ * share a filter. */
+tsgpu_status tsgpu_flat_distances_batch(tsgpu_index* idx, const float* queries, uint32_t nq, const uint32_t* ids, size_t n, float* out_dist);
 
 /* Wildcard + vector query (src/index.cpp:3645-3732). Filters / exclusions / sort clauses / topk come from `b`
  * (its combinations are ignored). */
@@ -375,6 +388,7 @@ typedef struct {
     uint64_t d2h_total;
     uint64_t calls_total;        /* C-ABI search calls since index creation */
     uint64_t knn_table_probes;   /* neighbour tests of the graph walks that missed the shared-memory visited cache (went to the HBM table) */
+    uint64_t flat_tc_queries;    /* flat-path queries answered by the tensor-core scan (groups sharing a candidate set) in the last call */
 } tsgpu_stats;
 tsgpu_status tsgpu_get_stats(tsgpu_index* idx, tsgpu_stats* out);
 /* Instrumentation: per graph walk of the last HNSW launch, out[2q] = expanded nodes, out[2q+1] = distance evaluations. */

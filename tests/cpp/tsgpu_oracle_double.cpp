@@ -19,7 +19,7 @@ static_assert(sizeof(tsgpu_kv) == sizeof(tso_kv), "KV layout");
 static_assert(sizeof(tsgpu_field) == sizeof(tso_field), "field layout");
 static_assert(sizeof(tsgpu_kw_batch) == sizeof(tso_kw_batch), "batch layout");
 static_assert(sizeof(tsgpu_hnsw) == sizeof(tso_hnsw), "hnsw layout");
-static_assert(sizeof(tsgpu_vec_params) == sizeof(tso_vec_params), "vec params layout");
+static_assert(sizeof(tsgpu_vec_params) == sizeof(tso_vec_params) + sizeof(uint32_t), "vec params layout: the oracle reads the leading fields (flags only select a device code path)");
 
 namespace {
 struct FieldCopy {
@@ -258,6 +258,12 @@ tsgpu_status tsgpu_flat_distances(tsgpu_index* idx, const float* query, const ui
     Double* d = D(idx);
     if(!d->has_g) { g_err = "no vector index loaded"; return TSGPU_ERR_INVALID; }
     tso_flat_distances(&d->g, query, ids, n, out_dist);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_flat_distances_batch(tsgpu_index* idx, const float* queries, uint32_t nq, const uint32_t* ids, size_t n, float* out_dist) {
+    Double* d = D(idx);
+    if(!d->has_g) { g_err = "no vector index loaded"; return TSGPU_ERR_INVALID; }
+    for(uint32_t q = 0; q < nq; q++) tso_flat_distances(&d->g, queries + (size_t) q * d->g.dim, ids, n, out_dist + (size_t) q * n);
     return TSGPU_OK;
 }
 tsgpu_status tsgpu_filter_create(tsgpu_index* idx, const uint32_t* ids, size_t n, int32_t* out_handle) {

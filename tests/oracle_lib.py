@@ -250,6 +250,14 @@ class OracleIndex:
         qv = np.ascontiguousarray(qvecs, np.float32)
         return self._run(self.L.tso_vector_search_batch, b, stride, threads, (qv.ctypes.data_as(f32p), C.byref(vp)))
 
+    def flat_distances(self, query: np.ndarray, ids: np.ndarray) -> np.ndarray:
+        """tso_flat_distances: process_results_bruteforce's loop (src/index.cpp:3345-3374), fp32, in id order."""
+        q = np.ascontiguousarray(query, np.float32)
+        ids = np.ascontiguousarray(ids, np.uint32)
+        out = np.zeros(max(len(ids), 1), np.float32)
+        self.L.tso_flat_distances(C.byref(self.hs), q.ctypes.data_as(f32p), p32(ids), len(ids), out.ctypes.data_as(f32p))
+        return out[:len(ids)]
+
     def knn(self, queries: np.ndarray, k: int, ef: int, q_filter=None, filters=(), threads: int = 1):
         q = np.ascontiguousarray(queries, np.float32)
         nq = q.shape[0]

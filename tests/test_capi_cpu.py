@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     assert capi.KV_DTYPE.itemsize == 56
     assert C.sizeof(capi.FieldStruct) == 8 + 4 * 8
-    assert C.sizeof(capi.VecParamsStruct) == 24
+    assert C.sizeof(capi.VecParamsStruct) == 28          # k, ef, flat_search_cutoff, distance_threshold, alpha, fetch_size, flags
 
 
 def _has_gpu():

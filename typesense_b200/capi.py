@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("TSGPU_LIB_PATH") or os.path.join(HERE, "libtsgpu.so")
 EXPORTS = [
     "tsgpu_last_error", "tsgpu_device_count", "tsgpu_index_create", "tsgpu_index_destroy", "tsgpu_index_load_field",
     "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_index_build_hnsw", "tsgpu_index_append_hnsw", "tsgpu_index_mark_deleted", "tsgpu_index_hnsw_info", "tsgpu_index_export_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy", "tsgpu_filter_numeric", "tsgpu_filter_combine", "tsgpu_filter_ids", "tsgpu_scored_ids_search_batch",
-    "tsgpu_intersect", "tsgpu_contains_atleast_one", "tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches", "tsgpu_ids_setop", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances",
+    "tsgpu_intersect", "tsgpu_contains_atleast_one", "tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches", "tsgpu_ids_setop", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances", "tsgpu_flat_distances_batch",
     "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats", "tsgpu_debug_knn_work", "tsgpu_comm_unique_id", "tsgpu_comm_init", "tsgpu_comm_destroy", "tsgpu_comm_gather", "tsgpu_comm_last_ms", "tsgpu_hybrid_fuse_batch", "tsgpu_index_load_facet", "tsgpu_facet_counts", "tsgpu_facet_counts_last", "tsgpu_all_result_ids_last", "tsgpu_index_load_art", "tsgpu_art_walk_batch",
 ]
 
@@ -78,6 +78,7 @@ def declare(L):
         L.tsgpu_knn_batch.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, i32p, C.c_uint32, u64p, u32p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
         L.tsgpu_flat_distances.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.tsgpu_flat_distances_batch.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]
         for n in ("tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch"):
             getattr(L, n).argtypes = [vp, C.POINTER(KwBatchStruct), C.c_void_p, C.POINTER(VecParamsStruct), C.c_void_p,
                                       C.c_uint32, C.c_void_p, C.c_void_p]
@@ -396,6 +397,16 @@ class GpuIndex:
         out = np.zeros(max(len(ids), 1), np.float32)
         _ck(self.L.tsgpu_flat_distances(self.h, q.ctypes.data, ids.ctypes.data, len(ids), out.ctypes.data))
         return out[:len(ids)]
+
+    def flat_distances_batch(self, queries: np.ndarray, ids: np.ndarray) -> np.ndarray:
+        """tsgpu_flat_distances_batch: [nq, n] distances of nq queries to one shared candidate set (tensor-core scan)."""
+        q = np.ascontiguousarray(queries, np.float32)
+        ids = np.ascontiguousarray(ids, np.uint32)
+        out = np.zeros((q.shape[0], max(len(ids), 1)), np.float32)
+        if len(ids):
+            out = np.zeros((q.shape[0], len(ids)), np.float32)
+            _ck(self.L.tsgpu_flat_distances_batch(self.h, q.ctypes.data, q.shape[0], ids.ctypes.data, len(ids), out.ctypes.data))
+        return out[:, :len(ids)]
 
     # ---- multi-GPU (SURVEY 8e): the library's own NCCL exchange
     def comm_unique_id(self) -> np.ndarray:

@@ -1044,6 +1044,7 @@ struct FlatParams {
     uint32_t nq;
     float* out_dist;               // aligned with ids
     unsigned long long* stats;
+    const uint8_t* q_skip;         // [nq] 1 = this query's range is answered by the tensor-core scan (flat_tc.cu); nullptr = none
 };
 
 template <int NCH>
@@ -1061,6 +1062,7 @@ flat_distance_kernel(const __grid_constant__ HnswDev g, const __grid_constant__ 
         // locate the query of element i (binary search over q_off)
         uint32_t lo = 0, hi = P.nq;
         while(lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; if(P.q_off[mid] <= i) lo = mid; else hi = mid; }
+        if(P.q_skip && P.q_skip[lo]) continue;
         if(lo != cur_q) {
             cur_q = lo;
             const float* qv = P.queries + (size_t) cur_q * dim;

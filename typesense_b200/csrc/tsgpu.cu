@@ -11,6 +11,7 @@
 #include <cstring>
 #include <chrono>
 #include <cmath>
+#include <map>
 #include <mutex>
 #include <random>
 #include <string>
@@ -22,6 +23,13 @@
 #include "hnsw_build.cuh"
 #include "facet_kernels.cuh"
 #include "postings_pack.h"
+
+// flat_tc.cu: the batched flat scan on the tensor cores (tcgen05, tf32 x 3)
+extern "C" size_t tsgpu_flat_tc_image_bytes_(uint32_t ng, uint32_t dim, uint32_t* n_tile_out, uint32_t* n_qtiles_out);
+extern "C" int tsgpu_flat_tc_supported_(uint32_t dim);
+extern "C" cudaError_t tsgpu_flat_tc_run_(const float* vectors, uint32_t n_nodes, uint32_t dim, const float* queries, const uint32_t* qsel, uint32_t ng,
+                                          const uint32_t* ids, uint32_t n_ids, const unsigned long long* out_off, float* out_dist,
+                                          unsigned char* img, int n_sms, cudaStream_t stream, int* launches);
 
 using namespace tsk;
 
@@ -118,7 +126,7 @@ struct tsgpu_index {
     uint32_t* knn_work_dev = nullptr; uint32_t knn_work_n = 0;   // per-walk counters of the last HNSW launch (tsgpu_debug_knn_work)
     unsigned char* knn_misc_dev = nullptr;    // counters of the last HNSW launch (read after the final sync)
     std::vector<unsigned char> knn_tables;   // host copies that must outlive the async uploads
-    std::vector<uint8_t> tmp_is_flat; std::vector<unsigned long long> tmp_foff;
+    std::vector<uint8_t> tmp_is_flat; std::vector<unsigned long long> tmp_foff; std::vector<unsigned char> flat_tc_host;
     std::mutex mu;
     std::vector<FieldMirror> fields;
     IndexDev ixdev{};
@@ -131,7 +139,7 @@ struct tsgpu_index {
     struct FacetMirror { tsfc::FacetDev dev{}; void* d_off = nullptr; void* d_vals = nullptr; };
     std::vector<FacetMirror> facets;
     std::vector<const uint32_t*> keep_bitmaps;      // per query of the last search: its all_result_ids bitmap (device) or nullptr
-    DevBuf d_keep_bm, d_facet, d_comm;
+    DevBuf d_keep_bm, d_facet, d_comm, d_flat_tc;
     void* comm = nullptr; int comm_rank = 0, comm_world = 1; float last_comm_ms = 0;       // ncclComm_t of tsgpu_comm_init
     int n_sms = 148;
     // scratch
@@ -792,6 +800,18 @@ tsgpu_status finish_knn(tsgpu_index* idx) {
     return TSGPU_OK;
 }
 
+// smallest group of flat-path queries sharing a candidate set that goes to the tensor-core scan (0 = never; TSGPU_FLAT_TC=0)
+int flat_tc_min_group() {
+    static const int v = [] {
+        if(const char* e = getenv("TSGPU_FLAT_TC")) if(atoi(e) == 0) return 0;
+        if(const char* e = getenv("TSGPU_FLAT_TC_MIN")) return std::max(1, atoi(e));
+        return 8;
+    }();
+    return v;
+}
+
+bool flat_tc_forced() { static const bool v = [] { const char* e = getenv("TSGPU_FLAT_TC"); return e && atoi(e) == 1; }(); return v; }
+
 template <int NCH>
 void launch_flat(tsgpu_index* idx, const tsv::FlatParams& P, unsigned long long total, unsigned grid, size_t smem) {
     tsv::flat_distance_kernel<NCH><<<grid, 256, smem, idx->vs>>>(idx->hnsw, P, total);
@@ -886,7 +906,8 @@ tsgpu_status run_vector_stage(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan&
     const size_t o_fo = (o_if + nq + 255) & ~size_t(255);
     const size_t o_fi = (o_fo + (size_t) (nq + 1) * 8 + 255) & ~size_t(255);
     const size_t o_fd = (o_fi + total_flat * 4 + 255) & ~size_t(255);
-    const size_t tot = o_fd + total_flat * 4 + 256;
+    const size_t o_sk = (o_fd + total_flat * 4 + 255) & ~size_t(255);
+    const size_t tot = o_sk + nq + 256;
     CU(idx->d_small.reserve(tot));
     unsigned char* base = idx->d_small.as<unsigned char>();
     CU(cudaMemcpyAsync(base + o_q, qvecs, q_bytes, cudaMemcpyDefault, st));
@@ -903,13 +924,72 @@ tsgpu_status run_vector_stage(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan&
     vs.flat_ids = reinterpret_cast<const uint32_t*>(base + o_fi);
     vs.flat_dist = reinterpret_cast<const float*>(base + o_fd);
     if(total_flat) {
-        tsv::FlatParams FP{};
-        FP.queries = reinterpret_cast<const float*>(base + o_q);
-        FP.ids = vs.flat_ids; FP.q_off = vs.flat_off; FP.nq = nq;
-        FP.out_dist = reinterpret_cast<float*>(base + o_fd);
-        FP.stats = nullptr;
-        tsgpu_status s = run_flat(idx, FP, total_flat);
-        if(s != TSGPU_OK) return s;
+        // Flat queries that share a candidate set (the same filter's id array) are a GEMM [ids x dim] . [dim x queries]: those
+        // groups go to the tensor-core scan (flat_tc.cu); the scalar kernel answers the rest.
+        std::vector<uint8_t> tc_skip;
+        std::vector<std::vector<uint32_t>> groups;
+        if(flat_tc_min_group() > 0 && ((vp->flags & TSGPU_VEC_FLAT_TENSOR) || flat_tc_forced()) && tsgpu_flat_tc_supported_(dim)) {
+            std::map<const uint32_t*, size_t> by_ids;
+            for(uint32_t q = 0; q < nq; q++) {
+                if(!is_flat[q] || pl.q_filter_n[q] < 128) continue;
+                auto it = by_ids.find(pl.q_filter_ids[q]);
+                if(it == by_ids.end()) { by_ids[pl.q_filter_ids[q]] = groups.size(); groups.emplace_back(1, q); }
+                else groups[it->second].push_back(q);
+            }
+            groups.erase(std::remove_if(groups.begin(), groups.end(), [](const std::vector<uint32_t>& g) { return g.size() < (size_t) flat_tc_min_group(); }), groups.end());
+        }
+        size_t skipped = 0;
+        if(!groups.empty()) {
+            tc_skip.assign(nq, 0);
+            // per group: [qsel u32 x ng | out_off u64 x ng] + the packed query tiles; one scratch buffer, laid out up front
+            std::vector<size_t> o_sel(groups.size()), o_off(groups.size()), o_img(groups.size());
+            size_t tot_tc = 0;
+            for(size_t gi = 0; gi < groups.size(); gi++) {
+                const size_t ng = groups[gi].size();
+                o_sel[gi] = tot_tc; tot_tc = (tot_tc + ng * 4 + 255) & ~size_t(255);
+                o_off[gi] = tot_tc; tot_tc = (tot_tc + ng * 8 + 1023) & ~size_t(1023);
+                o_img[gi] = tot_tc; tot_tc += tsgpu_flat_tc_image_bytes_((uint32_t) ng, dim, nullptr, nullptr);
+                tot_tc = (tot_tc + 1023) & ~size_t(1023);
+            }
+            CU(idx->d_flat_tc.reserve(tot_tc + 1024));
+            unsigned char* tb = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(idx->d_flat_tc.p) + 1023) & ~uintptr_t(1023));
+            std::vector<unsigned char>& hb = idx->flat_tc_host;
+            hb.assign(tot_tc, 0);
+            for(size_t gi = 0; gi < groups.size(); gi++) {
+                const auto& g = groups[gi];
+                for(size_t j = 0; j < g.size(); j++) {
+                    reinterpret_cast<uint32_t*>(hb.data() + o_sel[gi])[j] = g[j];
+                    reinterpret_cast<unsigned long long*>(hb.data() + o_off[gi])[j] = foff[g[j]];
+                    tc_skip[g[j]] = 1; skipped += pl.q_filter_n[g[j]];
+                }
+            }
+            // only the small index arrays travel (the image regions are written by the pack kernel)
+            for(size_t gi = 0; gi < groups.size(); gi++)
+                CU(cudaMemcpyAsync(tb + o_sel[gi], hb.data() + o_sel[gi], o_img[gi] - o_sel[gi], cudaMemcpyHostToDevice, st));
+            for(size_t gi = 0; gi < groups.size(); gi++) {
+                const auto& g = groups[gi];
+                int launches = 0;
+                CU(tsgpu_flat_tc_run_(idx->hnsw.vectors, idx->hnsw.n_nodes, dim, reinterpret_cast<const float*>(base + o_q),
+                                      reinterpret_cast<const uint32_t*>(tb + o_sel[gi]), (uint32_t) g.size(), pl.q_filter_ids[g[0]],
+                                      (uint32_t) pl.q_filter_n[g[0]], reinterpret_cast<const unsigned long long*>(tb + o_off[gi]),
+                                      reinterpret_cast<float*>(base + o_fd), tb + o_img[gi], idx->n_sms, st, &launches));
+                idx->stats.launches_total += launches;
+                idx->stats.flat_tc_queries += (uint32_t) g.size();
+            }
+        }
+        if(skipped < total_flat) {
+            tsv::FlatParams FP{};
+            FP.queries = reinterpret_cast<const float*>(base + o_q);
+            FP.ids = vs.flat_ids; FP.q_off = vs.flat_off; FP.nq = nq;
+            FP.out_dist = reinterpret_cast<float*>(base + o_fd);
+            FP.stats = nullptr;
+            if(!tc_skip.empty()) {
+                CU(cudaMemcpyAsync(base + o_sk, tc_skip.data(), nq, cudaMemcpyHostToDevice, st));
+                FP.q_skip = base + o_sk;
+            }
+            tsgpu_status s = run_flat(idx, FP, total_flat);
+            if(s != TSGPU_OK) return s;
+        }
     }
     // HNSW for the rest
     std::vector<uint32_t> nexcl(nq);
@@ -1600,6 +1680,56 @@ tsgpu_status tsgpu_flat_distances(tsgpu_index* idx, const float* query, const ui
     CU(cudaEventRecord(idx->ev[4], st));
     CU(cudaMemcpyAsync(out_dist, base + o_d, n * 4, cudaMemcpyDefault, st));
     idx->stats.d2h_bytes += n * 4;
+    return end_call(idx, false, true);
+}
+
+tsgpu_status tsgpu_flat_distances_batch(tsgpu_index* idx, const float* queries, uint32_t nq, const uint32_t* ids, size_t n, float* out_dist) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(nq && n && (!queries || !ids || !out_dist)) return fail(TSGPU_ERR_INVALID, "null argument");
+    if(!idx->has_hnsw) return fail(TSGPU_ERR_INVALID, "no vector index loaded");
+    if(n > 0xFFFFFFFFull) return fail(TSGPU_ERR_INVALID, "candidate set too large");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    begin_call(idx);
+    if(n == 0 || nq == 0) return end_call(idx, false, false);
+    cudaStream_t st = idx->stream;
+    const uint32_t dim = idx->hnsw.dim;
+    const bool tc = flat_tc_min_group() > 0 && tsgpu_flat_tc_supported_(dim);
+    // scratch: queries | q_off (nq+1 u64) | ids | (scalar path: ids repeated per query)
+    const size_t q_bytes = (size_t) nq * dim * 4;
+    const size_t o_off = (q_bytes + 255) & ~size_t(255);
+    const size_t o_ids = (o_off + (size_t) (nq + 1) * 8 + 255) & ~size_t(255);
+    const size_t n_rep = tc ? n : n * nq;
+    const size_t o_d = (o_ids + n_rep * 4 + 255) & ~size_t(255);
+    CU(idx->d_small.reserve(o_d + (size_t) nq * n * 4 + 256));
+    unsigned char* base = idx->d_small.as<unsigned char>();
+    std::vector<unsigned long long>& off = idx->tmp_foff;
+    off.resize((size_t) nq + 1);
+    for(uint32_t q = 0; q <= nq; q++) off[q] = (unsigned long long) q * n;
+    CU(cudaMemcpyAsync(base, queries, q_bytes, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(base + o_off, off.data(), (size_t) (nq + 1) * 8, cudaMemcpyHostToDevice, st));
+    for(size_t r = 0; r < (tc ? 1 : nq); r++) CU(cudaMemcpyAsync(base + o_ids + r * n * 4, ids, n * 4, cudaMemcpyDefault, st));
+    idx->stats.h2d_bytes += q_bytes + n * 4;
+    idx->vs = st;
+    CU(cudaEventRecord(idx->ev[3], st));
+    if(tc) {
+        CU(idx->d_flat_tc.reserve(tsgpu_flat_tc_image_bytes_(nq, dim, nullptr, nullptr) + 2048));
+        unsigned char* img = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(idx->d_flat_tc.p) + 1023) & ~uintptr_t(1023));
+        int launches = 0;
+        CU(tsgpu_flat_tc_run_(idx->hnsw.vectors, idx->hnsw.n_nodes, dim, reinterpret_cast<const float*>(base), nullptr, nq,
+                              reinterpret_cast<const uint32_t*>(base + o_ids), (uint32_t) n, reinterpret_cast<const unsigned long long*>(base + o_off),
+                              reinterpret_cast<float*>(base + o_d), img, idx->n_sms, st, &launches));
+        idx->stats.launches_total += launches;
+        idx->stats.flat_tc_queries += nq;
+    } else {
+        tsv::FlatParams FP{};
+        FP.queries = reinterpret_cast<const float*>(base); FP.ids = reinterpret_cast<const uint32_t*>(base + o_ids);
+        FP.q_off = reinterpret_cast<const unsigned long long*>(base + o_off); FP.nq = nq;
+        FP.out_dist = reinterpret_cast<float*>(base + o_d);
+        s = run_flat(idx, FP, (unsigned long long) nq * n); if(s) return s;
+    }
+    CU(cudaEventRecord(idx->ev[4], st));
+    CU(cudaMemcpyAsync(out_dist, base + o_d, (size_t) nq * n * 4, cudaMemcpyDefault, st));
+    idx->stats.d2h_bytes += (size_t) nq * n * 4;
     return end_call(idx, false, true);
 }
 

@@ -599,6 +599,13 @@ public:
         if(tsgpu_flat_distances(h, query_vector, ids.data(), ids.size(), dist.data()) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
         return Option<bool>(true);
     }
+    // the same loop for the requests of a multi_search that share one filter result: dist[q * ids.size() + i] (tensor-core scan)
+    Option<bool> flat_distances_batch(const float* query_vectors, uint32_t nq, const std::vector<uint32_t>& ids, std::vector<float>& dist) {
+        dist.assign((size_t) nq * ids.size(), 0.f);
+        if(ids.empty() || nq == 0) return Option<bool>(true);
+        if(tsgpu_flat_distances_batch(h, query_vectors, nq, ids.data(), ids.size(), dist.data()) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
+        return Option<bool>(true);
+    }
 
     // One Index::search_all_candidates call's worth of input (one "query" of tsgpu_kw_batch) and its answer.
     struct kw_query {
@@ -1404,7 +1411,7 @@ public:
         int32_t filter_handle = -1;
         const float* query_vector = nullptr;     // nullptr: keyword only
         size_t hits = 0;                         // results the caller will read (0: the whole Topster); bounds what the hybrid tail copies back
-        tsgpu_vec_params vp{0, 10, 0, 3.4028234663852886e38f, 0.3f, 10};
+        tsgpu_vec_params vp{0, 10, 0, 3.4028234663852886e38f, 0.3f, 10, 0};
     };
     struct batched_stats { size_t passes = 0, kw_batches = 0, kw_queries = 0, walk_batches = 0, walks = 0, host_walk_fallbacks = 0, fuse_queries = 0;
                            double ms_host_passes = 0, ms_kw_calls = 0, ms_walk_calls = 0, ms_fuse_calls = 0; };

@@ -79,7 +79,7 @@ int tshost_multi_search(void* h, const char* field, const char* sort_field, uint
         reqs[i].hits = stride;
         if(qvecs) {
             reqs[i].query_vector = qvecs + (size_t) i * dim;
-            reqs[i].vp = tsgpu_vec_params{o->vec_k, o->vec_ef, o->vec_flat_search_cutoff, o->vec_distance_threshold, o->vec_alpha, o->vec_fetch_size};
+            reqs[i].vp = tsgpu_vec_params{o->vec_k, o->vec_ef, o->vec_flat_search_cutoff, o->vec_distance_threshold, o->vec_alpha, o->vec_fetch_size, 0u};
         }
     }
     Ix::batched_stats bs;

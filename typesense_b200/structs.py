@@ -58,7 +58,7 @@ class HnswStruct(C.Structure):
 
 class VecParamsStruct(C.Structure):
     _fields_ = [("k", C.c_uint32), ("ef", C.c_uint32), ("flat_search_cutoff", C.c_uint32),
-                ("distance_threshold", C.c_float), ("alpha", C.c_float), ("fetch_size", C.c_uint32)]
+                ("distance_threshold", C.c_float), ("alpha", C.c_float), ("fetch_size", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class ArtStruct(C.Structure):
@@ -76,7 +76,7 @@ class StatsStruct(C.Structure):
                 ("knn_expanded", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("ms_kw_search", C.c_float), ("ms_kw_merge", C.c_float), ("ms_host_plan", C.c_float), ("knn_spec_hits", C.c_uint64),
                 ("knn_tier2_walks", C.c_uint64), ("knn_retried", C.c_uint64), ("h2d_total", C.c_uint64), ("d2h_total", C.c_uint64),
-                ("calls_total", C.c_uint64), ("knn_table_probes", C.c_uint64)]
+                ("calls_total", C.c_uint64), ("knn_table_probes", C.c_uint64), ("flat_tc_queries", C.c_uint64)]
 
 
 def _ptr(a: Optional[np.ndarray], typ):
@@ -300,8 +300,12 @@ class HnswGraph:
         return s
 
 
-def vec_params(k=0, ef=10, flat_search_cutoff=0, distance_threshold=3.4028234663852886e38, alpha=0.3, fetch_size=10):
+VEC_FLAT_TENSOR = 1
+
+
+def vec_params(k=0, ef=10, flat_search_cutoff=0, distance_threshold=3.4028234663852886e38, alpha=0.3, fetch_size=10, flags=0):
     s = VecParamsStruct()
+    s.flags = flags
     s.k, s.ef, s.flat_search_cutoff = k, ef, flat_search_cutoff
     s.distance_threshold, s.alpha, s.fetch_size = distance_threshold, alpha, fetch_size
     return s
