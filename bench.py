@@ -447,6 +447,35 @@ def other_configs(args, w, hi, gi, sl, qv_pin, host_opt, hbm_peak):
                                      "roofline_frac": algo / (st["ms_knn"] * 1e-3) / 1e9 / hbm_peak if st["ms_knn"] > 0 else None}
     except Exception as e:
         out["hnsw_knn_batch1024"] = {"error": str(e)[:200]}
+    try:        # K7: the flat scan (process_results_bruteforce) of the queries of a batch that share one filter, on the tensor cores
+        nqf = min(256, qv_pin[0].shape[0])
+        ids = np.ascontiguousarray(w.filters[0][:200000])
+        qf_ = qv_pin[0].numpy()[:nqf]
+        gi.flat_distances_batch(qf_[:16], ids[:1024])
+        ts = []
+        for _ in range(3):
+            dtc = gi.flat_distances_batch(qf_, ids)
+            ts.append(gi.stats()["ms_knn"])
+        tc_q = gi.stats()["flat_tc_queries"]
+        d0 = gi.flat_distances(qf_[0], ids[:8192])                 # the fp32 pair-by-pair kernel (bit-equal to the CPU loop)
+        ms = min(ts)
+        flops = 2.0 * nqf * len(ids) * w.dim
+        tf32_peak = None
+        try:
+            tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2
+        except Exception:
+            pass
+        out["flat_scan_tensor"] = {"queries": nqf, "candidates": int(len(ids)), "dim": w.dim, "kernel_ms": ms, "tensor_core_queries": int(tc_q),
+                                   "fp32_equivalent_tflops": flops / (ms * 1e-3) / 1e12 if ms > 0 else None,
+                                   "tf32_mma_tflops": 3 * flops / (ms * 1e-3) / 1e12 if ms > 0 else None,
+                                   "roofline": {"bound": "tensor", "achieved": 3 * flops / (ms * 1e-3) / 1e12 if ms > 0 else None, "peak": tf32_peak, "unit": "TFLOP/s",
+                                                "frac": (3 * flops / (ms * 1e-3) / 1e12 / tf32_peak) if (ms > 0 and tf32_peak) else None,
+                                                "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32 runs at half the bf16 rate); 3 tf32 MMAs per fp32 product"},
+                                   "rows_gbs": len(ids) * w.dim * 4 / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                                   "max_abs_dev_vs_fp32_kernel": float(np.abs(dtc[0, :len(d0)] - d0).max()),
+                                   "path": "tsgpu_flat_distances_batch: tcgen05 kind::tf32, 3-term split (csrc/flat_tc.cu); kernel time only, outputs copied to the host outside it"}
+    except Exception as e:
+        out["flat_scan_tensor"] = {"error": str(e)[:200]}
     try:        # configs[4]-shaped: facets over all_result_ids
         n_values = 50000
         rng = np.random.default_rng(99)

@@ -32,9 +32,9 @@ dev768 = max((r["max_abs"] for r in rows if r["dim"] == 768), default=None)
 out = {"cases": rows, "tensor_pipe_pct": pipe, "perf": perf, "ncu_file": os.path.basename(sys.argv[2]) if len(sys.argv) > 2 else None,
        "deviation": f"largest deviation from a double-precision dot over all cases of the check: {max(r['max_abs'] for r in rows):.2g} absolute ({dev768:.2g} at d = 768)",
        "hbm_peak_gbs": peaks.get("hbm_gbs"), "bf16_peak_tflops": peaks.get("bf16_tflops"),
-       "note": "tf32 dense peak is nominally half the bf16 one (B200_PROFILING.md: 1.1 PFLOP/s); tensor roofline frac of the 256-query case = 3 x fp32-equivalent TFLOP/s / 1100"}
+       "note": "tf32 dense peak is nominally half the bf16 one (B200_PROFILING.md: 1.1 PFLOP/s); tensor roofline frac of the 256-query case = 3 x fp32-equivalent TFLOP/s / (MEASURED_PEAKS bf16_tflops / 2)"}
 if 256 in best:
-    out["tensor_roofline_frac_256q"] = round(3 * best[256]["tflops_fp32_equiv"] / 1100.0, 3)
+    out["tensor_roofline_frac_256q"] = round(3 * best[256]["tflops_fp32_equiv"] / ((peaks.get("bf16_tflops") or 2200.0) / 2), 3)
 if 16 in best and peaks.get("hbm_gbs"):
     out["hbm_roofline_frac_16q"] = round(best[16]["rows_gbs"] / peaks["hbm_gbs"], 3)
 json.dump(out, open(os.path.join(ROOT, "profiles", "flat_tc.json"), "w"), indent=1)
