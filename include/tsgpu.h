@@ -151,6 +151,16 @@ void         tsgpu_index_destroy(tsgpu_index* idx);
 tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint32_t* out_field);
 /* Mirror sort_index[field] (include/index.h:442-447): dense [n_docs], INT64_MIN where the doc has no value. */
 tsgpu_status tsgpu_index_load_sort_column(tsgpu_index* idx, const int64_t* vals, uint32_t* out_col);
+/* SURVEY 8 f-4 (posting half): the device side of posting_t::upsert / posting_t::erase (src/posting.cpp:247-333; callers
+ * Index::index_field_in_memory src/index.cpp:1290-1400, Index::remove_field src/index.cpp:7295-7420). After a batch of writes the
+ * binding hands over, in the form of tsgpu_index_load_field, the CURRENT full posting list of every token the batch touched (new
+ * tokens included; an erased token = an empty list); they become lists *out_first_list .. *out_first_list + n_lists - 1 of `field`
+ * and the caller points those tokens at the new ids. The lists they replace stay in HBM, unreferenced, until the field is loaded
+ * again (the read-optimised layout has no holes to patch in place). seq_ids must stay below the n_docs the index was created with
+ * (create it with headroom). Searches on other threads wait on the index lock for the duration of the call. */
+tsgpu_status tsgpu_index_append_lists(tsgpu_index* idx, uint32_t field, const tsgpu_field* f, uint32_t* out_first_list);
+/* sort_index values of upserted / removed documents: column[ids[i]] = vals[i] (INT64_MIN = no value). */
+tsgpu_status tsgpu_index_set_sort_values(tsgpu_index* idx, uint32_t sort_col, const uint32_t* ids, const int64_t* vals, size_t n);
 /* Mirror hnsw_index_t (vectors + graph). Pointers may be host or device memory. */
 tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g);
 /* Build the vector index ON THE DEVICE: hnswlib's addPoint (the loop of Index::batch_memory_index, src/index.cpp:1003-1054,

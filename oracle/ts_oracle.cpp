@@ -935,6 +935,7 @@ int tso_has_phrase_match(uint32_t n_tokens, const uint32_t* tok_off, const uint1
 void* tso_index_new(uint32_t n_docs) { auto* ix = new Index(); ix->n_docs = n_docs; return ix; }
 void tso_index_free(void* idx) { delete (Index*) idx; }
 int tso_index_add_field(void* idx, const tso_field* f) { auto* ix = (Index*) idx; ix->fields.push_back(*f); return (int) ix->fields.size() - 1; }
+void tso_index_set_field(void* idx, int field, const tso_field* f) { auto* ix = (Index*) idx; ix->fields[(size_t) field] = *f; }
 int tso_index_add_sort_column(void* idx, const int64_t* vals) { auto* ix = (Index*) idx; ix->sort_cols.push_back(vals); return (int) ix->sort_cols.size() - 1; }
 void tso_index_set_hnsw(void* idx, const tso_hnsw* g) { auto* ix = (Index*) idx; ix->hnsw = *g; ix->has_hnsw = true; }
 

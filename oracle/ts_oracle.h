@@ -126,6 +126,7 @@ int tso_has_phrase_match(uint32_t n_tokens, const uint32_t* tok_off, const uint1
 void* tso_index_new(uint32_t n_docs);
 void  tso_index_free(void* idx);
 int   tso_index_add_field(void* idx, const tso_field* f);                    /* returns field id */
+void  tso_index_set_field(void* idx, int field, const tso_field* f);          /* the field's arrays were replaced (incremental mirror tests) */
 int   tso_index_add_sort_column(void* idx, const int64_t* vals);             /* [n_docs], INT64_MIN = missing */
 void  tso_index_set_hnsw(void* idx, const tso_hnsw* g);
 

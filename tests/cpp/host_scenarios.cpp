@@ -750,6 +750,62 @@ static void filter_scenarios() {
     CHECK(!tsgpu::parse_string_filter("tags", "=", exp).ok());        // "Filter value cannot be empty." (FilterOnTextFields :139)
 }
 
+// documents added, updated and removed after the mirror was loaded (Index::update_field -> tsgpu_index_append_lists):
+// the patched index answers like one built from the final documents — exact tokens, prefixes, typo candidates (the ART mirror is
+// rebuilt from the patched vocabulary) and the default sorting field of the new documents.
+static void incremental_scenarios() {
+    const std::vector<tsgpu::sort_by> sort_fields = {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::numeric, "points", true}};
+    std::vector<std::string> titles = {"The quick brown fox", "Rocket launch delayed by weather", "Brown bears of the north", "A rocket science primer",
+                                       "Launch day for the new rover", "Quick guide to foxes"};
+    const uint32_t capacity = 16;
+    tsgpu::Index index(capacity);
+    tsgpu::field_mirror_t m;
+    for(uint32_t i = 0; i < titles.size(); i++) m.index_plain_string(i, tsgpu::tokenize_ascii(titles[i]));
+    CHECK(index.add_field("title", m).ok());
+    m.take_delta();
+    std::unordered_map<uint32_t, int64_t> points;
+    for(uint32_t i = 0; i < titles.size(); i++) points[i] = 100 - i;
+    CHECK(index.add_sort_field("points", points).ok());
+    std::vector<tsgpu::KV> kvs;
+    size_t found = 0;
+    CHECK(index.search(tsgpu::tokenize_ascii("rocket"), {"title"}, sort_fields, 10, 250, kvs, found, opt(2, true)).ok());
+    CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 3}) && found == 2);
+    // one batch of writes: four new documents, document 2 rewritten, document 4 removed
+    titles.push_back("Rocket fuel and brown sugar");          // 6
+    titles.push_back("Foxes launch a quick rocket");          // 7
+    titles.push_back("Northern lights guide");                // 8
+    titles.push_back("Rover lands after long launch");        // 9
+    for(uint32_t i = 6; i < 10; i++) m.index_plain_string(i, tsgpu::tokenize_ascii(titles[i]));
+    titles[2] = "Rocket bears of the north";
+    m.remove(2); m.index_plain_string(2, tsgpu::tokenize_ascii(titles[2]));
+    m.remove(4);
+    CHECK(index.update_field("title", m.take_delta()).ok());
+    CHECK(index.set_sort_values("points", {6, 7, 8, 9, 4}, {94, 93, 92, 91, INT64_MIN}).ok());
+    // the same final state, loaded at once
+    tsgpu::Index fresh(capacity);
+    tsgpu::field_mirror_t mf;
+    std::unordered_map<uint32_t, int64_t> pf;
+    for(uint32_t i = 0; i < titles.size(); i++) if(i != 4) { mf.index_plain_string(i, tsgpu::tokenize_ascii(titles[i])); pf[i] = 100 - i; }
+    CHECK(fresh.add_field("title", mf).ok());
+    CHECK(fresh.add_sort_field("points", pf).ok());
+    CHECK(index.search(tsgpu::tokenize_ascii("rocket"), {"title"}, sort_fields, 10, 250, kvs, found, opt(2, true)).ok());
+    CHECK((keys_of(kvs) == std::vector<uint32_t>{1, 2, 3, 6, 7}) && found == 5);          // equal text scores: points descending
+    for(const char* q: {"rocket", "launch", "brown", "quick rocket", "rocket launch", "bears", "rover", "north", "lau", "rokcet", "foxs", "luanch day", "guide", "the"}) {
+        std::vector<tsgpu::KV> a, b;
+        size_t fa = 0, fb = 0;
+        const bool prefix = std::strlen(q) <= 3;
+        CHECK(index.search(tsgpu::tokenize_ascii(q), {"title"}, sort_fields, 1, 250, a, fa, opt(2, prefix)).ok());
+        CHECK(fresh.search(tsgpu::tokenize_ascii(q), {"title"}, sort_fields, 1, 250, b, fb, opt(2, prefix)).ok());
+        CHECK(fa == fb && keys_of(a) == keys_of(b));
+        if(!(fa == fb && keys_of(a) == keys_of(b))) printf("  incremental scenario: query '%s' differs (%zu vs %zu hits)\n", q, fa, fb);
+        for(size_t i = 0; i < a.size() && i < b.size(); i++) CHECK(a[i].scores[0] == b[i].scores[0] && a[i].scores[1] == b[i].scores[1]);
+        for(auto& kv: a) CHECK(kv.key != 4);                                       // the removed document is gone
+    }
+    // a removed token leaves the vocabulary: "day" only lived in document 4
+    CHECK(index.search(tsgpu::tokenize_ascii("day"), {"title"}, sort_fields, 0, 250, kvs, found, opt(0, false)).ok());
+    CHECK(found == 0 && kvs.empty());
+}
+
 int main(int argc, char** argv) {
     if(tsgpu_device_count() == 0) { printf("no CUDA device: nothing to run (the library has no CPU path)\n"); return 99; }
     posting_list_intersection_basics();
@@ -763,6 +819,7 @@ int main(int argc, char** argv) {
     phrase_scenarios();
     synonym_scenarios();
     filter_scenarios();
+    incremental_scenarios();
     {
         const auto& ws = tsgpu::Index::art_walk_stats();
         if(getenv("TSGPU_HOST_DEVICE_ART")) {

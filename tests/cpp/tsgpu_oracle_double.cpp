@@ -117,6 +117,31 @@ tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint
     if(out_field) *out_field = (uint32_t) id;
     return TSGPU_OK;
 }
+tsgpu_status tsgpu_index_append_lists(tsgpu_index* idx, uint32_t field, const tsgpu_field* f, uint32_t* out_first_list) {
+    Double* d = D(idx);
+    if(field >= d->fields.size()) { g_err = "no such field"; return TSGPU_ERR_INVALID; }
+    FieldCopy* c = d->fields[field];
+    const uint32_t L0 = c->view.n_lists;
+    if(out_first_list) *out_first_list = L0;
+    const uint64_t n_post0 = c->list_off[L0], n_pos0 = c->pos_off[n_post0], np = f->list_off[f->n_lists], npos = f->pos_off[np];
+    c->ids.resize(n_post0); c->positions.resize(n_pos0);           // drop the placeholders of an empty field
+    for(uint32_t l = 1; l <= f->n_lists; l++) c->list_off.push_back(n_post0 + f->list_off[l]);
+    c->ids.insert(c->ids.end(), f->ids, f->ids + np);
+    for(uint64_t i = 1; i <= np; i++) c->pos_off.push_back(n_pos0 + f->pos_off[i]);
+    c->positions.insert(c->positions.end(), f->positions, f->positions + npos);
+    if(c->ids.empty()) c->ids.push_back(0);
+    if(c->positions.empty()) c->positions.push_back(0);
+    c->view.n_lists = L0 + f->n_lists;
+    c->view.list_off = c->list_off.data(); c->view.ids = c->ids.data(); c->view.pos_off = c->pos_off.data(); c->view.positions = c->positions.data();
+    tso_index_set_field(d->oi, (int) field, &c->view);
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_index_set_sort_values(tsgpu_index* idx, uint32_t sort_col, const uint32_t* ids, const int64_t* vals, size_t n) {
+    Double* d = D(idx);
+    if(sort_col >= d->cols.size()) { g_err = "no such sort column"; return TSGPU_ERR_INVALID; }
+    for(size_t i = 0; i < n; i++) (*d->cols[sort_col])[ids[i]] = vals[i];
+    return TSGPU_OK;
+}
 tsgpu_status tsgpu_index_load_sort_column(tsgpu_index* idx, const int64_t* vals, uint32_t* out_col) {
     Double* d = D(idx);
     auto* c = new std::vector<int64_t>(vals, vals + d->n_docs);

@@ -19,6 +19,7 @@ GPU_ONLY = [
     "tests/test_facets.py::test_gpu_all_result_ids_and_facets_of_a_search_batch",  # all_result_ids live in device memory
     "tests/test_gpu_parity.py::test_knn_selective_filters_long_walks",            # builds its graph on the device, asserts device counters
     "tests/test_gpu_parity.py::test_hnsw_load_rejects_malformed_graph_and_keeps_the_old_one",   # asserts the library's load-time validation
+    "tests/test_incremental_mirror.py::test_append_lists_rejects_malformed_input",              # asserts the library's argument validation
 ]
 
 

@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("TSGPU_LIB_PATH") or os.path.join(HERE, "libtsgpu.so")
 
 EXPORTS = [
     "tsgpu_last_error", "tsgpu_device_count", "tsgpu_index_create", "tsgpu_index_destroy", "tsgpu_index_load_field",
-    "tsgpu_index_load_sort_column", "tsgpu_index_load_hnsw", "tsgpu_index_build_hnsw", "tsgpu_index_append_hnsw", "tsgpu_index_mark_deleted", "tsgpu_index_hnsw_info", "tsgpu_index_export_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy", "tsgpu_filter_numeric", "tsgpu_filter_combine", "tsgpu_filter_ids", "tsgpu_scored_ids_search_batch",
+    "tsgpu_index_load_sort_column", "tsgpu_index_append_lists", "tsgpu_index_set_sort_values", "tsgpu_index_load_hnsw", "tsgpu_index_build_hnsw", "tsgpu_index_append_hnsw", "tsgpu_index_mark_deleted", "tsgpu_index_hnsw_info", "tsgpu_index_export_hnsw", "tsgpu_filter_create", "tsgpu_filter_destroy", "tsgpu_filter_numeric", "tsgpu_filter_combine", "tsgpu_filter_ids", "tsgpu_scored_ids_search_batch",
     "tsgpu_intersect", "tsgpu_contains_atleast_one", "tsgpu_phrase_matches", "tsgpu_exact_matches", "tsgpu_prefix_matches", "tsgpu_ids_setop", "tsgpu_keyword_search_batch", "tsgpu_wildcard_search_batch", "tsgpu_knn_batch", "tsgpu_flat_distances", "tsgpu_flat_distances_batch",
     "tsgpu_vector_search_batch", "tsgpu_hybrid_search_batch", "tsgpu_get_stats", "tsgpu_debug_knn_work", "tsgpu_comm_unique_id", "tsgpu_comm_init", "tsgpu_comm_destroy", "tsgpu_comm_gather", "tsgpu_comm_last_ms", "tsgpu_hybrid_fuse_batch", "tsgpu_index_load_facet", "tsgpu_facet_counts", "tsgpu_facet_counts_last", "tsgpu_all_result_ids_last", "tsgpu_index_load_art", "tsgpu_art_walk_batch",
 ]
@@ -56,6 +56,8 @@ def declare(L):
         L.tsgpu_index_destroy.argtypes = [vp]
         L.tsgpu_index_load_field.argtypes = [vp, C.POINTER(FieldStruct), u32p]
         L.tsgpu_index_load_sort_column.argtypes = [vp, C.c_void_p, u32p]
+        L.tsgpu_index_append_lists.argtypes = [vp, C.c_uint32, C.POINTER(FieldStruct), u32p]
+        L.tsgpu_index_set_sort_values.argtypes = [vp, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]
         L.tsgpu_index_load_hnsw.argtypes = [vp, C.POINTER(HnswStruct)]
         L.tsgpu_index_build_hnsw.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
         L.tsgpu_index_append_hnsw.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -155,6 +157,18 @@ class GpuIndex:
         out = C.c_uint32(0)
         _ck(self.L.tsgpu_index_load_field(self.h, C.byref(s), C.byref(out)))
         return out.value
+
+    def append_lists(self, field: int, f: FlatField) -> int:
+        """tsgpu_index_append_lists (f-4): the current full lists of the tokens a batch of writes touched; returns the first new list id."""
+        s = f.struct()
+        out = C.c_uint32(0)
+        _ck(self.L.tsgpu_index_append_lists(self.h, field, C.byref(s), C.byref(out)))
+        return out.value
+
+    def set_sort_values(self, col: int, ids, vals):
+        ids = np.ascontiguousarray(ids, np.uint32)
+        vals = np.ascontiguousarray(vals, np.int64)
+        _ck(self.L.tsgpu_index_set_sort_values(self.h, col, ids.ctypes.data, vals.ctypes.data, len(ids)))
 
     def load_field_raw(self, n_lists: int, is_array: bool, list_off, ids, pos_off, positions) -> int:
         """Pointers may be torch CUDA tensors (device-resident synthetic data)."""

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -96,20 +98,39 @@ __global__ void __launch_bounds__(128)
 art_frontier_kernel(const ArtDev A, const ArtQuery* __restrict__ queries, const ArtWorkItem* __restrict__ in, uint32_t n_in,
                     ArtWorkItem* __restrict__ out, uint32_t out_cap, uint32_t* __restrict__ counters /* 0 next items, 1 hits, 2 overflow */,
                     Hit* __restrict__ hits, uint32_t hit_cap) {
+    // One slot allocation per WARP and level (prefix sum of the lanes' child counts, one atomicAdd by the last lane): the per-item
+    // atomicAdd on one counter was the kernel's bound — millions of same-address atomics per level.
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= n_in) return;
-    ArtWorkItem w = in[i];
-    const ArtQuery& Q = queries[w.search];
-    bool hit = false;
-    const bool descend = art_enter_fast(A, Q, w.at, &hit);
-    if(hit) {
-        const uint32_t pos = atomicAdd(counters + 1, 1u);
-        if(pos < hit_cap) hits[pos] = Hit{w.search, w.at.ref}; else atomicOr(counters + 2, 1u);
+    const uint32_t lane = threadIdx.x & 31;
+    const bool active = i < n_in;
+    ArtWorkItem w;
+    bool hit = false, descend = false;
+    if(active) {
+        w = in[i];
+        descend = art_enter_fast(A, queries[w.search], w.at, &hit);
     }
+    const uint32_t hit_mask = __ballot_sync(0xffffffffu, hit);
+    if(hit_mask) {
+        uint32_t hbase = 0;
+        if(lane == 0) hbase = atomicAdd(counters + 1, (uint32_t) __popc(hit_mask));
+        hbase = __shfl_sync(0xffffffffu, hbase, 0);
+        if(hit) {
+            const uint32_t pos = hbase + __popc(hit_mask & ((1u << lane) - 1u));
+            if(pos < hit_cap) hits[pos] = Hit{w.search, w.at.ref}; else atomicOr(counters + 2, 1u);
+        }
+    }
+    const uint32_t nch = descend ? A.nodes[w.at.ref].n_children : 0u;
+    uint32_t incl = nch;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if((int) lane >= o) incl += t; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if(total == 0) return;
+    uint32_t wbase = 0;
+    if(lane == 31) wbase = atomicAdd(counters + 0, total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    if(wbase + total > out_cap) { if(lane == 0) atomicOr(counters + 2, 2u); return; }
     if(descend) {
-        const uint32_t nch = A.nodes[w.at.ref].n_children;
-        const uint32_t base = atomicAdd(counters + 0, nch);
-        if(base + nch > out_cap) { atomicOr(counters + 2, 2u); return; }
+        const uint32_t base = wbase + incl - nch;
         const uint32_t first = A.nodes[w.at.ref].first_child;
         w.at.p = w.at.c;                          // art_child_item(): a child is its parent's state + the byte and link that lead to it
         for(uint32_t k = 0; k < nch; k++) {
@@ -290,6 +311,10 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
             for(size_t b0 = 0; b0 < heavy.size(); b0 += chunk2) work.emplace_back(heavy.begin() + b0, heavy.begin() + std::min(heavy.size(), b0 + chunk2));
             for(size_t b0 = 0; b0 < light.size(); b0 += chunk) work.emplace_back(light.begin() + b0, light.begin() + std::min(light.size(), b0 + chunk));
         }
+        static const bool art_timing = getenv("TSGPU_ART_TIMING") != nullptr;
+        const auto t_begin = std::chrono::steady_clock::now();
+        double ms_levels = 0, ms_sort = 0;
+        size_t n_levels = 0, n_chunks = 0, n_hits_total = 0;
         while(!work.empty()) {
             std::vector<uint32_t> ids = std::move(work.back());
             work.pop_back();
@@ -302,7 +327,10 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
             uint32_t n_cur = (uint32_t) ids.size(), h_cnt[4] = {0, 0, 0, 0};
             int cur = 0;
             bool overflow = false;
+            const auto t_lv = std::chrono::steady_clock::now();
+            n_chunks++;
             for(int level = 0; n_cur && level < 256; level++) {
+                n_levels++;
                 CUA(cudaMemsetAsync(d_cnt, 0, 4, st));                    // next-frontier counter only: hits accumulate over the levels
                 art_frontier_kernel<<<(n_cur + 127) / 128, 128, 0, st>>>(A, (const ArtQuery*) (d + o_q), bufs[cur], n_cur, bufs[cur ^ 1], item_cap, d_cnt,
                                                                          (Hit*) (d + o_hits), hit_cap);
@@ -313,6 +341,7 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
                 n_cur = h_cnt[0];
                 cur ^= 1;
             }
+            ms_levels += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_lv).count();
             if(overflow || n_cur) {
                 if(ids.size() > 1) {                                  // too many items for the buffers: two half chunks
                     const size_t half = ids.size() / 2;
@@ -321,6 +350,8 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
                 } else flags[ids[0]] = 4;                             // the host walks this search
                 continue;
             }
+            const auto t_so = std::chrono::steady_clock::now();
+            n_hits_total += h_cnt[1];
             h_hits.resize(h_cnt[1]);
             if(h_cnt[1]) CUA(cudaMemcpyAsync(h_hits.data(), d + o_hits, (size_t) h_cnt[1] * sizeof(Hit), cudaMemcpyDeviceToHost, st));
             CUA(cudaStreamSynchronize(st));
@@ -331,7 +362,11 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
                 c++;
             }
             for(uint32_t i: ids) if(counts[i] > cap) flags[i] = 4;
+            ms_sort += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_so).count();
         }
+        if(art_timing)
+            fprintf(stderr, "[tsgpu art] %u searches: %.2f ms in %zu chunks / %zu levels (launch + sync per level), %.2f ms hit copy + sort (%zu hits), %.2f ms before the copies out\n",
+                    n, ms_levels, n_chunks, n_levels, ms_sort, n_hits_total, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
         CUA(cudaMemcpy(out_counts, counts.data(), (size_t) n * 4, cudaMemcpyDefault));
         CUA(cudaMemcpy(out_flags, flags.data(), n, cudaMemcpyDefault));
         CUA(cudaMemcpy(out_hits, out.data(), (size_t) n * cap * 4, cudaMemcpyDefault));

@@ -103,6 +103,10 @@ struct FieldMirror {
     std::vector<uint32_t> h_list_blk_off;
     std::vector<uint32_t> h_list_dense;
     void* d_alloc[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // element counts of the device arrays (tsgpu_index_append_lists grows them)
+    uint64_t n_post = 0, n_pos = 0, n_words = 0;      // postings, raw offsets, packed words (without the padding word)
+    uint32_t n_blocks = 0, n_dense = 0;
+    uint64_t dense_min_df = 0;
 };
 
 struct Filter {
@@ -1146,9 +1150,135 @@ tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint
     fm.dev.dense_bits = (const uint32_t*) fm.d_alloc[8];
     fm.dev.dense_rank = (const uint32_t*) fm.d_alloc[9];
     fm.dev.dense_words = pk.dense_words; fm.dev.dense_groups = pk.dense_groups;
+    fm.n_post = n_post; fm.n_pos = n_pos; fm.n_words = pk.packed.size() - 1; fm.n_blocks = (uint32_t) pk.blk_first.size(); fm.n_dense = pk.n_dense;
+    fm.dense_min_df = std::max<uint64_t>(64, idx->n_docs / (uint64_t) std::max(1, getenv("TSGPU_DENSE_DIV") ? atoi(getenv("TSGPU_DENSE_DIV")) : 64));
     idx->ixdev.fields[idx->fields.size()] = fm.dev;
     *out_field = (uint32_t) idx->fields.size();
     idx->fields.push_back(std::move(fm));
+    return TSGPU_OK;
+}
+
+// SURVEY 8 f-4 (posting half). posting_t::upsert / erase (src/posting.cpp:247-333) change a token's list in place on the host; the
+// device layout is read-optimised (CSR + packed blocks), so a changed list is WRITTEN AGAIN at the end of the field's arrays and the
+// token is pointed at the new list id; the old list stays behind as garbage until the field is reloaded. Every array grows by
+// reallocation + device-to-device copy (O(field size) per call at HBM speed: batch the writes, as batch_memory_index does).
+tsgpu_status tsgpu_index_append_lists(tsgpu_index* idx, uint32_t field, const tsgpu_field* f, uint32_t* out_first_list) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(!f || !out_first_list) return fail(TSGPU_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if(field >= idx->fields.size()) return fail(TSGPU_ERR_INVALID, "no such field");
+    FieldMirror& fm = idx->fields[field];
+    const bool was_array = (fm.dev.is_array & tsdev::kFieldIsArray) != 0;
+    if((f->is_array != 0) != was_array) return fail(TSGPU_ERR_INVALID, "is_array differs from the loaded field");
+    const uint32_t L0 = fm.dev.n_lists, Ln = f->n_lists;
+    *out_first_list = L0;
+    if(Ln == 0) return TSGPU_OK;
+    if((uint64_t) L0 + Ln >= 0xFFFFFFFEull) return fail(TSGPU_ERR_CAPACITY, "too many lists");
+    std::vector<uint64_t> lo((size_t) Ln + 1);
+    CU(cudaMemcpy(lo.data(), f->list_off, ((size_t) Ln + 1) * 8, cudaMemcpyDefault));
+    if(lo[0] != 0) return fail(TSGPU_ERR_INVALID, "list_off[0] must be 0");
+    for(uint32_t l = 0; l < Ln; l++) if(lo[l + 1] < lo[l]) return fail(TSGPU_ERR_INVALID, "list_off not monotone");
+    const uint64_t np = lo[Ln];
+    std::vector<uint32_t> ids(np ? np : 1);
+    if(np) CU(cudaMemcpy(ids.data(), f->ids, np * 4, cudaMemcpyDefault));
+    for(uint32_t l = 0; l < Ln; l++)
+        for(uint64_t i = lo[l]; i < lo[l + 1]; i++) {
+            if(ids[i] >= idx->n_docs) return fail(TSGPU_ERR_INVALID, "seq_id >= n_docs in a posting list");
+            if(i > lo[l] && ids[i] <= ids[i - 1]) return fail(TSGPU_ERR_INVALID, "posting list ids must be strictly ascending");
+        }
+    std::vector<uint64_t> po(np + 1);
+    CU(cudaMemcpy(po.data(), f->pos_off, (np + 1) * 8, cudaMemcpyDefault));
+    if(po[0] != 0) return fail(TSGPU_ERR_INVALID, "pos_off[0] must be 0");
+    for(uint64_t i = 0; i < np; i++) if(po[i + 1] < po[i]) return fail(TSGPU_ERR_INVALID, "pos_off not monotone");
+    const uint64_t npos = po[np];
+    std::vector<uint32_t> pos(npos ? npos : 1);
+    if(npos) CU(cudaMemcpy(pos.data(), f->positions, npos * 4, cudaMemcpyDefault));
+    // the fast scoring paths hold only while every posting of the field qualifies
+    uint32_t flags = fm.dev.is_array;
+    if(!was_array && (flags & tsdev::kFieldPlainOk)) {
+        if(!tspack::plain_wellformed(po.data(), pos.data(), np)) flags &= ~(tsdev::kFieldPlainOk | tsdev::kFieldPos16);
+        else if((flags & tsdev::kFieldPos16) && !tspack::positions_fit_u16(pos.data(), npos)) flags &= ~tsdev::kFieldPos16;
+    }
+    tspack::PackedField pk;
+    tspack::pack_field(Ln, lo.data(), ids.data(), pk);
+    tspack::pack_dense(Ln, lo.data(), ids.data(), idx->n_docs, fm.dense_min_df, pk);
+    const uint64_t nw_new = pk.packed.size() - 1;
+    const uint32_t nb_new = (uint32_t) pk.blk_first.size();
+    if((uint64_t) fm.n_blocks + nb_new >= 0xFFFFFFFFull) return fail(TSGPU_ERR_CAPACITY, "too many posting blocks");
+    // rebase the new lists' offsets onto the end of the existing arrays
+    for(auto& v: lo) v += fm.n_post;
+    for(auto& v: po) v += fm.n_pos;
+    for(auto& v: pk.list_blk_off) v += fm.n_blocks;
+    for(auto& v: pk.blk_info) v = ((v & 0xFFFFFFFFFFull) + fm.n_words) | (v & ~0xFFFFFFFFFFull);
+    for(auto& v: pk.list_dense) if(v != tsdev::kNone) v += fm.n_dense;
+    if(fm.n_words + nw_new >= (1ull << 40)) return fail(TSGPU_ERR_CAPACITY, "packed postings exceed the 40-bit word offset");
+    // grow: [old | new] into fresh allocations, swap on success
+    void* fresh[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    struct Guard { void** v; bool keep = false; ~Guard() { if(!keep) for(int i = 0; i < 10; i++) if(v[i]) cudaFree(v[i]); } } guard{fresh};
+    auto grow = [&](int slot, size_t old_bytes, const void* add, size_t add_bytes, size_t tail_zero_bytes) -> cudaError_t {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, old_bytes + add_bytes + tail_zero_bytes + 16);
+        if(e != cudaSuccess) return e;
+        fresh[slot] = d;
+        if(old_bytes) { e = cudaMemcpy(d, fm.d_alloc[slot], old_bytes, cudaMemcpyDeviceToDevice); if(e != cudaSuccess) return e; }
+        if(add_bytes) { e = cudaMemcpy((char*) d + old_bytes, add, add_bytes, cudaMemcpyHostToDevice); if(e != cudaSuccess) return e; }
+        if(tail_zero_bytes) e = cudaMemset((char*) d + old_bytes + add_bytes, 0, tail_zero_bytes);
+        return e;
+    };
+    const size_t dw = fm.dev.dense_words, dg = fm.dev.dense_groups;
+    CU(grow(0, ((size_t) L0 + 1) * 8, lo.data() + 1, (size_t) Ln * 8, 0));
+    CU(grow(1, ((size_t) L0 + 1) * 4, pk.list_blk_off.data() + 1, (size_t) Ln * 4, 0));
+    CU(grow(2, (size_t) fm.n_blocks * 4, pk.blk_first.data(), (size_t) nb_new * 4, 0));
+    CU(grow(3, (size_t) fm.n_blocks * 8, pk.blk_info.data(), (size_t) nb_new * 8, 0));
+    CU(grow(4, (size_t) fm.n_words * 4, pk.packed.data(), (size_t) nw_new * 4, 4));              // + the padding word
+    CU(grow(5, ((size_t) fm.n_post + 1) * 8, po.data() + 1, (size_t) np * 8, 0));
+    CU(grow(6, (size_t) fm.n_pos * 4, pos.data(), (size_t) npos * 4, 0));
+    CU(grow(7, (size_t) L0 * 4, pk.list_dense.data(), (size_t) Ln * 4, 0));
+    CU(grow(8, (size_t) fm.n_dense * dw * 4, pk.dense_bits.data(), (size_t) pk.n_dense * dw * 4, 64));
+    CU(grow(9, (size_t) fm.n_dense * dg * 4, pk.dense_rank.data(), (size_t) pk.n_dense * dg * 4, 4));
+    CU(cudaDeviceSynchronize());              // no search of this index is in flight (idx->mu), other indexes' streams finish first
+    for(int i = 0; i < 10; i++) { cudaFree(fm.d_alloc[i]); fm.d_alloc[i] = fresh[i]; }
+    guard.keep = true;
+    fm.h_list_off.insert(fm.h_list_off.end(), lo.begin() + 1, lo.end());
+    fm.h_list_blk_off.insert(fm.h_list_blk_off.end(), pk.list_blk_off.begin() + 1, pk.list_blk_off.end());
+    fm.h_list_dense.resize(L0);               // (the loader keeps one spare entry for an empty field)
+    fm.h_list_dense.insert(fm.h_list_dense.end(), pk.list_dense.begin(), pk.list_dense.begin() + Ln);
+    fm.n_post += np; fm.n_pos += npos; fm.n_words += nw_new; fm.n_blocks += nb_new; fm.n_dense += pk.n_dense;
+    fm.dev.n_lists = L0 + Ln;
+    fm.dev.is_array = flags;
+    fm.dev.list_off = (const uint64_t*) fm.d_alloc[0];
+    fm.dev.list_blk_off = (const uint32_t*) fm.d_alloc[1];
+    fm.dev.blk_first = (const uint32_t*) fm.d_alloc[2];
+    fm.dev.blk_info = (const uint64_t*) fm.d_alloc[3];
+    fm.dev.packed = (const uint32_t*) fm.d_alloc[4];
+    fm.dev.pos_off = (const uint64_t*) fm.d_alloc[5];
+    fm.dev.positions = (const uint32_t*) fm.d_alloc[6];
+    fm.dev.list_dense = (const uint32_t*) fm.d_alloc[7];
+    fm.dev.dense_bits = (const uint32_t*) fm.d_alloc[8];
+    fm.dev.dense_rank = (const uint32_t*) fm.d_alloc[9];
+    idx->ixdev.fields[field] = fm.dev;
+    return TSGPU_OK;
+}
+
+// sort_index[field] values of upserted / removed documents (src/index.cpp:1160-1180 on the write path): vals[i] -> column[ids[i]];
+// INT64_MIN removes the value.
+tsgpu_status tsgpu_index_set_sort_values(tsgpu_index* idx, uint32_t sort_col, const uint32_t* ids, const int64_t* vals, size_t n) {
+    tsgpu_status s = check_device(idx); if(s) return s;
+    if(n && (!ids || !vals)) return fail(TSGPU_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if(sort_col >= idx->sort_cols.size()) return fail(TSGPU_ERR_INVALID, "no such sort column");
+    std::vector<uint32_t> h_ids(n ? n : 1);
+    std::vector<int64_t> h_vals(n ? n : 1);
+    if(n) { CU(cudaMemcpy(h_ids.data(), ids, n * 4, cudaMemcpyDefault)); CU(cudaMemcpy(h_vals.data(), vals, n * 8, cudaMemcpyDefault)); }
+    for(size_t i = 0; i < n; i++) if(h_ids[i] >= idx->n_docs) return fail(TSGPU_ERR_INVALID, "seq_id >= n_docs");
+    CU(cudaDeviceSynchronize());
+    // runs of consecutive ids travel as one copy (a batch of new documents is one run)
+    for(size_t i = 0; i < n;) {
+        size_t j = i + 1;
+        while(j < n && h_ids[j] == h_ids[j - 1] + 1) j++;
+        CU(cudaMemcpy(idx->sort_cols[sort_col] + h_ids[i], h_vals.data() + i, (j - i) * 8, cudaMemcpyHostToDevice));
+        i = j;
+    }
     return TSGPU_OK;
 }
 

@@ -101,10 +101,24 @@ public:
 class field_mirror_t {
     friend class Index;
     std::map<std::string, std::map<uint32_t, std::vector<uint32_t>>> postings;
+    std::set<std::string> dirty;          // tokens whose list changed since the last take_delta()
     bool is_array;
 public:
     explicit field_mirror_t(bool is_array = false): is_array(is_array) {}
-    void upsert(const std::string& token, uint32_t seq_id, const std::vector<uint32_t>& offsets) { postings[token][seq_id] = offsets; }
+    void upsert(const std::string& token, uint32_t seq_id, const std::vector<uint32_t>& offsets) { postings[token][seq_id] = offsets; dirty.insert(token); }
+    // Index::remove_field (src/index.cpp:7295-7420): posting_t::erase(seq_id) on every token of the document (a test convenience:
+    // the reference re-tokenises the stored document to know its tokens; here every list is looked at)
+    void remove(uint32_t seq_id) {
+        for(auto& p: postings) if(p.second.erase(seq_id)) dirty.insert(p.first);
+    }
+    // what a batch of writes hands to Index::update_field: the full current list of every token it touched (empty = erased token)
+    field_mirror_t take_delta() {
+        field_mirror_t d(is_array);
+        for(auto& t: dirty) { auto it = postings.find(t); d.postings[t] = it == postings.end() ? std::map<uint32_t, std::vector<uint32_t>>() : it->second; }
+        for(auto it = postings.begin(); it != postings.end();) { if(it->second.empty()) it = postings.erase(it); else ++it; }
+        dirty.clear();
+        return d;
+    }
     // Index::tokenize_string (src/index.cpp:1323-1349): positions 1-based, trailing 0 on the doc's last token
     void index_plain_string(uint32_t seq_id, const std::vector<std::string>& tokens) {
         std::map<std::string, std::vector<uint32_t>> t2o;
@@ -288,6 +302,7 @@ class Index {
     // ids (for max_score over the default sorting field)
     struct vocab_t { std::vector<std::string> tokens; std::vector<uint64_t> list_off; std::vector<uint32_t> ids; };
     std::vector<vocab_t> vocabs;
+    std::vector<char> field_is_array;                       // per field, as loaded (tsgpu_index_append_lists must agree)
     // per field: the ART mirror of its vocabulary for (MAX_SCORE, FREQUENCY) leaf scores; rebuilt lazily after a change of
     // fields or sort columns (a server-side binding loads it from an export of the live art_tree instead, see art_mirror.hpp)
     mutable std::vector<art_mirror_t> arts;
@@ -337,6 +352,8 @@ public:
         uint32_t fid = 0;
         if(tsgpu_index_load_field(h, &tf, &fid) != TSGPU_OK) return Option<uint32_t>(500, tsgpu_last_error());
         field_ids[name] = fid;
+        if(field_is_array.size() <= fid) field_is_array.resize(fid + 1, 0);
+        field_is_array[fid] = f.is_array ? 1 : 0;
         if(token_ids.size() <= fid) token_ids.resize(fid + 1);
         if(vocabs.size() <= fid) vocabs.resize(fid + 1);
         vocabs[fid].tokens.resize(tid.size());
@@ -358,6 +375,8 @@ public:
         uint32_t fid = 0;
         if(tsgpu_index_load_field(h, &tf, &fid) != TSGPU_OK) return Option<uint32_t>(500, tsgpu_last_error());
         field_ids[name] = fid;
+        if(field_is_array.size() <= fid) field_is_array.resize(fid + 1, 0);
+        field_is_array[fid] = is_array ? 1 : 0;
         if(token_ids.size() <= fid) token_ids.resize(fid + 1);
         if(vocabs.size() <= fid) vocabs.resize(fid + 1);
         token_ids[fid].clear();
@@ -370,6 +389,74 @@ public:
         arts_ready.assign(arts_ready.size(), 0);
         return Option<uint32_t>(fid);
     }
+    // ---- incremental maintenance of a field's posting lists. Index::index_field_in_memory / remove_field end in
+    // posting_t::upsert / erase per token (src/index.cpp:1290-1400, 7295-7420, src/posting.cpp:247-333); after a batch of writes the
+    // binding hands over, per touched token, its CURRENT full list (walked from the live posting_list_t under the exclusive lock).
+    // The device writes the lists again behind the field's arrays (tsgpu_index_append_lists) and the tokens are pointed at them; a
+    // token whose list became empty leaves the vocabulary (art_delete). The candidate-search mirror (ART) is rebuilt lazily.
+    Option<bool> update_lists(const std::string& name, const std::vector<std::string>& tokens, const std::vector<uint64_t>& list_off,
+                              const std::vector<uint32_t>& ids, const uint64_t* pos_off, const uint32_t* positions) {
+        auto fit = field_ids.find(name);
+        if(fit == field_ids.end()) return Option<bool>(404, "no such field: " + name);
+        if(tokens.size() + 1 != list_off.size()) return Option<bool>(400, "list_off must have one entry per token plus one");
+        if(tokens.empty()) return Option<bool>(true);
+        const uint32_t fid = fit->second;
+        vocab_t& v = vocabs[fid];
+        std::vector<uint32_t> ids_buf = ids;
+        if(ids_buf.empty()) ids_buf.push_back(0);
+        const uint64_t zero_off[1] = {0};
+        const uint32_t zero_pos[1] = {0};
+        tsgpu_field tf{(uint32_t) tokens.size(), 0u, list_off.data(), ids_buf.data(), pos_off ? pos_off : zero_off, positions ? positions : zero_pos};
+        {   // is_array as loaded: the library checks it; ask with the flag the field was created with
+            tf.is_array = field_is_array.size() > fid && field_is_array[fid] ? 1u : 0u;
+        }
+        uint32_t first = 0;
+        if(tsgpu_index_append_lists(h, fid, &tf, &first) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
+        const uint64_t base = v.list_off.empty() ? 0 : v.list_off.back();
+        if(v.list_off.empty()) v.list_off.push_back(0);
+        for(size_t t = 0; t < tokens.size(); t++) {
+            auto old = token_ids[fid].find(tokens[t]);
+            if(old != token_ids[fid].end()) v.tokens[old->second].clear();          // the replaced list: no token names it any more
+            const bool empty = list_off[t + 1] == list_off[t];
+            v.tokens.push_back(empty ? std::string() : tokens[t]);
+            v.list_off.push_back(base + list_off[t + 1]);
+            if(empty) { if(old != token_ids[fid].end()) token_ids[fid].erase(old); }
+            else token_ids[fid][tokens[t]] = first + (uint32_t) t;
+        }
+        v.ids.insert(v.ids.end(), ids.begin(), ids.end());
+        arts_ready.assign(arts_ready.size(), 0);
+        { std::lock_guard<std::mutex> lk(cache_mu); walk_cache.clear(); }
+        return Option<bool>(true);
+    }
+    // the same from the per-token map form of field_mirror_t (tests): `delta.postings[token]` = the token's full list now
+    Option<bool> update_field(const std::string& name, const field_mirror_t& delta) {
+        std::vector<std::string> tokens;
+        std::vector<uint64_t> list_off{0}, pos_off{0};
+        std::vector<uint32_t> ids, positions;
+        for(auto& tok: delta.postings) {
+            tokens.push_back(tok.first);
+            for(auto& p: tok.second) {
+                ids.push_back(p.first);
+                positions.insert(positions.end(), p.second.begin(), p.second.end());
+                pos_off.push_back(positions.size());
+            }
+            list_off.push_back(ids.size());
+        }
+        if(positions.empty()) positions.push_back(0);
+        return update_lists(name, tokens, list_off, ids, pos_off.data(), positions.data());
+    }
+    // sort_index[field] of upserted / removed documents (INT64_MIN: no value)
+    Option<bool> set_sort_values(const std::string& name, const std::vector<uint32_t>& seq_ids, const std::vector<int64_t>& values) {
+        auto it = sort_cols.find(name);
+        if(it == sort_cols.end()) return Option<bool>(404, "no such sort field: " + name);
+        if(seq_ids.size() != values.size()) return Option<bool>(400, "one value per id");
+        if(tsgpu_index_set_sort_values(h, it->second, seq_ids.data(), values.data(), seq_ids.size()) != TSGPU_OK) return Option<bool>(500, tsgpu_last_error());
+        auto sv = sort_values.find(name);
+        if(sv != sort_values.end()) for(size_t i = 0; i < seq_ids.size(); i++) if(seq_ids[i] < sv->second.size()) sv->second[seq_ids[i]] = values[i];
+        arts_ready.assign(arts_ready.size(), 0);                 // leaf max_score comes from the default sorting field
+        return Option<bool>(true);
+    }
+
     // A filter_by result kept on the device (tsgpu_filter_create) with its host-side bit set: searches name it by handle, the
     // device applies it, and the host uses the bits where the reference consults the filter while it picks candidate tokens
     // (validate_and_add_leaf: a token must hold a document of the filter, src/art.cpp:1016-1036).
@@ -1002,7 +1089,7 @@ public:
             if(sv != sort_values.end()) scores = &sv->second;
             std::vector<art_mirror_t::vocab_entry> entries;
             for(uint32_t l = 0; l < v.tokens.size(); l++) {
-                if(v.list_off[l + 1] == v.list_off[l]) continue;
+                if(v.list_off[l + 1] == v.list_off[l] || v.tokens[l].empty()) continue;       // empty, or replaced by a later list (update_lists)
                 int64_t best = INT64_MIN;
                 if(scores) for(uint64_t i = v.list_off[l]; i < v.list_off[l + 1]; i++) best = std::max(best, (*scores)[v.ids[i]]);
                 entries.push_back({v.tokens[l], best, (uint32_t) (v.list_off[l + 1] - v.list_off[l]), l});
