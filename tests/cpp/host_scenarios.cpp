@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <set>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -806,6 +807,101 @@ static void incremental_scenarios() {
     CHECK(found == 0 && kvs.empty());
 }
 
+// group_by: Topster<KV> with distinct > 0 (include/topster.h:357-376) + Index::populate_result_kvs (src/index.cpp:8961-9014).
+// (1) the table of TEST(TopsterTest, DistinctIntValues), test/topster_test.cpp:181-262, through host_group_topster_t: groups ranked by
+// their best KV, each group's KVs best first, the greatest KV per key. (2) Index::search_grouped against the definition: EVERY hit of
+// the search (a Topster larger than the result set) fed to the group Topsters — with a first Topster of 4 so that the truncated-list
+// paths run (larger Topster, rounds without the placed groups, rounds restricted to one group).
+static void group_by_scenarios() {
+    {
+        struct { uint64_t distinct_key; int64_t match_score, primary_attr, secondary_attr; } data[14] = {
+            {1, 11, 20, 30}, {1, 12, 20, 32}, {2, 4, 20, 30}, {3, 7, 20, 30}, {4, 14, 20, 30}, {5, 9, 20, 30}, {5, 10, 20, 32},
+            {5, 9, 20, 30}, {6, 6, 20, 30}, {7, 6, 22, 30}, {7, 6, 22, 30}, {8, 9, 20, 30}, {9, 8, 20, 30}, {10, 5, 20, 30}};
+        tsgpu::host_group_topster_t gt(5, 2);
+        for(int i = 0; i < 14; i++) {
+            tsgpu::KV kv{};
+            kv.key = (uint64_t) i + 100; kv.distinct_key = data[i].distinct_key;
+            kv.scores[0] = data[i].match_score; kv.scores[1] = data[i].primary_attr; kv.scores[2] = data[i].secondary_attr;
+            gt.add(kv);
+        }
+        const auto groups = gt.result();
+        std::vector<uint64_t> order;
+        for(auto& g: groups) order.push_back(g[0].distinct_key);
+        CHECK((order == std::vector<uint64_t>{4, 1, 5, 8, 9}));
+        for(auto& g: groups) {
+            if(g[0].distinct_key == 1) CHECK(g.size() == 2 && g[0].scores[0] == 12 && g[1].scores[0] == 11);
+            if(g[0].distinct_key == 5) CHECK(g.size() == 2 && g[0].scores[0] == 10 && g[0].key == 106 && g[1].scores[0] == 9 && g[1].key == 107);
+            if(g[0].distinct_key == 4) CHECK(g.size() == 1 && g[0].scores[0] == 14);
+        }
+    }
+    const std::vector<tsgpu::sort_by> sort_fields = {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::numeric, "points", true}};
+    const char* words[] = {"running", "shoe", "trail", "road", "light", "boot", "winter", "sandal", "leather", "kids"};
+    const uint32_t n = 120;
+    tsgpu::Index index(n);
+    tsgpu::field_mirror_t m;
+    std::unordered_map<uint32_t, int64_t> points, brand;
+    uint32_t rng = 12345;
+    auto next = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
+    for(uint32_t i = 0; i < n; i++) {
+        std::string title = "shoe";
+        const uint32_t extra = 1 + next() % 3;
+        for(uint32_t k = 0; k < extra; k++) { title += " "; title += words[next() % 10]; }
+        m.index_plain_string(i, tsgpu::tokenize_ascii(title));
+        points[i] = (int64_t) (next() % 50);
+        if(i % 11 != 0) brand[i] = 1000 + (int64_t) (next() % 9) * (int64_t) (1 + next() % 2);      // ~14 brands of uneven size; every 11th document has none
+    }
+    CHECK(index.add_field("title", m).ok());
+    CHECK(index.add_sort_field("points", points).ok());
+    CHECK(index.add_sort_field("brand", brand).ok());
+    for(const char* q: {"shoe", "trail shoe", "shoe runing", "boot", "light road shoe", "sandl"}) {
+        for(int variant = 0; variant < 3; variant++) {
+            const size_t capacity = variant == 0 ? 3 : (variant == 1 ? 6 : 40), L = variant == 1 ? 1 : 2;
+            const bool group_missing = variant == 2;
+            // the definition: every hit -> group Topsters
+            std::vector<tsgpu::KV> all;
+            size_t found = 0;
+            CHECK(index.search(tsgpu::tokenize_ascii(q), {"title"}, sort_fields, 1, 1024, all, found, opt(2, true)).ok());
+            CHECK(all.size() < 1024);
+            tsgpu::host_group_topster_t want(capacity, L);
+            std::set<uint64_t> want_groups;
+            for(auto kv: all) {
+                auto it = brand.find((uint32_t) kv.key);
+                kv.distinct_key = it == brand.end() ? (group_missing ? 1ull : kv.key) : (uint64_t) it->second;
+                want_groups.insert(kv.distinct_key);
+                want.add(kv);
+            }
+            const auto expect = want.result();
+            std::vector<std::vector<tsgpu::KV>> got;
+            size_t found_groups = 0;
+            // first Topster 4, never more than 8 hits per list: every follow-up path runs
+            CHECK(index.search_grouped(tsgpu::tokenize_ascii(q), {"title"}, sort_fields, 1, capacity, "brand", L, group_missing, got, found_groups, opt(2, true), 4, 8).ok());
+            bool same = got.size() == expect.size();
+            for(size_t g = 0; same && g < got.size(); g++) {
+                same = got[g].size() == expect[g].size();
+                for(size_t i = 0; same && i < got[g].size(); i++)
+                    same = got[g][i].key == expect[g][i].key && got[g][i].distinct_key == expect[g][i].distinct_key && got[g][i].scores[0] == expect[g][i].scores[0] &&
+                           got[g][i].scores[1] == expect[g][i].scores[1];
+            }
+            CHECK(same);
+            if(!same) {
+                printf("  group_by scenario: query '%s' variant %d: %zu groups vs %zu expected\n", q, variant, got.size(), expect.size());
+                for(size_t g = 0; g < std::max(got.size(), expect.size()); g++) {
+                    printf("    group %zu: got", g);
+                    if(g < got.size()) for(auto& kv: got[g]) printf(" (%llu|%llu|%lld,%lld)", (unsigned long long) kv.distinct_key, (unsigned long long) kv.key, (long long) kv.scores[0], (long long) kv.scores[1]);
+                    printf("  want");
+                    if(g < expect.size()) for(auto& kv: expect[g]) printf(" (%llu|%llu|%lld,%lld)", (unsigned long long) kv.distinct_key, (unsigned long long) kv.key, (long long) kv.scores[0], (long long) kv.scores[1]);
+                    printf("\n");
+                }
+            }
+            // and with the default first Topster (nothing truncated): the same groups
+            std::vector<std::vector<tsgpu::KV>> got2;
+            CHECK(index.search_grouped(tsgpu::tokenize_ascii(q), {"title"}, sort_fields, 1, capacity, "brand", L, group_missing, got2, found_groups, opt(2, true)).ok());
+            CHECK(got2.size() == expect.size() && found_groups == want_groups.size());
+            for(size_t g = 0; g < got2.size() && g < expect.size(); g++) CHECK(got2[g].size() == expect[g].size() && got2[g][0].key == expect[g][0].key);
+        }
+    }
+}
+
 int main(int argc, char** argv) {
     if(tsgpu_device_count() == 0) { printf("no CUDA device: nothing to run (the library has no CPU path)\n"); return 99; }
     posting_list_intersection_basics();
@@ -820,6 +916,7 @@ int main(int argc, char** argv) {
     synonym_scenarios();
     filter_scenarios();
     incremental_scenarios();
+    group_by_scenarios();
     {
         const auto& ws = tsgpu::Index::art_walk_stats();
         if(getenv("TSGPU_HOST_DEVICE_ART")) {

@@ -97,6 +97,31 @@ public:
     }
 };
 
+// Topster<KV> with distinct > 0 (group_by, include/topster.h:357-376 `group_kv_map`) + Index::populate_result_kvs
+// (src/index.cpp:8961-9014): every KV goes to the Topster of its distinct_key (capacity = group_limit, the greatest KV per key
+// survives), the groups are ranked by their best KV through a Topster of `capacity` group heads, and each group lists its KVs best
+// first. Exact when it is fed every KV; Index::search_grouped feeds it from device rounds that are top-k lists (see there).
+class host_group_topster_t {
+    size_t capacity, group_limit;
+    std::unordered_map<uint64_t, host_topster_t> groups;
+public:
+    host_group_topster_t(size_t capacity, size_t group_limit): capacity(capacity), group_limit(group_limit ? group_limit : 1) {}
+    void add(const KV& kv) {
+        auto it = groups.find(kv.distinct_key);
+        if(it == groups.end()) it = groups.emplace(kv.distinct_key, host_topster_t(group_limit)).first;
+        it->second.add(kv);
+    }
+    size_t n_groups() const { return groups.size(); }
+    std::vector<std::vector<KV>> result() const {
+        std::vector<std::vector<KV>> out;
+        out.reserve(groups.size());
+        for(auto& g: groups) { auto v = g.second.sort(); if(!v.empty()) out.push_back(std::move(v)); }
+        std::sort(out.begin(), out.end(), [](const std::vector<KV>& a, const std::vector<KV>& b) { return kv_is_greater(a[0], b[0]); });
+        if(out.size() > capacity) out.resize(capacity);
+        return out;
+    }
+};
+
 // write side of one string field: what Index::index_field_in_memory feeds to posting_t::upsert per token
 class field_mirror_t {
     friend class Index;
@@ -173,6 +198,10 @@ struct search_options {
     // f-1 (opt-in, not yet measured on a GPU): let the device do the tree walk of every candidate search
     // (tsgpu_art_walk_batch); the few matching subtrees come back and art_mirror_t::finish picks the leaves on the host
     bool device_art_walk = false;
+    // filter_by as a sorted id list (the filter_result_iterator's ids): only these documents can match; and ids that cannot
+    // (on top of the exclusion tokens). Index::search_grouped restricts its follow-up searches with them.
+    const std::vector<uint32_t>* restrict_ids = nullptr;
+    const std::vector<uint32_t>* also_excluded = nullptr;
 };
 
 // Incremental optimal-string-alignment rows as src/art.cpp:1412-1433 computes them while it walks a key: rows[i][col] =
@@ -598,11 +627,13 @@ public:
         else if(lockstep()) lockstep()->submit_and_wait(q);
         else { std::vector<kw_query*> one{&q}; run_kw_batch(one); }
         if(!q.status.ok()) return q.status;
+        if(std::vector<kw_query>* rec = round_recorder()) { rec->push_back(q); rec->back().kvs.clear(); }      // search_grouped replays the rounds
         for(uint32_t i = 0; i < q.count; i++) topster.add(q.kvs[i]);
         num_found = q.found;
         return Option<bool>(true);
     }
     struct kw_query;
+    static std::vector<kw_query>*& round_recorder() { static thread_local std::vector<kw_query>* r = nullptr; return r; }
     kw_query make_kw_query(const std::vector<std::vector<std::string>>& query_suggestions, size_t n_dropped,
                            const std::vector<uint32_t>& total_costs, const std::vector<std::string>& the_fields,
                            const std::vector<uint8_t>& field_weights, const std::vector<sort_by>& sort_fields,
@@ -1383,15 +1414,30 @@ public:
         st.weights = process_search_field_weights(the_fields.size(), opts.query_by_weights);
         auto xop = handle_exclusion(the_fields, opts, st.excluded);
         if(!xop.ok()) return xop;
+        if(opts.also_excluded && !opts.also_excluded->empty()) {
+            std::vector<uint32_t> merged;
+            xop = ids_setop(TSGPU_SET_OR, st.excluded, *opts.also_excluded, merged);
+            if(!xop.ok()) return xop;
+            st.excluded.swap(merged);
+        }
         if(!opts.phrases.empty()) {
             auto pop = phrase_filter_ids(the_fields, opts, st.excluded, st.filter_ids);
             if(!pop.ok()) return pop;
             st.filter_by_provided = true;
+            if(opts.restrict_ids) {
+                std::vector<uint32_t> both;
+                pop = ids_setop(TSGPU_SET_AND, st.filter_ids, *opts.restrict_ids, both);
+                if(!pop.ok()) return pop;
+                st.filter_ids.swap(both);
+            }
             if(tokens.empty()) return phrase_only_search(the_fields, sort_fields, topster_size, opts, st, raw_result_kvs, found);
+        } else if(opts.restrict_ids) {
+            st.filter_ids = *opts.restrict_ids;
+            st.filter_by_provided = true;
         }
         if(tokens.empty()) {
             // only exclusions: the query is `*` minus the excluded ids (src/index.cpp:3738-3745)
-            return search_wildcard(sort_fields, nullptr, st.excluded, topster_size, raw_result_kvs, found);
+            return search_wildcard(sort_fields, opts.restrict_ids ? &st.filter_ids : nullptr, st.excluded, topster_size, raw_result_kvs, found);
         }
         // syn_orig_num_tokens (src/index.cpp:3780-3828): -1 without synonyms, else the longest of the query and its variants
         int syn_orig = -1;
@@ -1426,6 +1472,170 @@ public:
         // all_result_ids_len: the device counts a round's matches exactly; the union over SEVERAL matching rounds is only known
         // through the ids the Topsters kept (a lower bound, exact below the Topster size)
         found = st.rounds_with_results == 1 ? st.found_of_round : st.all_result_ids.size();
+        return Option<bool>(true);
+    }
+
+    // ---- group_by (Collection::search group_by / group_limit; Topster<KV> distinct > 0, include/topster.h:357-376, and
+    // Index::populate_result_kvs, src/index.cpp:8961-9014): the `capacity` best groups by their best hit, each with its `group_limit`
+    // best hits. `group_field` names a sort column that holds the documents' distinct ids (Index::get_distinct_id's hash of the
+    // group_by fields, src/index.cpp:7100-7142, computed by the binding at mirror time); a document without a value is a group of its
+    // own (distinct id = seq_id) unless `group_missing_values` puts all of them in one group.
+    //
+    // The device answers top-k LISTS, the reference's group Topsters see every hit; exactness comes from what a list sorted by KV
+    // order guarantees: (1) the first hit of a group in the list is the group's best hit, and groups appear in head order, so the
+    // first `capacity` distinct groups of the list ARE the result's groups; (2) the first m hits of a group in the list are the
+    // group's m best. A list shorter than the Topster it came from holds every hit. Where the list ends too early the search runs
+    // again — with a 4 x larger Topster up to the device's limit, then without the documents of the groups already seen — and a
+    // group that shows fewer than `group_limit` hits in a truncated list is searched alone (the search restricted to its documents).
+    // `found_groups`: number of groups among the hits seen (exact when no list was truncated; a lower bound otherwise, like `found`).
+    Option<bool> search_grouped(const std::vector<std::string>& tokens, const std::vector<std::string>& the_fields,
+                                const std::vector<sort_by>& sort_fields, size_t drop_tokens_threshold, size_t capacity,
+                                const std::string& group_field, size_t group_limit, bool group_missing_values,
+                                std::vector<std::vector<KV>>& groups, size_t& found_groups, const search_options& opts = search_options(),
+                                size_t first_topster_size = 0, size_t max_topster_size = TSGPU_MAX_TOPK) {
+        max_topster_size = std::max<size_t>(1, std::min<size_t>(max_topster_size, TSGPU_MAX_TOPK));      // (tests lower it to reach the follow-up paths with small data)
+        groups.clear(); found_groups = 0;
+        auto gv = sort_values.find(group_field);
+        if(gv == sort_values.end()) return Option<bool>(404, "no such group_by column: " + group_field);
+        const std::vector<int64_t>& col = gv->second;
+        if(group_limit == 0) group_limit = 1;
+        if(capacity == 0) capacity = 1;
+        auto key_of = [&](uint64_t seq_id) -> uint64_t {
+            const int64_t v = seq_id < col.size() ? col[seq_id] : INT64_MIN;
+            if(v == INT64_MIN) return group_missing_values ? 1ull : seq_id;
+            return (uint64_t) v;
+        };
+        std::unordered_map<uint64_t, std::vector<uint32_t>> members_of;        // documents of a group, built when a follow-up needs them
+        bool members_built = false;
+        auto build_members = [&]() {
+            if(members_built) return;
+            for(uint32_t d = 0; d < col.size(); d++) members_of[key_of(d)].push_back(d);
+            members_built = true;
+        };
+        // ---- the search itself, once: Index::search's control flow (typo costs, drop-tokens) decides which keyword rounds run; they are
+        // recorded, and every follow-up below replays exactly those rounds on the device (a restricted search of its own would see
+        // fewer results and run rounds the reference never ran)
+        size_t T = first_topster_size ? first_topster_size : std::max<size_t>(capacity, 250);
+        T = std::min<size_t>(T, max_topster_size);
+        std::vector<kw_query> rounds;
+        std::vector<KV> kvs;
+        {
+            size_t found = 0;
+            round_recorder() = &rounds;
+            Option<bool> op(true);
+            try { op = search(tokens, the_fields, sort_fields, drop_tokens_threshold, T, kvs, found, opts); }
+            catch(...) { round_recorder() = nullptr; throw; }
+            round_recorder() = nullptr;
+            if(!op.ok()) return op;
+        }
+        // the recorded rounds with another Topster size, optionally restricted to / without some documents; one device call for all
+        struct followup { const std::vector<uint32_t>* restrict_ids; const std::vector<uint32_t>* without; size_t topk; std::vector<KV> out; };
+        auto replay_rounds = [&](std::vector<followup>& fs) -> Option<bool> {
+            std::vector<kw_query> qs;
+            qs.reserve(fs.size() * rounds.size());
+            for(auto& f: fs) for(const kw_query& r: rounds) {
+                kw_query q = r;
+                q.done = false; q.count = 0; q.found = 0; q.kvs.clear();
+                q.topk = (uint32_t) std::min<size_t>(f.topk, TSGPU_MAX_TOPK);
+                if(f.restrict_ids) {
+                    if(q.has_filter) {
+                        std::vector<uint32_t> both;
+                        std::set_intersection(q.filter_ids.begin(), q.filter_ids.end(), f.restrict_ids->begin(), f.restrict_ids->end(), std::back_inserter(both));
+                        q.filter_ids.swap(both);
+                    } else { q.filter_ids = *f.restrict_ids; q.has_filter = true; }
+                }
+                if(f.without && !f.without->empty()) {
+                    std::vector<uint32_t> merged;
+                    std::set_union(q.excl.begin(), q.excl.end(), f.without->begin(), f.without->end(), std::back_inserter(merged));
+                    q.excl.swap(merged);
+                }
+                qs.push_back(std::move(q));
+            }
+            std::vector<kw_query*> ptrs;
+            for(auto& q: qs) ptrs.push_back(&q);
+            if(!ptrs.empty()) run_kw_batch(ptrs);
+            size_t k = 0;
+            for(auto& f: fs) {
+                host_topster_t t(f.topk);
+                for(size_t r = 0; r < rounds.size(); r++, k++) {
+                    if(!qs[k].status.ok()) return qs[k].status;
+                    for(uint32_t i = 0; i < qs[k].count; i++) t.add(qs[k].kvs[i]);
+                }
+                f.out = t.sort();
+            }
+            return Option<bool>(true);
+        };
+        std::vector<uint64_t> order;                                   // groups in head order
+        std::unordered_map<uint64_t, std::vector<KV>> hits;            // a group's hits so far, best first
+        std::unordered_map<uint64_t, char> closed;                     // the group's hits are complete up to group_limit
+        std::vector<uint32_t> seen_docs;                               // documents of the groups already placed
+        std::set<uint64_t> all_groups;                                 // every group a hit was seen of (groups_processed, src/index.cpp:3631)
+        for(int pass = 0; pass < 256; pass++) {
+            const bool truncated = kvs.size() >= T;
+            size_t fresh = 0;
+            for(KV& kv: kvs) {
+                kv.distinct_key = key_of(kv.key);
+                all_groups.insert(kv.distinct_key);
+                auto it = hits.find(kv.distinct_key);
+                if(it == hits.end()) {
+                    if(order.size() >= capacity) continue;             // a group beyond the capacity: its head is below every placed one
+                    order.push_back(kv.distinct_key); fresh++;
+                    it = hits.emplace(kv.distinct_key, std::vector<KV>()).first;
+                }
+                if(it->second.size() < group_limit) it->second.push_back(kv);
+            }
+            // a group's hits are complete when it shows group_limit of them, or when the list it FIRST showed in held every hit
+            // (later lists exclude its documents and say nothing about it)
+            for(size_t gi = 0; gi < order.size(); gi++) {
+                const uint64_t g = order[gi];
+                if(closed.count(g)) continue;
+                if(hits[g].size() >= group_limit || (!truncated && gi >= order.size() - fresh)) closed[g] = 1;
+            }
+            if(!truncated || order.size() >= capacity) break;
+            if(rounds.empty()) return Option<bool>(400, "group_by: the hit list was truncated and the query has no keyword rounds to replay");
+            // the list ended before `capacity` groups showed: a larger Topster first, then the rounds without the placed groups' documents
+            std::vector<followup> fs(1);
+            if(T < max_topster_size && seen_docs.empty()) {
+                T = std::min<size_t>(T * 4, max_topster_size);
+                fs[0] = followup{nullptr, nullptr, T, {}};
+                order.clear(); hits.clear(); closed.clear();           // the larger list repeats the smaller one: start over
+            } else {
+                build_members();
+                std::vector<uint32_t> add;
+                for(uint64_t g: order) { auto& m = members_of[g]; add.insert(add.end(), m.begin(), m.end()); }
+                std::sort(add.begin(), add.end());
+                add.erase(std::unique(add.begin(), add.end()), add.end());
+                if(add.size() == seen_docs.size() && fresh == 0) break;
+                seen_docs.swap(add);
+                fs[0] = followup{nullptr, &seen_docs, T, {}};
+            }
+            auto op = replay_rounds(fs);
+            if(!op.ok()) return op;
+            kvs = std::move(fs[0].out);
+        }
+        // groups whose hit list may be cut short: the rounds again, restricted to the group's documents (all such groups in one call)
+        {
+            std::vector<followup> fs;
+            std::vector<uint64_t> which;
+            for(uint64_t g: order) if(!closed.count(g)) {
+                build_members();
+                fs.push_back(followup{&members_of[g], nullptr, group_limit, {}});
+                which.push_back(g);
+            }
+            if(!fs.empty()) {
+                if(rounds.empty()) return Option<bool>(400, "group_by: the hit list was truncated and the query has no keyword rounds to replay");
+                auto op = replay_rounds(fs);
+                if(!op.ok()) return op;
+                for(size_t i = 0; i < fs.size(); i++) {
+                    for(KV& kv: fs[i].out) kv.distinct_key = which[i];
+                    hits[which[i]] = std::move(fs[i].out);
+                }
+            }
+        }
+        host_group_topster_t gt(capacity, group_limit);
+        for(uint64_t g: order) for(const KV& kv: hits[g]) gt.add(kv);
+        groups = gt.result();
+        found_groups = all_groups.size();
         return Option<bool>(true);
     }
 
