@@ -142,6 +142,11 @@ typedef struct {
 
 const char* tsgpu_last_error(void);
 int tsgpu_device_count(void);
+/* Page-locked host memory for the buffers a caller passes to the search calls again and again (query vectors, KV records): copies to
+ * and from it run at the link's full rate and without the page faults of a fresh allocation. Any host pointer is accepted by every
+ * call; this is an optimisation, not a requirement. */
+tsgpu_status tsgpu_host_alloc(size_t bytes, void** out);
+tsgpu_status tsgpu_host_free(void* p);
 
 /* ---- index mirror ------------------------------------------------------------------------------------------- */
 tsgpu_status tsgpu_index_create(uint32_t n_docs, int device, tsgpu_index** out);

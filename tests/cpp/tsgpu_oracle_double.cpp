@@ -100,6 +100,8 @@ void tsgpu_index_destroy(tsgpu_index* idx) {
     for(auto c: d->cols) delete c;
     delete d;
 }
+tsgpu_status tsgpu_host_alloc(size_t bytes, void** out) { *out = malloc(bytes ? bytes : 16); return *out ? TSGPU_OK : TSGPU_ERR_CUDA; }
+tsgpu_status tsgpu_host_free(void* p) { free(p); return TSGPU_OK; }
 tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint32_t* out_field) {
     Double* d = D(idx);
     FieldCopy* c = new FieldCopy();

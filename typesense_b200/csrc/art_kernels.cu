@@ -38,6 +38,7 @@ struct ArtIndexState {
     cudaStream_t stream = nullptr;
     unsigned char* scratch = nullptr;
     size_t scratch_cap = 0;
+    std::vector<int32_t> out_stage;          // [n * cap] of the frontier form, kept between calls (a fresh vector per call was 24 MB of page faults)
     std::mutex call_mu;
 };
 std::mutex g_mu;                                                       // guards the table itself
@@ -269,7 +270,8 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
         std::vector<ArtQuery> hq(n);
         std::vector<uint8_t> flags(n, 0);
         std::vector<uint32_t> counts(n, 0);
-        std::vector<int32_t> out((size_t) n * cap, 0);
+        std::vector<int32_t>& out = is->out_stage;
+        if(out.size() < (size_t) n * cap) out.resize((size_t) n * cap);          // entries beyond counts[i] are unspecified
         for(uint32_t i = 0; i < n; i++) {
             const uint32_t len = h_off[i + 1] - h_off[i];
             ArtQuery& Q = hq[i];
@@ -369,7 +371,13 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
                     n, ms_levels, n_chunks, n_levels, ms_sort, n_hits_total, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
         CUA(cudaMemcpy(out_counts, counts.data(), (size_t) n * 4, cudaMemcpyDefault));
         CUA(cudaMemcpy(out_flags, flags.data(), n, cudaMemcpyDefault));
-        CUA(cudaMemcpy(out_hits, out.data(), (size_t) n * cap * 4, cudaMemcpyDefault));
+        {   // a host destination gets the found entries only; a device destination the whole block
+            cudaPointerAttributes pa{};
+            const bool dev_dst = cudaPointerGetAttributes(&pa, out_hits) == cudaSuccess && (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
+            (void) cudaGetLastError();
+            if(dev_dst) CUA(cudaMemcpy(out_hits, out.data(), (size_t) n * cap * 4, cudaMemcpyDefault));
+            else for(uint32_t i = 0; i < n; i++) { const uint32_t c = std::min(counts[i], cap); if(c) memcpy(out_hits + (size_t) i * cap, out.data() + (size_t) i * cap, (size_t) c * 4); }
+        }
         return TSGPU_OK;
     }
     std::vector<uint32_t> h_off((size_t) n + 1);

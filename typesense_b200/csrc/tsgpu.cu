@@ -1015,6 +1015,16 @@ tsgpu_status run_vector_stage(tsgpu_index* idx, const tsgpu_kw_batch* b, KwPlan&
 extern "C" {
 
 const char* tsgpu_last_error(void) { return g_err.c_str(); }
+tsgpu_status tsgpu_host_alloc(size_t bytes, void** out) {
+    if(!out) return fail(TSGPU_ERR_INVALID, "null argument");
+    *out = nullptr;
+    CU(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocPortable));
+    return TSGPU_OK;
+}
+tsgpu_status tsgpu_host_free(void* p) {
+    if(p) CU(cudaFreeHost(p));
+    return TSGPU_OK;
+}
 // for the other translation units of the library (art_kernels.cu)
 extern "C" __attribute__((visibility("hidden"))) int tsgpu_index_device_(const tsgpu_index* idx) { return idx->device; }
 extern "C" __attribute__((visibility("hidden"))) tsgpu_status tsgpu_fail_(tsgpu_status s, const char* msg) { return fail(s, msg); }

@@ -39,6 +39,7 @@
 #include <thread>
 #include <mutex>
 #include <condition_variable>
+#include <cstdlib>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -742,6 +743,49 @@ public:
         uint32_t count = 0, found = 0;
         bool done = false;
     };
+    // Staging buffers of the device calls (KV records in and out, query vectors): page-locked, kept for reuse. A fresh pageable
+    // std::vector per call cost page faults and zero-filling for every byte of the widest Topster (57 MB for a 4096-query round).
+    struct staging_pool_t {
+        struct buf { void* p; size_t cap; };
+        std::mutex mu;
+        std::vector<buf> free_list;
+        ~staging_pool_t() { for(auto& b: free_list) tsgpu_host_free(b.p); }
+        buf get(size_t bytes) {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                size_t best = free_list.size();
+                for(size_t i = 0; i < free_list.size(); i++)
+                    if(free_list[i].cap >= bytes && (best == free_list.size() || free_list[i].cap < free_list[best].cap)) best = i;
+                if(best != free_list.size()) { buf b = free_list[best]; free_list.erase(free_list.begin() + best); return b; }
+            }
+            buf b{nullptr, bytes + bytes / 4 + 4096};
+            if(tsgpu_host_alloc(b.cap, &b.p) != TSGPU_OK || !b.p) { b.p = std::malloc(b.cap); b.cap = b.p ? b.cap : 0; std::lock_guard<std::mutex> lk(mu); pageable.insert(b.p); }
+            return b;
+        }
+        void put(buf b) {
+            if(!b.p) return;
+            std::lock_guard<std::mutex> lk(mu);
+            if(pageable.count(b.p)) { pageable.erase(b.p); std::free(b.p); return; }
+            if(free_list.size() >= 32) {                 // bound the pool: drop the smallest
+                size_t smallest = 0;
+                for(size_t i = 1; i < free_list.size(); i++) if(free_list[i].cap < free_list[smallest].cap) smallest = i;
+                if(free_list[smallest].cap < b.cap) std::swap(free_list[smallest], b);
+                tsgpu_host_free(b.p);
+                return;
+            }
+            free_list.push_back(b);
+        }
+        std::set<void*> pageable;                        // (allocation of page-locked memory failed: plain memory, not pooled)
+    };
+    mutable staging_pool_t staging;
+    template <class T> struct staged {                   // RAII lease of n T's
+        staging_pool_t& pool; staging_pool_t::buf b; T* p;
+        staged(staging_pool_t& pool, size_t n): pool(pool), b(pool.get(std::max<size_t>(n, 1) * sizeof(T))), p(static_cast<T*>(b.p)) {}
+        ~staged() { pool.put(b); }
+        staged(const staged&) = delete;
+        T* data() const { return p; }
+        T& operator[](size_t i) const { return p[i]; }
+    };
     // tsgpu_kw_batch for several queries over the same searched fields: their arrays concatenated
     struct kw_batch_storage {
         std::vector<uint32_t> q_combo_off{0}, q_excl_off{0}, excl, q_topk, c_tok_off{0}, t_list, c_cost, filter_ids, fids;
@@ -795,7 +839,8 @@ public:
     void run_kw_batch(const std::vector<kw_query*>& qs, int what = 0, const float* qvecs = nullptr, const tsgpu_vec_params* vp = nullptr) {
         kw_batch_storage st(qs);
         const uint32_t nq = (uint32_t) qs.size(), stride = st.stride;
-        std::vector<KV> kvs((size_t) nq * stride);
+        staged<KV> kvs(staging, (size_t) nq * stride);
+        if(!kvs.data()) { const Option<bool> err(500, "out of host memory"); for(auto* q: qs) { q->status = err; q->done = true; } return; }
         std::vector<uint32_t> count(nq), found(nq);
         kw_device_calls()++;
         const tsgpu_status rc = what == 0 ? tsgpu_keyword_search_batch(h, &st.b, kvs.data(), stride, count.data(), found.data())
@@ -807,7 +852,7 @@ public:
             return;
         }
         for(uint32_t i = 0; i < nq; i++) {
-            qs[i]->kvs.assign(kvs.begin() + (size_t) i * stride, kvs.begin() + (size_t) i * stride + count[i]);
+            qs[i]->kvs.assign(kvs.data() + (size_t) i * stride, kvs.data() + (size_t) i * stride + count[i]);
             qs[i]->count = count[i]; qs[i]->found = found[i]; qs[i]->done = true;
         }
     }
@@ -1177,7 +1222,8 @@ public:
             cost8.push_back((uint8_t) r.cost); pre8.push_back(r.prefix ? 1 : 0);
         }
         terms.push_back(0);
-        std::vector<int32_t> hits((size_t) n * cap);
+        staged<int32_t> hits(staging, (size_t) n * cap);
+        if(!hits.data()) return;
         if(tsgpu_art_walk_batch(h, fid, n, off.data(), terms.data(), cost8.data(), cost8.data(), pre8.data(), hits.data(), cap, cnt.data(), flags.data()) != TSGPU_OK)
             return;
         art_walk_stats().launches++; art_walk_stats().searches += n;
@@ -1187,7 +1233,7 @@ public:
         for(uint32_t i = 0; i < n; i++)
             if(flags[i] == 0)            // flagged searches stay out of the cache: fuzzy_candidates walks them on the host
                 wc[std::make_tuple(fid, reqs[i].prefix, reqs[i].cost, reqs[i].token)] =
-                    std::vector<int32_t>(hits.begin() + (size_t) i * cap, hits.begin() + (size_t) i * cap + cnt[i]);
+                    std::vector<int32_t>(hits.data() + (size_t) i * cap, hits.data() + (size_t) i * cap + cnt[i]);
     }
     // Every walk fuzzy_search_fields could ask for — each token at each cost its length allows, in each searched field — in
     // one launch per field ("lets all cost combinations be speculated in one launch").
@@ -1824,19 +1870,19 @@ public:
                 stride_in = std::max<uint32_t>(stride_in, (uint32_t) out[i].raw_result_kvs.size());
             }
             kw_batch_storage st(qs);
-            std::vector<KV> kw((size_t) m * stride_in);
+            staged<KV> kw(staging, (size_t) m * stride_in);
             std::vector<uint32_t> kw_count(m), kw_found(m), kw_searched(m);
-            std::vector<float> vecs((size_t) m * dim);
+            staged<float> vecs(staging, (size_t) m * dim);
             for(size_t k = 0; k < m; k++) {
                 const size_t i = ids[k];
-                std::copy(out[i].raw_result_kvs.begin(), out[i].raw_result_kvs.end(), kw.begin() + k * stride_in);
+                std::copy(out[i].raw_result_kvs.begin(), out[i].raw_result_kvs.end(), kw.data() + k * stride_in);
                 kw_count[k] = (uint32_t) out[i].raw_result_kvs.size(); kw_found[k] = (uint32_t) out[i].found;
                 kw_searched[k] = (uint32_t) rs[i].executed.c_nreq.size();
-                std::copy(requests[i].query_vector, requests[i].query_vector + dim, vecs.begin() + k * dim);
+                std::copy(requests[i].query_vector, requests[i].query_vector + dim, vecs.data() + k * dim);
             }
             uint32_t stride = 1;
             for(size_t i: ids) stride = std::max<uint32_t>(stride, (uint32_t) std::min<size_t>(requests[i].hits ? requests[i].hits : requests[i].r.topster_size, st.stride));
-            std::vector<KV> okv((size_t) m * stride);
+            staged<KV> okv(staging, (size_t) m * stride);
             std::vector<uint32_t> ocount(m), ofound(m);
             const tsgpu_vec_params vp = requests[ids[0]].vp;
             if(tsgpu_hybrid_fuse_batch(h, &st.b, kw.data(), stride_in, kw_count.data(), kw_found.data(), kw_searched.data(), vecs.data(), &vp,
@@ -1847,7 +1893,7 @@ public:
             }
             bs.fuse_queries += m;
             for(size_t k = 0; k < m; k++) {
-                out[ids[k]].raw_result_kvs.assign(okv.begin() + k * stride, okv.begin() + k * stride + ocount[k]);
+                out[ids[k]].raw_result_kvs.assign(okv.data() + k * stride, okv.data() + k * stride + ocount[k]);
                 out[ids[k]].found = ofound[k];
             }
         }
