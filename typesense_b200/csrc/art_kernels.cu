@@ -230,6 +230,7 @@ extern "C" tsgpu_status tsgpu_index_load_art(tsgpu_index* idx, uint32_t field, c
             for(uint32_t k = 0; k < nch[r]; k++) stack.push_back(cref[first[r] + k]);
         }
     }
+    CUA(cudaDeviceSynchronize());      // the uploads used the default stream; the walk stream is non-blocking and does not order with it
     ArtIndexState* is = state_of(idx, true);
     std::lock_guard<std::mutex> lk(is->call_mu);
     auto& slot = is->fields[field];

@@ -538,18 +538,18 @@ tsgpu_status run_keyword(tsgpu_index* idx, KwPlan& pl, uint32_t kv_stride, KwDev
         const size_t tb = o_sc + n_sc * 8 + 64;
         CU(idx->d_small.reserve(tb));
         unsigned char* sb = idx->d_small.as<unsigned char>();
-        CU(cudaMemcpy(sb, qids.data(), (size_t) nq * 8, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(sb + (size_t) nq * 8, pl.q_nids.data(), (size_t) nq * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(sb, qids.data(), (size_t) nq * 8, cudaMemcpyHostToDevice, st));            // on the kernel's stream: the default stream does not order with it
+        CU(cudaMemcpyAsync(sb + (size_t) nq * 8, pl.q_nids.data(), (size_t) nq * 4, cudaMemcpyHostToDevice, st));
         idx->stats.h2d_bytes += (size_t) nq * 12;
         WcParams P{};
         P.qd = pl.d_qd; P.ud = pl.d_ud;
         P.q_ids = reinterpret_cast<const uint32_t* const*>(sb); P.q_nids = reinterpret_cast<const uint32_t*>(sb + (size_t) nq * 8);
         P.q_scores = nullptr;
         if(pl.id_scores) {                       // per-id match scores ride next to the ids they belong to
-            CU(cudaMemcpy(sb + o_sc, pl.id_scores, n_sc * 8, cudaMemcpyDefault));
+            CU(cudaMemcpyAsync(sb + o_sc, pl.id_scores, n_sc * 8, cudaMemcpyDefault, st));
             std::vector<const int64_t*> qsc(nq, nullptr);
             for(uint32_t q = 0; q < nq; q++) if(pl.q_inline_off[q] != ~0ull) qsc[q] = reinterpret_cast<const int64_t*>(sb + o_sc) + pl.q_inline_off[q];
-            CU(cudaMemcpy(sb + o_sp, qsc.data(), (size_t) nq * 8, cudaMemcpyHostToDevice));
+            CU(cudaMemcpyAsync(sb + o_sp, qsc.data(), (size_t) nq * 8, cudaMemcpyHostToDevice, st));
             P.q_scores = reinterpret_cast<const int64_t* const*>(sb + o_sp);
             idx->stats.h2d_bytes += n_sc * 8 + (size_t) nq * 8;
         }
@@ -1165,6 +1165,7 @@ tsgpu_status tsgpu_index_load_field(tsgpu_index* idx, const tsgpu_field* f, uint
     idx->ixdev.fields[idx->fields.size()] = fm.dev;
     *out_field = (uint32_t) idx->fields.size();
     idx->fields.push_back(std::move(fm));
+    CU(cudaDeviceSynchronize());       // default-stream uploads (device-to-device ones are asynchronous) land before any search stream reads them
     return TSGPU_OK;
 }
 
@@ -1289,6 +1290,7 @@ tsgpu_status tsgpu_index_set_sort_values(tsgpu_index* idx, uint32_t sort_col, co
         CU(cudaMemcpy(idx->sort_cols[sort_col] + h_ids[i], h_vals.data() + i, (j - i) * 8, cudaMemcpyHostToDevice));
         i = j;
     }
+    CU(cudaDeviceSynchronize());
     return TSGPU_OK;
 }
 
@@ -1299,6 +1301,7 @@ tsgpu_status tsgpu_index_load_sort_column(tsgpu_index* idx, const int64_t* vals,
     int64_t* d = nullptr;
     CU(cudaMalloc(&d, (size_t) std::max<uint32_t>(idx->n_docs, 1) * 8));
     CU(cudaMemcpy(d, vals, (size_t) idx->n_docs * 8, cudaMemcpyDefault));
+    CU(cudaDeviceSynchronize());
     *out_col = (uint32_t) idx->sort_cols.size();
     idx->sort_cols.push_back(d);
     return TSGPU_OK;
@@ -1337,6 +1340,7 @@ tsgpu_status tsgpu_index_load_hnsw(tsgpu_index* idx, const tsgpu_hnsw* g) {
     CU(up(g->links0, n * (2 * (size_t) g->M + 1) * 4, &p)); h.links0 = (const uint32_t*) p;
     CU(up(g->upper_off, (n + 1) * 8, &p)); h.upper_off = (const unsigned long long*) p;
     CU(up(g->links_up, n_up * ((size_t) g->M + 1) * 4, &p)); h.links_up = (const uint32_t*) p;
+    CU(cudaDeviceSynchronize());       // the uploads went through the default stream (device-to-device ones return at once); idx->stream does not order with it
     if(n) {
         uint32_t* d_bad = nullptr;
         CU(cudaMalloc(&d_bad, 4));
@@ -1384,15 +1388,19 @@ tsgpu_status tsgpu_filter_create(tsgpu_index* idx, const uint32_t* ids, size_t n
     std::lock_guard<std::mutex> lk(idx->mu);
     Filter f;
     const size_t words = ((size_t) idx->n_docs + 31) / 32;
+    // The clear, the upload and the kernel all go on the index's stream. (They used to be a cudaMemset and a cudaMemcpy on the legacy
+    // default stream followed by the kernel on idx->stream, which is NON-BLOCKING: nothing ordered them — a pageable cudaMemcpy returns
+    // once the data is staged, not once it has landed — and once in a while the clear ran after the kernel and wiped bits it had set:
+    // a filter missing a few documents for the lifetime of the index, seen as 7 of 1024 bench queries differing from the CPU arm.)
     CU(cudaMalloc(&f.d_bitmap, std::max<size_t>(words, 4) * 4));
-    CU(cudaMemset(f.d_bitmap, 0, std::max<size_t>(words, 4) * 4));
+    CU(cudaMemsetAsync(f.d_bitmap, 0, std::max<size_t>(words, 4) * 4, idx->stream));
     CU(cudaMalloc(&f.d_ids, std::max<size_t>(n, 4) * 4));
     if(n) {
-        CU(cudaMemcpy(f.d_ids, ids, n * 4, cudaMemcpyDefault));
+        CU(cudaMemcpyAsync(f.d_ids, ids, n * 4, cudaMemcpyDefault, idx->stream));
         bitmap_from_ids_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, idx->stream>>>(f.d_ids, n, f.d_bitmap, idx->n_docs);
         CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(idx->stream));
     }
+    CU(cudaStreamSynchronize(idx->stream));
     f.n = n; f.live = true;
     idx->filters.push_back(f);
     *out_handle = -((int32_t) idx->filters.size() - 1) - 2;      // encoded for tsgpu_kw_batch::q_filter

@@ -751,6 +751,12 @@ public:
         std::vector<buf> free_list;
         ~staging_pool_t() { for(auto& b: free_list) tsgpu_host_free(b.p); }
         buf get(size_t bytes) {
+            if(getenv("TSHOST_NO_STAGING")) {            // debugging aid: a fresh zero-filled block per lease, never pooled
+                buf z{std::calloc(1, bytes + 64), bytes + 64};
+                std::lock_guard<std::mutex> lk(mu);
+                pageable.insert(z.p);
+                return z;
+            }
             {
                 std::lock_guard<std::mutex> lk(mu);
                 size_t best = free_list.size();
