@@ -1163,6 +1163,10 @@ public:
     // query) only tokens that share a document with it in this field qualify (validate_and_add_leaf, src/art.cpp:1024-1036).
     // The mirror is built from the vocabulary, so tokens of EQUAL rank may come in another order than from a live tree.
     const art_mirror_t& art_of(uint32_t fid) const {
+        // every candidate search of every replay pass comes through here: the ready flag is read without the mutex (set with release
+        // order once the mirror is built), the mutex only serialises the build. With several requests in flight the lock was the
+        // host passes' bottleneck.
+        if(__atomic_load_n(&arts_ready[fid], __ATOMIC_ACQUIRE)) return arts[fid];
         std::lock_guard<std::mutex> lk(cache_mu);
         if(!arts_ready[fid]) {
             const vocab_t& v = vocabs[fid];
@@ -1177,9 +1181,9 @@ public:
                 entries.push_back({v.tokens[l], best, (uint32_t) (v.list_off[l + 1] - v.list_off[l]), l});
             }
             arts[fid].build(entries);
-            arts_ready[fid] = 1;
             arts_on_device[fid] = 0;
             walk_cache.clear();
+            __atomic_store_n(&arts_ready[fid], (char) 1, __ATOMIC_RELEASE);
         }
         return arts[fid];
     }
@@ -1188,12 +1192,23 @@ public:
     // `scope`: the walk results of one multi_search_batched call (they live and die with the call: nothing is carried from one
     // request list to the next); without it, the Index-wide cache that prefetch_walks fills for single searches.
     using walk_map = std::map<walk_key, std::vector<int32_t>>;
-    bool has_walk(const walk_key& k, const walk_map* scope = nullptr) const { std::lock_guard<std::mutex> lk(cache_mu); return (scope ? *scope : walk_cache).count(k) != 0; }
-    bool cached_walk(const walk_key& k, std::vector<int32_t>& hits, const walk_map* scope = nullptr) const {
+    // A call's own walk map (`scope`) is written only between passes, by the thread that runs the device batches: the passes' worker
+    // threads read it without the mutex. The Index-wide cache of single searches stays behind it.
+    bool has_walk(const walk_key& k, const walk_map* scope = nullptr) const {
+        if(scope) return scope->count(k) != 0;
         std::lock_guard<std::mutex> lk(cache_mu);
-        const walk_map& wc = scope ? *scope : walk_cache;
-        auto it = wc.find(k);
-        if(it == wc.end()) return false;
+        return walk_cache.count(k) != 0;
+    }
+    bool cached_walk(const walk_key& k, std::vector<int32_t>& hits, const walk_map* scope = nullptr) const {
+        if(scope) {
+            auto it = scope->find(k);
+            if(it == scope->end()) return false;
+            hits = it->second;
+            return true;
+        }
+        std::lock_guard<std::mutex> lk(cache_mu);
+        auto it = walk_cache.find(k);
+        if(it == walk_cache.end()) return false;
         hits = it->second;
         return true;
     }
@@ -1795,7 +1810,7 @@ public:
             // ---- one pass over the unfinished searches
             std::atomic<size_t> cursor{0};
             auto worker = [&] { for(;;) { const size_t k = cursor.fetch_add(1); if(k >= active.size()) break; run_one(active[k]); } };
-            const size_t nt = std::min(n_threads, active.size());
+            const size_t nt = std::min(n_threads, std::max<size_t>(1, active.size() / 8));      // a thread per >= 8 searches: late passes replay few of them
             if(nt <= 1) worker();
             else { std::vector<std::thread> th; for(size_t t = 0; t < nt; t++) th.emplace_back(worker); for(auto& t: th) t.join(); }
             bs.ms_host_passes += ms_since(tp);
