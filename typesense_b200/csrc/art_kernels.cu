@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -30,7 +31,7 @@ using namespace tsdev;
 struct ArtState {
     std::vector<void*> alloc;
     ArtDev dev{};
-    std::vector<uint32_t> node_rank, leaf_rank;          // pre-order ranks (host side): restore the recursion's hit order
+    std::shared_ptr<std::vector<uint32_t>> node_rank, leaf_rank;          // pre-order ranks (host side): restore the recursion's hit order; shared so that a walk call can sort after it let go of the lock
 };
 // per tsgpu_index: the fields' mirrors, a stream of its own and a grow-only staging buffer; walk calls on one index serialise
 struct ArtIndexState {
@@ -38,7 +39,6 @@ struct ArtIndexState {
     cudaStream_t stream = nullptr;
     unsigned char* scratch = nullptr;
     size_t scratch_cap = 0;
-    std::vector<int32_t> out_stage;          // [n * cap] of the frontier form, kept between calls (a fresh vector per call was 24 MB of page faults)
     std::mutex call_mu;
 };
 std::mutex g_mu;                                                       // guards the table itself
@@ -213,19 +213,19 @@ extern "C" tsgpu_status tsgpu_index_load_art(tsgpu_index* idx, uint32_t field, c
     if(e != cudaSuccess) { release(st); return tsgpu_fail_(TSGPU_ERR_CUDA, cudaGetErrorString(e)); }
     st.dev.root = a->root;
     st.dev.empty = a->n_leaves == 0 ? 1u : 0u;
-    st.node_rank.assign(a->n_nodes, 0);
-    st.leaf_rank.assign(a->n_leaves, 0);
+    st.node_rank = std::make_shared<std::vector<uint32_t>>(a->n_nodes, 0u);
+    st.leaf_rank = std::make_shared<std::vector<uint32_t>>(a->n_leaves, 0u);
     if(a->node_rank && a->leaf_rank) {
-        if(a->n_nodes) cudaMemcpy(st.node_rank.data(), a->node_rank, (size_t) a->n_nodes * 4, cudaMemcpyDefault);
-        if(a->n_leaves) cudaMemcpy(st.leaf_rank.data(), a->leaf_rank, (size_t) a->n_leaves * 4, cudaMemcpyDefault);
+        if(a->n_nodes) cudaMemcpy(st.node_rank->data(), a->node_rank, (size_t) a->n_nodes * 4, cudaMemcpyDefault);
+        if(a->n_leaves) cudaMemcpy(st.leaf_rank->data(), a->leaf_rank, (size_t) a->n_leaves * 4, cudaMemcpyDefault);
     } else if(a->n_leaves) {                  // pre-order with children from the largest byte down
         uint32_t next = 0;
         std::vector<int32_t> stack{a->root};
         while(!stack.empty()) {
             const int32_t r = stack.back();
             stack.pop_back();
-            if(r < 0) { st.leaf_rank[~r] = next++; continue; }
-            st.node_rank[r] = next++;
+            if(r < 0) { (*st.leaf_rank)[~r] = next++; continue; }
+            (*st.node_rank)[r] = next++;
             if(next > a->n_nodes + a->n_leaves) { release(st); return tsgpu_fail_(TSGPU_ERR_INVALID, "tsgpu_art: the links do not form a tree"); }
             for(uint32_t k = 0; k < nch[r]; k++) stack.push_back(cref[first[r] + k]);
         }
@@ -249,7 +249,7 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
     CUA(cudaSetDevice(tsgpu_index_device_(idx)));
     ArtIndexState* is = state_of(idx, false);
     if(!is) return tsgpu_fail_(TSGPU_ERR_INVALID, "no ART mirror loaded for this index");
-    std::lock_guard<std::mutex> lk(is->call_mu);
+    std::unique_lock<std::mutex> lk(is->call_mu);
     auto fit = is->fields.find(field);
     if(fit == is->fields.end()) return tsgpu_fail_(TSGPU_ERR_INVALID, "no ART mirror loaded for this field");
     const ArtDev A = fit->second.dev;
@@ -271,7 +271,7 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
         std::vector<ArtQuery> hq(n);
         std::vector<uint8_t> flags(n, 0);
         std::vector<uint32_t> counts(n, 0);
-        std::vector<int32_t>& out = is->out_stage;
+        static thread_local std::vector<int32_t> out;        // [n * cap], kept per calling thread (a fresh vector per call was 24 MB of page faults)
         if(out.size() < (size_t) n * cap) out.resize((size_t) n * cap);          // entries beyond counts[i] are unspecified
         for(uint32_t i = 0; i < n; i++) {
             const uint32_t len = h_off[i + 1] - h_off[i];
@@ -305,8 +305,13 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
         CUA(cudaMemcpyAsync(d + o_q, hq.data(), (size_t) n * sizeof(ArtQuery), cudaMemcpyHostToDevice, st));
         ArtWorkItem* bufs[2] = {(ArtWorkItem*) (d + o_a), (ArtWorkItem*) (d + o_b)};
         uint32_t* d_cnt = (uint32_t*) (d + o_cnt);
-        std::vector<Hit> h_hits;
-        auto rank_of = [&](int32_t r) { return r < 0 ? AS.leaf_rank[~r] : AS.node_rank[r]; };
+        // the chunks' hits are collected under the lock and put in order after it is released (the sort was a third of the call's time
+        // and kept other requests' walks waiting)
+        std::vector<Hit> all_hits;
+        std::vector<size_t> chunk_end;
+        std::vector<std::vector<uint32_t>> chunk_ids;
+        const std::shared_ptr<std::vector<uint32_t>> node_rank = AS.node_rank, leaf_rank = AS.leaf_rank;
+        auto rank_of = [&](int32_t r) { return r < 0 ? (*leaf_rank)[~r] : (*node_rank)[r]; };
         std::vector<std::vector<uint32_t>> work;               // chunks still to run (a stack)
         {
             std::vector<uint32_t> light, heavy;
@@ -353,18 +358,30 @@ extern "C" tsgpu_status tsgpu_art_walk_batch(tsgpu_index* idx, uint32_t field, u
                 } else flags[ids[0]] = 4;                             // the host walks this search
                 continue;
             }
-            const auto t_so = std::chrono::steady_clock::now();
             n_hits_total += h_cnt[1];
-            h_hits.resize(h_cnt[1]);
-            if(h_cnt[1]) CUA(cudaMemcpyAsync(h_hits.data(), d + o_hits, (size_t) h_cnt[1] * sizeof(Hit), cudaMemcpyDeviceToHost, st));
+            const size_t h0 = all_hits.size();
+            all_hits.resize(h0 + h_cnt[1]);
+            if(h_cnt[1]) CUA(cudaMemcpyAsync(all_hits.data() + h0, d + o_hits, (size_t) h_cnt[1] * sizeof(Hit), cudaMemcpyDeviceToHost, st));
             CUA(cudaStreamSynchronize(st));
-            std::sort(h_hits.begin(), h_hits.end(), [&](const Hit& x, const Hit& y) { return x.search != y.search ? x.search < y.search : rank_of(x.ref) < rank_of(y.ref); });
-            for(const Hit& hh: h_hits) {
-                uint32_t& c = counts[hh.search];
-                if(c < cap) out[(size_t) hh.search * cap + c] = hh.ref;
-                c++;
+            chunk_end.push_back(all_hits.size());
+            chunk_ids.push_back(std::move(ids));
+        }
+        lk.unlock();                 // the device part is over: other requests' walks may start
+        {
+            const auto t_so = std::chrono::steady_clock::now();
+            size_t h0 = 0;
+            for(size_t c = 0; c < chunk_end.size(); c++) {
+                std::sort(all_hits.begin() + h0, all_hits.begin() + chunk_end[c],
+                          [&](const Hit& x, const Hit& y) { return x.search != y.search ? x.search < y.search : rank_of(x.ref) < rank_of(y.ref); });
+                for(size_t i = h0; i < chunk_end[c]; i++) {
+                    const Hit& hh = all_hits[i];
+                    uint32_t& cnt_ = counts[hh.search];
+                    if(cnt_ < cap) out[(size_t) hh.search * cap + cnt_] = hh.ref;
+                    cnt_++;
+                }
+                for(uint32_t i: chunk_ids[c]) if(counts[i] > cap) flags[i] = 4;
+                h0 = chunk_end[c];
             }
-            for(uint32_t i: ids) if(counts[i] > cap) flags[i] = 4;
             ms_sort += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_so).count();
         }
         if(art_timing)
