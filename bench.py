@@ -1,22 +1,23 @@
 #!/usr/bin/env python
 """bench.py — queries/sec of the Typesense query hot path on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # CUDA path through the tsgpu C-ABI
-    python bench.py --impl reference --gpus N --steps K ...  # the CPU implementation of the same path (oracle port)
+    python bench.py --gpus N --steps K --warmup W            # CUDA path through the tsgpu C-ABI / the C++ host layer
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU implementation of the same path (same host layer over the oracle)
 
-Workload (config.workload = "hybrid10m"): BASELINE.json configs[3] on one GPU — 10 M docs, one `title` string field
-(Zipf 1.07 over 1 M words, 4-12 tokens), int64 `points`, int `cat` in [0,10) mirrored as 10 persistent filters, 10 M
-x 768 fp32 unit vectors with an HNSW-shaped graph (M=16); a step is ONE multi_search batch of 4096 hybrid queries
-(3 resolved terms, 30 % of the queries carry 4 typo-candidate combinations, half carry `cat:=c`, vector k=100 ef=100,
-alpha 0.3, sort _text_match desc, points desc, Topster 250, 100 hits returned). Synthetic, seeded; every rank holds a
-full replica and runs its own batch (weak scaling, no data-path collective except the NVLink gather of the top-k).
+Workload (config.workload = "hybrid10m"): BASELINE.json configs[3] — 10 M docs, one `title` string field (Zipf 1.07 over 1 M words,
+4-12 tokens), int64 `points`, int `cat` in [0,10) mirrored as 10 persistent filters, 10 M x 768 fp32 unit vectors with an HNSW graph
+built BY THE LIBRARY on the device (hnswlib's insertion, M=16, ef_construction=200); a step is ONE multi_search request of 4096 hybrid
+queries (3 terms, 30 % of the queries with one misspelt token, half with `cat:=c`, vector k=100 ef=100, alpha 0.3, sort _text_match
+desc, points desc, Topster 250, 100 hits returned). Synthetic, seeded. Every rank holds a full replica; with N > 1 every rank answers
+its slice of the SAME request and the slices' records are gathered by the library's NCCL exchange (strong scaling).
 
-`value`  : queries/s with query vectors + result buffers resident in HBM (wall clock of K steps, synchronised on both
-           sides, max over ranks).
-`e2e`    : the same metric through the same C-ABI call with HOST (pinned) buffers: H2D of the query vectors and batch
-           descriptors and D2H of the KV records happen inside the timed region.
-`roofline`: dominant kernel, algorithmic bytes / CUDA-event time measured inside the library on its own stream.
-`cpu_baseline`: the CPU oracle (a port of the reference algorithm, see oracle/) on all host cores, bounded sample.
+`value`  : queries/s of the device pipeline: the request's RESOLVED combinations, query vectors and result buffers resident in HBM, one
+           tsgpu_hybrid_search_batch per step (wall clock of K steps, synchronised on both sides, max over ranks).
+`e2e`    : the same metric end to end: query STRINGS in host memory -> C++ host layer (tokens, typo / prefix / drop-token control flow,
+           candidate walks on the device ART) -> device rounds -> KV records in host memory; `--e2e-depth` requests in flight.
+`roofline`: dominant kernel, algorithmic bytes / CUDA-event time measured inside the library on its own stream (isolated pass).
+`cpu_baseline`: the same host layer over the CPU oracle (a port of the reference algorithm, see oracle/) on all host cores, bounded sample.
+`other_configs`: BASELINE.json's other configurations + the tensor-core flat scan, measured next to the headline.
 """
 import argparse
 import ctypes as C

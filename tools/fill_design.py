@@ -90,9 +90,9 @@ def main():
     di = j.get("device_ms_isolated") or {}
     where = [f"Device time of a `value` step: {f(dm.get('total'), 2)} ms (keyword stream {f(dm.get('keyword'), 2)} ms, vector stage overlapped on its own stream {f(dm.get('knn_overlapped'), 2)} ms, fusion {f(dm.get('fuse'), 2)} ms, host planning {f(dm.get('host_plan'), 2)} ms); kernels alone: kw_search {f(di.get('kw_search'), 2)} ms, walk {f(di.get('knn'), 2)} ms.",
              "",
-             f"End to end, a 4096-query request is {f(hr.get('passes'), 1)} replay passes; per request the host passes take {f(hr.get('ms_host_passes'), 0)} ms, the keyword calls {f(hr.get('ms_kw_calls'), 0)} ms, the candidate-walk calls {f(hr.get('ms_walk_calls'), 0)} ms and the hybrid tail {f(hr.get('ms_fuse_calls'), 0)} ms of wall time (with several requests in flight these include waiting for the device). The end-to-end path is bound by the NUMBER of dependent rounds the reference's typo / drop-token control flow makes (each round = one host pass + one device call), not by any kernel.",
+             f"End to end, a 4096-query request is {f(hr.get('passes'), 1)} replay passes; per request the host passes take {f(hr.get('ms_host_passes'), 0)} ms, the keyword calls {f(hr.get('ms_kw_calls'), 0)} ms, the candidate-walk calls {f(hr.get('ms_walk_calls'), 0)} ms and the hybrid tail {f(hr.get('ms_fuse_calls'), 0)} ms of wall time (with several requests in flight these include waiting for the device). Alone, a keyword-only request of the same strings takes {f(((j.get('other_configs') or {}).get('keyword10m_typo') or {}).get('ms_per_batch'), 0)} ms: the end-to-end path is bound by the NUMBER of dependent rounds the reference's typo / drop-token control flow makes, and on the device by the 2-typo candidate walks (~3000 per request, ~18 us of frontier kernels each), not by the scoring or graph-walk kernels. What round 2 took out of it: the host passes' lock (ART mirror / walk-map lookups are lock-free now), page-locked reusable staging instead of a fresh 57 MB vector per round, the walks' hit ordering outside the walk lock, one slot allocation per warp in the frontier kernel.",
              "",
-             "Next, in order: (1) overlap expansion i+1's table probe with expansion i's admission in the walk kernel (the chain per expansion is what the 0.4 roofline fraction is made of); (2) speculate the rounds of the typo flow (issue cost-1 and cost-2 candidate walks and their keyword rounds together) to cut the passes per request; (3) group-by Topster; (4) posting-list upserts in place (f-4)."]
+             "Next, in order: (1) overlap expansion i+1's table probe with expansion i's admission in the walk kernel (the chain per expansion is what the 0.4 roofline fraction is made of); (2) speculate the rounds of the typo flow (issue cost-1 and cost-2 candidate walks and their keyword rounds together) to cut the passes per request; (3) a device-side group Topster so that group_by needs no follow-up rounds; (4) compaction of the appended posting lists without a full reload."]
     where_block = "\n".join(where)
 
     subst = {
