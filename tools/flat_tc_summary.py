@@ -15,7 +15,9 @@ for m in re.finditer(r"(ok|FAIL)\s+nq=(\d+) ids=(\d+) dim=(\d+): tc_queries=(\d+
 big = [r for r in rows if r["ids"] >= 100000]
 pipe = None
 if len(sys.argv) > 2:
-    m = re.search(r"sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \| ([\d.]+)", open(sys.argv[2]).read())
+    txt = open(sys.argv[2]).read()
+    i = txt.find("flat_tc_kernel")                      # the summary may hold several kernels: this kernel's section
+    m = re.search(r"sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \| ([\d.]+)", txt[i if i >= 0 else 0:])
     pipe = round(float(m[1]), 1) if m else None
 peaks = {}
 try:
