@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """profiles/r02_summary.md + profiles/traffic.json from the round's committed artefacts:
     tools/make_summary.py [tag]      (tag: the file prefix of the final run, default r02z)
-Reads profiles/<tag>_bench.json, <tag>_bench_reference.json, <tag>_ncu_full.md, <tag>_launches.csv, r02v_bench_*gpu.json."""
+Reads profiles/<tag>_bench.json, <tag>_bench_reference.json, <tag>_ncu_full.md, <tag>_launches.csv, <tag>_bench_*gpu.json (else r02v_bench_*gpu.json)."""
 import collections
 import csv
 import glob
@@ -152,7 +152,8 @@ def main():
         L.append("In the value leg the walk kernel and kw_search split the step as the live CUDA-event times above do "
                  f"({b['device_ms_isolated'].get('knn', 0):.1f} : {b['device_ms_isolated'].get('kw_search', 0):.1f} ms); the ART frontier launches belong to the end-to-end leg.")
     sc = []
-    for f in sorted(glob.glob(os.path.join(P, "r02v_bench_*gpu.json")), key=lambda x: int(re.search(r"_(\d+)gpu", x).group(1))):
+    scale_files = glob.glob(os.path.join(P, f"{tag}_bench_*gpu.json")) or glob.glob(os.path.join(P, "r02v_bench_*gpu.json"))      # this build's, else the round's earlier ones
+    for f in sorted(scale_files, key=lambda x: int(re.search(r"_(\d+)gpu", x).group(1))):
         sc.append(last_json(f))
     if sc:
         L += ["", "## Strong scaling (one 4096-query request, every rank answers its slice, gather inside the library)", "",
