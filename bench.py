@@ -74,7 +74,7 @@ def parse():
     ap.add_argument("--graph", default="hnsw", choices=["hnsw", "bulk"], help="hnsw: built by tsgpu_index_build_hnsw; bulk: r01's harness stand-in")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the secondary BASELINE.json configurations (other_configs)")
     ap.add_argument("--e2e-threads", type=int, default=32, help="host threads of one multi_search call's control-flow passes (capped at the core count)")
-    ap.add_argument("--e2e-depth", type=int, default=8, help="multi_search calls in flight in the end-to-end leg (1 = strictly one after the other)")
+    ap.add_argument("--e2e-depth", type=int, default=6, help="multi_search calls in flight in the end-to-end leg (1 = strictly one after the other; measured best of 4 / 6 / 8 / 12 / 16: profiles/r02n_e2e_depth.md)")
     ap.add_argument("--no-graph-cache", action="store_true", help="always rebuild the HNSW graph (default: reuse /tmp/tsgpu_bench_cache)")
     ap.add_argument("--exp-sorted-vectors", action="store_true",
                     help="experiment only: store vectors in cluster order (seq_id locality) to measure what row locality is worth")
