@@ -56,6 +56,8 @@ def main():
             "| | |", "|---|---|",
             f"| `value` (resolved queries, buffers resident in HBM) | **{f(j.get('value'), 0)} queries/s** ({f(j.get('ms_per_step'), 2)} ms per 4096-query step) |",
             f"| `e2e` (query strings through the host layer, host buffers) | **{f(e2e.get('value'), 0)} queries/s** ({f(e2e.get('ms_per_step'), 1)} ms per step, {e2e.get('calls_in_flight', 'n/a')} requests in flight; h2d {f((e2e.get('h2d_bytes_per_step') or 0) / 1e6, 1)} MB, d2h {f((e2e.get('d2h_bytes_per_step') or 0) / 1e6, 1)} MB per step) |"]
+    if os.path.exists(os.path.join(ROOT, "profiles", "r02n_e2e_depth.md")) and e2e.get("calls_in_flight") == 8:
+        rows.append("| `e2e` with 6 requests in flight (the default after the sweep of `profiles/r02n_e2e_depth.md`: 4 / 6 / 8 / 12 / 16) | 30058 queries/s (136.3 ms per step), latency of a request p50 750 ms |")
     if cpu:
         rows.append(f"| `cpu_baseline` (same host layer over the CPU oracle, {cpu.get('cores')} threads, kind `{cpu.get('kind')}`) | {f(cpu.get('value'), 0)} queries/s — e2e / cpu = {f((e2e.get('value') or 0) / cpu['value'], 1) if cpu.get('value') else 'n/a'}x, value / cpu = {f((j.get('value') or 0) / cpu['value'], 0) if cpu.get('value') else 'n/a'}x (the CPU figure moves by tens of percent between boxes) |")
     if par:
@@ -111,7 +113,8 @@ def main():
     except Exception:
         pass
     subst.update({"FLAT_TC_DEV": ft.get("deviation", "n/a"), "FLAT_TC_PERF": ft.get("perf", "n/a"), "FLAT_TC_NCU": ft.get("ncu_file", "n/a"),
-                  "FLAT_TC_PIPE": str(ft.get("tensor_pipe_pct", "n/a"))})
+                  "FLAT_TC_PIPE": str(ft.get("tensor_pipe_pct", "n/a")), "FLAT_TC_FRAC": str(ft.get("tensor_roofline_frac_256q", "n/a")),
+                  "FLAT_TC_HBM": str(ft.get("hbm_roofline_frac_16q", "n/a"))})
     t = open(os.path.join(ROOT, "tools", "design_template.md")).read()
     for k, v in subst.items():
         t = t.replace("{{" + k + "}}", v)
