@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <map>
 #include <set>
 #include <sstream>
 #include <string>
@@ -902,6 +903,99 @@ static void group_by_scenarios() {
     }
 }
 
+// TEST_F(CollectionGroupingTest, GroupingBasics), test/collection_grouping_test.cpp:64-198, over test/group_documents.jsonl
+// (tests/golden/group_documents.jsonl): group_by an int field and a float field under different sort clauses (wildcard query), the
+// per-group `found`, and "typo_tokens_threshold should respect num_groups" (the typo loop counts groups).
+static double json_float(const std::string& line, const std::string& key) {
+    size_t p = line.find("\"" + key + "\"");
+    p = line.find(':', p);
+    return std::strtod(line.c_str() + p + 1, nullptr);
+}
+static int64_t float_to_int64(float f) {                    // Index::float_to_int64_t, src/index.cpp:266-274
+    int32_t i;
+    std::memcpy(&i, &f, sizeof i);
+    if(i < 0) i ^= INT32_MAX;
+    return i;
+}
+static void grouping_basics(const std::string& jsonl) {
+    std::ifstream in(jsonl);
+    if(!in.good()) { printf("grouping fixture %s not found\n", jsonl.c_str()); CHECK(false); return; }
+    std::vector<std::string> lines;
+    for(std::string l; std::getline(in, l);) if(!l.empty()) lines.push_back(l);
+    const uint32_t n = (uint32_t) lines.size();
+    CHECK(n == 12);
+    tsgpu::Index index(n);
+    tsgpu::field_mirror_t title, brand;
+    std::unordered_map<uint32_t, int64_t> rating, size_col, size_key, rating_key, brand_key;
+    std::map<std::string, int64_t> brand_ids;
+    for(uint32_t i = 0; i < n; i++) {
+        title.index_plain_string(i, tsgpu::tokenize_ascii(json_str(lines[i], "title")));
+        const float r = (float) json_float(lines[i], "rating");
+        rating[i] = float_to_int64(r);
+        size_col[i] = json_int(lines[i], "size");
+        size_key[i] = 100 + json_int(lines[i], "size");                 // any injective stand-in for the facet hash get_distinct_id combines
+        rating_key[i] = 1000000 + float_to_int64(r);
+        if(lines[i].find("\"brand\"") != std::string::npos) {
+            const std::string b = json_str(lines[i], "brand");
+            brand.index_plain_string(i, tsgpu::tokenize_ascii(b));
+            if(!brand_ids.count(b)) brand_ids[b] = 7000 + (int64_t) brand_ids.size();
+            brand_key[i] = brand_ids[b];
+        }
+    }
+    CHECK(index.add_field("title", title).ok());
+    CHECK(index.add_field("brand", brand).ok());
+    CHECK(index.add_sort_field("rating", rating).ok());                  // the collection's default sorting field
+    CHECK(index.add_sort_field("size", size_col).ok());
+    CHECK(index.add_sort_field("size_key", size_key).ok());
+    CHECK(index.add_sort_field("rating_key", rating_key).ok());
+    CHECK(index.add_sort_field("brand_key", brand_key).ok());
+    std::vector<std::vector<tsgpu::KV>> groups;
+    std::vector<size_t> gfound;
+    size_t n_groups = 0;
+    auto ids_of = [](const std::vector<tsgpu::KV>& g) { std::vector<uint32_t> r; for(auto& kv: g) r.push_back((uint32_t) kv.key); return r; };
+    {   // `*` grouped by size, group_limit 2, default sort (rating desc)
+        const std::vector<tsgpu::sort_by> by_rating = {{tsgpu::sort_by::numeric, "rating", true}};
+        CHECK(index.search_grouped({}, {"title"}, by_rating, 1, 250, "size_key", 2, false, groups, n_groups, opt(0, false), 0, 1024, &gfound).ok());
+        CHECK(n_groups == 3 && groups.size() == 3);
+        if(groups.size() == 3) {
+            CHECK((ids_of(groups[0]) == std::vector<uint32_t>{5, 1}) && groups[0][0].distinct_key == 111 && gfound[0] == 2);
+            CHECK((ids_of(groups[1]) == std::vector<uint32_t>{4, 3}) && gfound[1] == 7);
+            CHECK((ids_of(groups[2]) == std::vector<uint32_t>{2, 8}) && gfound[2] == 3);
+        }
+    }
+    {   // `*` grouped by rating, sort by size desc: 7 unique ratings
+        const std::vector<tsgpu::sort_by> by_size = {{tsgpu::sort_by::numeric, "size", true}};
+        CHECK(index.search_grouped({}, {"title"}, by_size, 1, 250, "rating_key", 2, false, groups, n_groups, opt(0, false), 0, 1024, &gfound).ok());
+        CHECK(n_groups == 7 && groups.size() == 7);
+        if(groups.size() == 7) {
+            CHECK((ids_of(groups[0]) == std::vector<uint32_t>{8}) && gfound[0] == 1);
+            CHECK((ids_of(groups[1]) == std::vector<uint32_t>{6, 1}) && gfound[1] == 4);
+            CHECK((ids_of(groups[5]) == std::vector<uint32_t>{9}) && gfound[5] == 1);
+            CHECK((ids_of(groups[6]) == std::vector<uint32_t>{0}) && gfound[6] == 1);
+        }
+        // the same through the truncated-list paths
+        std::vector<std::vector<tsgpu::KV>> g2;
+        CHECK(index.search_grouped({}, {"title"}, by_size, 1, 250, "rating_key", 2, false, g2, n_groups, opt(0, false), 2, 1024).ok());
+        CHECK(g2.size() == groups.size());
+        for(size_t g = 0; g < g2.size() && g < groups.size(); g++) CHECK(ids_of(g2[g]) == ids_of(groups[g]));
+        // ... and with lists of at most 4 hits: placed groups excluded, short groups searched alone
+        CHECK(index.search_grouped({}, {"title"}, by_size, 1, 250, "rating_key", 2, false, g2, n_groups, opt(0, false), 2, 4).ok());
+        CHECK(g2.size() == groups.size());
+        for(size_t g = 0; g < g2.size() && g < groups.size(); g++) CHECK(ids_of(g2[g]) == ids_of(groups[g]));
+    }
+    {   // typo_tokens_threshold counts groups: "beta" in brand, threshold 2 -> Beta and (one typo away) Zeta; threshold 1 -> Beta only
+        const std::vector<tsgpu::sort_by> text_then_rating = {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::numeric, "rating", true}};
+        CHECK(index.search_grouped({"beta"}, {"brand"}, text_then_rating, 1, 250, "brand_key", 1, false, groups, n_groups, opt(2, false, 2), 0, 1024, &gfound).ok());
+        CHECK(n_groups == 2 && groups.size() == 2);
+        if(groups.size() == 2) {
+            CHECK(groups[0][0].distinct_key == (uint64_t) brand_ids["Beta"] && groups[1][0].distinct_key == (uint64_t) brand_ids["Zeta"]);
+            CHECK(gfound[0] == 3 && gfound[1] == 1);
+        }
+        CHECK(index.search_grouped({"beta"}, {"brand"}, text_then_rating, 1, 250, "brand_key", 1, false, groups, n_groups, opt(2, false, 1), 0, 1024, &gfound).ok());
+        CHECK(n_groups == 1 && groups.size() == 1 && gfound.size() == 1 && gfound[0] == 3);
+    }
+}
+
 int main(int argc, char** argv) {
     if(tsgpu_device_count() == 0) { printf("no CUDA device: nothing to run (the library has no CPU path)\n"); return 99; }
     posting_list_intersection_basics();
@@ -917,6 +1011,11 @@ int main(int argc, char** argv) {
     filter_scenarios();
     incremental_scenarios();
     group_by_scenarios();
+    {
+        std::string g = argc > 1 ? argv[1] : "tests/golden/documents.jsonl";
+        const size_t p = g.rfind("documents.jsonl");
+        grouping_basics(p == std::string::npos ? "tests/golden/group_documents.jsonl" : g.substr(0, p) + "group_documents.jsonl");
+    }
     {
         const auto& ws = tsgpu::Index::art_walk_stats();
         if(getenv("TSGPU_HOST_DEVICE_ART")) {

@@ -203,6 +203,11 @@ struct search_options {
     // (on top of the exclusion tokens). Index::search_grouped restricts its follow-up searches with them.
     const std::vector<uint32_t>* restrict_ids = nullptr;
     const std::vector<uint32_t>* also_excluded = nullptr;
+    // group_by: the typo loop counts GROUPS, not documents, against typo_tokens_threshold (`results_count = group_limit != 0 ?
+    // groups_processed.size() : all_result_ids_len`, src/index.cpp:5095); the drop-tokens loop keeps counting documents (:3922).
+    // The column holds the documents' distinct ids (INT64_MIN = no value), see Index::search_grouped.
+    const std::vector<int64_t>* group_column = nullptr;
+    bool group_missing_values = false;
 };
 
 // Incremental optimal-string-alignment rows as src/art.cpp:1412-1433 computes them while it walks a key: rows[i][col] =
@@ -1466,7 +1471,18 @@ public:
                 auto op = search_all_candidates(cands, dropped, the_fields, sort_fields, topster_size, o, st);
                 if(!op.ok()) return op;
             }
-            if(st.all_result_ids.size() >= o.typo_tokens_threshold) return Option<bool>(true);
+            {
+                size_t results_count = st.all_result_ids.size();
+                if(o.group_column) {
+                    std::set<uint64_t> groups;
+                    for(uint32_t id: st.all_result_ids) {
+                        const int64_t v = id < o.group_column->size() ? (*o.group_column)[id] : INT64_MIN;
+                        groups.insert(v == INT64_MIN ? (o.group_missing_values ? 1ull : (uint64_t) id) : (uint64_t) v);
+                    }
+                    results_count = groups.size();
+                }
+                if(results_count >= o.typo_tokens_threshold) return Option<bool>(true);
+            }
             n++;
         }
         return Option<bool>(true);
@@ -1559,7 +1575,8 @@ public:
                                 const std::vector<sort_by>& sort_fields, size_t drop_tokens_threshold, size_t capacity,
                                 const std::string& group_field, size_t group_limit, bool group_missing_values,
                                 std::vector<std::vector<KV>>& groups, size_t& found_groups, const search_options& opts = search_options(),
-                                size_t first_topster_size = 0, size_t max_topster_size = TSGPU_MAX_TOPK) {
+                                size_t first_topster_size = 0, size_t max_topster_size = TSGPU_MAX_TOPK,
+                                std::vector<size_t>* group_found = nullptr) {          // hits per returned group (groups_processed[distinct_key]); exact unless a list was truncated
         max_topster_size = std::max<size_t>(1, std::min<size_t>(max_topster_size, TSGPU_MAX_TOPK));      // (tests lower it to reach the follow-up paths with small data)
         groups.clear(); found_groups = 0;
         auto gv = sort_values.find(group_field);
@@ -1590,14 +1607,40 @@ public:
             size_t found = 0;
             round_recorder() = &rounds;
             Option<bool> op(true);
-            try { op = search(tokens, the_fields, sort_fields, drop_tokens_threshold, T, kvs, found, opts); }
+            search_options go = opts;
+            go.group_column = &col; go.group_missing_values = group_missing_values;
+            try { op = search(tokens, the_fields, sort_fields, drop_tokens_threshold, T, kvs, found, go); }
             catch(...) { round_recorder() = nullptr; throw; }
             round_recorder() = nullptr;
             if(!op.ok()) return op;
         }
         // the recorded rounds with another Topster size, optionally restricted to / without some documents; one device call for all
         struct followup { const std::vector<uint32_t>* restrict_ids; const std::vector<uint32_t>* without; size_t topk; std::vector<KV> out; };
+        // `*` (no tokens, no phrases) has no control flow to record: its follow-ups are the wildcard search itself with another
+        // filter / exclusion list / Topster size
+        const bool wildcard_query = tokens.empty() && opts.phrases.empty();
+        std::vector<uint32_t> wc_excluded;
+        if(wildcard_query) {
+            auto xop = handle_exclusion(the_fields, opts, wc_excluded);
+            if(!xop.ok()) return xop;
+            if(opts.also_excluded) { std::vector<uint32_t> m2; std::set_union(wc_excluded.begin(), wc_excluded.end(), opts.also_excluded->begin(), opts.also_excluded->end(), std::back_inserter(m2)); wc_excluded.swap(m2); }
+        }
         auto replay_rounds = [&](std::vector<followup>& fs) -> Option<bool> {
+            if(wildcard_query) {
+                for(auto& f: fs) {
+                    std::vector<uint32_t> filt, excl = wc_excluded;
+                    const std::vector<uint32_t>* fp = opts.restrict_ids;
+                    if(f.restrict_ids) {
+                        if(fp) { std::set_intersection(fp->begin(), fp->end(), f.restrict_ids->begin(), f.restrict_ids->end(), std::back_inserter(filt)); fp = &filt; }
+                        else fp = f.restrict_ids;
+                    }
+                    if(f.without && !f.without->empty()) { std::vector<uint32_t> m2; std::set_union(excl.begin(), excl.end(), f.without->begin(), f.without->end(), std::back_inserter(m2)); excl.swap(m2); }
+                    size_t fnd = 0;
+                    auto op = search_wildcard(sort_fields, fp, excl, std::min<size_t>(f.topk, TSGPU_MAX_TOPK), f.out, fnd);
+                    if(!op.ok()) return op;
+                }
+                return Option<bool>(true);
+            }
             std::vector<kw_query> qs;
             qs.reserve(fs.size() * rounds.size());
             for(auto& f: fs) for(const kw_query& r: rounds) {
@@ -1637,12 +1680,14 @@ public:
         std::unordered_map<uint64_t, char> closed;                     // the group's hits are complete up to group_limit
         std::vector<uint32_t> seen_docs;                               // documents of the groups already placed
         std::set<uint64_t> all_groups;                                 // every group a hit was seen of (groups_processed, src/index.cpp:3631)
+        std::unordered_map<uint64_t, size_t> hits_of_group;            // ... and how many
         for(int pass = 0; pass < 256; pass++) {
             const bool truncated = kvs.size() >= T;
             size_t fresh = 0;
             for(KV& kv: kvs) {
                 kv.distinct_key = key_of(kv.key);
                 all_groups.insert(kv.distinct_key);
+                hits_of_group[kv.distinct_key]++;
                 auto it = hits.find(kv.distinct_key);
                 if(it == hits.end()) {
                     if(order.size() >= capacity) continue;             // a group beyond the capacity: its head is below every placed one
@@ -1659,13 +1704,13 @@ public:
                 if(hits[g].size() >= group_limit || (!truncated && gi >= order.size() - fresh)) closed[g] = 1;
             }
             if(!truncated || order.size() >= capacity) break;
-            if(rounds.empty()) return Option<bool>(400, "group_by: the hit list was truncated and the query has no keyword rounds to replay");
+            if(rounds.empty() && !wildcard_query) return Option<bool>(400, "group_by: the hit list was truncated and the query has no keyword rounds to replay");
             // the list ended before `capacity` groups showed: a larger Topster first, then the rounds without the placed groups' documents
             std::vector<followup> fs(1);
             if(T < max_topster_size && seen_docs.empty()) {
                 T = std::min<size_t>(T * 4, max_topster_size);
                 fs[0] = followup{nullptr, nullptr, T, {}};
-                order.clear(); hits.clear(); closed.clear();           // the larger list repeats the smaller one: start over
+                order.clear(); hits.clear(); closed.clear(); hits_of_group.clear();           // the larger list repeats the smaller one: start over
             } else {
                 build_members();
                 std::vector<uint32_t> add;
@@ -1690,7 +1735,7 @@ public:
                 which.push_back(g);
             }
             if(!fs.empty()) {
-                if(rounds.empty()) return Option<bool>(400, "group_by: the hit list was truncated and the query has no keyword rounds to replay");
+                if(rounds.empty() && !wildcard_query) return Option<bool>(400, "group_by: the hit list was truncated and the query has no keyword rounds to replay");
                 auto op = replay_rounds(fs);
                 if(!op.ok()) return op;
                 for(size_t i = 0; i < fs.size(); i++) {
@@ -1703,6 +1748,7 @@ public:
         for(uint64_t g: order) for(const KV& kv: hits[g]) gt.add(kv);
         groups = gt.result();
         found_groups = all_groups.size();
+        if(group_found) { group_found->clear(); for(auto& g: groups) group_found->push_back(hits_of_group[g[0].distinct_key]); }
         return Option<bool>(true);
     }
 
