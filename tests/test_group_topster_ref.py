@@ -85,3 +85,23 @@ def test_plain_topster_equals_the_reference(libs, seed):
         na = ref.ref_topster(keys.ctypes.data_as(u64p), scores.ctypes.data_as(i64p), n, capacity, a.ctypes.data_as(u64p))
         nb = host.host_topster(keys.ctypes.data_as(u64p), scores.ctypes.data_as(i64p), n, capacity, b.ctypes.data_as(u64p))
         assert na == nb and a[:na].tolist() == b[:nb].tolist()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_oracle_topster_equals_the_reference(libs, seed):
+    """tso_topster_run — the restatement every GPU top-k is compared with — against the reference's compiled Topster<KV>"""
+    from typesense_b200.structs import KV_DTYPE
+    host, ref = libs
+    rng = np.random.default_rng(200 + seed)
+    for _ in range(40):
+        n = int(rng.integers(1, 600))
+        keys = rng.integers(0, max(2, n // 2), n).astype(np.uint64)
+        scores = np.ascontiguousarray(rng.integers(0, 5, (n, 3)), np.int64)
+        capacity = int(rng.integers(1, 300))
+        rows = np.zeros(n, KV_DTYPE)
+        rows["key"] = keys; rows["distinct_key"] = keys; rows["scores"] = scores
+        out = np.zeros(max(capacity, 1), KV_DTYPE)
+        no = ol.oracle().tso_topster_run(capacity, rows.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p))
+        a = np.zeros(n + 1, np.uint64)
+        na = ref.ref_topster(keys.ctypes.data_as(u64p), scores.ctypes.data_as(i64p), n, capacity, a.ctypes.data_as(u64p))
+        assert no == na and out["key"][:no].tolist() == a[:na].tolist()
