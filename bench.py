@@ -568,7 +568,7 @@ def run_tsgpu(args, rank, world, local_rank):
     E2E_DEPTH = max(1, args.e2e_depth)              # multi_search calls in flight in the end-to-end leg (client threads of a server)
     host_bufs = [(np.zeros((max_nl, stride), S.KV_DTYPE), np.zeros(max_nl, np.uint32), np.zeros(max_nl, np.uint32)) for _ in range(E2E_DEPTH)]
     host_kv, host_cnt, host_fnd = host_bufs[0]
-    host_opt = hostapi.Options(device_art_walk=1, n_threads=max(1, min(os.cpu_count() or 1, args.e2e_threads)), **HOST_OPTIONS)
+    host_opt = hostapi.Options(device_art_walk=1, n_threads=max(2, min((os.cpu_count() or 1) // max(1, world), args.e2e_threads)), **HOST_OPTIONS)      # the ranks of one node share its cores
     comm_ms = []
 
     def step(i, mode):
