@@ -244,7 +244,7 @@ enum { TSGPU_SET_AND = 0, TSGPU_SET_OR = 1, TSGPU_SET_EXCLUDE = 2 };
 tsgpu_status tsgpu_ids_setop(tsgpu_index* idx, int op, const uint32_t* a, size_t na, const uint32_t* b, size_t nb,
                              uint32_t* out_ids, size_t cap, size_t* out_n);
 
-/* ---- typo / prefix candidate tokens (not measured on a GPU yet) -------------------------------------
+/* ---- typo / prefix candidate tokens (measured: profiles/r02a_art_gpu_*.json, the bench's end-to-end leg) ----
  * A field's token index (art_tree, include/art.h:124-127; one per string field, Index::search_index) as flat arrays:
  * inner nodes with the first 8 bytes of their compressed path (MAX_PREFIX_LEN), child links ascending by key byte, leaf
  * keys. typesense_b200/host/art_mirror.hpp builds them from an export of the live tree. */

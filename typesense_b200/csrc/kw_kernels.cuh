@@ -198,7 +198,7 @@ constexpr int kQCap = 2 * kThreads;        // pending-match queue slots per CTA
 #ifndef TSGPU_KW_MIN_CTAS
 #define TSGPU_KW_MIN_CTAS 8
 #endif
-// REGSCORE (opt-in, TSGPU_REG_SCORE=1; not yet measured on a GPU): plain fields of combinations with at most kSmallTokens
+// REGSCORE (the default since round 2, TSGPU_REG_SCORE=0 switches it off; measured: profiles/r02a_bench_*.json): plain fields of combinations with at most kSmallTokens
 // rows are scored by score_field_plain_small(), which keeps the tokens and the Match window in registers instead of the
 // run-time indexed local arrays of score_field_plain(). <false> is the code that was profiled this round.
 // ONEFIELD (only instantiated next to REGSCORE): the batch searches a single field, so F is the constant 1 and the

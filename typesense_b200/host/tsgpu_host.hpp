@@ -196,7 +196,7 @@ struct search_options {
     // directions when the query has at most `drop_both_sides_token_limit` tokens
     enum drop_mode_t { right_to_left, left_to_right, both_sides } drop_tokens_mode = right_to_left;
     size_t drop_both_sides_token_limit = 0;
-    // f-1 (opt-in, not yet measured on a GPU): let the device do the tree walk of every candidate search
+    // f-1 (on in the bench's end-to-end leg; measured: profiles/r02a_art_gpu_*.json, r02_summary.md): let the device do the tree walk of every candidate search
     // (tsgpu_art_walk_batch); the few matching subtrees come back and art_mirror_t::finish picks the leaves on the host
     bool device_art_walk = false;
     // filter_by as a sorted id list (the filter_result_iterator's ids): only these documents can match; and ids that cannot
