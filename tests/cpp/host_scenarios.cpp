@@ -926,7 +926,7 @@ static void grouping_basics(const std::string& jsonl) {
     CHECK(n == 12);
     tsgpu::Index index(n);
     tsgpu::field_mirror_t title, brand;
-    std::unordered_map<uint32_t, int64_t> rating, size_col, size_key, rating_key, brand_key;
+    std::unordered_map<uint32_t, int64_t> rating, size_col, size_key, rating_key, brand_key, size_brand_key;
     std::map<std::string, int64_t> brand_ids;
     for(uint32_t i = 0; i < n; i++) {
         title.index_plain_string(i, tsgpu::tokenize_ascii(json_str(lines[i], "title")));
@@ -935,11 +935,13 @@ static void grouping_basics(const std::string& jsonl) {
         size_col[i] = json_int(lines[i], "size");
         size_key[i] = 100 + json_int(lines[i], "size");                 // any injective stand-in for the facet hash get_distinct_id combines
         rating_key[i] = 1000000 + float_to_int64(r);
+        size_brand_key[i] = 100000 * json_int(lines[i], "size");          // compound key: the optional brand adds nothing when absent
         if(lines[i].find("\"brand\"") != std::string::npos) {
             const std::string b = json_str(lines[i], "brand");
             brand.index_plain_string(i, tsgpu::tokenize_ascii(b));
             if(!brand_ids.count(b)) brand_ids[b] = 7000 + (int64_t) brand_ids.size();
             brand_key[i] = brand_ids[b];
+            size_brand_key[i] += brand_ids[b];
         }
     }
     CHECK(index.add_field("title", title).ok());
@@ -949,6 +951,7 @@ static void grouping_basics(const std::string& jsonl) {
     CHECK(index.add_sort_field("size_key", size_key).ok());
     CHECK(index.add_sort_field("rating_key", rating_key).ok());
     CHECK(index.add_sort_field("brand_key", brand_key).ok());
+    CHECK(index.add_sort_field("size_brand_key", size_brand_key).ok());
     std::vector<std::vector<tsgpu::KV>> groups;
     std::vector<size_t> gfound;
     size_t n_groups = 0;
@@ -982,6 +985,20 @@ static void grouping_basics(const std::string& jsonl) {
         CHECK(index.search_grouped({}, {"title"}, by_size, 1, 250, "rating_key", 2, false, g2, n_groups, opt(0, false), 2, 4).ok());
         CHECK(g2.size() == groups.size());
         for(size_t g = 0; g < g2.size() && g < groups.size(); g++) CHECK(ids_of(g2[g]) == ids_of(groups[g]));
+    }
+    {   // TEST_F(CollectionGroupingTest, GroupingCompoundKey), :200-232: `*` grouped by (size, brand), group_limit 2 — 10 groups; the
+        // documents without a brand group by their size alone
+        const std::vector<tsgpu::sort_by> by_rating = {{tsgpu::sort_by::numeric, "rating", true}};
+        CHECK(index.search_grouped({}, {"title"}, by_rating, 1, 250, "size_brand_key", 2, false, groups, n_groups, opt(0, false), 0, 1024, &gfound).ok());
+        CHECK(n_groups == 10 && groups.size() == 10);
+        if(groups.size() == 10) {
+            CHECK((ids_of(groups[0]) == std::vector<uint32_t>{5}) && gfound[0] == 1);
+            CHECK((ids_of(groups[1]) == std::vector<uint32_t>{4}) && gfound[1] == 1);
+            CHECK((ids_of(groups[2]) == std::vector<uint32_t>{3, 0}) && gfound[2] == 2);
+            CHECK((ids_of(groups[5]) == std::vector<uint32_t>{10, 11}));
+        }
+        // "pagination with page=2, per_page=2": the third and fourth groups
+        if(groups.size() >= 4) CHECK(groups[2][0].key == 3 && groups[2][1].key == 0 && groups[2][0].distinct_key == (uint64_t) (100000 * 10 + brand_ids["Omega"]));
     }
     {   // typo_tokens_threshold counts groups: "beta" in brand, threshold 2 -> Beta and (one typo away) Zeta; threshold 1 -> Beta only
         const std::vector<tsgpu::sort_by> text_then_rating = {{tsgpu::sort_by::text_match, "", true}, {tsgpu::sort_by::numeric, "rating", true}};
