@@ -123,3 +123,102 @@ def test_append_lists_rejects_malformed_input():
     # the field is unchanged
     assert gi.intersect(f, [0], n_docs).tolist() == fd.flat.ids[int(fd.flat.list_off[0]):int(fd.flat.list_off[1])].tolist()
     gi.close()
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built (reference tree absent)")
+@pytest.mark.skipif(__import__("os").environ.get("TSGPU_TEST_DOUBLE") != "1",
+                    reason="a check of the DATA PATH reference posting_list_t -> mirror: runs in the dry run against the oracle double "
+                           "(tests/test_gpu_tests_dryrun.py); the device side of the same calls is test_patched_mirror_equals_fresh_mirror")
+def test_mirror_follows_the_reference_posting_lists():
+    """The write side as the reference keeps it: one posting_list_t per token — the reference's OWN src/posting_list.cpp, compiled in
+    oracle/_ref — receives posting_t::upsert / erase for every written document; after each batch of writes the touched tokens' lists
+    are read back through the reference's iterator (what the binding of INTEGRATION.md §1 does) and handed to tsgpu_index_append_lists.
+    The patched mirror must answer exactly like the oracle over the reference's lists as they stand."""
+    import ctypes as C
+    R = ol.ref()
+    rng = np.random.default_rng(11)
+    vocab, n_docs = 80, 3000
+    zipf = np.arange(1, vocab + 1, dtype=np.float64) ** -1.0
+    zipf /= zipf.sum()
+    plists = [C.c_void_p(R.ref_plist_new(256)) for _ in range(vocab)]
+    doc_tokens = {}
+
+    def offsets_of(tokens):
+        """Index::tokenize_string (src/index.cpp:1323-1349): 1-based positions per token, a trailing 0 on the document's last token"""
+        per = {}
+        for pos, t in enumerate(tokens):
+            per.setdefault(int(t), []).append(pos + 1)
+        per[int(tokens[-1])].append(0)
+        return per
+
+    def write(doc, tokens, touched):
+        if doc in doc_tokens:                                   # an update: Index::remove_field first
+            for t in offsets_of(doc_tokens[doc]):
+                R.ref_plist_erase(plists[t], doc); touched.add(t)
+        if tokens is None:
+            doc_tokens.pop(doc, None)
+            return
+        for t, offs in offsets_of(tokens).items():
+            a = np.asarray(offs, np.uint32)
+            R.ref_plist_upsert(plists[t], doc, ol.p32(a), len(a)); touched.add(t)
+        doc_tokens[doc] = tokens
+
+    def dump(t):
+        n = R.ref_plist_num_ids(plists[t])
+        ids = np.zeros(n + 1, np.uint32); oi = np.zeros(n + 2, np.uint32); offs = np.zeros(8 * n + 16, np.uint32)
+        k = R.ref_plist_dump(plists[t], ol.p32(ids), ol.p32(oi), ol.p32(offs), len(ids), len(offs))
+        assert k == n
+        return [(int(ids[i]), offs[int(oi[i]):int(oi[i + 1])].tolist()) for i in range(n)]
+
+    def random_doc():
+        return rng.choice(vocab, int(rng.integers(2, 7)), p=zipf).tolist()
+
+    touched = set()
+    for d in range(2000):
+        write(d, random_doc(), touched)
+    flat0 = S.FlatField.from_postings([dump(t) for t in range(vocab)])
+    pts = synth.make_points(n_docs, 9)
+    gi = capi.GpuIndex(n_docs, 0)
+    f = gi.load_field(flat0)
+    gi.load_sort_column(pts)
+    remap = np.arange(vocab, dtype=np.int64)
+    sort = ((S.SORT_TEXT_MATCH, -1, 1, 0), (S.SORT_NUMERIC, 0, 1, 0), (S.SORT_NONE, -1, 1, 0))
+
+    def check(seed):
+        final = S.FlatField.from_postings([dump(t) for t in range(vocab)])
+        oi_ = ol.OracleIndex(n_docs, [final], [pts])
+        live = [t for t in range(vocab) if final.df(t) > 0]
+        r = np.random.default_rng(seed)
+        qf, qp = [], []
+        for _ in range(60):
+            nt = int(r.integers(1, 4))
+            toks = [int(t) for t in r.choice(live, nt, replace=False)]
+            qf.append(S.Query([S.Combo([[t] for t in toks], nt)], topk=50, sort=sort, num_query_tokens=nt))
+            qp.append(S.Query([S.Combo([[int(remap[t])] for t in toks], nt)], topk=50, sort=sort, num_query_tokens=nt))
+        okv, ocnt, ofound = oi_.keyword_search(S.KwBatch(qf, [0]), 64)
+        kv, cnt, found = gi.keyword_search(S.KwBatch(qp, [0]), 64)
+        assert cnt.tolist() == ocnt.tolist() and found.tolist() == ofound.tolist() and int(ocnt.sum()) > 100
+        for q in range(len(qf)):
+            n = int(cnt[q])
+            assert kv["key"][q, :n].tolist() == okv["key"][q, :n].tolist() and kv["scores"][q, :n].tolist() == okv["scores"][q, :n].tolist()
+
+    check(1)
+    for batch in range(3):
+        touched = set()
+        if batch == 0:
+            for d in range(2000, 2600):                         # new documents
+                write(d, random_doc(), touched)
+        elif batch == 1:
+            for d in rng.choice(2600, 150, replace=False):      # rewritten documents
+                write(int(d), random_doc(), touched)
+        else:
+            for d in rng.choice(2600, 200, replace=False):      # removed documents
+                write(int(d), None, touched)
+        part = sorted(touched)
+        first = gi.append_lists(f, S.FlatField.from_postings([dump(t) for t in part]))
+        for k, t in enumerate(part):
+            remap[t] = first + k
+        check(10 + batch)
+    for h in plists:
+        R.ref_plist_free(h)
+    gi.close()
